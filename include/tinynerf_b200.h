@@ -1,0 +1,178 @@
+/*
+ * tinynerf_b200 -- C ABI of the B200-native (sm_100a) packed-ray render/train hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  All pointers are DEVICE
+ * pointers on the calling thread's current CUDA device unless marked [host].  Every entry point
+ * returns 0 on success or a negative TNF_E_* code; tnf_last_error() gives a thread-local message.
+ * Entry points are re-entrant, keep no global state, and launch on the caller's stream
+ * (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream).
+ *
+ * Each function cites the reference interface (loicmagne/tinynerf, paths relative to the reference
+ * root) it replaces.  Conventions shared by all of them:
+ *   - floats are fp32, indices int32, "packing info" is int32 [n_rays][2] = (start, count)
+ *   - packed samples are row-major [n][7] = (x,y,z contracted to [-1,1], dx,dy,dz, step)
+ */
+#ifndef TINYNERF_B200_H_
+#define TINYNERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNF_OK            0
+#define TNF_E_INVALID    -1   /* bad argument (null pointer, negative size, bad enum) */
+#define TNF_E_CUDA       -2   /* a CUDA runtime call / kernel launch failed */
+#define TNF_E_UNSUPPORTED -3  /* device is not sm_100 or feature not built */
+
+/* ---- library ------------------------------------------------------------------------------- */
+
+/* ABI version (major*1000+minor). */
+int tnf_version(void);
+/* Thread-local message for the last non-zero return code on this thread ([host] string). */
+const char* tnf_last_error(void);
+/* Fills [host] ints: SM count, major, minor of the current device. */
+int tnf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- a1/a2: NeRF-equation weights over packed rays -------------------------------------------
+ * Replaces src/cuda.cu:66-95 (compute_weights_fwd, kernel :3-30) and src/cuda.cu:97-132
+ * (compute_weights_bwd, kernel :32-58).
+ *
+ *   weights[k] = T_k * (1 - a_k),  a_k = __expf(-sigmas[k]*steps[k]),  T_k = prod_{j<k in ray} a_j
+ *   a ray stops at the first k with T_k <= threshold; every later sample of that ray gets 0.
+ *   grad_sigmas[k] = steps[k] * (T_{k+1} * g_k - sum_{j>k in ray} weights[j]*g_j)   (no termination)
+ *
+ * `steps` may be strided (steps_stride in elements; 7 for the step column of packed samples, which
+ * removes the reference's .contiguous() copy at src/core.py:196).  Outputs are caller-allocated and
+ * EVERY element is written (no memset pass needed).
+ *
+ * flags:
+ *   TNF_W_TRUSTED_PARTITION  caller guarantees info is a sorted, gap-free partition of [0,n_samples)
+ *                            (what RayProvider emits); skips validation and the fallback launch.
+ *   TNF_W_NO_EXACT_TERMINATION  skip the serial re-evaluation of rays whose transmittance comes
+ *                            within rounding distance of `threshold` (with it ON the
+ *                            (weights>0) mask is bit-identical to the reference's serial kernel).
+ * `status` is a 4-byte device word used as scratch (may be NULL iff TNF_W_TRUSTED_PARTITION);
+ *   after the call bit0 is set when info was NOT a partition and the generic ray-serial kernel
+ *   produced the result instead.
+ */
+#define TNF_W_TRUSTED_PARTITION     1
+#define TNF_W_NO_EXACT_TERMINATION  2
+
+int tnf_weights_fwd(const float* sigmas, const float* steps, int64_t steps_stride,
+                    const int32_t* info, float threshold, float* weights,
+                    int64_t n_samples, int64_t n_rays, int flags, uint32_t* status, void* stream);
+
+int tnf_weights_bwd(const float* sigmas, const float* steps, int64_t steps_stride,
+                    const int32_t* info, const float* weights, const float* grad_weights,
+                    float* grad_sigmas, int64_t n_samples, int64_t n_rays, int flags,
+                    uint32_t* status, void* stream);
+
+/* ---- a4-a8,a10: ray marching + contraction + occupancy lookup + sample packing ----------------
+ * Replaces RayProvider.__call__ (src/core.py:165-188) together with RayMarcherAABB.__call__
+ * (:73-88), RayMarcherUnbounded.__call__ (:48-59), ContractionAABB (:27-31), ContractionMip360
+ * (:16-20, order=inf) and OccupancyGrid.forward (:148-156).
+ *
+ * Two calls per ray batch.  tnf_march_count evaluates the [n_rays, n_steps] sample lattice, writes
+ * the occupancy&bounds mask as a bitfield (n_rays x ceil(n_steps/32) words) and the packing info
+ * (exclusive int32 scan of per-ray counts + info_offset -- the `info[:,0] += current_size` of the
+ * dynamic-batch accumulator, src/run.py:231) and the total in *n_packed (device int64).  The caller
+ * reads n_packed, allocates packed[n_packed][7], and tnf_march_pack fills it in (ray, step) order.
+ */
+#define TNF_SCENE_AABB       0
+#define TNF_SCENE_UNBOUNDED  1
+
+typedef struct tnf_march_params {
+  int32_t scene;            /* TNF_SCENE_* */
+  int32_t n_steps;          /* samples per ray S */
+  float   aabb[6];          /* AABB: min xyz, max xyz (scene==AABB) */
+  float   near, far;        /* AABB: clamp of t_min (src/core.py:81) */
+  float   step_size;        /* AABB: ||aabb1-aabb0||/S as computed by the host (src/core.py:68-70) */
+  const float* t_table;     /* UNBOUNDED: device [S] t values   (src/core.py:52-57, ray independent) */
+  const float* step_table;  /* UNBOUNDED: device [S] step sizes */
+  const float* grid;        /* occupancy grid, device fp32 [gd][gh][gw] */
+  int32_t gd, gh, gw;
+  float   threshold;        /* min(base_threshold, mean) as fp32 (src/core.py:127,156) */
+  const float* noise;       /* optional device [n_rays][S] U[0,1) jitter (training); NULL = see seed */
+  int32_t jitter;           /* 0: no jitter (training=False); 1: jitter from `noise` or Philox(seed) */
+  uint64_t seed, offset;    /* Philox4x32-10 key/counter base when jitter && !noise */
+} tnf_march_params;
+
+int tnf_march_count(const tnf_march_params* p /*[host]*/, const float* rays_o, const float* rays_d,
+                    int64_t n_rays, int32_t info_offset, uint32_t* mask_bits, int32_t* info,
+                    int64_t* n_packed, void* stream);
+
+int tnf_march_pack(const tnf_march_params* p /*[host]*/, const float* rays_o, const float* rays_d,
+                   int64_t n_rays, int32_t info_offset, const uint32_t* mask_bits,
+                   const int32_t* info, float* packed, float* steps_out /*optional [n]*/,
+                   int32_t* ray_idx_out /*optional [n]*/, int64_t n_packed, void* stream);
+
+/* OccupancyGrid.forward alone (src/core.py:148-156): out[i] = trilinear(grid, coords[i]) > thr.
+ * coords are [-1,1] with coords[:,0] -> W (last grid dim).  Optionally returns the interpolated
+ * value (values may be NULL). */
+int tnf_occ_query(const float* grid, int32_t gd, int32_t gh, int32_t gw, const float* coords,
+                  int64_t n, float threshold, uint8_t* out_mask, float* values, void* stream);
+
+/* ---- a9: occupancy grid update / decay --------------------------------------------------------
+ * Replaces the body of OccupancyGrid.update (src/core.py:134-145), split around the sigma_fn call:
+ *   tnf_occ_update_coords: coords[c] = -1 + 2*(cell_xyz[c] + noise[c]) / size       (:137)
+ *   tnf_occ_update_apply : alpha = 1 - exp(-sigma*step); grid = alpha>thr ? 1 : decay*grid  (:139-144)
+ * operating on cells [cell0, cell0+n_cells) of the flattened [gd][gh][gw] grid.  `size3` is the
+ * reference's self.size = (gd,gh,gw) that divides (x,y,z) (quirk kept, src/core.py:109,137).
+ * noise: device [n_cells][3] U[0,1) or NULL for Philox(seed, offset).
+ */
+int tnf_occ_update_coords(int32_t gd, int32_t gh, int32_t gw, int64_t cell0, int64_t n_cells,
+                          const float* noise, uint64_t seed, uint64_t offset, float* coords,
+                          void* stream);
+int tnf_occ_update_apply(float* grid, int64_t cell0, int64_t n_cells, const float* sigma,
+                         float step_size, float threshold, float decay, void* stream);
+
+/* ---- a12: K-Planes fused feature lookup -------------------------------------------------------
+ * Replaces KPlanesFeatureField.forward (src/models.py:153-163) = 9x KPlanesFeaturePlane.forward
+ * (:105-113, F.grid_sample bilinear/zeros/align_corners=True) + 3 Hadamard products + concat, and
+ * its autograd backward (scatter-add of plane gradients).
+ *
+ * planes[s*3+p] points to plane p of scale s stored CHANNELS-LAST: [res_s][res_s][C] fp32 (the
+ * logical parameter stays [1,C,res,res]; see DESIGN.md "data layout").  Plane p uses coordinate
+ * pair (0,1),(0,2),(1,2): first -> W/x axis, second -> H/y axis.  C must be a multiple of 4, <=32.
+ * x is [n][x_stride] with xyz in the first 3 columns (x_stride=7 reads packed samples in place).
+ * out / grad_out are [n][n_scales*C].  Backward ACCUMULATES into grad_planes (same layout).
+ */
+int tnf_kplanes_fwd(const float* const* planes /*[host] n_scales*3 device ptrs*/,
+                    const int32_t* res /*[host] n_scales*/, int32_t n_scales, int32_t channels,
+                    const float* x, int64_t x_stride, int64_t n, float* out, void* stream);
+int tnf_kplanes_bwd(const float* const* planes, float* const* grad_planes, const int32_t* res,
+                    int32_t n_scales, int32_t channels, const float* x, int64_t x_stride, int64_t n,
+                    const float* grad_out, void* stream);
+
+/* ---- a14: Cobafa fused basis/coefficient lookup ----------------------------------------------
+ * Replaces CobafaFeatureField.forward up to the concat (src/models.py:258-264): coef = trilinear
+ * (coef_grid, x); y_l = trilinear(basis_l, 2*((f_l*x) mod 1)-1) * coef[l]; out = cat_l y_l.
+ * Grids are CHANNELS-LAST [r][r][r][c] fp32.  Backward accumulates into grad_basis/grad_coef.
+ */
+int tnf_cobafa_fwd(const float* const* basis /*[host] L device ptrs*/, const int32_t* basis_res,
+                   const int32_t* basis_ch, const float* freqs /*[host] L*/, int32_t n_levels,
+                   const float* coef, int32_t coef_res, const float* x, int64_t x_stride, int64_t n,
+                   float* out, void* stream);
+int tnf_cobafa_bwd(const float* const* basis, float* const* grad_basis, const int32_t* basis_res,
+                   const int32_t* basis_ch, const float* freqs, int32_t n_levels, const float* coef,
+                   float* grad_coef, int32_t coef_res, const float* x, int64_t x_stride, int64_t n,
+                   const float* grad_out, void* stream);
+
+/* ---- a18: compositing (segment sums over packed rays) -----------------------------------------
+ * Replaces the index_add_ block of NerfRenderer.forward (src/core.py:256-265; the reference's own
+ * "TODO: cuda kernel this"):  rgb_ray = sum_k w_k*rgb_k ; opacity = sum_k w_k ;
+ * out = rgb_ray + bg*(1-opacity) when bg != NULL ([host] 3 floats).
+ * Backward: grad_rgb[k] = w_k*go[ray] ; grad_w[k] = <rgb_k, go[ray]> - <bg, go[ray]>.
+ */
+int tnf_composite_fwd(const float* weights, const float* rgbs, const int32_t* info, int64_t n_samples,
+                      int64_t n_rays, const float* bg, float* out_rgb, float* out_opacity, void* stream);
+int tnf_composite_bwd(const float* weights, const float* rgbs, const int32_t* info, int64_t n_samples,
+                      int64_t n_rays, const float* bg, const float* grad_out, float* grad_weights,
+                      float* grad_rgbs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* TINYNERF_B200_H_ */

@@ -1,0 +1,130 @@
+"""ctypes binding of the C ABI in include/tinynerf_b200.h.
+
+There is NO fallback: if `libtinynerf_b200.so` is missing, or a call returns a non-zero code, a
+RuntimeError is raised.  ctypes releases the GIL around each call, so the entry points may be called
+from PyTorch's autograd thread (the reference's backward runs there, src/core.py:203-207).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libtinynerf_b200.so"
+_lib = None
+
+c_f32p = C.c_void_p  # device pointers are passed as integers
+c_i32p = C.c_void_p
+c_u32p = C.c_void_p
+
+
+class MarchParams(C.Structure):
+    """Mirror of `tnf_march_params` (include/tinynerf_b200.h)."""
+
+    _fields_ = [
+        ("scene", C.c_int32),
+        ("n_steps", C.c_int32),
+        ("aabb", C.c_float * 6),
+        ("near", C.c_float),
+        ("far", C.c_float),
+        ("step_size", C.c_float),
+        ("t_table", C.c_void_p),
+        ("step_table", C.c_void_p),
+        ("grid", C.c_void_p),
+        ("gd", C.c_int32),
+        ("gh", C.c_int32),
+        ("gw", C.c_int32),
+        ("threshold", C.c_float),
+        ("noise", C.c_void_p),
+        ("jitter", C.c_int32),
+        ("seed", C.c_uint64),
+        ("offset", C.c_uint64),
+    ]
+
+
+_SIGNATURES = {
+    "tnf_version": (C.c_int, []),
+    "tnf_last_error": (C.c_char_p, []),
+    "tnf_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "tnf_weights_fwd": (C.c_int, [c_f32p, c_f32p, C.c_int64, c_i32p, C.c_float, c_f32p, C.c_int64, C.c_int64,
+                                  C.c_int, c_u32p, C.c_void_p]),
+    "tnf_weights_bwd": (C.c_int, [c_f32p, c_f32p, C.c_int64, c_i32p, c_f32p, c_f32p, c_f32p, C.c_int64,
+                                  C.c_int64, C.c_int, c_u32p, C.c_void_p]),
+    "tnf_march_count": (C.c_int, [C.POINTER(MarchParams), c_f32p, c_f32p, C.c_int64, C.c_int32, c_u32p, c_i32p,
+                                  C.c_void_p, C.c_void_p]),
+    "tnf_march_pack": (C.c_int, [C.POINTER(MarchParams), c_f32p, c_f32p, C.c_int64, C.c_int32, c_u32p, c_i32p,
+                                 c_f32p, c_f32p, c_i32p, C.c_int64, C.c_void_p]),
+    "tnf_occ_query": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int64, C.c_float,
+                                C.c_void_p, c_f32p, C.c_void_p]),
+    "tnf_occ_update_coords": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_f32p,
+                                        C.c_uint64, C.c_uint64, c_f32p, C.c_void_p]),
+    "tnf_occ_update_apply": (C.c_int, [c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_float, C.c_float, C.c_float,
+                                       C.c_void_p]),
+    "tnf_kplanes_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_int32, c_f32p,
+                                  C.c_int64, C.c_int64, c_f32p, C.c_void_p]),
+    "tnf_kplanes_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
+                                  C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_void_p]),
+    "tnf_cobafa_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_float), C.c_int32, c_f32p, C.c_int32, c_f32p, C.c_int64,
+                                 C.c_int64, c_f32p, C.c_void_p]),
+    "tnf_cobafa_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_int32, c_f32p, c_f32p,
+                                 C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_void_p]),
+    "tnf_composite_fwd": (C.c_int, [c_f32p, c_f32p, c_i32p, C.c_int64, C.c_int64, C.POINTER(C.c_float), c_f32p,
+                                    c_f32p, C.c_void_p]),
+    "tnf_composite_bwd": (C.c_int, [c_f32p, c_f32p, c_i32p, C.c_int64, C.c_int64, C.POINTER(C.c_float), c_f32p,
+                                    c_f32p, c_f32p, C.c_void_p]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -m tinynerf_b200.build` "
+            "(tinynerf_b200 has no CPU or PyTorch fallback)"
+        )
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def declared_symbols():
+    return list(_SIGNATURES)
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().tnf_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    # same message as the reference's CHECK_CUDA (src/cuda.cu:62)
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def require_contiguous(t: torch.Tensor, name: str) -> None:
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")

@@ -1,0 +1,424 @@
+"""Host-side mirror of the reference's rendering core (src/core.py) over the sm_100a kernels.
+
+Same class names, constructor arguments, attributes and return values as the reference, so callers
+(src/run.py, the reference tests) work unchanged:
+
+    ContractionMip360 / ContractionAABB      src/core.py:11-33
+    RayMarcherUnbounded / RayMarcherAABB     src/core.py:36-90
+    OccupancyGrid                            src/core.py:93-156
+    RayProvider                              src/core.py:158-188
+    NerfWeights                              src/core.py:192-207
+    NerfRenderer                             src/core.py:209-267
+
+The per-ray helpers (contractions, marchers) keep their stand-alone PyTorch definitions because they
+are part of the public surface, but RayProvider never calls them on the hot path: it hands their
+parameters to the fused march/contract/occupancy/pack kernels (tnf_march_count / tnf_march_pack).
+There is no CPU path: CUDA tensors are required and the C-ABI library must be built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from functools import cached_property
+from typing import Any, Callable, List, Tuple
+
+import torch
+
+from . import _cuda, _lib
+
+# ------------------------------------------------------------------------------------------------
+# Scene contraction and ray marching strategies (public helpers, same math as the reference)
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class ContractionMip360:
+    order: float | int = float("inf")
+
+    @torch.no_grad()
+    def __call__(self, coords: torch.Tensor) -> Tuple[torch.Tensor, None]:
+        """Mip-NeRF 360 contraction to [-1,1] (src/core.py:16-20)."""
+        norm = torch.norm(coords, p=self.order, dim=-1, keepdim=True)  # type: ignore
+        coords = torch.where(norm <= 1.0, coords, (2.0 - 1.0 / norm) * coords / norm) / 2.0
+        return coords, None
+
+
+@dataclass
+class ContractionAABB:
+    aabb: torch.Tensor  # [2,3]
+
+    @torch.no_grad()
+    def __call__(self, coords: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Affine map of the box to [-1,1] plus inside-box mask (src/core.py:27-31)."""
+        mask = torch.all((coords >= self.aabb[0]) & (coords <= self.aabb[1]), dim=-1)
+        coords = (coords - self.aabb[0]) / (self.aabb[1] - self.aabb[0]) * 2.0 - 1.0
+        return coords, mask
+
+
+Contraction = ContractionMip360 | ContractionAABB
+
+
+@dataclass
+class RayMarcherUnbounded:
+    n_samples: int = 200
+    near: float = 0.0
+    far: float = 1e5
+    uniform_range: float = 1.0
+
+    @cached_property
+    def step_size(self) -> float:
+        return self.uniform_range / self.n_samples
+
+    @torch.no_grad()
+    def tables(self, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Ray-independent t / step tables, computed with the reference's own op sequence
+        (src/core.py:52-55) on `device` so the values are bit-identical to what it would produce."""
+        f = lambda x: torch.where(x < 0.5, 2 * x, 1 / (2 - 2 * x))
+        t_values = torch.linspace(0.0, 1.0 - (1.0 / (self.n_samples + 2)), self.n_samples + 1, device=device)
+        t_values = f(t_values) * self.uniform_range + self.near
+        step_sizes = t_values[1:] - t_values[:-1]
+        return t_values[:-1].contiguous(), step_sizes.contiguous()
+
+    @torch.no_grad()
+    def __call__(self, rays_o: torch.Tensor, rays_d: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        n_rays = rays_o.size(0)
+        t_values, step_sizes = self.tables(rays_o.device)
+        t_values = torch.broadcast_to(t_values, (n_rays, self.n_samples))
+        step_sizes = torch.broadcast_to(step_sizes, (n_rays, self.n_samples))
+        return t_values, step_sizes
+
+
+@dataclass
+class RayMarcherAABB:
+    aabb: torch.Tensor
+    n_samples: int = 200
+    near: float = 0.0
+    far: float = 1e5
+
+    @cached_property
+    def step_size(self) -> float:
+        # a 0-dim tensor on the aabb's device, like the reference (src/core.py:68-70)
+        return torch.norm(self.aabb[1] - self.aabb[0]) / self.n_samples
+
+    @torch.no_grad()
+    def __call__(self, rays_o: torch.Tensor, rays_d: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        device = rays_o.device
+        eps = 1e-9
+        aabb_distances = self.aabb.unsqueeze(1) - rays_o
+        aabb_intersections = aabb_distances / torch.where(rays_d == 0.0, rays_d + eps, rays_d)
+        t_min = torch.amax(torch.amin(aabb_intersections, dim=0), dim=1)
+        t_min = torch.clamp(t_min, min=self.near, max=self.far)
+        steps = torch.arange(self.n_samples, dtype=torch.float, device=device) * self.step_size
+        t_values = t_min[:, None] + steps
+        step_sizes = torch.full_like(t_values, self.step_size)
+        return t_values, step_sizes
+
+
+RayMarcher = RayMarcherUnbounded | RayMarcherAABB
+
+
+def _f32(x) -> float:
+    """Python float -> the fp32 value torch uses when the scalar meets a float32 tensor."""
+    return float(torch.tensor(float(x), dtype=torch.float32).item())
+
+
+# ------------------------------------------------------------------------------------------------
+# Occupancy grid
+# ------------------------------------------------------------------------------------------------
+
+
+class OccupancyGrid(torch.nn.Module):
+    """Float occupancy grid with trilinear lookup and jittered decay update (src/core.py:93-156).
+
+    `jitter_source`: "cpu" draws the update jitter slice by slice from torch's CPU generator exactly
+    like the reference (src/core.py:137), "device" uses the kernels' Philox stream (no host work).
+    `slices_per_call`: how many depth slices go through one sigma_fn call (reference: 1).
+    """
+
+    def __init__(self, size: List[int] | int, step_size: float, threshold: float = 0.01, decay: float = 0.95):
+        super().__init__()
+        size = size if isinstance(size, List) else [size, size, size]
+        self.decay = decay
+        self.step_size = step_size
+        self.base_threshold = threshold
+        self.grid: torch.Tensor
+        self.register_buffer("grid", torch.ones(size, dtype=torch.float))
+        self.size = torch.tensor(size, dtype=torch.float)
+        self.mean = 1.0
+        # kept for interface parity (the reference exposes .coords); the kernels derive cell
+        # coordinates from the flat index instead of reading this tensor
+        self.coords = torch.flip(torch.stack(torch.meshgrid([
+            torch.arange(size[0], dtype=torch.float),
+            torch.arange(size[1], dtype=torch.float),
+            torch.arange(size[2], dtype=torch.float),
+        ], indexing="ij"), -1), [-1])
+        self.jitter_source = "cpu"
+        self.slices_per_call = size[0]
+        self._update_calls = 0
+
+    @torch.no_grad()
+    def occupancy(self) -> float:
+        return (self.grid > self.threshold).sum().item() / self.grid.numel()
+
+    @property
+    def threshold(self) -> float:
+        return min(self.base_threshold, self.mean)
+
+    @property
+    def device(self) -> torch.device:
+        return self.grid.device
+
+    def _step_size_f32(self) -> float:
+        s = self.step_size
+        return float(s.item()) if isinstance(s, torch.Tensor) else _f32(s)
+
+    @torch.no_grad()
+    def update(self, sigma_fn: Callable[[torch.Tensor], torch.Tensor], noise: torch.Tensor | None = None):
+        """grid = where(1-exp(-sigma*step) > thr, 1, decay*grid) at jittered cell positions.
+
+        noise: optional [D,H,W,3] U[0,1) tensor (any device) replacing the internally drawn jitter.
+        """
+        lib = _lib.load()
+        _lib.require_cuda(self.grid, "occupancy grid")
+        D, H, W = self.grid.shape
+        dev = self.device
+        per_slice = H * W
+        thr, decay, step = _f32(self.threshold), _f32(self.decay), self._step_size_f32()
+        spc = max(1, min(int(self.slices_per_call), D))
+        with torch.cuda.device(dev):
+            stream = _lib.stream_ptr()
+            for z0 in range(0, D, spc):
+                z1 = min(D, z0 + spc)
+                n = (z1 - z0) * per_slice
+                if noise is not None:
+                    u = noise[z0:z1].reshape(-1, 3).to(dev, torch.float32).contiguous()
+                elif self.jitter_source == "cpu":
+                    # one CPU draw per depth slice, same generator consumption as the reference
+                    u = torch.stack([torch.rand(H, W, 3) for _ in range(z0, z1)]).view(-1, 3).to(dev)
+                else:
+                    u = None
+                coords = torch.empty(n, 3, device=dev)
+                _lib.check(lib.tnf_occ_update_coords(D, H, W, z0 * per_slice, n, _lib.ptr(u), 0x7E57,
+                                                     self._update_calls * D * per_slice, coords.data_ptr(),
+                                                     stream), "tnf_occ_update_coords")
+                sigma = sigma_fn(coords).reshape(-1).float().contiguous()
+                if sigma.numel() != n:
+                    raise RuntimeError(f"sigma_fn returned {sigma.numel()} values for {n} coordinates")
+                _lib.check(lib.tnf_occ_update_apply(self.grid.data_ptr(), z0 * per_slice, n, sigma.data_ptr(),
+                                                    step, thr, decay, stream), "tnf_occ_update_apply")
+        self._update_calls += 1
+        self.mean = self.grid.mean().item()
+
+    @torch.no_grad()
+    def forward(self, coords: torch.Tensor) -> torch.Tensor:
+        """coords: [..., 3] in [-1,1] -> bool [...]: trilinear(grid) > threshold (src/core.py:148-156)."""
+        lib = _lib.load()
+        _lib.require_cuda(self.grid, "occupancy grid")
+        new_shape = coords.shape[:-1]
+        flat = coords.reshape(-1, 3).to(self.device, torch.float32).contiguous()
+        out = torch.empty(flat.size(0), dtype=torch.bool, device=self.device)
+        D, H, W = self.grid.shape
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tnf_occ_query(self.grid.data_ptr(), D, H, W, flat.data_ptr(), flat.size(0),
+                                         _f32(self.threshold), out.data_ptr(), None, _lib.stream_ptr()),
+                       "tnf_occ_query")
+        return out.view(new_shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# Ray provider: march + contract + occupancy mask + pack, fused
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class RayProvider:
+    occupancy_grid: OccupancyGrid
+    contraction: Contraction
+    ray_marcher: RayMarcher
+
+    def _params(self, device, n_steps: int) -> _lib.MarchParams:
+        p = _lib.MarchParams()
+        grid = self.occupancy_grid.grid
+        _lib.require_cuda(grid, "occupancy grid")
+        if grid.device != device:
+            raise RuntimeError("rays and occupancy grid must live on the same device")
+        p.n_steps = n_steps
+        p.grid = grid.data_ptr()
+        p.gd, p.gh, p.gw = grid.shape
+        p.threshold = _f32(self.occupancy_grid.threshold)
+        keep = []  # tensors that must outlive the kernel launches
+        if isinstance(self.ray_marcher, RayMarcherAABB):
+            if not isinstance(self.contraction, ContractionAABB):
+                raise NotImplementedError("RayMarcherAABB is fused with ContractionAABB only")
+            aabb = self.contraction.aabb.detach().to("cpu", torch.float32)
+            m_aabb = self.ray_marcher.aabb.detach().to("cpu", torch.float32)
+            if not torch.equal(aabb, m_aabb):
+                raise NotImplementedError("marcher and contraction must share one aabb")
+            p.scene = 0
+            for i, v in enumerate(aabb.reshape(-1).tolist()):
+                p.aabb[i] = v
+            p.near, p.far = _f32(self.ray_marcher.near), _f32(self.ray_marcher.far)
+            ss = self.ray_marcher.step_size
+            p.step_size = float(ss.item()) if isinstance(ss, torch.Tensor) else _f32(ss)
+        elif isinstance(self.ray_marcher, RayMarcherUnbounded):
+            if not isinstance(self.contraction, ContractionMip360) or self.contraction.order != float("inf"):
+                raise NotImplementedError("RayMarcherUnbounded is fused with ContractionMip360(order=inf) only")
+            p.scene = 1
+            key = (str(device), self.ray_marcher.n_samples, self.ray_marcher.near, self.ray_marcher.uniform_range)
+            cache = self.__dict__.setdefault("_tables", {})
+            if key not in cache:
+                cache[key] = self.ray_marcher.tables(device)
+            t_tab, s_tab = cache[key]
+            p.t_table, p.step_table = t_tab.data_ptr(), s_tab.data_ptr()
+            keep += [t_tab, s_tab]
+        else:
+            raise NotImplementedError(f"unknown ray marcher {type(self.ray_marcher)}")
+        p._keep = keep
+        return p
+
+    @torch.no_grad()
+    def __call__(self, rays_o: torch.Tensor, rays_d: torch.Tensor, training: bool,
+                 noise: torch.Tensor | None = None, info_offset: int = 0):
+        """-> (packed_samples [N,7], packing_info [R,2] int32), same contents and order as the
+        reference (src/core.py:165-188).  packed_samples carries two extra attributes used by
+        NerfRenderer: `_tnf_steps` (contiguous copy of column 6) and packing_info `_tnf_partition`.
+
+        noise: optional [R,S] jitter in [0,1); default in training is torch.rand on the rays' device,
+        which consumes torch's CUDA generator exactly like the reference's rand_like (src/core.py:173).
+        """
+        lib = _lib.load()
+        _lib.require_cuda(rays_o, "rays_o")
+        _lib.require_cuda(rays_d, "rays_d")
+        dev = rays_o.device
+        rays_o = rays_o.to(torch.float32).contiguous()
+        rays_d = rays_d.to(torch.float32).contiguous()
+        R, S = rays_o.size(0), int(self.ray_marcher.n_samples)
+        with torch.cuda.device(dev):
+            p = self._params(dev, S)
+            if training:
+                if noise is None:
+                    noise = torch.rand(R, S, device=dev)
+                noise = noise.to(dev, torch.float32).contiguous()
+                if noise.numel() != R * S:
+                    raise RuntimeError("noise must have n_rays*n_samples elements")
+                p.jitter, p.noise = 1, noise.data_ptr()
+            words = (S + 31) // 32
+            mask_bits = torch.empty(max(R, 1) * words, dtype=torch.int32, device=dev)
+            info = torch.empty(R, 2, dtype=torch.int32, device=dev)
+            n_dev = torch.empty(1, dtype=torch.int64, device=dev)
+            stream = _lib.stream_ptr()
+            _lib.check(lib.tnf_march_count(C.byref(p), rays_o.data_ptr(), rays_d.data_ptr(), R, info_offset,
+                                           mask_bits.data_ptr(), info.data_ptr(), n_dev.data_ptr(), stream),
+                       "tnf_march_count")
+            n = int(n_dev.item())  # the one host sync of the provider (the reference has two)
+            packed = torch.empty(n, 7, device=dev)
+            steps = torch.empty(n, device=dev)
+            _lib.check(lib.tnf_march_pack(C.byref(p), rays_o.data_ptr(), rays_d.data_ptr(), R, info_offset,
+                                          mask_bits.data_ptr(), info.data_ptr(), packed.data_ptr(),
+                                          steps.data_ptr(), None, n, stream), "tnf_march_pack")
+        packed._tnf_steps = steps
+        info._tnf_partition = info_offset == 0
+        return packed, info
+
+
+# ------------------------------------------------------------------------------------------------
+# Rendering: weights op, compositing, renderer
+# ------------------------------------------------------------------------------------------------
+
+
+class NerfWeights(torch.autograd.Function):
+    """w_k = T_k (1 - exp(-sigma_k delta_k)) over packed rays (src/core.py:192-207)."""
+
+    @staticmethod
+    def forward(ctx: Any, sigmas: torch.Tensor, steps: torch.Tensor, info: torch.Tensor, threshold: float):  # type: ignore
+        sigmas = sigmas.contiguous()
+        info = info.contiguous()
+        flags = _cuda.TRUSTED_PARTITION if getattr(info, "_tnf_partition", False) else 0
+        weights = _cuda.weights_fwd(sigmas, steps, info, threshold, flags)  # steps may be a strided view
+        ctx.save_for_backward(sigmas, steps, info, weights)
+        ctx.flags = flags
+        return weights
+
+    @staticmethod
+    def backward(ctx: Any, grad_weights: torch.Tensor):  # type: ignore
+        grad_weights = grad_weights.contiguous()
+        sigmas, steps, info, weights = ctx.saved_tensors
+        grad_sigmas = _cuda.weights_bwd(sigmas, steps, info, weights, grad_weights, ctx.flags)
+        return grad_sigmas, None, None, None
+
+
+class Composite(torch.autograd.Function):
+    """rgb_ray = sum_k w_k rgb_k (+ bg (1 - sum_k w_k)) per packed ray (src/core.py:256-265)."""
+
+    @staticmethod
+    def forward(ctx: Any, weights: torch.Tensor, rgbs: torch.Tensor, info: torch.Tensor, bg):  # type: ignore
+        lib = _lib.load()
+        weights, rgbs, info = weights.contiguous(), rgbs.contiguous(), info.contiguous()
+        n, r = weights.size(0), info.size(0)
+        out = torch.empty(r, 3, device=weights.device)
+        bg_arr = None if bg is None else (C.c_float * 3)(*[float(v) for v in bg])
+        with torch.cuda.device(weights.device):
+            _lib.check(lib.tnf_composite_fwd(weights.data_ptr(), rgbs.data_ptr(), info.data_ptr(), n, r, bg_arr,
+                                             out.data_ptr(), None, _lib.stream_ptr()), "tnf_composite_fwd")
+        ctx.save_for_backward(weights, rgbs, info)
+        ctx.bg = bg
+        return out
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore
+        lib = _lib.load()
+        weights, rgbs, info = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        n, r = weights.size(0), info.size(0)
+        gw = torch.empty_like(weights) if ctx.needs_input_grad[0] else None
+        grgb = torch.empty_like(rgbs) if ctx.needs_input_grad[1] else None
+        bg_arr = None if ctx.bg is None else (C.c_float * 3)(*[float(v) for v in ctx.bg])
+        if gw is not None or grgb is not None:
+            with torch.cuda.device(weights.device):
+                _lib.check(lib.tnf_composite_bwd(weights.data_ptr(), rgbs.data_ptr(), info.data_ptr(), n, r,
+                                                 bg_arr, grad_out.data_ptr(), _lib.ptr(gw), _lib.ptr(grgb),
+                                                 _lib.stream_ptr()), "tnf_composite_bwd")
+        return gw, grgb, None, None
+
+
+class NerfRenderer(torch.nn.Module):
+    def __init__(self, feature_module: torch.nn.Module, sigma_decoder: torch.nn.Module,
+                 rgb_decoder: torch.nn.Module, bg_color: torch.Tensor | None = None):
+        super().__init__()
+        self.feature_module = feature_module
+        self.sigma_decoder = sigma_decoder
+        self.rgb_decoder = rgb_decoder
+        self.bg_color = bg_color
+        assert hasattr(self.feature_module, "feature_dim"), "feature module requires a feature_dim attribute"
+
+    def forward(self, packed_samples: torch.Tensor, packing_info: torch.Tensor,
+                early_termination_threshold: float = 1e-4) -> torch.Tensor:
+        """packed [N,7], info [R,2] -> rendered rgb [R,3] (src/core.py:225-267)."""
+        device = packed_samples.device
+        n_samples = packed_samples.size(0)
+        n_rays = packing_info.size(0)
+        steps = getattr(packed_samples, "_tnf_steps", None)
+        if steps is None:
+            steps = packed_samples[:, 6]  # strided view, read in place by the kernel
+        try:
+            if n_samples == 0:
+                raise ValueError("no samples remaining")
+            samples_features = self.feature_module(packed_samples[:, :3])
+            samples_sigmas = self.sigma_decoder(samples_features).ravel()
+            weights: torch.Tensor = NerfWeights.apply(samples_sigmas, steps, packing_info,
+                                                      early_termination_threshold)  # type: ignore
+            mask = weights > 0.0
+            idx = mask.nonzero(as_tuple=True)[0]  # one sync, shared by the three masked ops below
+            if idx.numel() == 0:
+                raise ValueError("no samples remaining")
+            rgbs_m = self.rgb_decoder(samples_features.index_select(0, idx),
+                                      packed_samples[:, 3:6].index_select(0, idx))
+            samples_rgbs = torch.zeros((n_samples, 3), device=device).index_copy(0, idx, rgbs_m)
+        except ValueError:
+            print("Empty iteration, every sample is masked")
+            samples_rgbs = torch.zeros((n_samples, 3), device=device, requires_grad=True)
+            weights = torch.zeros(n_samples, device=device, requires_grad=True)
+        bg = None if self.bg_color is None else self.bg_color.detach().reshape(-1).tolist()
+        if n_rays == 0:
+            return torch.zeros((0, 3), device=device)
+        return Composite.apply(weights, samples_rgbs, packing_info, bg)

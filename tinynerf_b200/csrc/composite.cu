@@ -1,0 +1,110 @@
+// a18 -- compositing: per-ray segment sums of w*rgb and w over packed samples, + background
+// (reference: the index_add_ block of NerfRenderer.forward, src/core.py:256-265, which the reference
+// itself marks "TODO: cuda kernel this").  The reference builds a [N] ray-index tensor with
+// repeat_interleave (host sync) and scatters with float atomics; here packing info gives each ray its
+// contiguous segment, so one warp reduces one ray with coalesced reads and no atomics (deterministic).
+#include "common.cuh"
+
+namespace tnf {
+namespace {
+
+constexpr int kWarpsC = 8;
+
+__global__ void __launch_bounds__(kWarpsC * 32)
+composite_fwd_kernel(const float* __restrict__ w, const float* __restrict__ rgb, const int2* __restrict__ info,
+                     long long n_samples, long long n_rays, bool has_bg, float bg0, float bg1, float bg2,
+                     float* __restrict__ out_rgb, float* __restrict__ out_op) {
+  const int lane = threadIdx.x & 31;
+  const long long ray = blockIdx.x * (long long)kWarpsC + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const int2 e = __ldg(&info[ray]);
+  long long k0 = e.x, k1 = (long long)e.x + e.y;
+  if (k0 < 0) k0 = 0;
+  if (k1 > n_samples) k1 = n_samples;
+  float r = 0.f, g = 0.f, b = 0.f, op = 0.f;
+  for (long long k = k0 + lane; k < k1; k += 32) {
+    const float wk = __ldg(w + k);
+    r = __fmaf_rn(wk, __ldg(rgb + 3 * k + 0), r);
+    g = __fmaf_rn(wk, __ldg(rgb + 3 * k + 1), g);
+    b = __fmaf_rn(wk, __ldg(rgb + 3 * k + 2), b);
+    op += wk;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    r += __shfl_xor_sync(kFullMask, r, d);
+    g += __shfl_xor_sync(kFullMask, g, d);
+    b += __shfl_xor_sync(kFullMask, b, d);
+    op += __shfl_xor_sync(kFullMask, op, d);
+  }
+  if (lane == 0) {
+    if (has_bg) {  // rendered + bg * (1 - opacity)   (src/core.py:265)
+      const float t = __fsub_rn(1.f, op);
+      r = __fadd_rn(r, __fmul_rn(bg0, t));
+      g = __fadd_rn(g, __fmul_rn(bg1, t));
+      b = __fadd_rn(b, __fmul_rn(bg2, t));
+    }
+    out_rgb[3 * ray + 0] = r;
+    out_rgb[3 * ray + 1] = g;
+    out_rgb[3 * ray + 2] = b;
+    if (out_op) out_op[ray] = op;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsC * 32)
+composite_bwd_kernel(const float* __restrict__ w, const float* __restrict__ rgb, const int2* __restrict__ info,
+                     long long n_samples, long long n_rays, bool has_bg, float bg0, float bg1, float bg2,
+                     const float* __restrict__ go, float* __restrict__ gw, float* __restrict__ grgb) {
+  const int lane = threadIdx.x & 31;
+  const long long ray = blockIdx.x * (long long)kWarpsC + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const int2 e = __ldg(&info[ray]);
+  long long k0 = e.x, k1 = (long long)e.x + e.y;
+  if (k0 < 0) k0 = 0;
+  if (k1 > n_samples) k1 = n_samples;
+  const float g0 = __ldg(go + 3 * ray), g1 = __ldg(go + 3 * ray + 1), g2 = __ldg(go + 3 * ray + 2);
+  const float gbg = has_bg ? (bg0 * g0 + bg1 * g1 + bg2 * g2) : 0.f;
+  for (long long k = k0 + lane; k < k1; k += 32) {
+    const float wk = __ldg(w + k);
+    if (gw) gw[k] = __ldg(rgb + 3 * k) * g0 + __ldg(rgb + 3 * k + 1) * g1 + __ldg(rgb + 3 * k + 2) * g2 - gbg;
+    if (grgb) {
+      grgb[3 * k + 0] = wk * g0;
+      grgb[3 * k + 1] = wk * g1;
+      grgb[3 * k + 2] = wk * g2;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace tnf
+
+extern "C" int tnf_composite_fwd(const float* weights, const float* rgbs, const int32_t* info,
+                                 int64_t n_samples, int64_t n_rays, const float* bg, float* out_rgb,
+                                 float* out_opacity, void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(n_samples >= 0 && n_rays >= 0, "negative size");
+  if (n_rays == 0) return TNF_OK;
+  TNF_REQUIRE(info && out_rgb, "null pointer");
+  TNF_REQUIRE(n_samples == 0 || (weights && rgbs), "null sample pointer");
+  TNF_REQUIRE((reinterpret_cast<uintptr_t>(info) & 7u) == 0, "info must be 8-byte aligned");
+  composite_fwd_kernel<<<(unsigned)ceil_div(n_rays, kWarpsC), kWarpsC * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      weights, rgbs, reinterpret_cast<const int2*>(info), n_samples, n_rays, bg != nullptr, bg ? bg[0] : 0.f,
+      bg ? bg[1] : 0.f, bg ? bg[2] : 0.f, out_rgb, out_opacity);
+  TNF_LAUNCH_CHECK("composite_fwd_kernel");
+  return TNF_OK;
+}
+
+extern "C" int tnf_composite_bwd(const float* weights, const float* rgbs, const int32_t* info,
+                                 int64_t n_samples, int64_t n_rays, const float* bg, const float* grad_out,
+                                 float* grad_weights, float* grad_rgbs, void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(n_samples >= 0 && n_rays >= 0, "negative size");
+  if (n_rays == 0 || n_samples == 0) return TNF_OK;
+  TNF_REQUIRE(info && grad_out && weights && rgbs, "null pointer");
+  TNF_REQUIRE(grad_weights || grad_rgbs, "no gradient requested");
+  TNF_REQUIRE((reinterpret_cast<uintptr_t>(info) & 7u) == 0, "info must be 8-byte aligned");
+  composite_bwd_kernel<<<(unsigned)ceil_div(n_rays, kWarpsC), kWarpsC * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      weights, rgbs, reinterpret_cast<const int2*>(info), n_samples, n_rays, bg != nullptr, bg ? bg[0] : 0.f,
+      bg ? bg[1] : 0.f, bg ? bg[2] : 0.f, grad_out, grad_weights, grad_rgbs);
+  TNF_LAUNCH_CHECK("composite_bwd_kernel");
+  return TNF_OK;
+}

@@ -1,0 +1,554 @@
+// a1/a2 -- NeRF-equation weights over packed variable-length rays (reference: src/cuda.cu:3-58).
+//
+// Design (see DESIGN.md "weights"): the reference walks each ray with one thread.  Here the sample
+// axis is streamed: every warp owns a "task" = all rays whose first sample lies in one tile of the
+// sample axis, reads that contiguous sample window with perfectly coalesced 128-bit loads (each
+// lane 4 consecutive samples, 512 B per warp instruction) and evaluates the segmented exclusive
+// cumprod of a_k = exp(-sigma_k*delta_k) with a warp-segmented scan (shuffle Hillis-Steele over
+// per-lane aggregates + a register carry from round to round).  Ray boundaries come from a per-warp
+// shared-memory bitfield of ray-head positions built from packing info.  Tasks are aligned to rays,
+// so warps never wait on each other (no look-back chain, no deadlock potential).
+//
+// Exact termination: the reference stops a ray at the first k with T_k <= thr where T_k is the
+// *serial* fp32 product.  A scan re-associates the product, so T can differ by <= (k-1)*2^-23
+// relative.  Any ray that has a sample whose scanned T lies inside that rigorous band around thr is
+// re-evaluated by one lane in the reference's serial order (rare: ~1e-3 of terminating rays), which
+// makes the (weights > 0) mask bit-identical to the reference.
+#include "common.cuh"
+
+namespace tnf {
+namespace {
+
+constexpr int kWarps = 8;                  // warps per CTA, each runs independent tasks
+constexpr int kMaxTile = 2048;             // max samples per task tile
+constexpr int kMaskWords = kMaxTile / 32;  // head bitfield words per warp
+constexpr int kQueue = 32;                 // per-task queue of samples needing serial re-evaluation
+
+struct WArgs {
+  const float* sigmas;
+  const float* steps;
+  long long sstride;
+  const int2* info;
+  float thr;
+  float* out;      // weights (fwd) / grad_sigmas (bwd)
+  const float* w;  // bwd: saved weights
+  const float* g;  // bwd: grad wrt weights
+  long long n;
+  int n_rays;
+  int tile;
+  int n_tasks;
+  unsigned* status;
+  int flags;
+};
+
+// MODE 0: all arrays contiguous + 16B aligned (float4 path); 1: steps strided, rest aligned; 2: scalar.
+template <int MODE>
+__device__ __forceinline__ void load_vec(const float* p, long long idx, long long n, float v[4]) {
+  if (MODE != 2 && idx + 3 < n) {
+    float4 t = ld_stream_f4(p + idx);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (idx + i < n) ? __ldg(p + idx + i) : 0.f;
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void load_steps(const float* p, long long stride, long long idx, long long n,
+                                           float v[4]) {
+  if (MODE == 0) {
+    load_vec<0>(p, idx, n, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (idx + i < n) ? __ldg(p + (idx + i) * stride) : 0.f;
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void store_vec(float* p, long long idx, long long lo, long long hi,
+                                          const float v[4]) {
+  if (MODE != 2 && idx >= lo && idx + 3 < hi) {
+    st_stream_f4(p + idx, make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (idx + i >= lo && idx + i < hi) p[idx + i] = v[i];
+  }
+}
+
+// First r in [0,n) with info[r].start >= key (n if none); warp-cooperative 32-ary search, 4 rounds
+// for 2^20 rays.  Terminates for arbitrary (unsorted) data.
+__device__ __forceinline__ int warp_lower_bound(const int2* __restrict__ info, int n, long long key,
+                                                int lane) {
+  int lo = 0, hi = n;
+  while (hi > lo) {
+    const int len = hi - lo;
+    const int step = (len + 31) >> 5;
+    const long long pl = (long long)lo + (long long)lane * step;
+    bool pred = false;
+    if (pl < hi) pred = (long long)__ldg(&info[pl].x) < key;
+    const unsigned b = __ballot_sync(kFullMask, pred);
+    // predicates are a prefix of ones when sorted; for garbage use the first zero as the split
+    const int cnt = __ffs(~b) - 1;  // number of leading true lanes (32 if all true -> ffs(0)=0 -> -1)
+    const int c = (b == kFullMask) ? 32 : cnt;
+    if (c == 0) {
+      hi = lo;
+    } else {
+      const long long q = (long long)lo + (long long)(c - 1) * step;
+      const long long nh = q + step;
+      lo = (int)(q + 1);
+      hi = (int)(nh < hi ? nh : hi);
+    }
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int find_head_le(const unsigned* mask, int b, int tile) {
+  if (b >= tile) b = tile - 1;
+  int w = b >> 5;
+  unsigned m = mask[w] & (0xFFFFFFFFu >> (31 - (b & 31)));
+  while (m == 0u && w > 0) m = mask[--w];
+  return m ? (w << 5) + 31 - __clz(m) : -1;
+}
+__device__ __forceinline__ int find_head_gt(const unsigned* mask, int b, int tile) {
+  ++b;
+  if (b >= tile) return -1;
+  int w = b >> 5;
+  const int nw = tile >> 5;
+  unsigned m = mask[w] & (0xFFFFFFFFu << (b & 31));
+  while (m == 0u && w + 1 < nw) m = mask[++w];
+  return m ? (w << 5) + __ffs(m) - 1 : -1;
+}
+// bits [rel, rel+5) of the head bitfield (zero beyond the tile)
+__device__ __forceinline__ unsigned head_bits5(const unsigned* mask, int rel, int tile) {
+  if (rel >= tile) return 0u;
+  const unsigned lo = mask[rel >> 5];
+  const unsigned hi = (rel + 32 < tile) ? mask[(rel >> 5) + 1] : 0u;
+  const unsigned long long both = ((unsigned long long)hi << 32) | lo;
+  return (unsigned)(both >> (rel & 31)) & 0x1Fu;
+}
+
+// The reference's loop, verbatim semantics (src/cuda.cu:19-28), plus the zeros it gets from
+// zeros_like (src/cuda.cu:84) for samples after termination.
+__device__ __noinline__ void serial_ray_fwd(const float* __restrict__ sig, const float* __restrict__ stp,
+                                            long long ss, long long start, long long end, float thr,
+                                            float* out) {
+  float transmittance = 1.f;
+  long long k = start;
+  while (transmittance > thr && k < end) {
+    const float alpha = __expf(-sig[k] * stp[k * ss]);
+    out[k] = transmittance * (1. - alpha);  // double multiply, as in the reference
+    transmittance *= alpha;
+    ++k;
+  }
+  for (; k < end; ++k) out[k] = 0.f;
+}
+// src/cuda.cu:49-56 (two serial passes; fused-multiply-adds written out explicitly).
+__device__ __noinline__ void serial_ray_bwd(const float* __restrict__ sig, const float* __restrict__ stp,
+                                            long long ss, const float* __restrict__ w,
+                                            const float* __restrict__ g, long long start, long long end,
+                                            float* out) {
+  float acc = 0.f, transmittance = 1.f;
+  for (long long k = start; k < end; ++k) acc = __fmaf_rn(-w[k], g[k], acc);
+  for (long long k = start; k < end; ++k) {
+    acc = __fmaf_rn(w[k], g[k], acc);
+    transmittance *= __expf(-sig[k] * stp[k * ss]);
+    out[k] = stp[k * ss] * __fmaf_rn(transmittance, g[k], acc);
+  }
+}
+
+struct Task {
+  long long tile0, s0, s1;
+  int r_lo, r_hi;
+  bool valid;
+};
+
+// Common task prologue: optional partition validation, ray range, sample window, head bitfield.
+__device__ __forceinline__ Task task_setup(const WArgs& A, int task, unsigned* mask, int lane) {
+  Task t;
+  const long long N = A.n;
+  const int R = A.n_rays;
+  if (!(A.flags & TNF_W_TRUSTED_PARTITION)) {
+    // every task validates a static slice of the ray list (coalesced 8 B/ray, +~1% traffic)
+    const long long rb = (long long)task * R / A.n_tasks, re = (long long)(task + 1) * R / A.n_tasks;
+    bool bad = false;
+    for (long long r = rb + lane; r < re; r += 32) {
+      const int2 e = __ldg(&A.info[r]);
+      const long long nxt = (r + 1 < R) ? (long long)__ldg(&A.info[r + 1].x) : N;
+      bad |= (e.y < 0) | (e.x < 0) | ((long long)e.x + e.y != nxt) | (r == 0 && e.x != 0);
+    }
+    if (__any_sync(kFullMask, bad) && lane == 0) atomicOr(A.status, 1u);
+  }
+  t.tile0 = (long long)task * A.tile;
+  t.r_lo = warp_lower_bound(A.info, R, t.tile0, lane);
+  t.r_hi = warp_lower_bound(A.info, R, t.tile0 + A.tile, lane);
+  long long s0 = (t.r_lo < R) ? (long long)__ldg(&A.info[t.r_lo].x) : N;
+  long long s1 = (t.r_hi < R) ? (long long)__ldg(&A.info[t.r_hi].x) : N;
+  s0 = s0 < 0 ? 0 : (s0 > N ? N : s0);
+  s1 = s1 < 0 ? 0 : (s1 > N ? N : s1);
+  t.s0 = s0;
+  t.s1 = s1;
+  t.valid = (s0 >= t.tile0) && (s1 > s0) && (t.r_hi > t.r_lo);
+  if (!t.valid) return t;
+  for (int i = lane; i < (A.tile >> 5); i += 32) mask[i] = 0u;
+  __syncwarp();
+  for (int r = t.r_lo + lane; r < t.r_hi; r += 32) {
+    const int2 e = __ldg(&A.info[r]);
+    const long long b = (long long)e.x - t.tile0;
+    if (e.y > 0 && b >= 0 && b < A.tile) atomicOr(&mask[b >> 5], 1u << (b & 31));
+  }
+  __syncwarp();
+  return t;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWarps * 32) weights_fwd_kernel(const WArgs A) {
+  __shared__ unsigned s_mask[kWarps][kMaskWords];
+  __shared__ int s_q[kWarps][kQueue];
+  __shared__ int s_qn[kWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned* mask = s_mask[wib];
+  int* queue = s_q[wib];
+  const bool exact = !(A.flags & TNF_W_NO_EXACT_TERMINATION);
+  const float thr = A.thr;
+  const bool tiny_thr = thr < 1.5777218e-30f;  // 2^-99: transmittance may underflow before stopping
+  const int n_warps = gridDim.x * kWarps;
+
+  for (int task = blockIdx.x * kWarps + wib; task < A.n_tasks; task += n_warps) {
+    if (!(A.flags & TNF_W_TRUSTED_PARTITION) && *(volatile unsigned*)A.status) return;
+    const Task t = task_setup(A, task, mask, lane);
+    if (!t.valid) continue;
+    if (lane == 0) s_qn[wib] = 0;
+    __syncwarp();
+
+    float carry = 1.f;  // product since the last ray head, through the end of the previous round
+    for (long long pos = t.tile0 + ((t.s0 - t.tile0) & ~127LL); pos < t.s1; pos += 128) {
+      const long long idx = pos + lane * 4;
+      const int rel = (int)(idx - t.tile0);
+      float s[4], d[4], a[4], T[4], w[4];
+      load_vec<MODE>(A.sigmas, idx, A.n, s);
+      load_steps<MODE>(A.steps, A.sstride, idx, A.n, d);
+      const unsigned hb = (rel < A.tile) ? ((mask[rel >> 5] >> (rel & 31)) & 0xFu) : 0u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = __expf(-s[i] * d[i]);
+
+      // lane aggregate: product of this lane's samples after its last head
+      float P = a[0];
+#pragma unroll
+      for (int i = 1; i < 4; ++i) P = ((hb >> i) & 1u) ? a[i] : P * a[i];
+      int F = hb != 0u;
+      if (lane == 0 && !F) P *= carry;
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const float Pu = __shfl_up_sync(kFullMask, P, dlt);
+        const int Fu = __shfl_up_sync(kFullMask, F, dlt);
+        if (lane >= dlt) {
+          if (!F) P *= Pu;
+          F |= Fu;
+        }
+      }
+      float E = __shfl_up_sync(kFullMask, P, 1);
+      if (lane == 0) E = carry;
+      carry = __shfl_sync(kFullMask, P, 31);
+
+      // exclusive transmittance per sample
+      T[0] = (hb & 1u) ? 1.f : E;
+#pragma unroll
+      for (int i = 1; i < 4; ++i) T[i] = ((hb >> i) & 1u) ? 1.f : T[i - 1] * a[i - 1];
+
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool alive = T[i] > thr;
+        // same arithmetic as the reference: one fp64 multiply, rounded to fp32 on store
+        w[i] = alive ? (float)((double)T[i] * (1. - (double)a[i])) : 0.f;
+      }
+      if (exact) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long k = idx + i;
+          if (k < t.s0 || k >= t.s1) continue;
+          // cheap prefilter with an upper bound on the sample's position in its ray
+          const float kub = (float)(k - t.s0 + 2);
+          bool sus = !(a[i] <= 1.f) || (fabsf(T[i] - thr) <= thr * kub * 1.7881393e-07f) ||
+                     (tiny_thr && T[i] < 7.8886091e-31f);
+          if (sus) {
+            bool push = !(a[i] <= 1.f) || (tiny_thr && T[i] < 7.8886091e-31f);
+            if (!push) {
+              const int h = find_head_le(mask, rel + i, A.tile);
+              const float krel = (float)(rel + i - h + 1);
+              push = (h < 0) || (fabsf(T[i] - thr) <= thr * krel * 1.7881393e-07f);  // 1.5 * 2^-23
+            }
+            if (push) {
+              const int slot = atomicAdd(&s_qn[wib], 1);
+              if (slot < kQueue) queue[slot] = rel + i;
+            }
+          }
+        }
+      }
+      store_vec<MODE>(A.out, idx, t.s0, t.s1, w);
+    }
+
+    if (exact) {
+      __syncwarp();
+      const int nq = s_qn[wib];
+      if (nq > kQueue) {  // pathological data: redo every ray of the task in reference order
+        for (int r = t.r_lo + lane; r < t.r_hi; r += 32) {
+          const int2 e = __ldg(&A.info[r]);
+          long long st = e.x, en = (long long)e.x + e.y;
+          if (e.y > 0 && st >= t.s0 && en <= t.s1) serial_ray_fwd(A.sigmas, A.steps, A.sstride, st, en, thr, A.out);
+        }
+      } else if (lane < nq) {
+        const int b = queue[lane];
+        const int hs = find_head_le(mask, b, A.tile);
+        const int he = find_head_gt(mask, b, A.tile);
+        if (hs >= 0) {
+          const long long st = t.tile0 + hs;
+          const long long en = (he < 0) ? t.s1 : t.tile0 + he;
+          serial_ray_fwd(A.sigmas, A.steps, A.sstride, st, en, thr, A.out);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWarps * 32) weights_bwd_kernel(const WArgs A) {
+  __shared__ unsigned s_mask[kWarps][kMaskWords];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned* mask = s_mask[wib];
+  const int n_warps = gridDim.x * kWarps;
+
+  for (int task = blockIdx.x * kWarps + wib; task < A.n_tasks; task += n_warps) {
+    if (!(A.flags & TNF_W_TRUSTED_PARTITION) && *(volatile unsigned*)A.status) return;
+    const Task t = task_setup(A, task, mask, lane);
+    if (!t.valid) continue;
+    const long long first = t.tile0 + ((t.s0 - t.tile0) & ~127LL);
+    const long long last = t.tile0 + ((t.s1 - 1 - t.tile0) & ~127LL);
+
+    // Pass A (descending): S_k = sum_{j>k in ray} w_j*g_j, parked in grad_sigmas.
+    float carry = 0.f;
+    for (long long pos = last; pos >= first; pos -= 128) {
+      const long long idx = pos + lane * 4;
+      const int rel = (int)(idx - t.tile0);
+      float w[4], g[4], c[4], S[4];
+      load_vec<MODE>(A.w, idx, A.n, w);
+      load_vec<MODE>(A.g, idx, A.n, g);
+      const unsigned hb5 = head_bits5(mask, rel, A.tile);
+      unsigned tail = 0u;  // bit i: sample idx+i is the last sample of its ray
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        c[i] = (idx + i < t.s1) ? w[i] * g[i] : 0.f;
+        tail |= ((((hb5 >> (i + 1)) & 1u) | (unsigned)(idx + i + 1 >= t.s1)) << i);
+      }
+      // lane aggregate in descending order: inclusive suffix sum of the lowest sample
+      float P = c[3];
+#pragma unroll
+      for (int i = 2; i >= 0; --i) P = ((tail >> i) & 1u) ? c[i] : P + c[i];
+      int F = tail != 0u;
+      if (lane == 31 && !F) P += carry;
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const float Pu = __shfl_down_sync(kFullMask, P, dlt);
+        const int Fu = __shfl_down_sync(kFullMask, F, dlt);
+        if (lane + dlt < 32) {
+          if (!F) P += Pu;
+          F |= Fu;
+        }
+      }
+      float E = __shfl_down_sync(kFullMask, P, 1);  // inclusive suffix sum of sample idx+4
+      if (lane == 31) E = carry;
+      carry = __shfl_sync(kFullMask, P, 0);
+      S[3] = ((tail >> 3) & 1u) ? 0.f : E;
+#pragma unroll
+      for (int i = 2; i >= 0; --i) S[i] = ((tail >> i) & 1u) ? 0.f : S[i + 1] + c[i + 1];
+      store_vec<MODE>(A.out, idx, t.s0, t.s1, S);
+    }
+    __syncwarp();
+
+    // Pass B (ascending): T_{k+1} = prod_{j<=k in ray} a_j (no termination, src/cuda.cu:52-56);
+    // grad_sigma_k = delta_k * (T_{k+1}*g_k - S_k).  Each lane re-reads the S it stored itself.
+    float carryT = 1.f;
+    for (long long pos = first; pos <= last; pos += 128) {
+      const long long idx = pos + lane * 4;
+      const int rel = (int)(idx - t.tile0);
+      float s[4], d[4], g[4], a[4], S[4], o[4];
+      load_vec<MODE>(A.sigmas, idx, A.n, s);
+      load_steps<MODE>(A.steps, A.sstride, idx, A.n, d);
+      load_vec<MODE>(A.g, idx, A.n, g);
+      if (MODE != 2 && idx >= t.s0 && idx + 3 < t.s1) {
+        const float4 v = *reinterpret_cast<const float4*>(A.out + idx);
+        S[0] = v.x; S[1] = v.y; S[2] = v.z; S[3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) S[i] = (idx + i >= t.s0 && idx + i < t.s1) ? A.out[idx + i] : 0.f;
+      }
+      const unsigned hb = (rel < A.tile) ? ((mask[rel >> 5] >> (rel & 31)) & 0xFu) : 0u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = __expf(-s[i] * d[i]);
+      float P = a[0];
+#pragma unroll
+      for (int i = 1; i < 4; ++i) P = ((hb >> i) & 1u) ? a[i] : P * a[i];
+      int F = hb != 0u;
+      if (lane == 0 && !F) P *= carryT;
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const float Pu = __shfl_up_sync(kFullMask, P, dlt);
+        const int Fu = __shfl_up_sync(kFullMask, F, dlt);
+        if (lane >= dlt) {
+          if (!F) P *= Pu;
+          F |= Fu;
+        }
+      }
+      float E = __shfl_up_sync(kFullMask, P, 1);
+      if (lane == 0) E = carryT;
+      carryT = __shfl_sync(kFullMask, P, 31);
+      float Tn = ((hb & 1u) ? 1.f : E) * a[0];  // inclusive product T_{k+1}
+      o[0] = d[0] * __fmaf_rn(Tn, g[0], -S[0]);
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        Tn = (((hb >> i) & 1u) ? 1.f : Tn) * a[i];
+        o[i] = d[i] * __fmaf_rn(Tn, g[i], -S[i]);
+      }
+      store_vec<MODE>(A.out, idx, t.s0, t.s1, o);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- generic path for packing info that is not a sorted partition (matches the reference for any
+// non-overlapping info: thread per ray in reference order, untouched samples are zero) ----------
+__global__ void fallback_zero_kernel(const unsigned* status, float* out, long long n) {
+  if (!(*status & 1u)) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = 0.f;
+}
+__global__ void fallback_fwd_kernel(const WArgs A) {
+  if (!(*A.status & 1u)) return;
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= A.n_rays) return;
+  const int2 e = A.info[r];
+  const long long st = e.x, en = (long long)e.x + e.y;
+  if (e.y <= 0 || st < 0 || en > A.n) return;
+  // reference semantics: nothing written after termination (stays zero from the zero pass)
+  float transmittance = 1.f;
+  long long k = st;
+  while (transmittance > A.thr && k < en) {
+    const float alpha = __expf(-A.sigmas[k] * A.steps[k * A.sstride]);
+    A.out[k] = transmittance * (1. - alpha);
+    transmittance *= alpha;
+    ++k;
+  }
+}
+__global__ void fallback_bwd_kernel(const WArgs A) {
+  if (!(*A.status & 1u)) return;
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= A.n_rays) return;
+  const int2 e = A.info[r];
+  const long long st = e.x, en = (long long)e.x + e.y;
+  if (e.y <= 0 || st < 0 || en > A.n) return;
+  serial_ray_bwd(A.sigmas, A.steps, A.sstride, A.w, A.g, st, en, A.out);
+}
+
+int pick_tile(long long n) {
+  // enough tasks to give every SM ~32 resident warps, tiles between 256 and 2048 samples
+  const long long want = (long long)sm_count() * 32;
+  long long tile = (n / want) & ~127LL;
+  if (tile < 256) tile = 256;
+  if (tile > kMaxTile) tile = kMaxTile;
+  return (int)tile;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int launch(bool bwd, WArgs A, cudaStream_t st) {
+  const bool trusted = A.flags & TNF_W_TRUSTED_PARTITION;
+  if (!trusted) TNF_CUDA(cudaMemsetAsync(A.status, 0, sizeof(unsigned), st));
+  A.tile = pick_tile(A.n);
+  const long long n_tasks = ceil_div(A.n, A.tile);
+  TNF_REQUIRE(n_tasks < (1LL << 30), "too many samples (%lld)", A.n);
+  A.n_tasks = (int)n_tasks;
+  bool al = aligned16(A.sigmas) && aligned16(A.out);
+  if (bwd) al = al && aligned16(A.w) && aligned16(A.g);
+  const int mode = !al ? 2 : ((A.sstride == 1 && aligned16(A.steps)) ? 0 : 1);
+  const long long max_ctas = (long long)sm_count() * 8;  // 64 warps/SM resident at most
+  long long ctas = ceil_div(n_tasks, kWarps);
+  if (ctas > max_ctas) ctas = max_ctas;
+  const dim3 grid((unsigned)ctas), block(kWarps * 32);
+  if (!bwd) {
+    if (mode == 0) weights_fwd_kernel<0><<<grid, block, 0, st>>>(A);
+    else if (mode == 1) weights_fwd_kernel<1><<<grid, block, 0, st>>>(A);
+    else weights_fwd_kernel<2><<<grid, block, 0, st>>>(A);
+    TNF_LAUNCH_CHECK("weights_fwd_kernel");
+  } else {
+    if (mode == 0) weights_bwd_kernel<0><<<grid, block, 0, st>>>(A);
+    else if (mode == 1) weights_bwd_kernel<1><<<grid, block, 0, st>>>(A);
+    else weights_bwd_kernel<2><<<grid, block, 0, st>>>(A);
+    TNF_LAUNCH_CHECK("weights_bwd_kernel");
+  }
+  if (!trusted) {
+    const int zb = (int)(ceil_div(A.n, 256 * 8) < sm_count() * 8 ? ceil_div(A.n, 256 * 8) : sm_count() * 8);
+    fallback_zero_kernel<<<zb, 256, 0, st>>>(A.status, A.out, A.n);
+    TNF_LAUNCH_CHECK("fallback_zero_kernel");
+    const unsigned rb = (unsigned)ceil_div(A.n_rays, 128);
+    if (!bwd) fallback_fwd_kernel<<<rb, 128, 0, st>>>(A);
+    else fallback_bwd_kernel<<<rb, 128, 0, st>>>(A);
+    TNF_LAUNCH_CHECK("fallback_ray_kernel");
+  }
+  return TNF_OK;
+}
+
+int check_common(const float* sigmas, const float* steps, int64_t stride, const int32_t* info,
+                 const float* out, int64_t n, int64_t r, int flags, const uint32_t* status) {
+  TNF_REQUIRE(n >= 0 && r >= 0, "negative size (n_samples=%lld, n_rays=%lld)", (long long)n, (long long)r);
+  TNF_REQUIRE(n < (1LL << 31) && r < (1LL << 31), "sizes must fit int32 (packing info is int32)");
+  if (n == 0) return TNF_OK;
+  TNF_REQUIRE(sigmas && steps && out, "null sample pointer");
+  TNF_REQUIRE(stride >= 1, "steps_stride must be >= 1");
+  TNF_REQUIRE(r == 0 || info, "null info pointer");
+  TNF_REQUIRE((reinterpret_cast<uintptr_t>(info) & 7u) == 0, "info must be 8-byte aligned");
+  TNF_REQUIRE((flags & TNF_W_TRUSTED_PARTITION) || status, "status word required unless TNF_W_TRUSTED_PARTITION");
+  return TNF_OK;
+}
+
+}  // namespace
+}  // namespace tnf
+
+extern "C" int tnf_weights_fwd(const float* sigmas, const float* steps, int64_t steps_stride,
+                               const int32_t* info, float threshold, float* weights, int64_t n_samples,
+                               int64_t n_rays, int flags, uint32_t* status, void* stream) {
+  using namespace tnf;
+  int rc = check_common(sigmas, steps, steps_stride, info, weights, n_samples, n_rays, flags, status);
+  if (rc != TNF_OK || n_samples == 0) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_rays == 0) {  // nothing covers the samples: all zero (src/cuda.cu:84)
+    TNF_CUDA(cudaMemsetAsync(weights, 0, sizeof(float) * n_samples, st));
+    return TNF_OK;
+  }
+  WArgs A{};
+  A.sigmas = sigmas; A.steps = steps; A.sstride = steps_stride;
+  A.info = reinterpret_cast<const int2*>(info);
+  A.thr = threshold; A.out = weights; A.n = n_samples; A.n_rays = (int)n_rays;
+  A.status = status; A.flags = flags;
+  return launch(false, A, st);
+}
+
+extern "C" int tnf_weights_bwd(const float* sigmas, const float* steps, int64_t steps_stride,
+                               const int32_t* info, const float* weights, const float* grad_weights,
+                               float* grad_sigmas, int64_t n_samples, int64_t n_rays, int flags,
+                               uint32_t* status, void* stream) {
+  using namespace tnf;
+  int rc = check_common(sigmas, steps, steps_stride, info, grad_sigmas, n_samples, n_rays, flags, status);
+  if (rc != TNF_OK || n_samples == 0) return rc;
+  TNF_REQUIRE(weights && grad_weights, "null weights/grad_weights pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_rays == 0) {
+    TNF_CUDA(cudaMemsetAsync(grad_sigmas, 0, sizeof(float) * n_samples, st));
+    return TNF_OK;
+  }
+  WArgs A{};
+  A.sigmas = sigmas; A.steps = steps; A.sstride = steps_stride;
+  A.info = reinterpret_cast<const int2*>(info);
+  A.out = grad_sigmas; A.w = weights; A.g = grad_weights; A.n = n_samples; A.n_rays = (int)n_rays;
+  A.status = status; A.flags = flags;
+  return launch(true, A, st);
+}

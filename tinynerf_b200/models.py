@@ -1,0 +1,387 @@
+"""Host-side mirror of the reference's models (src/models.py) over the sm_100a kernels.
+
+Same module names, constructor arguments, `feature_dim` attributes and state_dict keys/shapes:
+
+    MLP, PositionalEncoding, truncated_exp                      src/models.py:7-55
+    VanillaFeatureMLP / VanillaOpacityDecoder / VanillaColorDecoder   :59-89
+    KPlanesFeaturePlane / KPlanesFeatureField                   :93-181
+    SawtoothEncoding / CobafaGrid / CobafaFeatureField          :209-266
+
+Feature grids keep their logical [1,C,...] parameter shape but are stored channels-last, which is
+what the fused gather kernels (tnf_kplanes_*, tnf_cobafa_*) read: one interpolation corner = one
+contiguous C*4-byte line.  The small MLPs are dense contractions and stay nn.Linear stacks here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+from typing import Any, Callable, List, Tuple, cast
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+
+class MLP(torch.nn.Module):
+    """Linear/activation stack with the reference's module tree, hence the same state_dict keys
+    (`net.0`, `net.{2+i}.0`, `net.{2+h}`; src/models.py:17-26)."""
+
+    def __init__(self, in_features: int, hidden_features: int, hidden_layers: int,
+                 out_features: int | None = None, activation: Callable = torch.nn.ReLU):
+        super().__init__()
+        Lin, Seq = torch.nn.Linear, torch.nn.Sequential
+        blocks: List[torch.nn.Module] = [Lin(in_features, hidden_features), activation()]
+        for _ in range(hidden_layers):
+            blocks.append(Seq(Lin(hidden_features, hidden_features), activation()))
+        blocks.append(Lin(hidden_features, hidden_features if out_features is None else out_features))
+        self.net = Seq(*blocks)
+
+    def linears(self) -> List[torch.nn.Linear]:
+        """The Linear layers in evaluation order (used by the fused MLP kernels)."""
+        return [m for m in self.net.modules() if isinstance(m, torch.nn.Linear)]
+
+    def forward(self, x: torch.Tensor):
+        return self.net(x)
+
+
+class PositionalEncoding(torch.nn.Module):
+    def __init__(self, n_freqs: int):
+        super().__init__()
+        self.freqs: torch.Tensor
+        self.register_buffer("freqs", 2 ** torch.arange(0, n_freqs) * torch.pi)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = x[..., None] * self.freqs
+        x = torch.cat([torch.sin(x), torch.cos(x)], -1)
+        return x.flatten(-2)
+
+
+class TruncatedExponential(Function):
+    """exp forward, exp(clamp(x,-15,15)) backward (src/models.py:42-53)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.float()
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        x = ctx.saved_tensors[0]
+        return g * torch.exp(torch.clamp(x, min=-15, max=15))
+
+
+truncated_exp: Callable = TruncatedExponential.apply
+
+"""Vanilla NeRF"""
+
+
+class VanillaFeatureMLP(torch.nn.Module):
+    def __init__(self, n_freqs: int, hidden_features: int, hidden_layers: int):
+        super().__init__()
+        in_features = n_freqs * 2 * 3
+        self.encoding = PositionalEncoding(n_freqs=n_freqs)
+        self.net = MLP(in_features, hidden_features, hidden_layers)
+        self.feature_dim = hidden_features
+
+    def forward(self, x):
+        return self.net(self.encoding(x))
+
+
+class VanillaOpacityDecoder(torch.nn.Module):
+    def __init__(self, feature_dim):
+        super().__init__()
+        self.net = MLP(feature_dim, 64, 0, 1)
+        self.activation = lambda x: truncated_exp(x - 1.0)
+
+    def forward(self, features: torch.Tensor) -> torch.Tensor:
+        return self.activation(self.net(features))
+
+
+class VanillaColorDecoder(torch.nn.Module):
+    def __init__(self, n_freqs: int, in_features: int, hidden_features: int, hidden_layers: int):
+        super().__init__()
+        self.pe = PositionalEncoding(n_freqs)
+        total_features = in_features + n_freqs * 2 * 3 + 3
+        self.net = MLP(total_features, hidden_features, hidden_layers, 3)
+        self.activation = torch.nn.Sigmoid()
+
+    def forward(self, features: torch.Tensor, rays_d: torch.Tensor) -> torch.Tensor:
+        x = torch.cat([self.pe(rays_d), rays_d, features], -1)
+        return self.activation(self.net(x))
+
+
+"""K-Planes https://arxiv.org/abs/2301.10241"""
+
+
+def _channels_last_param(shape: Tuple[int, ...], init: Callable) -> torch.nn.Parameter:
+    """Parameter of logical shape [1,C,*spatial] whose memory is channels-last.  `init` runs on a
+    contiguous tensor first so a seeded init gives the same logical values as the reference."""
+    tmp = torch.empty(*shape)
+    init(tmp)
+    perm = (0, *range(2, len(shape)), 1)              # N, spatial..., C
+    inv = (0, len(shape) - 1, *range(1, len(shape) - 1))
+    storage = tmp.permute(*perm).contiguous()         # physically [1, *spatial, C]
+    return torch.nn.Parameter(storage.permute(*inv))  # logical view [1, C, *spatial]
+
+
+def _channels_last_storage(t: torch.Tensor) -> torch.Tensor:
+    """[1,C,*spatial] tensor -> contiguous [*spatial, C] view of the same memory (no copy when the
+    tensor already is channels-last, e.g. a parameter created by _channels_last_param)."""
+    nd = t.dim()
+    v = t.permute(0, *range(2, nd), 1)[0]
+    return v if v.is_contiguous() else None  # type: ignore
+
+
+def _ensure_channels_last_(p: torch.nn.Parameter) -> torch.Tensor:
+    v = _channels_last_storage(p.data)
+    if v is None:  # e.g. after load_state_dict(assign=True) or .to(memory_format=contiguous)
+        nd = p.dim()
+        perm = (0, *range(2, nd), 1)
+        inv = (0, nd - 1, *range(1, nd - 1))
+        p.data = p.data.permute(*perm).contiguous().permute(*inv)
+        v = _channels_last_storage(p.data)
+    return v
+
+
+class KPlanesFeaturePlane(torch.nn.Module):
+    def __init__(self, feature_dim: int = 8, resolution: Tuple[int, int] = (128, 128),
+                 init: Callable = torch.nn.init.uniform_):
+        super().__init__()
+        self.feature_dim = feature_dim
+        self.plane = _channels_last_param((1, feature_dim, *resolution), init)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: (..., 2).  Stand-alone single-plane lookup (src/models.py:105-113); the hot path is
+        KPlanesFeatureField.forward, which fuses all nine planes and never calls this."""
+        new_shape = [*x.size()[:-1], self.feature_dim]
+        output = torch.nn.functional.grid_sample(self.plane, x.view(1, -1, 1, 2), align_corners=True)
+        return output.squeeze().transpose(0, -1).contiguous().view(new_shape)
+
+    def loss_tv(self) -> torch.Tensor:
+        tv_x = torch.nn.functional.mse_loss(self.plane[:, :, 1:, :], self.plane[:, :, :-1, :])
+        tv_y = torch.nn.functional.mse_loss(self.plane[:, :, :, 1:], self.plane[:, :, :, :-1])
+        return tv_x + tv_y
+
+    def loss_l1(self) -> torch.Tensor:
+        return torch.mean(torch.abs(self.plane))
+
+
+class _KPlanesLookup(Function):
+    """features[N, S*C] = cat_s prod_p bilinear(plane[s][p], x[(i_p, j_p)])  via tnf_kplanes_fwd/bwd."""
+
+    @staticmethod
+    def forward(ctx: Any, x: torch.Tensor, channels: int, *planes: torch.Tensor):  # type: ignore
+        lib = _lib.load()
+        _lib.require_cuda(x, "x")
+        n_scales = len(planes) // 3
+        stor = []
+        for p in planes:
+            _lib.require_cuda(p, "plane")
+            v = _channels_last_storage(p)
+            if v is None or p.dtype != torch.float32:
+                raise RuntimeError("K-Planes parameters must be fp32 and channels-last")
+            stor.append(v)
+        res = [int(planes[3 * s].shape[-1]) for s in range(n_scales)]
+        for s in range(n_scales):
+            for p in planes[3 * s:3 * s + 3]:
+                if tuple(p.shape) != (1, channels, res[s], res[s]):
+                    raise RuntimeError("the fused K-Planes lookup needs square planes of one resolution per scale")
+        x2 = x.detach()
+        if x2.dim() != 2 or x2.size(1) != 3 or x2.dtype != torch.float32 or x2.stride(1) != 1:
+            x2 = x2.reshape(-1, 3).float().contiguous()
+        n = x2.size(0)
+        out = torch.empty(n, n_scales * channels, device=x.device)
+        ptrs = (C.c_void_p * len(stor))(*[t.data_ptr() for t in stor])
+        res_arr = (C.c_int32 * n_scales)(*res)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.tnf_kplanes_fwd(ptrs, res_arr, n_scales, channels, x2.data_ptr(),
+                                           x2.stride(0) if n > 0 else 3, n, out.data_ptr(), _lib.stream_ptr()),
+                       "tnf_kplanes_fwd")
+        ctx.save_for_backward(x2, *planes)
+        ctx.channels = channels
+        ctx.res = res
+        ctx.lead_shape = x.shape[:-1]
+        return out.view(*x.shape[:-1], n_scales * channels)
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore
+        lib = _lib.load()
+        x2, *planes = ctx.saved_tensors
+        n_scales = len(planes) // 3
+        channels = ctx.channels
+        n = x2.size(0)
+        grad_out = grad_out.reshape(n, n_scales * channels).contiguous()
+        grads = [torch.zeros_like(p) for p in planes]  # zeros_like preserves the channels-last strides
+        gstor = [_channels_last_storage(g) for g in grads]
+        stor = [_channels_last_storage(p) for p in planes]
+        ptrs = (C.c_void_p * len(stor))(*[t.data_ptr() for t in stor])
+        gptrs = (C.c_void_p * len(gstor))(*[t.data_ptr() for t in gstor])
+        res_arr = (C.c_int32 * n_scales)(*ctx.res)
+        with torch.cuda.device(x2.device):
+            _lib.check(lib.tnf_kplanes_bwd(ptrs, gptrs, res_arr, n_scales, channels, x2.data_ptr(),
+                                           x2.stride(0) if n > 0 else 3, n, grad_out.data_ptr(),
+                                           _lib.stream_ptr()), "tnf_kplanes_bwd")
+        return (None, None, *grads)
+
+
+class KPlanesFeatureField(torch.nn.Module):
+    def __init__(self, feature_dim: int = 32):
+        super().__init__()
+        self.planes = torch.nn.ModuleList([
+            torch.nn.ModuleList([KPlanesFeaturePlane(feature_dim, resolution=(r, r)) for _ in range(3)])
+            for r in (128, 256, 512)
+        ])
+        self.dropout = torch.nn.Dropout(0.0)
+        # pairs of coordinates used by the three planes of a scale, *in that order* (src/models.py:145)
+        self.dimension_pairs = list(itertools.combinations(range(3), 2))
+        self.plane_channels = feature_dim
+        self.feature_dim = 32 * len(self.planes)  # the reference hard-codes 32 here (src/models.py:146)
+        for plane_scale in self.planes:
+            assert isinstance(plane_scale, torch.nn.ModuleList)
+            assert len(plane_scale) == len(self.dimension_pairs)
+
+    def _plane_params(self) -> List[torch.nn.Parameter]:
+        out = []
+        for plane_scale in self.planes:
+            for plane in plane_scale:  # type: ignore
+                _ensure_channels_last_(plane.plane)
+                out.append(plane.plane)
+        return out
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: (..., 3) in [-1,1] -> (..., 3*C) (src/models.py:153-163); one fused kernel."""
+        return self.dropout(_KPlanesLookup.apply(x, self.plane_channels, *self._plane_params()))
+
+    def loss_tv(self) -> torch.Tensor:
+        loss = 0.0
+        count = 0
+        for plane_scale in self.planes:
+            for plane in plane_scale:  # type: ignore
+                loss += plane.loss_tv()
+                count += 1
+        return cast(torch.Tensor, loss) / count
+
+    def loss_l1(self) -> torch.Tensor:
+        loss = 0.0
+        count = 0
+        for plane_scale in self.planes:
+            for plane in plane_scale:  # type: ignore
+                loss += plane.loss_l1()
+                count += 1
+        return cast(torch.Tensor, loss) / count
+
+
+"""CoBaFa https://arxiv.org/abs/2302.01226"""
+
+
+class SawtoothEncoding(torch.nn.Module):
+    def __init__(self, f):
+        super().__init__()
+        self.f = f
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return 2.0 * ((self.f * x) % 1.0) - 1.0  # also normalize to [-1, 1]
+
+
+class CobafaGrid(torch.nn.Module):
+    def __init__(self, res: int | Tuple[int, int, int], feature_dim: int, init: Callable = torch.nn.init.uniform_):
+        super().__init__()
+        resolution = (res, res, res) if isinstance(res, int) else res
+        self.grid = _channels_last_param((1, feature_dim, *resolution), init)
+        self.feature_dim = feature_dim
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: (..., 3).  Stand-alone lookup (src/models.py:228-238); the hot path is the fused
+        CobafaFeatureField.forward."""
+        new_shape = [*x.size()[:-1], self.feature_dim]
+        output = torch.nn.functional.grid_sample(self.grid, x.view(1, -1, 1, 1, 3), align_corners=True)
+        return output.squeeze().transpose(0, -1).contiguous().view(new_shape)
+
+
+class _CobafaLookup(Function):
+    """features[N, sum c_l] = cat_l trilinear(basis_l, saw_l(x)) * trilinear(coef, x)[l]."""
+
+    @staticmethod
+    def _tables(basis, coef, freqs):
+        L = len(basis)
+        res, ch = [], []
+        for b in basis:
+            if b.shape[2] != b.shape[3] or b.shape[3] != b.shape[4]:
+                raise RuntimeError("the fused Cobafa lookup needs cubic basis grids")
+            res.append(int(b.shape[-1]))
+            ch.append(int(b.shape[1]))
+        if coef.shape[1] != L or not (coef.shape[2] == coef.shape[3] == coef.shape[4]):
+            raise RuntimeError("coef grid must be cubic with one channel per level")
+        return ((C.c_int32 * L)(*res), (C.c_int32 * L)(*ch), (C.c_float * L)(*[float(f) for f in freqs]), sum(ch))
+
+    @staticmethod
+    def forward(ctx: Any, x: torch.Tensor, freqs, coef: torch.Tensor, *basis: torch.Tensor):  # type: ignore
+        lib = _lib.load()
+        _lib.require_cuda(x, "x")
+        L = len(basis)
+        res_arr, ch_arr, f_arr, feat = _CobafaLookup._tables(basis, coef, freqs)
+        stor = [_channels_last_storage(b) for b in basis]
+        cst = _channels_last_storage(coef)
+        if cst is None or any(s is None for s in stor):
+            raise RuntimeError("Cobafa parameters must be channels-last")
+        x2 = x.detach()
+        if x2.dim() != 2 or x2.size(1) != 3 or x2.dtype != torch.float32 or x2.stride(1) != 1:
+            x2 = x2.reshape(-1, 3).float().contiguous()
+        n = x2.size(0)
+        out = torch.empty(n, feat, device=x.device)
+        ptrs = (C.c_void_p * L)(*[t.data_ptr() for t in stor])
+        with torch.cuda.device(x.device):
+            _lib.check(lib.tnf_cobafa_fwd(ptrs, res_arr, ch_arr, f_arr, L, cst.data_ptr(), int(coef.shape[-1]),
+                                          x2.data_ptr(), x2.stride(0) if n > 0 else 3, n, out.data_ptr(),
+                                          _lib.stream_ptr()), "tnf_cobafa_fwd")
+        ctx.save_for_backward(x2, coef, *basis)
+        ctx.freqs = list(freqs)
+        return out.view(*x.shape[:-1], feat)
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore
+        lib = _lib.load()
+        x2, coef, *basis = ctx.saved_tensors
+        L = len(basis)
+        res_arr, ch_arr, f_arr, feat = _CobafaLookup._tables(basis, coef, ctx.freqs)
+        n = x2.size(0)
+        grad_out = grad_out.reshape(n, feat).contiguous()
+        gb = [torch.zeros_like(b) for b in basis]
+        gc = torch.zeros_like(coef)
+        ptrs = (C.c_void_p * L)(*[_channels_last_storage(b).data_ptr() for b in basis])
+        gptrs = (C.c_void_p * L)(*[_channels_last_storage(g).data_ptr() for g in gb])
+        with torch.cuda.device(x2.device):
+            _lib.check(lib.tnf_cobafa_bwd(ptrs, gptrs, res_arr, ch_arr, f_arr, L,
+                                          _channels_last_storage(coef).data_ptr(),
+                                          _channels_last_storage(gc).data_ptr(), int(coef.shape[-1]),
+                                          x2.data_ptr(), x2.stride(0) if n > 0 else 3, n, grad_out.data_ptr(),
+                                          _lib.stream_ptr()), "tnf_cobafa_bwd")
+        return (None, None, gc, *gb)
+
+
+class CobafaFeatureField(torch.nn.Module):
+    def __init__(self, basis_res: List[int | Tuple[int, int, int]], coef_res: int | Tuple[int, int, int],
+                 freqs: List[float], channels: List[int], mlp_hidden_dim: int):
+        super().__init__()
+        assert len(basis_res) == len(freqs) == len(channels)
+        L = len(basis_res)
+        self.basis_grids = torch.nn.ModuleList([CobafaGrid(res, c) for res, c in zip(basis_res, channels)])
+        self.encoders = torch.nn.ModuleList([SawtoothEncoding(f) for f in freqs])
+        self.coef_grid = CobafaGrid(coef_res, L)
+        self.dropout = torch.nn.Dropout(0.01)
+        self.mlp = MLP(sum(channels), mlp_hidden_dim, 5)
+        self.feature_dim = mlp_hidden_dim
+
+    def lookup(self, x: torch.Tensor) -> torch.Tensor:
+        """The concatenated basis*coef features [.., sum(channels)] (src/models.py:260-264)."""
+        for g in [self.coef_grid, *self.basis_grids]:
+            _ensure_channels_last_(g.grid)  # type: ignore
+        freqs = [enc.f for enc in self.encoders]  # type: ignore
+        return _CobafaLookup.apply(x, freqs, self.coef_grid.grid, *[g.grid for g in self.basis_grids])  # type: ignore
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: [..., 3] normalized in [-1, 1] (src/models.py:258-266)."""
+        features = self.dropout(self.lookup(x))
+        return self.mlp(features)
