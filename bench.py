@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- ray samples/sec per train step of the packed-ray hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (config.workload = "kplanes_aabb_2e18"): BASELINE config #2 -- K-Planes + vanilla heads on a
+synthetic 800x800 Blender-shaped scene, AABB +-1.5, 128^3 occupancy grid held at a seeded analytic state
+(ball + torus; the cadence update IS executed, then the state is restored so every step sees the same
+occupancy), dynamic batches of 1024-ray chunks x 256 samples -> ~2^18 packed samples per step per GPU.
+One "step" = march+pack -> K-Planes gather -> heads -> weights -> composite -> MSE+TV -> backward -> Adam
+(+ the occupancy update when the reference's cadence says so).  Rays shard across ranks (weak scaling).
+
+value       : packed samples processed by all ranks / max-over-ranks device time, ray store in HBM
+e2e         : same through the public API with the ray store in pinned HOST memory (per-batch host
+              gather + H2D inside the timed region) and the loss read back (D2H) every step
+roofline    : the dominant kernel of ours in the step, CUDA-event timed per launch in the timed region
+cpu_baseline: the oracle's PyTorch-CPU restatement of the same step on this box's host cores (rank 0)
+--impl reference: that CPU path alone, as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "ray samples/sec per train step"
+UNIT = "samples/s"
+N_STORE = 1 << 21          # rays in the synthetic scene store (x36 B = 75 MB; > one epoch of the run)
+BATCH, N_SAMPLES = 1024, 256
+SEED = 1234
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ---- synthetic scene -------------------------------------------------------
+def make_scene(n_rays: int, seed: int):
+    from tinynerf_b200 import synthetic
+    o, d = synthetic.blender_rays(n_rays, seed=seed)
+    # colours of the analytic scene: white background, reddish ball / bluish torus hit test along the ray
+    g = torch.Generator().manual_seed(seed + 1)
+    rgbs = torch.rand(n_rays, 3, generator=g)
+    return o, d, rgbs
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        mx = max((float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- the reference arm / cpu_baseline: the oracle's CPU restatement of the same step -------------
+class CpuReferenceStep:
+    """K-Planes AABB training iteration in the reference's own pure-PyTorch formulation on the host cores
+    (oracle/ref_port.py, weights op = C restatement of src/cuda.cu).  Reported baseline, never shipped."""
+
+    def __init__(self, target_samples: int, seed: int):
+        from oracle import ref_port as rp
+        from tinynerf_b200 import synthetic
+        self.rp = rp
+        torch.manual_seed(seed)
+        self.aabb = torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]])
+        self.planes = [[torch.nn.Parameter(torch.rand(1, 32, r, r)) for _ in range(3)] for r in (128, 256, 512)]
+        lin = lambda i, o: (torch.nn.Parameter(torch.randn(o, i) / math.sqrt(i)), torch.nn.Parameter(torch.zeros(o)))
+        self.sig = [lin(96, 64), lin(64, 1)]
+        self.col = [lin(147, 64), lin(64, 64), lin(64, 64), lin(64, 64), lin(64, 3)]
+        params = [p for s in self.planes for p in s] + [t for l in self.sig + self.col for t in l]
+        self.opt = torch.optim.Adam(params, lr=1e-2, eps=1e-15, weight_decay=1e-5)
+        self.grid = synthetic.analytic_grid(128, seed=SEED + 2)
+        self.thr = min(0.01, self.grid.mean().item())
+        self.o, self.d, self.rgb = make_scene(1 << 16, seed)
+        self.pos, self.target = 0, target_samples
+        self.chunk = max(64, min(BATCH, target_samples // 64))
+
+    def step(self) -> int:
+        rp = self.rp
+        with torch.no_grad():  # dynamic batch accumulator, src/run.py:215-244
+            cur, proj, k, ps, infos, rgbs = 0, 0, 0, [], [], []
+            while proj < self.target:
+                if self.pos + self.chunk > self.o.size(0):
+                    self.pos = 0
+                sl = slice(self.pos, self.pos + self.chunk)
+                self.pos += self.chunk
+                noise = torch.rand(self.chunk, N_SAMPLES)
+                p, info, _ = rp.ray_provider(self.o[sl], self.d[sl], self.grid, self.thr, scene="aabb",
+                                             n_samples=N_SAMPLES, aabb=self.aabb, near=0.1, far=1e5, noise=noise)
+                info[:, 0] += cur
+                ps.append(p); infos.append(info); rgbs.append(self.rgb[sl])
+                cur += p.size(0); k += 1
+                proj = int(cur * (1 + 1 / k))
+            packed, info, rgb = torch.cat(ps), torch.cat(infos), torch.cat(rgbs)
+        out = rp.render(lambda x: rp.kplanes_features(self.planes, x), lambda f: rp.sigma_head(self.sig, f),
+                        lambda f, dd: rp.rgb_head(self.col, 8, f, dd), packed, info, torch.ones(3))
+        loss = torch.nn.functional.mse_loss(out, rgb) + 1e-4 * rp.kplanes_tv(self.planes)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return packed.size(0)
+
+
+def run_cpu(target_samples: int, steps: int, warmup: int):
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = CpuReferenceStep(target_samples, SEED)
+    for _ in range(warmup):
+        ref.step()
+    t0, n = time.perf_counter(), 0
+    for _ in range(steps):
+        n += ref.step()
+    dt = time.perf_counter() - t0
+    return n / dt, dt / steps * 1e3, n
+
+
+# ---- weights microbench (config 5), CUDA events around the launches --------------------------------
+def weights_microbench(dev, logn: int, peak: float):
+    from tinynerf_b200 import _cuda, synthetic
+    n = 1 << logn
+    sig, info, g = synthetic.packed_rays(n, seed=1000 + logn)
+    sig, info, g = sig.to(dev), info.to(dev), g.to(dev)
+    steps = torch.full_like(sig, 5.196 / 256)
+    r = info.size(0)
+    out = {}
+    w = _cuda.weights_fwd(sig, steps, info, 1e-4, _cuda.TRUSTED_PARTITION)
+    for name, fn, nbytes in (("fwd", lambda: _cuda.weights_fwd(sig, steps, info, 1e-4, _cuda.TRUSTED_PARTITION), 12 * n + 8 * r),
+                             ("bwd", lambda: _cuda.weights_bwd(sig, steps, info, w, g, _cuda.TRUSTED_PARTITION), 20 * n + 8 * r)):
+        for _ in range(3):
+            fn()
+        evs = []
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        ms = sorted(s.elapsed_time(e) for s, e in evs)[len(evs) // 2]
+        out[name] = {"us": round(ms * 1e3, 1), "GB/s": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / peak, 3)}
+    out["n_samples"], out["n_rays"] = n, r
+    return out
+
+
+def summarise_profile(records, peak):
+    """records: (name, start, end, bytes) -> per-entry-point totals and the dominant one."""
+    agg = {}
+    for name, s, e, nbytes in records:
+        a = agg.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0})
+        a["ms"] += s.elapsed_time(e)
+        a["launches"] += 1
+        a["bytes"] += nbytes
+    table = {}
+    for name, a in agg.items():
+        gbs = a["bytes"] / a["ms"] / 1e6 if a["ms"] > 0 else 0.0
+        table[name] = {"launches": a["launches"], "avg_us": round(a["ms"] / a["launches"] * 1e3, 2),
+                       "total_ms": round(a["ms"], 3), "alg_MB_per_launch": round(a["bytes"] / a["launches"] / 1e6, 3),
+                       "GB/s": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    dom = max(table, key=lambda k: table[k]["total_ms"]) if table else None
+    return table, dom
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-microbench", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        tgt = 1 << 16
+        v, ms, n = run_cpu(tgt, args.steps, args.warmup)
+        cores = os.cpu_count() or 1
+        sample = f"{args.steps} steps of ~2^16 packed samples each (1/4 of the 2^18 workload per step), torch threads={cores}"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 1), "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": "kplanes_aabb_2e18", "per_step_samples": tgt},
+                          "cpu_baseline": {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": round(v, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch.distributed as dist
+    from tinynerf_b200 import _lib, synthetic
+    from tinynerf_b200.run import RayStore, TrainConfig, Trainer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peak, peak_src = measured_peaks()
+
+    o, d, rgbs = make_scene(N_STORE, SEED)
+    analytic = synthetic.analytic_grid(128, seed=SEED + 2).to(dev)
+    cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=BATCH, n_samples=N_SAMPLES, seed=SEED)
+
+    def make_trainer(host: bool):
+        torch.manual_seed(SEED)
+        store = RayStore(o, d, rgbs, dev, host=host, seed=SEED, rank=rank, world=world)
+        tr = Trainer(cfg, store, dev, rank=rank, world=world)
+        tr.occupancy_grid.grid.copy_(analytic)
+        tr.occupancy_grid.mean = tr.occupancy_grid.grid.mean().item()
+        return tr
+
+    def one_step(tr, read_loss: bool):
+        upd = tr.train_step % tr.occupancy_grid_updates == 0
+        info = tr.step()
+        if upd:  # keep the occupancy state fixed (the update work itself was done inside tr.step())
+            tr.occupancy_grid.grid.copy_(analytic)
+            tr.occupancy_grid.mean = tr.occupancy_grid.grid.mean().item()
+        if read_loss:
+            float(info["loss"])  # D2H of the step's result
+        return info["n_samples"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(tr, steps, read_loss, profile):
+        barrier()
+        l0 = _lib.launch_count
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if profile:
+            _lib.profile_start()
+        s.record()
+        n = 0
+        for _ in range(steps):
+            n += one_step(tr, read_loss)
+        e.record()
+        barrier()
+        recs = _lib.profile_stop() if profile else None
+        ms = s.elapsed_time(e)
+        tot = torch.tensor([float(n), ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            n_all = tot[0].clone(); dist.all_reduce(n_all)
+            ms_all = tot[1].clone(); dist.all_reduce(ms_all, op=dist.ReduceOp.MAX)
+            n, ms = float(n_all), float(ms_all)
+        return n, ms, recs, _lib.launch_count - l0
+
+    # ---- device-resident arm (value) ----
+    tr = make_trainer(host=False)
+    for _ in range(args.warmup):
+        one_step(tr, False)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    n, ms, recs, launches = timed(tr, args.steps, False, profile=True)
+    clk = clocks.stop() if rank == 0 else None
+    value = n / (ms * 1e-3)
+    table, dom = summarise_profile(recs, peak)
+    del tr
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm (host buffers, H2D per batch, loss read back) ----
+    tr = make_trainer(host=True)
+    for _ in range(args.warmup):
+        one_step(tr, True)
+    h0 = tr.store.h2d_bytes
+    n2, ms2, _, _ = timed(tr, args.steps, True, profile=False)
+    e2e = n2 / (ms2 * 1e-3)
+    h2d = (tr.store.h2d_bytes - h0) / args.steps
+    batches_per_step = h2d / (BATCH * 36)
+    d2h = 4 + 8 * batches_per_step  # loss + one packed-sample count per provider call
+    del tr
+    torch.cuda.empty_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    micro = None if args.no_microbench else {f"2^{ln}": weights_microbench(dev, ln, peak) for ln in (22, 26)}
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cms, cn = run_cpu(1 << 18, 2, 1)
+        cpu = {"value": round(v, 1), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"2 full steps (~2^18 packed samples each) after 1 warm-up, {cms:.0f} ms/step, torch threads={os.cpu_count()}"}
+
+    roof = None
+    if dom:
+        t = table[dom]
+        roof = {"kernel": dom, "bound": "hbm", "achieved": t["GB/s"], "peak": peak, "unit": "GB/s", "frac": t["frac"],
+                "traffic": None, "peak_source": peak_src, "avg_us": t["avg_us"],
+                "alg_bytes_per_launch": int(t["alg_MB_per_launch"] * 1e6)}
+    line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "kplanes_aabb_2e18", "rays_per_chunk": BATCH, "samples_per_ray": N_SAMPLES,
+                       "packed_samples_per_step_per_gpu": round(n / args.steps / world), "grid": "128^3 analytic ball+torus",
+                       "l2": "inputs change every step (fresh rays; 396 MB of plane params+grads+Adam state stream through L2 > 126 MB)",
+                       "parallelism": f"ray-sharded dp{world}"},
+            "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": round(ms2 / args.steps, 4)},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": table,
+            "weights_microbench": micro, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+"""a12-a18 parity on the GPU through the C ABI: fused K-Planes / Cobafa lookups (fwd + scatter-add
+bwd), compositing, and the NerfRenderer pipeline, against the reference's golden outputs and the
+PyTorch restatement (same GPU and CPU).  Tolerance: 1e-5 relative fp32 (north_star)."""
+import pytest
+import torch
+
+from oracle import c as orc
+from oracle import ref_port as rp
+from tinynerf_b200 import core, models, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL = 1e-5
+
+
+def close(a, b, rtol=RTOL, atol=1e-7):
+    err = (a.double() - b.double()).abs()
+    tol = rtol * b.double().abs() + atol
+    assert bool((err <= tol).all()), f"worst excess {(err - tol).max().item():.3e}, worst rel {(err / b.double().abs().clamp_min(1e-12)).max().item():.3e}"
+
+
+def nchw_planes(field):
+    return [[p.plane for p in scale] for scale in field.planes]
+
+
+def test_kplanes_matches_reference_golden(golden):
+    g = golden("kplanes")
+    torch.manual_seed(21)
+    field = models.KPlanesFeatureField(32).to(DEV)
+    feats = field(g["x"].to(DEV))
+    close(feats.cpu(), g["features"])
+    (feats * g["grad_out"].to(DEV)).sum().backward()
+    for s in range(3):
+        for p in range(3):
+            gr = field.planes[s][p].plane.grad
+            assert gr.shape == (1, 32, 128 << s, 128 << s)
+            flat = gr.contiguous().reshape(-1).cpu()  # logical NCHW order, as the golden indices
+            close(flat[g[f"gidx_{s}_{p}"]], g[f"gval_{s}_{p}"], atol=1e-6)
+            assert float(gr.double().sum()) == pytest.approx(g[f"gsum_{s}_{p}"], rel=1e-4, abs=1e-4)
+            assert float(gr.double().abs().sum()) == pytest.approx(g[f"gabs_{s}_{p}"], rel=1e-5)
+
+
+@pytest.mark.parametrize("n", [1, 1000, 1 << 18])
+def test_kplanes_vs_torch_on_gpu(n):
+    torch.manual_seed(3)
+    field = models.KPlanesFeatureField(32).to(DEV)
+    gen = torch.Generator().manual_seed(n)
+    packed = torch.rand(n, 7, generator=gen).to(DEV) * 2.1 - 1.05
+    x = packed[:, :3]  # stride-7 view, read in place
+    go = torch.randn(n, 96, generator=gen).to(DEV)
+    feats = field(x)
+    want = rp.kplanes_features(nchw_planes(field), x)
+    close(feats, want)
+    (feats * go).sum().backward()
+    mine = [p.plane.grad.clone() for s in field.planes for p in s]
+    field.zero_grad()
+    (want * go).sum().backward()
+    for a, p in zip(mine, [p for s in field.planes for p in s]):
+        b = p.plane.grad
+        # scatter-add of up to thousands of terms per texel, order differs: tolerance relative to the texel's abs-sum scale
+        scale = b.abs().max()
+        assert (a - b).abs().max() <= 2e-5 * scale
+
+
+def test_cobafa_matches_reference_golden(golden):
+    g = golden("cobafa")
+    torch.manual_seed(31)
+    field = models.CobafaFeatureField(basis_res=[8, 11, 14], coef_res=9, freqs=torch.linspace(2.0, 8.0, 3).tolist(),
+                                      channels=[8, 4, 2], mlp_hidden_dim=32).to(DEV)
+    field.eval()
+    x = g["x"].to(DEV)
+    lookup = field.lookup(x)
+    close(lookup.cpu(), g["lookup"])
+    (lookup * g["grad_out"].to(DEV)).sum().backward()
+    for i, b in enumerate(field.basis_grids):
+        close(b.grid.grad.cpu(), g[f"gbasis_{i}"], atol=1e-6)
+    close(field.coef_grid.grid.grad.cpu(), g["gcoef"], atol=1e-6)
+    close(field(x).cpu(), g["forward_eval"], rtol=1e-4, atol=1e-6)  # through the cuBLAS trunk MLP
+
+
+def test_cobafa_full_size_vs_torch_on_gpu():
+    torch.manual_seed(5)
+    field = models.CobafaFeatureField(basis_res=torch.linspace(32.0, 128, 6).int().tolist(), coef_res=64,
+                                      freqs=torch.linspace(2.0, 8.0, 6).tolist(), channels=[8, 8, 8, 4, 4, 4],
+                                      mlp_hidden_dim=128).to(DEV)
+    n = 1 << 16
+    x = (torch.rand(n, 3, generator=torch.Generator().manual_seed(1)) * 2.1 - 1.05).to(DEV)
+    lookup = field.lookup(x)
+    want = rp.cobafa_lookup([b.grid for b in field.basis_grids], field.coef_grid.grid, [e.f for e in field.encoders], x)
+    close(lookup, want)
+    go = torch.randn_like(lookup)
+    (lookup * go).sum().backward()
+    mine = [b.grid.grad.clone() for b in field.basis_grids] + [field.coef_grid.grid.grad.clone()]
+    field.zero_grad()
+    (want * go).sum().backward()
+    ref = [b.grid.grad for b in field.basis_grids] + [field.coef_grid.grid.grad]
+    for a, b in zip(mine, ref):
+        assert (a - b).abs().max() <= 2e-5 * b.abs().max()
+
+
+def test_composite_vs_oracle():
+    sig, info, g = synthetic.packed_rays(1 << 14, seed=2)
+    n, r = sig.numel(), info.size(0)
+    gen = torch.Generator().manual_seed(4)
+    w = torch.rand(n, generator=gen) * 0.05
+    rgb = torch.rand(n, 3, generator=gen)
+    go = torch.randn(r, 3, generator=gen)
+    for bg in (None, [1.0, 0.5, 0.25]):
+        wd, rd = w.to(DEV).requires_grad_(True), rgb.to(DEV).requires_grad_(True)
+        out = core.Composite.apply(wd, rd, info.to(DEV), bg)
+        close(out.cpu(), orc.composite_fwd(w, rgb, info, bg), atol=1e-6)
+        out.backward(go.to(DEV))
+        gw, grgb = orc.composite_bwd(w, rgb, info, go, bg)
+        close(wd.grad.cpu(), gw, atol=1e-6)
+        close(rd.grad.cpu(), grgb, atol=1e-7)
+
+
+def test_renderer_matches_reference_golden(golden):
+    g = golden("renderer")
+    torch.manual_seed(51)
+    fm = models.VanillaFeatureMLP(4, 32, 1)
+    sd = models.VanillaOpacityDecoder(32)
+    cd = models.VanillaColorDecoder(4, 32, 32, 1)
+    with torch.no_grad():
+        sd.net.net[-1].bias += 5.0
+    renderer = core.NerfRenderer(fm, sd, cd, bg_color=torch.ones(3)).to(DEV)
+    aabb = torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]], device=DEV)
+    marcher = core.RayMarcherAABB(aabb, 48, 0.1)
+    og = core.OccupancyGrid(16, marcher.step_size, 0.01, synthetic.DECAY).to(DEV)
+    og.grid.copy_(g["grid"])
+    og.mean = og.grid.mean().item()
+    prov = core.RayProvider(og, core.ContractionAABB(aabb), marcher)
+    packed, info = prov(g["rays_o"].to(DEV), g["rays_d"].to(DEV), training=False)
+    assert torch.equal(packed.cpu(), g["packed"]) and torch.equal(info.cpu(), g["info"])
+    out = renderer(packed, info)
+    close(out.cpu(), g["rendered"], rtol=1e-4, atol=1e-6)   # through cuBLAS MLPs vs the CPU reference run
+    loss = ((out - 0.25) ** 2).mean()
+    loss.backward()
+    assert float(loss) == pytest.approx(g["loss"], rel=1e-4)
+    close(sd.net.net[0].weight.grad.cpu(), g["grad_sigma_w"], rtol=1e-3, atol=1e-7)
+    close(fm.net.net[0].weight.grad.cpu(), g["grad_feat_w"], rtol=1e-3, atol=1e-7)
+
+
+def test_kplanes_renderer_vs_torch_on_gpu():
+    """Config 2 shape: K-Planes + vanilla heads, AABB, 2^18-sample batch; whole render + backward
+    against the PyTorch restatement on the same GPU (weights via the reference's own kernel)."""
+    torch.manual_seed(0)
+    field = models.KPlanesFeatureField(32)
+    sd = models.VanillaOpacityDecoder(96)
+    cd = models.VanillaColorDecoder(8, 96, 64, 3)
+    with torch.no_grad():
+        sd.net.net[-1].bias += 3.0
+    renderer = core.NerfRenderer(field, sd, cd, bg_color=torch.ones(3)).to(DEV)
+    aabb = torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]], device=DEV)
+    marcher = core.RayMarcherAABB(aabb, 256, 0.1)
+    og = core.OccupancyGrid(128, marcher.step_size, 0.01, synthetic.DECAY).to(DEV)
+    og.grid.copy_(synthetic.analytic_grid(128, seed=1))
+    og.mean = og.grid.mean().item()
+    prov = core.RayProvider(og, core.ContractionAABB(aabb), marcher)
+    o, d = synthetic.blender_rays(4096, seed=2)
+    torch.manual_seed(5)
+    packed, info = prov(o.to(DEV), d.to(DEV), training=True)
+    assert packed.size(0) > 50_000
+    out = renderer(packed, info)
+    s_layers = [(l.weight, l.bias) for l in sd.net.linears()]
+    c_layers = [(l.weight, l.bias) for l in cd.net.linears()]
+    want, aux = rp.render(lambda x: rp.kplanes_features(nchw_planes(field), x), lambda f: rp.sigma_head(s_layers, f),
+                          lambda f, dd: rp.rgb_head(c_layers, 8, f, dd), packed, info, torch.ones(3), return_aux=True)
+    assert (aux["weights"] == 0).any()
+    close(out, want, rtol=1e-5, atol=2e-6)
+    target = torch.rand_like(out)
+    torch.nn.functional.mse_loss(out, target).backward()
+    mine = {k: p.grad.clone() for k, p in renderer.named_parameters()}
+    renderer.zero_grad()
+    torch.nn.functional.mse_loss(want, target).backward()
+    for k, p in renderer.named_parameters():
+        scale = p.grad.abs().max().clamp_min(1e-12)
+        assert (mine[k] - p.grad).abs().max() <= 5e-5 * scale, k

@@ -1,0 +1,183 @@
+"""a1/a2 parity on the GPU, through the C ABI: tnf_weights_fwd/bwd against
+  (1) the UNMODIFIED reference kernel (oracle/_ref/_cuda.so, built from /root/reference/src/cuda.cu),
+  (2) the C restatement (oracle/tnf_oracle.c) on the CPU,
+plus size-independent properties at BASELINE sizes.
+
+Tolerances (north_star: 1e-5 relative fp32):
+  weights : (w > 0) mask bit-identical (exact-termination path); |dw| <= 1e-5 |w_ref|
+  gradients: |dg| <= 1e-5 |g_ref| + 1e-5 * step_k * sum_ray |w_j g_j|   (the reference forms
+             -sum_{j>k} as (prefix - total) in fp32, so its own result carries an absolute error
+             proportional to the ray's sum; relative error of individual small entries is unbounded)
+"""
+import pytest
+import torch
+
+import oracle
+from oracle import c as orc
+from tinynerf_b200 import _cuda, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+STEP = 5.196 / 256
+
+
+def ray_ids(info):
+    return torch.repeat_interleave(torch.arange(info.size(0), device=info.device), info[:, 1].long())
+
+
+def check_weights(w, ref, rtol=1e-5):
+    assert torch.equal(w > 0, ref > 0), f"termination mask differs at {((w > 0) != (ref > 0)).sum().item()} samples"
+    err = (w - ref).abs()
+    bad = err > rtol * ref.abs()
+    assert not bad.any(), f"{bad.sum().item()} weights off; worst rel {(err / ref.abs().clamp_min(1e-30)).max().item():.3e}"
+
+
+def check_grads(gs, ref, steps, w, g, info, rtol=1e-5):
+    ids = ray_ids(info)
+    a = torch.zeros(info.size(0), device=w.device, dtype=torch.float64).index_add_(0, ids, (w * g).abs().double())
+    tol = rtol * ref.abs().double() + rtol * steps.double() * a[ids] + 1e-30
+    err = (gs.double() - ref.double()).abs()
+    assert bool((err <= tol).all()), f"worst grad excess {(err - tol).max().item():.3e}"
+
+
+def make(n, seed, scale=1.0, mean_len=64.0, max_len=1024):
+    sig, info, g = synthetic.packed_rays(n, seed=seed, mean_len=mean_len, max_len=max_len)
+    sig = sig * scale
+    steps = torch.full_like(sig, STEP)
+    return sig, steps, info, g
+
+
+@pytest.fixture(scope="module")
+def ref_cuda():
+    m = oracle.load_ref_cuda()
+    assert m is not None, "oracle/_ref/_cuda.so missing: run python oracle/build_ref.py in the build container"
+    return m
+
+
+@pytest.mark.parametrize("n,scale,thr", [(1 << 12, 8.0, 1e-4), (1 << 18, 1.0, 1e-4), (1 << 18, 8.0, 1e-4),
+                                         (1 << 18, 8.0, 0.0), (1 << 20, 4.0, 1e-4), (1 << 22, 8.0, 1e-4)])
+def test_fwd_bwd_vs_reference_kernel(ref_cuda, n, scale, thr):
+    sig, steps, info, g = [t.to(DEV) for t in make(n, seed=1000 + n.bit_length() - 1, scale=scale)]
+    assert info.size(0) <= (1 << 20)
+    w_ref = ref_cuda.compute_weights_fwd(sig, steps, info, thr)
+    w = _cuda.compute_weights_fwd(sig, steps, info, thr)
+    check_weights(w, w_ref)
+    if thr > 0:
+        assert (w_ref == 0).any(), "termination not exercised"
+    g_ref = ref_cuda.compute_weights_bwd(sig, steps, info, w_ref, g)
+    gs = _cuda.compute_weights_bwd(sig, steps, info, w_ref, g)
+    check_grads(gs, g_ref, steps, w_ref, g, info)
+
+
+@pytest.mark.parametrize("n,thr", [(5000, 1e-4), (1 << 16, 1e-4), (1 << 16, 0.0)])
+def test_fwd_bwd_vs_c_oracle(n, thr):
+    sig, steps, info, g = make(n, seed=7, scale=6.0, mean_len=32, max_len=256)
+    w_ref = orc.weights_fwd(sig, steps, info, thr)
+    w = _cuda.compute_weights_fwd(sig.to(DEV), steps.to(DEV), info.to(DEV), thr).cpu()
+    # the CPU port uses expf, the GPU __expf (<= 2 ulp + |x| 2^-24 apart): termination may flip where T ~ thr
+    flips = (w > 0) != (w_ref > 0)
+    assert flips.sum() <= max(2, n // 20000)
+    ok = ~flips
+    # |dw| <= T |d alpha|: expf vs __expf differ by a few ulp of alpha (<= 1), hence the absolute term
+    assert bool(((w - w_ref).abs()[ok] <= 2e-5 * w_ref.abs()[ok] + 3e-7).all())
+    g_ref = orc.weights_bwd(sig, steps, info, w_ref, g)
+    gs = _cuda.compute_weights_bwd(sig.to(DEV), steps.to(DEV), info.to(DEV), w_ref.to(DEV), g.to(DEV)).cpu()
+    check_grads(gs, g_ref, steps, w_ref, g, info, rtol=2e-5)
+
+
+def test_edge_cases(ref_cuda):
+    # empty input
+    e = torch.empty(0, device=DEV)
+    i0 = torch.zeros(3, 2, dtype=torch.int32, device=DEV)
+    assert _cuda.compute_weights_fwd(e, e, i0, 1e-4).numel() == 0
+    # only empty rays / single-sample rays / one ray longer than any tile / threshold >= 1
+    lens = [0, 1, 0, 0, 5000, 1, 1, 0, 3, 129, 127, 128, 0]
+    start = [sum(lens[:i]) for i in range(len(lens))]
+    info = torch.tensor(list(zip(start, lens)), dtype=torch.int32, device=DEV)
+    n = sum(lens)
+    gen = torch.Generator().manual_seed(5)
+    sig = (torch.rand(n, generator=gen) * 3).to(DEV)
+    steps = (torch.rand(n, generator=gen) * 0.05).to(DEV)
+    g = torch.randn(n, generator=gen).to(DEV)
+    for thr in (1e-4, 0.0, 0.5, 1.0, 2.0):
+        w_ref = ref_cuda.compute_weights_fwd(sig, steps, info, thr)
+        w = _cuda.compute_weights_fwd(sig, steps, info, thr)
+        check_weights(w, w_ref)
+        check_grads(_cuda.compute_weights_bwd(sig, steps, info, w_ref, g),
+                    ref_cuda.compute_weights_bwd(sig, steps, info, w_ref, g), steps, w_ref, g, info)
+    # zero rays: every weight is zero
+    assert torch.equal(_cuda.compute_weights_fwd(sig, steps, info[:0], 1e-4), torch.zeros_like(sig))
+
+
+def test_strided_steps_and_unaligned_views(ref_cuda):
+    sig, steps, info, g = [t.to(DEV) for t in make(1 << 15, seed=11, scale=5.0)]
+    packed = torch.randn(sig.numel(), 7, device=DEV)
+    packed[:, 6] = steps
+    w_ref = ref_cuda.compute_weights_fwd(sig, steps, info, 1e-4)
+    w = _cuda.weights_fwd(sig, packed[:, 6], info, 1e-4)          # stride-7 view, read in place
+    check_weights(w, w_ref)
+    gs = _cuda.weights_bwd(sig, packed[:, 6], info, w_ref, g)
+    check_grads(gs, ref_cuda.compute_weights_bwd(sig, steps, info, w_ref, g), steps, w_ref, g, info)
+    # 4-byte-aligned (not 16) contiguous views take the scalar path
+    big = torch.zeros(sig.numel() + 1, device=DEV)
+    big[1:] = sig
+    w2 = _cuda.compute_weights_fwd(big[1:], steps, info, 1e-4)
+    check_weights(w2, w_ref)
+
+
+def test_info_that_is_not_a_partition(ref_cuda):
+    """Reversed ray order and gaps: the reference handles any non-overlapping info ray by ray and leaves
+    uncovered samples at zero; tnf_weights_* detects it on the device and switches to the ray-serial path."""
+    sig, steps, info, g = [t.to(DEV) for t in make(1 << 14, seed=13, scale=5.0)]
+    perm = torch.randperm(info.size(0), generator=torch.Generator().manual_seed(1)).to(DEV)
+    info_p = info[perm].contiguous()
+    info_p[::7, 1] = (info_p[::7, 1] // 2)  # shorten some rays -> gaps
+    w_ref = ref_cuda.compute_weights_fwd(sig, steps, info_p, 1e-4)
+    w = _cuda.compute_weights_fwd(sig, steps, info_p, 1e-4)
+    assert torch.equal(w, w_ref)  # serial path reproduces the reference bit for bit
+    g_ref = ref_cuda.compute_weights_bwd(sig, steps, info_p, w_ref, g)
+    gs = _cuda.compute_weights_bwd(sig, steps, info_p, w_ref, g)
+    assert torch.allclose(gs, g_ref, rtol=1e-6, atol=1e-9)
+
+
+def test_shim_errors_match_reference():
+    s = torch.ones(4)
+    i = torch.zeros(1, 2, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="sigmas must be a CUDA tensor"):
+        _cuda.compute_weights_fwd(s, s, i, 1e-4)
+    sc = s.to(DEV)
+    with pytest.raises(RuntimeError, match="steps must be contiguous"):
+        _cuda.compute_weights_fwd(sc, torch.ones(8, device=DEV)[::2], i.to(DEV), 1e-4)
+    with pytest.raises(RuntimeError):
+        _cuda.compute_weights_fwd(sc, sc, torch.zeros(1, 3, dtype=torch.int32, device=DEV), 1e-4)
+
+
+@pytest.mark.parametrize("logn", [24, 26])
+def test_properties_at_full_size(logn):
+    """Config-5 sizes (beyond the reference kernel's 2^20-ray validity): size-independent properties.
+    (a) opacity identity: sum_ray w = 1 - T_end for non-terminated rays, checked as sum w <= 1 and
+        sum w + prod a == 1 to fp32 accuracy on a sampled subset; (b) linearity of bwd in grad_weights;
+    (c) rays are independent: re-running a slice of rays alone reproduces the same weights."""
+    n = 1 << logn
+    sig, info, g = synthetic.packed_rays(n, seed=1000 + logn)
+    sig, info, g = sig.to(DEV), info.to(DEV), g.to(DEV)
+    steps = torch.full_like(sig, STEP)
+    w = _cuda.compute_weights_fwd(sig, steps, info, 0.0)
+    ids = ray_ids(info)
+    opac = torch.zeros(info.size(0), device=DEV, dtype=torch.float64).index_add_(0, ids, w.double())
+    tau = torch.zeros(info.size(0), device=DEV, dtype=torch.float64).index_add_(0, ids, (sig * steps).double())
+    assert bool((opac <= 1 + 1e-5).all())
+    assert torch.allclose(opac, 1 - torch.exp(-tau), rtol=0, atol=2e-5)
+    g2 = torch.randn_like(g)
+    b1 = _cuda.compute_weights_bwd(sig, steps, info, w, g)
+    b2 = _cuda.compute_weights_bwd(sig, steps, info, w, g2)
+    b12 = _cuda.compute_weights_bwd(sig, steps, info, w, g + 2 * g2)
+    scale = (b1.abs() + 2 * b2.abs()).max()
+    assert (b12 - (b1 + 2 * b2)).abs().max() <= 1e-4 * scale
+    # slice of rays alone (offsets rebased) -> identical weights (tasks are ray-aligned, no cross-ray state)
+    r0, r1 = info.size(0) // 3, info.size(0) // 3 + 5000
+    s0, s1 = int(info[r0, 0]), int(info[r1, 0])
+    sub = info[r0:r1].clone()
+    sub[:, 0] -= s0
+    w_sub = _cuda.compute_weights_fwd(sig[s0:s1].clone(), steps[s0:s1].clone(), sub, 0.0)
+    assert torch.allclose(w_sub, w[s0:s1], rtol=2e-6, atol=0)

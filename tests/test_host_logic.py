@@ -1,0 +1,62 @@
+"""Host-side mirror of the reference interface (CPU-only checks): module trees / state_dict keys,
+channels-last parameter storage, seeded-init parity, marcher/contraction helpers against goldens."""
+import torch
+
+from tinynerf_b200 import core, models, synthetic
+
+
+def test_state_dict_keys_and_shapes_match_reference_layout():
+    f = models.KPlanesFeatureField(32)
+    keys = list(f.state_dict().keys())
+    assert keys == [f"planes.{s}.{p}.plane" for s in range(3) for p in range(3)]
+    assert [tuple(v.shape) for v in f.state_dict().values()] == [(1, 32, r, r) for r in (128, 256, 512) for _ in range(3)]
+    assert f.feature_dim == 96
+    c = models.CobafaFeatureField(torch.linspace(32.0, 128, 6).int().tolist(), 64, torch.linspace(2.0, 8.0, 6).tolist(),
+                                  [8, 8, 8, 4, 4, 4], 128)
+    k = list(c.state_dict().keys())
+    assert k[:7] == [f"basis_grids.{i}.grid" for i in range(6)] + ["coef_grid.grid"]
+    assert k[7] == "mlp.net.0.weight" and k[-1] == "mlp.net.7.bias"
+    assert sum(p.numel() for p in c.parameters()) == 21_991_356
+    d = models.VanillaColorDecoder(8, 96, 64, 3)
+    assert list(d.state_dict().keys()) == ["pe.freqs", "net.net.0.weight", "net.net.0.bias", "net.net.2.0.weight",
+                                            "net.net.2.0.bias", "net.net.3.0.weight", "net.net.3.0.bias",
+                                            "net.net.4.0.weight", "net.net.4.0.bias", "net.net.5.weight", "net.net.5.bias"]
+
+
+def test_planes_are_channels_last_with_reference_init(golden):
+    g = golden("kplanes")
+    torch.manual_seed(21)
+    f = models.KPlanesFeatureField(32)
+    p = f.planes[1][2].plane
+    assert p.shape == (1, 32, 256, 256) and p.stride() == (256 * 256 * 32, 1, 256 * 32, 32)
+    assert models._channels_last_storage(p).data_ptr() == p.data_ptr()
+    chk = float(sum(q.double().sum() for q in f.parameters()))
+    assert abs(chk - g["param_checksum"]) < 1e-6 * abs(g["param_checksum"])   # same values as the reference's seeded init
+    assert abs(float(f.loss_tv()) - g["tv"]) < 1e-6 * g["tv"] and abs(float(f.loss_l1()) - g["l1"]) < 1e-6 * g["l1"]
+    # round trip through a contiguous state_dict keeps the kernels' layout
+    sd = {k: v.contiguous() for k, v in f.state_dict().items()}
+    f.load_state_dict(sd)
+    assert models._ensure_channels_last_(f.planes[0][0].plane) is not None
+
+
+def test_marchers_and_contractions_match_reference(golden):
+    g = golden("provider_aabb")
+    m = core.RayMarcherAABB(g["aabb"], 64, 0.1)
+    t, s = m(g["rays_o"], g["rays_d"])
+    assert torch.equal(t, g["t_values"]) and torch.equal(s, g["step_sizes"])
+    g = golden("provider_unbounded")
+    m = core.RayMarcherUnbounded(64, 0.1, 1e5, uniform_range=1.7)
+    t, s = m(g["rays_o"], g["rays_d"])
+    assert torch.equal(t.contiguous(), g["t_values"]) and torch.equal(s.contiguous(), g["step_sizes"])
+    pts = torch.randn(100, 3) * 3
+    c, mask = core.ContractionMip360()(pts)
+    assert mask is None and c.abs().max() <= 1.0
+    c, mask = core.ContractionAABB(torch.tensor([[0.0, 0, 0], [2.0, 2, 2]]))(pts)
+    assert bool(((c[mask] >= -1) & (c[mask] <= 1)).all())
+
+
+def test_synthetic_packed_rays_are_a_partition():
+    sig, info, g = synthetic.packed_rays(1 << 14, seed=3)
+    assert int(info[0, 0]) == 0 and int(info[-1, 0] + info[-1, 1]) == 1 << 14
+    assert torch.equal(info[1:, 0], (info[:-1, 0] + info[:-1, 1]))
+    assert (info[:, 1] == 0).float().mean() > 0.05 and int(info[:, 1].max()) <= 1024

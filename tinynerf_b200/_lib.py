@@ -101,6 +101,44 @@ def load():
     return lib
 
 
+# ---- launch accounting / per-kernel timing (used by bench.py; off by default) ---------------------
+KERNELS_PER_CALL = {"tnf_weights_fwd": 1, "tnf_weights_bwd": 1, "tnf_march_count": 2, "tnf_march_pack": 1,
+                    "tnf_occ_query": 1, "tnf_occ_update_coords": 1, "tnf_occ_update_apply": 1, "tnf_kplanes_fwd": 1,
+                    "tnf_kplanes_bwd": 1, "tnf_cobafa_fwd": 1, "tnf_cobafa_bwd": 1, "tnf_composite_fwd": 1,
+                    "tnf_composite_bwd": 1}
+launch_count = 0
+_prof = None
+
+
+def profile_start():
+    """Start recording (name, start event, end event, algorithmic bytes) for every C-ABI call."""
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    global _prof
+    out, _prof = _prof, None
+    return out
+
+
+def call(name: str, *args, nbytes: int = 0, extra_kernels: int = 0):
+    """Invoke a C-ABI entry point on the current stream, raise on error, count its kernel launches and,
+    when profiling is on, bracket it with CUDA events on the launching stream."""
+    global launch_count
+    fn = getattr(load(), name)
+    if _prof is None:
+        rc = fn(*args)
+    else:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        _prof.append((name, s, e, nbytes))
+    check(rc, name)
+    launch_count += KERNELS_PER_CALL.get(name, 1) + extra_kernels
+
+
 def declared_symbols():
     return list(_SIGNATURES)
 

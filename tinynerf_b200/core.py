@@ -174,54 +174,67 @@ class OccupancyGrid(torch.nn.Module):
 
     @torch.no_grad()
     def update(self, sigma_fn: Callable[[torch.Tensor], torch.Tensor], noise: torch.Tensor | None = None):
-        """grid = where(1-exp(-sigma*step) > thr, 1, decay*grid) at jittered cell positions.
+        """grid = where(1-exp(-sigma*step) > thr, 1, decay*grid) at jittered cell positions, then
+        mean = grid.mean() (src/core.py:134-145).
 
         noise: optional [D,H,W,3] U[0,1) tensor (any device) replacing the internally drawn jitter.
         """
-        lib = _lib.load()
+        self.update_slices(sigma_fn, 0, self.grid.size(0), noise)
+        self.mean = self.grid.mean().item()
+
+    @torch.no_grad()
+    def update_slices(self, sigma_fn: Callable[[torch.Tensor], torch.Tensor], z_begin: int, z_end: int,
+                      noise: torch.Tensor | None = None):
+        """The update restricted to depth slices [z_begin, z_end) (a rank's shard); does not touch
+        `mean`.  The threshold used is the one in force when the call starts, as in the reference."""
+        _lib.load()
         _lib.require_cuda(self.grid, "occupancy grid")
         D, H, W = self.grid.shape
         dev = self.device
         per_slice = H * W
         thr, decay, step = _f32(self.threshold), _f32(self.decay), self._step_size_f32()
         spc = max(1, min(int(self.slices_per_call), D))
+        cpu_jitter = noise is None and self.jitter_source == "cpu"
+        if cpu_jitter:  # keep the CPU generator stream aligned with the reference for skipped slices
+            for _ in range(0, z_begin):
+                torch.rand(H, W, 3)
         with torch.cuda.device(dev):
             stream = _lib.stream_ptr()
-            for z0 in range(0, D, spc):
-                z1 = min(D, z0 + spc)
+            for z0 in range(z_begin, z_end, spc):
+                z1 = min(z_end, z0 + spc)
                 n = (z1 - z0) * per_slice
                 if noise is not None:
                     u = noise[z0:z1].reshape(-1, 3).to(dev, torch.float32).contiguous()
-                elif self.jitter_source == "cpu":
+                elif cpu_jitter:
                     # one CPU draw per depth slice, same generator consumption as the reference
                     u = torch.stack([torch.rand(H, W, 3) for _ in range(z0, z1)]).view(-1, 3).to(dev)
                 else:
                     u = None
                 coords = torch.empty(n, 3, device=dev)
-                _lib.check(lib.tnf_occ_update_coords(D, H, W, z0 * per_slice, n, _lib.ptr(u), 0x7E57,
-                                                     self._update_calls * D * per_slice, coords.data_ptr(),
-                                                     stream), "tnf_occ_update_coords")
+                _lib.call("tnf_occ_update_coords", D, H, W, z0 * per_slice, n, _lib.ptr(u), 0x7E57,
+                          self._update_calls * D * per_slice, coords.data_ptr(), stream, nbytes=12 * n)
                 sigma = sigma_fn(coords).reshape(-1).float().contiguous()
                 if sigma.numel() != n:
                     raise RuntimeError(f"sigma_fn returned {sigma.numel()} values for {n} coordinates")
-                _lib.check(lib.tnf_occ_update_apply(self.grid.data_ptr(), z0 * per_slice, n, sigma.data_ptr(),
-                                                    step, thr, decay, stream), "tnf_occ_update_apply")
+                _lib.call("tnf_occ_update_apply", self.grid.data_ptr(), z0 * per_slice, n, sigma.data_ptr(),
+                          step, thr, decay, stream, nbytes=12 * n)
+        if cpu_jitter:
+            for _ in range(z_end, D):
+                torch.rand(H, W, 3)
         self._update_calls += 1
-        self.mean = self.grid.mean().item()
 
     @torch.no_grad()
     def forward(self, coords: torch.Tensor) -> torch.Tensor:
         """coords: [..., 3] in [-1,1] -> bool [...]: trilinear(grid) > threshold (src/core.py:148-156)."""
-        lib = _lib.load()
+        _lib.load()
         _lib.require_cuda(self.grid, "occupancy grid")
         new_shape = coords.shape[:-1]
         flat = coords.reshape(-1, 3).to(self.device, torch.float32).contiguous()
         out = torch.empty(flat.size(0), dtype=torch.bool, device=self.device)
         D, H, W = self.grid.shape
         with torch.cuda.device(self.device):
-            _lib.check(lib.tnf_occ_query(self.grid.data_ptr(), D, H, W, flat.data_ptr(), flat.size(0),
-                                         _f32(self.threshold), out.data_ptr(), None, _lib.stream_ptr()),
-                       "tnf_occ_query")
+            _lib.call("tnf_occ_query", self.grid.data_ptr(), D, H, W, flat.data_ptr(), flat.size(0),
+                      _f32(self.threshold), out.data_ptr(), None, _lib.stream_ptr(), nbytes=13 * flat.size(0))
         return out.view(new_shape)
 
 
@@ -286,7 +299,7 @@ class RayProvider:
         noise: optional [R,S] jitter in [0,1); default in training is torch.rand on the rays' device,
         which consumes torch's CUDA generator exactly like the reference's rand_like (src/core.py:173).
         """
-        lib = _lib.load()
+        _lib.load()
         _lib.require_cuda(rays_o, "rays_o")
         _lib.require_cuda(rays_d, "rays_d")
         dev = rays_o.device
@@ -307,15 +320,15 @@ class RayProvider:
             info = torch.empty(R, 2, dtype=torch.int32, device=dev)
             n_dev = torch.empty(1, dtype=torch.int64, device=dev)
             stream = _lib.stream_ptr()
-            _lib.check(lib.tnf_march_count(C.byref(p), rays_o.data_ptr(), rays_d.data_ptr(), R, info_offset,
-                                           mask_bits.data_ptr(), info.data_ptr(), n_dev.data_ptr(), stream),
-                       "tnf_march_count")
+            _lib.call("tnf_march_count", C.byref(p), rays_o.data_ptr(), rays_d.data_ptr(), R, info_offset,
+                      mask_bits.data_ptr(), info.data_ptr(), n_dev.data_ptr(), stream,
+                      nbytes=24 * R + 8 * R + 4 * R * words)
             n = int(n_dev.item())  # the one host sync of the provider (the reference has two)
             packed = torch.empty(n, 7, device=dev)
             steps = torch.empty(n, device=dev)
-            _lib.check(lib.tnf_march_pack(C.byref(p), rays_o.data_ptr(), rays_d.data_ptr(), R, info_offset,
-                                          mask_bits.data_ptr(), info.data_ptr(), packed.data_ptr(),
-                                          steps.data_ptr(), None, n, stream), "tnf_march_pack")
+            _lib.call("tnf_march_pack", C.byref(p), rays_o.data_ptr(), rays_d.data_ptr(), R, info_offset,
+                      mask_bits.data_ptr(), info.data_ptr(), packed.data_ptr(), steps.data_ptr(), None, n, stream,
+                      nbytes=24 * R + 8 * R + 4 * R * words + 32 * n)
         packed._tnf_steps = steps
         info._tnf_partition = info_offset == 0
         return packed, info
@@ -352,21 +365,21 @@ class Composite(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx: Any, weights: torch.Tensor, rgbs: torch.Tensor, info: torch.Tensor, bg):  # type: ignore
-        lib = _lib.load()
+        _lib.load()
         weights, rgbs, info = weights.contiguous(), rgbs.contiguous(), info.contiguous()
         n, r = weights.size(0), info.size(0)
         out = torch.empty(r, 3, device=weights.device)
         bg_arr = None if bg is None else (C.c_float * 3)(*[float(v) for v in bg])
         with torch.cuda.device(weights.device):
-            _lib.check(lib.tnf_composite_fwd(weights.data_ptr(), rgbs.data_ptr(), info.data_ptr(), n, r, bg_arr,
-                                             out.data_ptr(), None, _lib.stream_ptr()), "tnf_composite_fwd")
+            _lib.call("tnf_composite_fwd", weights.data_ptr(), rgbs.data_ptr(), info.data_ptr(), n, r, bg_arr,
+                      out.data_ptr(), None, _lib.stream_ptr(), nbytes=16 * n + 20 * r)
         ctx.save_for_backward(weights, rgbs, info)
         ctx.bg = bg
         return out
 
     @staticmethod
     def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore
-        lib = _lib.load()
+        _lib.load()
         weights, rgbs, info = ctx.saved_tensors
         grad_out = grad_out.contiguous()
         n, r = weights.size(0), info.size(0)
@@ -375,9 +388,9 @@ class Composite(torch.autograd.Function):
         bg_arr = None if ctx.bg is None else (C.c_float * 3)(*[float(v) for v in ctx.bg])
         if gw is not None or grgb is not None:
             with torch.cuda.device(weights.device):
-                _lib.check(lib.tnf_composite_bwd(weights.data_ptr(), rgbs.data_ptr(), info.data_ptr(), n, r,
-                                                 bg_arr, grad_out.data_ptr(), _lib.ptr(gw), _lib.ptr(grgb),
-                                                 _lib.stream_ptr()), "tnf_composite_bwd")
+                _lib.call("tnf_composite_bwd", weights.data_ptr(), rgbs.data_ptr(), info.data_ptr(), n, r,
+                          bg_arr, grad_out.data_ptr(), _lib.ptr(gw), _lib.ptr(grgb), _lib.stream_ptr(),
+                          nbytes=32 * n + 20 * r)
         return gw, grgb, None, None
 
 

@@ -14,6 +14,7 @@
 // relative.  Any ray that has a sample whose scanned T lies inside that rigorous band around thr is
 // re-evaluated by one lane in the reference's serial order (rare: ~1e-3 of terminating rays), which
 // makes the (weights > 0) mask bit-identical to the reference.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace tnf {
@@ -42,35 +43,37 @@ struct WArgs {
 };
 
 // MODE 0: all arrays contiguous + 16B aligned (float4 path); 1: steps strided, rest aligned; 2: scalar.
+// `p` points at the task's tile origin, `rel` is the tile-relative index of the lane's first sample and
+// `lim` = n_samples - tile0 bounds the reads.
 template <int MODE>
-__device__ __forceinline__ void load_vec(const float* p, long long idx, long long n, float v[4]) {
-  if (MODE != 2 && idx + 3 < n) {
-    float4 t = ld_stream_f4(p + idx);
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, int rel, long long lim, float v[4]) {
+  if (MODE != 2 && rel + 3 < lim) {
+    const float4 t = ld_stream_f4(p + rel);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = (idx + i < n) ? __ldg(p + idx + i) : 0.f;
+    for (int i = 0; i < 4; ++i) v[i] = (rel + i < lim) ? __ldg(p + rel + i) : 0.f;
   }
 }
 template <int MODE>
-__device__ __forceinline__ void load_steps(const float* p, long long stride, long long idx, long long n,
+__device__ __forceinline__ void load_steps(const float* __restrict__ p, long long stride, int rel, long long lim,
                                            float v[4]) {
   if (MODE == 0) {
-    load_vec<0>(p, idx, n, v);
+    load_vec<0>(p, rel, lim, v);
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = (idx + i < n) ? __ldg(p + (idx + i) * stride) : 0.f;
+    for (int i = 0; i < 4; ++i) v[i] = (rel + i < lim) ? __ldg(p + (long long)(rel + i) * stride) : 0.f;
   }
 }
+// store the lane's 4 values, only samples in [lo, hi) (tile-relative) belong to this task
 template <int MODE>
-__device__ __forceinline__ void store_vec(float* p, long long idx, long long lo, long long hi,
-                                          const float v[4]) {
-  if (MODE != 2 && idx >= lo && idx + 3 < hi) {
-    st_stream_f4(p + idx, make_float4(v[0], v[1], v[2], v[3]));
+__device__ __forceinline__ void store_vec(float* p, int rel, int lo, int hi, const float v[4]) {
+  if (MODE != 2 && rel >= lo && rel + 3 < hi) {
+    st_stream_f4(p + rel, make_float4(v[0], v[1], v[2], v[3]));
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (idx + i >= lo && idx + i < hi) p[idx + i] = v[i];
+      if (rel + i >= lo && rel + i < hi) p[rel + i] = v[i];
   }
 }
 
@@ -158,6 +161,8 @@ __device__ __noinline__ void serial_ray_bwd(const float* __restrict__ sig, const
 struct Task {
   long long tile0, s0, s1;
   int r_lo, r_hi;
+  int lo, hi;        // s0 - tile0, s1 - tile0 (tile-relative sample window owned by the task)
+  long long lim;     // n_samples - tile0
   bool valid;
 };
 
@@ -186,6 +191,9 @@ __device__ __forceinline__ Task task_setup(const WArgs& A, int task, unsigned* m
   s1 = s1 < 0 ? 0 : (s1 > N ? N : s1);
   t.s0 = s0;
   t.s1 = s1;
+  t.lo = (int)(s0 - t.tile0);
+  t.hi = (int)(s1 - t.tile0);
+  t.lim = N - t.tile0;
   t.valid = (s0 >= t.tile0) && (s1 > s0) && (t.r_hi > t.r_lo);
   if (!t.valid) return t;
   for (int i = lane; i < (A.tile >> 5); i += 32) mask[i] = 0u;
@@ -219,13 +227,22 @@ __global__ void __launch_bounds__(kWarps * 32) weights_fwd_kernel(const WArgs A)
     if (lane == 0) s_qn[wib] = 0;
     __syncwarp();
 
+    const float* sig = A.sigmas + t.tile0;
+    const float* stp = A.steps + t.tile0 * A.sstride;
+    float* out = A.out + t.tile0;
     float carry = 1.f;  // product since the last ray head, through the end of the previous round
-    for (long long pos = t.tile0 + ((t.s0 - t.tile0) & ~127LL); pos < t.s1; pos += 128) {
-      const long long idx = pos + lane * 4;
-      const int rel = (int)(idx - t.tile0);
-      float s[4], d[4], a[4], T[4], w[4];
-      load_vec<MODE>(A.sigmas, idx, A.n, s);
-      load_steps<MODE>(A.steps, A.sstride, idx, A.n, d);
+    int rpos = t.lo & ~127;
+    float s[4], d[4];
+    load_vec<MODE>(sig, rpos + lane * 4, t.lim, s);
+    load_steps<MODE>(stp, A.sstride, rpos + lane * 4, t.lim, d);
+    for (; rpos < t.hi; rpos += 128) {
+      const int rel = rpos + lane * 4;
+      float sn[4], dn[4];  // software prefetch of the next round: two 512 B requests per warp stay in flight
+      if (rpos + 128 < t.hi) {
+        load_vec<MODE>(sig, rel + 128, t.lim, sn);
+        load_steps<MODE>(stp, A.sstride, rel + 128, t.lim, dn);
+      }
+      float a[4], T[4], w[4];
       const unsigned hb = (rel < A.tile) ? ((mask[rel >> 5] >> (rel & 31)) & 0xFu) : 0u;
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = __expf(-s[i] * d[i]);
@@ -261,29 +278,38 @@ __global__ void __launch_bounds__(kWarps * 32) weights_fwd_kernel(const WArgs A)
         w[i] = alive ? (float)((double)T[i] * (1. - (double)a[i])) : 0.f;
       }
       if (exact) {
+        // Cheap prefilter, warp-uniform band: |T - thr| <= thr * 1.5*2^-23 * (upper bound on the sample's
+        // position in its ray); plus non-monotone (a > 1 / NaN) and underflow cases.
+        const float bub = (float)(rpos + 130 - t.lo) * 1.7881393e-07f;
+        const float blo = thr - thr * bub, bhi = thr + thr * bub;
+        bool sus = !(fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])) <= 1.f);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const long long k = idx + i;
-          if (k < t.s0 || k >= t.s1) continue;
-          // cheap prefilter with an upper bound on the sample's position in its ray
-          const float kub = (float)(k - t.s0 + 2);
-          bool sus = !(a[i] <= 1.f) || (fabsf(T[i] - thr) <= thr * kub * 1.7881393e-07f) ||
-                     (tiny_thr && T[i] < 7.8886091e-31f);
-          if (sus) {
+        for (int i = 0; i < 4; ++i) sus |= (T[i] >= blo) & (T[i] <= bhi);
+        if (tiny_thr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sus |= T[i] < 7.8886091e-31f;
+        }
+        if (sus) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = rel + i;
+            if (k < t.lo || k >= t.hi) continue;
             bool push = !(a[i] <= 1.f) || (tiny_thr && T[i] < 7.8886091e-31f);
-            if (!push) {
-              const int h = find_head_le(mask, rel + i, A.tile);
-              const float krel = (float)(rel + i - h + 1);
-              push = (h < 0) || (fabsf(T[i] - thr) <= thr * krel * 1.7881393e-07f);  // 1.5 * 2^-23
+            if (!push && T[i] >= blo && T[i] <= bhi) {
+              const int h = find_head_le(mask, k, A.tile);
+              const float krel = (float)(k - h + 1);
+              push = (h < 0) || (fabsf(T[i] - thr) <= thr * krel * 1.7881393e-07f);  // 1.5 * 2^-23 per factor
             }
             if (push) {
               const int slot = atomicAdd(&s_qn[wib], 1);
-              if (slot < kQueue) queue[slot] = rel + i;
+              if (slot < kQueue) queue[slot] = k;
             }
           }
         }
       }
-      store_vec<MODE>(A.out, idx, t.s0, t.s1, w);
+      store_vec<MODE>(out, rel, t.lo, t.hi, w);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s[i] = sn[i]; d[i] = dn[i]; }
     }
 
     if (exact) {
@@ -321,94 +347,118 @@ __global__ void __launch_bounds__(kWarps * 32) weights_bwd_kernel(const WArgs A)
     if (!(A.flags & TNF_W_TRUSTED_PARTITION) && *(volatile unsigned*)A.status) return;
     const Task t = task_setup(A, task, mask, lane);
     if (!t.valid) continue;
-    const long long first = t.tile0 + ((t.s0 - t.tile0) & ~127LL);
-    const long long last = t.tile0 + ((t.s1 - 1 - t.tile0) & ~127LL);
+    const float* sig = A.sigmas + t.tile0;
+    const float* stp = A.steps + t.tile0 * A.sstride;
+    const float* wp = A.w + t.tile0;
+    const float* gp = A.g + t.tile0;
+    float* out = A.out + t.tile0;
+    const int first = t.lo & ~127;
+    const int last = (t.hi - 1) & ~127;
 
     // Pass A (descending): S_k = sum_{j>k in ray} w_j*g_j, parked in grad_sigmas.
-    float carry = 0.f;
-    for (long long pos = last; pos >= first; pos -= 128) {
-      const long long idx = pos + lane * 4;
-      const int rel = (int)(idx - t.tile0);
-      float w[4], g[4], c[4], S[4];
-      load_vec<MODE>(A.w, idx, A.n, w);
-      load_vec<MODE>(A.g, idx, A.n, g);
-      const unsigned hb5 = head_bits5(mask, rel, A.tile);
-      unsigned tail = 0u;  // bit i: sample idx+i is the last sample of its ray
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        c[i] = (idx + i < t.s1) ? w[i] * g[i] : 0.f;
-        tail |= ((((hb5 >> (i + 1)) & 1u) | (unsigned)(idx + i + 1 >= t.s1)) << i);
-      }
-      // lane aggregate in descending order: inclusive suffix sum of the lowest sample
-      float P = c[3];
-#pragma unroll
-      for (int i = 2; i >= 0; --i) P = ((tail >> i) & 1u) ? c[i] : P + c[i];
-      int F = tail != 0u;
-      if (lane == 31 && !F) P += carry;
-#pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const float Pu = __shfl_down_sync(kFullMask, P, dlt);
-        const int Fu = __shfl_down_sync(kFullMask, F, dlt);
-        if (lane + dlt < 32) {
-          if (!F) P += Pu;
-          F |= Fu;
+    {
+      float carry = 0.f;
+      float w[4], g[4];
+      load_vec<MODE>(wp, last + lane * 4, t.lim, w);
+      load_vec<MODE>(gp, last + lane * 4, t.lim, g);
+      for (int rpos = last; rpos >= first; rpos -= 128) {
+        const int rel = rpos + lane * 4;
+        float wn[4], gn[4];  // prefetch the next (lower) round
+        if (rpos - 128 >= first) {
+          load_vec<MODE>(wp, rel - 128, t.lim, wn);
+          load_vec<MODE>(gp, rel - 128, t.lim, gn);
         }
-      }
-      float E = __shfl_down_sync(kFullMask, P, 1);  // inclusive suffix sum of sample idx+4
-      if (lane == 31) E = carry;
-      carry = __shfl_sync(kFullMask, P, 0);
-      S[3] = ((tail >> 3) & 1u) ? 0.f : E;
+        float c[4], S[4];
+        const unsigned hb5 = head_bits5(mask, rel, A.tile);
+        unsigned tail = 0u;  // bit i: sample rel+i is the last sample of its ray
 #pragma unroll
-      for (int i = 2; i >= 0; --i) S[i] = ((tail >> i) & 1u) ? 0.f : S[i + 1] + c[i + 1];
-      store_vec<MODE>(A.out, idx, t.s0, t.s1, S);
+        for (int i = 0; i < 4; ++i) {
+          c[i] = (rel + i < t.hi) ? w[i] * g[i] : 0.f;
+          tail |= ((((hb5 >> (i + 1)) & 1u) | (unsigned)(rel + i + 1 >= t.hi)) << i);
+        }
+        // lane aggregate in descending order: inclusive suffix sum of the lane's lowest sample
+        float P = c[3];
+#pragma unroll
+        for (int i = 2; i >= 0; --i) P = ((tail >> i) & 1u) ? c[i] : P + c[i];
+        int F = tail != 0u;
+        if (lane == 31 && !F) P += carry;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const float Pu = __shfl_down_sync(kFullMask, P, dlt);
+          const int Fu = __shfl_down_sync(kFullMask, F, dlt);
+          if (lane + dlt < 32) {
+            if (!F) P += Pu;
+            F |= Fu;
+          }
+        }
+        float E = __shfl_down_sync(kFullMask, P, 1);  // inclusive suffix sum of sample rel+4
+        if (lane == 31) E = carry;
+        carry = __shfl_sync(kFullMask, P, 0);
+        S[3] = ((tail >> 3) & 1u) ? 0.f : E;
+#pragma unroll
+        for (int i = 2; i >= 0; --i) S[i] = ((tail >> i) & 1u) ? 0.f : S[i + 1] + c[i + 1];
+        store_vec<MODE>(out, rel, t.lo, t.hi, S);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { w[i] = wn[i]; g[i] = gn[i]; }
+      }
     }
     __syncwarp();
 
     // Pass B (ascending): T_{k+1} = prod_{j<=k in ray} a_j (no termination, src/cuda.cu:52-56);
     // grad_sigma_k = delta_k * (T_{k+1}*g_k - S_k).  Each lane re-reads the S it stored itself.
-    float carryT = 1.f;
-    for (long long pos = first; pos <= last; pos += 128) {
-      const long long idx = pos + lane * 4;
-      const int rel = (int)(idx - t.tile0);
-      float s[4], d[4], g[4], a[4], S[4], o[4];
-      load_vec<MODE>(A.sigmas, idx, A.n, s);
-      load_steps<MODE>(A.steps, A.sstride, idx, A.n, d);
-      load_vec<MODE>(A.g, idx, A.n, g);
-      if (MODE != 2 && idx >= t.s0 && idx + 3 < t.s1) {
-        const float4 v = *reinterpret_cast<const float4*>(A.out + idx);
-        S[0] = v.x; S[1] = v.y; S[2] = v.z; S[3] = v.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) S[i] = (idx + i >= t.s0 && idx + i < t.s1) ? A.out[idx + i] : 0.f;
-      }
-      const unsigned hb = (rel < A.tile) ? ((mask[rel >> 5] >> (rel & 31)) & 0xFu) : 0u;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = __expf(-s[i] * d[i]);
-      float P = a[0];
-#pragma unroll
-      for (int i = 1; i < 4; ++i) P = ((hb >> i) & 1u) ? a[i] : P * a[i];
-      int F = hb != 0u;
-      if (lane == 0 && !F) P *= carryT;
-#pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const float Pu = __shfl_up_sync(kFullMask, P, dlt);
-        const int Fu = __shfl_up_sync(kFullMask, F, dlt);
-        if (lane >= dlt) {
-          if (!F) P *= Pu;
-          F |= Fu;
+    {
+      float carryT = 1.f;
+      float s[4], d[4], g[4];
+      load_vec<MODE>(sig, first + lane * 4, t.lim, s);
+      load_steps<MODE>(stp, A.sstride, first + lane * 4, t.lim, d);
+      load_vec<MODE>(gp, first + lane * 4, t.lim, g);
+      for (int rpos = first; rpos <= last; rpos += 128) {
+        const int rel = rpos + lane * 4;
+        float sn[4], dn[4], gn[4];
+        if (rpos + 128 <= last) {
+          load_vec<MODE>(sig, rel + 128, t.lim, sn);
+          load_steps<MODE>(stp, A.sstride, rel + 128, t.lim, dn);
+          load_vec<MODE>(gp, rel + 128, t.lim, gn);
         }
-      }
-      float E = __shfl_up_sync(kFullMask, P, 1);
-      if (lane == 0) E = carryT;
-      carryT = __shfl_sync(kFullMask, P, 31);
-      float Tn = ((hb & 1u) ? 1.f : E) * a[0];  // inclusive product T_{k+1}
-      o[0] = d[0] * __fmaf_rn(Tn, g[0], -S[0]);
+        float a[4], S[4], o[4];
+        if (MODE != 2 && rel >= t.lo && rel + 3 < t.hi) {
+          const float4 v = *reinterpret_cast<const float4*>(out + rel);
+          S[0] = v.x; S[1] = v.y; S[2] = v.z; S[3] = v.w;
+        } else {
 #pragma unroll
-      for (int i = 1; i < 4; ++i) {
-        Tn = (((hb >> i) & 1u) ? 1.f : Tn) * a[i];
-        o[i] = d[i] * __fmaf_rn(Tn, g[i], -S[i]);
+          for (int i = 0; i < 4; ++i) S[i] = (rel + i >= t.lo && rel + i < t.hi) ? out[rel + i] : 0.f;
+        }
+        const unsigned hb = (rel < A.tile) ? ((mask[rel >> 5] >> (rel & 31)) & 0xFu) : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = __expf(-s[i] * d[i]);
+        float P = a[0];
+#pragma unroll
+        for (int i = 1; i < 4; ++i) P = ((hb >> i) & 1u) ? a[i] : P * a[i];
+        int F = hb != 0u;
+        if (lane == 0 && !F) P *= carryT;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const float Pu = __shfl_up_sync(kFullMask, P, dlt);
+          const int Fu = __shfl_up_sync(kFullMask, F, dlt);
+          if (lane >= dlt) {
+            if (!F) P *= Pu;
+            F |= Fu;
+          }
+        }
+        float E = __shfl_up_sync(kFullMask, P, 1);
+        if (lane == 0) E = carryT;
+        carryT = __shfl_sync(kFullMask, P, 31);
+        float Tn = ((hb & 1u) ? 1.f : E) * a[0];  // inclusive product T_{k+1}
+        o[0] = d[0] * __fmaf_rn(Tn, g[0], -S[0]);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+          Tn = (((hb >> i) & 1u) ? 1.f : Tn) * a[i];
+          o[i] = d[i] * __fmaf_rn(Tn, g[i], -S[i]);
+        }
+        store_vec<MODE>(out, rel, t.lo, t.hi, o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s[i] = sn[i]; d[i] = dn[i]; g[i] = gn[i]; }
       }
-      store_vec<MODE>(A.out, idx, t.s0, t.s1, o);
     }
     __syncwarp();
   }
@@ -450,11 +500,16 @@ __global__ void fallback_bwd_kernel(const WArgs A) {
 }
 
 int pick_tile(long long n) {
-  // enough tasks to give every SM ~32 resident warps, tiles between 256 and 2048 samples
-  const long long want = (long long)sm_count() * 32;
+  // enough tasks to give every SM several waves of resident warps; tiles between 256 and kMaxTile samples
+  static const int forced = [] {
+    const char* e = getenv("TNF_W_TILE");  // tuning knob (multiple of 128, <= 2048)
+    return e ? atoi(e) : 0;
+  }();
+  if (forced >= 128 && forced <= kMaxTile && forced % 128 == 0) return forced;
+  const long long want = (long long)sm_count() * 40 * 4;
   long long tile = (n / want) & ~127LL;
   if (tile < 256) tile = 256;
-  if (tile > kMaxTile) tile = kMaxTile;
+  if (tile > 1024) tile = 1024;
   return (int)tile;
 }
 
@@ -470,9 +525,7 @@ int launch(bool bwd, WArgs A, cudaStream_t st) {
   bool al = aligned16(A.sigmas) && aligned16(A.out);
   if (bwd) al = al && aligned16(A.w) && aligned16(A.g);
   const int mode = !al ? 2 : ((A.sstride == 1 && aligned16(A.steps)) ? 0 : 1);
-  const long long max_ctas = (long long)sm_count() * 8;  // 64 warps/SM resident at most
-  long long ctas = ceil_div(n_tasks, kWarps);
-  if (ctas > max_ctas) ctas = max_ctas;
+  const long long ctas = ceil_div(n_tasks, kWarps);  // one task per warp; the block scheduler balances
   const dim3 grid((unsigned)ctas), block(kWarps * 32);
   if (!bwd) {
     if (mode == 0) weights_fwd_kernel<0><<<grid, block, 0, st>>>(A);

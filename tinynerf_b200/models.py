@@ -173,7 +173,7 @@ class _KPlanesLookup(Function):
 
     @staticmethod
     def forward(ctx: Any, x: torch.Tensor, channels: int, *planes: torch.Tensor):  # type: ignore
-        lib = _lib.load()
+        _lib.load()
         _lib.require_cuda(x, "x")
         n_scales = len(planes) // 3
         stor = []
@@ -196,9 +196,10 @@ class _KPlanesLookup(Function):
         ptrs = (C.c_void_p * len(stor))(*[t.data_ptr() for t in stor])
         res_arr = (C.c_int32 * n_scales)(*res)
         with torch.cuda.device(x.device):
-            _lib.check(lib.tnf_kplanes_fwd(ptrs, res_arr, n_scales, channels, x2.data_ptr(),
-                                           x2.stride(0) if n > 0 else 3, n, out.data_ptr(), _lib.stream_ptr()),
-                       "tnf_kplanes_fwd")
+            pbytes = sum(t.numel() for t in stor) * 4
+            _lib.call("tnf_kplanes_fwd", ptrs, res_arr, n_scales, channels, x2.data_ptr(),
+                      x2.stride(0) if n > 0 else 3, n, out.data_ptr(), _lib.stream_ptr(),
+                      nbytes=n * (12 + 4 * n_scales * channels) + pbytes)
         ctx.save_for_backward(x2, *planes)
         ctx.channels = channels
         ctx.res = res
@@ -207,7 +208,7 @@ class _KPlanesLookup(Function):
 
     @staticmethod
     def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore
-        lib = _lib.load()
+        _lib.load()
         x2, *planes = ctx.saved_tensors
         n_scales = len(planes) // 3
         channels = ctx.channels
@@ -220,9 +221,10 @@ class _KPlanesLookup(Function):
         gptrs = (C.c_void_p * len(gstor))(*[t.data_ptr() for t in gstor])
         res_arr = (C.c_int32 * n_scales)(*ctx.res)
         with torch.cuda.device(x2.device):
-            _lib.check(lib.tnf_kplanes_bwd(ptrs, gptrs, res_arr, n_scales, channels, x2.data_ptr(),
-                                           x2.stride(0) if n > 0 else 3, n, grad_out.data_ptr(),
-                                           _lib.stream_ptr()), "tnf_kplanes_bwd")
+            pbytes = sum(t.numel() for t in stor) * 4
+            _lib.call("tnf_kplanes_bwd", ptrs, gptrs, res_arr, n_scales, channels, x2.data_ptr(),
+                      x2.stride(0) if n > 0 else 3, n, grad_out.data_ptr(), _lib.stream_ptr(),
+                      nbytes=n * (12 + 4 * n_scales * channels) + 2 * pbytes)
         return (None, None, *grads)
 
 
@@ -318,7 +320,7 @@ class _CobafaLookup(Function):
 
     @staticmethod
     def forward(ctx: Any, x: torch.Tensor, freqs, coef: torch.Tensor, *basis: torch.Tensor):  # type: ignore
-        lib = _lib.load()
+        _lib.load()
         _lib.require_cuda(x, "x")
         L = len(basis)
         res_arr, ch_arr, f_arr, feat = _CobafaLookup._tables(basis, coef, freqs)
@@ -333,16 +335,17 @@ class _CobafaLookup(Function):
         out = torch.empty(n, feat, device=x.device)
         ptrs = (C.c_void_p * L)(*[t.data_ptr() for t in stor])
         with torch.cuda.device(x.device):
-            _lib.check(lib.tnf_cobafa_fwd(ptrs, res_arr, ch_arr, f_arr, L, cst.data_ptr(), int(coef.shape[-1]),
-                                          x2.data_ptr(), x2.stride(0) if n > 0 else 3, n, out.data_ptr(),
-                                          _lib.stream_ptr()), "tnf_cobafa_fwd")
+            pbytes = (sum(t.numel() for t in stor) + cst.numel()) * 4
+            _lib.call("tnf_cobafa_fwd", ptrs, res_arr, ch_arr, f_arr, L, cst.data_ptr(), int(coef.shape[-1]),
+                      x2.data_ptr(), x2.stride(0) if n > 0 else 3, n, out.data_ptr(), _lib.stream_ptr(),
+                      nbytes=n * (12 + 4 * feat) + pbytes)
         ctx.save_for_backward(x2, coef, *basis)
         ctx.freqs = list(freqs)
         return out.view(*x.shape[:-1], feat)
 
     @staticmethod
     def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore
-        lib = _lib.load()
+        _lib.load()
         x2, coef, *basis = ctx.saved_tensors
         L = len(basis)
         res_arr, ch_arr, f_arr, feat = _CobafaLookup._tables(basis, coef, ctx.freqs)
@@ -353,11 +356,11 @@ class _CobafaLookup(Function):
         ptrs = (C.c_void_p * L)(*[_channels_last_storage(b).data_ptr() for b in basis])
         gptrs = (C.c_void_p * L)(*[_channels_last_storage(g).data_ptr() for g in gb])
         with torch.cuda.device(x2.device):
-            _lib.check(lib.tnf_cobafa_bwd(ptrs, gptrs, res_arr, ch_arr, f_arr, L,
-                                          _channels_last_storage(coef).data_ptr(),
-                                          _channels_last_storage(gc).data_ptr(), int(coef.shape[-1]),
-                                          x2.data_ptr(), x2.stride(0) if n > 0 else 3, n, grad_out.data_ptr(),
-                                          _lib.stream_ptr()), "tnf_cobafa_bwd")
+            pbytes = (sum(b.numel() for b in basis) + coef.numel()) * 4
+            _lib.call("tnf_cobafa_bwd", ptrs, gptrs, res_arr, ch_arr, f_arr, L,
+                      _channels_last_storage(coef).data_ptr(), _channels_last_storage(gc).data_ptr(),
+                      int(coef.shape[-1]), x2.data_ptr(), x2.stride(0) if n > 0 else 3, n, grad_out.data_ptr(),
+                      _lib.stream_ptr(), nbytes=n * (12 + 4 * feat) + 2 * pbytes)
         return (None, None, gc, *gb)
 
 

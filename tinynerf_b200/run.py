@@ -1,0 +1,209 @@
+"""Thin host-side caller of the hot path: the training iteration of the reference's loop
+(src/run.py:213-261) and its chunked render (src/run.py:15-50), one process per GPU.
+
+What is kept from the reference: model/marcher/grid/optimiser construction and constants
+(src/run.py:100-201), the dynamic-batch accumulator (:215-244), the occupancy-update cadence
+(:248-249), loss + TV regulariser (:252-256) and the un-unscaled GradScaler quirk (:259-260: the loss
+is multiplied by 2**10 and never unscaled, so Adam sees gradients x1024).
+
+What is new: rays shard across ranks, every rank accumulates its own ~batch*S packed
+samples, the MSE is normalised by the GLOBAL ray count, gradients are summed with NCCL all-reduce, and
+the occupancy update is sharded by depth slices and reconciled with an all-gather.  Data parsing, eval
+metrics, image writing and the CLI are out of scope (callers own them).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .core import (ContractionAABB, ContractionMip360, NerfRenderer, OccupancyGrid, RayMarcherAABB,
+                   RayMarcherUnbounded, RayProvider)
+from .models import (CobafaFeatureField, KPlanesFeatureField, VanillaColorDecoder, VanillaFeatureMLP,
+                     VanillaOpacityDecoder)
+
+
+class RayStore:
+    """Rays + colours of a scene, shuffled per epoch like DataLoader(shuffle=True) (src/run.py:116-122).
+    Lives on `device` (HBM-resident, no per-batch H2D) or in pinned host memory (`host=True`), in which
+    case every batch is gathered on the host and copied H2D, as in the reference (src/run.py:226-228).
+    With world_size > 1 each rank walks a disjoint 1/world slice of the same seeded permutation."""
+
+    def __init__(self, rays_o: torch.Tensor, rays_d: torch.Tensor, rgbs: torch.Tensor, device, host: bool = False,
+                 seed: int = 0, rank: int = 0, world: int = 1):
+        self.device, self.host, self.rank, self.world = torch.device(device), host, rank, world
+        data = torch.cat([rays_o, rays_d, rgbs], -1).float().contiguous()  # [n, 9]
+        self.data = data.pin_memory() if host else data.to(self.device)
+        self.n = data.size(0)
+        self.gen = torch.Generator(device="cpu" if host else self.device)
+        self.gen.manual_seed(seed)
+        self.h2d_bytes = 0
+        self._perm = None
+        self._pos = 0
+        self._stage = None
+
+    def _reshuffle(self):
+        perm = torch.randperm(self.n, generator=self.gen, device=self.gen.device)
+        self._perm = perm[self.rank::self.world]
+        self._pos = 0
+
+    def next(self, batch: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        if self._perm is None or self._pos + batch > self._perm.numel():
+            self._reshuffle()
+        idx = self._perm[self._pos:self._pos + batch]
+        self._pos += batch
+        if self.host:
+            if self._stage is None or self._stage.size(0) != batch:
+                self._stage = torch.empty(batch, 9).pin_memory()
+            torch.index_select(self.data, 0, idx, out=self._stage)
+            rows = self._stage.to(self.device, non_blocking=True)
+            self.h2d_bytes += rows.numel() * 4
+        else:
+            rows = self.data.index_select(0, idx)
+        return rows[:, 0:3], rows[:, 3:6], rows[:, 6:9]
+
+
+@dataclass
+class TrainConfig:
+    """The hot-path subset of the reference's TrainConfig (src/run.py:83-94) + scene description."""
+    method: str = "kplanes"             # vanilla | kplanes | cobafa
+    scene_type: str = "aabb"            # aabb | unbounded
+    batch_size: int = 1024
+    n_samples: int = 256
+    scene_scale: float = 1.0            # RaysDataset.scene_scale (unbounded marcher range)
+    bg_color: Tuple[float, float, float] | None = (1.0, 1.0, 1.0)
+    grad_scale: float = 2.0 ** 10       # GradScaler(2**10) that is never unscaled (src/run.py:201,259)
+    occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
+    seed: int = 0
+
+
+class Trainer:
+    def __init__(self, cfg: TrainConfig, store: RayStore, device, rank: int = 0, world: int = 1):
+        self.cfg, self.store, self.device, self.rank, self.world = cfg, store, torch.device(device), rank, world
+        bs_ratio = 4096 / cfg.batch_size
+        self.steps = int(2048 * bs_ratio)
+        self.occupancy_grid_updates = int(16 * bs_ratio)
+        thr, res = 0.01, 128
+        decay = thr ** (1 / 16)
+        dev = self.device
+        if cfg.method == "vanilla":
+            feature_module = VanillaFeatureMLP(10, 256, 8)
+        elif cfg.method == "kplanes":
+            feature_module = KPlanesFeatureField(32)
+        elif cfg.method == "cobafa":
+            feature_module = CobafaFeatureField(basis_res=torch.linspace(32.0, 128, 6).int().tolist(), coef_res=64,
+                                                freqs=torch.linspace(2.0, 8.0, 6).tolist(), channels=[8, 8, 8, 4, 4, 4],
+                                                mlp_hidden_dim=128)
+        else:
+            raise NotImplementedError(f"Unknown method {cfg.method}.")
+        dim = feature_module.feature_dim
+        sigma_decoder = VanillaOpacityDecoder(dim)
+        rgb_decoder = VanillaColorDecoder(8, dim, 64, 3)
+        if cfg.scene_type == "unbounded":
+            self.ray_marcher = RayMarcherUnbounded(cfg.n_samples, 0.1, 1e5, uniform_range=cfg.scene_scale)
+            contraction = ContractionMip360(order=float("inf"))
+        elif cfg.scene_type == "aabb":
+            aabb = torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]]).to(dev)
+            self.ray_marcher = RayMarcherAABB(aabb, cfg.n_samples, 0.1)
+            contraction = ContractionAABB(aabb)
+        else:
+            raise NotImplementedError(f"Unknown scene type {cfg.scene_type}.")
+        self.occupancy_grid = OccupancyGrid(size=res, step_size=self.ray_marcher.step_size, threshold=thr,
+                                            decay=decay).to(dev)
+        self.occupancy_grid.jitter_source = cfg.occupancy_jitter
+        self.ray_provider = RayProvider(self.occupancy_grid, contraction, self.ray_marcher)
+        bg = None if cfg.bg_color is None else torch.tensor(cfg.bg_color)
+        self.renderer = NerfRenderer(feature_module, sigma_decoder, rgb_decoder, bg_color=bg).to(dev)
+        if world > 1:  # identical replicas: broadcast rank 0's initial parameters
+            for p in self.renderer.parameters():
+                dist.broadcast(p.data, 0)
+        self.optimizer = torch.optim.Adam(self.renderer.parameters(), lr=1e-2, eps=1e-15, weight_decay=1e-5)
+        s = self.steps
+        self.scheduler = torch.optim.lr_scheduler.MultiStepLR(
+            self.optimizer, milestones=[s // 2, s * 3 // 4, s * 5 // 6, s * 9 // 10], gamma=0.33)
+        self.tv_reg_alpha, self.l1_reg_alpha = 0.0001, 0.0
+        self.train_step = 0
+        self.last: Dict[str, float] = {}
+
+    # ---- a11: dynamic batch accumulator (src/run.py:215-244) -----------------------------------
+    @torch.no_grad()
+    def next_batch(self):
+        target = self.cfg.batch_size * self.cfg.n_samples
+        current, projected, k = 0, 0, 0
+        acc_s, acc_i, acc_rgb, acc_steps = [], [], [], []
+        while projected < target:
+            rays_o, rays_d, rgbs = self.store.next(self.cfg.batch_size)
+            samples, info = self.ray_provider(rays_o, rays_d, training=True, info_offset=current)
+            acc_s.append(samples)
+            acc_steps.append(samples._tnf_steps)
+            acc_i.append(info)
+            acc_rgb.append(rgbs)
+            current += samples.size(0)
+            k += 1
+            projected = int(current * (1 + 1 / k))
+            if k > 4096:
+                raise RuntimeError("occupancy grid rejects every sample: cannot fill a batch")
+        packed = torch.cat(acc_s, 0)
+        packed._tnf_steps = torch.cat(acc_steps, 0)
+        info = torch.cat(acc_i, 0)
+        info._tnf_partition = True  # consecutive batches were packed at consecutive offsets
+        return packed, torch.cat(acc_rgb, 0), info
+
+    # ---- occupancy update, sharded by depth slice across ranks ----------------------------------
+    @torch.no_grad()
+    def update_occupancy(self):
+        og = self.occupancy_grid
+        sigma_fn = lambda t: self.renderer.sigma_decoder(self.renderer.feature_module(t))
+        if self.world == 1:
+            og.update(sigma_fn)
+            return
+        D = og.grid.size(0)
+        assert D % self.world == 0, "depth slices must divide the number of ranks"
+        per = D // self.world
+        z0 = self.rank * per
+        og.update_slices(sigma_fn, z0, z0 + per)
+        dist.all_gather_into_tensor(og.grid.view(-1), og.grid[z0:z0 + per].reshape(-1).clone())
+        og.mean = og.grid.mean().item()
+
+    # ---- one training iteration (src/run.py:246-261) -------------------------------------------
+    def step(self) -> Dict[str, float]:
+        packed, rgbs, info = self.next_batch()
+        self.renderer.train()
+        if self.train_step % self.occupancy_grid_updates == 0:
+            self.update_occupancy()
+        rendered = self.renderer(packed, info)
+        n_rays = torch.tensor([float(info.size(0))], device=self.device)
+        if self.world > 1:
+            dist.all_reduce(n_rays)
+        # MSE over the union batch: local sum of squares / (global rays * 3)
+        loss = ((rendered - rgbs) ** 2).sum() / (n_rays[0] * 3.0)
+        if self.cfg.method == "kplanes":
+            reg = self.renderer.feature_module.loss_tv() * self.tv_reg_alpha  # type: ignore
+            reg = reg + self.renderer.feature_module.loss_l1() * self.l1_reg_alpha  # type: ignore
+            loss = loss + reg / self.world  # summed over ranks it counts once
+        self.optimizer.zero_grad()
+        (loss * self.cfg.grad_scale).backward()
+        if self.world > 1:
+            for p in self.renderer.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+        self.optimizer.step()
+        self.scheduler.step()
+        self.train_step += 1
+        self.last = {"loss": loss.detach(), "n_samples": packed.size(0), "n_rays": info.size(0)}
+        return self.last
+
+    # ---- render half of the path (src/run.py:15-50, without image IO) ---------------------------
+    @torch.no_grad()
+    def render(self, rays_o: torch.Tensor, rays_d: torch.Tensor, batch_size: int = 2048) -> torch.Tensor:
+        self.renderer.eval()
+        out = []
+        for k in range(0, rays_o.size(0), batch_size):
+            o = rays_o[k:k + batch_size].to(self.device)
+            d = rays_d[k:k + batch_size].to(self.device)
+            samples, info = self.ray_provider(o, d, training=False)
+            out.append(self.renderer(samples, info))
+        return torch.cat(out, 0)

@@ -61,15 +61,18 @@ def blender_rays(n_rays: int, seed: int, radius: float = 4.0311, res: int = 800,
 
 
 def analytic_grid(res: int, seed: int, device="cpu") -> torch.Tensor:
-    """Occupancy grid state for the synthetic scene: cells inside a ball (r=0.5) or a torus are 1,
-    the rest decay^k with k ~ U{1..24} (so a fraction stays above the 0.01 threshold)."""
+    """Occupancy grid state of a trained scene: cells inside a ball (r=0.5) or a torus are 1, 4% of the
+    other cells are "floaters" at decay^k, k ~ U{1..15} (above the 0.01 threshold), the rest have decayed
+    below it (k ~ U{16..40}); about 10% of the cells are occupied."""
     g = torch.Generator().manual_seed(seed)
     ax = (torch.arange(res, dtype=torch.float32) + 0.5) / res * 3.0 - 1.5  # world coords of the aabb [-1.5,1.5]
     z, y, x = torch.meshgrid(ax, ax, ax, indexing="ij")
     ball = (x ** 2 + y ** 2 + z ** 2) < 0.5 ** 2
     torus = ((torch.sqrt(x ** 2 + y ** 2) - 0.9) ** 2 + z ** 2) < 0.25 ** 2
-    k = torch.randint(1, 25, (res, res, res), generator=g).float()
-    grid = torch.tensor(DECAY, dtype=torch.float32) ** k
+    floater = torch.rand(res, res, res, generator=g) < 0.04
+    k_lo = torch.randint(1, 16, (res, res, res), generator=g).float()
+    k_hi = torch.randint(16, 41, (res, res, res), generator=g).float()
+    grid = torch.tensor(DECAY, dtype=torch.float32) ** torch.where(floater, k_lo, k_hi)
     grid[ball | torus] = 1.0
     return grid.to(device)
 
