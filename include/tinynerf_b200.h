@@ -146,6 +146,30 @@ int tnf_kplanes_bwd(const float* const* planes, float* const* grad_planes, const
                     int32_t n_scales, int32_t channels, const float* x, int64_t x_stride, int64_t n,
                     const float* grad_out, void* stream);
 
+/* ---- a13: K-Planes total-variation regulariser ---------------------------------------------------
+ * Replaces KPlanesFeaturePlane.loss_tv / KPlanesFeatureField.loss_tv (src/models.py:115-118,165-172)
+ * and their autograd backward for a table of n_planes channels-last planes [res][res][C].
+ * fwd : sums[2*i+0] = sum (p[h+1,w]-p[h,w])^2, sums[2*i+1] = sum (p[h,w+1]-p[h,w])^2  (device doubles;
+ *       loss_tv(plane i) = sums[2i]/(C*(res-1)*res) + sums[2i+1]/(C*res*(res-1)))
+ * bwd : grads[i] (=|+=) plane_weight[i] * (*gscale) * d loss_tv(plane i)/d plane; gscale is a DEVICE
+ *       scalar (the upstream gradient), plane_weight a [host] array (NULL = 1), e.g. 1/9 for the field mean.
+ */
+int tnf_tv_fwd(const float* const* planes /*[host]*/, const int32_t* res /*[host]*/, int32_t n_planes,
+               int32_t channels, double* sums, void* stream);
+int tnf_tv_bwd(const float* const* planes, float* const* grads, const int32_t* res, int32_t n_planes,
+               int32_t channels, const float* plane_weight /*[host]*/, const float* gscale, int32_t accumulate,
+               void* stream);
+
+/* ---- Adam step over a table of tensors ------------------------------------------
+ * Replaces torch.optim.Adam.step as configured at src/run.py:186 (L2 weight decay folded into the
+ * gradient, bias correction, no amsgrad) for n_tensors flat fp32 tensors in one launch:
+ *   g += wd*p; m = lerp(m, g, 1-b1); v = b2*v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * All tables are [host] arrays of device pointers; `step` is the 1-based step count t.
+ */
+int tnf_adam_step(float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const int64_t* numel, int32_t n_tensors, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
 /* ---- a14: Cobafa fused basis/coefficient lookup ----------------------------------------------
  * Replaces CobafaFeatureField.forward up to the concat (src/models.py:258-264): coef = trilinear
  * (coef_grid, x); y_l = trilinear(basis_l, 2*((f_l*x) mod 1)-1) * coef[l]; out = cat_l y_l.

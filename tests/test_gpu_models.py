@@ -176,3 +176,46 @@ def test_kplanes_renderer_vs_torch_on_gpu():
     for k, p in renderer.named_parameters():
         scale = p.grad.abs().max().clamp_min(1e-12)
         assert (mine[k] - p.grad).abs().max() <= 5e-5 * scale, k
+
+
+def test_tv_regulariser_vs_reference_formula(golden):
+    """a13: fused TV kernel (fwd value + gradients) against the reference's slicing/mse_loss formula."""
+    g = golden("kplanes")
+    torch.manual_seed(21)
+    field = models.KPlanesFeatureField(32).to(DEV)
+    tv = field.loss_tv()
+    assert float(tv) == pytest.approx(g["tv"], rel=1e-5)
+    (tv * 3.0).backward()
+    mine = [p.plane.grad.clone() for s in field.planes for p in s]
+    field.zero_grad()
+    want = rp.kplanes_tv(nchw_planes(field))
+    assert float(tv) == pytest.approx(float(want), rel=1e-6)
+    (want * 3.0).backward()
+    for a, p in zip(mine, [p for s in field.planes for p in s]):
+        close(a, p.plane.grad, rtol=1e-5, atol=1e-6 * float(p.plane.grad.abs().max()))
+    single = field.planes[1][0]
+    assert float(single.loss_tv()) == pytest.approx(float(rp.kplanes_tv([[single.plane]])), rel=1e-5)
+
+
+def test_fused_adam_matches_torch_adam():
+    from tinynerf_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(1, 32, 64, 64), (64, 96), (64,), (3, 64), (5,)]
+    mk = lambda: [torch.nn.Parameter(torch.randn(*s, device=DEV)) for s in shapes]
+    a, b = mk(), mk()
+    with torch.no_grad():
+        for x, y in zip(a, b):
+            y.copy_(x)
+        a[0].data = a[0].data.contiguous(memory_format=torch.channels_last)  # strided param like the planes
+    kw = dict(lr=1e-2, eps=1e-15, weight_decay=1e-5)
+    oa, ob = FusedAdam(a, **kw), torch.optim.Adam(b, **kw)
+    sched = torch.optim.lr_scheduler.MultiStepLR(oa, milestones=[3], gamma=0.33)
+    sched_b = torch.optim.lr_scheduler.MultiStepLR(ob, milestones=[3], gamma=0.33)
+    for it in range(6):
+        for x, y in zip(a, b):
+            gr = torch.randn(x.shape, device=DEV) * 1024.0  # the reference's un-unscaled gradients
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step(); sched.step(); sched_b.step()
+        for x, y in zip(a, b):
+            close(x.detach(), y.detach(), rtol=2e-6, atol=1e-7)
+    assert set(oa.state[a[0]].keys()) == {"step", "exp_avg", "exp_avg_sq"}

@@ -71,6 +71,12 @@ _SIGNATURES = {
     "tnf_cobafa_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_int32, c_f32p, c_f32p,
                                  C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_void_p]),
+    "tnf_tv_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "tnf_tv_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                             C.POINTER(C.c_float), c_f32p, C.c_int32, C.c_void_p]),
+    "tnf_adam_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_float, C.c_float,
+                                C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
     "tnf_composite_fwd": (C.c_int, [c_f32p, c_f32p, c_i32p, C.c_int64, C.c_int64, C.POINTER(C.c_float), c_f32p,
                                     c_f32p, C.c_void_p]),
     "tnf_composite_bwd": (C.c_int, [c_f32p, c_f32p, c_i32p, C.c_int64, C.c_int64, C.POINTER(C.c_float), c_f32p,
@@ -105,7 +111,7 @@ def load():
 KERNELS_PER_CALL = {"tnf_weights_fwd": 1, "tnf_weights_bwd": 1, "tnf_march_count": 2, "tnf_march_pack": 1,
                     "tnf_occ_query": 1, "tnf_occ_update_coords": 1, "tnf_occ_update_apply": 1, "tnf_kplanes_fwd": 1,
                     "tnf_kplanes_bwd": 1, "tnf_cobafa_fwd": 1, "tnf_cobafa_bwd": 1, "tnf_composite_fwd": 1,
-                    "tnf_composite_bwd": 1}
+                    "tnf_composite_bwd": 1, "tnf_tv_fwd": 1, "tnf_tv_bwd": 1, "tnf_adam_step": 1}
 launch_count = 0
 _prof = None
 

@@ -29,56 +29,53 @@ struct KPArgs {
   const float* grad_out;
 };
 
-struct Bilinear {
-  int x0, y0;
-  float w[4];    // nw, ne, sw, se  (torch grid_sampler_2d order)
-  bool ok[4];
+// One axis of torch's grid_sampler (bilinear, zeros padding, align_corners=True):
+//   i = ((c+1)/2)*(res-1); i0 = floor(i); w0 = (i0+1) - i; w1 = i - i0
+// Out-of-range corners are skipped by torch; here their axis weight is zeroed and the index clamped,
+// which adds an exact +-0 instead (identical values for finite planes) and keeps every load unpredicated.
+struct Axis {
+  int i0, i1;     // clamped texel indices
+  float w0, w1;   // weights of i0 / i1 (0 when that texel is outside the plane)
 };
-
-// torch grid_sampler_2d (bilinear, zeros, align_corners=True) index/weight arithmetic
-__device__ __forceinline__ Bilinear bilinear_setup(float gx, float gy, int res) {
-  Bilinear b;
-  const float ix = TNF_MUL(TNF_MUL(TNF_ADD(gx, 1.f), 0.5f), (float)(res - 1));
-  const float iy = TNF_MUL(TNF_MUL(TNF_ADD(gy, 1.f), 0.5f), (float)(res - 1));
-  const float fx = floorf(ix), fy = floorf(iy);
-  b.x0 = (int)fx;
-  b.y0 = (int)fy;
-  const float wx0 = TNF_SUB((float)(b.x0 + 1), ix), wx1 = TNF_SUB(ix, (float)b.x0);
-  const float wy0 = TNF_SUB((float)(b.y0 + 1), iy), wy1 = TNF_SUB(iy, (float)b.y0);
-  b.w[0] = TNF_MUL(wx0, wy0);
-  b.w[1] = TNF_MUL(wx1, wy0);
-  b.w[2] = TNF_MUL(wx0, wy1);
-  b.w[3] = TNF_MUL(wx1, wy1);
-  const bool bx0 = (unsigned)b.x0 < (unsigned)res, bx1 = (unsigned)(b.x0 + 1) < (unsigned)res;
-  const bool by0 = (unsigned)b.y0 < (unsigned)res, by1 = (unsigned)(b.y0 + 1) < (unsigned)res;
-  b.ok[0] = bx0 && by0;
-  b.ok[1] = bx1 && by0;
-  b.ok[2] = bx0 && by1;
-  b.ok[3] = bx1 && by1;
-  return b;
+__device__ __forceinline__ Axis axis_setup(float c, int res) {
+  Axis a;
+  const float i = TNF_MUL(TNF_MUL(TNF_ADD(c, 1.f), 0.5f), (float)(res - 1));
+  const float f = floorf(i);
+  const int i0 = (int)f;
+  a.w0 = ((unsigned)i0 < (unsigned)res) ? TNF_SUB(f + 1.f, i) : 0.f;
+  a.w1 = ((unsigned)(i0 + 1) < (unsigned)res) ? TNF_SUB(i, f) : 0.f;
+  a.i0 = min(max(i0, 0), res - 1);
+  a.i1 = min(max(i0 + 1, 0), res - 1);
+  return a;
 }
 
-__device__ __forceinline__ long long corner_offset(const Bilinear& b, int k, int res, int C) {
-  const int xx = b.x0 + (k & 1), yy = b.y0 + (k >> 1);
-  return ((long long)yy * res + xx) * C;
+struct Corners {
+  int off[4];   // element offsets of nw, ne, sw, se (torch grid_sampler_2d order)
+  float w[4];
+};
+// plane indexed [y][x][C]; ax -> x/W axis, ay -> y/H axis
+__device__ __forceinline__ Corners corners(const Axis& ax, const Axis& ay, int res, int C, int ch) {
+  Corners c;
+  const int r0 = ay.i0 * res, r1 = ay.i1 * res;
+  c.off[0] = (r0 + ax.i0) * C + ch;
+  c.off[1] = (r0 + ax.i1) * C + ch;
+  c.off[2] = (r1 + ax.i0) * C + ch;
+  c.off[3] = (r1 + ax.i1) * C + ch;
+  c.w[0] = TNF_MUL(ax.w0, ay.w0);
+  c.w[1] = TNF_MUL(ax.w1, ay.w0);
+  c.w[2] = TNF_MUL(ax.w0, ay.w1);
+  c.w[3] = TNF_MUL(ax.w1, ay.w1);
+  return c;
 }
 
-__device__ __forceinline__ float4 gather_plane(const float* __restrict__ plane, const Bilinear& b, int res,
-                                               int C, int ch) {
-  float4 v[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    v[k] = b.ok[k] ? __ldg(reinterpret_cast<const float4*>(plane + corner_offset(b, k, res, C) + ch))
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ float4 blend(const float4 v[4], const Corners& c) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (b.ok[k]) {
-      acc.x = TNF_FMA(v[k].x, b.w[k], acc.x);
-      acc.y = TNF_FMA(v[k].y, b.w[k], acc.y);
-      acc.z = TNF_FMA(v[k].z, b.w[k], acc.z);
-      acc.w = TNF_FMA(v[k].w, b.w[k], acc.w);
-    }
+    acc.x = TNF_FMA(v[k].x, c.w[k], acc.x);
+    acc.y = TNF_FMA(v[k].y, c.w[k], acc.y);
+    acc.z = TNF_FMA(v[k].z, c.w[k], acc.z);
+    acc.w = TNF_FMA(v[k].w, c.w[k], acc.w);
   }
   return acc;
 }
@@ -87,36 +84,43 @@ __device__ __forceinline__ float4 mul4(float4 a, float4 b) {
   return make_float4(TNF_MUL(a.x, b.x), TNF_MUL(a.y, b.y), TNF_MUL(a.z, b.z), TNF_MUL(a.w, b.w));
 }
 
-// dimension pairs of itertools.combinations(range(3), 2) (src/models.py:145): first -> x/W, second -> y/H
-__device__ __constant__ int kPairA[3] = {0, 0, 1};
-__device__ __constant__ int kPairB[3] = {1, 2, 2};
-
+// Planes of a scale use the coordinate pairs of itertools.combinations(range(3), 2) (src/models.py:145):
+// plane 0 = (x,y), plane 1 = (x,z), plane 2 = (y,z); first coordinate -> W axis, second -> H axis.
 template <bool BWD>
 __global__ void __launch_bounds__(256) kplanes_kernel(const KPArgs A) {
-  const int lps = A.channels >> 2;  // lanes per sample (power of two, <= 8)
+  const int C = A.channels;
+  const int lps = C >> 2;  // lanes per sample (power of two, <= 8)
   const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long n = gt / lps;
   const int ch = (int)(gt % lps) * 4;
   if (n >= A.n) return;
-  float xyz[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) xyz[c] = __ldg(A.x + n * A.x_stride + c);
-  const int F = A.n_scales * A.channels;
+  const float* xp = A.x + n * A.x_stride;
+  const float cx = __ldg(xp), cy = __ldg(xp + 1), cz = __ldg(xp + 2);
+  const int F = A.n_scales * C;
+#pragma unroll 1
   for (int s = 0; s < A.n_scales; ++s) {
     const int res = A.res[s];
-    Bilinear b[3];
-    float4 f[3];
+    const Axis ax = axis_setup(cx, res), ay = axis_setup(cy, res), az = axis_setup(cz, res);
+    Corners c[3];
+    c[0] = corners(ax, ay, res, C, ch);
+    c[1] = corners(ax, az, res, C, ch);
+    c[2] = corners(ay, az, res, C, ch);
+    float4 v[3][4];
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
-      b[p] = bilinear_setup(xyz[kPairA[p]], xyz[kPairB[p]], res);
-      f[p] = gather_plane(A.planes[s * 3 + p], b[p], res, A.channels, ch);
+      const float* pl = A.planes[s * 3 + p];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[p][k] = __ldg(reinterpret_cast<const float4*>(pl + c[p].off[k]));
     }
+    float4 f[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) f[p] = blend(v[p], c[p]);
     if (!BWD) {
       // current_scale_features = 1.; *= plane0; *= plane1; *= plane2  (src/models.py:158-160)
       const float4 o = mul4(mul4(f[0], f[1]), f[2]);
-      *reinterpret_cast<float4*>(A.out + n * F + s * A.channels + ch) = o;
+      *reinterpret_cast<float4*>(A.out + n * F + s * C + ch) = o;
     } else {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(A.grad_out + n * F + s * A.channels + ch));
+      const float4 g = __ldg(reinterpret_cast<const float4*>(A.grad_out + n * F + s * C + ch));
       // autograd of ((f0*f1)*f2): d f2 = g*(f0*f1); d(f0*f1) = g*f2; d f0 = (g*f2)*f1; d f1 = (g*f2)*f0
       const float4 g01 = mul4(g, f[2]);
       float4 gp[3];
@@ -128,12 +132,10 @@ __global__ void __launch_bounds__(256) kplanes_kernel(const KPArgs A) {
         float* gpl = A.grads[s * 3 + p];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (b[p].ok[k]) {
-            const float wk = b[p].w[k];
-            red_add_f4(gpl + corner_offset(b[p], k, res, A.channels) + ch,
-                       make_float4(TNF_MUL(wk, gp[p].x), TNF_MUL(wk, gp[p].y), TNF_MUL(wk, gp[p].z),
-                                   TNF_MUL(wk, gp[p].w)));
-          }
+          const float wk = c[p].w[k];
+          if (wk != 0.f)  // also skips the clamped out-of-range corners, like torch's safe_add_2d
+            red_add_f4(gpl + c[p].off[k], make_float4(TNF_MUL(wk, gp[p].x), TNF_MUL(wk, gp[p].y),
+                                                      TNF_MUL(wk, gp[p].z), TNF_MUL(wk, gp[p].w)));
         }
       }
     }

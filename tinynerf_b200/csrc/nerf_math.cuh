@@ -149,8 +149,9 @@ TNF_HD SampleOut march_sample(const MarchConst& M, const float o[3], const float
     }
   }
   s.step = step;
-  const float v = trilinear_zeros(M.grid, M.gd, M.gh, M.gw, s.p[0], s.p[1], s.p[2]);  // src/core.py:151-156
-  s.keep = inside && (v > M.thr);
+  // src/core.py:151-156,176: mask = marcher_mask & (trilinear(grid) > thr); the lookup has no side effect,
+  // so it is skipped for samples the marcher mask already rejects (about half of an AABB lattice)
+  s.keep = inside && (trilinear_zeros(M.grid, M.gd, M.gh, M.gw, s.p[0], s.p[1], s.p[2]) > M.thr);
   return s;
 }
 

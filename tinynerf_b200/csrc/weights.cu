@@ -46,7 +46,7 @@ struct WArgs {
 // `p` points at the task's tile origin, `rel` is the tile-relative index of the lane's first sample and
 // `lim` = n_samples - tile0 bounds the reads.
 template <int MODE>
-__device__ __forceinline__ void load_vec(const float* __restrict__ p, int rel, long long lim, float v[4]) {
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, int rel, int lim, float v[4]) {
   if (MODE != 2 && rel + 3 < lim) {
     const float4 t = ld_stream_f4(p + rel);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -56,7 +56,7 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ p, int rel, l
   }
 }
 template <int MODE>
-__device__ __forceinline__ void load_steps(const float* __restrict__ p, long long stride, int rel, long long lim,
+__device__ __forceinline__ void load_steps(const float* __restrict__ p, long long stride, int rel, int lim,
                                            float v[4]) {
   if (MODE == 0) {
     load_vec<0>(p, rel, lim, v);
@@ -129,6 +129,51 @@ __device__ __forceinline__ unsigned head_bits5(const unsigned* mask, int rel, in
   return (unsigned)(both >> (rel & 31)) & 0x1Fu;
 }
 
+// Warp-segmented scans over per-lane aggregates without shuffling flags: the lanes that contain a ray
+// head (resp. a ray tail) are known to the whole warp from one ballot, so every lane derives how many
+// lanes below (resp. above) it may absorb: `lim`.  Step d of the Hillis-Steele scan applies iff lim >= d.
+__device__ __forceinline__ int absorb_limit_up(unsigned heads, int lane) {
+  const unsigned below = heads & (0xFFFFFFFFu >> (31 - lane));  // lanes 0..lane
+  return below ? lane - (31 - __clz(below)) : lane;
+}
+__device__ __forceinline__ int absorb_limit_down(unsigned tails, int lane) {
+  const unsigned above = tails >> lane;  // bit 0 = this lane
+  return above ? __ffs(above) - 1 : 31 - lane;
+}
+__device__ __forceinline__ float seg_scan_mul_up(float P, int lim) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float Pu = __shfl_up_sync(kFullMask, P, d);
+    if (lim >= d) P *= Pu;
+  }
+  return P;
+}
+__device__ __forceinline__ float seg_scan_add_down(float P, int lim) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float Pu = __shfl_down_sync(kFullMask, P, d);
+    if (lim >= d) P += Pu;
+  }
+  return P;
+}
+
+// w = T*(1.-a) exactly as the reference's fp64 expression (src/cuda.cu:25).  For a in [0.5, 2] the fp32
+// evaluation is bit-identical: 1-a is exact (Sterbenz) and the 48-bit product is exact in fp64, so both
+// round the same real number to fp32 once.  Only a < 0.5 (sigma*delta > 0.69) takes the fp64 path.
+__device__ __forceinline__ void weights_from_T(const float T[4], const float a[4], float thr, float w[4]) {
+  bool dp = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    w[i] = (T[i] > thr) ? T[i] * (1.f - a[i]) : 0.f;
+    dp |= !(a[i] >= 0.5f);
+  }
+  if (dp) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (!(a[i] >= 0.5f) && T[i] > thr) w[i] = (float)((double)T[i] * (1. - (double)a[i]));
+  }
+}
+
 // The reference's loop, verbatim semantics (src/cuda.cu:19-28), plus the zeros it gets from
 // zeros_like (src/cuda.cu:84) for samples after termination.
 __device__ __noinline__ void serial_ray_fwd(const float* __restrict__ sig, const float* __restrict__ stp,
@@ -162,7 +207,7 @@ struct Task {
   long long tile0, s0, s1;
   int r_lo, r_hi;
   int lo, hi;        // s0 - tile0, s1 - tile0 (tile-relative sample window owned by the task)
-  long long lim;     // n_samples - tile0
+  int lim;           // n_samples - tile0 (< 2^31: packing info is int32)
   bool valid;
 };
 
@@ -193,7 +238,7 @@ __device__ __forceinline__ Task task_setup(const WArgs& A, int task, unsigned* m
   t.s1 = s1;
   t.lo = (int)(s0 - t.tile0);
   t.hi = (int)(s1 - t.tile0);
-  t.lim = N - t.tile0;
+  t.lim = (int)(N - t.tile0);
   t.valid = (s0 >= t.tile0) && (s1 > s0) && (t.r_hi > t.r_lo);
   if (!t.valid) return t;
   for (int i = lane; i < (A.tile >> 5); i += 32) mask[i] = 0u;
@@ -208,7 +253,7 @@ __device__ __forceinline__ Task task_setup(const WArgs& A, int task, unsigned* m
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kWarps * 32) weights_fwd_kernel(const WArgs A) {
+__global__ void __launch_bounds__(kWarps * 32, 4) weights_fwd_kernel(const WArgs A) {
   __shared__ unsigned s_mask[kWarps][kMaskWords];
   __shared__ int s_q[kWarps][kQueue];
   __shared__ int s_qn[kWarps];
@@ -251,17 +296,9 @@ __global__ void __launch_bounds__(kWarps * 32) weights_fwd_kernel(const WArgs A)
       float P = a[0];
 #pragma unroll
       for (int i = 1; i < 4; ++i) P = ((hb >> i) & 1u) ? a[i] : P * a[i];
-      int F = hb != 0u;
-      if (lane == 0 && !F) P *= carry;
-#pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const float Pu = __shfl_up_sync(kFullMask, P, dlt);
-        const int Fu = __shfl_up_sync(kFullMask, F, dlt);
-        if (lane >= dlt) {
-          if (!F) P *= Pu;
-          F |= Fu;
-        }
-      }
+      const unsigned heads = __ballot_sync(kFullMask, hb != 0u);
+      if (lane == 0 && !(heads & 1u)) P *= carry;
+      P = seg_scan_mul_up(P, absorb_limit_up(heads, lane));
       float E = __shfl_up_sync(kFullMask, P, 1);
       if (lane == 0) E = carry;
       carry = __shfl_sync(kFullMask, P, 31);
@@ -270,13 +307,9 @@ __global__ void __launch_bounds__(kWarps * 32) weights_fwd_kernel(const WArgs A)
       T[0] = (hb & 1u) ? 1.f : E;
 #pragma unroll
       for (int i = 1; i < 4; ++i) T[i] = ((hb >> i) & 1u) ? 1.f : T[i - 1] * a[i - 1];
+      weights_from_T(T, a, thr, w);
 
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool alive = T[i] > thr;
-        // same arithmetic as the reference: one fp64 multiply, rounded to fp32 on store
-        w[i] = alive ? (float)((double)T[i] * (1. - (double)a[i])) : 0.f;
-      }
+      const bool edge = (rpos < t.lo) | (rpos + 128 > t.hi);  // warp-uniform: round not fully owned
       if (exact) {
         // Cheap prefilter, warp-uniform band: |T - thr| <= thr * 1.5*2^-23 * (upper bound on the sample's
         // position in its ray); plus non-monotone (a > 1 / NaN) and underflow cases.
@@ -307,7 +340,8 @@ __global__ void __launch_bounds__(kWarps * 32) weights_fwd_kernel(const WArgs A)
           }
         }
       }
-      store_vec<MODE>(out, rel, t.lo, t.hi, w);
+      if (MODE != 2 && !edge) st_stream_f4(out + rel, make_float4(w[0], w[1], w[2], w[3]));
+      else store_vec<MODE>(out, rel, t.lo, t.hi, w);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { s[i] = sn[i]; d[i] = dn[i]; }
     }
@@ -337,7 +371,7 @@ __global__ void __launch_bounds__(kWarps * 32) weights_fwd_kernel(const WArgs A)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kWarps * 32) weights_bwd_kernel(const WArgs A) {
+__global__ void __launch_bounds__(kWarps * 32, 4) weights_bwd_kernel(const WArgs A) {
   __shared__ unsigned s_mask[kWarps][kMaskWords];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned* mask = s_mask[wib];
@@ -368,36 +402,34 @@ __global__ void __launch_bounds__(kWarps * 32) weights_bwd_kernel(const WArgs A)
           load_vec<MODE>(wp, rel - 128, t.lim, wn);
           load_vec<MODE>(gp, rel - 128, t.lim, gn);
         }
+        const bool edge = (rpos < t.lo) | (rpos + 128 > t.hi);
         float c[4], S[4];
         const unsigned hb5 = head_bits5(mask, rel, A.tile);
-        unsigned tail = 0u;  // bit i: sample rel+i is the last sample of its ray
+        unsigned tail = (hb5 >> 1) & 0xFu;  // bit i: sample rel+i is the last sample of its ray
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          c[i] = (rel + i < t.hi) ? w[i] * g[i] : 0.f;
-          tail |= ((((hb5 >> (i + 1)) & 1u) | (unsigned)(rel + i + 1 >= t.hi)) << i);
+        for (int i = 0; i < 4; ++i) c[i] = w[i] * g[i];
+        if (rpos + 128 >= t.hi) {  // last owned sample closes its ray; samples beyond it contribute nothing
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (rel + i >= t.hi) c[i] = 0.f;
+            tail |= (unsigned)(rel + i + 1 >= t.hi) << i;
+          }
         }
         // lane aggregate in descending order: inclusive suffix sum of the lane's lowest sample
         float P = c[3];
 #pragma unroll
         for (int i = 2; i >= 0; --i) P = ((tail >> i) & 1u) ? c[i] : P + c[i];
-        int F = tail != 0u;
-        if (lane == 31 && !F) P += carry;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-          const float Pu = __shfl_down_sync(kFullMask, P, dlt);
-          const int Fu = __shfl_down_sync(kFullMask, F, dlt);
-          if (lane + dlt < 32) {
-            if (!F) P += Pu;
-            F |= Fu;
-          }
-        }
+        const unsigned tails = __ballot_sync(kFullMask, tail != 0u);
+        if (lane == 31 && !(tails >> 31)) P += carry;
+        P = seg_scan_add_down(P, absorb_limit_down(tails, lane));
         float E = __shfl_down_sync(kFullMask, P, 1);  // inclusive suffix sum of sample rel+4
         if (lane == 31) E = carry;
         carry = __shfl_sync(kFullMask, P, 0);
         S[3] = ((tail >> 3) & 1u) ? 0.f : E;
 #pragma unroll
         for (int i = 2; i >= 0; --i) S[i] = ((tail >> i) & 1u) ? 0.f : S[i + 1] + c[i + 1];
-        store_vec<MODE>(out, rel, t.lo, t.hi, S);
+        if (MODE != 2 && !edge) *reinterpret_cast<float4*>(out + rel) = make_float4(S[0], S[1], S[2], S[3]);
+        else store_vec<MODE>(out, rel, t.lo, t.hi, S);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { w[i] = wn[i]; g[i] = gn[i]; }
       }
@@ -420,8 +452,9 @@ __global__ void __launch_bounds__(kWarps * 32) weights_bwd_kernel(const WArgs A)
           load_steps<MODE>(stp, A.sstride, rel + 128, t.lim, dn);
           load_vec<MODE>(gp, rel + 128, t.lim, gn);
         }
+        const bool edge = (rpos < t.lo) | (rpos + 128 > t.hi);
         float a[4], S[4], o[4];
-        if (MODE != 2 && rel >= t.lo && rel + 3 < t.hi) {
+        if (MODE != 2 && !edge) {
           const float4 v = *reinterpret_cast<const float4*>(out + rel);
           S[0] = v.x; S[1] = v.y; S[2] = v.z; S[3] = v.w;
         } else {
@@ -434,17 +467,9 @@ __global__ void __launch_bounds__(kWarps * 32) weights_bwd_kernel(const WArgs A)
         float P = a[0];
 #pragma unroll
         for (int i = 1; i < 4; ++i) P = ((hb >> i) & 1u) ? a[i] : P * a[i];
-        int F = hb != 0u;
-        if (lane == 0 && !F) P *= carryT;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-          const float Pu = __shfl_up_sync(kFullMask, P, dlt);
-          const int Fu = __shfl_up_sync(kFullMask, F, dlt);
-          if (lane >= dlt) {
-            if (!F) P *= Pu;
-            F |= Fu;
-          }
-        }
+        const unsigned heads = __ballot_sync(kFullMask, hb != 0u);
+        if (lane == 0 && !(heads & 1u)) P *= carryT;
+        P = seg_scan_mul_up(P, absorb_limit_up(heads, lane));
         float E = __shfl_up_sync(kFullMask, P, 1);
         if (lane == 0) E = carryT;
         carryT = __shfl_sync(kFullMask, P, 31);
@@ -455,7 +480,8 @@ __global__ void __launch_bounds__(kWarps * 32) weights_bwd_kernel(const WArgs A)
           Tn = (((hb >> i) & 1u) ? 1.f : Tn) * a[i];
           o[i] = d[i] * __fmaf_rn(Tn, g[i], -S[i]);
         }
-        store_vec<MODE>(out, rel, t.lo, t.hi, o);
+        if (MODE != 2 && !edge) st_stream_f4(out + rel, make_float4(o[0], o[1], o[2], o[3]));
+        else store_vec<MODE>(out, rel, t.lo, t.hi, o);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { s[i] = sn[i]; d[i] = dn[i]; g[i] = gn[i]; }
       }
@@ -506,10 +532,10 @@ int pick_tile(long long n) {
     return e ? atoi(e) : 0;
   }();
   if (forced >= 128 && forced <= kMaxTile && forced % 128 == 0) return forced;
-  const long long want = (long long)sm_count() * 40 * 4;
+  const long long want = (long long)sm_count() * 32;
   long long tile = (n / want) & ~127LL;
   if (tile < 256) tile = 256;
-  if (tile > 1024) tile = 1024;
+  if (tile > kMaxTile) tile = kMaxTile;
   return (int)tile;
 }
 

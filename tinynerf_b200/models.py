@@ -160,12 +160,55 @@ class KPlanesFeaturePlane(torch.nn.Module):
         return output.squeeze().transpose(0, -1).contiguous().view(new_shape)
 
     def loss_tv(self) -> torch.Tensor:
+        """mse(p[1:]-p[:-1]) along H + along W (src/models.py:115-118); one fused kernel for square CUDA planes."""
+        if self.plane.is_cuda and self.plane.shape[2] == self.plane.shape[3] and self.feature_dim % 4 == 0:
+            _ensure_channels_last_(self.plane)
+            return _KPlanesTV.apply(self.feature_dim, self.plane)
         tv_x = torch.nn.functional.mse_loss(self.plane[:, :, 1:, :], self.plane[:, :, :-1, :])
         tv_y = torch.nn.functional.mse_loss(self.plane[:, :, :, 1:], self.plane[:, :, :, :-1])
         return tv_x + tv_y
 
     def loss_l1(self) -> torch.Tensor:
         return torch.mean(torch.abs(self.plane))
+
+
+class _KPlanesTV(Function):
+    """mean_i loss_tv(plane_i) for square channels-last planes, via tnf_tv_fwd / tnf_tv_bwd."""
+
+    @staticmethod
+    def forward(ctx: Any, channels: int, *planes: torch.Tensor):  # type: ignore
+        _lib.load()
+        n = len(planes)
+        stor = [_channels_last_storage(p) for p in planes]
+        if any(v is None for v in stor):
+            raise RuntimeError("K-Planes parameters must be channels-last")
+        res = [int(p.shape[-1]) for p in planes]
+        dev = planes[0].device
+        sums = torch.empty(2 * n, dtype=torch.float64, device=dev)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in stor])
+        res_arr = (C.c_int32 * n)(*res)
+        with torch.cuda.device(dev):
+            _lib.call("tnf_tv_fwd", ptrs, res_arr, n, channels, sums.data_ptr(), _lib.stream_ptr(),
+                      nbytes=sum(t.numel() for t in stor) * 4)
+        denom = torch.tensor([float(channels * (r - 1) * r) for r in res for _ in range(2)], dtype=torch.float64)
+        ctx.save_for_backward(*planes)
+        ctx.channels, ctx.res = channels, res
+        return ((sums / denom.to(dev)).sum() / n).float()
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore
+        planes = ctx.saved_tensors
+        n = len(planes)
+        grads = [torch.empty_like(p) for p in planes]  # every element is written by the kernel
+        ptrs = (C.c_void_p * n)(*[_channels_last_storage(p).data_ptr() for p in planes])
+        gptrs = (C.c_void_p * n)(*[_channels_last_storage(g).data_ptr() for g in grads])
+        res_arr = (C.c_int32 * n)(*ctx.res)
+        wts = (C.c_float * n)(*[1.0 / n] * n)
+        gs = grad_out.detach().float().reshape(1).contiguous()
+        with torch.cuda.device(gs.device):
+            _lib.call("tnf_tv_bwd", ptrs, gptrs, res_arr, n, ctx.channels, wts, gs.data_ptr(), 0, _lib.stream_ptr(),
+                      nbytes=2 * sum(p.numel() for p in planes) * 4)
+        return (None, *grads)
 
 
 class _KPlanesLookup(Function):
@@ -257,6 +300,10 @@ class KPlanesFeatureField(torch.nn.Module):
         return self.dropout(_KPlanesLookup.apply(x, self.plane_channels, *self._plane_params()))
 
     def loss_tv(self) -> torch.Tensor:
+        """mean over the nine planes of plane.loss_tv() (src/models.py:165-172); one kernel each way."""
+        params = self._plane_params()
+        if params[0].is_cuda and self.plane_channels % 4 == 0:
+            return _KPlanesTV.apply(self.plane_channels, *params)
         loss = 0.0
         count = 0
         for plane_scale in self.planes:

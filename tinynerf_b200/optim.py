@@ -1,0 +1,61 @@
+"""Adam as one streaming pass per step.
+
+`FusedAdam` is a torch.optim.Optimizer with torch.optim.Adam's hyper-parameters and state names
+(`step`, `exp_avg`, `exp_avg_sq`), as configured by the reference at src/run.py:186 (L2 weight decay,
+no amsgrad).  Every parameter tensor of every group goes through tnf_adam_step: p, g, m, v are read
+once and p, m, v written once (28 B/param) instead of torch's ~10 foreach passes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        _lib.load()
+        for group in self.param_groups:
+            ps, gs, ms, vs = [], [], [], []
+            step = None
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                _lib.require_cuda(p, "parameter")
+                if p.dtype != torch.float32:
+                    raise RuntimeError("FusedAdam handles fp32 parameters only")
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                step = st["step"] if step is None else step
+                if st["step"] != step:
+                    raise RuntimeError("FusedAdam expects all parameters of a group to share the step count")
+                g = p.grad
+                if g.stride() != p.stride():  # bring the gradient to the parameter's memory order
+                    g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(g)
+                ps.append(p); gs.append(g); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
+            if not ps:
+                continue
+            n = len(ps)
+            tab = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+            numel = (C.c_int64 * n)(*[t.numel() for t in ps])
+            b1, b2 = group["betas"]
+            with torch.cuda.device(ps[0].device):
+                _lib.call("tnf_adam_step", tab(ps), tab(gs), tab(ms), tab(vs), numel, n, float(group["lr"]), float(b1),
+                          float(b2), float(group["eps"]), float(group["weight_decay"]), int(step), _lib.stream_ptr(),
+                          nbytes=28 * sum(t.numel() for t in ps), extra_kernels=math.ceil(n / 48) - 1)
+        return loss

@@ -22,8 +22,43 @@ import torch.distributed as dist
 from . import _lib
 from .core import (ContractionAABB, ContractionMip360, NerfRenderer, OccupancyGrid, RayMarcherAABB,
                    RayMarcherUnbounded, RayProvider)
+from .optim import FusedAdam
 from .models import (CobafaFeatureField, KPlanesFeatureField, VanillaColorDecoder, VanillaFeatureMLP,
                      VanillaOpacityDecoder)
+
+
+# ---- data-parallel plumbing (device-agnostic; exercised on CPU with gloo in tests/test_dp_gloo.py) ----
+
+
+def global_ray_count(n_local: int, device, world: int) -> torch.Tensor:
+    """Number of rays in the union batch of all ranks (0-dim float tensor on `device`)."""
+    n = torch.tensor(float(n_local), device=device)
+    if world > 1:
+        dist.all_reduce(n)
+    return n
+
+
+def dp_mse(rendered: torch.Tensor, target: torch.Tensor, n_rays_global: torch.Tensor) -> torch.Tensor:
+    """This rank's share of MSELoss over the union batch (src/run.py:252): the sum over ranks equals
+    mse_loss(cat(rendered), cat(target)) although every rank holds a different number of rays."""
+    return ((rendered - target) ** 2).sum() / (n_rays_global * rendered.size(-1))
+
+
+def allreduce_gradients(params, world: int) -> None:
+    """Sum the per-rank gradients (NCCL over NVLink on the GPU box)."""
+    if world <= 1:
+        return
+    for p in params:
+        if p.grad is not None:
+            dist.all_reduce(p.grad)
+
+
+def shard_slices(depth: int, rank: int, world: int) -> Tuple[int, int]:
+    """Depth slices [z0, z1) of the occupancy grid owned by `rank`."""
+    if depth % world != 0:
+        raise ValueError("occupancy grid depth must be divisible by the number of ranks")
+    per = depth // world
+    return rank * per, (rank + 1) * per
 
 
 class RayStore:
@@ -120,7 +155,7 @@ class Trainer:
         if world > 1:  # identical replicas: broadcast rank 0's initial parameters
             for p in self.renderer.parameters():
                 dist.broadcast(p.data, 0)
-        self.optimizer = torch.optim.Adam(self.renderer.parameters(), lr=1e-2, eps=1e-15, weight_decay=1e-5)
+        self.optimizer = FusedAdam(self.renderer.parameters(), lr=1e-2, eps=1e-15, weight_decay=1e-5)
         s = self.steps
         self.scheduler = torch.optim.lr_scheduler.MultiStepLR(
             self.optimizer, milestones=[s // 2, s * 3 // 4, s * 5 // 6, s * 9 // 10], gamma=0.33)
@@ -160,12 +195,9 @@ class Trainer:
         if self.world == 1:
             og.update(sigma_fn)
             return
-        D = og.grid.size(0)
-        assert D % self.world == 0, "depth slices must divide the number of ranks"
-        per = D // self.world
-        z0 = self.rank * per
-        og.update_slices(sigma_fn, z0, z0 + per)
-        dist.all_gather_into_tensor(og.grid.view(-1), og.grid[z0:z0 + per].reshape(-1).clone())
+        z0, z1 = shard_slices(og.grid.size(0), self.rank, self.world)
+        og.update_slices(sigma_fn, z0, z1)
+        dist.all_gather_into_tensor(og.grid.view(-1), og.grid[z0:z1].reshape(-1).clone())
         og.mean = og.grid.mean().item()
 
     # ---- one training iteration (src/run.py:246-261) -------------------------------------------
@@ -175,21 +207,15 @@ class Trainer:
         if self.train_step % self.occupancy_grid_updates == 0:
             self.update_occupancy()
         rendered = self.renderer(packed, info)
-        n_rays = torch.tensor([float(info.size(0))], device=self.device)
-        if self.world > 1:
-            dist.all_reduce(n_rays)
-        # MSE over the union batch: local sum of squares / (global rays * 3)
-        loss = ((rendered - rgbs) ** 2).sum() / (n_rays[0] * 3.0)
+        loss = dp_mse(rendered, rgbs, global_ray_count(info.size(0), self.device, self.world))
         if self.cfg.method == "kplanes":
             reg = self.renderer.feature_module.loss_tv() * self.tv_reg_alpha  # type: ignore
-            reg = reg + self.renderer.feature_module.loss_l1() * self.l1_reg_alpha  # type: ignore
+            if self.l1_reg_alpha != 0.0:  # the reference multiplies by 0. (src/run.py:114,256): no contribution
+                reg = reg + self.renderer.feature_module.loss_l1() * self.l1_reg_alpha  # type: ignore
             loss = loss + reg / self.world  # summed over ranks it counts once
         self.optimizer.zero_grad()
         (loss * self.cfg.grad_scale).backward()
-        if self.world > 1:
-            for p in self.renderer.parameters():
-                if p.grad is not None:
-                    dist.all_reduce(p.grad)
+        allreduce_gradients(self.renderer.parameters(), self.world)
         self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
