@@ -184,6 +184,27 @@ int tnf_cobafa_bwd(const float* const* basis, float* const* grad_basis, const in
                    float* grad_coef, int32_t coef_res, const float* x, int64_t x_stride, int64_t n,
                    const float* grad_out, void* stream);
 
+/* ---- a15-a17: dense layers of the MLP heads on tcgen05 tensor cores (3xTF32, fp32 accumulate in TMEM) ----
+ * Replace the nn.Linear (+ReLU) stacks of MLP / VanillaOpacityDecoder / VanillaColorDecoder / the Cobafa trunk
+ * (src/models.py:7-28,70-89,255,266) and their autograd backward.  Row-major fp32, weight = nn.Linear.weight
+ * [n, k]; k <= 160, n in {32,64,96,128}; x/y/dy/dx 16-byte aligned with leading dimensions multiple of 4.
+ *   fwd  : y = act(x W^T + b) (relu flag); optionally a fused small head on the (activated) y:
+ *          head_out[m, o] = head_act(sum_j y[m,j] head_w[o,j] + head_b[o]), n_head <= 4,
+ *          head_act 0 = identity, 1 = exp(v - 1) (truncated_exp(x - 1.), src/models.py:74), 2 = sigmoid (:85)
+ *   dgrad: dx = (dy W) (* (relu_src > 0) when relu_src != NULL: ReLU backward of the producer of x)
+ *   wgrad: dweight += dy^T x ; dbias += column sums of dy      (atomic accumulation: zero them first)
+ *   head_bwd: gradients of the fused head: dh (masked by h > 0), dhead_w, dhead_b (accumulated)
+ */
+int tnf_linear_fwd(const float* x, int64_t ldx, const float* weight, const float* bias, float* y, int64_t ldy,
+                   int64_t m, int32_t n, int32_t k, int32_t relu, const float* head_w, const float* head_b,
+                   float* head_out, int32_t n_head, int32_t head_act, void* stream);
+int tnf_linear_bwd_data(const float* dy, int64_t lddy, const float* weight, float* dx, int64_t lddx,
+                        const float* relu_src, int64_t ldrs, int64_t m, int32_t n, int32_t k, void* stream);
+int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dweight, float* dbias,
+                          int64_t m, int32_t n, int32_t k, void* stream);
+int tnf_head_bwd(const float* h, int64_t ldh, const float* head_w, const float* out, const float* dout, float* dh,
+                 float* dhead_w, float* dhead_b, int64_t m, int32_t n, int32_t n_head, int32_t head_act, void* stream);
+
 /* ---- a18: compositing (segment sums over packed rays) -----------------------------------------
  * Replaces the index_add_ block of NerfRenderer.forward (src/core.py:256-265; the reference's own
  * "TODO: cuda kernel this"):  rgb_ray = sum_k w_k*rgb_k ; opacity = sum_k w_k ;

@@ -1,0 +1,555 @@
+// a15-a17 -- the MLP heads' dense layers on the 5th-generation tensor cores (tcgen05 + TMEM).
+// Reference: MLP / VanillaOpacityDecoder / VanillaColorDecoder / Cobafa trunk, src/models.py:7-28,70-89,
+// executed there as fp32 cuBLAS SGEMMs (allow_tf32 is off) plus separate bias/ReLU kernels.
+//
+// fp32-grade accuracy on TF32 tensor cores: every operand x is split into hi = tf32(x) and
+// lo = tf32(x - hi) while it is staged in shared memory and each product is issued as three
+// tcgen05.mma.kind::tf32 (hi*hi + lo*hi + hi*lo) accumulating in fp32 in TMEM ("3xTF32", ~2^-21 relative
+// per product; the dropped lo*lo term is below fp32 rounding of the sum).
+//
+// One smem image serves every GEMM of fwd and bwd: an "atom" = 128 rows x 32 fp32 (128 B per row) in the
+// canonical 128-byte-swizzle layout (16-byte chunk index XOR row%8).  Read as a K-major operand its rows are
+// the M/N index and its 32 columns are K; read as an MN-major operand its rows are K and its columns are M/N:
+//   forward   Y[m,n]  = act(sum_k X[m,k] W[n,k] + b[n])  A = X atoms (K-major)      B = W atoms (K-major)
+//   dgrad     dX[m,k] = sum_n dY[m,n] W[n,k]             A = dY atoms (K-major)     B = W atoms (MN-major)
+//   wgrad     dW[n,k] = sum_m dY[m,n] X[m,k]             A = dY atoms (MN-major)    B = X atoms (MN-major)
+// so activations/gradients [rows, features] and nn.Linear weights [out, in] are staged exactly as they lie
+// in HBM, with coalesced 128-bit loads, no transposes.
+//
+// Structure (v1, deliberately simple): 128 threads per CTA, persistent over 128-row tiles, two CTAs per SM so
+// one CTA's loads overlap the other's MMAs/epilogue; operands staged by all threads (LDG -> split -> STS),
+// one elected thread issues the MMAs, completion through tcgen05.commit -> mbarrier, accumulator read back
+// with tcgen05.ld (thread == TMEM lane == output row) for the fused bias / ReLU / head epilogue.
+#include "common.cuh"
+
+namespace tnf {
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kAtomBytes = 128 * 128;        // 128 rows x 32 fp32
+constexpr int kMaxKAtoms = 5;                // K <= 160
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, int ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, int ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32-bit, 32 consecutive columns per thread (thread i of warp w reads TMEM lane 32*(w%4)+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor, InstrDescriptor) -------------------
+// shared-memory matrix descriptor, 128-byte swizzle, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// K-major operand: 8-row groups are 1024 B apart (SBO); LBO is ignored for swizzled K-major layouts.
+// k-step kk (8 tf32 = 32 B) advances the start address inside the 128-byte row.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t atom_saddr, int kk) { return smem_desc(atom_saddr + kk * 32, 16, 1024); }
+// MN-major operand: MN blocks of 32 elements are one atom apart (LBO), 8-row K groups 1024 B apart (SBO);
+// k-step kk (8 rows) advances the start address by one 1024-byte group.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t atom_saddr, int kk) { return smem_desc(atom_saddr + kk * 1024, kAtomBytes, 1024); }
+// instruction descriptor: D fp32, A/B tf32, dense
+__device__ __forceinline__ uint32_t instr_desc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- operand staging --------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+}
+// Stage rows [row0, row0+128) x cols [col0, col0+32) of a row-major matrix (leading dimension ld, `rows` x
+// `cols` valid, zero elsewhere) as hi/lo atoms.  ld and col0 multiples of 4 and a 16-byte aligned base.
+// `relu_src`: multiply by (src > 0) of a second matrix with the same indexing (fused ReLU backward).
+__device__ __forceinline__ void stage_atom(const float* __restrict__ g, long long ld, long long row0, long long rows,
+                                           int col0, int cols, uint8_t* hi_atom, uint8_t* lo_atom, int tid,
+                                           float colsum[4] /*optional accumulation of column sums*/, int atom_rows = 128) {
+  const int c = tid & 7;
+  const int r0 = tid >> 3;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(g) & 15u) == 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 16 * i;
+    if (r >= atom_rows) break;
+    const long long row = row0 + r;
+    const int col = col0 + 4 * c;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows && col < cols) {
+      if (col + 3 < cols && vec) {
+        v = __ldg(reinterpret_cast<const float4*>(g + row * ld + col));
+      } else if (col + 3 < cols) {
+        const float* p = g + row * ld + col;
+        v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+      } else {
+        const float* p = g + row * ld + col;
+        v.x = __ldg(p);
+        if (col + 1 < cols) v.y = __ldg(p + 1);
+        if (col + 2 < cols) v.z = __ldg(p + 2);
+      }
+    }
+    if (colsum) { colsum[0] += v.x; colsum[1] += v.y; colsum[2] += v.z; colsum[3] += v.w; }
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    const int off = r * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<float4*>(hi_atom + off) = h;
+    *reinterpret_cast<float4*>(lo_atom + off) = l;
+  }
+}
+
+struct LinArgs {
+  const float* X; long long ldx;   // fwd: input [M,K]        dgrad: dY [M,N]          wgrad: dY [M,N]
+  const float* W;                  // [N,K] row-major (nn.Linear.weight)
+  const float* bias;               // fwd: [N] or null
+  float* Y; long long ldy;         // fwd: output [M,N]       dgrad: dX [M,K] (ldy)    wgrad: unused
+  const float* X2; long long ldx2; // dgrad: activation whose >0 mask gates dX (or null)   wgrad: X [M,K]
+  float* dW; float* db;            // wgrad outputs (accumulated with atomics; caller zeroes)
+  const float* head_w; const float* head_b; float* head_out; int n_head; int head_act;  // fwd: fused small head
+  long long M; int N, K;
+  int relu;
+  int n_tiles;
+};
+
+__device__ __forceinline__ float head_activation(float x, int act) {
+  if (act == 1) return expf(x - 1.f);                 // truncated_exp(x - 1.)  (src/models.py:74)
+  if (act == 2) return 1.f / (1.f + expf(-x));        // sigmoid               (src/models.py:85)
+  return x;
+}
+
+// dynamic smem: [W hi atoms][W lo atoms][A hi][A lo] (+ second operand pair for wgrad), 1024-byte aligned
+template <int MODE>  // 0 fwd, 1 dgrad
+__global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // GEMM view: D[128, ND] += sum over KD of A[128, KD] * B[ND, KD]
+  const int KD = (MODE == 0) ? A.K : A.N;            // contraction length
+  const int ND = (MODE == 0) ? A.N : ((A.K + 15) & ~15);  // output columns (dgrad: K_in padded to 16)
+  const int ka = (KD + 31) >> 5;                     // contraction atoms
+  const int w_atoms = (A.K + 31) >> 5;               // weight image: N rows x K cols -> atoms along K
+  const int w_rows = (A.N + 15) & ~15;               // rows staged per weight atom
+  const int w_stride = ((w_rows * 128) + 1023) & ~1023;  // bytes between weight atoms (1024-aligned)
+  uint8_t* w_hi = smem;
+  uint8_t* w_lo = smem + w_atoms * w_stride;
+  uint8_t* a_hi = smem + 2 * w_atoms * w_stride;
+  uint8_t* a_lo = a_hi + kAtomBytes;
+
+  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  const int tmem_cols = ND <= 32 ? 32 : (ND <= 64 ? 64 : (ND <= 128 ? 128 : 256));
+  if (warp == 0) tmem_alloc(&s_tmem, tmem_cols);
+  // weights: N rows (<=128) x K columns, staged once per CTA
+  for (int j = 0; j < w_atoms; ++j)
+    stage_atom(A.W, A.K, 0, A.N, 32 * j, A.K, w_hi + j * w_stride, w_lo + j * w_stride, tid, nullptr, w_rows);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = s_tmem;
+  const uint32_t idesc = instr_desc(128, ND, false, MODE == 1);
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+    const long long row0 = (long long)tile * 128;
+    for (int j = 0; j < ka; ++j) {
+      stage_atom(A.X, A.ldx, row0, A.M, 32 * j, KD, a_hi, a_lo, tid, nullptr);
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t aa = (pass == 1) ? al : ah;
+          const uint8_t* wb = (pass == 2) ? w_lo : w_hi;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint64_t bd;
+            if (MODE == 0) bd = desc_kmajor(smem_u32(wb + j * w_stride), kk);
+            else           bd = smem_desc(smem_u32(wb) + j * 4096 /*32 rows of n_out*/ + kk * 1024, w_stride, 1024);
+            mma_tf32(tmem_d, desc_kmajor(aa, kk), bd, idesc, (j | pass | kk) != 0);
+          }
+        }
+        mma_commit(&s_bar);
+      }
+      mbar_wait(&s_bar, phase);   // MMAs of this atom done: A buffers reusable, (last atom) D complete
+      phase ^= 1;
+    }
+    tc_fence_after();
+    // epilogue: thread = TMEM lane = row
+    const long long row = row0 + warp * 32 + lane;
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+    float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c0 = 0; c0 < ND; c0 += 32) {
+      float v[32];
+      tmem_ld32(taddr + c0, v);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float y = v[i] + (A.bias ? __ldg(A.bias + c0 + i) : 0.f);
+          if (A.relu) y = fmaxf(y, 0.f);
+          v[i] = y;
+        }
+        if (A.n_head > 0) {
+          for (int o = 0; o < A.n_head; ++o) {
+            float acc = head_acc[o];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc = __fmaf_rn(v[i], __ldg(A.head_w + o * A.N + c0 + i), acc);
+            head_acc[o] = acc;
+          }
+        }
+        if (row < A.M && A.Y) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (c0 + i < A.N)
+              *reinterpret_cast<float4*>(A.Y + row * A.ldy + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      } else {
+        if (row < A.M) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int col = c0 + i;
+            if (col < A.K) {
+              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (A.X2) {  // ReLU backward of the layer that produced this layer's input
+                const float4 xin = __ldg(reinterpret_cast<const float4*>(A.X2 + row * A.ldx2 + col));
+                o.x = xin.x > 0.f ? o.x : 0.f; o.y = xin.y > 0.f ? o.y : 0.f;
+                o.z = xin.z > 0.f ? o.z : 0.f; o.w = xin.w > 0.f ? o.w : 0.f;
+              }
+              if (col + 3 < A.K) {
+                *reinterpret_cast<float4*>(A.Y + row * A.ldy + col) = o;
+              } else {
+                float* p = A.Y + row * A.ldy + col;
+                p[0] = o.x;
+                if (col + 1 < A.K) p[1] = o.y;
+                if (col + 2 < A.K) p[2] = o.z;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (MODE == 0 && A.n_head > 0 && row < A.M)
+      for (int o = 0; o < A.n_head; ++o)
+        A.head_out[row * A.n_head + o] = head_activation(head_acc[o] + __ldg(A.head_b + o), A.head_act);
+    tc_fence_before();
+    __syncthreads();   // every warp has drained its TMEM lanes before the next tile overwrites D
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// wgrad: dW[n,k] += sum_m dY[m,n] X[m,k] ; db[n] += sum_m dY[m,n].  D[N_out, 32] per X atom lives in TMEM for the
+// whole kernel (columns 32*j.. of atom j) and is flushed with atomics once per CTA.
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_db[128];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ny = (A.N + 31) >> 5;   // dY atoms (N_out / 32)
+  const int kx = (A.K + 31) >> 5;   // X atoms
+  uint8_t* y_hi = smem;
+  uint8_t* y_lo = smem + ny * kAtomBytes;
+  uint8_t* x_hi = smem + 2 * ny * kAtomBytes;
+  uint8_t* x_lo = x_hi + kAtomBytes;
+  const int MM = (A.N <= 64) ? 64 : 128;  // UMMA M = N_out
+  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  const int ncol = kx * 32;
+  const int tmem_cols = ncol <= 32 ? 32 : (ncol <= 64 ? 64 : (ncol <= 128 ? 128 : 256));
+  if (warp == 0) tmem_alloc(&s_tmem, tmem_cols);
+  if (tid < 128) s_db[tid] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = s_tmem;
+  const uint32_t idesc = instr_desc(MM, 32, true, true);
+  uint32_t phase = 0;
+  bool first = true;
+  float colsum[kMaxKAtoms - 1][4];
+#pragma unroll
+  for (int a = 0; a < kMaxKAtoms - 1; ++a) colsum[a][0] = colsum[a][1] = colsum[a][2] = colsum[a][3] = 0.f;
+
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+    const long long row0 = (long long)tile * 128;
+#pragma unroll
+    for (int a = 0; a < kMaxKAtoms - 1; ++a)
+      if (a < ny) stage_atom(A.X, A.ldx, row0, A.M, 32 * a, A.N, y_hi + a * kAtomBytes, y_lo + a * kAtomBytes, tid, colsum[a]);
+    for (int j = 0; j < kx; ++j) {
+      stage_atom(A.X2, A.ldx2, row0, A.M, 32 * j, A.K, x_hi, x_lo, tid, nullptr);
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t yh = smem_u32(y_hi), yl = smem_u32(y_lo), xh = smem_u32(x_hi), xl = smem_u32(x_lo);
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ya = (pass == 1) ? yl : yh;
+          const uint32_t xa = (pass == 2) ? xl : xh;
+#pragma unroll 1
+          for (int kk = 0; kk < 16; ++kk)  // 128 samples = 16 k-steps of 8 rows
+            mma_tf32(tmem_d + 32 * j, desc_mnmajor(ya, kk), desc_mnmajor(xa, kk), idesc, !(first && pass == 0 && kk == 0));
+        }
+        mma_commit(&s_bar);
+      }
+      mbar_wait(&s_bar, phase);
+      phase ^= 1;
+    }
+    first = false;
+  }
+  // bias gradient: column sums of dY gathered while staging
+  if (A.db) {
+#pragma unroll
+    for (int a = 0; a < kMaxKAtoms - 1; ++a)
+      if (a < ny)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) atomicAdd(&s_db[32 * a + 4 * (tid & 7) + q], colsum[a][q]);
+  }
+  tc_fence_after();
+  __syncthreads();
+  if (A.db && tid < A.N) atomicAdd(A.db + tid, s_db[tid]);
+  if (!first) {
+    // D rows = output features: M=128 -> lane == row; M=64 -> row m sits in lane 32*(m/16) + m%16
+    int n_out;
+    bool active;
+    if (MM == 128) { n_out = warp * 32 + lane; active = true; }
+    else { n_out = warp * 16 + lane; active = lane < 16; }
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < ncol; c0 += 32) {
+      float v[32];
+      tmem_ld32(taddr + c0, v);
+      if (active && n_out < A.N) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < A.K) atomicAdd(A.dW + (long long)n_out * A.K + c0 + i, v[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// Backward of a fused head (n_head <= 4 outputs on top of a ReLU hidden layer H[M,N]):
+//   dpre[o] = dOut[o] * act'(.) ; dH[m,j] = (H[m,j] > 0) * sum_o dpre[o] * Wh[o,j] ; dWh[o,j] += dpre[o]*H[m,j] ; dbh[o] += dpre[o]
+// act: 1 = truncated_exp(x-1) (backward uses exp(clamp(x-1,-15,15)), src/models.py:52-53; out = exp(x-1) is given),
+//      2 = sigmoid (out given).  One warp handles 32 rows at a time; lanes own columns j, j+32 (+64, +96).
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ H, long long ldh, const float* __restrict__ Wh,
+                                                       const float* __restrict__ out, const float* __restrict__ dout,
+                                                       float* __restrict__ dH, float* __restrict__ dWh, float* __restrict__ dbh,
+                                                       long long M, int N, int n_head, int act) {
+  __shared__ float s_dw[4 * 128];
+  __shared__ float s_dbh[4];
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 4 * 128; i += 256) s_dw[i] = 0.f;
+  if (tid < 4) s_dbh[tid] = 0.f;
+  __syncthreads();
+  const int warps_total = gridDim.x * 8;
+  const int wid = blockIdx.x * 8 + (tid >> 5);
+  float wreg[4][4];  // Wh[o][lane + 32*q]
+  float dwacc[4][4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = lane + 32 * q;
+      wreg[o][q] = (o < n_head && j < N) ? __ldg(Wh + o * N + j) : 0.f;
+      dwacc[o][q] = 0.f;
+    }
+  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long m = wid; m < M; m += warps_total) {
+    float dpre[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float d = 0.f;
+      if (o < n_head) {
+        const float y = __ldg(out + m * n_head + o), g = __ldg(dout + m * n_head + o);
+        if (act == 1) {
+          // y = exp(x-1); backward multiplies by exp(clamp(x-1, -15, 15))
+          const float xm1 = logf(y);
+          d = g * ((xm1 > 15.f) ? expf(15.f) : ((xm1 < -15.f) ? expf(-15.f) : y));
+        } else if (act == 2) {
+          d = g * y * (1.f - y);
+        } else {
+          d = g;
+        }
+      }
+      dpre[o] = d;
+      dbacc[o] += d;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = lane + 32 * q;
+      if (j < N) {
+        const float h = __ldg(H + m * ldh + j);
+        float acc = 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          acc = __fmaf_rn(dpre[o], wreg[o][q], acc);
+          dwacc[o][q] = __fmaf_rn(dpre[o], h, dwacc[o][q]);
+        }
+        dH[m * ldh + j] = h > 0.f ? acc : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) atomicAdd(&s_dw[o * 128 + lane + 32 * q], dwacc[o][q]);
+    if (lane == 0) atomicAdd(&s_dbh[o], dbacc[o]);
+  }
+  __syncthreads();
+  for (int i = tid; i < n_head * N; i += 256) atomicAdd(dWh + i, s_dw[(i / N) * 128 + (i % N)]);
+  if (tid < n_head) atomicAdd(dbh + tid, s_dbh[tid]);
+}
+
+int check_lin(long long M, int N, int K) {
+  TNF_REQUIRE(M >= 0, "negative M");
+  TNF_REQUIRE(N >= 8 && N <= 128 && N % 8 == 0, "out_features must be a multiple of 8 in [8,128] (got %d)", N);
+  TNF_REQUIRE(K >= 1 && K <= 32 * kMaxKAtoms, "in_features must be in [1,%d] (got %d)", 32 * kMaxKAtoms, K);
+  return TNF_OK;
+}
+bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename Kern>
+int launch_lin(Kern kern, const LinArgs& A, size_t smem, cudaStream_t st, const char* name) {
+  static thread_local const void* configured[8] = {nullptr};
+  bool done = false;
+  for (auto c : configured) done |= (c == (const void*)kern);
+  if (!done) {
+    TNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (auto& c : configured) if (!c) { c = (const void*)kern; break; }
+  }
+  int grid = A.n_tiles < 2 * sm_count() ? A.n_tiles : 2 * sm_count();
+  kern<<<grid, kThreads, smem, st>>>(A);
+  TNF_LAUNCH_CHECK(name);
+  return TNF_OK;
+}
+
+}  // namespace
+}  // namespace tnf
+
+extern "C" int tnf_linear_fwd(const float* x, int64_t ldx, const float* weight, const float* bias, float* y, int64_t ldy,
+                              int64_t m, int32_t n, int32_t k, int32_t relu, const float* head_w, const float* head_b,
+                              float* head_out, int32_t n_head, int32_t head_act, void* stream) {
+  using namespace tnf;
+  int rc = check_lin(m, n, k);
+  if (rc != TNF_OK || m == 0) return rc;
+  TNF_REQUIRE(x && weight && (y || n_head > 0), "null pointer");
+  TNF_REQUIRE(n % 32 == 0, "forward needs out_features to be a multiple of 32");
+  TNF_REQUIRE(al16(x) && ldx % 4 == 0 && (!y || (al16(y) && ldy % 4 == 0)), "x/y must be 16-byte aligned with ld %% 4 == 0");
+  TNF_REQUIRE(n_head >= 0 && n_head <= 4 && (n_head == 0 || (head_w && head_b && head_out)), "bad head");
+  LinArgs A{};
+  A.X = x; A.ldx = ldx; A.W = weight; A.bias = bias; A.Y = y; A.ldy = ldy; A.M = m; A.N = n; A.K = k; A.relu = relu;
+  A.head_w = head_w; A.head_b = head_b; A.head_out = head_out; A.n_head = n_head; A.head_act = head_act;
+  A.n_tiles = (int)ceil_div(m, 128);
+  const size_t smem = (size_t)(2 * ((k + 31) / 32)) * ((((n + 15) & ~15) * 128 + 1023) & ~1023) + 2 * kAtomBytes + 1024;
+  return launch_lin(linear_kernel<0>, A, smem, static_cast<cudaStream_t>(stream), "linear_fwd_kernel");
+}
+
+extern "C" int tnf_linear_bwd_data(const float* dy, int64_t lddy, const float* weight, float* dx, int64_t lddx,
+                                   const float* relu_src, int64_t ldrs, int64_t m, int32_t n, int32_t k, void* stream) {
+  using namespace tnf;
+  int rc = check_lin(m, n, k);
+  if (rc != TNF_OK || m == 0) return rc;
+  TNF_REQUIRE(dy && weight && dx, "null pointer");
+  TNF_REQUIRE(n % 32 == 0, "dgrad needs out_features to be a multiple of 32");
+  TNF_REQUIRE(al16(dy) && lddy % 4 == 0 && al16(dx) && lddx % 4 == 0, "dy/dx must be 16-byte aligned with ld %% 4 == 0");
+  TNF_REQUIRE(!relu_src || (al16(relu_src) && ldrs % 4 == 0), "relu_src must be 16-byte aligned with ld %% 4 == 0");
+  LinArgs A{};
+  A.X = dy; A.ldx = lddy; A.W = weight; A.Y = dx; A.ldy = lddx; A.X2 = relu_src; A.ldx2 = ldrs; A.M = m; A.N = n; A.K = k;
+  A.n_tiles = (int)ceil_div(m, 128);
+  const size_t smem = (size_t)(2 * ((k + 31) / 32)) * ((((n + 15) & ~15) * 128 + 1023) & ~1023) + 2 * kAtomBytes + 1024;
+  return launch_lin(linear_kernel<1>, A, smem, static_cast<cudaStream_t>(stream), "linear_dgrad_kernel");
+}
+
+extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dweight, float* dbias,
+                                     int64_t m, int32_t n, int32_t k, void* stream) {
+  using namespace tnf;
+  int rc = check_lin(m, n, k);
+  if (rc != TNF_OK || m == 0) return rc;
+  TNF_REQUIRE(dy && x && dweight, "null pointer");
+  TNF_REQUIRE(n % 32 == 0 && n <= 128, "wgrad needs out_features in {32,64,96,128}");
+  TNF_REQUIRE(al16(dy) && lddy % 4 == 0 && al16(x) && ldx % 4 == 0, "dy/x must be 16-byte aligned with ld %% 4 == 0");
+  LinArgs A{};
+  A.X = dy; A.ldx = lddy; A.X2 = x; A.ldx2 = ldx; A.dW = dweight; A.db = dbias; A.M = m; A.N = n; A.K = k;
+  A.n_tiles = (int)ceil_div(m, 128);
+  const size_t smem = (size_t)(2 * ((n + 31) / 32) + 2) * kAtomBytes + 1024;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static thread_local bool configured = false;
+  if (!configured) {
+    TNF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const int grid = A.n_tiles < 2 * sm_count() ? A.n_tiles : 2 * sm_count();
+  wgrad_kernel<<<grid, kThreads, smem, st>>>(A);
+  TNF_LAUNCH_CHECK("linear_wgrad_kernel");
+  return TNF_OK;
+}
+
+extern "C" int tnf_head_bwd(const float* h, int64_t ldh, const float* head_w, const float* out, const float* dout, float* dh,
+                            float* dhead_w, float* dhead_b, int64_t m, int32_t n, int32_t n_head, int32_t head_act,
+                            void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(m >= 0 && n >= 1 && n <= 128 && n_head >= 1 && n_head <= 4, "bad head shape");
+  if (m == 0) return TNF_OK;
+  TNF_REQUIRE(h && head_w && out && dout && dh && dhead_w && dhead_b, "null pointer");
+  const int grid = (int)(ceil_div(m, 8 * 16) < 4 * sm_count() ? ceil_div(m, 8 * 16) : 4 * sm_count());
+  head_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ldh, head_w, out, dout, dh, dhead_w, dhead_b, m, n,
+                                                                         n_head, head_act);
+  TNF_LAUNCH_CHECK("head_bwd_kernel");
+  return TNF_OK;
+}

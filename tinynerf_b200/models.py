@@ -20,7 +20,12 @@ from typing import Any, Callable, List, Tuple, cast
 import torch
 from torch.autograd import Function
 
-from . import _lib
+import os
+
+from . import _lib, mlp_ops
+
+# TNF_MLP=torch keeps the dense layers on cuBLAS fp32 (A/B switch; default: tcgen05 3xTF32 kernels on CUDA)
+_USE_TC_MLP = os.environ.get("TNF_MLP", "tcgen05") != "torch"
 
 
 class MLP(torch.nn.Module):
@@ -36,12 +41,21 @@ class MLP(torch.nn.Module):
             blocks.append(Seq(Lin(hidden_features, hidden_features), activation()))
         blocks.append(Lin(hidden_features, hidden_features if out_features is None else out_features))
         self.net = Seq(*blocks)
+        self._relu = activation is torch.nn.ReLU
 
     def linears(self) -> List[torch.nn.Linear]:
         """The Linear layers in evaluation order (used by the fused MLP kernels)."""
         return [m for m in self.net.modules() if isinstance(m, torch.nn.Linear)]
 
-    def forward(self, x: torch.Tensor):
+    def fused_ok(self, x: torch.Tensor) -> bool:
+        return _USE_TC_MLP and self._relu and mlp_ops.supported(self.linears(), x)
+
+    def forward(self, x: torch.Tensor, head_act: int = 0):
+        """head_act != 0 asks for the decoder's output activation fused into the last layer (tensor-core path
+        only; see mlp_ops)."""
+        if self.fused_ok(x):
+            return mlp_ops.fused_mlp(x, self.linears(), head_act)
+        assert head_act == 0
         return self.net(x)
 
 
@@ -96,6 +110,8 @@ class VanillaOpacityDecoder(torch.nn.Module):
         self.activation = lambda x: truncated_exp(x - 1.0)
 
     def forward(self, features: torch.Tensor) -> torch.Tensor:
+        if self.net.fused_ok(features):
+            return self.net(features, head_act=1)  # truncated_exp(x - 1.) fused into the layer epilogue
         return self.activation(self.net(features))
 
 
@@ -109,6 +125,8 @@ class VanillaColorDecoder(torch.nn.Module):
 
     def forward(self, features: torch.Tensor, rays_d: torch.Tensor) -> torch.Tensor:
         x = torch.cat([self.pe(rays_d), rays_d, features], -1)
+        if self.net.fused_ok(x):
+            return self.net(x, head_act=2)  # sigmoid fused into the layer epilogue
         return self.activation(self.net(x))
 
 
