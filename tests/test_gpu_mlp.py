@@ -94,8 +94,8 @@ def test_fused_heads_forward_backward_vs_torch(m):
     sig64, col64, trunk64 = [__import__("copy").deepcopy(mm).double() for mm in (sig, col, trunk)]
     f64 = f.detach().double().requires_grad_(True)
     z64 = z.detach().double().requires_grad_(True)
-    o64 = [sig64.activation(sig64.net.net(f64)),
-           col64.activation(col64.net.net(torch.cat([col64.pe(d.double()), d.double(), f64], -1))), trunk64.net(z64)]
+    o64 = [torch.exp(sig64.net.net(f64) - 1.0),
+           torch.sigmoid(col64.net.net(torch.cat([col64.pe(d.double()), d.double(), f64], -1))), trunk64.net(z64)]
     for a, b in zip(outs, o64):
         assert torch.allclose(a.double(), b, rtol=1e-5, atol=1e-6), (a.double() - b).abs().max()
     sum((o * go.double()).sum() for o, go in zip(o64, gos)).backward()

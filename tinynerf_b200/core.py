@@ -290,15 +290,10 @@ class RayProvider:
         return p
 
     @torch.no_grad()
-    def __call__(self, rays_o: torch.Tensor, rays_d: torch.Tensor, training: bool,
-                 noise: torch.Tensor | None = None, info_offset: int = 0):
-        """-> (packed_samples [N,7], packing_info [R,2] int32), same contents and order as the
-        reference (src/core.py:165-188).  packed_samples carries two extra attributes used by
-        NerfRenderer: `_tnf_steps` (contiguous copy of column 6) and packing_info `_tnf_partition`.
-
-        noise: optional [R,S] jitter in [0,1); default in training is torch.rand on the rays' device,
-        which consumes torch's CUDA generator exactly like the reference's rand_like (src/core.py:173).
-        """
+    def count(self, rays_o: torch.Tensor, rays_d: torch.Tensor, training: bool, noise: torch.Tensor | None = None,
+              info_offset: int = 0):
+        """First half of __call__: evaluate the sample lattice, return a handle holding the keep-mask bitfield,
+        the packing info [R,2] and the packed-sample total (device int64) -- no host sync."""
         _lib.load()
         _lib.require_cuda(rays_o, "rays_o")
         _lib.require_cuda(rays_d, "rays_d")
@@ -319,19 +314,43 @@ class RayProvider:
             mask_bits = torch.empty(max(R, 1) * words, dtype=torch.int32, device=dev)
             info = torch.empty(R, 2, dtype=torch.int32, device=dev)
             n_dev = torch.empty(1, dtype=torch.int64, device=dev)
-            stream = _lib.stream_ptr()
             _lib.call("tnf_march_count", C.byref(p), rays_o.data_ptr(), rays_d.data_ptr(), R, info_offset,
-                      mask_bits.data_ptr(), info.data_ptr(), n_dev.data_ptr(), stream,
+                      mask_bits.data_ptr(), info.data_ptr(), n_dev.data_ptr(), _lib.stream_ptr(),
                       nbytes=24 * R + 8 * R + 4 * R * words)
-            n = int(n_dev.item())  # the one host sync of the provider (the reference has two)
+        return dict(p=p, rays_o=rays_o, rays_d=rays_d, noise=noise, mask_bits=mask_bits, info=info, n_dev=n_dev,
+                    info_offset=info_offset, words=words)
+
+    @torch.no_grad()
+    def pack(self, h, n_rays: int | None = None, n: int | None = None):
+        """Second half: write the packed samples of the first `n_rays` rays of a count() handle (`n` = their
+        packed-sample total; read from the device when omitted)."""
+        dev = h["rays_o"].device
+        R = h["rays_o"].size(0) if n_rays is None else n_rays
+        if n is None:
+            n = int(h["n_dev"].item())
+        info = h["info"][:R]
+        with torch.cuda.device(dev):
             packed = torch.empty(n, 7, device=dev)
             steps = torch.empty(n, device=dev)
-            _lib.call("tnf_march_pack", C.byref(p), rays_o.data_ptr(), rays_d.data_ptr(), R, info_offset,
-                      mask_bits.data_ptr(), info.data_ptr(), packed.data_ptr(), steps.data_ptr(), None, n, stream,
-                      nbytes=24 * R + 8 * R + 4 * R * words + 32 * n)
+            _lib.call("tnf_march_pack", C.byref(h["p"]), h["rays_o"].data_ptr(), h["rays_d"].data_ptr(), R,
+                      h["info_offset"], h["mask_bits"].data_ptr(), info.data_ptr(), packed.data_ptr(), steps.data_ptr(),
+                      None, n, _lib.stream_ptr(), nbytes=24 * R + 8 * R + 4 * R * h["words"] + 32 * n)
         packed._tnf_steps = steps
-        info._tnf_partition = info_offset == 0
+        info._tnf_partition = h["info_offset"] == 0
         return packed, info
+
+    @torch.no_grad()
+    def __call__(self, rays_o: torch.Tensor, rays_d: torch.Tensor, training: bool,
+                 noise: torch.Tensor | None = None, info_offset: int = 0):
+        """-> (packed_samples [N,7], packing_info [R,2] int32), same contents and order as the
+        reference (src/core.py:165-188).  packed_samples carries two extra attributes used by
+        NerfRenderer: `_tnf_steps` (contiguous copy of column 6) and packing_info `_tnf_partition`.
+
+        noise: optional [R,S] jitter in [0,1); default in training is torch.rand on the rays' device,
+        which consumes torch's CUDA generator exactly like the reference's rand_like (src/core.py:173).
+        One host sync (the packed-sample count); the reference has two.
+        """
+        return self.pack(self.count(rays_o, rays_d, training, noise, info_offset))
 
 
 # ------------------------------------------------------------------------------------------------

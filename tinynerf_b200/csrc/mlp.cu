@@ -87,17 +87,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
 }
 
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor, InstrDescriptor) -------------------
-// shared-memory matrix descriptor, 128-byte swizzle, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor, version 1 (Blackwell); layout_type 2 = SWIZZLE_128B (16-byte chunks XOR row%8),
+// 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4) -- the only layout available to MN-major tf32 operands
+// (cutlass/gemm/collective/builders/sm100_common.inl:92).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
+         (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 // K-major operand: 8-row groups are 1024 B apart (SBO); LBO is ignored for swizzled K-major layouts.
 // k-step kk (8 tf32 = 32 B) advances the start address inside the 128-byte row.
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t atom_saddr, int kk) { return smem_desc(atom_saddr + kk * 32, 16, 1024); }
-// MN-major operand: MN blocks of 32 elements are one atom apart (LBO), 8-row K groups 1024 B apart (SBO);
-// k-step kk (8 rows) advances the start address by one 1024-byte group.
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t atom_saddr, int kk) { return smem_desc(atom_saddr + kk * 1024, kAtomBytes, 1024); }
+// MN-major tf32 operand (SWIZZLE_128B_BASE32B): MN blocks of 32 elements are `lbo` bytes apart, 4-row K groups
+// 512 B apart (SBO); k-step kk (8 rows) advances the start address by 1024 bytes.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t atom_saddr, int kk, uint32_t lbo = kAtomBytes) {
+  return smem_desc(atom_saddr + kk * 1024, lbo, 512, 1);
+}
 // instruction descriptor: D fp32, A/B tf32, dense
 __device__ __forceinline__ uint32_t instr_desc(int M, int N, bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -114,7 +118,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // `relu_src`: multiply by (src > 0) of a second matrix with the same indexing (fused ReLU backward).
 __device__ __forceinline__ void stage_atom(const float* __restrict__ g, long long ld, long long row0, long long rows,
                                            int col0, int cols, uint8_t* hi_atom, uint8_t* lo_atom, int tid,
-                                           float colsum[4] /*optional accumulation of column sums*/, int atom_rows = 128) {
+                                           float colsum[4] /*optional accumulation of column sums*/, int atom_rows = 128,
+                                           bool mn32 = false /*SWIZZLE_128B_BASE32B image for MN-major reads*/) {
   const int c = tid & 7;
   const int r0 = tid >> 3;
   const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(g) & 15u) == 0);
@@ -141,7 +146,7 @@ __device__ __forceinline__ void stage_atom(const float* __restrict__ g, long lon
     if (colsum) { colsum[0] += v.x; colsum[1] += v.y; colsum[2] += v.z; colsum[3] += v.w; }
     float4 h, l;
     split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    const int off = r * 128 + ((c ^ (r & 7)) << 4);
+    const int off = mn32 ? (r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4))) : (r * 128 + ((c ^ (r & 7)) << 4));
     *reinterpret_cast<float4*>(hi_atom + off) = h;
     *reinterpret_cast<float4*>(lo_atom + off) = l;
   }
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
   if (warp == 0) tmem_alloc(&s_tmem, tmem_cols);
   // weights: N rows (<=128) x K columns, staged once per CTA
   for (int j = 0; j < w_atoms; ++j)
-    stage_atom(A.W, A.K, 0, A.N, 32 * j, A.K, w_hi + j * w_stride, w_lo + j * w_stride, tid, nullptr, w_rows);
+    stage_atom(A.W, A.K, 0, A.N, 32 * j, A.K, w_hi + j * w_stride, w_lo + j * w_stride, tid, nullptr, w_rows, MODE == 1);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
           for (int kk = 0; kk < 4; ++kk) {
             uint64_t bd;
             if (MODE == 0) bd = desc_kmajor(smem_u32(wb + j * w_stride), kk);
-            else           bd = smem_desc(smem_u32(wb) + j * 4096 /*32 rows of n_out*/ + kk * 1024, w_stride, 1024);
+            else           bd = desc_mnmajor(smem_u32(wb) + j * 4096 /*32 rows of n_out*/, kk, w_stride);
             mma_tf32(tmem_d, desc_kmajor(aa, kk), bd, idesc, (j | pass | kk) != 0);
           }
         }
@@ -327,9 +332,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
     const long long row0 = (long long)tile * 128;
 #pragma unroll
     for (int a = 0; a < kMaxKAtoms - 1; ++a)
-      if (a < ny) stage_atom(A.X, A.ldx, row0, A.M, 32 * a, A.N, y_hi + a * kAtomBytes, y_lo + a * kAtomBytes, tid, colsum[a]);
+      if (a < ny) stage_atom(A.X, A.ldx, row0, A.M, 32 * a, A.N, y_hi + a * kAtomBytes, y_lo + a * kAtomBytes, tid, colsum[a], 128, true);
     for (int j = 0; j < kx; ++j) {
-      stage_atom(A.X2, A.ldx2, row0, A.M, 32 * j, A.K, x_hi, x_lo, tid, nullptr);
+      stage_atom(A.X2, A.ldx2, row0, A.M, 32 * j, A.K, x_hi, x_lo, tid, nullptr, 128, true);
       fence_async_smem();
       __syncthreads();
       if (tid == 0) {

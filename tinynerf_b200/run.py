@@ -85,6 +85,14 @@ class RayStore:
         self._perm = perm[self.rank::self.world]
         self._pos = 0
 
+    def rewind(self, n_rays: int) -> None:
+        """Give back the last `n_rays` rays handed out by next() (speculatively marched, not used)."""
+        self._pos -= n_rays
+        assert self._pos >= 0
+
+    def remaining(self) -> int:
+        return 0 if self._perm is None else self._perm.numel() - self._pos
+
     def next(self, batch: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         if self._perm is None or self._pos + batch > self._perm.numel():
             self._reshuffle()
@@ -111,6 +119,7 @@ class TrainConfig:
     scene_scale: float = 1.0            # RaysDataset.scene_scale (unbounded marcher range)
     bg_color: Tuple[float, float, float] | None = (1.0, 1.0, 1.0)
     grad_scale: float = 2.0 ** 10       # GradScaler(2**10) that is never unscaled (src/run.py:201,259)
+    accumulate: str = "batched"         # "sequential" = the reference's chunk-by-chunk loop (one sync per chunk)
     occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
     seed: int = 0
 
@@ -161,11 +170,19 @@ class Trainer:
             self.optimizer, milestones=[s // 2, s * 3 // 4, s * 5 // 6, s * 9 // 10], gamma=0.33)
         self.tv_reg_alpha, self.l1_reg_alpha = 0.0001, 0.0
         self.train_step = 0
+        self._chunks_guess = 0.0
         self.last: Dict[str, float] = {}
 
     # ---- a11: dynamic batch accumulator (src/run.py:215-244) -----------------------------------
     @torch.no_grad()
     def next_batch(self):
+        if self.cfg.accumulate == "sequential":
+            return self._next_batch_sequential()
+        return self._next_batch_batched()
+
+    @torch.no_grad()
+    def _next_batch_sequential(self):
+        """The reference's loop verbatim: one provider call (and host sync) per chunk of batch_size rays."""
         target = self.cfg.batch_size * self.cfg.n_samples
         current, projected, k = 0, 0, 0
         acc_s, acc_i, acc_rgb, acc_steps = [], [], [], []
@@ -186,6 +203,60 @@ class Trainer:
         info = torch.cat(acc_i, 0)
         info._tnf_partition = True  # consecutive batches were packed at consecutive offsets
         return packed, torch.cat(acc_rgb, 0), info
+
+    @torch.no_grad()
+    def _next_batch_batched(self):
+        """Same rays, same jitter stream, same packed output as the sequential loop, but the lattice of several
+        chunks is marched in ONE launch and the chunk count k is then chosen on the host by the reference's rule
+        (`int(cur*(1+1/k)) >= target`) from the per-chunk totals: one host sync per step instead of one per chunk.
+        Chunks marched speculatively beyond k are handed back (rays rewound, generator offset restored)."""
+        B, S = self.cfg.batch_size, self.cfg.n_samples
+        target = B * S
+        dev = self.device
+        gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+        current, k_done = 0, 0
+        parts = []
+        while True:
+            K = max(1, int(self._chunks_guess) + 1)
+            K = min(K, max(1, self.store.remaining() // B)) if self.store.remaining() >= B else K
+            rays_o, rays_d, rgbs = self.store.next(K * B)
+            noise = torch.empty(K * B, S, device=dev)
+            offsets = []
+            for i in range(K):  # chunk-wise draws: the same generator consumption as the reference's rand_like per chunk
+                torch.rand(B, S, out=noise[i * B:(i + 1) * B])
+                offsets.append(gen.get_offset())
+            h = self.ray_provider.count(rays_o, rays_d, True, noise, info_offset=current)
+            ends = (h["info"][B - 1::B, 0].long() + h["info"][B - 1::B, 1].long()).tolist()  # the one host sync
+            k_use = None
+            for i, e in enumerate(ends):
+                k_tot = k_done + i + 1
+                if int(e * (1 + 1 / k_tot)) >= target:
+                    k_use = i + 1
+                    break
+            used = K if k_use is None else k_use
+            n_here = ends[used - 1] - current
+            packed, info = self.ray_provider.pack(h, used * B, n_here)
+            parts.append((packed, info, rgbs[:used * B]))
+            current = ends[used - 1]
+            k_done += used
+            if k_use is not None:
+                if used < K:
+                    self.store.rewind((K - used) * B)
+                    gen.set_offset(offsets[used - 1])
+                break
+            self._chunks_guess = max(self._chunks_guess, k_done) * 1.5
+            if k_done > 4096:
+                raise RuntimeError("occupancy grid rejects every sample: cannot fill a batch")
+        self._chunks_guess = 0.5 * self._chunks_guess + 0.5 * k_done if self._chunks_guess else float(k_done)
+        if len(parts) == 1:
+            packed, info, rgb = parts[0]
+        else:
+            packed = torch.cat([p[0] for p in parts], 0)
+            packed._tnf_steps = torch.cat([p[0]._tnf_steps for p in parts], 0)
+            info = torch.cat([p[1] for p in parts], 0)
+            rgb = torch.cat([p[2] for p in parts], 0)
+        info._tnf_partition = True
+        return packed, rgb, info
 
     # ---- occupancy update, sharded by depth slice across ranks ----------------------------------
     @torch.no_grad()
