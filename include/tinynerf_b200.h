@@ -209,7 +209,9 @@ int tnf_head_bwd(const float* h, int64_t ldh, const float* head_w, const float* 
  * Replaces the index_add_ block of NerfRenderer.forward (src/core.py:256-265; the reference's own
  * "TODO: cuda kernel this"):  rgb_ray = sum_k w_k*rgb_k ; opacity = sum_k w_k ;
  * out = rgb_ray + bg*(1-opacity) when bg != NULL ([host] 3 floats).
- * Backward: grad_rgb[k] = w_k*go[ray] ; grad_w[k] = <rgb_k, go[ray]> - <bg, go[ray]>.
+ * Colours are defined only where w_k > 0 (the reference evaluates the colour head on that subset and leaves 0
+ * elsewhere, src/core.py:243-250); rgbs[k] is ignored where w_k <= 0, so callers may pass a dense evaluation.
+ * Backward: grad_rgb[k] = w_k*go[ray] ; grad_w[k] = [w_k > 0] <rgb_k, go[ray]> - <bg, go[ray]>.
  */
 int tnf_composite_fwd(const float* weights, const float* rgbs, const int32_t* info, int64_t n_samples,
                       int64_t n_rays, const float* bg, float* out_rgb, float* out_opacity, void* stream);

@@ -69,7 +69,7 @@ def test_heads_match_reference_golden(golden):
     assert torch.allclose(col(f, d).cpu(), g["rgb"], rtol=1e-5, atol=1e-7)
 
 
-def _safe_rows(mod64, x64, margin=1e-4):
+def _safe_rows(mod64, x64, margin=1e-5):
     """Rows whose hidden pre-activations all stay `margin` away from 0 in the fp64 reference.  A ReLU whose
     input is within rounding distance of 0 may switch on/off between any two correct fp32 evaluations (cuBLAS
     vs these kernels vs fp64), which changes that row's gradient by O(1/width): such rows are excluded by
@@ -102,7 +102,7 @@ def test_fused_heads_forward_backward_vs_torch(m):
     xcol64 = torch.cat([col64.pe(d.double()), d.double(), f64], -1)
     o64 = [torch.exp(sig64.net.net(f64) - 1.0), torch.sigmoid(col64.net.net(xcol64)), trunk64.net(z64)]
     safes = [_safe_rows(sig64.net, f64.detach()), _safe_rows(col64.net, xcol64.detach()), _safe_rows(trunk64, z64.detach())]
-    assert all(s.float().mean() > 0.95 for s in safes)
+    assert all(s.float().mean() > 0.9 for s in safes), [s.float().mean().item() for s in safes]
     f = f0.clone().requires_grad_(True)
     z = z0.clone().requires_grad_(True)
     outs = [sig(f), col(f, d), trunk(z)]

@@ -103,14 +103,16 @@ def test_composite_vs_oracle():
     n, r = sig.numel(), info.size(0)
     gen = torch.Generator().manual_seed(4)
     w = torch.rand(n, generator=gen) * 0.05
+    w[torch.rand(n, generator=gen) < 0.3] = 0.0      # terminated samples
     rgb = torch.rand(n, 3, generator=gen)
+    rgb_masked = rgb * (w > 0)[:, None]              # what the reference feeds the composite
     go = torch.randn(r, 3, generator=gen)
     for bg in (None, [1.0, 0.5, 0.25]):
         wd, rd = w.to(DEV).requires_grad_(True), rgb.to(DEV).requires_grad_(True)
         out = core.Composite.apply(wd, rd, info.to(DEV), bg)
-        close(out.cpu(), orc.composite_fwd(w, rgb, info, bg), atol=1e-6)
+        close(out.cpu(), orc.composite_fwd(w, rgb_masked, info, bg), atol=1e-6)
         out.backward(go.to(DEV))
-        gw, grgb = orc.composite_bwd(w, rgb, info, go, bg)
+        gw, grgb = orc.composite_bwd(w, rgb_masked, info, go, bg)
         close(wd.grad.cpu(), gw, atol=1e-6)
         close(rd.grad.cpu(), grgb, atol=1e-7)
 
@@ -141,9 +143,26 @@ def test_renderer_matches_reference_golden(golden):
     close(fm.net.net[0].weight.grad.cpu(), g["grad_feat_w"], rtol=1e-3, atol=1e-7)
 
 
-def test_kplanes_renderer_vs_torch_on_gpu():
-    """Config 2 shape: K-Planes + vanilla heads, AABB, 2^18-sample batch; whole render + backward
-    against the PyTorch restatement on the same GPU (weights via the reference's own kernel)."""
+@pytest.mark.parametrize("tensor_core_mlp", [False, True])
+def test_kplanes_renderer_vs_torch_on_gpu(tensor_core_mlp):
+    """Config 2 shape: K-Planes + vanilla heads, AABB, 2^18-sample batch; whole render + backward against the
+    PyTorch restatement on the same GPU (weights via the reference's own kernel).
+
+    tensor_core_mlp=False keeps the heads on cuBLAS fp32 in both pipelines, which isolates march / K-Planes /
+    weights / composite at the tight bar.  With the 3xTF32 tensor-core heads the two pipelines are two *different*
+    correct fp32 evaluations of ReLU networks: a hidden unit whose pre-activation is within rounding of 0
+    (a few hundred of the 2^18 x 320 units) switches on in one and off in the other, changing that sample's
+    gradient by O(1/64).  Forward colours still meet 1e-5; gradients are then compared in relative L2 (1e-3) with
+    element-wise agreement required on all but 0.1% of the entries."""
+    saved = models._USE_TC_MLP
+    models._USE_TC_MLP = tensor_core_mlp
+    try:
+        _renderer_case(tensor_core_mlp)
+    finally:
+        models._USE_TC_MLP = saved
+
+
+def _renderer_case(tensor_core_mlp):
     torch.manual_seed(0)
     field = models.KPlanesFeatureField(32)
     sd = models.VanillaOpacityDecoder(96)
@@ -157,10 +176,10 @@ def test_kplanes_renderer_vs_torch_on_gpu():
     og.grid.copy_(synthetic.analytic_grid(128, seed=1))
     og.mean = og.grid.mean().item()
     prov = core.RayProvider(og, core.ContractionAABB(aabb), marcher)
-    o, d = synthetic.blender_rays(4096, seed=2)
+    o, d = synthetic.blender_rays(9000, seed=2)
     torch.manual_seed(5)
     packed, info = prov(o.to(DEV), d.to(DEV), training=True)
-    assert packed.size(0) > 50_000
+    assert packed.size(0) > 200_000
     out = renderer(packed, info)
     s_layers = [(l.weight, l.bias) for l in sd.net.linears()]
     c_layers = [(l.weight, l.bias) for l in cd.net.linears()]
@@ -173,16 +192,13 @@ def test_kplanes_renderer_vs_torch_on_gpu():
     mine = {k: p.grad.clone() for k, p in renderer.named_parameters()}
     renderer.zero_grad()
     torch.nn.functional.mse_loss(want, target).backward()
-    # Two correct fp32 evaluations of the ReLU heads (cuBLAS SGEMM vs the 3xTF32 tensor-core kernels) may
-    # switch a hidden unit on/off when its pre-activation is within rounding of 0 (a handful of the 2^18 x 320
-    # units); each flip changes one sample's gradient by O(1/64).  Hence: tight relative L2 error on every
-    # parameter, and element-wise 5e-5-of-max agreement on all but a vanishing fraction of the entries.
+    l2_tol, frac_tol = (1e-3, 1e-3) if tensor_core_mlp else (2e-5, 1e-5)
     for k, p in renderer.named_parameters():
         ref, got = p.grad.double(), mine[k].double()
         scale = ref.abs().max().clamp_min(1e-12)
         rel_l2 = ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
         frac_bad = ((got - ref).abs() > 5e-5 * scale).float().mean().item()
-        assert rel_l2 <= 1e-4 and frac_bad <= 1e-4, (k, rel_l2, frac_bad)
+        assert rel_l2 <= l2_tol and frac_bad <= frac_tol, (k, rel_l2, frac_bad)
 
 
 def test_tv_regulariser_vs_reference_formula(golden):

@@ -421,6 +421,10 @@ class NerfRenderer(torch.nn.Module):
         self.sigma_decoder = sigma_decoder
         self.rgb_decoder = rgb_decoder
         self.bg_color = bg_color
+        # dense_rgb: evaluate the colour head on every sample instead of gathering the (weights > 0) subset.
+        # Same result (a masked-out sample has weight 0, so it adds exactly 0 to the ray and receives exactly 0
+        # gradient) without the nonzero() host sync and the gather/scatter passes of src/core.py:243-250.
+        self.dense_rgb = True
         assert hasattr(self.feature_module, "feature_dim"), "feature module requires a feature_dim attribute"
 
     def forward(self, packed_samples: torch.Tensor, packing_info: torch.Tensor,
@@ -439,13 +443,16 @@ class NerfRenderer(torch.nn.Module):
             samples_sigmas = self.sigma_decoder(samples_features).ravel()
             weights: torch.Tensor = NerfWeights.apply(samples_sigmas, steps, packing_info,
                                                       early_termination_threshold)  # type: ignore
-            mask = weights > 0.0
-            idx = mask.nonzero(as_tuple=True)[0]  # one sync, shared by the three masked ops below
-            if idx.numel() == 0:
-                raise ValueError("no samples remaining")
-            rgbs_m = self.rgb_decoder(samples_features.index_select(0, idx),
-                                      packed_samples[:, 3:6].index_select(0, idx))
-            samples_rgbs = torch.zeros((n_samples, 3), device=device).index_copy(0, idx, rgbs_m)
+            if self.dense_rgb:
+                samples_rgbs = self.rgb_decoder(samples_features, packed_samples[:, 3:6])
+            else:
+                mask = weights > 0.0
+                idx = mask.nonzero(as_tuple=True)[0]  # one sync, shared by the three masked ops below
+                if idx.numel() == 0:
+                    raise ValueError("no samples remaining")
+                rgbs_m = self.rgb_decoder(samples_features.index_select(0, idx),
+                                          packed_samples[:, 3:6].index_select(0, idx))
+                samples_rgbs = torch.zeros((n_samples, 3), device=device).index_copy(0, idx, rgbs_m)
         except ValueError:
             print("Empty iteration, every sample is masked")
             samples_rgbs = torch.zeros((n_samples, 3), device=device, requires_grad=True)

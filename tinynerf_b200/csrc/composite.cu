@@ -24,9 +24,11 @@ composite_fwd_kernel(const float* __restrict__ w, const float* __restrict__ rgb,
   float r = 0.f, g = 0.f, b = 0.f, op = 0.f;
   for (long long k = k0 + lane; k < k1; k += 32) {
     const float wk = __ldg(w + k);
-    r = __fmaf_rn(wk, __ldg(rgb + 3 * k + 0), r);
-    g = __fmaf_rn(wk, __ldg(rgb + 3 * k + 1), g);
-    b = __fmaf_rn(wk, __ldg(rgb + 3 * k + 2), b);
+    if (wk > 0.f) {  // colours exist only where weights > 0 (the reference's mask, src/core.py:243-250)
+      r = __fmaf_rn(wk, __ldg(rgb + 3 * k + 0), r);
+      g = __fmaf_rn(wk, __ldg(rgb + 3 * k + 1), g);
+      b = __fmaf_rn(wk, __ldg(rgb + 3 * k + 2), b);
+    }
     op += wk;
   }
 #pragma unroll
@@ -65,11 +67,12 @@ composite_bwd_kernel(const float* __restrict__ w, const float* __restrict__ rgb,
   const float gbg = has_bg ? (bg0 * g0 + bg1 * g1 + bg2 * g2) : 0.f;
   for (long long k = k0 + lane; k < k1; k += 32) {
     const float wk = __ldg(w + k);
-    if (gw) gw[k] = __ldg(rgb + 3 * k) * g0 + __ldg(rgb + 3 * k + 1) * g1 + __ldg(rgb + 3 * k + 2) * g2 - gbg;
+    const bool on = wk > 0.f;  // masked-out samples carry colour 0 in the reference: no colour term in gw, no grgb
+    if (gw) gw[k] = (on ? __ldg(rgb + 3 * k) * g0 + __ldg(rgb + 3 * k + 1) * g1 + __ldg(rgb + 3 * k + 2) * g2 : 0.f) - gbg;
     if (grgb) {
-      grgb[3 * k + 0] = wk * g0;
-      grgb[3 * k + 1] = wk * g1;
-      grgb[3 * k + 2] = wk * g2;
+      grgb[3 * k + 0] = on ? wk * g0 : 0.f;
+      grgb[3 * k + 1] = on ? wk * g1 : 0.f;
+      grgb[3 * k + 2] = on ? wk * g2 : 0.f;
     }
   }
 }

@@ -124,7 +124,12 @@ class VanillaColorDecoder(torch.nn.Module):
         self.activation = torch.nn.Sigmoid()
 
     def forward(self, features: torch.Tensor, rays_d: torch.Tensor) -> torch.Tensor:
-        x = torch.cat([self.pe(rays_d), rays_d, features], -1)
+        parts = [self.pe(rays_d), rays_d, features]
+        width = sum(p.shape[-1] for p in parts)
+        if _USE_TC_MLP and features.is_cuda and width % 4 != 0:
+            # pad the row to a multiple of 4 floats so the kernels can read it in place with 128-bit loads
+            parts.append(features.new_zeros(*features.shape[:-1], 4 - width % 4))
+        x = torch.cat(parts, -1)[..., :width]
         if self.net.fused_ok(x):
             return self.net(x, head_act=2)  # sigmoid fused into the layer epilogue
         return self.activation(self.net(x))
