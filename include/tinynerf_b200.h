@@ -202,6 +202,10 @@ int tnf_linear_bwd_data(const float* dy, int64_t lddy, const float* weight, floa
                         const float* relu_src, int64_t ldrs, int64_t m, int32_t n, int32_t k, void* stream);
 int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dweight, float* dbias,
                           int64_t m, int32_t n, int32_t k, void* stream);
+/* Input row of VanillaColorDecoder.forward (src/models.py:87): out[m] = [PE_{n_freqs}(dirs[m]) | dirs[m] | feats[m]],
+ * zero-padded to ld_out floats (PositionalEncoding layout, src/models.py:36-39). */
+int tnf_color_input(const float* dirs, int64_t ld_dirs, const float* feats, int64_t ld_feats, int32_t n_freqs,
+                    int32_t feat_dim, float* out, int64_t ld_out, int64_t n, void* stream);
 int tnf_head_bwd(const float* h, int64_t ldh, const float* head_w, const float* out, const float* dout, float* dh,
                  float* dhead_w, float* dhead_b, int64_t m, int32_t n, int32_t n_head, int32_t head_act, void* stream);
 

@@ -122,3 +122,20 @@ def test_fused_heads_forward_backward_vs_torch(m):
         if e > 2e-5:
             bad[k] = e
     assert not bad, bad
+
+
+def test_color_input_matches_positional_encoding_bitwise(golden):
+    """tnf_color_input == cat([PE(d), d, f]) of the reference (src/models.py:33-39,87), bit for bit, plus the
+    reference's own PE golden values."""
+    g = golden("heads")
+    pe = models.PositionalEncoding(8).to(DEV)
+    gen = torch.Generator().manual_seed(0)
+    d = torch.nn.functional.normalize(torch.randn(5000, 3, generator=gen), dim=-1).to(DEV)
+    f = torch.randn(5000, 96, generator=gen).to(DEV).requires_grad_(True)
+    x = mlp_ops.color_input(f, d, 8)
+    want = torch.cat([pe(d), d, f], -1)
+    assert x.shape == (5000, 147) and torch.equal(x, want)
+    x.backward(torch.ones_like(x))
+    assert torch.equal(f.grad, torch.ones_like(f))
+    xg = mlp_ops.color_input(g["feats"].to(DEV), g["dirs"].to(DEV), 8)
+    assert torch.allclose(xg[:, :48].cpu(), g["pe"], rtol=0, atol=2e-6)  # CPU sinf/cosf of the golden run vs GPU

@@ -143,26 +143,37 @@ def test_renderer_matches_reference_golden(golden):
     close(fm.net.net[0].weight.grad.cpu(), g["grad_feat_w"], rtol=1e-3, atol=1e-7)
 
 
+def _relu_kink_samples(layers, x64, margin):
+    """Samples with a hidden pre-activation within `margin` of the ReLU kink (float64 evaluation)."""
+    near = torch.zeros(x64.size(0), dtype=torch.bool, device=x64.device)
+    h = x64
+    for w, b in layers[:-1]:
+        pre = torch.nn.functional.linear(h, w.double(), b.double())
+        near |= (pre.abs() < margin).any(1)
+        h = pre.relu()
+    return near
+
+
 @pytest.mark.parametrize("tensor_core_mlp", [False, True])
 def test_kplanes_renderer_vs_torch_on_gpu(tensor_core_mlp):
-    """Config 2 shape: K-Planes + vanilla heads, AABB, 2^18-sample batch; whole render + backward against the
-    PyTorch restatement on the same GPU (weights via the reference's own kernel).
+    """Config 2 shape: K-Planes + vanilla heads, AABB, ~2^18-sample batch; whole render + backward against the
+    PyTorch restatement on the same GPU (weights via the reference's own kernel), colours and every parameter
+    gradient at the 1e-5 bar.
 
-    tensor_core_mlp=False keeps the heads on cuBLAS fp32 in both pipelines, which isolates march / K-Planes /
-    weights / composite at the tight bar.  With the 3xTF32 tensor-core heads the two pipelines are two *different*
-    correct fp32 evaluations of ReLU networks: a hidden unit whose pre-activation is within rounding of 0
-    (a few hundred of the 2^18 x 320 units) switches on in one and off in the other, changing that sample's
-    gradient by O(1/64).  Forward colours still meet 1e-5; gradients are then compared in relative L2 (1e-3) with
-    element-wise agreement required on all but 0.1% of the entries."""
+    Two correct fp32 evaluations of a ReLU network (cuBLAS on M rows vs cuBLAS on a different M vs the 3xTF32
+    tensor-core kernels) may switch a hidden unit on/off when its pre-activation is within rounding (~1e-6) of 0,
+    which changes that sample's gradient by O(1/64) in either of them.  Rays that contain such a sample (float64
+    pre-activation within 2e-5 of the kink; ~1-3% of the rays) are given zero loss weight in BOTH pipelines, so the
+    comparison measures arithmetic, not the kink lottery."""
     saved = models._USE_TC_MLP
     models._USE_TC_MLP = tensor_core_mlp
     try:
-        _renderer_case(tensor_core_mlp)
+        _renderer_case()
     finally:
         models._USE_TC_MLP = saved
 
 
-def _renderer_case(tensor_core_mlp):
+def _renderer_case():
     torch.manual_seed(0)
     field = models.KPlanesFeatureField(32)
     sd = models.VanillaOpacityDecoder(96)
@@ -187,18 +198,28 @@ def _renderer_case(tensor_core_mlp):
                           lambda f, dd: rp.rgb_head(c_layers, 8, f, dd), packed, info, torch.ones(3), return_aux=True)
     assert (aux["weights"] == 0).any()
     close(out, want, rtol=1e-5, atol=2e-6)
+    with torch.no_grad():
+        f64 = aux["features"].double()
+        xcol = torch.cat([rp.positional_encoding(packed[:, 3:6], 8), packed[:, 3:6], aux["features"]], -1).double()
+        kink = _relu_kink_samples(s_layers, f64, 2e-5) | _relu_kink_samples(c_layers, xcol, 2e-5)
+        ray_id = torch.repeat_interleave(torch.arange(info.size(0), device=DEV), info[:, 1].long())
+        bad_ray = torch.zeros(info.size(0), device=DEV).index_add_(0, ray_id, kink.float()) > 0
+        assert bad_ray.float().mean() < 0.1
+        ray_w = (~bad_ray).float()[:, None]
     target = torch.rand_like(out)
-    torch.nn.functional.mse_loss(out, target).backward()
+    (((out - target) ** 2) * ray_w).mean().backward()
     mine = {k: p.grad.clone() for k, p in renderer.named_parameters()}
     renderer.zero_grad()
-    torch.nn.functional.mse_loss(want, target).backward()
-    l2_tol, frac_tol = (1e-3, 1e-3) if tensor_core_mlp else (2e-5, 1e-5)
+    (((want - target) ** 2) * ray_w).mean().backward()
+    bad = {}
     for k, p in renderer.named_parameters():
         ref, got = p.grad.double(), mine[k].double()
         scale = ref.abs().max().clamp_min(1e-12)
         rel_l2 = ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
-        frac_bad = ((got - ref).abs() > 5e-5 * scale).float().mean().item()
-        assert rel_l2 <= l2_tol and frac_bad <= frac_tol, (k, rel_l2, frac_bad)
+        worst = ((got - ref).abs().max() / scale).item()
+        if rel_l2 > 2e-5 or worst > 5e-5:
+            bad[k] = (rel_l2, worst)
+    assert not bad, bad
 
 
 def test_tv_regulariser_vs_reference_formula(golden):

@@ -83,6 +83,8 @@ _SIGNATURES = {
                                       C.c_int32, C.c_int32, C.c_void_p]),
     "tnf_linear_bwd_weight": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, C.c_int32,
                                         C.c_int32, C.c_void_p]),
+    "tnf_color_input": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_int64, C.c_int64,
+                                  C.c_void_p]),
     "tnf_head_bwd": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32,
                                C.c_int32, C.c_int32, C.c_void_p]),
     "tnf_composite_fwd": (C.c_int, [c_f32p, c_f32p, c_i32p, C.c_int64, C.c_int64, C.POINTER(C.c_float), c_f32p,

@@ -28,6 +28,7 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kAtomBytes = 128 * 128;        // 128 rows x 32 fp32
 constexpr int kMaxKAtoms = 5;                // K <= 160
+constexpr int kMaxRing = 4;                  // raw cp.async ring slots (atoms in flight per CTA: ring - 1)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,6 +144,37 @@ __device__ __forceinline__ void load_atom_regs(const float* __restrict__ g, long
     }
   }
 }
+// Asynchronous variant: the same per-thread 16-byte chunks are copied global -> shared with cp.async into a raw
+// ring slot (zero-filled outside the matrix), so several atoms per CTA are in flight without holding registers;
+// each thread later reads back exactly the chunks it copied (no cross-thread hazard), splits and writes the operand
+// images.  Requires 16-byte aligned rows (ld % 4 == 0, aligned base); otherwise callers use load_atom_regs.
+__device__ __forceinline__ void cp_async_atom(const float* __restrict__ g, long long ld, long long row0, long long rows,
+                                              int col0, int cols, int tid, uint8_t* raw) {
+  const int c = tid & 7;
+  const int r0 = tid >> 3;
+  const int col = col0 + 4 * c;
+  int nbytes = (cols - col) * 4;
+  nbytes = nbytes < 0 ? 0 : (nbytes > 16 ? 16 : nbytes);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 16 * i;
+    const long long row = row0 + r;
+    const bool ok = row < rows && nbytes > 0;
+    const float* src = ok ? (g + row * ld + col) : g;
+    const uint32_t dst = smem_u32(raw + r * 128 + c * 16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? nbytes : 0) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void read_raw_atom(const uint8_t* raw, int tid, float4 v[8]) {
+  const int c = tid & 7;
+  const int r0 = tid >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(raw + (r0 + 16 * i) * 128 + c * 16);
+}
+
 // mn32: SWIZZLE_128B_BASE32B image (32-byte chunks XOR row%4) for MN-major reads, else SWIZZLE_128B (16-byte
 // chunks XOR row%8) for K-major reads.
 __device__ __forceinline__ int swz_off(int r, int c, bool mn32) {
@@ -183,6 +215,7 @@ struct LinArgs {
   long long M; int N, K;
   int relu;
   int n_tiles;
+  int ring;        // cp.async ring slots (2..kMaxRing), chosen by the host from the shared-memory budget
 };
 
 __device__ __forceinline__ float head_activation(float x, int act) {
@@ -225,20 +258,39 @@ __global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
   const uint32_t idesc = instr_desc(128, ND, false, MODE == 1);
   uint32_t phase = 0;
 
-  // Flattened (tile, atom) pipeline: the loads of item i+1 are issued into registers before the MMAs of item i,
-  // so HBM latency overlaps tensor-core work and the epilogue; the single smem A stage is rewritten only after
-  // the mbarrier reports the MMAs that read it complete.  Two CTAs per SM interleave their phases.
-  int tile = blockIdx.x, j = 0;
-  bool have = tile < A.n_tiles, pending = false;
+  // Flattened (tile, atom) pipeline.  Global loads run kRing items ahead: cp.async into a raw ring (or, for
+  // unaligned inputs, one item ahead in registers), so HBM latency overlaps staging, tensor-core work and the
+  // epilogue; the single operand stage is rewritten only after the mbarrier reports the MMAs that read it complete.
+  uint8_t* ring = a_lo + kAtomBytes;
+  const int nring = A.ring;
+  const bool use_ring = ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0);
+  const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_items = my_tiles * ka;
+  auto issue = [&](int it) {   // item it -> (tile, atom)
+    const int t = blockIdx.x + (it / ka) * gridDim.x, jj = it % ka;
+    if (it < n_items) cp_async_atom(A.X, A.ldx, (long long)t * 128, A.M, 32 * jj, KD, tid, ring + (it % nring) * kAtomBytes);
+    else asm volatile("cp.async.commit_group;" ::: "memory");  // keep the group count uniform
+  };
   float4 pre[8];
-  if (have) load_atom_regs(A.X, A.ldx, (long long)tile * 128, A.M, 0, KD, tid, pre);
-  while (have) {
+  if (use_ring) {
+    for (int it = 0; it < nring - 1; ++it) issue(it);
+  } else if (n_items > 0) {
+    load_atom_regs(A.X, A.ldx, (long long)blockIdx.x * 128, A.M, 0, KD, tid, pre);
+  }
+  bool pending = false;
+  for (int it = 0; it < n_items; ++it) {
+    const int tile = blockIdx.x + (it / ka) * gridDim.x, j = it % ka;
+    if (use_ring) {
+      issue(it + nring - 1);          // slot (it-1) % nring: consumed in the previous iteration
+      if (nring == 2) cp_async_wait<1>(); else if (nring == 3) cp_async_wait<2>(); else cp_async_wait<3>();  // item `it` landed
+      read_raw_atom(ring + (it % nring) * kAtomBytes, tid, pre);
+    }
     if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
     store_atom_regs(pre, a_hi, a_lo, tid, false, nullptr);
-    int ntile = tile, nj = j + 1;
-    if (nj == ka) { nj = 0; ntile = tile + gridDim.x; }
-    const bool nhave = ntile < A.n_tiles;
-    if (nhave) load_atom_regs(A.X, A.ldx, (long long)ntile * 128, A.M, 32 * nj, KD, tid, pre);
+    if (!use_ring && it + 1 < n_items) {
+      const int nt = blockIdx.x + ((it + 1) / ka) * gridDim.x, nj = (it + 1) % ka;
+      load_atom_regs(A.X, A.ldx, (long long)nt * 128, A.M, 32 * nj, KD, tid, pre);
+    }
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -332,8 +384,8 @@ __global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
       __syncthreads();   // every warp has drained its TMEM lanes (and the staging buffer) before the next tile
       tc_fence_after();
     }
-    tile = ntile; j = nj; have = nhave;
   }
+  cp_async_wait<0>();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
 }
@@ -371,13 +423,49 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
   for (int a = 0; a < kMaxKAtoms - 1; ++a) colsum[a][0] = colsum[a][1] = colsum[a][2] = colsum[a][3] = 0.f;
 
   // Flattened pipeline over (tile, item): items 0..ny-1 stage the dY atoms of the tile, items ny.. stage one X atom
-  // each and trigger its MMAs; the next item's global loads are in flight (registers) during the MMAs.
+  // each and trigger its MMAs.  Global loads run ahead through the cp.async ring (or one item ahead in registers
+  // for unaligned inputs).
   const int per_tile = ny + kx;
-  int tile = blockIdx.x, item = 0;
-  bool have = tile < A.n_tiles, pending = false;
+  uint8_t* ring = x_lo + kAtomBytes;
+  const int nring = A.ring;
+  const bool use_ring = ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0) && ((A.ldx2 & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(A.X2) & 15u) == 0);
+  const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_items = my_tiles * per_tile;
+  auto src_of = [&](int it, const float*& g, long long& ld, int& col0, int& cols, long long& row0) {
+    const int t = blockIdx.x + (it / per_tile) * gridDim.x, item = it % per_tile;
+    row0 = (long long)t * 128;
+    if (item < ny) { g = A.X; ld = A.ldx; col0 = 32 * item; cols = A.N; }
+    else { g = A.X2; ld = A.ldx2; col0 = 32 * (item - ny); cols = A.K; }
+  };
+  auto issue = [&](int it) {
+    if (it < n_items) {
+      const float* g; long long ld, row0; int col0, cols;
+      src_of(it, g, ld, col0, cols, row0);
+      cp_async_atom(g, ld, row0, A.M, col0, cols, tid, ring + (it % nring) * kAtomBytes);
+    } else {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  };
+  auto load_regs = [&](int it, float4 v[8]) {
+    const float* g; long long ld, row0; int col0, cols;
+    src_of(it, g, ld, col0, cols, row0);
+    load_atom_regs(g, ld, row0, A.M, col0, cols, tid, v);
+  };
   float4 pre[8];
-  if (have) load_atom_regs(A.X, A.ldx, (long long)tile * 128, A.M, 0, A.N, tid, pre);
-  while (have) {
+  if (use_ring) {
+    for (int it = 0; it < nring - 1; ++it) issue(it);
+  } else if (n_items > 0) {
+    load_regs(0, pre);
+  }
+  bool pending = false;
+  for (int it = 0; it < n_items; ++it) {
+    const int item = it % per_tile;
+    if (use_ring) {
+      issue(it + nring - 1);
+      if (nring == 2) cp_async_wait<1>(); else if (nring == 3) cp_async_wait<2>(); else cp_async_wait<3>();
+      read_raw_atom(ring + (it % nring) * kAtomBytes, tid, pre);
+    }
     if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
     const bool is_y = item < ny;
     if (is_y) {
@@ -388,13 +476,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
     } else {
       store_atom_regs(pre, x_hi, x_lo, tid, true, nullptr);
     }
-    int ntile = tile, nitem = item + 1;
-    if (nitem == per_tile) { nitem = 0; ntile = tile + gridDim.x; }
-    const bool nhave = ntile < A.n_tiles;
-    if (nhave) {
-      if (nitem < ny) load_atom_regs(A.X, A.ldx, (long long)ntile * 128, A.M, 32 * nitem, A.N, tid, pre);
-      else            load_atom_regs(A.X2, A.ldx2, (long long)ntile * 128, A.M, 32 * (nitem - ny), A.K, tid, pre);
-    }
+    if (!use_ring && it + 1 < n_items) load_regs(it + 1, pre);
     fence_async_smem();
     __syncthreads();
     if (!is_y) {
@@ -415,9 +497,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
       pending = true;
       if (item == per_tile - 1) first = false;
     }
-    tile = ntile; item = nitem; have = nhave;
   }
   if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
+  cp_async_wait<0>();
   // bias gradient: column sums of dY gathered while staging
   if (A.db) {
 #pragma unroll
@@ -524,6 +606,36 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   if (tid < n_head) atomicAdd(dbh + tid, s_dbh[tid]);
 }
 
+// Input row of VanillaColorDecoder (src/models.py:87): [PE(d) | d | features] written in one pass.
+// PE layout per coordinate c: sin(2^k pi d_c), k < n_freqs, then cos(...) (src/models.py:36-39); the frequencies are
+// fl32(pi) * 2^k like the reference's `2**arange(n) * torch.pi` buffer, products rounded to fp32 before sinf/cosf.
+__global__ void __launch_bounds__(256) color_input_kernel(const float* __restrict__ dirs, long long ld_dirs,
+                                                          const float* __restrict__ feats, long long ld_feats, int n_freqs,
+                                                          int feat_dim, float* __restrict__ out, long long ld_out, long long n) {
+  const int pe = 6 * n_freqs;
+  const int width = pe + 3 + feat_dim;
+  const int lanes = 32;  // one warp per row
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / lanes;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* d = dirs + row * ld_dirs;
+  float* o = out + row * ld_out;
+  for (int j = lane; j < ld_out; j += lanes) {
+    float v = 0.f;
+    if (j < pe) {
+      const int c = j / (2 * n_freqs), r = j % (2 * n_freqs);
+      const int k = r % n_freqs;
+      const float arg = __fmul_rn(__ldg(d + c), ldexpf(3.14159274101257324219f, k));
+      v = (r < n_freqs) ? sinf(arg) : cosf(arg);
+    } else if (j < pe + 3) {
+      v = __ldg(d + (j - pe));
+    } else if (j < width) {
+      v = __ldg(feats + row * ld_feats + (j - pe - 3));
+    }
+    o[j] = v;
+  }
+}
+
 int check_lin(long long M, int N, int K) {
   TNF_REQUIRE(M >= 0, "negative M");
   TNF_REQUIRE(N >= 8 && N <= 128 && N % 8 == 0, "out_features must be a multiple of 8 in [8,128] (got %d)", N);
@@ -532,16 +644,34 @@ int check_lin(long long M, int N, int K) {
 }
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// shared-memory plan of linear_kernel: weight images + one operand stage + cp.async ring; keeps two CTAs per SM
+// (113 KB each) whenever at least a 2-slot ring fits, else one CTA with the deepest ring.
+size_t plan_smem(int n, int k, int* ring) {
+  const size_t w_stride = ((((size_t)(n + 15) & ~15) * 128) + 1023) & ~(size_t)1023;
+  const size_t base = 2 * ((k + 31) / 32) * w_stride + 2 * kAtomBytes + 1024;
+  const size_t two_cta = 113 * 1024, one_cta = 226 * 1024;
+  int r;
+  if (base + 3 * kAtomBytes <= two_cta) r = 3;
+  else if (base + 2 * kAtomBytes <= two_cta) r = 2;
+  else {
+    r = (int)((one_cta - base) / kAtomBytes);
+    r = r > kMaxRing ? kMaxRing : (r < 2 ? 2 : r);
+  }
+  *ring = r;
+  return base + (size_t)r * kAtomBytes;
+}
+
 template <typename Kern>
 int launch_lin(Kern kern, const LinArgs& A, size_t smem, cudaStream_t st, const char* name) {
   static thread_local const void* configured[8] = {nullptr};
   bool done = false;
   for (auto c : configured) done |= (c == (const void*)kern);
   if (!done) {
-    TNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     for (auto& c : configured) if (!c) { c = (const void*)kern; break; }
   }
-  int grid = A.n_tiles < 2 * sm_count() ? A.n_tiles : 2 * sm_count();
+  const int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  const int grid = A.n_tiles < per_sm * sm_count() ? A.n_tiles : per_sm * sm_count();
   kern<<<grid, kThreads, smem, st>>>(A);
   TNF_LAUNCH_CHECK(name);
   return TNF_OK;
@@ -564,7 +694,7 @@ extern "C" int tnf_linear_fwd(const float* x, int64_t ldx, const float* weight, 
   A.X = x; A.ldx = ldx; A.W = weight; A.bias = bias; A.Y = y; A.ldy = ldy; A.M = m; A.N = n; A.K = k; A.relu = relu;
   A.head_w = head_w; A.head_b = head_b; A.head_out = head_out; A.n_head = n_head; A.head_act = head_act;
   A.n_tiles = (int)ceil_div(m, 128);
-  const size_t smem = (size_t)(2 * ((k + 31) / 32)) * ((((n + 15) & ~15) * 128 + 1023) & ~1023) + 2 * kAtomBytes + 1024;
+  const size_t smem = plan_smem(n, k, &A.ring);
   return launch_lin(linear_kernel<0>, A, smem, static_cast<cudaStream_t>(stream), "linear_fwd_kernel");
 }
 
@@ -580,7 +710,7 @@ extern "C" int tnf_linear_bwd_data(const float* dy, int64_t lddy, const float* w
   LinArgs A{};
   A.X = dy; A.ldx = lddy; A.W = weight; A.Y = dx; A.ldy = lddx; A.X2 = relu_src; A.ldx2 = ldrs; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);
-  const size_t smem = (size_t)(2 * ((k + 31) / 32)) * ((((n + 15) & ~15) * 128 + 1023) & ~1023) + 2 * kAtomBytes + 1024;
+  const size_t smem = plan_smem(n, k, &A.ring);
   return launch_lin(linear_kernel<1>, A, smem, static_cast<cudaStream_t>(stream), "linear_dgrad_kernel");
 }
 
@@ -595,16 +725,34 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   LinArgs A{};
   A.X = dy; A.ldx = lddy; A.X2 = x; A.ldx2 = ldx; A.dW = dweight; A.db = dbias; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);
-  const size_t smem = (size_t)(2 * ((n + 31) / 32) + 2) * kAtomBytes + 1024;
+  const size_t base = (size_t)(2 * ((n + 31) / 32) + 2) * kAtomBytes + 1024;
+  // two CTAs per SM when the operand images plus a 2-slot ring fit in 113 KB, else one CTA with the deepest ring
+  int ctas_per_sm = 1;
+  if (base + 2 * kAtomBytes <= 113 * 1024) { A.ring = (base + 3 * kAtomBytes <= 113 * 1024) ? 3 : 2; ctas_per_sm = 2; }
+  else { A.ring = (int)((226 * 1024 - base) / kAtomBytes); A.ring = A.ring > kMaxRing ? kMaxRing : (A.ring < 2 ? 2 : A.ring); }
+  const size_t smem = base + (size_t)A.ring * kAtomBytes;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static thread_local bool configured = false;
   if (!configured) {
-    TNF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TNF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
-  const int grid = A.n_tiles < 2 * sm_count() ? A.n_tiles : 2 * sm_count();
+  const int grid = A.n_tiles < ctas_per_sm * sm_count() ? A.n_tiles : ctas_per_sm * sm_count();
   wgrad_kernel<<<grid, kThreads, smem, st>>>(A);
   TNF_LAUNCH_CHECK("linear_wgrad_kernel");
+  return TNF_OK;
+}
+
+extern "C" int tnf_color_input(const float* dirs, int64_t ld_dirs, const float* feats, int64_t ld_feats, int32_t n_freqs,
+                               int32_t feat_dim, float* out, int64_t ld_out, int64_t n, void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(n >= 0 && n_freqs >= 0 && n_freqs <= 24 && feat_dim >= 0, "bad sizes");
+  if (n == 0) return TNF_OK;
+  TNF_REQUIRE(dirs && (feats || feat_dim == 0) && out, "null pointer");
+  TNF_REQUIRE(ld_out >= 6 * n_freqs + 3 + feat_dim, "ld_out too small");
+  color_input_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dirs, ld_dirs, feats, ld_feats, n_freqs, feat_dim, out, ld_out, n);
+  TNF_LAUNCH_CHECK("color_input_kernel");
   return TNF_OK;
 }
 

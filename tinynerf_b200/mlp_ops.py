@@ -149,3 +149,34 @@ def fused_mlp(x: torch.Tensor, linears: Sequence[torch.nn.Linear], head_act: int
     for l in linears:
         params += [l.weight, l.bias]
     return _FusedMLP.apply(x, head_act, *params)
+
+
+class _ColorInput(Function):
+    """[PE(d) | d | features] rows of the colour head (src/models.py:87) in one pass; gradient flows to features."""
+
+    @staticmethod
+    def forward(ctx, features, dirs, n_freqs):
+        _lib.load()
+        f = features.detach().reshape(-1, features.shape[-1])
+        d = dirs.detach().reshape(-1, 3)
+        if f.stride(1) != 1:
+            f = f.contiguous()
+        if d.stride(1) != 1:
+            d = d.contiguous()
+        n, fd = f.shape
+        width = 6 * n_freqs + 3 + fd
+        ld = (width + 3) // 4 * 4
+        out = torch.empty(n, ld, device=f.device)
+        with torch.cuda.device(f.device):
+            _lib.call("tnf_color_input", d.data_ptr(), d.stride(0), f.data_ptr(), f.stride(0), n_freqs, fd, out.data_ptr(), ld, n,
+                      _lib.stream_ptr(), nbytes=n * (12 + 4 * fd + 4 * ld))
+        ctx.fd, ctx.width, ctx.shape = fd, width, features.shape
+        return out[:, :width]
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, ctx.width - ctx.fd:ctx.width].reshape(ctx.shape), None, None
+
+
+def color_input(features: torch.Tensor, dirs: torch.Tensor, n_freqs: int) -> torch.Tensor:
+    return _ColorInput.apply(features, dirs, n_freqs)

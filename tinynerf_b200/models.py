@@ -124,6 +124,11 @@ class VanillaColorDecoder(torch.nn.Module):
         self.activation = torch.nn.Sigmoid()
 
     def forward(self, features: torch.Tensor, rays_d: torch.Tensor) -> torch.Tensor:
+        if (_USE_TC_MLP and features.is_cuda and features.dim() == 2 and features.dtype == torch.float32
+                and rays_d.dtype == torch.float32):
+            x = mlp_ops.color_input(features, rays_d, self.pe.freqs.numel())  # one kernel instead of sin/cos/cat/cat
+            if self.net.fused_ok(x):
+                return self.net(x, head_act=2)
         parts = [self.pe(rays_d), rays_d, features]
         width = sum(p.shape[-1] for p in parts)
         if _USE_TC_MLP and features.is_cuda and width % 4 != 0:

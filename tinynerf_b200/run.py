@@ -120,6 +120,7 @@ class TrainConfig:
     bg_color: Tuple[float, float, float] | None = (1.0, 1.0, 1.0)
     grad_scale: float = 2.0 ** 10       # GradScaler(2**10) that is never unscaled (src/run.py:201,259)
     accumulate: str = "batched"         # "sequential" = the reference's chunk-by-chunk loop (one sync per chunk)
+    prefetch: bool = True               # march the next step's batch on a side stream while this step trains
     occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
     seed: int = 0
 
@@ -171,6 +172,8 @@ class Trainer:
         self.tv_reg_alpha, self.l1_reg_alpha = 0.0001, 0.0
         self.train_step = 0
         self._chunks_guess = 0.0
+        self._side = torch.cuda.Stream(device=self.device) if (cfg.prefetch and self.device.type == "cuda") else None
+        self._next = None
         self.last: Dict[str, float] = {}
 
     # ---- a11: dynamic batch accumulator (src/run.py:215-244) -----------------------------------
@@ -272,11 +275,34 @@ class Trainer:
         og.mean = og.grid.mean().item()
 
     # ---- one training iteration (src/run.py:246-261) -------------------------------------------
+    def _prefetch(self, after: torch.cuda.Event) -> None:
+        """March the next batch on the side stream.  It depends only on the occupancy grid, which the reference also
+        leaves untouched between this point and the next iteration's batch generation (src/run.py:215-249), and it
+        draws its jitter after this step's forward was enqueued, i.e. in the reference's generator order."""
+        side = self._side
+        side.wait_event(after)
+        with torch.cuda.stream(side):
+            batch = self.next_batch()
+            done = side.record_event()
+        self._next = (batch, done)
+
+    def _take_batch(self):
+        if self._next is None:
+            return self.next_batch()
+        (packed, rgbs, info), done = self._next
+        self._next = None
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(done)
+        for t in (packed, packed._tnf_steps, rgbs, info):
+            t.record_stream(main)
+        return packed, rgbs, info
+
     def step(self) -> Dict[str, float]:
-        packed, rgbs, info = self.next_batch()
+        packed, rgbs, info = self._take_batch()
         self.renderer.train()
         if self.train_step % self.occupancy_grid_updates == 0:
             self.update_occupancy()
+        grid_ready = torch.cuda.current_stream(self.device).record_event() if self._side is not None else None
         rendered = self.renderer(packed, info)
         loss = dp_mse(rendered, rgbs, global_ray_count(info.size(0), self.device, self.world))
         if self.cfg.method == "kplanes":
@@ -290,6 +316,10 @@ class Trainer:
         self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
+        if self._side is not None:
+            # everything above is enqueued; the next batch is marched on the side stream while the GPU is still
+            # busy with this step's backward + optimiser, so its host sync no longer stalls the step
+            self._prefetch(grid_ready)
         self.last = {"loss": loss.detach(), "n_samples": packed.size(0), "n_rays": info.size(0)}
         return self.last
 
