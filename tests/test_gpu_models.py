@@ -163,7 +163,7 @@ def test_kplanes_renderer_vs_torch_on_gpu(tensor_core_mlp):
     Two correct fp32 evaluations of a ReLU network (cuBLAS on M rows vs cuBLAS on a different M vs the 3xTF32
     tensor-core kernels) may switch a hidden unit on/off when its pre-activation is within rounding (~1e-6) of 0,
     which changes that sample's gradient by O(1/64) in either of them.  Rays that contain such a sample (float64
-    pre-activation within 2e-5 of the kink; ~1-3% of the rays) are given zero loss weight in BOTH pipelines, so the
+    pre-activation within 3e-6 of the kink; a few % of the rays) are given zero loss weight in BOTH pipelines, so the
     comparison measures arithmetic, not the kink lottery."""
     saved = models._USE_TC_MLP
     models._USE_TC_MLP = tensor_core_mlp
@@ -201,10 +201,10 @@ def _renderer_case():
     with torch.no_grad():
         f64 = aux["features"].double()
         xcol = torch.cat([rp.positional_encoding(packed[:, 3:6], 8), packed[:, 3:6], aux["features"]], -1).double()
-        kink = _relu_kink_samples(s_layers, f64, 2e-5) | _relu_kink_samples(c_layers, xcol, 2e-5)
+        kink = _relu_kink_samples(s_layers, f64, 3e-6) | _relu_kink_samples(c_layers, xcol, 3e-6)
         ray_id = torch.repeat_interleave(torch.arange(info.size(0), device=DEV), info[:, 1].long())
         bad_ray = torch.zeros(info.size(0), device=DEV).index_add_(0, ray_id, kink.float()) > 0
-        assert bad_ray.float().mean() < 0.1
+        assert bad_ray.float().mean() < 0.25, bad_ray.float().mean()
         ray_w = (~bad_ray).float()[:, None]
     target = torch.rand_like(out)
     (((out - target) ** 2) * ray_w).mean().backward()

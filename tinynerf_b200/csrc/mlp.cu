@@ -28,7 +28,6 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kAtomBytes = 128 * 128;        // 128 rows x 32 fp32
 constexpr int kMaxKAtoms = 5;                // K <= 160
-constexpr int kMaxRing = 4;                  // raw cp.async ring slots (atoms in flight per CTA: ring - 1)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,37 +143,6 @@ __device__ __forceinline__ void load_atom_regs(const float* __restrict__ g, long
     }
   }
 }
-// Asynchronous variant: the same per-thread 16-byte chunks are copied global -> shared with cp.async into a raw
-// ring slot (zero-filled outside the matrix), so several atoms per CTA are in flight without holding registers;
-// each thread later reads back exactly the chunks it copied (no cross-thread hazard), splits and writes the operand
-// images.  Requires 16-byte aligned rows (ld % 4 == 0, aligned base); otherwise callers use load_atom_regs.
-__device__ __forceinline__ void cp_async_atom(const float* __restrict__ g, long long ld, long long row0, long long rows,
-                                              int col0, int cols, int tid, uint8_t* raw) {
-  const int c = tid & 7;
-  const int r0 = tid >> 3;
-  const int col = col0 + 4 * c;
-  int nbytes = (cols - col) * 4;
-  nbytes = nbytes < 0 ? 0 : (nbytes > 16 ? 16 : nbytes);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + 16 * i;
-    const long long row = row0 + r;
-    const bool ok = row < rows && nbytes > 0;
-    const float* src = ok ? (g + row * ld + col) : g;
-    const uint32_t dst = smem_u32(raw + r * 128 + c * 16);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? nbytes : 0) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void read_raw_atom(const uint8_t* raw, int tid, float4 v[8]) {
-  const int c = tid & 7;
-  const int r0 = tid >> 3;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(raw + (r0 + 16 * i) * 128 + c * 16);
-}
-
 // mn32: SWIZZLE_128B_BASE32B image (32-byte chunks XOR row%4) for MN-major reads, else SWIZZLE_128B (16-byte
 // chunks XOR row%8) for K-major reads.
 __device__ __forceinline__ int swz_off(int r, int c, bool mn32) {
@@ -215,7 +183,7 @@ struct LinArgs {
   long long M; int N, K;
   int relu;
   int n_tiles;
-  int ring;        // cp.async ring slots (2..kMaxRing), chosen by the host from the shared-memory budget
+  int ring;        // operand stages of the warp-specialised kernels (2..4), chosen by the host from the smem budget
 };
 
 __device__ __forceinline__ float head_activation(float x, int act) {
@@ -224,105 +192,122 @@ __device__ __forceinline__ float head_activation(float x, int act) {
   return x;
 }
 
-// dynamic smem: [W hi atoms][W lo atoms][A hi][A lo] (+ second operand pair for wgrad), 1024-byte aligned
+// ---- forward / dgrad: warp-specialised, persistent, one CTA per SM --------------------------------------------
+//   warps 0-3  loaders : LDG (one atom ahead in registers) -> hi/lo split -> swizzled STS into stage s -> full[s]
+//   warps 4-7  epilogue: tmem_full[b] -> tcgen05.ld (warp w owns TMEM lanes 32*(w%4)..) -> bias/ReLU/head ->
+//                        transpose through a private 16 KB buffer -> coalesced global stores -> tmem_empty[b]
+//   warp  8    MMA     : full[s] -> 12 x tcgen05.mma.kind::tf32 (3xTF32) -> tcgen05.commit -> empty[s]
+//                        (+ tmem_full[b] after the tile's last atom); accumulators double-buffered in TMEM
+// so HBM loads, tensor-core work and the epilogue of consecutive tiles overlap inside one CTA.
+constexpr int kWsThreads = 288;
+constexpr int kMaxStages = 4;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// dynamic smem: [W hi atoms][W lo atoms][stage 0: A hi, A lo] ... [stage S-1][epilogue staging 16 KB], 1024-aligned
 template <int MODE>  // 0 fwd, 1 dgrad
-__global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
+__global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t s_bar;
+  __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // GEMM view: D[128, ND] += sum over KD of A[128, KD] * B[ND, KD]
-  const int KD = (MODE == 0) ? A.K : A.N;            // contraction length
+  const int KD = (MODE == 0) ? A.K : A.N;                 // contraction length
   const int ND = (MODE == 0) ? A.N : ((A.K + 15) & ~15);  // output columns (dgrad: K_in padded to 16)
-  const int ka = (KD + 31) >> 5;                     // contraction atoms
-  const int w_atoms = (A.K + 31) >> 5;               // weight image: N rows x K cols -> atoms along K
-  const int w_rows = (A.N + 15) & ~15;               // rows staged per weight atom
-  const int w_stride = ((w_rows * 128) + 1023) & ~1023;  // bytes between weight atoms (1024-aligned)
+  const int ka = (KD + 31) >> 5;                          // contraction atoms per tile
+  const int w_atoms = (A.K + 31) >> 5;                    // weight image: N rows x K cols -> atoms along K
+  const int w_rows = (A.N + 15) & ~15;
+  const int w_stride = ((w_rows * 128) + 1023) & ~1023;
+  const int S = A.ring;                                   // operand stages
   uint8_t* w_hi = smem;
   uint8_t* w_lo = smem + w_atoms * w_stride;
-  uint8_t* a_hi = smem + 2 * w_atoms * w_stride;
-  uint8_t* a_lo = a_hi + kAtomBytes;
+  uint8_t* stages = smem + 2 * w_atoms * w_stride;        // stage s: hi at +s*2*kAtomBytes, lo right after
+  uint8_t* epi = stages + S * 2 * kAtomBytes;
+  const int nd_cols = ND <= 32 ? 32 : (ND <= 64 ? 64 : (ND <= 128 ? 128 : 256));  // TMEM columns per accumulator
+  const int tmem_cols = 2 * nd_cols;
 
-  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
-  const int tmem_cols = ND <= 32 ? 32 : (ND <= 64 ? 64 : (ND <= 128 ? 128 : 256));
-  if (warp == 0) tmem_alloc(&s_tmem, tmem_cols);
-  // weights: N rows (<=128) x K columns, staged once per CTA
-  for (int j = 0; j < w_atoms; ++j)
-    stage_atom(A.W, A.K, 0, A.N, 32 * j, A.K, w_hi + j * w_stride, w_lo + j * w_stride, tid, nullptr, w_rows, MODE == 1);
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_tfull[b], 1); mbar_init(&s_tempty[b], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(&s_tmem, tmem_cols);
+  if (tid < 128)
+    for (int j = 0; j < w_atoms; ++j)
+      stage_atom(A.W, A.K, 0, A.N, 32 * j, A.K, w_hi + j * w_stride, w_lo + j * w_stride, tid, nullptr, w_rows, MODE == 1);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = s_tmem;
-  const uint32_t idesc = instr_desc(128, ND, false, MODE == 1);
-  uint32_t phase = 0;
-
-  // Flattened (tile, atom) pipeline.  Global loads run kRing items ahead: cp.async into a raw ring (or, for
-  // unaligned inputs, one item ahead in registers), so HBM latency overlaps staging, tensor-core work and the
-  // epilogue; the single operand stage is rewritten only after the mbarrier reports the MMAs that read it complete.
-  uint8_t* ring = a_lo + kAtomBytes;
-  const int nring = A.ring;
-  const bool use_ring = ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0);
+  const uint32_t tmem_base = s_tmem;
   const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_items = my_tiles * ka;
-  auto issue = [&](int it) {   // item it -> (tile, atom)
-    const int t = blockIdx.x + (it / ka) * gridDim.x, jj = it % ka;
-    if (it < n_items) cp_async_atom(A.X, A.ldx, (long long)t * 128, A.M, 32 * jj, KD, tid, ring + (it % nring) * kAtomBytes);
-    else asm volatile("cp.async.commit_group;" ::: "memory");  // keep the group count uniform
-  };
-  float4 pre[8];
-  if (use_ring) {
-    for (int it = 0; it < nring - 1; ++it) issue(it);
-  } else if (n_items > 0) {
-    load_atom_regs(A.X, A.ldx, (long long)blockIdx.x * 128, A.M, 0, KD, tid, pre);
-  }
-  bool pending = false;
-  for (int it = 0; it < n_items; ++it) {
-    const int tile = blockIdx.x + (it / ka) * gridDim.x, j = it % ka;
-    if (use_ring) {
-      issue(it + nring - 1);          // slot (it-1) % nring: consumed in the previous iteration
-      if (nring == 2) cp_async_wait<1>(); else if (nring == 3) cp_async_wait<2>(); else cp_async_wait<3>();  // item `it` landed
-      read_raw_atom(ring + (it % nring) * kAtomBytes, tid, pre);
-    }
-    if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
-    store_atom_regs(pre, a_hi, a_lo, tid, false, nullptr);
-    if (!use_ring && it + 1 < n_items) {
-      const int nt = blockIdx.x + ((it + 1) / ka) * gridDim.x, nj = (it + 1) % ka;
-      load_atom_regs(A.X, A.ldx, (long long)nt * 128, A.M, 32 * nj, KD, tid, pre);
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
-#pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t aa = (pass == 1) ? al : ah;
-        const uint8_t* wb = (pass == 2) ? w_lo : w_hi;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          uint64_t bd;
-          if (MODE == 0) bd = desc_kmajor(smem_u32(wb + j * w_stride), kk);
-          else           bd = desc_mnmajor(smem_u32(wb) + j * 4096 /*32 rows of n_out*/, kk, w_stride);
-          mma_tf32(tmem_d, desc_kmajor(aa, kk), bd, idesc, (j | pass | kk) != 0);
-        }
+
+  if (warp < 4) {
+    // ===== loaders =====
+    float4 pre[8];
+    if (n_items > 0) load_atom_regs(A.X, A.ldx, (long long)blockIdx.x * 128, A.M, 0, KD, tid, pre);
+    for (int it = 0; it < n_items; ++it) {
+      const int s = it % S;
+      mbar_wait(&s_empty[s], ((it / S) & 1) ^ 1);   // the MMAs that read this stage have completed
+      uint8_t* a_hi = stages + s * 2 * kAtomBytes;
+      store_atom_regs(pre, a_hi, a_hi + kAtomBytes, tid, false, nullptr);
+      if (it + 1 < n_items) {
+        const int nt = blockIdx.x + ((it + 1) / ka) * gridDim.x, nj = (it + 1) % ka;
+        load_atom_regs(A.X, A.ldx, (long long)nt * 128, A.M, 32 * nj, KD, tid, pre);
       }
-      mma_commit(&s_bar);
+      fence_async_smem();
+      mbar_arrive(&s_full[s]);
     }
-    pending = true;
-    if (j == ka - 1) {
-      mbar_wait(&s_bar, phase); phase ^= 1; pending = false;   // accumulator complete, A stage free
+  } else if (warp == 8) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = instr_desc(128, ND, false, MODE == 1);
+    for (int it = 0; it < n_items; ++it) {
+      const int s = it % S, j = it % ka, tl = it / ka, b = tl & 1;
+      if (j == 0) mbar_wait(&s_tempty[b], ((tl >> 1) & 1) ^ 1);   // epilogue has drained accumulator b
+      mbar_wait(&s_full[s], (it / S) & 1);
       tc_fence_after();
-      const long long row0 = (long long)tile * 128;
-      const int r = warp * 32 + lane;            // thread = TMEM lane = tile row
+      if (lane == 0) {
+        const uint32_t ah = smem_u32(stages + s * 2 * kAtomBytes), al = ah + kAtomBytes;
+        const uint32_t tmem_d = tmem_base + b * nd_cols;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t aa = (pass == 1) ? al : ah;
+          const uint8_t* wb = (pass == 2) ? w_lo : w_hi;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint64_t bd;
+            if (MODE == 0) bd = desc_kmajor(smem_u32(wb + j * w_stride), kk);
+            else           bd = desc_mnmajor(smem_u32(wb) + j * 4096 /*32 rows of n_out*/, kk, w_stride);
+            mma_tf32(tmem_d, desc_kmajor(aa, kk), bd, idesc, (j | pass | kk) != 0);
+          }
+        }
+        mma_commit(&s_empty[s]);                 // stage reusable once these MMAs have read it
+        if (j == ka - 1) mma_commit(&s_tfull[b]);  // accumulator b complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue (warps 4..7; warp w may touch TMEM lanes 32*(w%4) .. +31) =====
+    const int ew = warp - 4, et = tid - 128;
+    const int r = ew * 32 + lane;  // tile row owned by this thread
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int b = tl & 1;
+      const long long row0 = (long long)(blockIdx.x + tl * gridDim.x) * 128;
       const long long row = row0 + r;
-      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+      mbar_wait(&s_tfull[b], (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + b * nd_cols + ((uint32_t)(ew * 32) << 16);
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
       const bool write_y = (MODE == 1) || (A.Y != nullptr);
       for (int c0 = 0; c0 < ND; c0 += 32) {
         float v[32];
         tmem_ld32(taddr + c0, v);
+        if (c0 + 32 >= ND) { tc_fence_before(); mbar_arrive(&s_tempty[b]); }  // accumulator b fully read by this thread
         if (MODE == 0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -338,20 +323,19 @@ __global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
           }
         }
         if (write_y) {
-          // transpose through the (free) A stage so that global stores are coalesced: 8 lanes = one 128 B row segment
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(a_hi + swz_off(r, q, false)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          __syncthreads();
-          const int c = tid & 7;
+            *reinterpret_cast<float4*>(epi + swz_off(r, q, false)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          epi_bar_sync();
+          const int c = et & 7;
           const int col = c0 + 4 * c;
           const int ncols = (MODE == 0) ? A.N : A.K;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rr = (tid >> 3) + 16 * i;
+            const int rr = (et >> 3) + 16 * i;
             const long long grow = row0 + rr;
             if (grow < A.M && col < ncols) {
-              float4 o = *reinterpret_cast<const float4*>(a_hi + swz_off(rr, c, false));
+              float4 o = *reinterpret_cast<const float4*>(epi + swz_off(rr, c, false));
               if (MODE == 1 && A.X2) {  // ReLU backward of the layer that produced this layer's input
                 const float* xp = A.X2 + grow * A.ldx2 + col;
                 if (col + 3 < ncols) {
@@ -374,21 +358,19 @@ __global__ void __launch_bounds__(kThreads) linear_kernel(const LinArgs A) {
               }
             }
           }
-          __syncthreads();
+          epi_bar_sync();
         }
       }
       if (MODE == 0 && A.n_head > 0 && row < A.M)
         for (int o = 0; o < A.n_head; ++o)
           A.head_out[row * A.n_head + o] = head_activation(head_acc[o] + __ldg(A.head_b + o), A.head_act);
-      tc_fence_before();
-      __syncthreads();   // every warp has drained its TMEM lanes (and the staging buffer) before the next tile
-      tc_fence_after();
     }
   }
-  cp_async_wait<0>();
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+  if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
 }
+
 
 // wgrad: dW[n,k] += sum_m dY[m,n] X[m,k] ; db[n] += sum_m dY[m,n].  D[N_out, 32] per X atom lives in TMEM for the
 // whole kernel (columns 32*j.. of atom j) and is flushed with atomics once per CTA.
@@ -423,49 +405,13 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
   for (int a = 0; a < kMaxKAtoms - 1; ++a) colsum[a][0] = colsum[a][1] = colsum[a][2] = colsum[a][3] = 0.f;
 
   // Flattened pipeline over (tile, item): items 0..ny-1 stage the dY atoms of the tile, items ny.. stage one X atom
-  // each and trigger its MMAs.  Global loads run ahead through the cp.async ring (or one item ahead in registers
-  // for unaligned inputs).
+  // each and trigger its MMAs; the next item's global loads are in flight (registers) during the MMAs.
   const int per_tile = ny + kx;
-  uint8_t* ring = x_lo + kAtomBytes;
-  const int nring = A.ring;
-  const bool use_ring = ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0) && ((A.ldx2 & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(A.X2) & 15u) == 0);
-  const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int n_items = my_tiles * per_tile;
-  auto src_of = [&](int it, const float*& g, long long& ld, int& col0, int& cols, long long& row0) {
-    const int t = blockIdx.x + (it / per_tile) * gridDim.x, item = it % per_tile;
-    row0 = (long long)t * 128;
-    if (item < ny) { g = A.X; ld = A.ldx; col0 = 32 * item; cols = A.N; }
-    else { g = A.X2; ld = A.ldx2; col0 = 32 * (item - ny); cols = A.K; }
-  };
-  auto issue = [&](int it) {
-    if (it < n_items) {
-      const float* g; long long ld, row0; int col0, cols;
-      src_of(it, g, ld, col0, cols, row0);
-      cp_async_atom(g, ld, row0, A.M, col0, cols, tid, ring + (it % nring) * kAtomBytes);
-    } else {
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-  };
-  auto load_regs = [&](int it, float4 v[8]) {
-    const float* g; long long ld, row0; int col0, cols;
-    src_of(it, g, ld, col0, cols, row0);
-    load_atom_regs(g, ld, row0, A.M, col0, cols, tid, v);
-  };
+  int tile = blockIdx.x, item = 0;
+  bool have = tile < A.n_tiles, pending = false;
   float4 pre[8];
-  if (use_ring) {
-    for (int it = 0; it < nring - 1; ++it) issue(it);
-  } else if (n_items > 0) {
-    load_regs(0, pre);
-  }
-  bool pending = false;
-  for (int it = 0; it < n_items; ++it) {
-    const int item = it % per_tile;
-    if (use_ring) {
-      issue(it + nring - 1);
-      if (nring == 2) cp_async_wait<1>(); else if (nring == 3) cp_async_wait<2>(); else cp_async_wait<3>();
-      read_raw_atom(ring + (it % nring) * kAtomBytes, tid, pre);
-    }
+  if (have) load_atom_regs(A.X, A.ldx, (long long)tile * 128, A.M, 0, A.N, tid, pre);
+  while (have) {
     if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
     const bool is_y = item < ny;
     if (is_y) {
@@ -476,7 +422,13 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
     } else {
       store_atom_regs(pre, x_hi, x_lo, tid, true, nullptr);
     }
-    if (!use_ring && it + 1 < n_items) load_regs(it + 1, pre);
+    int ntile = tile, nitem = item + 1;
+    if (nitem == per_tile) { nitem = 0; ntile = tile + gridDim.x; }
+    const bool nhave = ntile < A.n_tiles;
+    if (nhave) {
+      if (nitem < ny) load_atom_regs(A.X, A.ldx, (long long)ntile * 128, A.M, 32 * nitem, A.N, tid, pre);
+      else            load_atom_regs(A.X2, A.ldx2, (long long)ntile * 128, A.M, 32 * (nitem - ny), A.K, tid, pre);
+    }
     fence_async_smem();
     __syncthreads();
     if (!is_y) {
@@ -497,9 +449,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
       pending = true;
       if (item == per_tile - 1) first = false;
     }
+    tile = ntile; item = nitem; have = nhave;
   }
   if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
-  cp_async_wait<0>();
   // bias gradient: column sums of dY gathered while staging
   if (A.db) {
 #pragma unroll
@@ -606,32 +558,30 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   if (tid < n_head) atomicAdd(dbh + tid, s_dbh[tid]);
 }
 
-// Input row of VanillaColorDecoder (src/models.py:87): [PE(d) | d | features] written in one pass.
+// Input row of VanillaColorDecoder (src/models.py:87): [PE(d) | d | features] written in one pass, 32 lanes per row.
 // PE layout per coordinate c: sin(2^k pi d_c), k < n_freqs, then cos(...) (src/models.py:36-39); the frequencies are
-// fl32(pi) * 2^k like the reference's `2**arange(n) * torch.pi` buffer, products rounded to fp32 before sinf/cosf.
+// fl32(pi) * 2^k like the reference's `2**arange(n) * torch.pi` buffer, products rounded to fp32 before sin/cos.
 __global__ void __launch_bounds__(256) color_input_kernel(const float* __restrict__ dirs, long long ld_dirs,
                                                           const float* __restrict__ feats, long long ld_feats, int n_freqs,
                                                           int feat_dim, float* __restrict__ out, long long ld_out, long long n) {
   const int pe = 6 * n_freqs;
-  const int width = pe + 3 + feat_dim;
-  const int lanes = 32;  // one warp per row
-  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / lanes;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
   const float* d = dirs + row * ld_dirs;
   float* o = out + row * ld_out;
-  for (int j = lane; j < ld_out; j += lanes) {
+  for (int j = lane; j < 3 * n_freqs; j += 32) {  // one (coordinate, frequency) pair per lane: sin and cos together
+    const int c = j / n_freqs, k = j % n_freqs;
+    const float arg = __fmul_rn(__ldg(d + c), ldexpf(3.14159274101257324219f, k));
+    float sv, cv;
+    sincosf(arg, &sv, &cv);
+    o[c * 2 * n_freqs + k] = sv;
+    o[c * 2 * n_freqs + n_freqs + k] = cv;
+  }
+  for (int j = pe + lane; j < ld_out; j += 32) {
     float v = 0.f;
-    if (j < pe) {
-      const int c = j / (2 * n_freqs), r = j % (2 * n_freqs);
-      const int k = r % n_freqs;
-      const float arg = __fmul_rn(__ldg(d + c), ldexpf(3.14159274101257324219f, k));
-      v = (r < n_freqs) ? sinf(arg) : cosf(arg);
-    } else if (j < pe + 3) {
-      v = __ldg(d + (j - pe));
-    } else if (j < width) {
-      v = __ldg(feats + row * ld_feats + (j - pe - 3));
-    }
+    if (j < pe + 3) v = __ldg(d + (j - pe));
+    else if (j < pe + 3 + feat_dim) v = __ldg(feats + row * ld_feats + (j - pe - 3));
     o[j] = v;
   }
 }
@@ -644,25 +594,20 @@ int check_lin(long long M, int N, int K) {
 }
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// shared-memory plan of linear_kernel: weight images + one operand stage + cp.async ring; keeps two CTAs per SM
-// (113 KB each) whenever at least a 2-slot ring fits, else one CTA with the deepest ring.
-size_t plan_smem(int n, int k, int* ring) {
+// shared-memory plan of linear_kernel: weight images + S operand stages (32 KB each) + 16 KB epilogue staging
+size_t plan_smem(int n, int k, int* stages) {
   const size_t w_stride = ((((size_t)(n + 15) & ~15) * 128) + 1023) & ~(size_t)1023;
-  const size_t base = 2 * ((k + 31) / 32) * w_stride + 2 * kAtomBytes + 1024;
-  const size_t two_cta = 113 * 1024, one_cta = 226 * 1024;
-  int r;
-  if (base + 3 * kAtomBytes <= two_cta) r = 3;
-  else if (base + 2 * kAtomBytes <= two_cta) r = 2;
-  else {
-    r = (int)((one_cta - base) / kAtomBytes);
-    r = r > kMaxRing ? kMaxRing : (r < 2 ? 2 : r);
-  }
-  *ring = r;
-  return base + (size_t)r * kAtomBytes;
+  const size_t fixed = 2 * ((k + 31) / 32) * w_stride + kAtomBytes + 1024;
+  int s = (int)((226 * 1024 - fixed) / (2 * kAtomBytes));
+  s = s > kMaxStages ? kMaxStages : s;
+  *stages = s;
+  return fixed + (size_t)s * 2 * kAtomBytes;
 }
 
 template <typename Kern>
-int launch_lin(Kern kern, const LinArgs& A, size_t smem, cudaStream_t st, const char* name) {
+int launch_lin(Kern kern, LinArgs& A, cudaStream_t st, const char* name) {
+  const size_t smem = plan_smem(A.N, A.K, &A.ring);
+  TNF_REQUIRE(A.ring >= 2, "layer too large for the shared-memory plan (n=%d, k=%d)", A.N, A.K);
   static thread_local const void* configured[8] = {nullptr};
   bool done = false;
   for (auto c : configured) done |= (c == (const void*)kern);
@@ -670,9 +615,8 @@ int launch_lin(Kern kern, const LinArgs& A, size_t smem, cudaStream_t st, const 
     TNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     for (auto& c : configured) if (!c) { c = (const void*)kern; break; }
   }
-  const int per_sm = smem <= 113 * 1024 ? 2 : 1;
-  const int grid = A.n_tiles < per_sm * sm_count() ? A.n_tiles : per_sm * sm_count();
-  kern<<<grid, kThreads, smem, st>>>(A);
+  const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
+  kern<<<grid, kWsThreads, smem, st>>>(A);
   TNF_LAUNCH_CHECK(name);
   return TNF_OK;
 }
@@ -694,8 +638,7 @@ extern "C" int tnf_linear_fwd(const float* x, int64_t ldx, const float* weight, 
   A.X = x; A.ldx = ldx; A.W = weight; A.bias = bias; A.Y = y; A.ldy = ldy; A.M = m; A.N = n; A.K = k; A.relu = relu;
   A.head_w = head_w; A.head_b = head_b; A.head_out = head_out; A.n_head = n_head; A.head_act = head_act;
   A.n_tiles = (int)ceil_div(m, 128);
-  const size_t smem = plan_smem(n, k, &A.ring);
-  return launch_lin(linear_kernel<0>, A, smem, static_cast<cudaStream_t>(stream), "linear_fwd_kernel");
+  return launch_lin(linear_kernel<0>, A, static_cast<cudaStream_t>(stream), "linear_fwd_kernel");
 }
 
 extern "C" int tnf_linear_bwd_data(const float* dy, int64_t lddy, const float* weight, float* dx, int64_t lddx,
@@ -710,8 +653,7 @@ extern "C" int tnf_linear_bwd_data(const float* dy, int64_t lddy, const float* w
   LinArgs A{};
   A.X = dy; A.ldx = lddy; A.W = weight; A.Y = dx; A.ldy = lddx; A.X2 = relu_src; A.ldx2 = ldrs; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);
-  const size_t smem = plan_smem(n, k, &A.ring);
-  return launch_lin(linear_kernel<1>, A, smem, static_cast<cudaStream_t>(stream), "linear_dgrad_kernel");
+  return launch_lin(linear_kernel<1>, A, static_cast<cudaStream_t>(stream), "linear_dgrad_kernel");
 }
 
 extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dweight, float* dbias,
@@ -725,19 +667,14 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   LinArgs A{};
   A.X = dy; A.ldx = lddy; A.X2 = x; A.ldx2 = ldx; A.dW = dweight; A.db = dbias; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);
-  const size_t base = (size_t)(2 * ((n + 31) / 32) + 2) * kAtomBytes + 1024;
-  // two CTAs per SM when the operand images plus a 2-slot ring fit in 113 KB, else one CTA with the deepest ring
-  int ctas_per_sm = 1;
-  if (base + 2 * kAtomBytes <= 113 * 1024) { A.ring = (base + 3 * kAtomBytes <= 113 * 1024) ? 3 : 2; ctas_per_sm = 2; }
-  else { A.ring = (int)((226 * 1024 - base) / kAtomBytes); A.ring = A.ring > kMaxRing ? kMaxRing : (A.ring < 2 ? 2 : A.ring); }
-  const size_t smem = base + (size_t)A.ring * kAtomBytes;
+  const size_t smem = (size_t)(2 * ((n + 31) / 32) + 2) * kAtomBytes + 1024;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static thread_local bool configured = false;
   if (!configured) {
-    TNF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    TNF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  const int grid = A.n_tiles < ctas_per_sm * sm_count() ? A.n_tiles : ctas_per_sm * sm_count();
+  const int grid = A.n_tiles < 2 * sm_count() ? A.n_tiles : 2 * sm_count();
   wgrad_kernel<<<grid, kThreads, smem, st>>>(A);
   TNF_LAUNCH_CHECK("linear_wgrad_kernel");
   return TNF_OK;
