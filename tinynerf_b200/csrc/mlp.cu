@@ -143,6 +143,40 @@ __device__ __forceinline__ void load_atom_regs(const float* __restrict__ g, long
     }
   }
 }
+// Asynchronous variant: the same per-thread 16-byte chunks are copied global -> shared with cp.async into a raw
+// ring slot (zero-filled outside the matrix), so several atoms per CTA are in flight without holding registers;
+// each thread later reads back exactly the chunks it copied (no cross-thread hazard), splits and writes the operand
+// images.  Requires 16-byte aligned rows (ld % 4 == 0, aligned base); otherwise callers use load_atom_regs.
+__device__ __forceinline__ void cp_async_atom(const float* __restrict__ g, long long ld, long long row0, long long rows,
+                                              int col0, int cols, int tid, uint8_t* raw) {
+  const int c = tid & 7;
+  const int r0 = tid >> 3;
+  const int col = col0 + 4 * c;
+  int nbytes = (cols - col) * 4;
+  nbytes = nbytes < 0 ? 0 : (nbytes > 16 ? 16 : nbytes);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 16 * i;
+    const long long row = row0 + r;
+    const bool ok = row < rows && nbytes > 0;
+    const float* src = ok ? (g + row * ld + col) : g;
+    const uint32_t dst = smem_u32(raw + r * 128 + c * 16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? nbytes : 0) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // pending in 0..3
+  if (pending <= 0) cp_async_wait<0>(); else if (pending == 1) cp_async_wait<1>(); else if (pending == 2) cp_async_wait<2>(); else cp_async_wait<3>();
+}
+__device__ __forceinline__ void read_raw_atom(const uint8_t* raw, int tid, float4 v[8]) {
+  const int c = tid & 7;
+  const int r0 = tid >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(raw + (r0 + 16 * i) * 128 + c * 16);
+}
+
 // mn32: SWIZZLE_128B_BASE32B image (32-byte chunks XOR row%4) for MN-major reads, else SWIZZLE_128B (16-byte
 // chunks XOR row%8) for K-major reads.
 __device__ __forceinline__ int swz_off(int r, int c, bool mn32) {
@@ -184,6 +218,7 @@ struct LinArgs {
   int relu;
   int n_tiles;
   int ring;        // operand stages of the warp-specialised kernels (2..4), chosen by the host from the smem budget
+  int raw;         // raw cp.async ring slots of the loaders (0 = register prefetch, else 2..kRawRing)
 };
 
 __device__ __forceinline__ float head_activation(float x, int act) {
@@ -201,6 +236,7 @@ __device__ __forceinline__ float head_activation(float x, int act) {
 // so HBM loads, tensor-core work and the epilogue of consecutive tiles overlap inside one CTA.
 constexpr int kWsThreads = 288;
 constexpr int kMaxStages = 4;
+constexpr int kRawRing = 4;   // raw cp.async ring slots of the loaders (3 atoms = 48 KB of loads in flight per SM)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -249,20 +285,42 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
 
   if (warp < 4) {
     // ===== loaders =====
+    // Global loads run kRawRing-1 atoms ahead through a raw cp.async ring (16-byte aligned inputs), or one atom
+    // ahead in registers otherwise; then split hi/lo and write the swizzled operand stage.
     float4 pre[8];
-    if (n_items > 0) load_atom_regs(A.X, A.ldx, (long long)blockIdx.x * 128, A.M, 0, KD, tid, pre);
+    uint8_t* raw = epi + kAtomBytes;
+    const int nraw = A.raw;
+    const bool use_ring = nraw >= 2 && ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0);
+    auto issue = [&](int it) {
+      if (it < n_items) {
+        const int t = blockIdx.x + (it / ka) * gridDim.x, jj = it % ka;
+        cp_async_atom(A.X, A.ldx, (long long)t * 128, A.M, 32 * jj, KD, tid, raw + (it % nraw) * kAtomBytes);
+      }
+      cp_async_commit();  // (possibly empty) group: keeps the group count uniform
+    };
+    if (use_ring) {
+      for (int it = 0; it < nraw - 1; ++it) issue(it);
+    } else if (n_items > 0) {
+      load_atom_regs(A.X, A.ldx, (long long)blockIdx.x * 128, A.M, 0, KD, tid, pre);
+    }
     for (int it = 0; it < n_items; ++it) {
       const int s = it % S;
+      if (use_ring) {
+        issue(it + nraw - 1);            // reuses the slot read in the previous iteration (by this same thread)
+        cp_async_wait_dyn(nraw - 1);     // item `it` has landed
+        read_raw_atom(raw + (it % nraw) * kAtomBytes, tid, pre);
+      }
       mbar_wait(&s_empty[s], ((it / S) & 1) ^ 1);   // the MMAs that read this stage have completed
       uint8_t* a_hi = stages + s * 2 * kAtomBytes;
       store_atom_regs(pre, a_hi, a_hi + kAtomBytes, tid, false, nullptr);
-      if (it + 1 < n_items) {
+      if (!use_ring && it + 1 < n_items) {
         const int nt = blockIdx.x + ((it + 1) / ka) * gridDim.x, nj = (it + 1) % ka;
         load_atom_regs(A.X, A.ldx, (long long)nt * 128, A.M, 32 * nj, KD, tid, pre);
       }
       fence_async_smem();
       mbar_arrive(&s_full[s]);
     }
+    cp_async_wait<0>();
   } else if (warp == 8) {
     // ===== MMA issuer =====
     const uint32_t idesc = instr_desc(128, ND, false, MODE == 1);
@@ -594,19 +652,29 @@ int check_lin(long long M, int N, int K) {
 }
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// shared-memory plan of linear_kernel: weight images + S operand stages (32 KB each) + 16 KB epilogue staging
-size_t plan_smem(int n, int k, int* stages) {
+// shared-memory plan of linear_kernel: weight images + S operand stages (32 KB each) + 16 KB epilogue staging +
+// raw cp.async ring (16 KB per slot).  Prefers a deep raw ring (loads in flight), then more operand stages.
+size_t plan_smem(int n, int k, int* stages, int* raw) {
   const size_t w_stride = ((((size_t)(n + 15) & ~15) * 128) + 1023) & ~(size_t)1023;
   const size_t fixed = 2 * ((k + 31) / 32) * w_stride + kAtomBytes + 1024;
-  int s = (int)((226 * 1024 - fixed) / (2 * kAtomBytes));
-  s = s > kMaxStages ? kMaxStages : s;
-  *stages = s;
-  return fixed + (size_t)s * 2 * kAtomBytes;
+  const size_t budget = 226 * 1024;
+  for (int r : {kRawRing, 3, 2, 0}) {
+    const size_t f = fixed + (size_t)r * kAtomBytes;
+    if (f + 2 * 2 * kAtomBytes > budget) continue;
+    int s = (int)((budget - f) / (2 * kAtomBytes));
+    s = s > kMaxStages ? kMaxStages : s;
+    *stages = s;
+    *raw = r;
+    return f + (size_t)s * 2 * kAtomBytes;
+  }
+  *stages = 0;
+  *raw = 0;
+  return 0;
 }
 
 template <typename Kern>
 int launch_lin(Kern kern, LinArgs& A, cudaStream_t st, const char* name) {
-  const size_t smem = plan_smem(A.N, A.K, &A.ring);
+  const size_t smem = plan_smem(A.N, A.K, &A.ring, &A.raw);
   TNF_REQUIRE(A.ring >= 2, "layer too large for the shared-memory plan (n=%d, k=%d)", A.N, A.K);
   static thread_local const void* configured[8] = {nullptr};
   bool done = false;
