@@ -42,11 +42,12 @@ SEED = 1234
 
 
 def measured_peaks():
+    """(HBM GB/s, dense TF32 TFLOP/s = half the measured bf16 burst figure, source)"""
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]) / 2, "measured"
+    return 6650.0, 1590.0 / 2, "fallback"
 
 
 # ---- synthetic scene (SURVEY 8d config 2) -------------------------------------------------------
@@ -186,20 +187,27 @@ def weights_microbench(dev, logn: int, peak: float):
     return out
 
 
-def summarise_profile(records, peak):
-    """records: (name, start, end, bytes) -> per-entry-point totals and the dominant one."""
+def summarise_profile(records, peak, tf32_peak):
+    """records: (name, start, end, bytes, flops) -> per-entry-point totals and the dominant one."""
     agg = {}
-    for name, s, e, nbytes in records:
-        a = agg.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0})
+    for name, s, e, nbytes, flops in records:
+        a = agg.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0, "flops": 0})
         a["ms"] += s.elapsed_time(e)
         a["launches"] += 1
         a["bytes"] += nbytes
+        a["flops"] += flops
     table = {}
     for name, a in agg.items():
         gbs = a["bytes"] / a["ms"] / 1e6 if a["ms"] > 0 else 0.0
-        table[name] = {"launches": a["launches"], "avg_us": round(a["ms"] / a["launches"] * 1e3, 2),
-                       "total_ms": round(a["ms"], 3), "alg_MB_per_launch": round(a["bytes"] / a["launches"] / 1e6, 3),
-                       "GB/s": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        row = {"launches": a["launches"], "avg_us": round(a["ms"] / a["launches"] * 1e3, 2),
+               "total_ms": round(a["ms"], 3), "alg_MB_per_launch": round(a["bytes"] / a["launches"] / 1e6, 3),
+               "GB/s": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        if a["flops"]:
+            # issued tensor work = 3 TF32 MMAs per fp32-accurate product ("3xTF32")
+            tf = a["flops"] / a["ms"] / 1e9
+            row.update({"TFLOP/s_fp32_equiv": round(tf, 2), "TFLOP/s_tf32_issued": round(3 * tf, 2),
+                        "tensor_frac_issued": round(3 * tf / tf32_peak, 4)})
+        table[name] = row
     dom = max(table, key=lambda k: table[k]["total_ms"]) if table else None
     return table, dom
 
@@ -239,7 +247,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    peak, peak_src = measured_peaks()
+    peak, tf32_peak, peak_src = measured_peaks()
 
     o, d, rgbs = make_scene(N_STORE, SEED)
     analytic = synthetic.analytic_grid(128, seed=SEED + 2).to(dev)
@@ -302,7 +310,7 @@ def main():
     # same trainer, same timed-region structure, now with a CUDA-event pair around every C-ABI call on its
     # launching stream (kept out of the headline pass: ~30 extra event records per step)
     _, _, recs, _ = timed(tr, min(args.steps, 16), False, profile=True)
-    table, dom = summarise_profile(recs, peak)
+    table, dom = summarise_profile(recs, peak, tf32_peak)
     del tr
     torch.cuda.empty_cache()
 

@@ -121,13 +121,14 @@ def load():
 KERNELS_PER_CALL = {"tnf_weights_fwd": 1, "tnf_weights_bwd": 1, "tnf_march_count": 2, "tnf_march_pack": 1,
                     "tnf_occ_query": 1, "tnf_occ_update_coords": 1, "tnf_occ_update_apply": 1, "tnf_kplanes_fwd": 1,
                     "tnf_kplanes_bwd": 1, "tnf_cobafa_fwd": 1, "tnf_cobafa_bwd": 1, "tnf_composite_fwd": 1,
-                    "tnf_composite_bwd": 1, "tnf_tv_fwd": 1, "tnf_tv_bwd": 1, "tnf_adam_step": 1}
+                    "tnf_composite_bwd": 1, "tnf_tv_fwd": 1, "tnf_tv_bwd": 1, "tnf_adam_step": 1, "tnf_linear_fwd": 1,
+                    "tnf_linear_bwd_data": 1, "tnf_linear_bwd_weight": 1, "tnf_head_bwd": 1, "tnf_color_input": 1}
 launch_count = 0
 _prof = None
 
 
 def profile_start():
-    """Start recording (name, start event, end event, algorithmic bytes) for every C-ABI call."""
+    """Start recording (name, start event, end event, algorithmic bytes, flops) for every C-ABI call."""
     global _prof
     _prof = []
 
@@ -138,7 +139,7 @@ def profile_stop():
     return out
 
 
-def call(name: str, *args, nbytes: int = 0, extra_kernels: int = 0):
+def call(name: str, *args, nbytes: int = 0, extra_kernels: int = 0, flops: int = 0):
     """Invoke a C-ABI entry point on the current stream, raise on error, count its kernel launches and,
     when profiling is on, bracket it with CUDA events on the launching stream."""
     global launch_count
@@ -150,7 +151,7 @@ def call(name: str, *args, nbytes: int = 0, extra_kernels: int = 0):
         s.record()
         rc = fn(*args)
         e.record()
-        _prof.append((name, s, e, nbytes))
+        _prof.append((name, s, e, nbytes, flops))
     check(rc, name)
     launch_count += KERNELS_PER_CALL.get(name, 1) + extra_kernels
 

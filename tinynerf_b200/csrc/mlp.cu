@@ -363,6 +363,28 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
       const bool write_y = (MODE == 1) || (A.Y != nullptr);
       for (int c0 = 0; c0 < ND; c0 += 32) {
+        // coalesced-store mapping of this thread for the chunk: 16-byte column chunk c of rows et/8 + 16 i
+        const int c = et & 7;
+        const int col = c0 + 4 * c;
+        const int ncols = (MODE == 0) ? A.N : A.K;
+        float4 xin[8];
+        if (MODE == 1 && A.X2) {  // ReLU-backward mask source: issue the loads now, they land during the TMEM read
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long grow = row0 + (et >> 3) + 16 * i;
+            xin[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (grow < A.M && col < ncols) {
+              const float* xp = A.X2 + grow * A.ldx2 + col;
+              if (col + 3 < ncols) {
+                xin[i] = __ldg(reinterpret_cast<const float4*>(xp));
+              } else {
+                xin[i].x = __ldg(xp);
+                if (col + 1 < ncols) xin[i].y = __ldg(xp + 1);
+                if (col + 2 < ncols) xin[i].z = __ldg(xp + 2);
+              }
+            }
+          }
+        }
         float v[32];
         tmem_ld32(taddr + c0, v);
         if (c0 + 32 >= ND) { tc_fence_before(); mbar_arrive(&s_tempty[b]); }  // accumulator b fully read by this thread
@@ -385,9 +407,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(epi + swz_off(r, q, false)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           epi_bar_sync();
-          const int c = et & 7;
-          const int col = c0 + 4 * c;
-          const int ncols = (MODE == 0) ? A.N : A.K;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = (et >> 3) + 16 * i;
@@ -395,16 +414,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
             if (grow < A.M && col < ncols) {
               float4 o = *reinterpret_cast<const float4*>(epi + swz_off(rr, c, false));
               if (MODE == 1 && A.X2) {  // ReLU backward of the layer that produced this layer's input
-                const float* xp = A.X2 + grow * A.ldx2 + col;
-                if (col + 3 < ncols) {
-                  const float4 xin = __ldg(reinterpret_cast<const float4*>(xp));
-                  o.x = xin.x > 0.f ? o.x : 0.f; o.y = xin.y > 0.f ? o.y : 0.f;
-                  o.z = xin.z > 0.f ? o.z : 0.f; o.w = xin.w > 0.f ? o.w : 0.f;
-                } else {
-                  o.x = __ldg(xp) > 0.f ? o.x : 0.f;
-                  if (col + 1 < ncols) o.y = __ldg(xp + 1) > 0.f ? o.y : 0.f;
-                  if (col + 2 < ncols) o.z = __ldg(xp + 2) > 0.f ? o.z : 0.f;
-                }
+                o.x = xin[i].x > 0.f ? o.x : 0.f; o.y = xin[i].y > 0.f ? o.y : 0.f;
+                o.z = xin[i].z > 0.f ? o.z : 0.f; o.w = xin[i].w > 0.f ? o.w : 0.f;
               }
               float* yp = A.Y + grow * A.ldy + col;
               if (col + 3 < ncols) {
@@ -430,98 +441,149 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
 }
 
 
-// wgrad: dW[n,k] += sum_m dY[m,n] X[m,k] ; db[n] += sum_m dY[m,n].  D[N_out, 32] per X atom lives in TMEM for the
-// whole kernel (columns 32*j.. of atom j) and is flushed with atomics once per CTA.
-__global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
+// wgrad: dW[n,k] += sum_m dY[m,n] X[m,k] ; db[n] += sum_m dY[m,n].  Warp-specialised like linear_kernel:
+//   warps 0-3 loaders: per 128-sample tile stage the dY atoms (one resident set) and then the X atoms (ring of
+//                      stages), global loads running ahead through the raw cp.async ring; column sums of dY
+//                      accumulate in registers for the bias gradient
+//   warp  4   MMA    : per X atom j: D[N_out, 32j..32j+32) += dY^T X_j, 16 k-steps x 3 (3xTF32), both operands
+//                      MN-major; D lives in TMEM for the whole kernel and is flushed with atomics once per CTA.
+constexpr int kWgThreads = 160;
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t s_bar;
+  __shared__ uint64_t s_xfull[kMaxStages], s_xempty[kMaxStages], s_yfull, s_yempty, s_done;
   __shared__ uint32_t s_tmem;
   __shared__ float s_db[128];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ny = (A.N + 31) >> 5;   // dY atoms (N_out / 32)
   const int kx = (A.K + 31) >> 5;   // X atoms
+  const int S = A.ring, nraw = A.raw;
   uint8_t* y_hi = smem;
   uint8_t* y_lo = smem + ny * kAtomBytes;
-  uint8_t* x_hi = smem + 2 * ny * kAtomBytes;
-  uint8_t* x_lo = x_hi + kAtomBytes;
-  const int MM = (A.N <= 64) ? 64 : 128;  // UMMA M = N_out
-  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  uint8_t* xst = smem + 2 * ny * kAtomBytes;      // X stage s: hi at +s*2*kAtomBytes, lo right after
+  uint8_t* raw = xst + S * 2 * kAtomBytes;
+  const int MM = (A.N <= 64) ? 64 : 128;          // UMMA M = N_out
   const int ncol = kx * 32;
   const int tmem_cols = ncol <= 32 ? 32 : (ncol <= 64 ? 64 : (ncol <= 128 ? 128 : 256));
-  if (warp == 0) tmem_alloc(&s_tmem, tmem_cols);
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&s_xfull[s], 128); mbar_init(&s_xempty[s], 1); }
+    mbar_init(&s_yfull, 128 * ny); mbar_init(&s_yempty, 1); mbar_init(&s_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(&s_tmem, tmem_cols);
   if (tid < 128) s_db[tid] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = s_tmem;
-  const uint32_t idesc = instr_desc(MM, 32, true, true);
-  uint32_t phase = 0;
-  bool first = true;
-  float colsum[kMaxKAtoms - 1][4];
-#pragma unroll
-  for (int a = 0; a < kMaxKAtoms - 1; ++a) colsum[a][0] = colsum[a][1] = colsum[a][2] = colsum[a][3] = 0.f;
-
-  // Flattened pipeline over (tile, item): items 0..ny-1 stage the dY atoms of the tile, items ny.. stage one X atom
-  // each and trigger its MMAs; the next item's global loads are in flight (registers) during the MMAs.
   const int per_tile = ny + kx;
-  int tile = blockIdx.x, item = 0;
-  bool have = tile < A.n_tiles, pending = false;
-  float4 pre[8];
-  if (have) load_atom_regs(A.X, A.ldx, (long long)tile * 128, A.M, 0, A.N, tid, pre);
-  while (have) {
-    if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
-    const bool is_y = item < ny;
-    if (is_y) {
-      // column sums of dY for the bias gradient (static register indexing)
+  const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_items = my_tiles * per_tile;
+
+  if (warp < 4) {
+    // ===== loaders =====
+    float colsum[kMaxKAtoms - 1][4];
+#pragma unroll
+    for (int a = 0; a < kMaxKAtoms - 1; ++a) colsum[a][0] = colsum[a][1] = colsum[a][2] = colsum[a][3] = 0.f;
+    const bool use_ring = nraw >= 2 && ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0) &&
+                          ((A.ldx2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X2) & 15u) == 0);
+    auto src_of = [&](int it, const float*& g, long long& ld, int& col0, int& cols, long long& row0) {
+      const int t = blockIdx.x + (it / per_tile) * gridDim.x, item = it % per_tile;
+      row0 = (long long)t * 128;
+      if (item < ny) { g = A.X; ld = A.ldx; col0 = 32 * item; cols = A.N; }
+      else { g = A.X2; ld = A.ldx2; col0 = 32 * (item - ny); cols = A.K; }
+    };
+    auto issue = [&](int it) {
+      if (it < n_items) {
+        const float* g; long long ld, row0; int col0, cols;
+        src_of(it, g, ld, col0, cols, row0);
+        cp_async_atom(g, ld, row0, A.M, col0, cols, tid, raw + (it % nraw) * kAtomBytes);
+      }
+      cp_async_commit();
+    };
+    auto load_regs = [&](int it, float4 v[8]) {
+      const float* g; long long ld, row0; int col0, cols;
+      src_of(it, g, ld, col0, cols, row0);
+      load_atom_regs(g, ld, row0, A.M, col0, cols, tid, v);
+    };
+    float4 pre[8];
+    if (use_ring) {
+      for (int it = 0; it < nraw - 1; ++it) issue(it);
+    } else if (n_items > 0) {
+      load_regs(0, pre);
+    }
+    int xi = 0;  // running X-item counter (stage ring position)
+    for (int it = 0; it < n_items; ++it) {
+      const int item = it % per_tile, tl = it / per_tile;
+      if (use_ring) {
+        issue(it + nraw - 1);
+        cp_async_wait_dyn(nraw - 1);
+        read_raw_atom(raw + (it % nraw) * kAtomBytes, tid, pre);
+      }
+      if (item < ny) {
+        if (item == 0) mbar_wait(&s_yempty, (tl & 1) ^ 1);   // the previous tile's MMAs have read the dY set
+#pragma unroll
+        for (int a = 0; a < kMaxKAtoms - 1; ++a)
+          if (a == item) store_atom_regs(pre, y_hi + a * kAtomBytes, y_lo + a * kAtomBytes, tid, true, colsum[a]);
+        if (!use_ring && it + 1 < n_items) load_regs(it + 1, pre);
+        fence_async_smem();
+        mbar_arrive(&s_yfull);
+      } else {
+        const int s = xi % S;
+        mbar_wait(&s_xempty[s], ((xi / S) & 1) ^ 1);
+        uint8_t* x_hi = xst + s * 2 * kAtomBytes;
+        store_atom_regs(pre, x_hi, x_hi + kAtomBytes, tid, true, nullptr);
+        if (!use_ring && it + 1 < n_items) load_regs(it + 1, pre);
+        fence_async_smem();
+        mbar_arrive(&s_xfull[s]);
+        ++xi;
+      }
+    }
+    cp_async_wait<0>();
+    // bias gradient: column sums of dY gathered while staging
+    if (A.db) {
 #pragma unroll
       for (int a = 0; a < kMaxKAtoms - 1; ++a)
-        if (a == item) store_atom_regs(pre, y_hi + a * kAtomBytes, y_lo + a * kAtomBytes, tid, true, colsum[a]);
-    } else {
-      store_atom_regs(pre, x_hi, x_lo, tid, true, nullptr);
+        if (a < ny)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) atomicAdd(&s_db[32 * a + 4 * (tid & 7) + q], colsum[a][q]);
     }
-    int ntile = tile, nitem = item + 1;
-    if (nitem == per_tile) { nitem = 0; ntile = tile + gridDim.x; }
-    const bool nhave = ntile < A.n_tiles;
-    if (nhave) {
-      if (nitem < ny) load_atom_regs(A.X, A.ldx, (long long)ntile * 128, A.M, 32 * nitem, A.N, tid, pre);
-      else            load_atom_regs(A.X2, A.ldx2, (long long)ntile * 128, A.M, 32 * (nitem - ny), A.K, tid, pre);
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (!is_y) {
-      const int j = item - ny;
-      if (tid == 0) {
+  } else {
+    // ===== MMA issuer =====
+    const uint32_t idesc = instr_desc(MM, 32, true, true);
+    int xi = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      mbar_wait(&s_yfull, tl & 1);
+      for (int j = 0; j < kx; ++j, ++xi) {
+        const int s = xi % S;
+        mbar_wait(&s_xfull[s], (xi / S) & 1);
         tc_fence_after();
-        const uint32_t yh = smem_u32(y_hi), yl = smem_u32(y_lo), xh = smem_u32(x_hi), xl = smem_u32(x_lo);
+        if (lane == 0) {
+          const uint32_t yh = smem_u32(y_hi), yl = smem_u32(y_lo);
+          const uint32_t xh = smem_u32(xst + s * 2 * kAtomBytes), xl = xh + kAtomBytes;
 #pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t ya = (pass == 1) ? yl : yh;
-          const uint32_t xa = (pass == 2) ? xl : xh;
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ya = (pass == 1) ? yl : yh;
+            const uint32_t xa = (pass == 2) ? xl : xh;
 #pragma unroll 1
-          for (int kk = 0; kk < 16; ++kk)  // 128 samples = 16 k-steps of 8 rows
-            mma_tf32(tmem_d + 32 * j, desc_mnmajor(ya, kk), desc_mnmajor(xa, kk), idesc, !(first && pass == 0 && kk == 0));
+            for (int kk = 0; kk < 16; ++kk)  // 128 samples = 16 k-steps of 8 rows
+              mma_tf32(tmem_d + 32 * j, desc_mnmajor(ya, kk), desc_mnmajor(xa, kk), idesc, !(tl == 0 && pass == 0 && kk == 0));
+          }
+          mma_commit(&s_xempty[s]);
+          if (j == kx - 1) mma_commit(&s_yempty);
         }
-        mma_commit(&s_bar);
+        __syncwarp();
       }
-      pending = true;
-      if (item == per_tile - 1) first = false;
     }
-    tile = ntile; item = nitem; have = nhave;
+    if (lane == 0) mma_commit(&s_done);
+    __syncwarp();
   }
-  if (pending) { mbar_wait(&s_bar, phase); phase ^= 1; pending = false; }
-  // bias gradient: column sums of dY gathered while staging
-  if (A.db) {
-#pragma unroll
-    for (int a = 0; a < kMaxKAtoms - 1; ++a)
-      if (a < ny)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) atomicAdd(&s_db[32 * a + 4 * (tid & 7) + q], colsum[a][q]);
-  }
+  mbar_wait(&s_done, 0);   // every MMA of this CTA has completed
   tc_fence_after();
   __syncthreads();
   if (A.db && tid < A.N) atomicAdd(A.db + tid, s_db[tid]);
-  if (!first) {
+  if (my_tiles > 0 && warp < 4) {
     // D rows = output features: M=128 -> lane == row; M=64 -> row m sits in lane 32*(m/16) + m%16
     int n_out;
     bool active;
@@ -540,7 +602,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const LinArgs A) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+  if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
 }
 
 // Backward of a fused head (n_head <= 4 outputs on top of a ReLU hidden layer H[M,N]):
@@ -551,26 +613,29 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ out, const float* __restrict__ dout,
                                                        float* __restrict__ dH, float* __restrict__ dWh, float* __restrict__ dbh,
                                                        long long M, int N, int n_head, int act) {
+  // N/4 lanes per row (one float4 of H each), 32/(N/4) rows per warp iteration; N in {32, 64, 128}
   __shared__ float s_dw[4 * 128];
   __shared__ float s_dbh[4];
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < 4 * 128; i += 256) s_dw[i] = 0.f;
   if (tid < 4) s_dbh[tid] = 0.f;
   __syncthreads();
-  const int warps_total = gridDim.x * 8;
-  const int wid = blockIdx.x * 8 + (tid >> 5);
-  float wreg[4][4];  // Wh[o][lane + 32*q]
-  float dwacc[4][4];
+  const int lpr = N >> 2;            // lanes per row
+  const int rpw = 32 / lpr;          // rows per warp iteration
+  const int sub = lane / lpr;        // row slot of this lane
+  const int c4 = (lane % lpr) * 4;   // first column of this lane
+  const long long warps_total = (long long)gridDim.x * 8;
+  const long long wid = blockIdx.x * 8LL + (tid >> 5);
+  float4 wreg[4], dwacc[4];
 #pragma unroll
-  for (int o = 0; o < 4; ++o)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = lane + 32 * q;
-      wreg[o][q] = (o < n_head && j < N) ? __ldg(Wh + o * N + j) : 0.f;
-      dwacc[o][q] = 0.f;
-    }
+  for (int o = 0; o < 4; ++o) {
+    wreg[o] = (o < n_head) ? __ldg(reinterpret_cast<const float4*>(Wh + o * N + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dwacc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long m = wid; m < M; m += warps_total) {
+  for (long long m0 = wid * rpw; m0 < M; m0 += warps_total * rpw) {
+    const long long m = m0 + sub;
+    if (m >= M) continue;
     float dpre[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
@@ -578,9 +643,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       if (o < n_head) {
         const float y = __ldg(out + m * n_head + o), g = __ldg(dout + m * n_head + o);
         if (act == 1) {
-          // y = exp(x-1); backward multiplies by exp(clamp(x-1, -15, 15))
-          const float xm1 = logf(y);
-          d = g * ((xm1 > 15.f) ? expf(15.f) : ((xm1 < -15.f) ? expf(-15.f) : y));
+          // y = exp(x-1); backward multiplies by exp(clamp(x-1, -15, 15)) (src/models.py:52-53)
+          d = g * fminf(fmaxf(y, 3.0590232050182579e-07f), 3269017.372472110639f);
         } else if (act == 2) {
           d = g * y * (1.f - y);
         } else {
@@ -588,28 +652,25 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
         }
       }
       dpre[o] = d;
-      dbacc[o] += d;
+      if (lane % lpr == 0) dbacc[o] += d;
     }
+    const float4 h = __ldg(reinterpret_cast<const float4*>(H + m * ldh + c4));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = lane + 32 * q;
-      if (j < N) {
-        const float h = __ldg(H + m * ldh + j);
-        float acc = 0.f;
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          acc = __fmaf_rn(dpre[o], wreg[o][q], acc);
-          dwacc[o][q] = __fmaf_rn(dpre[o], h, dwacc[o][q]);
-        }
-        dH[m * ldh + j] = h > 0.f ? acc : 0.f;
-      }
+    for (int o = 0; o < 4; ++o) {
+      acc.x = __fmaf_rn(dpre[o], wreg[o].x, acc.x); acc.y = __fmaf_rn(dpre[o], wreg[o].y, acc.y);
+      acc.z = __fmaf_rn(dpre[o], wreg[o].z, acc.z); acc.w = __fmaf_rn(dpre[o], wreg[o].w, acc.w);
+      dwacc[o].x = __fmaf_rn(dpre[o], h.x, dwacc[o].x); dwacc[o].y = __fmaf_rn(dpre[o], h.y, dwacc[o].y);
+      dwacc[o].z = __fmaf_rn(dpre[o], h.z, dwacc[o].z); dwacc[o].w = __fmaf_rn(dpre[o], h.w, dwacc[o].w);
     }
+    *reinterpret_cast<float4*>(dH + m * ldh + c4) =
+        make_float4(h.x > 0.f ? acc.x : 0.f, h.y > 0.f ? acc.y : 0.f, h.z > 0.f ? acc.z : 0.f, h.w > 0.f ? acc.w : 0.f);
   }
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) atomicAdd(&s_dw[o * 128 + lane + 32 * q], dwacc[o][q]);
-    if (lane == 0) atomicAdd(&s_dbh[o], dbacc[o]);
+    atomicAdd(&s_dw[o * 128 + c4 + 0], dwacc[o].x); atomicAdd(&s_dw[o * 128 + c4 + 1], dwacc[o].y);
+    atomicAdd(&s_dw[o * 128 + c4 + 2], dwacc[o].z); atomicAdd(&s_dw[o * 128 + c4 + 3], dwacc[o].w);
+    atomicAdd(&s_dbh[o], dbacc[o]);
   }
   __syncthreads();
   for (int i = tid; i < n_head * N; i += 256) atomicAdd(dWh + i, s_dw[(i / N) * 128 + (i % N)]);
@@ -735,15 +796,30 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   LinArgs A{};
   A.X = dy; A.ldx = lddy; A.X2 = x; A.ldx2 = ldx; A.dW = dweight; A.db = dbias; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);
-  const size_t smem = (size_t)(2 * ((n + 31) / 32) + 2) * kAtomBytes + 1024;
+  // shared-memory plan: resident dY set + S X stages (32 KB each) + raw cp.async ring (16 KB per slot)
+  const size_t fixed = (size_t)(2 * ((n + 31) / 32)) * kAtomBytes + 1024;
+  const size_t budget = 226 * 1024;
+  size_t smem = 0;
+  for (int r : {kRawRing, 3, 2, 0}) {
+    const size_t f = fixed + (size_t)r * kAtomBytes;
+    if (f + 2 * kAtomBytes > budget) continue;
+    int st_ = (int)((budget - f) / (2 * kAtomBytes));
+    if (st_ < 1) continue;
+    if (r >= 3 && st_ < 2) continue;   // prefer two X stages over a deeper raw ring
+    A.ring = st_ > kMaxStages ? kMaxStages : st_;
+    A.raw = r;
+    smem = f + (size_t)A.ring * 2 * kAtomBytes;
+    break;
+  }
+  TNF_REQUIRE(smem > 0, "layer too large for the wgrad shared-memory plan (n=%d)", n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static thread_local bool configured = false;
   if (!configured) {
-    TNF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TNF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
-  const int grid = A.n_tiles < 2 * sm_count() ? A.n_tiles : 2 * sm_count();
-  wgrad_kernel<<<grid, kThreads, smem, st>>>(A);
+  const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
+  wgrad_kernel<<<grid, kWgThreads, smem, st>>>(A);
   TNF_LAUNCH_CHECK("linear_wgrad_kernel");
   return TNF_OK;
 }
@@ -765,10 +841,12 @@ extern "C" int tnf_head_bwd(const float* h, int64_t ldh, const float* head_w, co
                             float* dhead_w, float* dhead_b, int64_t m, int32_t n, int32_t n_head, int32_t head_act,
                             void* stream) {
   using namespace tnf;
-  TNF_REQUIRE(m >= 0 && n >= 1 && n <= 128 && n_head >= 1 && n_head <= 4, "bad head shape");
+  TNF_REQUIRE(m >= 0 && (n == 32 || n == 64 || n == 128) && n_head >= 1 && n_head <= 4, "bad head shape");
+  TNF_REQUIRE((ldh & 3) == 0 && ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(head_w)) & 15u) == 0,
+              "h/dh/head_w must be 16-byte aligned with ldh %% 4 == 0");
   if (m == 0) return TNF_OK;
   TNF_REQUIRE(h && head_w && out && dout && dh && dhead_w && dhead_b, "null pointer");
-  const int grid = (int)(ceil_div(m, 8 * 16) < 4 * sm_count() ? ceil_div(m, 8 * 16) : 4 * sm_count());
+  const int grid = (int)(ceil_div(m, 8 * 8) < 8 * sm_count() ? ceil_div(m, 8 * 8) : 8 * sm_count());
   head_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ldh, head_w, out, dout, dh, dhead_w, dhead_b, m, n,
                                                                          n_head, head_act);
   TNF_LAUNCH_CHECK("head_bwd_kernel");

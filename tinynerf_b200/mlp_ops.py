@@ -59,9 +59,9 @@ def _lin_fwd(x, w, b, relu, head=None, head_act=0, want_y=True):
         hw, hb = head
         nh = hw.size(0)
         ho = torch.empty(m, nh, device=x.device)
-    flops = 2 * m * n * k
     _lib.call("tnf_linear_fwd", x.data_ptr(), x.stride(0), w.data_ptr(), _lib.ptr(b), _lib.ptr(y), n, m, n, k,
-              int(relu), _lib.ptr(hw), _lib.ptr(hb), _lib.ptr(ho), nh, head_act, _lib.stream_ptr(), nbytes=flops)
+              int(relu), _lib.ptr(hw), _lib.ptr(hb), _lib.ptr(ho), nh, head_act, _lib.stream_ptr(),
+              nbytes=4 * (m * (k + (n if want_y else 0) + nh) + n * k), flops=2 * m * n * (k + nh))
     return y, ho
 
 
@@ -113,30 +113,35 @@ class _FusedMLP(Function):
                 dh = torch.empty_like(h_last)
                 _lib.call("tnf_head_bwd", h_last.data_ptr(), h_last.stride(0), ws[-1].data_ptr(), out.data_ptr(),
                           grad_out.data_ptr(), dh.data_ptr(), gws[-1].data_ptr(), gbs[-1].data_ptr(), m,
-                          h_last.size(1), ws[-1].size(0), ctx.head_act, stream, nbytes=0)
+                          h_last.size(1), ws[-1].size(0), ctx.head_act, stream,
+                          nbytes=4 * m * (2 * h_last.size(1) + 2 * ws[-1].size(0)))
             else:  # wide last layer without activation
                 n, k = ws[-1].shape
                 _lib.call("tnf_linear_bwd_weight", grad_out.data_ptr(), grad_out.stride(0), h_last.data_ptr(),
-                          h_last.stride(0), gws[-1].data_ptr(), gbs[-1].data_ptr(), m, n, k, stream, nbytes=2 * m * n * k)
+                          h_last.stride(0), gws[-1].data_ptr(), gbs[-1].data_ptr(), m, n, k, stream,
+                          nbytes=4 * (m * (n + k) + n * k), flops=2 * m * n * k)
                 dh = torch.empty_like(h_last)
                 _lib.call("tnf_linear_bwd_data", grad_out.data_ptr(), grad_out.stride(0), ws[-1].data_ptr(), dh.data_ptr(),
-                          dh.stride(0), h_last.data_ptr(), h_last.stride(0), m, n, k, stream, nbytes=2 * m * n * k)
+                          dh.stride(0), h_last.data_ptr(), h_last.stride(0), m, n, k, stream,
+                          nbytes=4 * (m * (n + 2 * k) + n * k), flops=2 * m * n * k)
             gx = None
             for i in range(L - 2, -1, -1):
                 inp = acts[i - 1] if i > 0 else x2
                 n, k = ws[i].shape
                 _lib.call("tnf_linear_bwd_weight", dh.data_ptr(), dh.stride(0), inp.data_ptr(), inp.stride(0),
-                          gws[i].data_ptr(), gbs[i].data_ptr(), m, n, k, stream, nbytes=2 * m * n * k)
+                          gws[i].data_ptr(), gbs[i].data_ptr(), m, n, k, stream,
+                          nbytes=4 * (m * (n + k) + n * k), flops=2 * m * n * k)
                 if i > 0:
                     dprev = torch.empty_like(inp)
                     _lib.call("tnf_linear_bwd_data", dh.data_ptr(), dh.stride(0), ws[i].data_ptr(), dprev.data_ptr(),
-                              dprev.stride(0), inp.data_ptr(), inp.stride(0), m, n, k, stream, nbytes=2 * m * n * k)
+                              dprev.stride(0), inp.data_ptr(), inp.stride(0), m, n, k, stream,
+                              nbytes=4 * (m * (n + 2 * k) + n * k), flops=2 * m * n * k)
                     dh = dprev
                 elif ctx.x_needs_grad:
                     ld = (k + 3) // 4 * 4
                     buf = torch.empty(m, ld, device=dev)
                     _lib.call("tnf_linear_bwd_data", dh.data_ptr(), dh.stride(0), ws[i].data_ptr(), buf.data_ptr(), ld,
-                              None, 0, m, n, k, stream, nbytes=2 * m * n * k)
+                              None, 0, m, n, k, stream, nbytes=4 * (m * (n + k) + n * k), flops=2 * m * n * k)
                     gx = buf[:, :k].reshape(ctx.in_shape)
         grads = []
         for gw, gb in zip(gws, gbs):
