@@ -84,6 +84,15 @@ def test_two_rank_step_equals_single_process_on_union_batch(tmp_path):
         assert torch.allclose(a, p.grad, rtol=1e-4, atol=1e-7)
 
 
+def test_flat_view_of_channels_last_gradients():
+    from tinynerf_b200.run import _flat_dense
+    g = torch.arange(2 * 3 * 4 * 5, dtype=torch.float32).reshape(1, 6, 4, 5).contiguous(memory_format=torch.channels_last)
+    flat = _flat_dense(g)
+    assert flat.is_contiguous() and flat.numel() == g.numel() and flat.data_ptr() == g.data_ptr()
+    flat.mul_(2.0)
+    assert torch.equal(g, torch.arange(120, dtype=torch.float32).reshape(1, 6, 4, 5) * 2)
+
+
 def test_ray_store_shards_are_a_partition_of_each_epoch():
     o = torch.arange(30, dtype=torch.float32)[:, None].repeat(1, 3)
     stores = [RayStore(o, o, o, "cpu", seed=3, rank=r, world=3) for r in range(3)]

@@ -263,3 +263,27 @@ def test_fused_adam_matches_torch_adam():
         for x, y in zip(a, b):
             close(x.detach(), y.detach(), rtol=2e-6, atol=1e-7)
     assert set(oa.state[a[0]].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_trainer_fused_tv_grad_equals_autograd_path():
+    """Trainer.step with the TV gradient written straight into the plane grads == the autograd formulation."""
+    from tinynerf_b200.run import RayStore, TrainConfig, Trainer
+    o, d = synthetic.blender_rays(1 << 15, seed=3)
+    rgb = torch.rand(1 << 15, 3, generator=torch.Generator().manual_seed(4))
+    grid_vals = synthetic.analytic_grid(128, seed=5).to(DEV)
+    grads = {}
+    for fused in (False, True):
+        cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=256, n_samples=128, fused_tv_grad=fused, prefetch=False)
+        torch.manual_seed(9)
+        tr = Trainer(cfg, RayStore(o, d, rgb, DEV, seed=1), DEV)
+        tr.occupancy_grid.grid.copy_(grid_vals)
+        tr.occupancy_grid.mean = tr.occupancy_grid.grid.mean().item()
+        tr.train_step = 1          # skip the occupancy update of step 0
+        tr.optimizer.step = lambda: None   # keep the gradients of this step for inspection
+        torch.manual_seed(10)
+        info = tr.step()
+        grads[fused] = ({k: p.grad.clone() for k, p in tr.renderer.named_parameters()}, float(info["loss"]))
+    assert grads[True][1] == pytest.approx(grads[False][1], rel=1e-6)
+    for k in grads[True][0]:
+        a, b = grads[True][0][k], grads[False][0][k]
+        assert (a - b).abs().max() <= 1e-5 * b.abs().max().clamp_min(1e-12), k

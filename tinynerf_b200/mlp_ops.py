@@ -104,8 +104,18 @@ class _FusedMLP(Function):
         m = x2.size(0)
         dev = x2.device
         grad_out = grad_out.reshape(m, -1).contiguous().float()
-        gws = [torch.zeros_like(w) for w in ws]
-        gbs = [torch.zeros(w.size(0), device=dev) for w in ws]
+        # one zero-fill for every weight/bias gradient of the stack (the kernels accumulate with atomics);
+        # each slice starts on a 16-byte boundary
+        sizes = []
+        for w in ws:
+            sizes += [w.numel(), w.size(0)]
+        offs, tot = [], 0
+        for n_el in sizes:
+            offs.append(tot)
+            tot += (n_el + 3) // 4 * 4
+        flat = torch.zeros(tot, device=dev)
+        gws = [flat[offs[2 * i]:offs[2 * i] + ws[i].numel()].view_as(ws[i]) for i in range(L)]
+        gbs = [flat[offs[2 * i + 1]:offs[2 * i + 1] + ws[i].size(0)] for i in range(L)]
         stream = _lib.stream_ptr()
         with torch.cuda.device(dev):
             h_last = acts[-1]

@@ -285,7 +285,12 @@ class _KPlanesLookup(Function):
         channels = ctx.channels
         n = x2.size(0)
         grad_out = grad_out.reshape(n, n_scales * channels).contiguous()
-        grads = [torch.zeros_like(p) for p in planes]  # zeros_like preserves the channels-last strides
+        # one zero-fill for all plane gradients; each gradient is a channels-last view like its parameter
+        flat = torch.zeros(sum(p.numel() for p in planes), device=x2.device)
+        grads, off = [], 0
+        for p in planes:
+            grads.append(torch.as_strided(flat, p.shape, p.stride(), off))
+            off += p.numel()
         gstor = [_channels_last_storage(g) for g in grads]
         stor = [_channels_last_storage(p) for p in planes]
         ptrs = (C.c_void_p * len(stor))(*[t.data_ptr() for t in stor])
@@ -348,6 +353,27 @@ class KPlanesFeatureField(torch.nn.Module):
                 loss += plane.loss_l1()
                 count += 1
         return cast(torch.Tensor, loss) / count
+
+    @torch.no_grad()
+    def add_tv_grad_(self, scale: float) -> None:
+        """p.grad += scale * d loss_tv / d p for the nine planes, straight into the existing gradient buffers
+        (tnf_tv_bwd with accumulate=1): what autograd would add for a `scale * loss_tv()` term of the loss, without
+        nine temporaries and nine accumulation passes."""
+        params = self._plane_params()
+        n = len(params)
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            if p.grad.stride() != p.stride():
+                p.grad = torch.empty_like(p).copy_(p.grad)
+        ptrs = (C.c_void_p * n)(*[_channels_last_storage(p).data_ptr() for p in params])
+        gptrs = (C.c_void_p * n)(*[_channels_last_storage(p.grad).data_ptr() for p in params])
+        res_arr = (C.c_int32 * n)(*[int(p.shape[-1]) for p in params])
+        wts = (C.c_float * n)(*[1.0 / n] * n)
+        gs = torch.full((1,), float(scale), device=params[0].device)
+        with torch.cuda.device(gs.device):
+            _lib.call("tnf_tv_bwd", ptrs, gptrs, res_arr, n, self.plane_channels, wts, gs.data_ptr(), 1, _lib.stream_ptr(),
+                      nbytes=3 * sum(p.numel() for p in params) * 4)
 
 
 """CoBaFa https://arxiv.org/abs/2302.01226"""

@@ -44,13 +44,21 @@ def dp_mse(rendered: torch.Tensor, target: torch.Tensor, n_rays_global: torch.Te
     return ((rendered - target) ** 2).sum() / (n_rays_global * rendered.size(-1))
 
 
+def _flat_dense(t: torch.Tensor) -> torch.Tensor:
+    """1-D view over the memory of a dense tensor of any stride order (the channels-last plane gradients are dense
+    but not `contiguous()`, which the collectives require)."""
+    if t.is_contiguous():
+        return t.view(-1)
+    return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
+
+
 def allreduce_gradients(params, world: int) -> None:
     """Sum the per-rank gradients (NCCL over NVLink on the GPU box)."""
     if world <= 1:
         return
     for p in params:
         if p.grad is not None:
-            dist.all_reduce(p.grad)
+            dist.all_reduce(_flat_dense(p.grad))
 
 
 def shard_slices(depth: int, rank: int, world: int) -> Tuple[int, int]:
@@ -121,6 +129,7 @@ class TrainConfig:
     grad_scale: float = 2.0 ** 10       # GradScaler(2**10) that is never unscaled (src/run.py:201,259)
     accumulate: str = "batched"         # "sequential" = the reference's chunk-by-chunk loop (one sync per chunk)
     prefetch: bool = True               # march the next step's batch on a side stream while this step trains
+    fused_tv_grad: bool = True          # TV gradient written straight into the plane grads (no autograd temporaries)
     occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
     seed: int = 0
 
@@ -164,7 +173,7 @@ class Trainer:
         self.renderer = NerfRenderer(feature_module, sigma_decoder, rgb_decoder, bg_color=bg).to(dev)
         if world > 1:  # identical replicas: broadcast rank 0's initial parameters
             for p in self.renderer.parameters():
-                dist.broadcast(p.data, 0)
+                dist.broadcast(_flat_dense(p.data), 0)
         self.optimizer = FusedAdam(self.renderer.parameters(), lr=1e-2, eps=1e-15, weight_decay=1e-5)
         s = self.steps
         self.scheduler = torch.optim.lr_scheduler.MultiStepLR(
@@ -305,13 +314,25 @@ class Trainer:
         grid_ready = torch.cuda.current_stream(self.device).record_event() if self._side is not None else None
         rendered = self.renderer(packed, info)
         loss = dp_mse(rendered, rgbs, global_ray_count(info.size(0), self.device, self.world))
+        tv_direct = 0.0
         if self.cfg.method == "kplanes":
-            reg = self.renderer.feature_module.loss_tv() * self.tv_reg_alpha  # type: ignore
+            fm = self.renderer.feature_module
+            if self.cfg.fused_tv_grad:
+                # loss += tv_alpha * loss_tv (src/run.py:254-255): the value joins the reported loss, its gradient
+                # (a constant-coefficient stencil) is added straight into the plane gradients after backward()
+                with torch.no_grad():
+                    loss_report = loss.detach() + fm.loss_tv() * (self.tv_reg_alpha / self.world)  # type: ignore
+                tv_direct = self.tv_reg_alpha / self.world * self.cfg.grad_scale
+            else:
+                reg = fm.loss_tv() * self.tv_reg_alpha  # type: ignore
+                loss = loss + reg / self.world  # summed over ranks it counts once
             if self.l1_reg_alpha != 0.0:  # the reference multiplies by 0. (src/run.py:114,256): no contribution
-                reg = reg + self.renderer.feature_module.loss_l1() * self.l1_reg_alpha  # type: ignore
-            loss = loss + reg / self.world  # summed over ranks it counts once
+                loss = loss + fm.loss_l1() * (self.l1_reg_alpha / self.world)  # type: ignore
         self.optimizer.zero_grad()
         (loss * self.cfg.grad_scale).backward()
+        if tv_direct:
+            self.renderer.feature_module.add_tv_grad_(tv_direct)  # type: ignore
+            loss = loss_report
         allreduce_gradients(self.renderer.parameters(), self.world)
         self.optimizer.step()
         self.scheduler.step()
