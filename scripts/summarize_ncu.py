@@ -54,8 +54,13 @@ def launch(path, skip=0):
     agg = {}
     tot = 0.0
     for r in rows:
-        name = re.sub(r"\(.*", "", r["Kernel Name"])
-        name = re.sub(r"<.*", "", name).replace("void ", "")[-70:]
+        name = r["Kernel Name"].replace("tnf::<unnamed>::", "tnf::").replace("void ", "")
+        m = re.search(r"(tnf::\w+)", name)
+        if m:
+            name = m.group(1)
+        else:
+            f = re.search(r"(\w+Functor\w*|\w+_kernel_cuda\w*|CatArrayBatchedCopy\w*|reduce_kernel|distribution_elementwise\w*|RadixSort\w+)", name)
+            name = "torch:" + (f.group(1) if f else re.sub(r"[<(].*", "", name)[-50:])
         v = float(r["Metric Value"])
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
