@@ -159,6 +159,11 @@ int tnf_tv_fwd(const float* const* planes /*[host]*/, const int32_t* res /*[host
 int tnf_tv_bwd(const float* const* planes, float* const* grads, const int32_t* res, int32_t n_planes,
                int32_t channels, const float* plane_weight /*[host]*/, const float* gscale, int32_t accumulate,
                void* stream);
+/* tnf_tv_bwd that also returns tnf_tv_fwd's `sums` from the same pass over the planes (loss value for reporting +
+ * gradient: one read of the planes instead of two). */
+int tnf_tv_fwd_bwd(const float* const* planes, float* const* grads, const int32_t* res, int32_t n_planes,
+                   int32_t channels, const float* plane_weight /*[host]*/, const float* gscale, int32_t accumulate,
+                   double* sums, void* stream);
 
 /* ---- Adam step over a table of tensors ------------------------------------------
  * Replaces torch.optim.Adam.step as configured at src/run.py:186 (L2 weight decay folded into the
@@ -222,6 +227,14 @@ int tnf_composite_fwd(const float* weights, const float* rgbs, const int32_t* in
 int tnf_composite_bwd(const float* weights, const float* rgbs, const int32_t* info, int64_t n_samples,
                       int64_t n_rays, const float* bg, const float* grad_out, float* grad_weights,
                       float* grad_rgbs, void* stream);
+
+/* Loss of the training iteration and its gradient wrt the rendered colours (src/run.py:252 nn.MSELoss, :259
+ * `scaler.scale(loss).backward()` with the never-unscaled factor `grad_scale`), normalised by the ray count of the
+ * UNION batch of all ranks: denom = 3 * n_rays_global (read from the device scalar when given).
+ *   *loss_out = sum (rendered - target)^2 / denom ;  grad_rendered = grad_scale * 2 (rendered - target) / denom */
+int tnf_mse_loss_grad(const float* rendered, const float* target, int64_t n_rays, float n_rays_global,
+                      const float* n_rays_global_dev /*optional*/, float grad_scale, float* grad_rendered /*optional*/,
+                      float* loss_out /*optional*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,108 @@
+"""The autograd-free training iteration (tinynerf_b200/fused.py) against the module/autograd path on the same batch,
+plus the two small kernels it adds (tnf_mse_loss_grad, tnf_tv_fwd_bwd).  All through the C ABI on the GPU."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tinynerf_b200 import _lib, models, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _trainer(fused_step, seed=9, **kw):
+    from tinynerf_b200.run import RayStore, TrainConfig, Trainer
+    o, d = synthetic.blender_rays(1 << 15, seed=3)
+    rgb = torch.rand(1 << 15, 3, generator=torch.Generator().manual_seed(4))
+    cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=256, n_samples=128, fused_tv_grad=False,
+                      prefetch=False, fused_step=fused_step, **kw)
+    torch.manual_seed(seed)
+    tr = Trainer(cfg, RayStore(o, d, rgb, DEV, seed=1), DEV)
+    tr.occupancy_grid.grid.copy_(synthetic.analytic_grid(128, seed=5).to(DEV))
+    tr.occupancy_grid.mean = tr.occupancy_grid.grid.mean().item()
+    tr.train_step = 1  # skip the occupancy update of step 0
+    return tr
+
+
+def test_fused_step_matches_autograd_step():
+    res = {}
+    for fused in (False, True):
+        tr = _trainer(fused)
+        assert (tr._fused is not None) == fused
+        tr.optimizer.step = lambda: None  # keep this step's gradients for inspection
+        torch.manual_seed(10)
+        info = tr.step()
+        res[fused] = ({k: p.grad.clone() for k, p in tr.renderer.named_parameters()}, float(info["loss"]), info["n_samples"])
+    assert res[True][2] == res[False][2] > 0
+    assert res[True][1] == pytest.approx(res[False][1], rel=2e-6)
+    for k, b in res[False][0].items():
+        a = res[True][0][k]
+        assert a.shape == b.shape and a.stride() == b.stride(), k
+        assert (a - b).abs().max() <= 1e-5 * b.abs().max().clamp_min(1e-12), k
+
+
+def test_fused_training_trajectory_matches_autograd():
+    """Five full iterations (Adam included): parameters stay together."""
+    trs = {f: _trainer(f, seed=11) for f in (False, True)}
+    for it in range(5):
+        for f, tr in trs.items():
+            torch.manual_seed(100 + it)
+            tr.step()
+    pa, pb = dict(trs[True].renderer.named_parameters()), dict(trs[False].renderer.named_parameters())
+    for k in pb:
+        assert (pa[k] - pb[k]).abs().max() <= 2e-4 * pb[k].abs().max().clamp_min(1e-12), k
+    assert float(trs[True].last["loss"]) == pytest.approx(float(trs[False].last["loss"]), rel=1e-3)
+
+
+def test_fused_step_survives_zero_grad_and_growth():
+    tr = _trainer(True)
+    tr.step()
+    tr.optimizer.zero_grad()  # set_to_none=True: the fused step re-attaches its gradient views
+    tr._fused._cap_n = tr._fused._cap_r = 0  # force a workspace re-allocation
+    out = tr.step()
+    assert torch.isfinite(out["loss"]) and all(p.grad is not None for p in tr.renderer.parameters())
+
+
+def test_mse_loss_grad_kernel():
+    torch.manual_seed(0)
+    for r, n_glob in ((1, None), (1000, None), (4097, 9000.0)):
+        a = torch.rand(r, 3, device=DEV, requires_grad=True)
+        t = torch.rand(r, 3, device=DEV)
+        denom = (n_glob or r) * 3
+        loss_ref = ((a - t) ** 2).sum() / denom
+        (loss_ref * 1024.0).backward()
+        g, l = torch.empty(r, 3, device=DEV), torch.zeros(1, device=DEV)
+        ng = None if n_glob is None else torch.tensor(n_glob, device=DEV)
+        _lib.call("tnf_mse_loss_grad", a.data_ptr(), t.data_ptr(), r, float(r), _lib.ptr(ng), 1024.0, g.data_ptr(), l.data_ptr(),
+                  _lib.stream_ptr())
+        assert float(l) == pytest.approx(float(loss_ref), rel=2e-6)
+        assert torch.allclose(g, a.grad, rtol=2e-6, atol=0)
+
+
+def test_tv_fwd_bwd_equals_separate_passes():
+    torch.manual_seed(1)
+    field = models.KPlanesFeatureField(32).to(DEV)
+    params = field._plane_params()
+    n = len(params)
+    stor = [models._channels_last_storage(p) for p in params]
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in stor])
+    res = (C.c_int32 * n)(*[int(p.shape[-1]) for p in params])
+    wts = (C.c_float * n)(*[1.0 / n] * n)
+    gs = torch.full((1,), 0.37, device=DEV)
+    sums_a = torch.empty(2 * n, dtype=torch.float64, device=DEV)
+    sums_b = torch.empty(2 * n, dtype=torch.float64, device=DEV)
+    base = [torch.randn_like(t) for t in stor]
+    ga, gb = [b.clone() for b in base], [b.clone() for b in base]
+    st = _lib.stream_ptr()
+    _lib.call("tnf_tv_fwd", ptrs, res, n, 32, sums_a.data_ptr(), st)
+    _lib.call("tnf_tv_bwd", ptrs, (C.c_void_p * n)(*[t.data_ptr() for t in ga]), res, n, 32, wts, gs.data_ptr(), 1, st)
+    _lib.call("tnf_tv_fwd_bwd", ptrs, (C.c_void_p * n)(*[t.data_ptr() for t in gb]), res, n, 32, wts, gs.data_ptr(), 1,
+              sums_b.data_ptr(), st)
+    assert torch.allclose(sums_a, sums_b, rtol=1e-12, atol=0)
+    for x, y in zip(ga, gb):
+        assert torch.equal(x, y)
+    # and the value is the reference's loss_tv
+    ref = field.loss_tv()
+    denom = torch.tensor([float(32 * (r - 1) * r) for r in res for _ in range(2)], dtype=torch.float64, device=DEV)
+    assert float((sums_b / denom).sum() / n) == pytest.approx(float(ref), rel=1e-6)

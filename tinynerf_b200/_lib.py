@@ -74,6 +74,9 @@ _SIGNATURES = {
     "tnf_tv_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "tnf_tv_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
                              C.POINTER(C.c_float), c_f32p, C.c_int32, C.c_void_p]),
+    "tnf_tv_fwd_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                 C.POINTER(C.c_float), c_f32p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "tnf_mse_loss_grad": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_float, c_f32p, C.c_float, c_f32p, c_f32p, C.c_void_p]),
     "tnf_adam_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                 C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),

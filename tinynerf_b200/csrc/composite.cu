@@ -77,8 +77,49 @@ composite_bwd_kernel(const float* __restrict__ w, const float* __restrict__ rgb,
   }
 }
 
+// MSE over the union batch of all ranks + its gradient (src/run.py:252 MSELoss, :259 scaled backward):
+//   loss_out = sum (r-t)^2 / denom ;  grad[i] = grad_scale * 2 (r_i - t_i) / denom ,  denom = n_rays_global * 3
+// One CTA, fixed reduction order: deterministic.
+__global__ void __launch_bounds__(1024) mse_loss_grad_kernel(const float* __restrict__ r, const float* __restrict__ t, long long n,
+                                                             float n_rays_global, const float* __restrict__ n_rays_global_dev,
+                                                             float grad_scale, float* __restrict__ grad, float* __restrict__ loss_out) {
+  __shared__ double s_red[32];
+  const float denom = (n_rays_global_dev ? __ldg(n_rays_global_dev) : n_rays_global) * 3.f;
+  const float gs = grad_scale / denom;   // d(loss*grad_scale)/d(sum) as autograd forms it: scale / denom
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const float d = __ldg(r + i) - __ldg(t + i);
+    acc += (double)(d * d);
+    if (grad) grad[i] = gs * 2.f * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = s_red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+    if (threadIdx.x == 0 && loss_out) *loss_out = (float)(acc / (double)denom);
+  }
+}
+
 }  // namespace
 }  // namespace tnf
+
+extern "C" int tnf_mse_loss_grad(const float* rendered, const float* target, int64_t n_rays, float n_rays_global,
+                                 const float* n_rays_global_dev, float grad_scale, float* grad_rendered, float* loss_out,
+                                 void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(n_rays >= 0, "negative size");
+  TNF_REQUIRE(grad_rendered || loss_out, "nothing requested");
+  TNF_REQUIRE(n_rays == 0 || (rendered && target), "null pointer");
+  TNF_REQUIRE(n_rays_global_dev || n_rays_global > 0.f, "n_rays_global must be positive");
+  mse_loss_grad_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(rendered, target, 3 * n_rays, n_rays_global,
+                                                                          n_rays_global_dev, grad_scale, grad_rendered, loss_out);
+  TNF_LAUNCH_CHECK("mse_loss_grad_kernel");
+  return TNF_OK;
+}
 
 extern "C" int tnf_composite_fwd(const float* weights, const float* rgbs, const int32_t* info,
                                  int64_t n_samples, int64_t n_rays, const float* bg, float* out_rgb,

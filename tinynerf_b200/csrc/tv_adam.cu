@@ -72,31 +72,61 @@ __global__ void __launch_bounds__(256) tv_fwd_kernel(const TVArgs A) {
   }
 }
 
+// SUMS: also emit the forward's sums of squared differences (the "down" and "right" neighbours are loaded for the
+// gradient anyway), so one pass over the planes yields loss value and gradient.
+template <bool SUMS>
 __global__ void __launch_bounds__(256) tv_bwd_kernel(const TVArgs A) {
+  __shared__ float s_red[2][8];
   const int pi = find_plane(A, blockIdx.x);
   const int res = A.res[pi], C = A.channels, c4 = C >> 2;
   const long long t = (blockIdx.x - A.first_block[pi]) * 256LL + threadIdx.x;
   const long long n_vec = (long long)res * res * c4;
-  if (t >= n_vec) return;
-  const long long texel = t / c4;
-  const int h = (int)(texel / res), w = (int)(texel % res);
-  const float gs = __ldg(A.gscale);
-  const float ch = A.coef_h[pi] * gs, cw = A.coef_w[pi] * gs;
-  const float* p = A.planes[pi] + t * 4;
-  const long long sH = (long long)res * C;
-  const float4 v = ld4(p);
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  // d/dp[h,w] of sum (p[h+1]-p[h])^2 = 2 (p[h]-p[h-1]) [h>0] - 2 (p[h+1]-p[h]) [h<H-1]
-  if (h > 0) { const float4 u = ld4(p - sH); g.x += ch * (v.x - u.x); g.y += ch * (v.y - u.y); g.z += ch * (v.z - u.z); g.w += ch * (v.w - u.w); }
-  if (h + 1 < res) { const float4 u = ld4(p + sH); g.x -= ch * (u.x - v.x); g.y -= ch * (u.y - v.y); g.z -= ch * (u.z - v.z); g.w -= ch * (u.w - v.w); }
-  if (w > 0) { const float4 u = ld4(p - C); g.x += cw * (v.x - u.x); g.y += cw * (v.y - u.y); g.z += cw * (v.z - u.z); g.w += cw * (v.w - u.w); }
-  if (w + 1 < res) { const float4 u = ld4(p + C); g.x -= cw * (u.x - v.x); g.y -= cw * (u.y - v.y); g.z -= cw * (u.z - v.z); g.w -= cw * (u.w - v.w); }
-  float4* out = reinterpret_cast<float4*>(A.grads[pi] + t * 4);
-  if (A.accumulate) {
-    const float4 o = *out;
-    g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+  float sh = 0.f, sw = 0.f;
+  if (t < n_vec) {
+    const long long texel = t / c4;
+    const int h = (int)(texel / res), w = (int)(texel % res);
+    const float gs = __ldg(A.gscale);
+    const float ch = A.coef_h[pi] * gs, cw = A.coef_w[pi] * gs;
+    const float* p = A.planes[pi] + t * 4;
+    const long long sH = (long long)res * C;
+    const float4 v = ld4(p);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    // d/dp[h,w] of sum (p[h+1]-p[h])^2 = 2 (p[h]-p[h-1]) [h>0] - 2 (p[h+1]-p[h]) [h<H-1]
+    if (h > 0) { const float4 u = ld4(p - sH); g.x += ch * (v.x - u.x); g.y += ch * (v.y - u.y); g.z += ch * (v.z - u.z); g.w += ch * (v.w - u.w); }
+    if (h + 1 < res) {
+      const float4 u = ld4(p + sH);
+      g.x -= ch * (u.x - v.x); g.y -= ch * (u.y - v.y); g.z -= ch * (u.z - v.z); g.w -= ch * (u.w - v.w);
+      if (SUMS) sh = sq4(u, v);
+    }
+    if (w > 0) { const float4 u = ld4(p - C); g.x += cw * (v.x - u.x); g.y += cw * (v.y - u.y); g.z += cw * (v.z - u.z); g.w += cw * (v.w - u.w); }
+    if (w + 1 < res) {
+      const float4 u = ld4(p + C);
+      g.x -= cw * (u.x - v.x); g.y -= cw * (u.y - v.y); g.z -= cw * (u.z - v.z); g.w -= cw * (u.w - v.w);
+      if (SUMS) sw = sq4(u, v);
+    }
+    float4* out = reinterpret_cast<float4*>(A.grads[pi] + t * 4);
+    if (A.accumulate) {
+      const float4 o = *out;
+      g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+    }
+    *out = g;
   }
-  *out = g;
+  if (SUMS) {  // same reduction tree as tv_fwd_kernel: identical sums
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sh += __shfl_xor_sync(kFullMask, sh, d);
+      sw += __shfl_xor_sync(kFullMask, sw, d);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_red[0][wid] = sh; s_red[1][wid] = sw; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc += (double)s_red[threadIdx.x][i];
+      atomicAdd(A.sums + 2 * pi + threadIdx.x, acc);
+    }
+  }
 }
 
 int fill_tv(TVArgs* A, const float* const* planes, float* const* grads, const int32_t* res, int n_planes,
@@ -207,8 +237,28 @@ extern "C" int tnf_tv_bwd(const float* const* planes, float* const* grads, const
     for (int i = 0; i < n_planes; ++i) { A.coef_h[i] *= plane_weight[i]; A.coef_w[i] *= plane_weight[i]; }
   A.gscale = gscale;
   A.accumulate = accumulate;
-  tv_bwd_kernel<<<(unsigned)A.first_block[n_planes], 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  tv_bwd_kernel<false><<<(unsigned)A.first_block[n_planes], 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   TNF_LAUNCH_CHECK("tv_bwd_kernel");
+  return TNF_OK;
+}
+
+extern "C" int tnf_tv_fwd_bwd(const float* const* planes, float* const* grads, const int32_t* res, int32_t n_planes,
+                              int32_t channels, const float* plane_weight, const float* gscale, int32_t accumulate,
+                              double* sums, void* stream) {
+  using namespace tnf;
+  TVArgs A{};
+  TNF_REQUIRE(grads && gscale && sums, "null grads/gscale/sums");
+  int rc = fill_tv(&A, planes, grads, res, n_planes, channels);
+  if (rc != TNF_OK) return rc;
+  if (plane_weight)
+    for (int i = 0; i < n_planes; ++i) { A.coef_h[i] *= plane_weight[i]; A.coef_w[i] *= plane_weight[i]; }
+  A.gscale = gscale;
+  A.accumulate = accumulate;
+  A.sums = sums;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TNF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * n_planes, st));
+  tv_bwd_kernel<true><<<(unsigned)A.first_block[n_planes], 256, 0, st>>>(A);
+  TNF_LAUNCH_CHECK("tv_fwd_bwd_kernel");
   return TNF_OK;
 }
 

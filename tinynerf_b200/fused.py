@@ -1,0 +1,232 @@
+"""One training iteration of the packed-ray path as a straight sequence of C-ABI calls (no autograd graph, no
+PyTorch glue kernels): the caller-side fast path of `run.Trainer` for K-Planes + the vanilla heads.
+
+It evaluates exactly what `NerfRenderer.forward` + `MSELoss` + `loss_tv` + `backward()` evaluate through the
+module/autograd path (src/core.py:225-267, src/run.py:251-259) with the same kernels in the same order; what it
+removes is host work: ~70 torch ops per iteration (allocations, `cat`, strided adds, nine gradient accumulations,
+the loss arithmetic) and the autograd engine's thread hop.  `tests/test_gpu_fused.py` checks it against the
+autograd path on the same batch.
+
+    fs = FusedKPlanesStep(renderer, tv_alpha=1e-4, grad_scale=2**10)
+    out = fs.forward_backward(packed, info, target_rgb)      # p.grad of every parameter is set
+    optimizer.step()
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List
+
+import torch
+
+from . import _cuda, _lib
+from .core import NerfRenderer
+from .models import (KPlanesFeatureField, VanillaColorDecoder, VanillaOpacityDecoder, _channels_last_storage,
+                     _ensure_channels_last_)
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class FusedKPlanesStep:
+    @staticmethod
+    def supported(renderer: NerfRenderer) -> bool:
+        fm, sd, cd = renderer.feature_module, renderer.sigma_decoder, renderer.rgb_decoder
+        if not (isinstance(fm, KPlanesFeatureField) and isinstance(sd, VanillaOpacityDecoder)
+                and isinstance(cd, VanillaColorDecoder)):
+            return False
+        if fm.dropout.p != 0.0 or not renderer.dense_rgb:
+            return False
+        sl, cl = sd.net.linears(), cd.net.linears()
+        if len(sl) != 2 or sl[-1].out_features != 1 or cl[-1].out_features != 3:
+            return False
+        if any(l.out_features not in (32, 64, 128) for l in sl[:-1] + cl[:-1]):
+            return False
+        return all(p.is_cuda and p.dtype == torch.float32 for p in renderer.parameters())
+
+    def __init__(self, renderer: NerfRenderer, tv_alpha: float = 0.0, grad_scale: float = 1.0, world: int = 1,
+                 threshold: float = 1e-4):
+        if not self.supported(renderer):
+            raise RuntimeError("FusedKPlanesStep needs KPlanesFeatureField + VanillaOpacityDecoder + VanillaColorDecoder on CUDA")
+        _lib.load()
+        self.renderer = renderer
+        self.tv_alpha, self.grad_scale, self.world, self.threshold = float(tv_alpha), float(grad_scale), int(world), threshold
+        fm: KPlanesFeatureField = renderer.feature_module  # type: ignore
+        self.planes = fm._plane_params()
+        self.channels = fm.plane_channels
+        self.n_scales = len(self.planes) // 3
+        self.res = [int(self.planes[3 * s].shape[-1]) for s in range(self.n_scales)]
+        self.feat = self.n_scales * self.channels
+        self.sig_lin = renderer.sigma_decoder.net.linears()   # type: ignore
+        self.col_lin = renderer.rgb_decoder.net.linears()     # type: ignore
+        self.n_freqs = int(renderer.rgb_decoder.pe.freqs.numel())  # type: ignore
+        self.dev = self.planes[0].device
+        self.bg = None if renderer.bg_color is None else (C.c_float * 3)(*[float(v) for v in renderer.bg_color.reshape(-1).tolist()])
+        self.xc_width = 6 * self.n_freqs + 3 + self.feat
+        self.xc_ld = _pad4(self.xc_width)
+        assert self.col_lin[0].in_features == self.xc_width and self.sig_lin[0].in_features == self.feat
+        # ---- one flat gradient buffer; p.grad are views of it (planes keep their channels-last strides) ----
+        params: List[torch.nn.Parameter] = list(self.planes)
+        for l in self.sig_lin + self.col_lin:
+            params += [l.weight, l.bias]
+        offs, tot = [], 0
+        for p in params:
+            offs.append(tot)
+            tot += _pad4(p.numel())
+        self.flat_grad = torch.zeros(tot, device=self.dev)
+        self.grads = [torch.as_strided(self.flat_grad, p.shape, p.stride(), off) for p, off in zip(params, offs)]
+        self.params = params
+        self._g = {id(p): g for p, g in zip(params, self.grads)}
+        self.attach_grads()
+        others = [p for p in renderer.parameters() if all(p is not q for q in params)]
+        if others:
+            raise RuntimeError("renderer has parameters outside the fused step")
+        n = len(self.planes)
+        self._plane_ptrs = (C.c_void_p * n)(*[_channels_last_storage(p).data_ptr() for p in self.planes])
+        self._grad_ptrs = (C.c_void_p * n)(*[_channels_last_storage(self._g[id(p)]).data_ptr() for p in self.planes])
+        self._res_scales = (C.c_int32 * self.n_scales)(*self.res)
+        self._res_planes = (C.c_int32 * n)(*[int(p.shape[-1]) for p in self.planes])
+        self._tv_w = (C.c_float * n)(*[1.0 / n] * n)
+        self._plane_bytes = 4 * sum(p.numel() for p in self.planes)
+        self._tv_gscale = torch.full((1,), self.tv_alpha / self.world * self.grad_scale, device=self.dev)
+        self._tv_sums = torch.zeros(2 * n, dtype=torch.float64, device=self.dev)
+        # loss_tv = mean_i (sums[2i] + sums[2i+1]) / (C (res-1) res); reported with weight tv_alpha / world
+        self._tv_coef = torch.tensor([self.tv_alpha / self.world / n / float(self.channels * (r - 1) * r)
+                                      for r in self._res_planes for _ in range(2)], dtype=torch.float64, device=self.dev)
+        self._cap_n = self._cap_r = 0
+        self._ws: Dict[str, torch.Tensor] = {}
+
+    def attach_grads(self) -> None:
+        """p.grad = its view of the flat gradient buffer (undoes optimizer.zero_grad(set_to_none=True))."""
+        for p, g in zip(self.params, self.grads):
+            p.grad = g
+
+    # ---- workspace ---------------------------------------------------------------------------------
+    def _reserve(self, n: int, r: int) -> None:
+        if n > self._cap_n:
+            cap = int(n * 1.25) + 1024
+            hid_c = self.col_lin[0].out_features
+            hid_s = self.sig_lin[0].out_features
+            e = lambda *s: torch.empty(*s, device=self.dev)
+            ws = self._ws
+            ws["feats"], ws["dfeat"] = e(cap, self.feat), e(cap, self.feat)
+            ws["hs"], ws["dhs"] = e(cap, hid_s), e(cap, hid_s)
+            ws["sigma"], ws["gsigma"], ws["w"], ws["gw"] = e(cap), e(cap), e(cap), e(cap)
+            ws["xc"], ws["dxc"] = e(cap, self.xc_ld), e(cap, self.xc_ld)
+            for i in range(len(self.col_lin) - 1):
+                ws[f"h{i}"] = e(cap, hid_c)
+            ws["dha"], ws["dhb"] = e(cap, hid_c), e(cap, hid_c)
+            ws["rgb"], ws["grgb"] = e(cap, 3), e(cap, 3)
+            self._cap_n = cap
+        if r > self._cap_r:
+            cap = int(r * 1.25) + 256
+            self._ws["rendered"] = torch.empty(cap, 3, device=self.dev)
+            self._ws["grend"] = torch.empty(cap, 3, device=self.dev)
+            self._ws["loss"] = torch.zeros(1, device=self.dev)
+            self._cap_r = cap
+
+    # ---- the iteration -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_backward(self, packed: torch.Tensor, info: torch.Tensor, target: torch.Tensor,
+                         n_rays_global: torch.Tensor | None = None) -> Dict[str, torch.Tensor]:
+        """packed [N,7], info [R,2] int32 (a RayProvider partition), target [R,3].  Sets p.grad of every parameter to
+        d(grad_scale * (MSE_union + tv_alpha/world * loss_tv))/dp and returns {"loss", "rendered"}."""
+        _lib.require_cuda(packed, "packed_samples")
+        n, r = packed.size(0), info.size(0)
+        if n == 0 or r == 0:
+            raise ValueError("no samples remaining")
+        if not (packed.is_contiguous() and info.is_contiguous() and info.dtype == torch.int32):
+            raise RuntimeError("packed samples / packing info must be contiguous ([N,7] fp32, [R,2] int32)")
+        target = target.contiguous()
+        steps = getattr(packed, "_tnf_steps", None)
+        sstride = 1
+        if steps is None:
+            steps, sstride = packed[:, 6], 7
+        flags = _cuda.TRUSTED_PARTITION if getattr(info, "_tnf_partition", False) else 0
+        status = None if flags else torch.empty(1, dtype=torch.int32, device=self.dev)
+        self._reserve(n, r)
+        self.attach_grads()
+        ws, call, st = self._ws, _lib.call, _lib.stream_ptr()
+        P = lambda t: t.data_ptr()
+        G = lambda p: self._g[id(p)].data_ptr()
+        F, xw, xld = self.feat, self.xc_width, self.xc_ld
+        sl, cl = self.sig_lin, self.col_lin
+        hs_w, hc_w = sl[0].out_features, cl[0].out_features
+        nh = len(cl) - 1  # hidden layers of the colour head
+
+        def lin_fwd(x, ldx, lin, y, head=None, head_out=None, head_act=0):
+            nn_, k = lin.out_features, lin.in_features
+            n_head = 0 if head is None else head.out_features
+            call("tnf_linear_fwd", x, ldx, P(lin.weight), P(lin.bias), P(y), nn_, n, nn_, k, 1,
+                 None if head is None else P(head.weight), None if head is None else P(head.bias),
+                 None if head is None else P(head_out), n_head, head_act, st,
+                 nbytes=4 * (n * (k + nn_ + n_head) + nn_ * k), flops=2 * n * nn_ * (k + n_head))
+
+        def wgrad(dy, lddy, x, ldx, lin):
+            nn_, k = lin.out_features, lin.in_features
+            call("tnf_linear_bwd_weight", dy, lddy, x, ldx, G(lin.weight), G(lin.bias), n, nn_, k, st,
+                 nbytes=4 * (n * (nn_ + k) + nn_ * k), flops=2 * n * nn_ * k)
+
+        def dgrad(dy, lddy, lin, dx, lddx, relu_src, ldrs):
+            nn_, k = lin.out_features, lin.in_features
+            call("tnf_linear_bwd_data", dy, lddy, P(lin.weight), dx, lddx, relu_src, ldrs, n, nn_, k, st,
+                 nbytes=4 * (n * (nn_ + (2 if relu_src else 1) * k) + nn_ * k), flops=2 * n * nn_ * k)
+
+        with torch.cuda.device(self.dev):
+            self.flat_grad.zero_()
+            # ---- forward (src/core.py:225-267) ----
+            call("tnf_kplanes_fwd", self._plane_ptrs, self._res_scales, self.n_scales, self.channels, P(packed), 7, n,
+                 P(ws["feats"]), st, nbytes=n * (12 + 4 * F) + self._plane_bytes)
+            lin_fwd(P(ws["feats"]), F, sl[0], ws["hs"], head=sl[1], head_out=ws["sigma"], head_act=1)
+            call("tnf_weights_fwd", P(ws["sigma"]), P(steps), sstride, P(info), float(self.threshold), P(ws["w"]), n, r,
+                 flags, _lib.ptr(status), st, nbytes=12 * n + 8 * r, extra_kernels=0 if flags else 3)
+            call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, F, P(ws["xc"]), xld, n, st,
+                 nbytes=n * (12 + 4 * F + 4 * xld))
+            x, ldx = P(ws["xc"]), xld
+            for i in range(nh):
+                last = i == nh - 1
+                lin_fwd(x, ldx, cl[i], ws[f"h{i}"], head=cl[-1] if last else None,
+                        head_out=ws["rgb"] if last else None, head_act=2 if last else 0)
+                x, ldx = P(ws[f"h{i}"]), hc_w
+            call("tnf_composite_fwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(ws["rendered"]), None, st,
+                 nbytes=16 * n + 20 * r)
+            # ---- loss + its gradient (src/run.py:252,259) ----
+            call("tnf_mse_loss_grad", P(ws["rendered"]), P(target), r, float(r), _lib.ptr(n_rays_global), self.grad_scale,
+                 P(ws["grend"]), P(ws["loss"]), st, nbytes=36 * r)
+            # ---- backward ----
+            call("tnf_composite_bwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(ws["grend"]), P(ws["gw"]),
+                 P(ws["grgb"]), st, nbytes=32 * n + 20 * r)
+            # colour head: fused output layer + sigmoid, then hidden layers from the last to the first
+            h_last = ws[f"h{nh - 1}"]
+            dh, dh_other = ws["dha"], ws["dhb"]
+            call("tnf_head_bwd", P(h_last), hc_w, P(cl[-1].weight), P(ws["rgb"]), P(ws["grgb"]), P(dh), G(cl[-1].weight),
+                 G(cl[-1].bias), n, hc_w, 3, 2, st, nbytes=4 * n * (2 * hc_w + 6))
+            for i in range(nh - 1, 0, -1):
+                inp = ws[f"h{i - 1}"]
+                wgrad(P(dh), hc_w, P(inp), hc_w, cl[i])
+                dgrad(P(dh), hc_w, cl[i], P(dh_other), hc_w, P(inp), hc_w)
+                dh, dh_other = dh_other, dh
+            wgrad(P(dh), hc_w, P(ws["xc"]), xld, cl[0])
+            dgrad(P(dh), hc_w, cl[0], P(ws["dxc"]), xld, None, 0)
+            # density branch: weights backward, fused output layer + truncated_exp, hidden layer
+            call("tnf_weights_bwd", P(ws["sigma"]), P(steps), sstride, P(info), P(ws["w"]), P(ws["gw"]), P(ws["gsigma"]), n, r,
+                 flags, _lib.ptr(status), st, nbytes=20 * n + 8 * r, extra_kernels=0 if flags else 3)
+            call("tnf_head_bwd", P(ws["hs"]), hs_w, P(sl[1].weight), P(ws["sigma"]), P(ws["gsigma"]), P(ws["dhs"]),
+                 G(sl[1].weight), G(sl[1].bias), n, hs_w, 1, 1, st, nbytes=4 * n * (2 * hs_w + 2))
+            wgrad(P(ws["dhs"]), hs_w, P(ws["feats"]), F, sl[0])
+            dgrad(P(ws["dhs"]), hs_w, sl[0], P(ws["dfeat"]), F, None, 0)
+            # the features feed both heads: d feats = d(sigma branch) + d(colour input)[:, feature columns]
+            dfeat = ws["dfeat"][:n]
+            torch.add(dfeat, ws["dxc"][:n, xw - F:xw], out=dfeat)
+            _lib.launch_count += 1
+            call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
+                 P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
+            loss = ws["loss"][0]
+            if self.tv_alpha != 0.0:
+                # loss += tv_alpha * loss_tv (src/run.py:254-255): value and gradient from one pass over the planes
+                call("tnf_tv_fwd_bwd", self._plane_ptrs, self._grad_ptrs, self._res_planes, len(self.planes), self.channels,
+                     self._tv_w, P(self._tv_gscale), 1, P(self._tv_sums), st, nbytes=3 * self._plane_bytes)
+                loss = loss + torch.dot(self._tv_sums, self._tv_coef).float()
+            else:
+                loss = loss.clone()
+        return {"loss": loss, "rendered": ws["rendered"][:r]}

@@ -130,6 +130,7 @@ class TrainConfig:
     accumulate: str = "batched"         # "sequential" = the reference's chunk-by-chunk loop (one sync per chunk)
     prefetch: bool = True               # march the next step's batch on a side stream while this step trains
     fused_tv_grad: bool = True          # TV gradient written straight into the plane grads (no autograd temporaries)
+    fused_step: bool = True             # K-Planes: forward+loss+backward as one C-ABI call sequence (fused.py), no autograd
     occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
     seed: int = 0
 
@@ -180,6 +181,12 @@ class Trainer:
             self.optimizer, milestones=[s // 2, s * 3 // 4, s * 5 // 6, s * 9 // 10], gamma=0.33)
         self.tv_reg_alpha, self.l1_reg_alpha = 0.0001, 0.0
         self.train_step = 0
+        self._fused = None
+        if cfg.fused_step and cfg.method == "kplanes" and self.device.type == "cuda" and self.l1_reg_alpha == 0.0:
+            from .fused import FusedKPlanesStep
+            if FusedKPlanesStep.supported(self.renderer):
+                self._fused = FusedKPlanesStep(self.renderer, tv_alpha=self.tv_reg_alpha, grad_scale=cfg.grad_scale,
+                                               world=world)
         self._chunks_guess = 0.0
         self._side = torch.cuda.Stream(device=self.device) if (cfg.prefetch and self.device.type == "cuda") else None
         self._next = None
@@ -312,6 +319,8 @@ class Trainer:
         if self.train_step % self.occupancy_grid_updates == 0:
             self.update_occupancy()
         grid_ready = torch.cuda.current_stream(self.device).record_event() if self._side is not None else None
+        if self._fused is not None:
+            return self._step_fused(packed, rgbs, info, grid_ready)
         rendered = self.renderer(packed, info)
         loss = dp_mse(rendered, rgbs, global_ray_count(info.size(0), self.device, self.world))
         tv_direct = 0.0
@@ -342,6 +351,20 @@ class Trainer:
             # busy with this step's backward + optimiser, so its host sync no longer stalls the step
             self._prefetch(grid_ready)
         self.last = {"loss": loss.detach(), "n_samples": packed.size(0), "n_rays": info.size(0)}
+        return self.last
+
+    def _step_fused(self, packed, rgbs, info, grid_ready) -> Dict[str, float]:
+        """Same iteration through fused.FusedKPlanesStep: identical kernels and order, no autograd / glue ops."""
+        n_glob = global_ray_count(info.size(0), self.device, self.world) if self.world > 1 else None
+        out = self._fused.forward_backward(packed, info, rgbs, n_glob)
+        if self.world > 1:
+            dist.all_reduce(self._fused.flat_grad)  # every parameter gradient in one collective
+        self.optimizer.step()
+        self.scheduler.step()
+        self.train_step += 1
+        if self._side is not None:
+            self._prefetch(grid_ready)
+        self.last = {"loss": out["loss"], "n_samples": packed.size(0), "n_rays": info.size(0)}
         return self.last
 
     # ---- render half of the path (src/run.py:15-50, without image IO) ---------------------------
