@@ -276,6 +276,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms, host_dist = [], []
+
     def timed(tr, steps, read_loss, profile):
         barrier()
         l0 = _lib.launch_count
@@ -284,9 +286,16 @@ def main():
             _lib.profile_start()
         s.record()
         n = 0
+        h0 = time.perf_counter()
+        per = []
         for _ in range(steps):
             n += one_step(tr, read_loss)
+            per.append(time.perf_counter())
         e.record()
+        host_ms.append((time.perf_counter() - h0) * 1e3 / steps)  # host time per step (includes the batch-size sync)
+        d = sorted(b - a for a, b in zip([h0] + per[:-1], per))
+        host_dist.append({"p50": round(d[len(d) // 2] * 1e3, 3), "p90": round(d[int(len(d) * 0.9)] * 1e3, 3),
+                          "max": round(d[-1] * 1e3, 3)})
         barrier()
         recs = _lib.profile_stop() if profile else None
         ms = s.elapsed_time(e)
@@ -354,7 +363,7 @@ def main():
                        "parallelism": f"ray-sharded dp{world}"},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": round(ms2 / args.steps, 4)},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": table,
+            "gpu_launches": int(launches), "host_ms_per_step": round(host_ms[0], 4), "host_step_ms": {"value_arm": host_dist[0], "e2e_arm": host_dist[-1]}, "clocks": clk, "roofline": roof, "kernels": table,
             "weights_microbench": micro, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:

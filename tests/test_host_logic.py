@@ -60,3 +60,23 @@ def test_synthetic_packed_rays_are_a_partition():
     assert int(info[0, 0]) == 0 and int(info[-1, 0] + info[-1, 1]) == 1 << 14
     assert torch.equal(info[1:, 0], (info[:-1, 0] + info[:-1, 1]))
     assert (info[:, 1] == 0).float().mean() > 0.05 and int(info[:, 1].max()) <= 1024
+
+
+def test_multistep_lr_matches_torch():
+    """run.MultiStepLR (no per-step Python bookkeeping) follows torch's MultiStepLR, repeated milestones included."""
+    import torch
+    from tinynerf_b200.run import MultiStepLR
+    for milestones in ([3, 5, 8], [2, 2, 6], [1]):
+        pa, pb = [torch.nn.Parameter(torch.zeros(1))], [torch.nn.Parameter(torch.zeros(1))]
+        oa, ob = torch.optim.SGD(pa, lr=1e-2), torch.optim.SGD(pb, lr=1e-2)
+        sa, sb = MultiStepLR(oa, milestones, 0.33), torch.optim.lr_scheduler.MultiStepLR(ob, milestones, 0.33)
+        for _ in range(12):
+            oa.step(); ob.step(); sa.step(); sb.step()
+            assert abs(sa.get_last_lr()[0] - sb.get_last_lr()[0]) <= 1e-12 * sb.get_last_lr()[0]
+
+
+def test_f32_rounding_helper():
+    import torch
+    from tinynerf_b200.core import _f32
+    for v in (0.01, 0.01 ** (1 / 16), 5.196152422706632 / 256, 1e5, 0.1, 1e-45, 3.4e38):
+        assert _f32(v) == torch.tensor(v, dtype=torch.float32).item()

@@ -118,8 +118,8 @@ RayMarcher = RayMarcherUnbounded | RayMarcherAABB
 
 
 def _f32(x) -> float:
-    """Python float -> the fp32 value torch uses when the scalar meets a float32 tensor."""
-    return float(torch.tensor(float(x), dtype=torch.float32).item())
+    """Python float -> the fp32 value torch uses when the scalar meets a float32 tensor (round to nearest even)."""
+    return C.c_float(float(x)).value
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,15 +250,34 @@ class RayProvider:
     ray_marcher: RayMarcher
 
     def _params(self, device, n_steps: int) -> _lib.MarchParams:
-        p = _lib.MarchParams()
+        """tnf_march_params for this provider.  The scene part (aabb / tables / step size) needs device->host reads of
+        0-dim tensors, so it is built once per (device, n_steps, scene tensors) and cached; the occupancy state
+        (grid pointer, threshold) is refreshed on every call."""
         grid = self.occupancy_grid.grid
         _lib.require_cuda(grid, "occupancy grid")
         if grid.device != device:
             raise RuntimeError("rays and occupancy grid must live on the same device")
-        p.n_steps = n_steps
+        marcher, contraction = self.ray_marcher, self.contraction
+        aabb_t = getattr(contraction, "aabb", None)
+        key = (str(device), n_steps, id(marcher), id(contraction), None if aabb_t is None else (aabb_t.data_ptr(), aabb_t._version),
+               getattr(marcher, "near", None), getattr(marcher, "far", None), getattr(marcher, "uniform_range", None))
+        cache = self.__dict__.setdefault("_param_cache", {})
+        base = cache.get(key)
+        if base is None:
+            base = self._scene_params(device, n_steps)
+            cache.clear()
+            cache[key] = base
+        p = _lib.MarchParams()
+        C.memmove(C.byref(p), C.byref(base), C.sizeof(p))
+        p._keep = base._keep
         p.grid = grid.data_ptr()
         p.gd, p.gh, p.gw = grid.shape
         p.threshold = _f32(self.occupancy_grid.threshold)
+        return p
+
+    def _scene_params(self, device, n_steps: int) -> _lib.MarchParams:
+        p = _lib.MarchParams()
+        p.n_steps = n_steps
         keep = []  # tensors that must outlive the kernel launches
         if isinstance(self.ray_marcher, RayMarcherAABB):
             if not isinstance(self.contraction, ContractionAABB):
@@ -277,11 +296,7 @@ class RayProvider:
             if not isinstance(self.contraction, ContractionMip360) or self.contraction.order != float("inf"):
                 raise NotImplementedError("RayMarcherUnbounded is fused with ContractionMip360(order=inf) only")
             p.scene = 1
-            key = (str(device), self.ray_marcher.n_samples, self.ray_marcher.near, self.ray_marcher.uniform_range)
-            cache = self.__dict__.setdefault("_tables", {})
-            if key not in cache:
-                cache[key] = self.ray_marcher.tables(device)
-            t_tab, s_tab = cache[key]
+            t_tab, s_tab = self.ray_marcher.tables(device)
             p.t_table, p.step_table = t_tab.data_ptr(), s_tab.data_ptr()
             keep += [t_tab, s_tab]
         else:

@@ -66,6 +66,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "r"((uint32_t)accumulate)
       : "memory");
 }
+// One lane of a converged warp, chosen by the hardware.  Unlike `lane == 0` the compiler keeps the code under it on the
+// uniform datapath (descriptors in uniform registers, no R2UR + waterfall loop per tcgen05.mma): measured 48 instead of
+// 147 cycles per 128x64x8 tf32 MMA (scripts/ubench/mma_bench.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -329,7 +337,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
       if (j == 0) mbar_wait(&s_tempty[b], ((tl >> 1) & 1) ^ 1);   // epilogue has drained accumulator b
       mbar_wait(&s_full[s], (it / S) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t ah = smem_u32(stages + s * 2 * kAtomBytes), al = ah + kAtomBytes;
         const uint32_t tmem_d = tmem_base + b * nd_cols;
 #pragma unroll 1
@@ -559,7 +567,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
         const int s = xi % S;
         mbar_wait(&s_xfull[s], (xi / S) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t yh = smem_u32(y_hi), yl = smem_u32(y_lo);
           const uint32_t xh = smem_u32(xst + s * 2 * kAtomBytes), xl = xh + kAtomBytes;
 #pragma unroll 1
@@ -576,7 +584,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
         __syncwarp();
       }
     }
-    if (lane == 0) mma_commit(&s_done);
+    if (elect_one()) mma_commit(&s_done);
     __syncwarp();
   }
   mbar_wait(&s_done, 0);   // every MMA of this CTA has completed

@@ -51,11 +51,17 @@ class FusedAdam(torch.optim.Optimizer):
             if not ps:
                 continue
             n = len(ps)
-            tab = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
-            numel = (C.c_int64 * n)(*[t.numel() for t in ps])
+            key = tuple(t.data_ptr() for ts in (ps, gs, ms, vs) for t in ts)
+            tables = self.__dict__.setdefault("_tnf_tables", {})
+            cached = tables.get(id(group))
+            if cached is None or cached[0] != key:  # pointer tables are rebuilt only when a tensor moved
+                tab = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+                cached = (key, tab(ps), tab(gs), tab(ms), tab(vs), (C.c_int64 * n)(*[t.numel() for t in ps]))
+                tables[id(group)] = cached
+            _, tp, tg, tm, tv, numel = cached
             b1, b2 = group["betas"]
             with torch.cuda.device(ps[0].device):
-                _lib.call("tnf_adam_step", tab(ps), tab(gs), tab(ms), tab(vs), numel, n, float(group["lr"]), float(b1),
+                _lib.call("tnf_adam_step", tp, tg, tm, tv, numel, n, float(group["lr"]), float(b1),
                           float(b2), float(group["eps"]), float(group["weight_decay"]), int(step), _lib.stream_ptr(),
                           nbytes=28 * sum(t.numel() for t in ps), extra_kernels=math.ceil(n / 48) - 1)
         return loss

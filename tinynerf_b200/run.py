@@ -69,6 +69,27 @@ def shard_slices(depth: int, rank: int, world: int) -> Tuple[int, int]:
     return rank * per, (rank + 1) * per
 
 
+class MultiStepLR:
+    """torch.optim.lr_scheduler.MultiStepLR as the reference configures it (src/run.py:188-199) without the per-step
+    Python bookkeeping of the torch class (~0.2 ms per call, comparable to a whole iteration's device time here):
+    lr = base_lr * gamma ** (number of milestones <= epoch), milestones counted with multiplicity."""
+
+    def __init__(self, optimizer, milestones, gamma: float):
+        self.optimizer, self.milestones, self.gamma = optimizer, sorted(int(m) for m in milestones), float(gamma)
+        self.base_lrs = [g["lr"] for g in optimizer.param_groups]
+        self.last_epoch = 0
+
+    def step(self) -> None:
+        self.last_epoch += 1
+        if self.last_epoch in self.milestones:  # torch multiplies the CURRENT lr by gamma once per occurrence
+            k = self.milestones.count(self.last_epoch)
+            for g in self.optimizer.param_groups:
+                g["lr"] = g["lr"] * self.gamma ** k
+
+    def get_last_lr(self):
+        return [g["lr"] for g in self.optimizer.param_groups]
+
+
 class RayStore:
     """Rays + colours of a scene, shuffled per epoch like DataLoader(shuffle=True) (src/run.py:116-122).
     Lives on `device` (HBM-resident, no per-batch H2D) or in pinned host memory (`host=True`), in which
@@ -107,10 +128,11 @@ class RayStore:
         idx = self._perm[self._pos:self._pos + batch]
         self._pos += batch
         if self.host:
-            if self._stage is None or self._stage.size(0) != batch:
-                self._stage = torch.empty(batch, 9).pin_memory()
-            torch.index_select(self.data, 0, idx, out=self._stage)
-            rows = self._stage.to(self.device, non_blocking=True)
+            if self._stage is None or self._stage.size(0) < batch:  # grow-only: pinning memory is a slow, synchronising call
+                self._stage = torch.empty(max(batch, 2 * (0 if self._stage is None else self._stage.size(0))), 9).pin_memory()
+            stage = self._stage[:batch]
+            torch.index_select(self.data, 0, idx, out=stage)
+            rows = stage.to(self.device, non_blocking=True)
             self.h2d_bytes += rows.numel() * 4
         else:
             rows = self.data.index_select(0, idx)
@@ -177,8 +199,7 @@ class Trainer:
                 dist.broadcast(_flat_dense(p.data), 0)
         self.optimizer = FusedAdam(self.renderer.parameters(), lr=1e-2, eps=1e-15, weight_decay=1e-5)
         s = self.steps
-        self.scheduler = torch.optim.lr_scheduler.MultiStepLR(
-            self.optimizer, milestones=[s // 2, s * 3 // 4, s * 5 // 6, s * 9 // 10], gamma=0.33)
+        self.scheduler = MultiStepLR(self.optimizer, milestones=[s // 2, s * 3 // 4, s * 5 // 6, s * 9 // 10], gamma=0.33)
         self.tv_reg_alpha, self.l1_reg_alpha = 0.0001, 0.0
         self.train_step = 0
         self._fused = None
@@ -315,7 +336,8 @@ class Trainer:
 
     def step(self) -> Dict[str, float]:
         packed, rgbs, info = self._take_batch()
-        self.renderer.train()
+        if not self.renderer.training:
+            self.renderer.train()
         if self.train_step % self.occupancy_grid_updates == 0:
             self.update_occupancy()
         grid_ready = torch.cuda.current_stream(self.device).record_event() if self._side is not None else None
