@@ -42,6 +42,22 @@ struct WArgs {
   int flags;
 };
 
+// ---- per-warp cp.async ring -------------------------------------------------------------------------
+// Every lane copies the 16 bytes (4 samples) it will consume itself straight from global to its private slot of a
+// shared-memory ring (LDGSTS, no registers held, L1 bypassed) kDepth-1 rounds ahead, and later reads the slot back
+// with one LDS.128.  No cross-lane traffic, so cp.async.wait_group is the only synchronisation.  This keeps
+// (kDepth-1) x 1-1.5 KB of loads in flight per warp instead of the one round a register prefetch can afford.
+constexpr int kDepth = 4;
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool ok) {  // !ok: zero-fill, nothing is read
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_ring() { asm volatile("cp.async.wait_group %0;" ::"n"(kDepth - 1) : "memory"); }
+
 // MODE 0: all arrays contiguous + 16B aligned (float4 path); 1: steps strided, rest aligned; 2: scalar.
 // `p` points at the task's tile origin, `rel` is the tile-relative index of the lane's first sample and
 // `lim` = n_samples - tile0 bounds the reads.
@@ -65,6 +81,28 @@ __device__ __forceinline__ void load_steps(const float* __restrict__ p, long lon
     for (int i = 0; i < 4; ++i) v[i] = (rel + i < lim) ? __ldg(p + (long long)(rel + i) * stride) : 0.f;
   }
 }
+// asynchronous variants of load_vec / load_steps into a ring slot (zeros beyond the end of the arrays)
+template <int MODE>
+__device__ __forceinline__ void ring_vec(float4* slot, const float* __restrict__ p, int rel, int lim) {
+  if (MODE != 2 && rel + 3 < lim) {
+    cp_async16(slot, p + rel);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cp_async4(reinterpret_cast<float*>(slot) + i, (rel + i < lim) ? p + rel + i : p, rel + i < lim);
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void ring_steps(float4* slot, const float* __restrict__ p, long long stride, int rel, int lim) {
+  if (MODE == 0) {
+    ring_vec<0>(slot, p, rel, lim);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      cp_async4(reinterpret_cast<float*>(slot) + i, (rel + i < lim) ? p + (long long)(rel + i) * stride : p, rel + i < lim);
+  }
+}
+__device__ __forceinline__ void unpack4(const float4 t, float v[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+
 // store the lane's 4 values, only samples in [lo, hi) (tile-relative) belong to this task
 template <int MODE>
 __device__ __forceinline__ void store_vec(float* p, int rel, int lo, int hi, const float v[4]) {
@@ -157,17 +195,25 @@ __device__ __forceinline__ float seg_scan_add_down(float P, int lim) {
   return P;
 }
 
+// a = __expf(x), x = -sigma*delta <= 0 (src/cuda.cu:24).  __expf is ex2.approx(x * log2e) wrapped in a rescaling that
+// only acts when the result is below 2^-126 (6 instructions per sample).  FTZ == true drops the wrapper: bit-identical
+// for every a >= 2^-126 and 0 instead of a denormal below -- indistinguishable downstream unless the threshold itself
+// is below ~2^-99 (the caller keeps the exact form then): T*a is <= thr either way, and 1.-a is 1 in both.
+template <bool FTZ>
+__device__ __forceinline__ float exp_fast(float x) {
+  if (!FTZ) return __expf(x);
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950216293334961f));
+  return y;
+}
+
 // w = T*(1.-a) exactly as the reference's fp64 expression (src/cuda.cu:25).  For a in [0.5, 2] the fp32
 // evaluation is bit-identical: 1-a is exact (Sterbenz) and the 48-bit product is exact in fp64, so both
 // round the same real number to fp32 once.  Only a < 0.5 (sigma*delta > 0.69) takes the fp64 path.
 __device__ __forceinline__ void weights_from_T(const float T[4], const float a[4], float thr, float w[4]) {
-  bool dp = false;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    w[i] = (T[i] > thr) ? T[i] * (1.f - a[i]) : 0.f;
-    dp |= !(a[i] >= 0.5f);
-  }
-  if (dp) {
+  for (int i = 0; i < 4; ++i) w[i] = (T[i] > thr) ? T[i] * (1.f - a[i]) : 0.f;
+  if (!(fminf(fminf(a[0], a[1]), fminf(a[2], a[3])) >= 0.5f)) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (!(a[i] >= 0.5f) && T[i] > thr) w[i] = (float)((double)T[i] * (1. - (double)a[i]));
@@ -181,6 +227,26 @@ __device__ __noinline__ void serial_ray_fwd(const float* __restrict__ sig, const
                                             float* out) {
   float transmittance = 1.f;
   long long k = start;
+  // Eight samples at a time while none of them terminates: the loads and exponentials of a batch are independent, only
+  // the transmittance products form a chain, in the reference's order -- same values, ~5x fewer stall cycles for the
+  // one lane that walks.  The scalar loop below finishes the ray (termination inside a batch, tail).
+  while (k + 8 <= end) {
+    float al[8], tr[9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) al[i] = __expf(-sig[k + i] * stp[(k + i) * ss]);
+    tr[0] = transmittance;
+    bool alive = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      alive &= tr[i] > thr;
+      tr[i + 1] = tr[i] * al[i];
+    }
+    if (!alive) break;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[k + i] = tr[i] * (1. - al[i]);  // double multiply, as in the reference
+    transmittance = tr[8];
+    k += 8;
+  }
   while (transmittance > thr && k < end) {
     const float alpha = __expf(-sig[k] * stp[k * ss]);
     out[k] = transmittance * (1. - alpha);  // double multiply, as in the reference
@@ -228,8 +294,34 @@ __device__ __forceinline__ Task task_setup(const WArgs& A, int task, unsigned* m
     if (__any_sync(kFullMask, bad) && lane == 0) atomicOr(A.status, 1u);
   }
   t.tile0 = (long long)task * A.tile;
+  const long long tile_end = t.tile0 + A.tile;
   t.r_lo = warp_lower_bound(A.info, R, t.tile0, lane);
-  t.r_hi = warp_lower_bound(A.info, R, t.tile0 + A.tile, lane);
+  for (int i = lane; i < (A.tile >> 5); i += 32) mask[i] = 0u;
+  __syncwarp();
+  // The rays of the tile follow r_lo contiguously: one forward sweep over packing info both scatters the ray heads
+  // into the bitfield and finds r_hi (first ray starting at or after the tile's end) -- no second binary search.
+  // Bounded (64 x 32 rays) so that arbitrary, unsorted info cannot make it run long; beyond that, search.
+  t.r_hi = -1;
+  int base = t.r_lo;
+  for (int it = 0; it < 64; ++it, base += 32) {
+    const int r = base + lane;
+    int2 e = make_int2(0, 0);
+    if (r < R) e = __ldg(&A.info[r]);
+    const bool beyond = (r >= R) || ((long long)e.x >= tile_end);
+    const unsigned bm = __ballot_sync(kFullMask, beyond);
+    const bool mine = bm ? (lane < __ffs(bm) - 1) : true;  // rays before the first "beyond" ray
+    const long long b = (long long)e.x - t.tile0;
+    if (mine && e.y > 0 && b >= 0 && b < A.tile) atomicOr(&mask[b >> 5], 1u << (b & 31));
+    if (bm) { t.r_hi = base + __ffs(bm) - 1; break; }
+  }
+  if (t.r_hi < 0) {
+    t.r_hi = warp_lower_bound(A.info, R, tile_end, lane);
+    for (int r = base + lane; r < t.r_hi; r += 32) {
+      const int2 e = __ldg(&A.info[r]);
+      const long long b = (long long)e.x - t.tile0;
+      if (e.y > 0 && b >= 0 && b < A.tile) atomicOr(&mask[b >> 5], 1u << (b & 31));
+    }
+  }
   long long s0 = (t.r_lo < R) ? (long long)__ldg(&A.info[t.r_lo].x) : N;
   long long s1 = (t.r_hi < R) ? (long long)__ldg(&A.info[t.r_hi].x) : N;
   s0 = s0 < 0 ? 0 : (s0 > N ? N : s0);
@@ -240,20 +332,13 @@ __device__ __forceinline__ Task task_setup(const WArgs& A, int task, unsigned* m
   t.hi = (int)(s1 - t.tile0);
   t.lim = (int)(N - t.tile0);
   t.valid = (s0 >= t.tile0) && (s1 > s0) && (t.r_hi > t.r_lo);
-  if (!t.valid) return t;
-  for (int i = lane; i < (A.tile >> 5); i += 32) mask[i] = 0u;
-  __syncwarp();
-  for (int r = t.r_lo + lane; r < t.r_hi; r += 32) {
-    const int2 e = __ldg(&A.info[r]);
-    const long long b = (long long)e.x - t.tile0;
-    if (e.y > 0 && b >= 0 && b < A.tile) atomicOr(&mask[b >> 5], 1u << (b & 31));
-  }
   __syncwarp();
   return t;
 }
 
-template <int MODE>
+template <int MODE, bool FTZ>
 __global__ void __launch_bounds__(kWarps * 32, 4) weights_fwd_kernel(const WArgs A) {
+  extern __shared__ float4 s_ring_dyn[];  // [kWarps][kDepth][2 arrays][32 lanes]
   __shared__ unsigned s_mask[kWarps][kMaskWords];
   __shared__ int s_q[kWarps][kQueue];
   __shared__ int s_qn[kWarps];
@@ -276,21 +361,32 @@ __global__ void __launch_bounds__(kWarps * 32, 4) weights_fwd_kernel(const WArgs
     const float* stp = A.steps + t.tile0 * A.sstride;
     float* out = A.out + t.tile0;
     float carry = 1.f;  // product since the last ray head, through the end of the previous round
-    int rpos = t.lo & ~127;
-    float s[4], d[4];
-    load_vec<MODE>(sig, rpos + lane * 4, t.lim, s);
-    load_steps<MODE>(stp, A.sstride, rpos + lane * 4, t.lim, d);
-    for (; rpos < t.hi; rpos += 128) {
-      const int rel = rpos + lane * 4;
-      float sn[4], dn[4];  // software prefetch of the next round: two 512 B requests per warp stay in flight
-      if (rpos + 128 < t.hi) {
-        load_vec<MODE>(sig, rel + 128, t.lim, sn);
-        load_steps<MODE>(stp, A.sstride, rel + 128, t.lim, dn);
+    const int r_first = t.lo & ~127;
+    const int n_rounds = (t.hi - r_first + 127) >> 7;
+    float4* ring = s_ring_dyn + wib * (kDepth * 2 * 32) + lane;  // slot (stage, array) at ring[(stage*2+array)*32]
+    auto issue = [&](int j) {  // start the copies of round j (an empty group past the end keeps the count uniform)
+      if (j < n_rounds) {
+        const int rl = r_first + j * 128 + lane * 4;
+        float4* slot = ring + ((j & (kDepth - 1)) * 2) * 32;
+        ring_vec<MODE>(slot, sig, rl, t.lim);
+        ring_steps<MODE>(slot + 32, stp, A.sstride, rl, t.lim);
       }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int j = 0; j < kDepth - 1; ++j) issue(j);
+    for (int j = 0; j < n_rounds; ++j) {
+      const int rpos = r_first + j * 128;
+      const int rel = rpos + lane * 4;
+      issue(j + kDepth - 1);  // refills the stage consumed in the previous iteration
+      cp_async_wait_ring();   // round j has landed
+      float s[4], d[4];
+      unpack4(ring[((j & (kDepth - 1)) * 2) * 32], s);
+      unpack4(ring[((j & (kDepth - 1)) * 2 + 1) * 32], d);
       float a[4], T[4], w[4];
       const unsigned hb = (rel < A.tile) ? ((mask[rel >> 5] >> (rel & 31)) & 0xFu) : 0u;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = __expf(-s[i] * d[i]);
+      for (int i = 0; i < 4; ++i) a[i] = exp_fast<FTZ>(-s[i] * d[i]);
 
       // lane aggregate: product of this lane's samples after its last head
       float P = a[0];
@@ -315,9 +411,10 @@ __global__ void __launch_bounds__(kWarps * 32, 4) weights_fwd_kernel(const WArgs
         // position in its ray); plus non-monotone (a > 1 / NaN) and underflow cases.
         const float bub = (float)(rpos + 130 - t.lo) * 1.7881393e-07f;
         const float blo = thr - thr * bub, bhi = thr + thr * bub;
-        bool sus = !(fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])) <= 1.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sus |= (T[i] >= blo) & (T[i] <= bhi);
+        // one compare on the closest approach of the four T to thr (|T - thr| <= thr*bub, the same band up to an ulp
+        // of thr; the per-sample test below decides with the exact per-ray bound)
+        const float near = fminf(fminf(fabsf(T[0] - thr), fabsf(T[1] - thr)), fminf(fabsf(T[2] - thr), fabsf(T[3] - thr)));
+        bool sus = !(fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])) <= 1.f) | !(near > thr * (bub + 2.4e-7f));
         if (tiny_thr) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) sus |= T[i] < 7.8886091e-31f;
@@ -342,8 +439,6 @@ __global__ void __launch_bounds__(kWarps * 32, 4) weights_fwd_kernel(const WArgs
       }
       if (MODE != 2 && !edge) st_stream_f4(out + rel, make_float4(w[0], w[1], w[2], w[3]));
       else store_vec<MODE>(out, rel, t.lo, t.hi, w);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { s[i] = sn[i]; d[i] = dn[i]; }
     }
 
     if (exact) {
@@ -371,7 +466,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) weights_fwd_kernel(const WArgs
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kWarps * 32, 4) weights_bwd_kernel(const WArgs A) {
+__global__ void __launch_bounds__(kWarps * 32, 3) weights_bwd_kernel(const WArgs A) {
+  extern __shared__ float4 s_ring_dyn[];  // [kWarps][kDepth][3 arrays][32 lanes]
   __shared__ unsigned s_mask[kWarps][kMaskWords];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned* mask = s_mask[wib];
@@ -388,20 +484,31 @@ __global__ void __launch_bounds__(kWarps * 32, 4) weights_bwd_kernel(const WArgs
     float* out = A.out + t.tile0;
     const int first = t.lo & ~127;
     const int last = (t.hi - 1) & ~127;
+    const int n_rounds = ((last - first) >> 7) + 1;
+    float4* ring = s_ring_dyn + wib * (kDepth * 3 * 32) + lane;  // slot (stage, array) at ring[(stage*3+array)*32]
 
     // Pass A (descending): S_k = sum_{j>k in ray} w_j*g_j, parked in grad_sigmas.
     {
       float carry = 0.f;
-      float w[4], g[4];
-      load_vec<MODE>(wp, last + lane * 4, t.lim, w);
-      load_vec<MODE>(gp, last + lane * 4, t.lim, g);
-      for (int rpos = last; rpos >= first; rpos -= 128) {
-        const int rel = rpos + lane * 4;
-        float wn[4], gn[4];  // prefetch the next (lower) round
-        if (rpos - 128 >= first) {
-          load_vec<MODE>(wp, rel - 128, t.lim, wn);
-          load_vec<MODE>(gp, rel - 128, t.lim, gn);
+      auto issue = [&](int j) {
+        if (j < n_rounds) {
+          const int rl = last - j * 128 + lane * 4;
+          float4* slot = ring + ((j & (kDepth - 1)) * 3) * 32;
+          ring_vec<MODE>(slot, wp, rl, t.lim);
+          ring_vec<MODE>(slot + 32, gp, rl, t.lim);
         }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int j = 0; j < kDepth - 1; ++j) issue(j);
+      for (int j = 0; j < n_rounds; ++j) {
+        const int rpos = last - j * 128;
+        const int rel = rpos + lane * 4;
+        issue(j + kDepth - 1);
+        cp_async_wait_ring();
+        float w[4], g[4];
+        unpack4(ring[((j & (kDepth - 1)) * 3) * 32], w);
+        unpack4(ring[((j & (kDepth - 1)) * 3 + 1) * 32], g);
         const bool edge = (rpos < t.lo) | (rpos + 128 > t.hi);
         float c[4], S[4];
         const unsigned hb5 = head_bits5(mask, rel, A.tile);
@@ -430,8 +537,6 @@ __global__ void __launch_bounds__(kWarps * 32, 4) weights_bwd_kernel(const WArgs
         for (int i = 2; i >= 0; --i) S[i] = ((tail >> i) & 1u) ? 0.f : S[i + 1] + c[i + 1];
         if (MODE != 2 && !edge) *reinterpret_cast<float4*>(out + rel) = make_float4(S[0], S[1], S[2], S[3]);
         else store_vec<MODE>(out, rel, t.lo, t.hi, S);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { w[i] = wn[i]; g[i] = gn[i]; }
       }
     }
     __syncwarp();
@@ -440,30 +545,46 @@ __global__ void __launch_bounds__(kWarps * 32, 4) weights_bwd_kernel(const WArgs
     // grad_sigma_k = delta_k * (T_{k+1}*g_k - S_k).  Each lane re-reads the S it stored itself.
     {
       float carryT = 1.f;
-      float s[4], d[4], g[4];
-      load_vec<MODE>(sig, first + lane * 4, t.lim, s);
-      load_steps<MODE>(stp, A.sstride, first + lane * 4, t.lim, d);
-      load_vec<MODE>(gp, first + lane * 4, t.lim, g);
-      for (int rpos = first; rpos <= last; rpos += 128) {
-        const int rel = rpos + lane * 4;
-        float sn[4], dn[4], gn[4];
-        if (rpos + 128 <= last) {
-          load_vec<MODE>(sig, rel + 128, t.lim, sn);
-          load_steps<MODE>(stp, A.sstride, rel + 128, t.lim, dn);
-          load_vec<MODE>(gp, rel + 128, t.lim, gn);
+      auto issue = [&](int j) {
+        if (j < n_rounds) {
+          const int rl = first + j * 128 + lane * 4;
+          float4* slot = ring + ((j & (kDepth - 1)) * 3) * 32;
+          ring_vec<MODE>(slot, sig, rl, t.lim);
+          ring_steps<MODE>(slot + 32, stp, A.sstride, rl, t.lim);
+          ring_vec<MODE>(slot + 64, gp, rl, t.lim);
         }
+        cp_async_commit();
+      };
+      // S is re-read with plain loads (program order after this lane's own stores of pass A), one round ahead
+      auto load_S = [&](int rpos, float S[4]) {
+        const int rel = rpos + lane * 4;
         const bool edge = (rpos < t.lo) | (rpos + 128 > t.hi);
-        float a[4], S[4], o[4];
         if (MODE != 2 && !edge) {
-          const float4 v = *reinterpret_cast<const float4*>(out + rel);
-          S[0] = v.x; S[1] = v.y; S[2] = v.z; S[3] = v.w;
+          unpack4(*reinterpret_cast<const float4*>(out + rel), S);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) S[i] = (rel + i >= t.lo && rel + i < t.hi) ? out[rel + i] : 0.f;
         }
+      };
+#pragma unroll
+      for (int j = 0; j < kDepth - 1; ++j) issue(j);
+      float S[4], Sn[4];
+      load_S(first, S);
+      for (int j = 0; j < n_rounds; ++j) {
+        const int rpos = first + j * 128;
+        const int rel = rpos + lane * 4;
+        issue(j + kDepth - 1);
+        if (j + 1 < n_rounds) load_S(rpos + 128, Sn);
+        cp_async_wait_ring();
+        float s[4], d[4], g[4];
+        unpack4(ring[((j & (kDepth - 1)) * 3) * 32], s);
+        unpack4(ring[((j & (kDepth - 1)) * 3 + 1) * 32], d);
+        unpack4(ring[((j & (kDepth - 1)) * 3 + 2) * 32], g);
+        const bool edge = (rpos < t.lo) | (rpos + 128 > t.hi);
+        float a[4], o[4];
         const unsigned hb = (rel < A.tile) ? ((mask[rel >> 5] >> (rel & 31)) & 0xFu) : 0u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = __expf(-s[i] * d[i]);
+        for (int i = 0; i < 4; ++i) a[i] = exp_fast<true>(-s[i] * d[i]);  // gradients carry a tolerance, not bit parity
         float P = a[0];
 #pragma unroll
         for (int i = 1; i < 4; ++i) P = ((hb >> i) & 1u) ? a[i] : P * a[i];
@@ -483,7 +604,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) weights_bwd_kernel(const WArgs
         if (MODE != 2 && !edge) st_stream_f4(out + rel, make_float4(o[0], o[1], o[2], o[3]));
         else store_vec<MODE>(out, rel, t.lo, t.hi, o);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { s[i] = sn[i]; d[i] = dn[i]; g[i] = gn[i]; }
+        for (int i = 0; i < 4; ++i) S[i] = Sn[i];
       }
     }
     __syncwarp();
@@ -525,15 +646,19 @@ __global__ void fallback_bwd_kernel(const WArgs A) {
   serial_ray_bwd(A.sigmas, A.steps, A.sstride, A.w, A.g, st, en, A.out);
 }
 
-int pick_tile(long long n) {
-  // enough tasks to give every SM several waves of resident warps; tiles between 256 and kMaxTile samples
+int pick_tile(long long n, int warps_per_sm) {
+  // Tiles between 256 and kMaxTile samples.  Small inputs get ONE wave: the tile is rounded UP so that the task count
+  // does not exceed the resident warps (a second, mostly empty wave would double the latency-bound run time).
   static const int forced = [] {
     const char* e = getenv("TNF_W_TILE");  // tuning knob (multiple of 128, <= 2048)
     return e ? atoi(e) : 0;
   }();
   if (forced >= 128 && forced <= kMaxTile && forced % 128 == 0) return forced;
-  const long long want = (long long)sm_count() * 32;
-  long long tile = (n / want) & ~127LL;
+  // One task per resident warp and k full waves: the smallest k whose tile fits kMaxTile, then the tile rounded UP
+  // so the task count does not spill into a mostly empty extra wave (worth 13% at 2^24 samples).
+  const long long slots = (long long)sm_count() * warps_per_sm;
+  const long long k = ceil_div(n, slots * kMaxTile);
+  long long tile = (ceil_div(n, k * slots) + 127) & ~127LL;
   if (tile < 256) tile = 256;
   if (tile > kMaxTile) tile = kMaxTile;
   return (int)tile;
@@ -544,7 +669,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 int launch(bool bwd, WArgs A, cudaStream_t st) {
   const bool trusted = A.flags & TNF_W_TRUSTED_PARTITION;
   if (!trusted) TNF_CUDA(cudaMemsetAsync(A.status, 0, sizeof(unsigned), st));
-  A.tile = pick_tile(A.n);
+  A.tile = pick_tile(A.n, bwd ? 3 * kWarps : 4 * kWarps);
   const long long n_tasks = ceil_div(A.n, A.tile);
   TNF_REQUIRE(n_tasks < (1LL << 30), "too many samples (%lld)", A.n);
   A.n_tasks = (int)n_tasks;
@@ -553,15 +678,25 @@ int launch(bool bwd, WArgs A, cudaStream_t st) {
   const int mode = !al ? 2 : ((A.sstride == 1 && aligned16(A.steps)) ? 0 : 1);
   const long long ctas = ceil_div(n_tasks, kWarps);  // one task per warp; the block scheduler balances
   const dim3 grid((unsigned)ctas), block(kWarps * 32);
+  const size_t ring_fwd = (size_t)kWarps * kDepth * 2 * 32 * sizeof(float4);  // 32 KB
+  const size_t ring_bwd = (size_t)kWarps * kDepth * 3 * 32 * sizeof(float4);  // 48 KB
+  static thread_local bool configured = false;
+  if (!configured) {  // the backward ring plus the static arrays exceeds the 48 KB default
+    TNF_CUDA(cudaFuncSetAttribute(weights_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bwd));
+    TNF_CUDA(cudaFuncSetAttribute(weights_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bwd));
+    TNF_CUDA(cudaFuncSetAttribute(weights_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bwd));
+    configured = true;
+  }
   if (!bwd) {
-    if (mode == 0) weights_fwd_kernel<0><<<grid, block, 0, st>>>(A);
-    else if (mode == 1) weights_fwd_kernel<1><<<grid, block, 0, st>>>(A);
-    else weights_fwd_kernel<2><<<grid, block, 0, st>>>(A);
+    const bool ftz = A.thr >= 1.5777218e-30f;  // 2^-99, the kernel's tiny_thr boundary (see exp_fast)
+    if (mode == 0) { if (ftz) weights_fwd_kernel<0, true><<<grid, block, ring_fwd, st>>>(A); else weights_fwd_kernel<0, false><<<grid, block, ring_fwd, st>>>(A); }
+    else if (mode == 1) { if (ftz) weights_fwd_kernel<1, true><<<grid, block, ring_fwd, st>>>(A); else weights_fwd_kernel<1, false><<<grid, block, ring_fwd, st>>>(A); }
+    else { if (ftz) weights_fwd_kernel<2, true><<<grid, block, ring_fwd, st>>>(A); else weights_fwd_kernel<2, false><<<grid, block, ring_fwd, st>>>(A); }
     TNF_LAUNCH_CHECK("weights_fwd_kernel");
   } else {
-    if (mode == 0) weights_bwd_kernel<0><<<grid, block, 0, st>>>(A);
-    else if (mode == 1) weights_bwd_kernel<1><<<grid, block, 0, st>>>(A);
-    else weights_bwd_kernel<2><<<grid, block, 0, st>>>(A);
+    if (mode == 0) weights_bwd_kernel<0><<<grid, block, ring_bwd, st>>>(A);
+    else if (mode == 1) weights_bwd_kernel<1><<<grid, block, ring_bwd, st>>>(A);
+    else weights_bwd_kernel<2><<<grid, block, ring_bwd, st>>>(A);
     TNF_LAUNCH_CHECK("weights_bwd_kernel");
   }
   if (!trusted) {

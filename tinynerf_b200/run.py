@@ -209,9 +209,26 @@ class Trainer:
                 self._fused = FusedKPlanesStep(self.renderer, tv_alpha=self.tv_reg_alpha, grad_scale=cfg.grad_scale,
                                                world=world)
         self._chunks_guess = 0.0
+        if world > 1 and self.device.type == "cuda":
+            self._warm_collectives()
         self._side = torch.cuda.Stream(device=self.device) if (cfg.prefetch and self.device.type == "cuda") else None
         self._next = None
         self.last: Dict[str, float] = {}
+
+    def _warm_collectives(self) -> None:
+        """Run every collective of an iteration once at its real size (gradient all-reduce, ray-count all-reduce,
+        occupancy all-gather) so NCCL's lazy channel/buffer set-up happens at construction, not inside a step."""
+        grads = self._fused.flat_grad if self._fused is not None else torch.zeros(
+            sum(p.numel() for p in self.renderer.parameters()), device=self.device)
+        for _ in range(2):
+            dist.all_reduce(grads)
+            global_ray_count(1, self.device, self.world)
+            g = self.occupancy_grid.grid
+            z0, z1 = shard_slices(g.size(0), self.rank, self.world)
+            dist.all_gather_into_tensor(torch.empty_like(g).view(-1), g[z0:z1].reshape(-1).clone())
+        if self._fused is not None:
+            grads.zero_()
+        torch.cuda.synchronize(self.device)
 
     # ---- a11: dynamic batch accumulator (src/run.py:215-244) -----------------------------------
     @torch.no_grad()
