@@ -214,6 +214,23 @@ int tnf_color_input(const float* dirs, int64_t ld_dirs, const float* feats, int6
 int tnf_head_bwd(const float* h, int64_t ldh, const float* head_w, const float* out, const float* dout, float* dh,
                  float* dhead_w, float* dhead_b, int64_t m, int32_t n, int32_t n_head, int32_t head_act, void* stream);
 
+/* Both decoder heads of the K-Planes / Cobafa pipelines in one persistent kernel (forward):
+ *   sigma = exp(W_s1 relu(W_s0 f + b_s0) + b_s1 - 1)                   VanillaOpacityDecoder.forward, src/models.py:76-77
+ *   rgb   = sigmoid(W_c4 relu(W_c3 relu(W_c2 relu(W_c1 relu(W_c0 x + b_c0) ...))))   VanillaColorDecoder.forward, :86-89
+ * feats [m, feat_dim] are the feature rows f, xc [m, k0] the colour-input rows x = [PE(d) | d | f] (tnf_color_input).
+ * color_w/color_b: [host] arrays of 5 device pointers (W_c0 [64,k0], W_c1..3 [64,64], W_c4 [3,64] and biases);
+ * sigma_w/sigma_b: 2 device pointers (W_s0 [64,feat_dim], W_s1 [1,64]).  Hidden width is 64, three hidden colour layers
+ * (the reference's VanillaColorDecoder(8, dim, 64, 3) / VanillaOpacityDecoder(dim), src/run.py:131-150).
+ * h_out: optional [host] array of 4 device pointers [m,64] receiving the colour head's hidden activations, hs_out [m,64]
+ * the density head's (the backward kernels read them); rgb [m,3], sigma [m].  workspace: device scratch of
+ * tnf_heads_workspace_bytes(feat_dim, k0) bytes (packed weight images), 16-byte aligned. */
+int64_t tnf_heads_workspace_bytes(int32_t feat_dim, int32_t k0);
+int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_dim, const float* xc, int64_t ld_xc, int32_t k0,
+                  const float* const* color_w /*[host]*/, const float* const* color_b /*[host]*/,
+                  const float* const* sigma_w /*[host]*/, const float* const* sigma_b /*[host]*/,
+                  float* const* h_out /*[host], optional*/, float* hs_out /*optional*/, float* rgb, float* sigma, int64_t m,
+                  void* workspace, void* stream);
+
 /* ---- a18: compositing (segment sums over packed rays) -----------------------------------------
  * Replaces the index_add_ block of NerfRenderer.forward (src/core.py:256-265; the reference's own
  * "TODO: cuda kernel this"):  rgb_ray = sum_k w_k*rgb_k ; opacity = sum_k w_k ;

@@ -1,0 +1,70 @@
+"""tnf_heads_fwd (both decoder heads fused in one tcgen05 kernel) against the per-layer modules (which are themselves
+checked against torch fp32 in test_gpu_mlp.py) and against a float64 evaluation.  Tolerance 1e-5 relative (north_star)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tinynerf_b200 import _lib, mlp_ops, models
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run_fused(sig, col, feats, dirs):
+    lib = _lib.load()
+    n, F = feats.shape
+    xc = mlp_ops.color_input(feats, dirs, col.pe.freqs.numel())
+    k0, ld = xc.size(1), xc.stride(0)
+    sl, cl = sig.net.linears(), col.net.linears()
+    tab = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    hs = torch.full((n, 64), float("nan"), device=DEV)
+    h = [torch.full((n, 64), float("nan"), device=DEV) for _ in range(4)]
+    rgb = torch.full((n, 3), float("nan"), device=DEV)
+    sigma = torch.full((n,), float("nan"), device=DEV)
+    ws = torch.empty(int(lib.tnf_heads_workspace_bytes(F, k0)) // 4, device=DEV)
+    _lib.call("tnf_heads_fwd", feats.data_ptr(), feats.stride(0), F, xc.data_ptr(), ld, k0, tab([l.weight for l in cl]),
+              tab([l.bias for l in cl]), tab([l.weight for l in sl]), tab([l.bias for l in sl]), tab(h), hs.data_ptr(),
+              rgb.data_ptr(), sigma.data_ptr(), n, ws.data_ptr(), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return sigma, rgb, hs, h, xc
+
+
+def _ref64(sig, col, feats, xc):
+    f64 = lambda t: t.detach().double()
+    sl, cl = sig.net.linears(), col.net.linears()
+    hs = torch.relu(f64(feats) @ f64(sl[0].weight).T + f64(sl[0].bias))
+    sigma = torch.exp(hs @ f64(sl[1].weight).T + f64(sl[1].bias) - 1.0).ravel()
+    x = f64(xc)
+    hl = []
+    for l in cl[:-1]:
+        x = torch.relu(x @ f64(l.weight).T + f64(l.bias))
+        hl.append(x)
+    rgb = torch.sigmoid(x @ f64(cl[-1].weight).T + f64(cl[-1].bias))
+    return sigma, rgb, hs, hl
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 300, 148 * 128 + 5, 2 * 148 * 128 + 77, 1 << 18])
+def test_heads_fwd_matches_float64_and_per_layer_kernels(n):
+    torch.manual_seed(n)
+    sig = models.VanillaOpacityDecoder(96).to(DEV)
+    col = models.VanillaColorDecoder(8, 96, 64, 3).to(DEV)
+    feats = torch.randn(n, 96, device=DEV) * 0.5
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+    sigma, rgb, hs, h, xc = _run_fused(sig, col, feats, dirs)
+    s64, r64, hs64, h64 = _ref64(sig, col, feats, xc)
+
+    def close(a, b, what):
+        err = (a.double() - b).abs()
+        tol = 1e-5 * b.abs() + 2e-6
+        assert bool((err <= tol).all()), f"{what}: worst excess {(err - tol).max().item():.3e} at n={n}"
+
+    close(hs, hs64, "sigma hidden")
+    close(sigma, s64, "sigma")
+    for i in range(4):
+        close(h[i], h64[i], f"colour hidden {i}")
+    close(rgb, r64, "rgb")
+    # and the per-layer module path gives the same numbers to fp32 rounding
+    with torch.no_grad():
+        assert torch.allclose(sig(feats).ravel(), sigma, rtol=2e-5, atol=1e-6)
+        assert torch.allclose(col(feats, dirs), rgb, rtol=2e-5, atol=1e-6)

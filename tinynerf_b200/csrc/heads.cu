@@ -1,0 +1,408 @@
+// a15/a16 -- both decoder heads of a sample tile in ONE persistent tcgen05 kernel (forward):
+//   sigma  = truncated_exp(W_s1 relu(W_s0 f + b_s0) + b_s1 - 1)                     VanillaOpacityDecoder, src/models.py:70-77
+//   rgb    = sigmoid(W_c4 relu(W_c3 relu(W_c2 relu(W_c1 relu(W_c0 x + b)...))))     VanillaColorDecoder,   src/models.py:79-89
+// with x = [PE(d) | d | f] (the colour-input row, tnf_color_input) and f the feature row.
+//
+// The per-layer kernels (mlp.cu) stream every hidden activation through HBM and pay a launch per layer.  Here a
+// 128-sample tile stays on chip from the inputs to sigma/rgb:
+//   * layer 0 of both heads: the input atoms (128 rows x 32 fp32) are copied global -> shared by cp.async straight into
+//     the swizzled K-major operand image (the raw fp32 tile IS the tf32 "hi" operand; the loader warps only add the
+//     "lo" = x - trunc(x) image) and multiplied SS-mode into two TMEM accumulators (colour, sigma);
+//   * hidden layers 1..3: the epilogue warps read the accumulator (tcgen05.ld), add bias, ReLU, split hi/lo and write
+//     the result back to TENSOR MEMORY (tcgen05.st) where the next layer's MMAs take it as their A operand (TS-mode):
+//     no shared-memory round trip for activations, and the tensor core no longer competes for shared-memory bandwidth;
+//   * the weights do not fit next to the rings (224 KB as hi/lo tf32 images), so a tiny pack kernel writes them once per
+//     call as 16 KB chunks (64 x 32 hi + lo, swizzled) in the order the tile loop consumes them and the loader warps
+//     stream the chunks through a shared-memory ring with cp.async (L2-resident, 224 KB per tile);
+//   * the MMA warp follows a static software pipeline: the three hidden layers of tile t are interleaved with layer 0 of
+//     tile t+1 (double-buffered accumulators), so the tensor core works while the epilogue warps turn a layer around;
+//   * fp32-grade accuracy by 3xTF32 (hi*hi + lo*hi + hi*lo), as in mlp.cu.
+// The hidden activations are also written to HBM ([M,64] each) because the backward kernels read them.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace tnf {
+namespace {
+
+constexpr int kHThreads = 13 * 32;  // warps 0-3 loaders, 4-7 colour epilogue, 8-11 sigma epilogue, 12 MMA issuer
+constexpr int kChunkBytes = 16384;  // weight chunk: [hi 64 rows x 128 B][lo 64 rows x 128 B]
+constexpr int kAH = 4, kAL = 2, kWN = 6, kDist = 2;  // ring sizes (see the deadlock argument at `issue`)
+constexpr int kHid = 64;
+
+struct HeadsArgs {
+  const float* feats; long long ld_feats; int F;
+  const float* xc; long long ld_xc; int K0;
+  const uint8_t* wimg;
+  const float* bias_c[4]; const float* bias_s;
+  const float* head_c_w; const float* head_c_b; const float* head_s_w; const float* head_s_b;
+  float* h[4]; float* hs; float* rgb; float* sigma;
+  long long M; int n_tiles;
+};
+
+// ---- the static schedule ---------------------------------------------------------------------------------------------
+// Layer-0 work of a tile is n0 = kx + kf "items" (kx colour-input atoms, then kf feature atoms); the hidden layers are
+// three more units.  Units in issue order for a CTA with T tiles:
+//   prologue: L0(tile 0) items 0..n0-1
+//   tile t  : H1(t) | L0(t+1) items 0,1 | H2(t) | L0(t+1) items 2,3 | H3(t) | L0(t+1) items 4..n0-1     (no L0 after the last tile)
+struct Unit { int hidden; int tile; int q; };  // hidden: 0 = layer-0 item q of `tile`, else hidden layer index 1..3 of `tile`
+__device__ __forceinline__ int n_units(int T, int n0) { return T <= 0 ? 0 : n0 + (T - 1) * (3 + n0) + 3; }
+__device__ __forceinline__ Unit decode_unit(int u, int T, int n0) {
+  Unit x;
+  if (u < n0) { x.hidden = 0; x.tile = 0; x.q = u; return x; }
+  const int U = 3 + n0;
+  int v = u - n0;
+  int t = v / U, r = v - t * U;
+  if (t >= T - 1) { t = T - 1; r = v - t * U; x.hidden = r + 1; x.tile = t; x.q = 0; return x; }
+  x.tile = t;
+  x.q = 0;
+  if (r == 0) x.hidden = 1;
+  else if (r <= 2) { x.hidden = 0; x.tile = t + 1; x.q = r - 1; }
+  else if (r == 3) x.hidden = 2;
+  else if (r <= 5) { x.hidden = 0; x.tile = t + 1; x.q = r - 2; }
+  else if (r == 6) x.hidden = 3;
+  else { x.hidden = 0; x.tile = t + 1; x.q = r - 3; }
+  return x;
+}
+// chunk index inside the packed image (steady-state order: [W1a W1b][items 0,1][W2a W2b][items 2,3][W3a W3b][items 4..])
+__host__ __device__ __forceinline__ int chunk_of_item(int q) { return q < 2 ? 2 + q : (q < 4 ? 4 + q : 6 + q); }
+__host__ __device__ __forceinline__ int chunk_of_hidden(int i, int half) { return (i - 1) * 4 + half; }
+
+__global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t s_afull[kAL], s_alempty[kAL], s_ahempty[kAH], s_wfull[kWN], s_wempty[kWN];
+  __shared__ uint64_t s_tfull_c[2], s_tfull_s[2], s_dsempty[2], s_actfull;
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* ahi = smem;                               // kAH x 16 KB
+  uint8_t* alo = ahi + kAH * kAtomBytes;             // kAL x 16 KB
+  uint8_t* wring = alo + kAL * kAtomBytes;           // kWN x 16 KB
+  uint8_t* epi = wring + kWN * kChunkBytes;          // 8 x 4 KB warp transpose buffers
+  const int kx = (A.K0 + 31) >> 5, kf = (A.F + 31) >> 5, n0 = kx + kf;
+  const int T = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int NU = n_units(T, n0);
+
+  if (tid == 0) {
+    for (int i = 0; i < kAL; ++i) { mbar_init(&s_afull[i], 128); mbar_init(&s_alempty[i], 1); }
+    for (int i = 0; i < kAH; ++i) mbar_init(&s_ahempty[i], 1);
+    for (int i = 0; i < kWN; ++i) { mbar_init(&s_wfull[i], 128); mbar_init(&s_wempty[i], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_tfull_c[b], 1); mbar_init(&s_tfull_s[b], 1); mbar_init(&s_dsempty[b], 128); }
+    mbar_init(&s_actfull, 128);
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc(&s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = s_tmem;
+  // TMEM columns: colour accumulators 0/64, sigma accumulators 128/192, hidden activation hi 256, lo 320
+  const uint32_t tm_dc = tm, tm_ds = tm + 128, tm_ahi = tm + 256, tm_alo = tm + 320;
+
+  if (warp < 4) {
+    // ===== loaders: input atoms + weight chunks, kDist units ahead =====
+    // Deadlock-freedom of waiting for a free slot while issuing unit u+kDist: the slot's previous occupant must belong to
+    // a unit < u.  kDist+1 = 3 consecutive units hold at most 3 atoms (< kAH = 4) and at most 5 chunks (< kWN = 6).
+    int ia = 0, iw = 0;   // issue-side counters (atoms, chunks)
+    int ca = 0, cw = 0;   // completion-side counters
+    auto copy_chunk = [&](int chunk_idx, int slot) {
+      const uint8_t* src = A.wimg + (size_t)chunk_idx * kChunkBytes;
+      uint8_t* dst = wring + slot * kChunkBytes;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int off = (tid + 128 * i) * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + off)), "l"(src + off) : "memory");
+      }
+    };
+    auto issue = [&](int u) {
+      if (u < NU) {
+        const Unit x = decode_unit(u, T, n0);
+        if (x.hidden == 0) {
+          const int h = ia % kAH;
+          mbar_wait(&s_ahempty[h], ((ia / kAH) & 1) ^ 1);
+          const long long row0 = (long long)(blockIdx.x + x.tile * gridDim.x) * 128;
+          if (x.q < kx) cp_async_atom_swz(A.xc, A.ld_xc, row0, A.M, 32 * x.q, A.K0, tid, ahi + h * kAtomBytes, false);
+          else cp_async_atom_swz(A.feats, A.ld_feats, row0, A.M, 32 * (x.q - kx), A.F, tid, ahi + h * kAtomBytes, false);
+          ++ia;
+          const int w = iw % kWN;
+          mbar_wait(&s_wempty[w], ((iw / kWN) & 1) ^ 1);
+          copy_chunk(chunk_of_item(x.q), w);
+          ++iw;
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int w = iw % kWN;
+            mbar_wait(&s_wempty[w], ((iw / kWN) & 1) ^ 1);
+            copy_chunk(chunk_of_hidden(x.hidden, half), w);
+            ++iw;
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    for (int u = 0; u < kDist; ++u) issue(u);
+    for (int u = 0; u < NU; ++u) {
+      issue(u + kDist);
+      cp_async_wait<kDist>();
+      const Unit x = decode_unit(u, T, n0);
+      if (x.hidden == 0) {
+        const int l = ca % kAL;
+        mbar_wait(&s_alempty[l], ((ca / kAL) & 1) ^ 1);
+        make_lo_atom(ahi + (ca % kAH) * kAtomBytes, alo + l * kAtomBytes, tid, false, nullptr);
+        fence_async_smem();
+        mbar_arrive(&s_afull[l]);
+        mbar_arrive(&s_wfull[cw % kWN]);
+        ++ca;
+        ++cw;
+      } else {
+        fence_async_smem();
+        mbar_arrive(&s_wfull[cw % kWN]);
+        mbar_arrive(&s_wfull[(cw + 1) % kWN]);
+        cw += 2;
+      }
+    }
+    cp_async_wait<0>();
+  } else if (warp == 12) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = instr_desc(128, kHid, false, false);
+    int ca = 0, cw = 0, cact = 0;
+    for (int u = 0; u < NU; ++u) {
+      const Unit x = decode_unit(u, T, n0);
+      const int b = x.tile & 1;
+      if (x.hidden == 0) {
+        const int h = ca % kAH, l = ca % kAL, w = cw % kWN;
+        const bool colour = x.q < kx;
+        if (x.q == kx) mbar_wait(&s_dsempty[b], ((x.tile >> 1) & 1) ^ 1);  // sigma epilogue of tile-2 has drained Ds[b]
+        mbar_wait(&s_afull[l], (ca / kAL) & 1);
+        mbar_wait(&s_wfull[w], (cw / kWN) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_h = smem_u32(ahi + h * kAtomBytes), a_l = smem_u32(alo + l * kAtomBytes);
+          const uint32_t w_h = smem_u32(wring + w * kChunkBytes), w_l = w_h + kChunkBytes / 2;
+          const uint32_t d = (colour ? tm_dc : tm_ds) + b * kHid;
+          const bool first = (x.q == 0) || (x.q == kx);
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t aa = (pass == 1) ? a_l : a_h;
+            const uint32_t ww = (pass == 2) ? w_l : w_h;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) mma_tf32(d, desc_kmajor(aa, kk), desc_kmajor(ww, kk), idesc, !(first && pass == 0 && kk == 0));
+            if (pass == 1) mma_commit(&s_alempty[l]);
+          }
+          mma_commit(&s_ahempty[h]);
+          mma_commit(&s_wempty[w]);
+          if (x.q == kx - 1) mma_commit(&s_tfull_c[b]);
+          if (x.q == n0 - 1) mma_commit(&s_tfull_s[b]);
+        }
+        __syncwarp();
+        ++ca;
+        ++cw;
+      } else {
+        const int w0 = cw % kWN, w1 = (cw + 1) % kWN;
+        mbar_wait(&s_actfull, cact & 1);
+        mbar_wait(&s_wfull[w0], (cw / kWN) & 1);
+        mbar_wait(&s_wfull[w1], ((cw + 1) / kWN) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d = tm_dc + b * kHid;
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t aa = (pass == 1) ? tm_alo : tm_ahi;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t ww = smem_u32(wring + (half ? w1 : w0) * kChunkBytes) + (pass == 2 ? kChunkBytes / 2 : 0);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                mma_tf32_ts(d, aa + half * 32 + kk * 8, desc_kmajor(ww, kk), idesc, (pass | half | kk) != 0);
+            }
+          }
+          mma_commit(&s_wempty[w0]);
+          mma_commit(&s_wempty[w1]);
+          mma_commit(&s_tfull_c[b]);
+        }
+        __syncwarp();
+        cw += 2;
+        ++cact;
+      }
+    }
+  } else {
+    // ===== epilogue warps: 4-7 colour chain, 8-11 sigma head.  Warp w owns TMEM lanes 32*(w%4).. and tile rows likewise.
+    const int q4 = warp & 3;
+    const bool colour = warp < 8;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    uint8_t* wbuf = epi + (warp - 4) * 4096;      // 32 rows x 128 B, 16-byte chunks XOR row%8
+    const int lr = lane >> 3, c = lane & 7;       // coalesced mapping: rows lr + 4 i, 16-byte column chunk c
+    // store the warp's 32 rows x 32 columns (v = this thread's row) to dst[M, 64] columns c0..c0+31, coalesced
+    auto store_rows = [&](float* dst, long long row0, int c0, const float v[32]) {
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq)
+        *reinterpret_cast<float4*>(wbuf + lane * 128 + ((qq ^ (lane & 7)) << 4)) = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = lr + 4 * i;
+        const long long grow = row0 + q4 * 32 + rr;
+        if (grow < A.M)
+          *reinterpret_cast<float4*>(dst + grow * kHid + c0 + 4 * c) = *reinterpret_cast<const float4*>(wbuf + rr * 128 + ((c ^ (rr & 7)) << 4));
+      }
+      __syncwarp();
+    };
+    int ph[2] = {0, 0};
+    for (int tl = 0; tl < T; ++tl) {
+      const int b = tl & 1;
+      const long long row0 = (long long)(blockIdx.x + tl * gridDim.x) * 128;
+      const long long row = row0 + r;
+      if (colour) {
+        for (int layer = 0; layer < 4; ++layer) {
+          mbar_wait(&s_tfull_c[b], ph[b]);
+          ph[b] ^= 1;
+          tc_fence_after();
+          const float* bias = A.bias_c[layer];
+          float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int c0 = 0; c0 < kHid; c0 += 32) {
+            float v[32];
+            tmem_ld32(tm_dc + b * kHid + lane_off + c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(bias + c0 + i), 0.f);
+            if (A.h[layer]) store_rows(A.h[layer], row0, c0, v);
+            if (layer < 3) {
+              tmem_st32(tm_ahi + lane_off + c0, v);   // hi operand = the fp32 value itself (the tensor core truncates)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+              tmem_st32(tm_alo + lane_off + c0, v);
+            } else {
+#pragma unroll
+              for (int o = 0; o < 3; ++o)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[o] = __fmaf_rn(v[i], __ldg(A.head_c_w + o * kHid + c0 + i), acc[o]);
+            }
+          }
+          if (layer < 3) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&s_actfull);
+          } else if (row < A.M) {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) A.rgb[row * 3 + o] = 1.f / (1.f + expf(-(acc[o] + __ldg(A.head_c_b + o))));  // sigmoid
+          }
+        }
+      } else {
+        mbar_wait(&s_tfull_s[b], ph[b]);
+        ph[b] ^= 1;
+        tc_fence_after();
+        float acc = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHid; c0 += 32) {
+          float v[32];
+          tmem_ld32(tm_ds + b * kHid + lane_off + c0, v);
+          if (c0 + 32 >= kHid) { tc_fence_before(); mbar_arrive(&s_dsempty[b]); }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(A.bias_s + c0 + i), 0.f);
+          if (A.hs) store_rows(A.hs, row0, c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc = __fmaf_rn(v[i], __ldg(A.head_s_w + c0 + i), acc);
+        }
+        if (row < A.M) A.sigma[row] = expf(acc + __ldg(A.head_s_b) - 1.f);  // truncated_exp(x - 1.)
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tm, 512);
+}
+
+// ---- weight packing: nn.Linear weights -> 16 KB chunks (hi image, lo image; 64 rows x 128 B, 16-byte chunks XOR row%8) ----
+struct PackArgs {
+  const float* wc0; int K0;   // [64, K0]
+  const float* ws0; int F;    // [64, F]
+  const float* w123[3];       // [64, 64]
+  uint8_t* img;
+  int kx, kf;
+};
+__global__ void __launch_bounds__(256) pack_heads_kernel(const PackArgs P) {
+  const int n_chunks = 6 + P.kx + P.kf;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (chunk, row, 16-byte column chunk)
+  if (t >= n_chunks * 64 * 8) return;
+  const int chunk = t / 512, r = (t % 512) / 8, c = t % 8;
+  // which matrix / k-atom does this chunk hold?
+  const float* W = nullptr;
+  int ld = 0, K = 0, atom = 0;
+  const int blk = chunk / 4, pos = chunk % 4;       // blocks of [Wi a, Wi b, item, item] for the first two groups
+  if (chunk < 8) {
+    if (pos < 2) { W = P.w123[blk]; ld = K = kHid; atom = pos; }
+    else { const int q = blk * 2 + (pos - 2); if (q < P.kx) { W = P.wc0; ld = K = P.K0; atom = q; } else { W = P.ws0; ld = K = P.F; atom = q - P.kx; } }
+  } else if (chunk < 10) {
+    W = P.w123[2]; ld = K = kHid; atom = chunk - 8;
+  } else {
+    const int q = chunk - 6;
+    if (q < P.kx) { W = P.wc0; ld = K = P.K0; atom = q; } else { W = P.ws0; ld = K = P.F; atom = q - P.kx; }
+  }
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = atom * 32 + c * 4 + i;
+    v[i] = (k < K) ? __ldg(W + (long long)r * ld + k) : 0.f;
+  }
+  uint8_t* base = P.img + (size_t)chunk * kChunkBytes;
+  const int off = r * 128 + ((c ^ (r & 7)) << 4);
+  *reinterpret_cast<float4*>(base + off) = make_float4(v[0], v[1], v[2], v[3]);
+  float4 lo;
+  lo.x = v[0] - __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u);
+  lo.y = v[1] - __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u);
+  lo.z = v[2] - __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u);
+  lo.w = v[3] - __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u);
+  *reinterpret_cast<float4*>(base + kChunkBytes / 2 + off) = lo;
+}
+
+}  // namespace
+}  // namespace tnf
+
+extern "C" int64_t tnf_heads_workspace_bytes(int32_t feat_dim, int32_t k0) {
+  const int kx = (k0 + 31) / 32, kf = (feat_dim + 31) / 32;
+  return (int64_t)(6 + kx + kf) * tnf::kChunkBytes;
+}
+
+extern "C" int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_dim, const float* xc, int64_t ld_xc, int32_t k0,
+                             const float* const* color_w, const float* const* color_b, const float* const* sigma_w,
+                             const float* const* sigma_b, float* const* h_out, float* hs_out, float* rgb, float* sigma,
+                             int64_t m, void* workspace, void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(m >= 0, "negative m");
+  if (m == 0) return TNF_OK;
+  TNF_REQUIRE(feats && xc && color_w && color_b && sigma_w && sigma_b && rgb && sigma && workspace, "null pointer");
+  TNF_REQUIRE(feat_dim >= 1 && k0 >= 1, "bad widths");
+  const int kx = (k0 + 31) / 32, kf = (feat_dim + 31) / 32;
+  TNF_REQUIRE(kx + kf >= 4 && kx + kf <= 12, "unsupported input widths (k0=%d, feat_dim=%d)", k0, feat_dim);
+  TNF_REQUIRE(ld_feats % 4 == 0 && ld_xc % 4 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(xc) & 15u) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0,
+              "feats/xc/workspace must be 16-byte aligned with leading dimensions multiple of 4");
+  for (int i = 0; i < 5; ++i) TNF_REQUIRE(color_w[i] && color_b[i], "null colour layer %d", i);
+  for (int i = 0; i < 2; ++i) TNF_REQUIRE(sigma_w[i] && sigma_b[i], "null sigma layer %d", i);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PackArgs P{};
+  P.wc0 = color_w[0]; P.K0 = k0; P.ws0 = sigma_w[0]; P.F = feat_dim;
+  for (int i = 0; i < 3; ++i) P.w123[i] = color_w[1 + i];
+  P.img = static_cast<uint8_t*>(workspace); P.kx = kx; P.kf = kf;
+  const int pack_threads = (6 + kx + kf) * 512;
+  pack_heads_kernel<<<(pack_threads + 255) / 256, 256, 0, st>>>(P);
+  TNF_LAUNCH_CHECK("pack_heads_kernel");
+  HeadsArgs A{};
+  A.feats = feats; A.ld_feats = ld_feats; A.F = feat_dim; A.xc = xc; A.ld_xc = ld_xc; A.K0 = k0;
+  A.wimg = static_cast<const uint8_t*>(workspace);
+  for (int i = 0; i < 4; ++i) { A.bias_c[i] = color_b[i]; A.h[i] = h_out ? h_out[i] : nullptr; }
+  A.bias_s = sigma_b[0];
+  A.head_c_w = color_w[4]; A.head_c_b = color_b[4]; A.head_s_w = sigma_w[1]; A.head_s_b = sigma_b[1];
+  A.hs = hs_out; A.rgb = rgb; A.sigma = sigma; A.M = m;
+  A.n_tiles = (int)ceil_div(m, 128);
+  const size_t smem = (size_t)(kAH + kAL) * kAtomBytes + (size_t)kWN * kChunkBytes + 8 * 4096 + 1024;
+  static thread_local bool configured = false;
+  if (!configured) {
+    TNF_CUDA(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
+  heads_fwd_kernel<<<grid, kHThreads, smem, st>>>(A);
+  TNF_LAUNCH_CHECK("heads_fwd_kernel");
+  return TNF_OK;
+}

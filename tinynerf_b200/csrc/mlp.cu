@@ -21,198 +21,17 @@
 // one elected thread issues the MMAs, completion through tcgen05.commit -> mbarrier, accumulator read back
 // with tcgen05.ld (thread == TMEM lane == output row) for the fused bias / ReLU / head epilogue.
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace tnf {
 namespace {
-
-constexpr int kThreads = 128;
-constexpr int kAtomBytes = 128 * 128;        // 128 rows x 32 fp32
-constexpr int kMaxKAtoms = 5;                // K <= 160
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, int ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, int ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
-      "r"((uint32_t)accumulate)
-      : "memory");
-}
-// One lane of a converged warp, chosen by the hardware.  Unlike `lane == 0` the compiler keeps the code under it on the
-// uniform datapath (descriptors in uniform registers, no R2UR + waterfall loop per tcgen05.mma): measured 48 instead of
-// 147 cycles per 128x64x8 tf32 MMA (scripts/ubench/mma_bench.cu).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t p;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
-  return p != 0;
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 32-bit, 32 consecutive columns per thread (thread i of warp w reads TMEM lane 32*(w%4)+i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// ---- descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor, InstrDescriptor) -------------------
-// shared-memory matrix descriptor, version 1 (Blackwell); layout_type 2 = SWIZZLE_128B (16-byte chunks XOR row%8),
-// 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4) -- the only layout available to MN-major tf32 operands
-// (cutlass/gemm/collective/builders/sm100_common.inl:92).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46) | ((uint64_t)layout_type << 61);
-}
-// K-major operand: 8-row groups are 1024 B apart (SBO); LBO is ignored for swizzled K-major layouts.
-// k-step kk (8 tf32 = 32 B) advances the start address inside the 128-byte row.
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t atom_saddr, int kk) { return smem_desc(atom_saddr + kk * 32, 16, 1024); }
-// MN-major tf32 operand (SWIZZLE_128B_BASE32B): MN blocks of 32 elements are `lbo` bytes apart, 4-row K groups
-// 512 B apart (SBO); k-step kk (8 rows) advances the start address by 1024 bytes.
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t atom_saddr, int kk, uint32_t lbo = kAtomBytes) {
-  return smem_desc(atom_saddr + kk * 1024, lbo, 512, 1);
-}
-// instruction descriptor: D fp32, A/B tf32, dense
-__device__ __forceinline__ uint32_t instr_desc(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
-// ---- operand staging --------------------------------------------------------------------------------
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
-}
-// Operand staging is split in two so the global loads of the NEXT atom can be in flight (in registers) while the
-// tensor core works on the current one: load_atom_regs issues the 8 coalesced 128-bit loads of a thread,
-// store_atom_regs splits hi/lo and writes the swizzled shared-memory images.
-// Atom = rows [row0, row0+128) x cols [col0, col0+32) of a row-major matrix (leading dimension ld, `rows` x `cols`
-// valid, zero elsewhere).  Thread t covers 16-byte chunk t%8 of rows t/8 + 16 i.
-__device__ __forceinline__ void load_atom_regs(const float* __restrict__ g, long long ld, long long row0, long long rows,
-                                               int col0, int cols, int tid, float4 v[8], int atom_rows = 128) {
-  const int c = tid & 7;
-  const int r0 = tid >> 3;
-  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(g) & 15u) == 0);
-  const int col = col0 + 4 * c;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + 16 * i;
-    const long long row = row0 + r;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < atom_rows && row < rows && col < cols) {
-      const float* p = g + row * ld + col;
-      if (col + 3 < cols && vec) {
-        v[i] = __ldg(reinterpret_cast<const float4*>(p));
-      } else if (col + 3 < cols) {
-        v[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
-      } else {
-        v[i].x = __ldg(p);
-        if (col + 1 < cols) v[i].y = __ldg(p + 1);
-        if (col + 2 < cols) v[i].z = __ldg(p + 2);
-      }
-    }
-  }
-}
-// Asynchronous variant: the same per-thread 16-byte chunks are copied global -> shared with cp.async into a raw
-// ring slot (zero-filled outside the matrix), so several atoms per CTA are in flight without holding registers;
-// each thread later reads back exactly the chunks it copied (no cross-thread hazard), splits and writes the operand
-// images.  Requires 16-byte aligned rows (ld % 4 == 0, aligned base); otherwise callers use load_atom_regs.
-__device__ __forceinline__ void cp_async_atom(const float* __restrict__ g, long long ld, long long row0, long long rows,
-                                              int col0, int cols, int tid, uint8_t* raw) {
-  const int c = tid & 7;
-  const int r0 = tid >> 3;
-  const int col = col0 + 4 * c;
-  int nbytes = (cols - col) * 4;
-  nbytes = nbytes < 0 ? 0 : (nbytes > 16 ? 16 : nbytes);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + 16 * i;
-    const long long row = row0 + r;
-    const bool ok = row < rows && nbytes > 0;
-    const float* src = ok ? (g + row * ld + col) : g;
-    const uint32_t dst = smem_u32(raw + r * 128 + c * 16);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? nbytes : 0) : "memory");
-  }
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // pending in 0..3
-  if (pending <= 0) cp_async_wait<0>(); else if (pending == 1) cp_async_wait<1>(); else if (pending == 2) cp_async_wait<2>(); else cp_async_wait<3>();
-}
-__device__ __forceinline__ void read_raw_atom(const uint8_t* raw, int tid, float4 v[8]) {
-  const int c = tid & 7;
-  const int r0 = tid >> 3;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(raw + (r0 + 16 * i) * 128 + c * 16);
-}
-
-// mn32: SWIZZLE_128B_BASE32B image (32-byte chunks XOR row%4) for MN-major reads, else SWIZZLE_128B (16-byte
-// chunks XOR row%8) for K-major reads.
-__device__ __forceinline__ int swz_off(int r, int c, bool mn32) {
-  return mn32 ? (r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4))) : (r * 128 + ((c ^ (r & 7)) << 4));
-}
-__device__ __forceinline__ void store_atom_regs(const float4 v[8], uint8_t* hi_atom, uint8_t* lo_atom, int tid, bool mn32,
-                                                float colsum[4] /*optional column sums*/, int atom_rows = 128) {
-  const int c = tid & 7;
-  const int r0 = tid >> 3;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + 16 * i;
-    if (r >= atom_rows) break;
-    if (colsum) { colsum[0] += v[i].x; colsum[1] += v[i].y; colsum[2] += v[i].z; colsum[3] += v[i].w; }
-    float4 h, l;
-    split_tf32(v[i].x, h.x, l.x); split_tf32(v[i].y, h.y, l.y); split_tf32(v[i].z, h.z, l.z); split_tf32(v[i].w, h.w, l.w);
-    const int off = swz_off(r, c, mn32);
-    *reinterpret_cast<float4*>(hi_atom + off) = h;
-    *reinterpret_cast<float4*>(lo_atom + off) = l;
-  }
-}
-__device__ __forceinline__ void stage_atom(const float* __restrict__ g, long long ld, long long row0, long long rows,
-                                           int col0, int cols, uint8_t* hi_atom, uint8_t* lo_atom, int tid,
-                                           float colsum[4], int atom_rows = 128, bool mn32 = false) {
-  float4 v[8];
-  load_atom_regs(g, ld, row0, rows, col0, cols, tid, v, atom_rows);
-  store_atom_regs(v, hi_atom, lo_atom, tid, mn32, colsum, atom_rows);
-}
+// role timing (diagnostics): cycles spent waiting, accumulated per CTA into dbg[role*8 + slot] when set
+__device__ long long* g_dbg = nullptr;
+struct Tm {
+  long long t0;
+  __device__ __forceinline__ void start() { t0 = clock64(); }
+  __device__ __forceinline__ void stop(long long& acc) { acc += clock64() - t0; }
+};
 
 struct LinArgs {
   const float* X; long long ldx;   // fwd: input [M,K]        dgrad: dY [M,N]          wgrad: dY [M,N]
@@ -225,8 +44,8 @@ struct LinArgs {
   long long M; int N, K;
   int relu;
   int n_tiles;
-  int ring;        // operand stages of the warp-specialised kernels (2..4), chosen by the host from the smem budget
-  int raw;         // raw cp.async ring slots of the loaders (0 = register prefetch, else 2..kRawRing)
+  int ring;        // hi-image slots of the operand ring (16 KB each), chosen by the host from the smem budget
+  int raw;         // lo-image slots (16 KB each); ring - raw atoms of global loads are kept in flight
 };
 
 __device__ __forceinline__ float head_activation(float x, int act) {
@@ -236,26 +55,28 @@ __device__ __forceinline__ float head_activation(float x, int act) {
 }
 
 // ---- forward / dgrad: warp-specialised, persistent, one CTA per SM --------------------------------------------
-//   warps 0-3  loaders : LDG (one atom ahead in registers) -> hi/lo split -> swizzled STS into stage s -> full[s]
-//   warps 4-7  epilogue: tmem_full[b] -> tcgen05.ld (warp w owns TMEM lanes 32*(w%4)..) -> bias/ReLU/head ->
-//                        transpose through a private 16 KB buffer -> coalesced global stores -> tmem_empty[b]
-//   warp  8    MMA     : full[s] -> 12 x tcgen05.mma.kind::tf32 (3xTF32) -> tcgen05.commit -> empty[s]
+//   warps 0-3  loaders : cp.async global -> swizzled hi slot (the raw fp32 tile is the hi operand), several atoms in
+//                        flight; then lo = x - trunc(x) from the landed chunks -> lo slot -> full[l]
+//   warps 4-11 epilogue: tmem_full[b] -> tcgen05.ld (warp w owns TMEM lanes 32*(w%4)..; two warps per quarter split
+//                        the column chunks) -> bias/ReLU/head -> warp-private transpose -> coalesced stores -> tmem_empty[b]
+//   warp  12   MMA     : full[s] -> 12 x tcgen05.mma.kind::tf32 (3xTF32) -> tcgen05.commit -> empty[s]
 //                        (+ tmem_full[b] after the tile's last atom); accumulators double-buffered in TMEM
 // so HBM loads, tensor-core work and the epilogue of consecutive tiles overlap inside one CTA.
-constexpr int kWsThreads = 288;
+constexpr int kWsThreads = 416;   // 4 loader + 8 epilogue + 1 MMA warps
 constexpr int kMaxStages = 4;
-constexpr int kRawRing = 4;   // raw cp.async ring slots of the loaders (3 atoms = 48 KB of loads in flight per SM)
+constexpr int kRawRing = 4;   // wgrad: raw cp.async ring slots of the loaders
+constexpr int kMaxHi = 7;     // fwd/dgrad: hi slots (cp.async targets + MMA operands)
+constexpr int kMaxLo = 3;     // fwd/dgrad: lo slots
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// dynamic smem: [W hi atoms][W lo atoms][stage 0: A hi, A lo] ... [stage S-1][epilogue staging 16 KB], 1024-aligned
+// dynamic smem: [W hi atoms][W lo atoms][hi ring: H x 16 KB][lo ring: L x 16 KB][epilogue staging 16 KB], 1024-aligned
 template <int MODE>  // 0 fwd, 1 dgrad
 __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_tfull[2], s_tempty[2];
+  long long k_entry = 0;
+  if (g_dbg && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_entry)); if (blockIdx.x == 0) g_dbg[24] = k_entry; }
+  const long long c_entry = clock64();
+  __shared__ uint64_t s_full[kMaxLo], s_lempty[kMaxLo], s_hempty[kMaxHi], s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -266,20 +87,22 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
   const int w_atoms = (A.K + 31) >> 5;                    // weight image: N rows x K cols -> atoms along K
   const int w_rows = (A.N + 15) & ~15;
   const int w_stride = ((w_rows * 128) + 1023) & ~1023;
-  const int S = A.ring;                                   // operand stages
+  const int H = A.ring, L = A.raw;                        // hi / lo slots
   uint8_t* w_hi = smem;
   uint8_t* w_lo = smem + w_atoms * w_stride;
-  uint8_t* stages = smem + 2 * w_atoms * w_stride;        // stage s: hi at +s*2*kAtomBytes, lo right after
-  uint8_t* epi = stages + S * 2 * kAtomBytes;
+  uint8_t* hi_ring = smem + 2 * w_atoms * w_stride;
+  uint8_t* lo_ring = hi_ring + H * kAtomBytes;
+  uint8_t* epi = lo_ring + L * kAtomBytes;
   const int nd_cols = ND <= 32 ? 32 : (ND <= 64 ? 64 : (ND <= 128 ? 128 : 256));  // TMEM columns per accumulator
   const int tmem_cols = 2 * nd_cols;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_tfull[b], 1); mbar_init(&s_tempty[b], 128); }
+    for (int i = 0; i < L; ++i) { mbar_init(&s_full[i], 128); mbar_init(&s_lempty[i], 1); }
+    for (int i = 0; i < H; ++i) mbar_init(&s_hempty[i], 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_tfull[b], 1); mbar_init(&s_tempty[b], 256); }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(&s_tmem, tmem_cols);
+  if (warp == 12) tmem_alloc(&s_tmem, tmem_cols);
   if (tid < 128)
     for (int j = 0; j < w_atoms; ++j)
       stage_atom(A.W, A.K, 0, A.N, 32 * j, A.K, w_hi + j * w_stride, w_lo + j * w_stride, tid, nullptr, w_rows, MODE == 1);
@@ -293,52 +116,74 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
 
   if (warp < 4) {
     // ===== loaders =====
-    // Global loads run kRawRing-1 atoms ahead through a raw cp.async ring (16-byte aligned inputs), or one atom
-    // ahead in registers otherwise; then split hi/lo and write the swizzled operand stage.
-    float4 pre[8];
-    uint8_t* raw = epi + kAtomBytes;
-    const int nraw = A.raw;
-    const bool use_ring = nraw >= 2 && ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0);
-    auto issue = [&](int it) {
-      if (it < n_items) {
-        const int t = blockIdx.x + (it / ka) * gridDim.x, jj = it % ka;
-        cp_async_atom(A.X, A.ldx, (long long)t * 128, A.M, 32 * jj, KD, tid, raw + (it % nraw) * kAtomBytes);
+    const bool direct = ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0);
+    const int D = H - L;  // atoms of global loads in flight
+    auto src_row0 = [&](int it) { return (long long)(blockIdx.x + (it / ka) * gridDim.x) * 128; };
+    if (direct) {
+      long long w_h = 0, w_cp = 0, w_l = 0, w_lo = 0, w_tot = 0;
+      Tm tm, tt;
+      tt.start();
+      if (g_dbg && tid == 0 && blockIdx.x == 0) g_dbg[6] = tt.t0 - c_entry;  // cycles from kernel entry to role start
+      auto issue = [&](int it) {
+        if (it < n_items) {
+          const int h = it % H;
+          tm.start();
+          mbar_wait(&s_hempty[h], ((it / H) & 1) ^ 1);   // the MMAs that read the slot's previous atom have completed
+          tm.stop(w_h);
+          cp_async_atom_swz(A.X, A.ldx, src_row0(it), A.M, 32 * (it % ka), KD, tid, hi_ring + h * kAtomBytes, false);
+        }
+        cp_async_commit();  // (possibly empty) group: keeps the group count uniform
+      };
+      for (int it = 0; it < D; ++it) issue(it);
+      for (int it = 0; it < n_items; ++it) {
+        issue(it + D);
+        tm.start();
+        cp_async_wait_dyn(D);                            // this thread's chunks of item `it` have landed
+        tm.stop(w_cp);
+        const int l = it % L;
+        tm.start();
+        mbar_wait(&s_lempty[l], ((it / L) & 1) ^ 1);
+        tm.stop(w_l);
+        tm.start();
+        make_lo_atom(hi_ring + (it % H) * kAtomBytes, lo_ring + l * kAtomBytes, tid, false, nullptr);
+        fence_async_smem();
+        mbar_arrive(&s_full[l]);
+        tm.stop(w_lo);
       }
-      cp_async_commit();  // (possibly empty) group: keeps the group count uniform
-    };
-    if (use_ring) {
-      for (int it = 0; it < nraw - 1; ++it) issue(it);
-    } else if (n_items > 0) {
-      load_atom_regs(A.X, A.ldx, (long long)blockIdx.x * 128, A.M, 0, KD, tid, pre);
+      cp_async_wait<0>();
+      tt.stop(w_tot);
+      if (g_dbg && tid == 0 && blockIdx.x == 0) { g_dbg[0] = w_h; g_dbg[1] = w_cp; g_dbg[2] = w_l; g_dbg[3] = w_lo; g_dbg[4] = w_tot; g_dbg[5] = n_items; }
+    } else {
+      // unaligned rows: registers, one atom ahead
+      float4 pre[8];
+      if (n_items > 0) load_atom_regs(A.X, A.ldx, src_row0(0), A.M, 0, KD, tid, pre);
+      for (int it = 0; it < n_items; ++it) {
+        const int h = it % H, l = it % L;
+        mbar_wait(&s_hempty[h], ((it / H) & 1) ^ 1);
+        mbar_wait(&s_lempty[l], ((it / L) & 1) ^ 1);
+        store_atom_regs(pre, hi_ring + h * kAtomBytes, lo_ring + l * kAtomBytes, tid, false, nullptr);
+        if (it + 1 < n_items) load_atom_regs(A.X, A.ldx, src_row0(it + 1), A.M, 32 * ((it + 1) % ka), KD, tid, pre);
+        fence_async_smem();
+        mbar_arrive(&s_full[l]);
+      }
     }
-    for (int it = 0; it < n_items; ++it) {
-      const int s = it % S;
-      if (use_ring) {
-        issue(it + nraw - 1);            // reuses the slot read in the previous iteration (by this same thread)
-        cp_async_wait_dyn(nraw - 1);     // item `it` has landed
-        read_raw_atom(raw + (it % nraw) * kAtomBytes, tid, pre);
-      }
-      mbar_wait(&s_empty[s], ((it / S) & 1) ^ 1);   // the MMAs that read this stage have completed
-      uint8_t* a_hi = stages + s * 2 * kAtomBytes;
-      store_atom_regs(pre, a_hi, a_hi + kAtomBytes, tid, false, nullptr);
-      if (!use_ring && it + 1 < n_items) {
-        const int nt = blockIdx.x + ((it + 1) / ka) * gridDim.x, nj = (it + 1) % ka;
-        load_atom_regs(A.X, A.ldx, (long long)nt * 128, A.M, 32 * nj, KD, tid, pre);
-      }
-      fence_async_smem();
-      mbar_arrive(&s_full[s]);
-    }
-    cp_async_wait<0>();
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ===== MMA issuer =====
     const uint32_t idesc = instr_desc(128, ND, false, MODE == 1);
+    long long w_te = 0, w_f = 0, w_tot = 0;
+    Tm tm, tt;
+    tt.start();
     for (int it = 0; it < n_items; ++it) {
-      const int s = it % S, j = it % ka, tl = it / ka, b = tl & 1;
+      const int h = it % H, l = it % L, j = it % ka, tl = it / ka, b = tl & 1;
+      tm.start();
       if (j == 0) mbar_wait(&s_tempty[b], ((tl >> 1) & 1) ^ 1);   // epilogue has drained accumulator b
-      mbar_wait(&s_full[s], (it / S) & 1);
+      tm.stop(w_te);
+      tm.start();
+      mbar_wait(&s_full[l], (it / L) & 1);
+      tm.stop(w_f);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t ah = smem_u32(stages + s * 2 * kAtomBytes), al = ah + kAtomBytes;
+        const uint32_t ah = smem_u32(hi_ring + h * kAtomBytes), al = smem_u32(lo_ring + l * kAtomBytes);
         const uint32_t tmem_d = tmem_base + b * nd_cols;
 #pragma unroll 1
         for (int pass = 0; pass < 3; ++pass) {
@@ -351,35 +196,50 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
             else           bd = desc_mnmajor(smem_u32(wb) + j * 4096 /*32 rows of n_out*/, kk, w_stride);
             mma_tf32(tmem_d, desc_kmajor(aa, kk), bd, idesc, (j | pass | kk) != 0);
           }
+          if (pass == 1) mma_commit(&s_lempty[l]);   // the lo slot is free once the first two passes have read it
         }
-        mma_commit(&s_empty[s]);                 // stage reusable once these MMAs have read it
+        mma_commit(&s_hempty[h]);                  // hi slot reusable once all three passes have read it
         if (j == ka - 1) mma_commit(&s_tfull[b]);  // accumulator b complete
       }
       __syncwarp();
     }
+    tt.stop(w_tot);
+    if (g_dbg && lane == 0 && blockIdx.x == 0) { g_dbg[8] = w_te; g_dbg[9] = w_f; g_dbg[10] = w_tot; }
   } else {
-    // ===== epilogue (warps 4..7; warp w may touch TMEM lanes 32*(w%4) .. +31) =====
-    const int ew = warp - 4, et = tid - 128;
-    const int r = ew * 32 + lane;  // tile row owned by this thread
+    // ===== epilogue (warps 4..11).  Warp w may touch TMEM lanes 32*(w%4) .. +31: two warps share each lane quarter
+    // and split the 32-column chunks between them (group g takes chunks g, g+2, ...).  A chunk goes TMEM -> registers
+    // (thread == row) -> bias/ReLU/head -> warp-private 4 KB transpose buffer -> coalesced 128-byte row stores; only
+    // __syncwarp inside, one named barrier per tile when the fused head needs the two groups' partial sums.
+    const int ew = warp - 4, q4 = ew & 3, g = ew >> 2;
+    const int r = q4 * 32 + lane;                 // tile row owned by this thread in TMEM
+    uint8_t* wbuf = epi + ew * 4096;              // 32 rows x 128 B, 16-byte chunks XOR row%8
+    float* s_head = reinterpret_cast<float*>(epi + 8 * 4096);  // [2][128][4] partial head sums of group 1
+    const int lr = lane >> 3, c = lane & 7;       // coalesced mapping: rows lr + 4 i of the warp's 32, column chunk c
+    const int ncols = (MODE == 0) ? A.N : A.K;
+    const bool write_y = (MODE == 1) || (A.Y != nullptr);
+    const int n_chunks = (ND + 31) >> 5;
+    const bool split_head = (MODE == 0) && A.n_head > 0 && n_chunks > 1;
+    long long w_tf = 0, w_tot = 0;
+    Tm tm, tt;
+    tt.start();
     for (int tl = 0; tl < my_tiles; ++tl) {
       const int b = tl & 1;
       const long long row0 = (long long)(blockIdx.x + tl * gridDim.x) * 128;
-      const long long row = row0 + r;
+      tm.start();
       mbar_wait(&s_tfull[b], (tl >> 1) & 1);
+      tm.stop(w_tf);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + b * nd_cols + ((uint32_t)(ew * 32) << 16);
+      const uint32_t taddr = tmem_base + b * nd_cols + ((uint32_t)(q4 * 32) << 16);
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const bool write_y = (MODE == 1) || (A.Y != nullptr);
-      for (int c0 = 0; c0 < ND; c0 += 32) {
-        // coalesced-store mapping of this thread for the chunk: 16-byte column chunk c of rows et/8 + 16 i
-        const int c = et & 7;
+      bool released = false;
+      for (int ch = g; ch < n_chunks; ch += 2) {
+        const int c0 = ch * 32;
         const int col = c0 + 4 * c;
-        const int ncols = (MODE == 0) ? A.N : A.K;
         float4 xin[8];
         if (MODE == 1 && A.X2) {  // ReLU-backward mask source: issue the loads now, they land during the TMEM read
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const long long grow = row0 + (et >> 3) + 16 * i;
+            const long long grow = row0 + q4 * 32 + lr + 4 * i;
             xin[i] = make_float4(1.f, 1.f, 1.f, 1.f);
             if (grow < A.M && col < ncols) {
               const float* xp = A.X2 + grow * A.ldx2 + col;
@@ -395,7 +255,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
         }
         float v[32];
         tmem_ld32(taddr + c0, v);
-        if (c0 + 32 >= ND) { tc_fence_before(); mbar_arrive(&s_tempty[b]); }  // accumulator b fully read by this thread
+        if (ch + 2 >= n_chunks) { tc_fence_before(); mbar_arrive(&s_tempty[b]); released = true; }  // last read of accumulator b
         if (MODE == 0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -412,15 +272,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
         }
         if (write_y) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(epi + swz_off(r, q, false)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          epi_bar_sync();
+          for (int qq = 0; qq < 8; ++qq)
+            *reinterpret_cast<float4*>(wbuf + lane * 128 + ((qq ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
+          __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rr = (et >> 3) + 16 * i;
-            const long long grow = row0 + rr;
+            const int rr = lr + 4 * i;
+            const long long grow = row0 + q4 * 32 + rr;
             if (grow < A.M && col < ncols) {
-              float4 o = *reinterpret_cast<const float4*>(epi + swz_off(rr, c, false));
+              float4 o = *reinterpret_cast<const float4*>(wbuf + rr * 128 + ((c ^ (rr & 7)) << 4));
               if (MODE == 1 && A.X2) {  // ReLU backward of the layer that produced this layer's input
                 o.x = xin[i].x > 0.f ? o.x : 0.f; o.y = xin[i].y > 0.f ? o.y : 0.f;
                 o.z = xin[i].z > 0.f ? o.z : 0.f; o.w = xin[i].w > 0.f ? o.w : 0.f;
@@ -435,17 +296,41 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
               }
             }
           }
-          epi_bar_sync();
+          __syncwarp();
         }
       }
-      if (MODE == 0 && A.n_head > 0 && row < A.M)
-        for (int o = 0; o < A.n_head; ++o)
-          A.head_out[row * A.n_head + o] = head_activation(head_acc[o] + __ldg(A.head_b + o), A.head_act);
+      if (!released) { tc_fence_before(); mbar_arrive(&s_tempty[b]); }  // a group without chunks still releases
+      if (MODE == 0 && A.n_head > 0) {
+        const long long row = row0 + r;
+        if (split_head) {  // group 1 hands its partial sums to group 0 (double-buffered by tile parity)
+          float* hp = s_head + (b * 128 + r) * 4;
+          if (g == 1) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) hp[o] = head_acc[o];
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (g == 0) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) head_acc[o] += hp[o];
+          }
+        }
+        if (g == 0 && row < A.M)
+          for (int o = 0; o < A.n_head; ++o)
+            A.head_out[row * A.n_head + o] = head_activation(head_acc[o] + __ldg(A.head_b + o), A.head_act);
+      }
     }
+    tt.stop(w_tot);
+    if (g_dbg && tid == 128 && blockIdx.x == 0) { g_dbg[16] = w_tf; g_dbg[17] = w_tot; g_dbg[18] = my_tiles; }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+  if (g_dbg && threadIdx.x == 0) {
+    long long k_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_exit));
+    atomicMax((unsigned long long*)&g_dbg[25], (unsigned long long)k_exit);
+    atomicMin((unsigned long long*)&g_dbg[26], (unsigned long long)k_entry);
+  }
+  if (warp == 12) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 
@@ -721,30 +606,29 @@ int check_lin(long long M, int N, int K) {
 }
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// shared-memory plan of linear_kernel: weight images + S operand stages (32 KB each) + 16 KB epilogue staging +
-// raw cp.async ring (16 KB per slot).  Prefers a deep raw ring (loads in flight), then more operand stages.
-size_t plan_smem(int n, int k, int* stages, int* raw) {
+// shared-memory plan of linear_kernel: weight images + H hi slots + L lo slots (16 KB each) + 16 KB epilogue staging.
+// L = 3 lets the lo pass run two atoms ahead of the tensor core; every further hi slot is another atom of global loads
+// in flight (H - L of them, up to 4).
+size_t plan_smem(int n, int k, int* hi_slots, int* lo_slots) {
   const size_t w_stride = ((((size_t)(n + 15) & ~15) * 128) + 1023) & ~(size_t)1023;
-  const size_t fixed = 2 * ((k + 31) / 32) * w_stride + kAtomBytes + 1024;
+  const size_t fixed = 2 * ((k + 31) / 32) * w_stride + 9 * 4096 + 1024;  // + 8 warp transpose buffers + head partials
   const size_t budget = 226 * 1024;
-  for (int r : {kRawRing, 3, 2, 0}) {
-    const size_t f = fixed + (size_t)r * kAtomBytes;
-    if (f + 2 * 2 * kAtomBytes > budget) continue;
-    int s = (int)((budget - f) / (2 * kAtomBytes));
-    s = s > kMaxStages ? kMaxStages : s;
-    *stages = s;
-    *raw = r;
-    return f + (size_t)s * 2 * kAtomBytes;
-  }
-  *stages = 0;
-  *raw = 0;
-  return 0;
+  *hi_slots = *lo_slots = 0;
+  if (fixed + 3 * kAtomBytes > budget) return 0;
+  const int slots = (int)((budget - fixed) / kAtomBytes);
+  int lo = slots >= 6 ? kMaxLo : (slots >= 4 ? 2 : 1);
+  int hi = slots - lo;
+  if (hi > lo + 4) hi = lo + 4;
+  if (hi > kMaxHi) hi = kMaxHi;
+  *hi_slots = hi;
+  *lo_slots = lo;
+  return fixed + (size_t)(hi + lo) * kAtomBytes;
 }
 
 template <typename Kern>
 int launch_lin(Kern kern, LinArgs& A, cudaStream_t st, const char* name) {
   const size_t smem = plan_smem(A.N, A.K, &A.ring, &A.raw);
-  TNF_REQUIRE(A.ring >= 2, "layer too large for the shared-memory plan (n=%d, k=%d)", A.N, A.K);
+  TNF_REQUIRE(A.ring >= 2 && A.raw >= 1, "layer too large for the shared-memory plan (n=%d, k=%d)", A.N, A.K);
   static thread_local const void* configured[8] = {nullptr};
   bool done = false;
   for (auto c : configured) done |= (c == (const void*)kern);
@@ -760,6 +644,10 @@ int launch_lin(Kern kern, LinArgs& A, cudaStream_t st, const char* name) {
 
 }  // namespace
 }  // namespace tnf
+
+extern "C" int tnf_debug_role_timing(long long* buf) {  // diagnostics only (not part of the public header)
+  return cudaMemcpyToSymbol(tnf::g_dbg, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int tnf_linear_fwd(const float* x, int64_t ldx, const float* weight, const float* bias, float* y, int64_t ldy,
                               int64_t m, int32_t n, int32_t k, int32_t relu, const float* head_w, const float* head_b,

@@ -14,6 +14,7 @@ autograd path on the same batch.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List
 
 import torch
@@ -95,6 +96,16 @@ class FusedKPlanesStep:
                                       for r in self._res_planes for _ in range(2)], dtype=torch.float64, device=self.dev)
         self._cap_n = self._cap_r = 0
         self._ws: Dict[str, torch.Tensor] = {}
+        # both heads' forward in one kernel (tnf_heads_fwd) when the shapes are the reference's: hidden width 64,
+        # three hidden colour layers, one hidden density layer.  TNF_FUSED_HEADS=0 keeps the per-layer kernels.
+        self.fused_heads = (os.environ.get("TNF_FUSED_HEADS", "1") != "0" and len(self.col_lin) == 5
+                            and all(l.out_features == 64 for l in self.col_lin[:-1]) and self.sig_lin[0].out_features == 64)
+        if self.fused_heads:
+            tab = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+            self._cw, self._cb = tab([l.weight for l in self.col_lin]), tab([l.bias for l in self.col_lin])
+            self._sw, self._sb = tab([l.weight for l in self.sig_lin]), tab([l.bias for l in self.sig_lin])
+            nbytes = int(_lib.load().tnf_heads_workspace_bytes(self.feat, self.xc_width))
+            self._heads_ws = torch.empty(nbytes // 4, device=self.dev)
 
     def attach_grads(self) -> None:
         """p.grad = its view of the flat gradient buffer (undoes optimizer.zero_grad(set_to_none=True))."""
@@ -177,13 +188,23 @@ class FusedKPlanesStep:
             # ---- forward (src/core.py:225-267) ----
             call("tnf_kplanes_fwd", self._plane_ptrs, self._res_scales, self.n_scales, self.channels, P(packed), 7, n,
                  P(ws["feats"]), st, nbytes=n * (12 + 4 * F) + self._plane_bytes)
-            lin_fwd(P(ws["feats"]), F, sl[0], ws["hs"], head=sl[1], head_out=ws["sigma"], head_act=1)
+            if self.fused_heads:
+                call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, F, P(ws["xc"]), xld, n, st,
+                     nbytes=n * (12 + 4 * F + 4 * xld))
+                hptrs = (C.c_void_p * 4)(*[P(ws[f"h{i}"]) for i in range(4)])
+                mlp_flops = 2 * n * (64 * (F + 1) + 64 * xw + 3 * 64 * 64 + 3 * 64)
+                call("tnf_heads_fwd", P(ws["feats"]), F, F, P(ws["xc"]), xld, xw, self._cw, self._cb, self._sw, self._sb, hptrs,
+                     P(ws["hs"]), P(ws["rgb"]), P(ws["sigma"]), n, P(self._heads_ws), st,
+                     nbytes=4 * n * (F + xld + 5 * 64 + 4), flops=mlp_flops)
+            else:
+                lin_fwd(P(ws["feats"]), F, sl[0], ws["hs"], head=sl[1], head_out=ws["sigma"], head_act=1)
             call("tnf_weights_fwd", P(ws["sigma"]), P(steps), sstride, P(info), float(self.threshold), P(ws["w"]), n, r,
                  flags, _lib.ptr(status), st, nbytes=12 * n + 8 * r, extra_kernels=0 if flags else 3)
-            call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, F, P(ws["xc"]), xld, n, st,
-                 nbytes=n * (12 + 4 * F + 4 * xld))
+            if not self.fused_heads:
+                call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, F, P(ws["xc"]), xld, n, st,
+                     nbytes=n * (12 + 4 * F + 4 * xld))
             x, ldx = P(ws["xc"]), xld
-            for i in range(nh):
+            for i in range(0 if self.fused_heads else nh):
                 last = i == nh - 1
                 lin_fwd(x, ldx, cl[i], ws[f"h{i}"], head=cl[-1] if last else None,
                         head_out=ws["rgb"] if last else None, head_act=2 if last else 0)
