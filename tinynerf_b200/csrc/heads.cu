@@ -18,16 +18,32 @@
 //     tile t+1 (double-buffered accumulators), so the tensor core works while the epilogue warps turn a layer around;
 //   * fp32-grade accuracy by 3xTF32 (hi*hi + lo*hi + hi*lo), as in mlp.cu.
 // The hidden activations are also written to HBM ([M,64] each) because the backward kernels read them.
+#include <cuda.h>
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace tnf {
 namespace {
 
-constexpr int kHThreads = 13 * 32;  // warps 0-3 loaders, 4-7 colour epilogue, 8-11 sigma epilogue, 12 MMA issuer
+constexpr int kLoadWarps = 8;        // loader warps (input atoms: cp.async + lo image)
+constexpr int kLoadThreads = kLoadWarps * 32;
+constexpr int kMmaWarp = kLoadWarps + 8;
+constexpr int kTmaWarp = kLoadWarps + 9;
+constexpr int kHThreads = (kLoadWarps + 10) * 32;  // lo-pass warps | 4 colour epilogue | 4 sigma epilogue | MMA issuer | TMA producer
 constexpr int kChunkBytes = 16384;  // weight chunk: [hi 64 rows x 128 B][lo 64 rows x 128 B]
-constexpr int kAH = 4, kAL = 2, kWN = 6, kDist = 2;  // ring sizes (see the deadlock argument at `issue`)
+constexpr int kAH = 6, kAL = 2, kWN = 4;  // ring slots: input atoms (hi image, TMA target), lo images, weight chunks
 constexpr int kHid = 64;
+
+__device__ long long* g_hdbg = nullptr;   // diagnostics: wait cycles per role (CTA 0)
+#ifdef TNF_HEADS_TIMING
+#define HT0() long long _t0 = clock64()
+#define HT1(acc) acc += clock64() - _t0
+#define HCLK() clock64()
+#else
+#define HT0() do {} while (0)
+#define HT1(acc) do {} while (0)
+#define HCLK() 0LL
+#endif
 
 struct HeadsArgs {
   const float* feats; long long ld_feats; int F;
@@ -67,30 +83,35 @@ __device__ __forceinline__ Unit decode_unit(int u, int T, int n0) {
 __host__ __device__ __forceinline__ int chunk_of_item(int q) { return q < 2 ? 2 + q : (q < 4 ? 4 + q : 6 + q); }
 __host__ __device__ __forceinline__ int chunk_of_hidden(int i, int half) { return (i - 1) * 4 + half; }
 
-__global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs A) {
+__global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs A, const __grid_constant__ CUtensorMap tm_xc,
+                                                                 const __grid_constant__ CUtensorMap tm_feats) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t s_afull[kAL], s_alempty[kAL], s_ahempty[kAH], s_wfull[kWN], s_wempty[kWN];
+  __shared__ uint64_t s_afull[kAL], s_alempty[kAL], s_ahfull[kAH], s_ahempty[kAH], s_wfull[kWN], s_wempty[kWN];
   __shared__ uint64_t s_tfull_c[2], s_tfull_s[2], s_dsempty[2], s_actfull;
   __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_bias[5][kHid];    // colour layers 0..3, sigma layer 0
+  __shared__ __align__(16) float s_headw[4][kHid];   // colour head rows 0..2, sigma head
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 5 * kHid) s_bias[tid / kHid][tid % kHid] = __ldg((tid < 4 * kHid ? A.bias_c[tid / kHid] : A.bias_s) + tid % kHid);
+  if (tid < 4 * kHid) s_headw[tid / kHid][tid % kHid] = __ldg((tid < 3 * kHid ? A.head_c_w : A.head_s_w - 3 * kHid) + tid);
   uint8_t* ahi = smem;                               // kAH x 16 KB
   uint8_t* alo = ahi + kAH * kAtomBytes;             // kAL x 16 KB
   uint8_t* wring = alo + kAL * kAtomBytes;           // kWN x 16 KB
-  uint8_t* epi = wring + kWN * kChunkBytes;          // 8 x 4 KB warp transpose buffers
+  uint8_t* epi = wring + kWN * kChunkBytes;          // 8 x 2 KB warp transpose buffers
   const int kx = (A.K0 + 31) >> 5, kf = (A.F + 31) >> 5, n0 = kx + kf;
   const int T = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int NU = n_units(T, n0);
 
   if (tid == 0) {
-    for (int i = 0; i < kAL; ++i) { mbar_init(&s_afull[i], 128); mbar_init(&s_alempty[i], 1); }
-    for (int i = 0; i < kAH; ++i) mbar_init(&s_ahempty[i], 1);
-    for (int i = 0; i < kWN; ++i) { mbar_init(&s_wfull[i], 128); mbar_init(&s_wempty[i], 1); }
+    for (int i = 0; i < kAL; ++i) { mbar_init(&s_afull[i], kLoadThreads); mbar_init(&s_alempty[i], 1); }
+    for (int i = 0; i < kAH; ++i) { mbar_init(&s_ahfull[i], 1); mbar_init(&s_ahempty[i], 1); }
+    for (int i = 0; i < kWN; ++i) { mbar_init(&s_wfull[i], 1); mbar_init(&s_wempty[i], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&s_tfull_c[b], 1); mbar_init(&s_tfull_s[b], 1); mbar_init(&s_dsempty[b], 128); }
     mbar_init(&s_actfull, 128);
     fence_mbar_init();
   }
-  if (warp == 12) tmem_alloc(&s_tmem, 512);
+  if (warp == kMmaWarp) tmem_alloc(&s_tmem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -98,83 +119,64 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
   // TMEM columns: colour accumulators 0/64, sigma accumulators 128/192, hidden activation hi 256, lo 320
   const uint32_t tm_dc = tm, tm_ds = tm + 128, tm_ahi = tm + 256, tm_alo = tm + 320;
 
-  if (warp < 4) {
-    // ===== loaders: input atoms + weight chunks, kDist units ahead =====
-    // Deadlock-freedom of waiting for a free slot while issuing unit u+kDist: the slot's previous occupant must belong to
-    // a unit < u.  kDist+1 = 3 consecutive units hold at most 3 atoms (< kAH = 4) and at most 5 chunks (< kWN = 6).
-    int ia = 0, iw = 0;   // issue-side counters (atoms, chunks)
-    int ca = 0, cw = 0;   // completion-side counters
-    auto copy_chunk = [&](int chunk_idx, int slot) {
-      const uint8_t* src = A.wimg + (size_t)chunk_idx * kChunkBytes;
-      uint8_t* dst = wring + slot * kChunkBytes;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int off = (tid + 128 * i) * 16;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + off)), "l"(src + off) : "memory");
-      }
-    };
-    auto issue = [&](int u) {
-      if (u < NU) {
+  if (warp == kTmaWarp) {
+    // ===== TMA producer: one thread walks the unit sequence and keeps the rings full.  Input atoms are 2-D tensor-map
+    // loads (box 32 x 128 fp32, 128-byte swizzle = the K-major operand image; rows/columns outside the tensor arrive as
+    // zeros), weight chunks are 16 KB bulk copies.  No LSU work, and as many loads in flight as there are free slots.
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_xc);
+      tma_prefetch_desc(&tm_feats);
+      int ia = 0, iw = 0;
+      for (int u = 0; u < NU; ++u) {
         const Unit x = decode_unit(u, T, n0);
         if (x.hidden == 0) {
           const int h = ia % kAH;
           mbar_wait(&s_ahempty[h], ((ia / kAH) & 1) ^ 1);
-          const long long row0 = (long long)(blockIdx.x + x.tile * gridDim.x) * 128;
-          if (x.q < kx) cp_async_atom_swz(A.xc, A.ld_xc, row0, A.M, 32 * x.q, A.K0, tid, ahi + h * kAtomBytes, false);
-          else cp_async_atom_swz(A.feats, A.ld_feats, row0, A.M, 32 * (x.q - kx), A.F, tid, ahi + h * kAtomBytes, false);
+          const int row0 = (blockIdx.x + x.tile * gridDim.x) * 128;
+          mbar_expect_tx(&s_ahfull[h], kAtomBytes);
+          if (x.q < kx) tma_load_2d(ahi + h * kAtomBytes, &tm_xc, 32 * x.q, row0, &s_ahfull[h]);
+          else tma_load_2d(ahi + h * kAtomBytes, &tm_feats, 32 * (x.q - kx), row0, &s_ahfull[h]);
           ++ia;
+        }
+        const int n_chunks = x.hidden ? 2 : 1;
+        for (int half = 0; half < n_chunks; ++half) {
           const int w = iw % kWN;
           mbar_wait(&s_wempty[w], ((iw / kWN) & 1) ^ 1);
-          copy_chunk(chunk_of_item(x.q), w);
+          mbar_expect_tx(&s_wfull[w], kChunkBytes);
+          bulk_copy_g2s(wring + w * kChunkBytes, A.wimg + (size_t)(x.hidden ? chunk_of_hidden(x.hidden, half) : chunk_of_item(x.q)) * kChunkBytes,
+                        kChunkBytes, &s_wfull[w]);
           ++iw;
-        } else {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int w = iw % kWN;
-            mbar_wait(&s_wempty[w], ((iw / kWN) & 1) ^ 1);
-            copy_chunk(chunk_of_hidden(x.hidden, half), w);
-            ++iw;
-          }
         }
       }
-      cp_async_commit();
-    };
-    for (int u = 0; u < kDist; ++u) issue(u);
-    for (int u = 0; u < NU; ++u) {
-      issue(u + kDist);
-      cp_async_wait<kDist>();
-      const Unit x = decode_unit(u, T, n0);
-      if (x.hidden == 0) {
-        const int l = ca % kAL;
-        mbar_wait(&s_alempty[l], ((ca / kAL) & 1) ^ 1);
-        make_lo_atom(ahi + (ca % kAH) * kAtomBytes, alo + l * kAtomBytes, tid, false, nullptr);
-        fence_async_smem();
-        mbar_arrive(&s_afull[l]);
-        mbar_arrive(&s_wfull[cw % kWN]);
-        ++ca;
-        ++cw;
-      } else {
-        fence_async_smem();
-        mbar_arrive(&s_wfull[cw % kWN]);
-        mbar_arrive(&s_wfull[(cw + 1) % kWN]);
-        cw += 2;
-      }
     }
-    cp_async_wait<0>();
-  } else if (warp == 12) {
+  } else if (warp < kLoadWarps) {
+    // ===== lo-pass warps: for every input atom, lo = x - trunc(x) from the landed hi image into a lo slot =====
+    const int n_atoms = T * n0;
+    for (int ca = 0; ca < n_atoms; ++ca) {
+      const int h = ca % kAH, l = ca % kAL;
+      mbar_wait(&s_ahfull[h], (ca / kAH) & 1);
+      mbar_wait(&s_alempty[l], ((ca / kAL) & 1) ^ 1);
+      make_lo_atom<kLoadThreads>(ahi + h * kAtomBytes, alo + l * kAtomBytes, tid, false, nullptr);
+      fence_async_smem();
+      mbar_arrive(&s_afull[l]);
+    }
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer =====
     const uint32_t idesc = instr_desc(128, kHid, false, false);
     int ca = 0, cw = 0, cact = 0;
+    long long d_ds = 0, d_af = 0, d_wf = 0, d_act = 0, d_iss0 = 0, d_issh = 0;
+    const long long d_start = HCLK();
     for (int u = 0; u < NU; ++u) {
       const Unit x = decode_unit(u, T, n0);
       const int b = x.tile & 1;
       if (x.hidden == 0) {
         const int h = ca % kAH, l = ca % kAL, w = cw % kWN;
         const bool colour = x.q < kx;
-        if (x.q == kx) mbar_wait(&s_dsempty[b], ((x.tile >> 1) & 1) ^ 1);  // sigma epilogue of tile-2 has drained Ds[b]
-        mbar_wait(&s_afull[l], (ca / kAL) & 1);
-        mbar_wait(&s_wfull[w], (cw / kWN) & 1);
+        { HT0(); if (x.q == kx) mbar_wait(&s_dsempty[b], ((x.tile >> 1) & 1) ^ 1); HT1(d_ds); }  // sigma epilogue of tile-2 has drained Ds[b]
+        { HT0(); mbar_wait(&s_afull[l], (ca / kAL) & 1); HT1(d_af); }
+        { HT0(); mbar_wait(&s_wfull[w], (cw / kWN) & 1); HT1(d_wf); }
         tc_fence_after();
+        const long long _ti = HCLK();
         if (elect_one()) {
           const uint32_t a_h = smem_u32(ahi + h * kAtomBytes), a_l = smem_u32(alo + l * kAtomBytes);
           const uint32_t w_h = smem_u32(wring + w * kChunkBytes), w_l = w_h + kChunkBytes / 2;
@@ -194,14 +196,16 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
           if (x.q == n0 - 1) mma_commit(&s_tfull_s[b]);
         }
         __syncwarp();
+        d_iss0 += HCLK() - _ti;
         ++ca;
         ++cw;
       } else {
         const int w0 = cw % kWN, w1 = (cw + 1) % kWN;
-        mbar_wait(&s_actfull, cact & 1);
-        mbar_wait(&s_wfull[w0], (cw / kWN) & 1);
-        mbar_wait(&s_wfull[w1], ((cw + 1) / kWN) & 1);
+        { HT0(); mbar_wait(&s_actfull, cact & 1); HT1(d_act); }
+        { HT0(); mbar_wait(&s_wfull[w0], (cw / kWN) & 1);
+        mbar_wait(&s_wfull[w1], ((cw + 1) / kWN) & 1); HT1(d_wf); }
         tc_fence_after();
+        const long long _ti = HCLK();
         if (elect_one()) {
           const uint32_t d = tm_dc + b * kHid;
 #pragma unroll 1
@@ -220,75 +224,95 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
           mma_commit(&s_tfull_c[b]);
         }
         __syncwarp();
+        d_issh += HCLK() - _ti;
         cw += 2;
         ++cact;
       }
     }
+    if (g_hdbg && lane == 0 && blockIdx.x == 0) { g_hdbg[8] = d_ds; g_hdbg[9] = d_af; g_hdbg[10] = d_wf; g_hdbg[11] = d_act; g_hdbg[12] = d_iss0; g_hdbg[13] = d_issh; g_hdbg[14] = HCLK() - d_start; }
   } else {
     // ===== epilogue warps: 4-7 colour chain, 8-11 sigma head.  Warp w owns TMEM lanes 32*(w%4).. and tile rows likewise.
     const int q4 = warp & 3;
-    const bool colour = warp < 8;
+    const bool colour = warp < kLoadWarps + 4;
     const int r = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-    uint8_t* wbuf = epi + (warp - 4) * 4096;      // 32 rows x 128 B, 16-byte chunks XOR row%8
-    const int lr = lane >> 3, c = lane & 7;       // coalesced mapping: rows lr + 4 i, 16-byte column chunk c
-    // store the warp's 32 rows x 32 columns (v = this thread's row) to dst[M, 64] columns c0..c0+31, coalesced
+    uint8_t* wbuf = epi + (warp - kLoadWarps) * 2048;      // 32 rows x 64 B (16 columns), 16-byte chunks XOR (row>>1)&3
+    // store the warp's 32 rows x 32 columns (v = this thread's row) to dst[M, 64] columns c0..c0+31: two passes of 16
+    // columns through the warp-private buffer, written back as 64-byte row segments (8 rows per instruction)
     auto store_rows = [&](float* dst, long long row0, int c0, const float v[32]) {
+      const int rr0 = lane >> 2, cc = lane & 3;
 #pragma unroll
-      for (int qq = 0; qq < 8; ++qq)
-        *reinterpret_cast<float4*>(wbuf + lane * 128 + ((qq ^ (lane & 7)) << 4)) = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
-      __syncwarp();
+      for (int p = 0; p < 2; ++p) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = lr + 4 * i;
-        const long long grow = row0 + q4 * 32 + rr;
-        if (grow < A.M)
-          *reinterpret_cast<float4*>(dst + grow * kHid + c0 + 4 * c) = *reinterpret_cast<const float4*>(wbuf + rr * 128 + ((c ^ (rr & 7)) << 4));
+        for (int qq = 0; qq < 4; ++qq)
+          *reinterpret_cast<float4*>(wbuf + lane * 64 + ((qq ^ ((lane >> 1) & 3)) << 4)) =
+              make_float4(v[16 * p + 4 * qq], v[16 * p + 4 * qq + 1], v[16 * p + 4 * qq + 2], v[16 * p + 4 * qq + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = rr0 + 8 * i;
+          const long long grow = row0 + q4 * 32 + rr;
+          if (grow < A.M)
+            *reinterpret_cast<float4*>(dst + grow * kHid + c0 + 16 * p + 4 * cc) =
+                *reinterpret_cast<const float4*>(wbuf + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+        }
+        __syncwarp();
       }
-      __syncwarp();
     };
     int ph[2] = {0, 0};
+    long long d_wait = 0, e_ld = 0, e_bias = 0, e_store = 0, e_st = 0, e_head = 0;
+    const long long d_start = HCLK();
     for (int tl = 0; tl < T; ++tl) {
       const int b = tl & 1;
       const long long row0 = (long long)(blockIdx.x + tl * gridDim.x) * 128;
       const long long row = row0 + r;
       if (colour) {
         for (int layer = 0; layer < 4; ++layer) {
-          mbar_wait(&s_tfull_c[b], ph[b]);
+          { HT0(); mbar_wait(&s_tfull_c[b], ph[b]); HT1(d_wait); }
           ph[b] ^= 1;
           tc_fence_after();
-          const float* bias = A.bias_c[layer];
+          const float* bias = s_bias[layer];
           float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
           for (int c0 = 0; c0 < kHid; c0 += 32) {
             float v[32];
-            tmem_ld32(tm_dc + b * kHid + lane_off + c0, v);
+            { HT0(); tmem_ld32(tm_dc + b * kHid + lane_off + c0, v); HT1(e_ld); }
+            { HT0();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(bias + c0 + i), 0.f);
-            if (A.h[layer]) store_rows(A.h[layer], row0, c0, v);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + i);
+              v[i] = fmaxf(v[i] + bb.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + bb.y, 0.f);
+              v[i + 2] = fmaxf(v[i + 2] + bb.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + bb.w, 0.f);
+            }
+            HT1(e_bias); }
+            { HT0(); if (A.h[layer]) store_rows(A.h[layer], row0, c0, v); HT1(e_store); }
             if (layer < 3) {
+              HT0();
               tmem_st32(tm_ahi + lane_off + c0, v);   // hi operand = the fp32 value itself (the tensor core truncates)
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
               tmem_st32(tm_alo + lane_off + c0, v);
+              HT1(e_st);
             } else {
 #pragma unroll
               for (int o = 0; o < 3; ++o)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[o] = __fmaf_rn(v[i], __ldg(A.head_c_w + o * kHid + c0 + i), acc[o]);
+                for (int i = 0; i < 32; ++i) acc[o] = __fmaf_rn(v[i], s_headw[o][c0 + i], acc[o]);
             }
           }
           if (layer < 3) {
+            HT0();
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&s_actfull);
+            HT1(e_st);
           } else if (row < A.M) {
 #pragma unroll
             for (int o = 0; o < 3; ++o) A.rgb[row * 3 + o] = 1.f / (1.f + expf(-(acc[o] + __ldg(A.head_c_b + o))));  // sigmoid
           }
         }
       } else {
-        mbar_wait(&s_tfull_s[b], ph[b]);
+        { HT0(); mbar_wait(&s_tfull_s[b], ph[b]); HT1(d_wait); }
         ph[b] ^= 1;
         tc_fence_after();
         float acc = 0.f;
@@ -298,18 +322,20 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
           tmem_ld32(tm_ds + b * kHid + lane_off + c0, v);
           if (c0 + 32 >= kHid) { tc_fence_before(); mbar_arrive(&s_dsempty[b]); }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(A.bias_s + c0 + i), 0.f);
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + s_bias[4][c0 + i], 0.f);
           if (A.hs) store_rows(A.hs, row0, c0, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc = __fmaf_rn(v[i], __ldg(A.head_s_w + c0 + i), acc);
+          for (int i = 0; i < 32; ++i) acc = __fmaf_rn(v[i], s_headw[3][c0 + i], acc);
         }
         if (row < A.M) A.sigma[row] = expf(acc + __ldg(A.head_s_b) - 1.f);  // truncated_exp(x - 1.)
       }
     }
+    if (g_hdbg && blockIdx.x == 0 && lane == 0 && warp == kLoadWarps) { g_hdbg[24] = e_ld; g_hdbg[25] = e_bias; g_hdbg[26] = e_store; g_hdbg[27] = e_st; }
+    if (g_hdbg && blockIdx.x == 0 && lane == 0 && (warp == kLoadWarps || warp == kLoadWarps + 4)) { g_hdbg[warp == kLoadWarps ? 16 : 20] = d_wait; g_hdbg[warp == kLoadWarps ? 17 : 21] = HCLK() - d_start; }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tm, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tm, 512);
 }
 
 // ---- weight packing: nn.Linear weights -> 16 KB chunks (hi image, lo image; 64 rows x 128 B, 16-byte chunks XOR row%8) ----
@@ -358,6 +384,37 @@ __global__ void __launch_bounds__(256) pack_heads_kernel(const PackArgs P) {
 }  // namespace
 }  // namespace tnf
 
+extern "C" int tnf_debug_heads_timing(long long* buf) {  // diagnostics only
+  return cudaMemcpyToSymbol(tnf::g_hdbg, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
+
+namespace tnf {
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// row-major fp32 [rows, cols] with leading dimension ld -> tensor map with a 32 x 128 box in the 128-byte swizzle
+int make_atom_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  static EncodeTiledFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(fn);
+  }();
+  TNF_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TNF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TNF_OK;
+}
+}  // namespace
+}  // namespace tnf
+
 extern "C" int64_t tnf_heads_workspace_bytes(int32_t feat_dim, int32_t k0) {
   const int kx = (k0 + 31) / 32, kf = (feat_dim + 31) / 32;
   return (int64_t)(6 + kx + kf) * tnf::kChunkBytes;
@@ -395,14 +452,20 @@ extern "C" int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_
   A.head_c_w = color_w[4]; A.head_c_b = color_b[4]; A.head_s_w = sigma_w[1]; A.head_s_b = sigma_b[1];
   A.hs = hs_out; A.rgb = rgb; A.sigma = sigma; A.M = m;
   A.n_tiles = (int)ceil_div(m, 128);
-  const size_t smem = (size_t)(kAH + kAL) * kAtomBytes + (size_t)kWN * kChunkBytes + 8 * 4096 + 1024;
+  const size_t smem = (size_t)(kAH + kAL) * kAtomBytes + (size_t)kWN * kChunkBytes + 8 * 2048 + 1024;
   static thread_local bool configured = false;
   if (!configured) {
     TNF_CUDA(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  TNF_REQUIRE(m < (1LL << 31) - 256, "too many rows for the tensor-map coordinates");
+  CUtensorMap tm_xc, tm_feats;
+  int rc = make_atom_map(&tm_xc, xc, m, k0, ld_xc);
+  if (rc != TNF_OK) return rc;
+  rc = make_atom_map(&tm_feats, feats, m, feat_dim, ld_feats);
+  if (rc != TNF_OK) return rc;
   const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
-  heads_fwd_kernel<<<grid, kHThreads, smem, st>>>(A);
+  heads_fwd_kernel<<<grid, kHThreads, smem, st>>>(A, tm_xc, tm_feats);
   TNF_LAUNCH_CHECK("heads_fwd_kernel");
   return TNF_OK;
 }

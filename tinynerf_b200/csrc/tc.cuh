@@ -164,6 +164,7 @@ __device__ __forceinline__ void cp_async_atom(const float* __restrict__ g, long 
 // Same copy, but straight into an operand image: chunk (r, c) lands at its swizzled position.  The raw fp32 tile IS the
 // "hi" operand (kind::tf32 ignores the low 13 mantissa bits), so the global->shared copy needs no register pass at all;
 // only the "lo" image (x - trunc(x)) is computed by the loader threads, each from the chunks it copied itself.
+template <int NT = 128>  // NT loader threads share the atom: thread t covers chunk t%8 of rows t/8 + (NT/8) i
 __device__ __forceinline__ void cp_async_atom_swz(const float* __restrict__ g, long long ld, long long row0, long long rows,
                                                   int col0, int cols, int tid, uint8_t* img, bool mn32) {
   const int c = tid & 7;
@@ -172,8 +173,8 @@ __device__ __forceinline__ void cp_async_atom_swz(const float* __restrict__ g, l
   int nbytes = (cols - col) * 4;
   nbytes = nbytes < 0 ? 0 : (nbytes > 16 ? 16 : nbytes);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + 16 * i;
+  for (int i = 0; i < 1024 / NT; ++i) {
+    const int r = r0 + (NT / 8) * i;
     const long long row = row0 + r;
     const bool ok = row < rows && nbytes > 0;
     const float* src = ok ? (g + row * ld + col) : g;
@@ -189,12 +190,13 @@ __device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // pending in 
   else if (pending == 3) cp_async_wait<3>(); else cp_async_wait<4>();
 }
 // lo image of an atom from its hi image: every thread handles the 8 chunks it copied itself (no cross-thread hazard)
+template <int NT = 128>
 __device__ __forceinline__ void make_lo_atom(const uint8_t* hi_img, uint8_t* lo_img, int tid, bool mn32, float colsum[4]) {
   const int c = tid & 7;
   const int r0 = tid >> 3;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + 16 * i;
+  for (int i = 0; i < 1024 / NT; ++i) {
+    const int r = r0 + (NT / 8) * i;
     const int off = mn32 ? (r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4))) : (r * 128 + ((c ^ (r & 7)) << 4));
     const float4 v = *reinterpret_cast<const float4*>(hi_img + off);
     if (colsum) { colsum[0] += v.x; colsum[1] += v.y; colsum[2] += v.z; colsum[3] += v.w; }
@@ -245,6 +247,26 @@ __device__ __forceinline__ void stage_atom(const float* __restrict__ g, long lon
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// TMA bulk copy global -> shared (no LSU work: one instruction per block), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 2-D TMA tile load (tensor map in kernel parameter space): box lands in shared memory in the map's swizzle, rows/cols
+// outside the tensor are zero-filled; completion counted in bytes on the mbarrier.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 // A operand from TMEM (lane == row, 32-bit column == k): D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
