@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
   uint8_t* ahi = smem;                               // kAH x 16 KB
   uint8_t* alo = ahi + kAH * kAtomBytes;             // kAL x 16 KB
   uint8_t* wring = alo + kAL * kAtomBytes;           // kWN x 16 KB
-  uint8_t* epi = wring + kWN * kChunkBytes;          // 8 x 2 KB warp transpose buffers
+  uint8_t* epi = wring + kWN * kChunkBytes;          // 8 x 2 KB warp transpose buffers + 4 KB head partial sums
   const int kx = (A.K0 + 31) >> 5, kf = (A.F + 31) >> 5, n0 = kx + kf;
   const int T = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int NU = n_units(T, n0);
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
     for (int i = 0; i < kAL; ++i) { mbar_init(&s_afull[i], kLoadThreads); mbar_init(&s_alempty[i], 1); }
     for (int i = 0; i < kAH; ++i) { mbar_init(&s_ahfull[i], 1); mbar_init(&s_ahempty[i], 1); }
     for (int i = 0; i < kWN; ++i) { mbar_init(&s_wfull[i], 1); mbar_init(&s_wempty[i], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_tfull_c[b], 1); mbar_init(&s_tfull_s[b], 1); mbar_init(&s_dsempty[b], 128); }
-    mbar_init(&s_actfull, 128);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_tfull_c[b], 1); mbar_init(&s_tfull_s[b], 1); mbar_init(&s_dsempty[b], 256); }
+    mbar_init(&s_actfull, 256);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&s_tmem, 512);
@@ -231,15 +231,19 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
     }
     if (g_hdbg && lane == 0 && blockIdx.x == 0) { g_hdbg[8] = d_ds; g_hdbg[9] = d_af; g_hdbg[10] = d_wf; g_hdbg[11] = d_act; g_hdbg[12] = d_iss0; g_hdbg[13] = d_issh; g_hdbg[14] = HCLK() - d_start; }
   } else {
-    // ===== epilogue warps: 4-7 colour chain, 8-11 sigma head.  Warp w owns TMEM lanes 32*(w%4).. and tile rows likewise.
-    const int q4 = warp & 3;
-    const bool colour = warp < kLoadWarps + 4;
+    // ===== epilogue warps (8): warp w owns TMEM lanes 32*(w%4).. (tile rows likewise); the two warps of a lane quarter
+    // split the 64 output columns (group g = columns 32g..32g+31).  Every warp serves both chains: the four colour
+    // stages of a tile (the critical path: each stage turns one layer's accumulator into the next layer's TMEM operand)
+    // and the tile's sigma stage, slotted in after colour layer 0.
+    const int ew = warp - kLoadWarps, q4 = ew & 3, g = ew >> 2;
     const int r = q4 * 32 + lane;
+    const int c0 = 32 * g;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-    uint8_t* wbuf = epi + (warp - kLoadWarps) * 2048;      // 32 rows x 64 B (16 columns), 16-byte chunks XOR (row>>1)&3
+    uint8_t* wbuf = epi + ew * 2048;              // 32 rows x 64 B (16 columns), 16-byte chunks XOR (row>>1)&3
+    float* s_part = reinterpret_cast<float*>(epi + 8 * 2048);   // [2 parity][128 rows][4]: head partial sums of group 1
     // store the warp's 32 rows x 32 columns (v = this thread's row) to dst[M, 64] columns c0..c0+31: two passes of 16
     // columns through the warp-private buffer, written back as 64-byte row segments (8 rows per instruction)
-    auto store_rows = [&](float* dst, long long row0, int c0, const float v[32]) {
+    auto store_rows = [&](float* dst, long long row0, const float v[32]) {
       const int rr0 = lane >> 2, cc = lane & 3;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
@@ -259,79 +263,75 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
         __syncwarp();
       }
     };
-    int ph[2] = {0, 0};
-    long long d_wait = 0, e_ld = 0, e_bias = 0, e_store = 0, e_st = 0, e_head = 0;
-    const long long d_start = HCLK();
+    // accumulator chunk -> relu(acc + bias) in registers
+    auto load_act = [&](uint32_t taddr, const float* bias, float v[32]) {
+      tmem_ld32(taddr + lane_off + c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + i);
+        v[i] = fmaxf(v[i] + bb.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + bb.y, 0.f);
+        v[i + 2] = fmaxf(v[i + 2] + bb.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + bb.w, 0.f);
+      }
+    };
+    int phc[2] = {0, 0}, phs[2] = {0, 0};
+    int n_sync = 0;   // named-barrier uses so far (parity of the partial-sum buffer)
     for (int tl = 0; tl < T; ++tl) {
       const int b = tl & 1;
       const long long row0 = (long long)(blockIdx.x + tl * gridDim.x) * 128;
       const long long row = row0 + r;
-      if (colour) {
-        for (int layer = 0; layer < 4; ++layer) {
-          { HT0(); mbar_wait(&s_tfull_c[b], ph[b]); HT1(d_wait); }
-          ph[b] ^= 1;
-          tc_fence_after();
-          const float* bias = s_bias[layer];
-          float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int c0 = 0; c0 < kHid; c0 += 32) {
-            float v[32];
-            { HT0(); tmem_ld32(tm_dc + b * kHid + lane_off + c0, v); HT1(e_ld); }
-            { HT0();
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + i);
-              v[i] = fmaxf(v[i] + bb.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + bb.y, 0.f);
-              v[i + 2] = fmaxf(v[i + 2] + bb.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + bb.w, 0.f);
-            }
-            HT1(e_bias); }
-            { HT0(); if (A.h[layer]) store_rows(A.h[layer], row0, c0, v); HT1(e_store); }
-            if (layer < 3) {
-              HT0();
-              tmem_st32(tm_ahi + lane_off + c0, v);   // hi operand = the fp32 value itself (the tensor core truncates)
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
-              tmem_st32(tm_alo + lane_off + c0, v);
-              HT1(e_st);
-            } else {
-#pragma unroll
-              for (int o = 0; o < 3; ++o)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) acc[o] = __fmaf_rn(v[i], s_headw[o][c0 + i], acc[o]);
-            }
-          }
-          if (layer < 3) {
-            HT0();
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&s_actfull);
-            HT1(e_st);
-          } else if (row < A.M) {
-#pragma unroll
-            for (int o = 0; o < 3; ++o) A.rgb[row * 3 + o] = 1.f / (1.f + expf(-(acc[o] + __ldg(A.head_c_b + o))));  // sigmoid
-          }
-        }
-      } else {
-        { HT0(); mbar_wait(&s_tfull_s[b], ph[b]); HT1(d_wait); }
-        ph[b] ^= 1;
+      for (int layer = 0; layer < 4; ++layer) {
+        mbar_wait(&s_tfull_c[b], phc[b]);
+        phc[b] ^= 1;
         tc_fence_after();
-        float acc = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kHid; c0 += 32) {
-          float v[32];
-          tmem_ld32(tm_ds + b * kHid + lane_off + c0, v);
-          if (c0 + 32 >= kHid) { tc_fence_before(); mbar_arrive(&s_dsempty[b]); }
+        float v[32];
+        load_act(tm_dc + b * kHid, s_bias[layer], v);
+        if (layer < 3) {
+          tmem_st32(tm_ahi + lane_off + c0, v);   // hi operand = the fp32 value itself (the tensor core truncates)
+          float lo[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + s_bias[4][c0 + i], 0.f);
-          if (A.hs) store_rows(A.hs, row0, c0, v);
+          for (int i = 0; i < 32; ++i) lo[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+          tmem_st32(tm_alo + lane_off + c0, lo);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&s_actfull);                // the next layer's MMAs may start; the HBM copy follows off the chain
+          if (A.h[layer]) store_rows(A.h[layer], row0, v);
+        } else {
+          if (A.h[layer]) store_rows(A.h[layer], row0, v);
+          float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc = __fmaf_rn(v[i], s_headw[3][c0 + i], acc);
+          for (int o = 0; o < 3; ++o)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[o] = __fmaf_rn(v[i], s_headw[o][c0 + i], acc[o]);
+          float* part = s_part + ((n_sync & 1) * 128 + r) * 4;
+          if (g == 1) { part[0] = acc[0]; part[1] = acc[1]; part[2] = acc[2]; }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          ++n_sync;
+          if (g == 0 && row < A.M) {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) A.rgb[row * 3 + o] = 1.f / (1.f + expf(-(acc[o] + part[o] + __ldg(A.head_c_b + o))));  // sigmoid
+          }
         }
-        if (row < A.M) A.sigma[row] = expf(acc + __ldg(A.head_s_b) - 1.f);  // truncated_exp(x - 1.)
+        if (layer == 0) {
+          // the tile's density head (its accumulator completes right after colour layer 0's)
+          mbar_wait(&s_tfull_s[b], phs[b]);
+          phs[b] ^= 1;
+          tc_fence_after();
+          float u[32];
+          load_act(tm_ds + b * kHid, s_bias[4], u);
+          tc_fence_before();
+          mbar_arrive(&s_dsempty[b]);
+          if (A.hs) store_rows(A.hs, row0, u);
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc = __fmaf_rn(u[i], s_headw[3][c0 + i], acc);
+          float* part = s_part + ((n_sync & 1) * 128 + r) * 4;
+          if (g == 1) part[0] = acc;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          ++n_sync;
+          if (g == 0 && row < A.M) A.sigma[row] = expf(acc + part[0] + __ldg(A.head_s_b) - 1.f);  // truncated_exp(x - 1.)
+        }
       }
     }
-    if (g_hdbg && blockIdx.x == 0 && lane == 0 && warp == kLoadWarps) { g_hdbg[24] = e_ld; g_hdbg[25] = e_bias; g_hdbg[26] = e_store; g_hdbg[27] = e_st; }
-    if (g_hdbg && blockIdx.x == 0 && lane == 0 && (warp == kLoadWarps || warp == kLoadWarps + 4)) { g_hdbg[warp == kLoadWarps ? 16 : 20] = d_wait; g_hdbg[warp == kLoadWarps ? 17 : 21] = HCLK() - d_start; }
   }
   tc_fence_before();
   __syncthreads();
@@ -452,7 +452,7 @@ extern "C" int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_
   A.head_c_w = color_w[4]; A.head_c_b = color_b[4]; A.head_s_w = sigma_w[1]; A.head_s_b = sigma_b[1];
   A.hs = hs_out; A.rgb = rgb; A.sigma = sigma; A.M = m;
   A.n_tiles = (int)ceil_div(m, 128);
-  const size_t smem = (size_t)(kAH + kAL) * kAtomBytes + (size_t)kWN * kChunkBytes + 8 * 2048 + 1024;
+  const size_t smem = (size_t)(kAH + kAL) * kAtomBytes + (size_t)kWN * kChunkBytes + 8 * 2048 + 4096 + 1024;
   static thread_local bool configured = false;
   if (!configured) {
     TNF_CUDA(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -27,10 +27,15 @@ namespace tnf {
 namespace {
 // role timing (diagnostics): cycles spent waiting, accumulated per CTA into dbg[role*8 + slot] when set
 __device__ long long* g_dbg = nullptr;
+#ifdef TNF_ROLE_TIMING
+#define TNF_CLK() clock64()
+#else
+#define TNF_CLK() 0LL
+#endif
 struct Tm {
   long long t0;
-  __device__ __forceinline__ void start() { t0 = clock64(); }
-  __device__ __forceinline__ void stop(long long& acc) { acc += clock64() - t0; }
+  __device__ __forceinline__ void start() { t0 = TNF_CLK(); }
+  __device__ __forceinline__ void stop(long long& acc) { acc += TNF_CLK() - t0; }
 };
 
 struct LinArgs {
@@ -74,8 +79,10 @@ template <int MODE>  // 0 fwd, 1 dgrad
 __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   long long k_entry = 0;
+#ifdef TNF_ROLE_TIMING
   if (g_dbg && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_entry)); if (blockIdx.x == 0) g_dbg[24] = k_entry; }
-  const long long c_entry = clock64();
+#endif
+  const long long c_entry = TNF_CLK();
   __shared__ uint64_t s_full[kMaxLo], s_lempty[kMaxLo], s_hempty[kMaxHi], s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -324,47 +331,58 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_kernel(const LinArgs A) 
   }
   tc_fence_before();
   __syncthreads();
+#ifdef TNF_ROLE_TIMING
   if (g_dbg && threadIdx.x == 0) {
     long long k_exit;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_exit));
     atomicMax((unsigned long long*)&g_dbg[25], (unsigned long long)k_exit);
     atomicMin((unsigned long long*)&g_dbg[26], (unsigned long long)k_entry);
   }
+#endif
   if (warp == 12) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 
 // wgrad: dW[n,k] += sum_m dY[m,n] X[m,k] ; db[n] += sum_m dY[m,n].  Warp-specialised like linear_kernel:
-//   warps 0-3 loaders: per 128-sample tile stage the dY atoms (one resident set) and then the X atoms (ring of
-//                      stages), global loads running ahead through the raw cp.async ring; column sums of dY
-//                      accumulate in registers for the bias gradient
-//   warp  4   MMA    : per X atom j: D[N_out, 32j..32j+32) += dY^T X_j, 16 k-steps x 3 (3xTF32), both operands
+//   warps 0-7 loaders: per 128-sample tile the dY atoms (into one of TWO resident sets, so the next tile's dY is staged
+//                      while the tensor core still reads this tile's) and then the X atoms (ring), all copied by
+//                      cp.async straight into the MN-major operand images (SWIZZLE_128B_BASE32B), a few atoms in
+//                      flight; the loaders add the lo images and the column sums of dY (bias gradient)
+//   warp  8   MMA    : per X atom j: D[N_out, 32j..32j+32) += dY^T X_j, 16 k-steps x 3 (3xTF32), both operands
 //                      MN-major; D lives in TMEM for the whole kernel and is flushed with atomics once per CTA.
-constexpr int kWgThreads = 160;
+constexpr int kWgLoadWarps = 8;
+constexpr int kWgLoadThreads = kWgLoadWarps * 32;
+constexpr int kWgThreads = kWgLoadThreads + 32;
+constexpr int kWgDist = 2;   // atoms of global loads in flight
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t s_xfull[kMaxStages], s_xempty[kMaxStages], s_yfull, s_yempty, s_done;
+  __shared__ uint64_t s_xfull[kMaxStages], s_xempty[kMaxStages], s_yfull[2], s_yempty[2], s_done;
   __shared__ uint32_t s_tmem;
   __shared__ float s_db[128];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ny = (A.N + 31) >> 5;   // dY atoms (N_out / 32)
   const int kx = (A.K + 31) >> 5;   // X atoms
-  const int S = A.ring, nraw = A.raw;
-  uint8_t* y_hi = smem;
-  uint8_t* y_lo = smem + ny * kAtomBytes;
-  uint8_t* xst = smem + 2 * ny * kAtomBytes;      // X stage s: hi at +s*2*kAtomBytes, lo right after
-  uint8_t* raw = xst + S * 2 * kAtomBytes;
-  const int MM = (A.N <= 64) ? 64 : 128;          // UMMA M = N_out
-  const int ncol = kx * 32;
-  const int tmem_cols = ncol <= 32 ? 32 : (ncol <= 64 ? 64 : (ncol <= 128 ? 128 : 256));
+  const int S = A.ring;             // X stages (hi + lo image each)
+  const int n_sets = A.raw;         // resident dY sets (2 when they fit, else 1)
+  const int set_bytes = 2 * ny * kAtomBytes;      // [hi atoms][lo atoms]
+  uint8_t* ysets = smem;
+  uint8_t* xst = smem + n_sets * set_bytes;       // X stage s: hi at +s*2*kAtomBytes, lo right after
+  // N_out == 64: ONE MMA per k-step computes all four hi/lo products: A = [dY_hi ; dY_lo] (M = 128: the set's four
+  // atoms are consecutive MN blocks), B = [X_hi | X_lo] (N = 64: the stage's two images are consecutive MN blocks).
+  // D quadrants (lanes n / n+64, columns c / c+32 of the atom's 64) are summed when the accumulator is flushed.
+  const bool stacked = (A.N == 64);
+  const int MM = stacked ? 128 : ((A.N <= 64) ? 64 : 128);   // UMMA M
+  const int ncol = kx * (stacked ? 64 : 32);
+  const int tmem_cols = ncol <= 32 ? 32 : (ncol <= 64 ? 64 : (ncol <= 128 ? 128 : (ncol <= 256 ? 256 : 512)));
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&s_xfull[s], 128); mbar_init(&s_xempty[s], 1); }
-    mbar_init(&s_yfull, 128 * ny); mbar_init(&s_yempty, 1); mbar_init(&s_done, 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&s_xfull[s], kWgLoadThreads); mbar_init(&s_xempty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_yfull[i], kWgLoadThreads * ny); mbar_init(&s_yempty[i], 1); }
+    mbar_init(&s_done, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(&s_tmem, tmem_cols);
+  if (warp == kWgLoadWarps) tmem_alloc(&s_tmem, tmem_cols);
   if (tid < 128) s_db[tid] = 0.f;
   tc_fence_before();
   __syncthreads();
@@ -374,13 +392,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
   const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_items = my_tiles * per_tile;
 
-  if (warp < 4) {
+  if (warp < kWgLoadWarps) {
     // ===== loaders =====
     float colsum[kMaxKAtoms - 1][4];
 #pragma unroll
     for (int a = 0; a < kMaxKAtoms - 1; ++a) colsum[a][0] = colsum[a][1] = colsum[a][2] = colsum[a][3] = 0.f;
-    const bool use_ring = nraw >= 2 && ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0) &&
-                          ((A.ldx2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X2) & 15u) == 0);
+    const bool direct = ((A.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15u) == 0) && ((A.ldx2 & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(A.X2) & 15u) == 0);
+    // item `it` of this CTA: tile it / per_tile, atom it % per_tile (dY atoms first).  X atoms use ring stage xi % S where
+    // xi counts X atoms; dY atoms go to set tile % n_sets.
+    auto hi_image = [&](int it) -> uint8_t* {
+      const int tl = it / per_tile, item = it % per_tile;
+      if (item < ny) return ysets + (tl % n_sets) * set_bytes + item * kAtomBytes;
+      return xst + ((tl * kx + item - ny) % S) * 2 * kAtomBytes;
+    };
+    auto wait_free = [&](int it) {   // the MMAs that read the slot's previous content have completed
+      const int tl = it / per_tile, item = it % per_tile;
+      if (item == 0) mbar_wait(&s_yempty[tl % n_sets], ((tl / n_sets) & 1) ^ 1);
+      if (item >= ny) { const int xi = tl * kx + item - ny; mbar_wait(&s_xempty[xi % S], ((xi / S) & 1) ^ 1); }
+    };
     auto src_of = [&](int it, const float*& g, long long& ld, int& col0, int& cols, long long& row0) {
       const int t = blockIdx.x + (it / per_tile) * gridDim.x, item = it % per_tile;
       row0 = (long long)t * 128;
@@ -389,49 +419,51 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
     };
     auto issue = [&](int it) {
       if (it < n_items) {
+        wait_free(it);
         const float* g; long long ld, row0; int col0, cols;
         src_of(it, g, ld, col0, cols, row0);
-        cp_async_atom(g, ld, row0, A.M, col0, cols, tid, raw + (it % nraw) * kAtomBytes);
+        cp_async_atom_swz<kWgLoadThreads>(g, ld, row0, A.M, col0, cols, tid, hi_image(it), true);
       }
       cp_async_commit();
     };
-    auto load_regs = [&](int it, float4 v[8]) {
-      const float* g; long long ld, row0; int col0, cols;
-      src_of(it, g, ld, col0, cols, row0);
-      load_atom_regs(g, ld, row0, A.M, col0, cols, tid, v);
-    };
-    float4 pre[8];
-    if (use_ring) {
-      for (int it = 0; it < nraw - 1; ++it) issue(it);
-    } else if (n_items > 0) {
-      load_regs(0, pre);
+    // atoms in flight: bounded by the X ring (the slot of an atom being issued must not belong to an atom this loop has
+    // not completed yet); with a single dY set the next tile's dY can only be issued once this tile is consumed -> 0
+    const int dist = (n_sets == 2) ? (kWgDist < S - 1 ? kWgDist : S - 1) : 0;
+    if (direct) {
+      for (int it = 0; it < dist; ++it) issue(it);
     }
-    int xi = 0;  // running X-item counter (stage ring position)
     for (int it = 0; it < n_items; ++it) {
-      const int item = it % per_tile, tl = it / per_tile;
-      if (use_ring) {
-        issue(it + nraw - 1);
-        cp_async_wait_dyn(nraw - 1);
-        read_raw_atom(raw + (it % nraw) * kAtomBytes, tid, pre);
-      }
-      if (item < ny) {
-        if (item == 0) mbar_wait(&s_yempty, (tl & 1) ^ 1);   // the previous tile's MMAs have read the dY set
+      const int tl = it / per_tile, item = it % per_tile;
+      uint8_t* hi = hi_image(it);
+      uint8_t* lo = (item < ny) ? hi + ny * kAtomBytes : hi + kAtomBytes;
+      if (direct) {
+        issue(it + dist);
+        cp_async_wait_dyn(dist);
+        if (item < ny) {
 #pragma unroll
-        for (int a = 0; a < kMaxKAtoms - 1; ++a)
-          if (a == item) store_atom_regs(pre, y_hi + a * kAtomBytes, y_lo + a * kAtomBytes, tid, true, colsum[a]);
-        if (!use_ring && it + 1 < n_items) load_regs(it + 1, pre);
-        fence_async_smem();
-        mbar_arrive(&s_yfull);
-      } else {
-        const int s = xi % S;
-        mbar_wait(&s_xempty[s], ((xi / S) & 1) ^ 1);
-        uint8_t* x_hi = xst + s * 2 * kAtomBytes;
-        store_atom_regs(pre, x_hi, x_hi + kAtomBytes, tid, true, nullptr);
-        if (!use_ring && it + 1 < n_items) load_regs(it + 1, pre);
-        fence_async_smem();
-        mbar_arrive(&s_xfull[s]);
-        ++xi;
+          for (int a = 0; a < kMaxKAtoms - 1; ++a)
+            if (a == item) make_lo_atom<kWgLoadThreads>(hi, lo, tid, true, colsum[a]);
+        } else {
+          make_lo_atom<kWgLoadThreads>(hi, lo, tid, true, nullptr);
+        }
+      } else if (tid < 128) {
+        // unaligned rows: 128 threads stage through registers (hi and lo images written together)
+        wait_free(it);
+        const float* g; long long ld, row0; int col0, cols;
+        src_of(it, g, ld, col0, cols, row0);
+        float4 v[8];
+        load_atom_regs(g, ld, row0, A.M, col0, cols, tid, v);
+        if (item < ny) {
+#pragma unroll
+          for (int a = 0; a < kMaxKAtoms - 1; ++a)
+            if (a == item) store_atom_regs(v, hi, lo, tid, true, colsum[a]);
+        } else {
+          store_atom_regs(v, hi, lo, tid, true, nullptr);
+        }
       }
+      fence_async_smem();
+      if (item < ny) mbar_arrive(&s_yfull[tl % n_sets]);
+      else mbar_arrive(&s_xfull[(tl * kx + item - ny) % S]);
     }
     cp_async_wait<0>();
     // bias gradient: column sums of dY gathered while staging
@@ -444,17 +476,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
     }
   } else {
     // ===== MMA issuer =====
-    const uint32_t idesc = instr_desc(MM, 32, true, true);
+    const uint32_t idesc = instr_desc(MM, stacked ? 64 : 32, true, true);
     int xi = 0;
+    long long w_y = 0, w_x = 0, w_iss = 0;
+    const long long t_start = TNF_CLK();
     for (int tl = 0; tl < my_tiles; ++tl) {
-      mbar_wait(&s_yfull, tl & 1);
+      const int set = tl % n_sets;
+      { const long long t0 = TNF_CLK(); mbar_wait(&s_yfull[set], (tl / n_sets) & 1); w_y += TNF_CLK() - t0; }
       for (int j = 0; j < kx; ++j, ++xi) {
         const int s = xi % S;
-        mbar_wait(&s_xfull[s], (xi / S) & 1);
+        { const long long t0 = TNF_CLK(); mbar_wait(&s_xfull[s], (xi / S) & 1); w_x += TNF_CLK() - t0; }
+        const long long ti = TNF_CLK();
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t yh = smem_u32(y_hi), yl = smem_u32(y_lo);
+          const uint32_t yh = smem_u32(ysets + set * set_bytes), yl = yh + ny * kAtomBytes;
           const uint32_t xh = smem_u32(xst + s * 2 * kAtomBytes), xl = xh + kAtomBytes;
+          if (stacked) {
+#pragma unroll 4
+            for (int kk = 0; kk < 16; ++kk)
+              mma_tf32(tmem_d + 64 * j, desc_mnmajor(yh, kk), desc_mnmajor(xh, kk), idesc, !(tl == 0 && kk == 0));
+          } else
 #pragma unroll 1
           for (int pass = 0; pass < 3; ++pass) {
             const uint32_t ya = (pass == 1) ? yl : yh;
@@ -464,19 +505,42 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
               mma_tf32(tmem_d + 32 * j, desc_mnmajor(ya, kk), desc_mnmajor(xa, kk), idesc, !(tl == 0 && pass == 0 && kk == 0));
           }
           mma_commit(&s_xempty[s]);
-          if (j == kx - 1) mma_commit(&s_yempty);
+          if (j == kx - 1) mma_commit(&s_yempty[set]);
         }
         __syncwarp();
+        w_iss += TNF_CLK() - ti;
       }
     }
     if (elect_one()) mma_commit(&s_done);
     __syncwarp();
+    if (g_dbg && lane == 0 && blockIdx.x == 0) { g_dbg[8] = w_y; g_dbg[9] = w_x; g_dbg[10] = TNF_CLK() - t_start; g_dbg[11] = w_iss; }
   }
+  { const long long t0 = TNF_CLK();
   mbar_wait(&s_done, 0);   // every MMA of this CTA has completed
+  if (g_dbg && tid == 0 && blockIdx.x == 0) g_dbg[12] = TNF_CLK() - t0; }
+  const long long t_flush = TNF_CLK();
   tc_fence_after();
   __syncthreads();
   if (A.db && tid < A.N) atomicAdd(A.db + tid, s_db[tid]);
-  if (my_tiles > 0 && warp < 4) {
+  if (my_tiles > 0 && warp < 4 && stacked) {
+    const int n_out = (warp * 32 + lane) & 63;      // lanes n and n + 64 hold the dY_hi / dY_lo rows of feature n
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+    for (int j = 0; j < kx; ++j) {
+      float v[32], u[32];
+      tmem_ld32(taddr + 64 * j, v);        // x X_hi
+      tmem_ld32(taddr + 64 * j + 32, u);   // x X_lo
+      float* dst = A.dW + (long long)n_out * A.K + 32 * j;
+      if ((A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(A.dW) & 15u) == 0 && 32 * j + 31 < A.K) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)   // one L2 reduction per 16 bytes
+          red_add_f4(dst + i, make_float4(v[i] + u[i], v[i + 1] + u[i + 1], v[i + 2] + u[i + 2], v[i + 3] + u[i + 3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (32 * j + i < A.K) atomicAdd(dst + i, v[i] + u[i]);
+      }
+    }
+  } else if (my_tiles > 0 && warp < 4) {
     // D rows = output features: M=128 -> lane == row; M=64 -> row m sits in lane 32*(m/16) + m%16
     int n_out;
     bool active;
@@ -495,7 +559,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
+  if (g_dbg && tid == 0 && blockIdx.x == 0) g_dbg[13] = TNF_CLK() - t_flush;
+  if (warp == kWgLoadWarps) tmem_dealloc(tmem_d, tmem_cols);
 }
 
 // Backward of a fused head (n_head <= 4 outputs on top of a ReLU hidden layer H[M,N]):
@@ -692,22 +757,15 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   LinArgs A{};
   A.X = dy; A.ldx = lddy; A.X2 = x; A.ldx2 = ldx; A.dW = dweight; A.db = dbias; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);
-  // shared-memory plan: resident dY set + S X stages (32 KB each) + raw cp.async ring (16 KB per slot)
-  const size_t fixed = (size_t)(2 * ((n + 31) / 32)) * kAtomBytes + 1024;
-  const size_t budget = 226 * 1024;
-  size_t smem = 0;
-  for (int r : {kRawRing, 3, 2, 0}) {
-    const size_t f = fixed + (size_t)r * kAtomBytes;
-    if (f + 2 * kAtomBytes > budget) continue;
-    int st_ = (int)((budget - f) / (2 * kAtomBytes));
-    if (st_ < 1) continue;
-    if (r >= 3 && st_ < 2) continue;   // prefer two X stages over a deeper raw ring
-    A.ring = st_ > kMaxStages ? kMaxStages : st_;
-    A.raw = r;
-    smem = f + (size_t)A.ring * 2 * kAtomBytes;
-    break;
-  }
-  TNF_REQUIRE(smem > 0, "layer too large for the wgrad shared-memory plan (n=%d)", n);
+  // shared-memory plan: dY sets (hi + lo images of n/32 atoms each; two sets when they leave room for >= 2 X stages)
+  // + S X stages (32 KB each)
+  const size_t set_bytes = (size_t)(2 * ((n + 31) / 32)) * kAtomBytes;
+  const size_t budget = 226 * 1024 - 1024;
+  A.raw = (2 * set_bytes + 2 * 2 * kAtomBytes <= budget) ? 2 : 1;
+  TNF_REQUIRE((size_t)A.raw * set_bytes + 2 * kAtomBytes <= budget, "layer too large for the wgrad shared-memory plan (n=%d)", n);
+  int st_ = (int)((budget - (size_t)A.raw * set_bytes) / (2 * kAtomBytes));
+  A.ring = st_ > kMaxStages ? kMaxStages : st_;
+  const size_t smem = (size_t)A.raw * set_bytes + (size_t)A.ring * 2 * kAtomBytes + 1024;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static thread_local bool configured = false;
   if (!configured) {
