@@ -146,6 +146,12 @@ int tnf_kplanes_bwd(const float* const* planes, float* const* grad_planes, const
                     int32_t n_scales, int32_t channels, const float* x, int64_t x_stride, int64_t n,
                     const float* grad_out, void* stream);
 
+/* tnf_kplanes_bwd restricted to scales [scale_begin, scale_end): lets a data-parallel caller start the all-reduce of one
+ * scale's plane gradients while the other scales are still being scattered (grad_out keeps its full [n][n_scales*C] rows). */
+int tnf_kplanes_bwd_scales(const float* const* planes, float* const* grad_planes, const int32_t* res, int32_t n_scales,
+                           int32_t channels, const float* x, int64_t x_stride, int64_t n, const float* grad_out,
+                           int32_t scale_begin, int32_t scale_end, void* stream);
+
 /* ---- a13: K-Planes total-variation regulariser ---------------------------------------------------
  * Replaces KPlanesFeaturePlane.loss_tv / KPlanesFeatureField.loss_tv (src/models.py:115-118,165-172)
  * and their autograd backward for a table of n_planes channels-last planes [res][res][C].

@@ -27,6 +27,7 @@ struct KPArgs {
   long long n;
   float* out;
   const float* grad_out;
+  int scale0;   // first scale handled by this launch (blockIdx.y counts from it)
 };
 
 // One axis of torch's grid_sampler (bilinear, zeros padding, align_corners=True):
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256) kplanes_kernel(const KPArgs A) {
   // 12 corner lines -> blend) than a loop over the scales, and since the blocks of one scale are scheduled together the
   // live working set is that scale's three planes (6 / 25 / 100 MB for 128 / 256 / 512: each fits the 126 MB L2).
   {
-    const int s = blockIdx.y;
+    const int s = blockIdx.y + A.scale0;
     const int res = A.res[s];
     const Axis ax = axis_setup(cx, res), ay = axis_setup(cy, res), az = axis_setup(cz, res);
     Corners c[3];
@@ -195,15 +196,24 @@ extern "C" int tnf_kplanes_fwd(const float* const* planes, const int32_t* res, i
 extern "C" int tnf_kplanes_bwd(const float* const* planes, float* const* grad_planes, const int32_t* res,
                                int32_t n_scales, int32_t channels, const float* x, int64_t x_stride,
                                int64_t n, const float* grad_out, void* stream) {
+  return tnf_kplanes_bwd_scales(planes, grad_planes, res, n_scales, channels, x, x_stride, n, grad_out, 0, n_scales, stream);
+}
+
+extern "C" int tnf_kplanes_bwd_scales(const float* const* planes, float* const* grad_planes, const int32_t* res,
+                                      int32_t n_scales, int32_t channels, const float* x, int64_t x_stride, int64_t n,
+                                      const float* grad_out, int32_t scale_begin, int32_t scale_end, void* stream) {
   using namespace tnf;
   KPArgs A{};
   TNF_REQUIRE(grad_planes, "null grad plane table");
+  TNF_REQUIRE(scale_begin >= 0 && scale_begin <= scale_end && scale_end <= n_scales, "bad scale range [%d,%d)", scale_begin, scale_end);
+  if (scale_begin == scale_end) return TNF_OK;
   int rc = fill_args(&A, planes, grad_planes, res, n_scales, channels, x, x_stride, n);
   if (rc != TNF_OK || n == 0) return rc;
   TNF_REQUIRE(grad_out && (reinterpret_cast<uintptr_t>(grad_out) & 15u) == 0, "grad_out null/misaligned");
   A.grad_out = grad_out;
+  A.scale0 = scale_begin;
   const long long threads = n * (channels / 4);
-  kplanes_kernel<true><<<dim3((unsigned)ceil_div(threads, 256), (unsigned)n_scales), 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  kplanes_kernel<true><<<dim3((unsigned)ceil_div(threads, 256), (unsigned)(scale_end - scale_begin)), 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   TNF_LAUNCH_CHECK("kplanes_bwd_kernel");
   return TNF_OK;
 }

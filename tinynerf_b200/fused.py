@@ -18,6 +18,7 @@ import os
 from typing import Dict, List
 
 import torch
+import torch.distributed as dist
 
 from . import _cuda, _lib
 from .core import NerfRenderer
@@ -139,9 +140,10 @@ class FusedKPlanesStep:
     # ---- the iteration -----------------------------------------------------------------------------
     @torch.no_grad()
     def forward_backward(self, packed: torch.Tensor, info: torch.Tensor, target: torch.Tensor,
-                         n_rays_global: torch.Tensor | None = None) -> Dict[str, torch.Tensor]:
+                         n_rays_global: torch.Tensor | None = None, reduce: bool = False) -> Dict[str, torch.Tensor]:
         """packed [N,7], info [R,2] int32 (a RayProvider partition), target [R,3].  Sets p.grad of every parameter to
-        d(grad_scale * (MSE_union + tv_alpha/world * loss_tv))/dp and returns {"loss", "rendered"}."""
+        d(grad_scale * (MSE_union + tv_alpha/world * loss_tv))/dp and returns {"loss", "rendered"}.  With `reduce` the
+        gradients are all-reduced over the ranks (sum) before returning, overlapped with the tail of backward."""
         _lib.require_cuda(packed, "packed_samples")
         n, r = packed.size(0), info.size(0)
         if n == 0 or r == 0:
@@ -240,13 +242,39 @@ class FusedKPlanesStep:
             dfeat = ws["dfeat"][:n]
             torch.add(dfeat, ws["dxc"][:n, xw - F:xw], out=dfeat)
             _lib.launch_count += 1
-            call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
-                 P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
+            np_ = len(self.planes)
+
+            def planes_bwd(s0, s1):
+                """plane gradients of scales [s0, s1): scatter-add of the data term + TV value and gradient
+                (loss += tv_alpha * loss_tv, src/run.py:254-255) from one pass over those planes"""
+                call("tnf_kplanes_bwd_scales", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
+                     P(packed), 7, n, P(dfeat), s0, s1, st,
+                     nbytes=n * (12 + 4 * self.channels * (s1 - s0)) + 2 * 4 * sum(p.numel() for p in self.planes[3 * s0:3 * s1]))
+                if self.tv_alpha != 0.0:
+                    k = 3 * (s1 - s0)
+                    sub = lambda arr, typ: (typ * k)(*arr[3 * s0:3 * s1])
+                    call("tnf_tv_fwd_bwd", sub(self._plane_ptrs, C.c_void_p), sub(self._grad_ptrs, C.c_void_p),
+                         sub(self._res_planes, C.c_int32), k, self.channels, sub(self._tv_w, C.c_float), P(self._tv_gscale), 1,
+                         P(self._tv_sums) + 16 * 3 * s0, st, nbytes=3 * 4 * sum(p.numel() for p in self.planes[3 * s0:3 * s1]))
+
+            if reduce and self.world > 1 and self.n_scales > 1:
+                # data parallel: the largest scale's gradients (3/4 of all bytes) go first and their all-reduce runs on
+                # NCCL's stream while the remaining scales are scattered; the rest follows in two more collectives
+                big = self.n_scales - 1
+                lo_ = sum(_pad4(p.numel()) for p in self.planes[:3 * big])
+                hi_ = lo_ + sum(_pad4(p.numel()) for p in self.planes[3 * big:])
+                planes_bwd(big, big + 1)
+                work = dist.all_reduce(self.flat_grad[lo_:hi_], async_op=True)
+                planes_bwd(0, big)
+                dist.all_reduce(self.flat_grad[:lo_])
+                dist.all_reduce(self.flat_grad[hi_:])
+                work.wait()
+            else:
+                planes_bwd(0, self.n_scales)
+                if reduce and self.world > 1:
+                    dist.all_reduce(self.flat_grad)
             loss = ws["loss"][0]
             if self.tv_alpha != 0.0:
-                # loss += tv_alpha * loss_tv (src/run.py:254-255): value and gradient from one pass over the planes
-                call("tnf_tv_fwd_bwd", self._plane_ptrs, self._grad_ptrs, self._res_planes, len(self.planes), self.channels,
-                     self._tv_w, P(self._tv_gscale), 1, P(self._tv_sums), st, nbytes=3 * self._plane_bytes)
                 loss = loss + torch.dot(self._tv_sums, self._tv_coef).float()
             else:
                 loss = loss.clone()

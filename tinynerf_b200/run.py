@@ -395,9 +395,7 @@ class Trainer:
     def _step_fused(self, packed, rgbs, info, grid_ready) -> Dict[str, float]:
         """Same iteration through fused.FusedKPlanesStep: identical kernels and order, no autograd / glue ops."""
         n_glob = global_ray_count(info.size(0), self.device, self.world) if self.world > 1 else None
-        out = self._fused.forward_backward(packed, info, rgbs, n_glob)
-        if self.world > 1:
-            dist.all_reduce(self._fused.flat_grad)  # every parameter gradient in one collective
+        out = self._fused.forward_backward(packed, info, rgbs, n_glob, reduce=self.world > 1)  # incl. the gradient all-reduce
         self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
