@@ -77,6 +77,7 @@ class FusedKPlanesStep:
             tot += _pad4(p.numel())
         self.flat_grad = torch.zeros(tot, device=self.dev)
         self.grads = [torch.as_strided(self.flat_grad, p.shape, p.stride(), off) for p, off in zip(params, offs)]
+        self._plane_grad_end = offs[len(self.planes)]   # flat_grad[:end] = plane gradients, [end:] = the heads' 
         self.params = params
         self._g = {id(p): g for p, g in zip(params, self.grads)}
         self.attach_grads()
@@ -127,7 +128,8 @@ class FusedKPlanesStep:
             ws["xc"], ws["dxc"] = e(cap, self.xc_ld), e(cap, self.xc_ld)
             for i in range(len(self.col_lin) - 1):
                 ws[f"h{i}"] = e(cap, hid_c)
-            ws["dha"], ws["dhb"] = e(cap, hid_c), e(cap, hid_c)
+            for i in range(len(self.col_lin) - 1):
+                ws[f"dh{i}"] = e(cap, hid_c)
             ws["rgb"], ws["grgb"] = e(cap, 3), e(cap, 3)
             self._cap_n = cap
         if r > self._cap_r:
@@ -140,7 +142,7 @@ class FusedKPlanesStep:
     # ---- the iteration -----------------------------------------------------------------------------
     @torch.no_grad()
     def forward_backward(self, packed: torch.Tensor, info: torch.Tensor, target: torch.Tensor,
-                         n_rays_global: torch.Tensor | None = None, reduce: bool = False) -> Dict[str, torch.Tensor]:
+                         n_rays_global: torch.Tensor | None = None, reduce: bool = False, n_rays_work=None) -> Dict[str, torch.Tensor]:
         """packed [N,7], info [R,2] int32 (a RayProvider partition), target [R,3].  Sets p.grad of every parameter to
         d(grad_scale * (MSE_union + tv_alpha/world * loss_tv))/dp and returns {"loss", "rendered"}.  With `reduce` the
         gradients are all-reduced over the ranks (sum) before returning, overlapped with the tail of backward."""
@@ -214,65 +216,52 @@ class FusedKPlanesStep:
             call("tnf_composite_fwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(ws["rendered"]), None, st,
                  nbytes=16 * n + 20 * r)
             # ---- loss + its gradient (src/run.py:252,259) ----
+            if n_rays_work is not None:
+                n_rays_work.wait()   # the union batch's ray count (async all-reduce started before the forward)
             call("tnf_mse_loss_grad", P(ws["rendered"]), P(target), r, float(r), _lib.ptr(n_rays_global), self.grad_scale,
                  P(ws["grend"]), P(ws["loss"]), st, nbytes=36 * r)
             # ---- backward ----
             call("tnf_composite_bwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(ws["grend"]), P(ws["gw"]),
                  P(ws["grgb"]), st, nbytes=32 * n + 20 * r)
-            # colour head: fused output layer + sigmoid, then hidden layers from the last to the first
-            h_last = ws[f"h{nh - 1}"]
-            dh, dh_other = ws["dha"], ws["dhb"]
-            call("tnf_head_bwd", P(h_last), hc_w, P(cl[-1].weight), P(ws["rgb"]), P(ws["grgb"]), P(dh), G(cl[-1].weight),
-                 G(cl[-1].bias), n, hc_w, 3, 2, st, nbytes=4 * n * (2 * hc_w + 6))
+            # Order: the data-gradient chain first (it ends in the plane gradients, 99.8 % of the bytes a data-parallel run
+            # has to all-reduce), then the weight gradients of the heads -- 0.5 ms of work that depends only on the saved
+            # dh / activations and hides the plane all-reduce completely.
+            # colour head: fused output layer + sigmoid, then the hidden layers' data gradients from the last to the first
+            dh = [ws[f"dh{i}"] for i in range(nh)]   # dh[i] = gradient wrt the pre-activation of colour layer i
+            call("tnf_head_bwd", P(ws[f"h{nh - 1}"]), hc_w, P(cl[-1].weight), P(ws["rgb"]), P(ws["grgb"]), P(dh[nh - 1]),
+                 G(cl[-1].weight), G(cl[-1].bias), n, hc_w, 3, 2, st, nbytes=4 * n * (2 * hc_w + 6))
             for i in range(nh - 1, 0, -1):
                 inp = ws[f"h{i - 1}"]
-                wgrad(P(dh), hc_w, P(inp), hc_w, cl[i])
-                dgrad(P(dh), hc_w, cl[i], P(dh_other), hc_w, P(inp), hc_w)
-                dh, dh_other = dh_other, dh
-            wgrad(P(dh), hc_w, P(ws["xc"]), xld, cl[0])
-            dgrad(P(dh), hc_w, cl[0], P(ws["dxc"]), xld, None, 0)
+                dgrad(P(dh[i]), hc_w, cl[i], P(dh[i - 1]), hc_w, P(inp), hc_w)
+            dgrad(P(dh[0]), hc_w, cl[0], P(ws["dxc"]), xld, None, 0)
             # density branch: weights backward, fused output layer + truncated_exp, hidden layer
             call("tnf_weights_bwd", P(ws["sigma"]), P(steps), sstride, P(info), P(ws["w"]), P(ws["gw"]), P(ws["gsigma"]), n, r,
                  flags, _lib.ptr(status), st, nbytes=20 * n + 8 * r, extra_kernels=0 if flags else 3)
             call("tnf_head_bwd", P(ws["hs"]), hs_w, P(sl[1].weight), P(ws["sigma"]), P(ws["gsigma"]), P(ws["dhs"]),
                  G(sl[1].weight), G(sl[1].bias), n, hs_w, 1, 1, st, nbytes=4 * n * (2 * hs_w + 2))
-            wgrad(P(ws["dhs"]), hs_w, P(ws["feats"]), F, sl[0])
             dgrad(P(ws["dhs"]), hs_w, sl[0], P(ws["dfeat"]), F, None, 0)
             # the features feed both heads: d feats = d(sigma branch) + d(colour input)[:, feature columns]
             dfeat = ws["dfeat"][:n]
             torch.add(dfeat, ws["dxc"][:n, xw - F:xw], out=dfeat)
             _lib.launch_count += 1
-            np_ = len(self.planes)
-
-            def planes_bwd(s0, s1):
-                """plane gradients of scales [s0, s1): scatter-add of the data term + TV value and gradient
-                (loss += tv_alpha * loss_tv, src/run.py:254-255) from one pass over those planes"""
-                call("tnf_kplanes_bwd_scales", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
-                     P(packed), 7, n, P(dfeat), s0, s1, st,
-                     nbytes=n * (12 + 4 * self.channels * (s1 - s0)) + 2 * 4 * sum(p.numel() for p in self.planes[3 * s0:3 * s1]))
-                if self.tv_alpha != 0.0:
-                    k = 3 * (s1 - s0)
-                    sub = lambda arr, typ: (typ * k)(*arr[3 * s0:3 * s1])
-                    call("tnf_tv_fwd_bwd", sub(self._plane_ptrs, C.c_void_p), sub(self._grad_ptrs, C.c_void_p),
-                         sub(self._res_planes, C.c_int32), k, self.channels, sub(self._tv_w, C.c_float), P(self._tv_gscale), 1,
-                         P(self._tv_sums) + 16 * 3 * s0, st, nbytes=3 * 4 * sum(p.numel() for p in self.planes[3 * s0:3 * s1]))
-
-            if reduce and self.world > 1 and self.n_scales > 1:
-                # data parallel: the largest scale's gradients (3/4 of all bytes) go first and their all-reduce runs on
-                # NCCL's stream while the remaining scales are scattered; the rest follows in two more collectives
-                big = self.n_scales - 1
-                lo_ = sum(_pad4(p.numel()) for p in self.planes[:3 * big])
-                hi_ = lo_ + sum(_pad4(p.numel()) for p in self.planes[3 * big:])
-                planes_bwd(big, big + 1)
-                work = dist.all_reduce(self.flat_grad[lo_:hi_], async_op=True)
-                planes_bwd(0, big)
-                dist.all_reduce(self.flat_grad[:lo_])
-                dist.all_reduce(self.flat_grad[hi_:])
+            # plane gradients: scatter-add of the data term, then TV value + gradient (loss += tv_alpha * loss_tv,
+            # src/run.py:254-255) from one pass over the planes
+            call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
+                 P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
+            if self.tv_alpha != 0.0:
+                call("tnf_tv_fwd_bwd", self._plane_ptrs, self._grad_ptrs, self._res_planes, len(self.planes), self.channels,
+                     self._tv_w, P(self._tv_gscale), 1, P(self._tv_sums), st, nbytes=3 * self._plane_bytes)
+            work = None
+            if reduce and self.world > 1:
+                work = dist.all_reduce(self.flat_grad[:self._plane_grad_end], async_op=True)  # runs under the wgrads
+            # weight gradients of both heads
+            for i in range(nh - 1, 0, -1):
+                wgrad(P(dh[i]), hc_w, P(ws[f"h{i - 1}"]), hc_w, cl[i])
+            wgrad(P(dh[0]), hc_w, P(ws["xc"]), xld, cl[0])
+            wgrad(P(ws["dhs"]), hs_w, P(ws["feats"]), F, sl[0])
+            if work is not None:
+                dist.all_reduce(self.flat_grad[self._plane_grad_end:])
                 work.wait()
-            else:
-                planes_bwd(0, self.n_scales)
-                if reduce and self.world > 1:
-                    dist.all_reduce(self.flat_grad)
             loss = ws["loss"][0]
             if self.tv_alpha != 0.0:
                 loss = loss + torch.dot(self._tv_sums, self._tv_coef).float()

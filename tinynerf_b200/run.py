@@ -394,8 +394,11 @@ class Trainer:
 
     def _step_fused(self, packed, rgbs, info, grid_ready) -> Dict[str, float]:
         """Same iteration through fused.FusedKPlanesStep: identical kernels and order, no autograd / glue ops."""
-        n_glob = global_ray_count(info.size(0), self.device, self.world) if self.world > 1 else None
-        out = self._fused.forward_backward(packed, info, rgbs, n_glob, reduce=self.world > 1)  # incl. the gradient all-reduce
+        n_glob = work = None
+        if self.world > 1:  # ray count of the union batch: reduced while the forward runs
+            n_glob = torch.tensor(float(info.size(0)), device=self.device)
+            work = dist.all_reduce(n_glob, async_op=True)
+        out = self._fused.forward_backward(packed, info, rgbs, n_glob, reduce=self.world > 1, n_rays_work=work)  # incl. the gradient all-reduce
         self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
