@@ -265,6 +265,7 @@ def main():
 
     o, d, rgbs = make_scene(N_STORE, SEED)
     analytic = synthetic.analytic_grid(128, seed=SEED + 2).to(dev)
+    analytic_mean = analytic.mean().item()
     cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=BATCH, n_samples=N_SAMPLES, seed=SEED)
 
     def make_trainer(host: bool):
@@ -272,15 +273,16 @@ def main():
         store = RayStore(o, d, rgbs, dev, host=host, seed=SEED, rank=rank, world=world)
         tr = Trainer(cfg, store, dev, rank=rank, world=world)
         tr.occupancy_grid.grid.copy_(analytic)
-        tr.occupancy_grid.mean = tr.occupancy_grid.grid.mean().item()
+        tr.occupancy_grid.mean = analytic_mean
+
+        def pin_state(t):  # keep the occupancy state fixed (the update work itself has just been done inside step())
+            t.occupancy_grid.grid.copy_(analytic)
+            t.occupancy_grid.mean = analytic_mean
+        tr.post_update = pin_state
         return tr
 
     def one_step(tr, read_loss: bool):
-        upd = tr.train_step % tr.occupancy_grid_updates == 0
         info = tr.step()
-        if upd:  # keep the occupancy state fixed (the update work itself was done inside tr.step())
-            tr.occupancy_grid.grid.copy_(analytic)
-            tr.occupancy_grid.mean = tr.occupancy_grid.grid.mean().item()
         if read_loss:
             float(info["loss"])  # D2H of the step's result
         return info["n_samples"]

@@ -97,6 +97,8 @@ typedef struct tnf_march_params {
   const float* noise;       /* optional device [n_rays][S] U[0,1) jitter (training); NULL = see seed */
   int32_t jitter;           /* 0: no jitter (training=False); 1: jitter from `noise` or Philox(seed) */
   uint64_t seed, offset;    /* Philox4x32-10 key/counter base when jitter && !noise */
+  const float* threshold_dev; /* optional DEVICE scalar that replaces `threshold` (e.g. min(base, grid.mean()) computed on the
+                               device right after an occupancy update, so the update needs no host synchronisation) */
 } tnf_march_params;
 
 int tnf_march_count(const tnf_march_params* p /*[host]*/, const float* rays_o, const float* rays_d,
@@ -127,6 +129,10 @@ int tnf_occ_update_coords(int32_t gd, int32_t gh, int32_t gw, int64_t cell0, int
                           void* stream);
 int tnf_occ_update_apply(float* grid, int64_t cell0, int64_t n_cells, const float* sigma,
                          float step_size, float threshold, float decay, void* stream);
+/* same, with the threshold optionally read from a device scalar (the value min(base, mean) left on the device by the
+ * previous update: a training loop then never synchronises the host for the grid update) */
+int tnf_occ_update_apply_dev(float* grid, int64_t cell0, int64_t n_cells, const float* sigma, float step_size,
+                             float threshold, const float* threshold_dev /*optional*/, float decay, void* stream);
 
 /* ---- a12: K-Planes fused feature lookup -------------------------------------------------------
  * Replaces KPlanesFeatureField.forward (src/models.py:153-163) = 9x KPlanesFeaturePlane.forward

@@ -40,6 +40,7 @@ class MarchParams(C.Structure):
         ("jitter", C.c_int32),
         ("seed", C.c_uint64),
         ("offset", C.c_uint64),
+        ("threshold_dev", C.c_void_p),
     ]
 
 
@@ -61,6 +62,8 @@ _SIGNATURES = {
                                         C.c_uint64, C.c_uint64, c_f32p, C.c_void_p]),
     "tnf_occ_update_apply": (C.c_int, [c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_float, C.c_float, C.c_float,
                                        C.c_void_p]),
+    "tnf_occ_update_apply_dev": (C.c_int, [c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_float, C.c_float, c_f32p, C.c_float,
+                                           C.c_void_p]),
     "tnf_kplanes_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_int32, c_f32p,
                                   C.c_int64, C.c_int64, c_f32p, C.c_void_p]),
     "tnf_kplanes_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,

@@ -144,7 +144,9 @@ class OccupancyGrid(torch.nn.Module):
         self.grid: torch.Tensor
         self.register_buffer("grid", torch.ones(size, dtype=torch.float))
         self.size = torch.tensor(size, dtype=torch.float)
-        self.mean = 1.0
+        self._mean: float | None = 1.0           # host value; None while only the device value is current
+        self._mean_t: torch.Tensor | None = None  # device scalar written by update() (no host sync)
+        self._thr_t: torch.Tensor | None = None   # device scalar min(base_threshold, mean) for the march kernels
         # kept for interface parity (the reference exposes .coords); the kernels derive cell
         # coordinates from the flat index instead of reading this tensor
         self.coords = torch.flip(torch.stack(torch.meshgrid([
@@ -155,6 +157,30 @@ class OccupancyGrid(torch.nn.Module):
         self.jitter_source = "cpu"
         self.slices_per_call = size[0]
         self._update_calls = 0
+
+    @property
+    def mean(self) -> float:
+        """grid.mean() after the last update (src/core.py:145).  update() leaves it on the device; reading it here is what
+        synchronises, so a training loop that never looks at it never waits for the update."""
+        if self._mean is None:
+            self._mean = float(self._mean_t.item())  # type: ignore
+        return self._mean
+
+    @mean.setter
+    def mean(self, value: float) -> None:
+        self._mean, self._mean_t, self._thr_t = float(value), None, None
+
+    def threshold_tensor(self) -> torch.Tensor | None:
+        """Device scalar min(base_threshold, mean) when the mean currently lives on the device, else None."""
+        if self._mean_t is None:
+            return None
+        if self._thr_t is None:
+            self._thr_t = torch.clamp(self._mean_t.float(), max=_f32(self.base_threshold)).reshape(1)
+        return self._thr_t
+
+    def _set_mean_from_grid(self) -> None:
+        self._mean, self._thr_t = None, None
+        self._mean_t = self.grid.mean()
 
     @torch.no_grad()
     def occupancy(self) -> float:
@@ -170,7 +196,12 @@ class OccupancyGrid(torch.nn.Module):
 
     def _step_size_f32(self) -> float:
         s = self.step_size
-        return float(s.item()) if isinstance(s, torch.Tensor) else _f32(s)
+        if isinstance(s, torch.Tensor):  # a 0-dim device tensor in the reference (src/core.py:68-70): read it once
+            key = (s.data_ptr(), s._version)
+            if getattr(self, "_step_cache", (None, None))[0] != key:
+                self._step_cache = (key, float(s.item()))
+            return self._step_cache[1]
+        return _f32(s)
 
     @torch.no_grad()
     def update(self, sigma_fn: Callable[[torch.Tensor], torch.Tensor], noise: torch.Tensor | None = None):
@@ -180,7 +211,7 @@ class OccupancyGrid(torch.nn.Module):
         noise: optional [D,H,W,3] U[0,1) tensor (any device) replacing the internally drawn jitter.
         """
         self.update_slices(sigma_fn, 0, self.grid.size(0), noise)
-        self.mean = self.grid.mean().item()
+        self._set_mean_from_grid()
 
     @torch.no_grad()
     def update_slices(self, sigma_fn: Callable[[torch.Tensor], torch.Tensor], z_begin: int, z_end: int,
@@ -192,7 +223,11 @@ class OccupancyGrid(torch.nn.Module):
         D, H, W = self.grid.shape
         dev = self.device
         per_slice = H * W
-        thr, decay, step = _f32(self.threshold), _f32(self.decay), self._step_size_f32()
+        # the threshold in force when the call starts (src/core.py:127,141): the device scalar left by the previous
+        # update when there is one (no host sync), else the host value
+        thr_t = self.threshold_tensor()
+        thr = _f32(self.base_threshold) if thr_t is not None else _f32(self.threshold)
+        decay, step = _f32(self.decay), self._step_size_f32()
         spc = max(1, min(int(self.slices_per_call), D))
         cpu_jitter = noise is None and self.jitter_source == "cpu"
         if cpu_jitter:  # keep the CPU generator stream aligned with the reference for skipped slices
@@ -216,8 +251,8 @@ class OccupancyGrid(torch.nn.Module):
                 sigma = sigma_fn(coords).reshape(-1).float().contiguous()
                 if sigma.numel() != n:
                     raise RuntimeError(f"sigma_fn returned {sigma.numel()} values for {n} coordinates")
-                _lib.call("tnf_occ_update_apply", self.grid.data_ptr(), z0 * per_slice, n, sigma.data_ptr(),
-                          step, thr, decay, stream, nbytes=12 * n)
+                _lib.call("tnf_occ_update_apply_dev", self.grid.data_ptr(), z0 * per_slice, n, sigma.data_ptr(),
+                          step, thr, _lib.ptr(thr_t), decay, stream, nbytes=12 * n)
         if cpu_jitter:
             for _ in range(z_end, D):
                 torch.rand(H, W, 3)
@@ -272,7 +307,13 @@ class RayProvider:
         p._keep = base._keep
         p.grid = grid.data_ptr()
         p.gd, p.gh, p.gw = grid.shape
-        p.threshold = _f32(self.occupancy_grid.threshold)
+        thr_t = self.occupancy_grid.threshold_tensor()
+        if thr_t is not None:   # the mean of the last update is still on the device: hand the kernels the device scalar
+            p.threshold_dev = thr_t.data_ptr()
+            p.threshold = _f32(self.occupancy_grid.base_threshold)
+            p._keep = list(p._keep) + [thr_t]
+        else:
+            p.threshold = _f32(self.occupancy_grid.threshold)
         return p
 
     def _scene_params(self, device, n_steps: int) -> _lib.MarchParams:

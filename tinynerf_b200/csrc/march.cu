@@ -179,7 +179,7 @@ int make_const(const tnf_march_params* p, MarchConst* M) {
   M->near_ = p->near; M->far_ = p->far; M->step_size = p->step_size;
   M->t_table = p->t_table; M->step_table = p->step_table;
   M->grid = p->grid; M->gd = p->gd; M->gh = p->gh; M->gw = p->gw;
-  M->thr = p->threshold; M->noise = p->noise; M->jitter = p->jitter;
+  M->thr = p->threshold; M->thr_dev = p->threshold_dev; M->noise = p->noise; M->jitter = p->jitter;
   M->seed = p->seed; M->offset = p->offset;
   return TNF_OK;
 }

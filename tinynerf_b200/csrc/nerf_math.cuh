@@ -42,6 +42,7 @@ struct MarchConst {
   const float* grid;
   int gd, gh, gw;
   float thr;
+  const float* thr_dev;   // optional device scalar overriding thr (keeps the occupancy update free of host syncs)
   const float* noise;
   int jitter;
   unsigned long long seed, offset;
@@ -151,7 +152,7 @@ TNF_HD SampleOut march_sample(const MarchConst& M, const float o[3], const float
   s.step = step;
   // src/core.py:151-156,176: mask = marcher_mask & (trilinear(grid) > thr); the lookup has no side effect,
   // so it is skipped for samples the marcher mask already rejects (about half of an AABB lattice)
-  s.keep = inside && (trilinear_zeros(M.grid, M.gd, M.gh, M.gw, s.p[0], s.p[1], s.p[2]) > M.thr);
+  s.keep = inside && (trilinear_zeros(M.grid, M.gd, M.gh, M.gw, s.p[0], s.p[1], s.p[2]) > (M.thr_dev ? *M.thr_dev : M.thr));
   return s;
 }
 

@@ -36,9 +36,11 @@ __global__ void occ_coords_kernel(int gd, int gh, int gw, long long cell0, long 
 }
 
 __global__ void occ_apply_kernel(float* __restrict__ grid, long long cell0, long long n,
-                                 const float* __restrict__ sigma, float step, float thr, float decay) {
+                                 const float* __restrict__ sigma, float step, float thr,
+                                 const float* __restrict__ thr_dev, float decay) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (thr_dev) thr = __ldg(thr_dev);
   const float alpha = TNF_SUB(1.f, expf(TNF_MUL(-__ldg(sigma + i), step)));
   const float old = grid[cell0 + i];
   grid[cell0 + i] = (alpha > thr) ? 1.f : TNF_MUL(decay, old);
@@ -63,12 +65,17 @@ extern "C" int tnf_occ_update_coords(int32_t gd, int32_t gh, int32_t gw, int64_t
 
 extern "C" int tnf_occ_update_apply(float* grid, int64_t cell0, int64_t n_cells, const float* sigma,
                                     float step_size, float threshold, float decay, void* stream) {
+  return tnf_occ_update_apply_dev(grid, cell0, n_cells, sigma, step_size, threshold, nullptr, decay, stream);
+}
+
+extern "C" int tnf_occ_update_apply_dev(float* grid, int64_t cell0, int64_t n_cells, const float* sigma, float step_size,
+                                        float threshold, const float* threshold_dev, float decay, void* stream) {
   using namespace tnf;
   TNF_REQUIRE(cell0 >= 0 && n_cells >= 0, "bad cell range");
   if (n_cells == 0) return TNF_OK;
   TNF_REQUIRE(grid && sigma, "null pointer");
   occ_apply_kernel<<<(unsigned)ceil_div(n_cells, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      grid, cell0, n_cells, sigma, step_size, threshold, decay);
+      grid, cell0, n_cells, sigma, step_size, threshold, threshold_dev, decay);
   TNF_LAUNCH_CHECK("occ_apply_kernel");
   return TNF_OK;
 }

@@ -150,9 +150,13 @@ class TrainConfig:
     bg_color: Tuple[float, float, float] | None = (1.0, 1.0, 1.0)
     grad_scale: float = 2.0 ** 10       # GradScaler(2**10) that is never unscaled (src/run.py:201,259)
     accumulate: str = "batched"         # "sequential" = the reference's chunk-by-chunk loop (one sync per chunk)
-    prefetch: bool = True               # march the next step's batch on a side stream while this step trains
+    prefetch: bool = True               # march the coming batches on a side stream while this step trains
+    prefetch_depth: int = 2             # batches kept marched ahead (2: the host's per-batch sync never waits for the step
+                                        # in flight, so a host hiccup on one rank is absorbed instead of stalling a collective)
     fused_tv_grad: bool = True          # TV gradient written straight into the plane grads (no autograd temporaries)
     fused_step: bool = True             # K-Planes: forward+loss+backward as one C-ABI call sequence (fused.py), no autograd
+    manual_gc: bool = True              # collect Python garbage at the occupancy-update cadence instead of at random steps
+                                        # (a generation-2 pause on ONE rank stalls every rank at the next collective)
     occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
     seed: int = 0
 
@@ -191,6 +195,9 @@ class Trainer:
         self.occupancy_grid = OccupancyGrid(size=res, step_size=self.ray_marcher.step_size, threshold=thr,
                                             decay=decay).to(dev)
         self.occupancy_grid.jitter_source = cfg.occupancy_jitter
+        # 16 depth slices (2^18 points) per sigma_fn call: the update's temporaries stay the size of a training batch's
+        # (no GB-sized allocations that the caching allocator would have to cudaMalloc around live per-step buffers)
+        self.occupancy_grid.slices_per_call = 16
         self.ray_provider = RayProvider(self.occupancy_grid, contraction, self.ray_marcher)
         bg = None if cfg.bg_color is None else torch.tensor(cfg.bg_color)
         self.renderer = NerfRenderer(feature_module, sigma_decoder, rgb_decoder, bg_color=bg).to(dev)
@@ -212,7 +219,10 @@ class Trainer:
         if world > 1 and self.device.type == "cuda":
             self._warm_collectives()
         self._side = torch.cuda.Stream(device=self.device) if (cfg.prefetch and self.device.type == "cuda") else None
-        self._next = None
+        self.post_update = None         # optional callable(trainer) run right after every occupancy update
+        self._gc_frozen = False
+        self._queue: List = []          # prefetched (batch, done event), oldest first
+        self._grid_event = None         # recorded after the latest occupancy update: batches marched later must see it
         self.last: Dict[str, float] = {}
 
     def _warm_collectives(self) -> None:
@@ -326,25 +336,31 @@ class Trainer:
         z0, z1 = shard_slices(og.grid.size(0), self.rank, self.world)
         og.update_slices(sigma_fn, z0, z1)
         dist.all_gather_into_tensor(og.grid.view(-1), og.grid[z0:z1].reshape(-1).clone())
-        og.mean = og.grid.mean().item()
+        og._set_mean_from_grid()
 
     # ---- one training iteration (src/run.py:246-261) -------------------------------------------
-    def _prefetch(self, after: torch.cuda.Event) -> None:
-        """March the next batch on the side stream.  It depends only on the occupancy grid, which the reference also
-        leaves untouched between this point and the next iteration's batch generation (src/run.py:215-249), and it
-        draws its jitter after this step's forward was enqueued, i.e. in the reference's generator order."""
+    def _prefetch(self) -> None:
+        """Keep `prefetch_depth` batches marched ahead on the side stream.  A batch depends only on the occupancy grid:
+        the batch of iteration j is generated before j's own update (src/run.py:215-249), so it must see the updates of
+        iterations < j.  After enqueueing iteration t, batch t+1 is always eligible; batch t+2 only if iteration t+1 does
+        not update the grid.  Batches are marched in order, so rays and jitter are consumed in the reference's order."""
         side = self._side
-        side.wait_event(after)
-        with torch.cuda.stream(side):
-            batch = self.next_batch()
-            done = side.record_event()
-        self._next = (batch, done)
+        t = self.train_step  # index of the next iteration to run
+        while len(self._queue) < max(1, self.cfg.prefetch_depth):
+            j = t + len(self._queue)          # iteration this batch is for
+            if any(i % self.occupancy_grid_updates == 0 for i in range(t, j)):
+                break                          # an update between now and j has not been enqueued yet
+            if self._grid_event is not None:
+                side.wait_event(self._grid_event)
+            with torch.cuda.stream(side):
+                batch = self.next_batch()
+                done = side.record_event()
+            self._queue.append((batch, done))
 
     def _take_batch(self):
-        if self._next is None:
+        if not self._queue:
             return self.next_batch()
-        (packed, rgbs, info), done = self._next
-        self._next = None
+        (packed, rgbs, info), done = self._queue.pop(0)
         main = torch.cuda.current_stream(self.device)
         main.wait_event(done)
         for t in (packed, packed._tnf_steps, rgbs, info):
@@ -352,14 +368,26 @@ class Trainer:
         return packed, rgbs, info
 
     def step(self) -> Dict[str, float]:
+        if self.cfg.manual_gc and self.device.type == "cuda":
+            import gc
+            if not self._gc_frozen:
+                gc.collect()
+                gc.freeze()    # everything allocated so far (torch's ~10^6 module objects) leaves the collector's reach:
+                gc.disable()   # later collections only scan what the loop itself created
+                self._gc_frozen = True
+            elif self.train_step % self.occupancy_grid_updates == 0:
+                gc.collect()
         packed, rgbs, info = self._take_batch()
         if not self.renderer.training:
             self.renderer.train()
         if self.train_step % self.occupancy_grid_updates == 0:
             self.update_occupancy()
-        grid_ready = torch.cuda.current_stream(self.device).record_event() if self._side is not None else None
+            if self.post_update is not None:
+                self.post_update(self)   # e.g. the benchmark pins the occupancy state here, inside the stream order
+            if self._side is not None:
+                self._grid_event = torch.cuda.current_stream(self.device).record_event()
         if self._fused is not None:
-            return self._step_fused(packed, rgbs, info, grid_ready)
+            return self._step_fused(packed, rgbs, info)
         rendered = self.renderer(packed, info)
         loss = dp_mse(rendered, rgbs, global_ray_count(info.size(0), self.device, self.world))
         tv_direct = 0.0
@@ -386,13 +414,13 @@ class Trainer:
         self.scheduler.step()
         self.train_step += 1
         if self._side is not None:
-            # everything above is enqueued; the next batch is marched on the side stream while the GPU is still
-            # busy with this step's backward + optimiser, so its host sync no longer stalls the step
-            self._prefetch(grid_ready)
+            # everything above is enqueued; the coming batches are marched on the side stream while the GPU is still
+            # busy with this step's backward + optimiser, so their host sync no longer stalls the step
+            self._prefetch()
         self.last = {"loss": loss.detach(), "n_samples": packed.size(0), "n_rays": info.size(0)}
         return self.last
 
-    def _step_fused(self, packed, rgbs, info, grid_ready) -> Dict[str, float]:
+    def _step_fused(self, packed, rgbs, info) -> Dict[str, float]:
         """Same iteration through fused.FusedKPlanesStep: identical kernels and order, no autograd / glue ops."""
         n_glob = work = None
         if self.world > 1:  # ray count of the union batch: reduced while the forward runs
@@ -403,7 +431,7 @@ class Trainer:
         self.scheduler.step()
         self.train_step += 1
         if self._side is not None:
-            self._prefetch(grid_ready)
+            self._prefetch()
         self.last = {"loss": out["loss"], "n_samples": packed.size(0), "n_rays": info.size(0)}
         return self.last
 
