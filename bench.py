@@ -50,6 +50,20 @@ def measured_peaks():
     return 6650.0, 1590.0 / 2, "fallback"
 
 
+def set_blocking_sync(device_index: int) -> bool:
+    """cudaDeviceScheduleBlockingSync for this process's device, before its context exists: a host thread waiting for the
+    GPU sleeps instead of spinning.  With one process per GPU plus NCCL's proxy threads, eight spinning main threads on a
+    16-core host preempt each other for whole timeslices (we measured 30-60 ms stalls in the per-step-synchronised arm)."""
+    try:
+        import ctypes
+        import glob
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+        rt = ctypes.CDLL(cands[0] if cands else "libcudart.so")
+        return rt.cudaSetDevice(device_index) == 0 and rt.cudaSetDeviceFlags(4) == 0  # cudaDeviceScheduleBlockingSync
+    except Exception:
+        return False
+
+
 # ---- synthetic scene (SURVEY 8d config 2) -------------------------------------------------------
 def make_scene(n_rays: int, seed: int):
     from tinynerf_b200 import synthetic
@@ -257,6 +271,9 @@ def main():
     import torch.distributed as dist
     from tinynerf_b200 import _lib, synthetic
     from tinynerf_b200.run import RayStore, TrainConfig, Trainer
+    # opt-in (TNF_BLOCKING_SYNC=1): measured at 8 ranks it trades the 30-60 ms scheduling stalls of the per-step-synchronised
+    # arm (e2e 268 -> 468 M samples/s) for wake-up latency on every wait (value arm 746 -> 663 M samples/s)
+    blocking_sync = set_blocking_sync(local_rank) if os.environ.get("TNF_BLOCKING_SYNC") == "1" else False
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -377,7 +394,7 @@ def main():
             "config": {"workload": "kplanes_aabb_2e18", "rays_per_chunk": BATCH, "samples_per_ray": N_SAMPLES,
                        "packed_samples_per_step_per_gpu": round(n / args.steps / world), "grid": "128^3 analytic ball+torus",
                        "l2": "inputs change every step (fresh rays; 396 MB of plane params+grads+Adam state stream through L2 > 126 MB)",
-                       "parallelism": f"ray-sharded dp{world}"},
+                       "parallelism": f"ray-sharded dp{world}", "host_wait": "blocking" if blocking_sync else "spin"},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": round(ms2 / args.steps, 4)},
             "gpu_launches": int(launches), "host_ms_per_step": round(host_ms[0], 4), "host_step_ms": {"value_arm": host_dist[0], "e2e_arm": host_dist[-1]}, "clocks": clk, "roofline": roof, "kernels": table,
