@@ -243,6 +243,21 @@ int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_dim, const 
                   float* const* h_out /*[host], optional*/, float* hs_out /*optional*/, float* rgb, float* sigma, int64_t m,
                   void* workspace, void* stream);
 
+/* The data-gradient ("dgrad") chain of both heads in one persistent kernel: from the gradients at the last hidden layers
+ * (dh3 [m,64] of the colour head, dhs [m,64] of the density head, as produced by tnf_head_bwd) to the gradient of the
+ * feature rows that feed both heads:
+ *   dh2 = (h2>0)*(dh3 W_c3), dh1 = (h1>0)*(dh2 W_c2), dh0 = (h0>0)*(dh1 W_c1),
+ *   dfeat = dh0 W_c0[:, feat_col0 : feat_col0+feat_dim] + dhs W_s0
+ * masks: [host] {h2, h1, h0} saved activations [m,64]; color_w: [host] {W_c0 [64,k0], W_c1, W_c2, W_c3 [64,64]};
+ * dh_out: optional [host] {dh2, dh1, dh0} [m,64] (inputs of the weight-gradient kernels); dfeat [m, ld_dfeat].
+ * Replaces five tnf_linear_bwd_data launches and the add of the two feature-gradient terms.  workspace:
+ * tnf_heads_bwd_workspace_bytes(feat_dim) bytes of device scratch, 16-byte aligned. */
+int64_t tnf_heads_bwd_workspace_bytes(int32_t feat_dim);
+int tnf_heads_bwd_data(const float* dh3, const float* dhs, const float* const* masks /*[host]*/,
+                       const float* const* color_w /*[host]*/, int32_t k0, int32_t feat_col0, const float* sigma_w0,
+                       int32_t feat_dim, float* const* dh_out /*[host], optional*/, float* dfeat, int64_t ld_dfeat, int64_t m,
+                       void* workspace, void* stream);
+
 /* ---- a18: compositing (segment sums over packed rays) -----------------------------------------
  * Replaces the index_add_ block of NerfRenderer.forward (src/core.py:256-265; the reference's own
  * "TODO: cuda kernel this"):  rgb_ray = sum_k w_k*rgb_k ; opacity = sum_k w_k ;

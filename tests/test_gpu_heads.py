@@ -68,3 +68,38 @@ def test_heads_fwd_matches_float64_and_per_layer_kernels(n):
     with torch.no_grad():
         assert torch.allclose(sig(feats).ravel(), sigma, rtol=2e-5, atol=1e-6)
         assert torch.allclose(col(feats, dirs), rgb, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 129, 300, 148 * 128 + 5, 2 * 148 * 128 + 77, 1 << 18])
+def test_heads_bwd_data_matches_float64(n):
+    """tnf_heads_bwd_data (the data-gradient chain of both heads in one kernel) against a float64 evaluation."""
+    torch.manual_seed(1000 + n)
+    lib = _lib.load()
+    F, K0, col0 = 96, 147, 51
+    dh3 = torch.randn(n, 64, device=DEV)
+    dhs = torch.randn(n, 64, device=DEV)
+    hmask = [torch.randn(n, 64, device=DEV).clamp_min(0.0) for _ in range(3)]        # h2, h1, h0 (post-ReLU: ~half zero)
+    W = [torch.randn(64, K0, device=DEV) / 8] + [torch.randn(64, 64, device=DEV) / 8 for _ in range(3)]   # W0..W3
+    Ws0 = torch.randn(64, F, device=DEV) / 8
+    dh_out = [torch.full((n, 64), float("nan"), device=DEV) for _ in range(3)]
+    dfeat = torch.full((n, F), float("nan"), device=DEV)
+    ws = torch.empty(int(lib.tnf_heads_bwd_workspace_bytes(F)) // 4, device=DEV)
+    tab = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    _lib.call("tnf_heads_bwd_data", dh3.data_ptr(), dhs.data_ptr(), tab(hmask), tab(W), K0, col0, Ws0.data_ptr(), F, tab(dh_out),
+              dfeat.data_ptr(), F, n, ws.data_ptr(), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    d = dh3.double()
+    want = []
+    for layer, m in zip((3, 2, 1), hmask):
+        d = (d @ W[layer].double()) * (m > 0)
+        want.append(d)
+    feat = d @ W[0].double()[:, col0:col0 + F] + dhs.double() @ Ws0.double()
+
+    def close(a, b, what):
+        err = (a.double() - b).abs()
+        tol = 1e-5 * b.abs() + 3e-6 * b.abs().max()   # entries are sums with cancellation: the floor scales with the tensor
+        assert bool((err <= tol).all()), f"{what}: worst excess {(err - tol).max().item():.3e} (max |ref| {b.abs().max().item():.3e})"
+
+    for i in range(3):
+        close(dh_out[i], want[i], f"dh{2 - i}")
+    close(dfeat, feat, "dfeat")

@@ -108,6 +108,12 @@ class FusedKPlanesStep:
             self._sw, self._sb = tab([l.weight for l in self.sig_lin]), tab([l.bias for l in self.sig_lin])
             nbytes = int(_lib.load().tnf_heads_workspace_bytes(self.feat, self.xc_width))
             self._heads_ws = torch.empty(nbytes // 4, device=self.dev)
+            # ... and their data-gradient chain in one kernel (tnf_heads_bwd_data); TNF_FUSED_HEADS_BWD=0 keeps the per-layer path
+            self.fused_heads_bwd = os.environ.get("TNF_FUSED_HEADS_BWD", "1") != "0" and self.feat % 32 == 0 and self.feat <= 128
+            if self.fused_heads_bwd:
+                self._heads_bwd_ws = torch.empty(int(_lib.load().tnf_heads_bwd_workspace_bytes(self.feat)) // 4, device=self.dev)
+        else:
+            self.fused_heads_bwd = False
 
     def attach_grads(self) -> None:
         """p.grad = its view of the flat gradient buffer (undoes optimizer.zero_grad(set_to_none=True))."""
@@ -230,20 +236,29 @@ class FusedKPlanesStep:
             dh = [ws[f"dh{i}"] for i in range(nh)]   # dh[i] = gradient wrt the pre-activation of colour layer i
             call("tnf_head_bwd", P(ws[f"h{nh - 1}"]), hc_w, P(cl[-1].weight), P(ws["rgb"]), P(ws["grgb"]), P(dh[nh - 1]),
                  G(cl[-1].weight), G(cl[-1].bias), n, hc_w, 3, 2, st, nbytes=4 * n * (2 * hc_w + 6))
-            for i in range(nh - 1, 0, -1):
-                inp = ws[f"h{i - 1}"]
-                dgrad(P(dh[i]), hc_w, cl[i], P(dh[i - 1]), hc_w, P(inp), hc_w)
-            dgrad(P(dh[0]), hc_w, cl[0], P(ws["dxc"]), xld, None, 0)
+            if not self.fused_heads_bwd:
+                for i in range(nh - 1, 0, -1):
+                    inp = ws[f"h{i - 1}"]
+                    dgrad(P(dh[i]), hc_w, cl[i], P(dh[i - 1]), hc_w, P(inp), hc_w)
+                dgrad(P(dh[0]), hc_w, cl[0], P(ws["dxc"]), xld, None, 0)
             # density branch: weights backward, fused output layer + truncated_exp, hidden layer
             call("tnf_weights_bwd", P(ws["sigma"]), P(steps), sstride, P(info), P(ws["w"]), P(ws["gw"]), P(ws["gsigma"]), n, r,
                  flags, _lib.ptr(status), st, nbytes=20 * n + 8 * r, extra_kernels=0 if flags else 3)
             call("tnf_head_bwd", P(ws["hs"]), hs_w, P(sl[1].weight), P(ws["sigma"]), P(ws["gsigma"]), P(ws["dhs"]),
                  G(sl[1].weight), G(sl[1].bias), n, hs_w, 1, 1, st, nbytes=4 * n * (2 * hs_w + 2))
-            dgrad(P(ws["dhs"]), hs_w, sl[0], P(ws["dfeat"]), F, None, 0)
-            # the features feed both heads: d feats = d(sigma branch) + d(colour input)[:, feature columns]
             dfeat = ws["dfeat"][:n]
-            torch.add(dfeat, ws["dxc"][:n, xw - F:xw], out=dfeat)
-            _lib.launch_count += 1
+            if self.fused_heads_bwd:
+                # the whole data-gradient chain of both heads, down to the feature rows, in one kernel
+                masks = (C.c_void_p * 3)(*[P(ws[f"h{i}"]) for i in (2, 1, 0)])
+                dh_out = (C.c_void_p * 3)(*[P(dh[i]) for i in (2, 1, 0)])
+                call("tnf_heads_bwd_data", P(dh[3]), P(ws["dhs"]), masks, self._cw, xw, xw - F, P(sl[0].weight), F, dh_out,
+                     P(ws["dfeat"]), F, n, P(self._heads_bwd_ws), st, nbytes=4 * n * (2 * 64 + 3 * 64 + 3 * 64 + F),
+                     flops=2 * n * 64 * (3 * 64 + 2 * F))
+            else:
+                dgrad(P(ws["dhs"]), hs_w, sl[0], P(ws["dfeat"]), F, None, 0)
+                # the features feed both heads: d feats = d(sigma branch) + d(colour input)[:, feature columns]
+                torch.add(dfeat, ws["dxc"][:n, xw - F:xw], out=dfeat)
+                _lib.launch_count += 1
             # plane gradients: scatter-add of the data term, then TV value + gradient (loss += tv_alpha * loss_tv,
             # src/run.py:254-255) from one pass over the planes
             call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
