@@ -215,6 +215,18 @@ def weights_microbench(dev, logn: int, peak: float):
     return out
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r01_ncu_full.md, M = 2^18 rows / N ~ 2^18 samples): the `traffic` of the roofline object.
+NCU_TRAFFIC_BYTES = {
+    "tnf_linear_bwd_weight": 171.5e6,   # wgrad_kernel, 96-wide layer instance: 167.9 MB read + 3.6 MB written
+    "tnf_heads_fwd": 548.2e6,           # 257.0 + 291.2 MB
+    "tnf_kplanes_bwd": 652.8e6,         # ~0.5 GB + 152.8 MB
+    "tnf_kplanes_fwd": 294.4e6,         # ~0.2 GB + 94.4 MB
+    "tnf_linear_bwd_data": 171.3e6,
+    "tnf_linear_fwd": 133.0e6,
+}
+
+
 def summarise_profile(records, peak, tf32_peak):
     """records: (name, start, end, bytes, flops) -> per-entry-point totals and the dominant one."""
     agg = {}
@@ -386,7 +398,8 @@ def main():
     if dom:
         t = table[dom]
         roof = {"kernel": dom, "bound": "hbm", "achieved": t["GB/s"], "peak": peak, "unit": "GB/s", "frac": t["frac"],
-                "traffic": None, "peak_source": peak_src, "avg_us": t["avg_us"],
+                "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r01_ncu_full.md" if dom in NCU_TRAFFIC_BYTES else None,
+                "peak_source": peak_src, "avg_us": t["avg_us"],
                 "alg_bytes_per_launch": int(t["alg_MB_per_launch"] * 1e6)}
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
