@@ -9,7 +9,7 @@ buf = torch.zeros(32, dtype=torch.int64, device="cuda")
 lib.tnf_debug_role_timing.argtypes = [C.c_void_p]
 assert lib.tnf_debug_role_timing(buf.data_ptr()) == 0
 m = 1 << 18
-for (k, n) in ((64, 64), (148, 64)):
+for (k, n) in ((64, 64), (96, 64), (148, 64)):
     ld = (k + 3) // 4 * 4
     x = torch.randn(m, ld, device="cuda"); dy = torch.randn(m, n, device="cuda")
     dw = torch.zeros(n, k, device="cuda"); db = torch.zeros(n, device="cuda")

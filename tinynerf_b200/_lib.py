@@ -7,11 +7,13 @@ from PyTorch's autograd thread (the reference's backward runs there, src/core.py
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "libtinynerf_b200.so"
+# TNF_LIB_PATH: diagnostics only (an instrumented build of the same sources, scripts/build_timing_lib.py)
+_LIB_PATH = Path(os.environ.get("TNF_LIB_PATH") or Path(__file__).resolve().parent / "libtinynerf_b200.so")
 _lib = None
 
 c_f32p = C.c_void_p  # device pointers are passed as integers

@@ -386,8 +386,11 @@ class RayProvider:
             n = int(h["n_dev"].item())
         info = h["info"][:R]
         with torch.cuda.device(dev):
-            packed = torch.empty(n, 7, device=dev)
-            steps = torch.empty(n, device=dev)
+            # row capacity rounded up to 16 Ki samples: batch sizes wander by a few percent, and a request a little larger
+            # than every cached block makes the caching allocator cudaMalloc (which waits for all queued GPU work)
+            cap = (n + 16383) & ~16383
+            packed = torch.empty(cap, 7, device=dev)[:n]
+            steps = torch.empty(cap, device=dev)[:n]
             _lib.call("tnf_march_pack", C.byref(h["p"]), h["rays_o"].data_ptr(), h["rays_d"].data_ptr(), R,
                       h["info_offset"], h["mask_bits"].data_ptr(), info.data_ptr(), packed.data_ptr(), steps.data_ptr(),
                       None, n, _lib.stream_ptr(), nbytes=24 * R + 8 * R + 4 * R * h["words"] + 32 * n)

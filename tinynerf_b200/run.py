@@ -155,6 +155,10 @@ class TrainConfig:
                                         # in flight, so a host hiccup on one rank is absorbed instead of stalling a collective)
     fused_tv_grad: bool = True          # TV gradient written straight into the plane grads (no autograd temporaries)
     fused_step: bool = True             # K-Planes: forward+loss+backward as one C-ABI call sequence (fused.py), no autograd
+    max_inflight_steps: int = 3         # the host enqueues at most this many iterations ahead of the GPU (0 = unbounded): a
+                                        # free-running host ends up a launch-queue's worth of steps ahead, every batch it has
+                                        # marched stays allocated until the GPU gets there, and the allocator's cudaMalloc
+                                        # calls then wait for the whole queue
     manual_gc: bool = True              # collect Python garbage at the occupancy-update cadence instead of at random steps
                                         # (a generation-2 pause on ONE rank stalls every rank at the next collective)
     occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
@@ -222,6 +226,7 @@ class Trainer:
         self.post_update = None         # optional callable(trainer) run right after every occupancy update
         self._gc_frozen = False
         self._queue: List = []          # prefetched (batch, done event), oldest first
+        self._inflight: List = []       # end-of-iteration events of the iterations enqueued and not yet waited for
         self._grid_event = None         # recorded after the latest occupancy update: batches marched later must see it
         self.last: Dict[str, float] = {}
 
@@ -377,6 +382,9 @@ class Trainer:
                 self._gc_frozen = True
             elif self.train_step % self.occupancy_grid_updates == 0:
                 gc.collect()
+        if self.cfg.max_inflight_steps > 0 and self.device.type == "cuda":
+            while len(self._inflight) >= self.cfg.max_inflight_steps:
+                self._inflight.pop(0).synchronize()
         packed, rgbs, info = self._take_batch()
         if not self.renderer.training:
             self.renderer.train()
@@ -413,12 +421,17 @@ class Trainer:
         self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
+        self._mark_enqueued()
         if self._side is not None:
             # everything above is enqueued; the coming batches are marched on the side stream while the GPU is still
             # busy with this step's backward + optimiser, so their host sync no longer stalls the step
             self._prefetch()
         self.last = {"loss": loss.detach(), "n_samples": packed.size(0), "n_rays": info.size(0)}
         return self.last
+
+    def _mark_enqueued(self) -> None:
+        if self.cfg.max_inflight_steps > 0 and self.device.type == "cuda":
+            self._inflight.append(torch.cuda.current_stream(self.device).record_event())
 
     def _step_fused(self, packed, rgbs, info) -> Dict[str, float]:
         """Same iteration through fused.FusedKPlanesStep: identical kernels and order, no autograd / glue ops."""
@@ -430,6 +443,7 @@ class Trainer:
         self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
+        self._mark_enqueued()
         if self._side is not None:
             self._prefetch()
         self.last = {"loss": out["loss"], "n_samples": packed.size(0), "n_rays": info.size(0)}
