@@ -352,9 +352,14 @@ def main():
             n, ms = float(n_all), float(ms_all)
         return n, ms, recs, _lib.launch_count - l0
 
+    # Before the W warm-up steps of each arm the trainer runs one full occupancy-update cycle untimed ("settle_steps"): the
+    # update iteration allocates its temporaries while several steps are in flight, and the first time that happens the
+    # caching allocator has to cudaMalloc (milliseconds, once per process) -- a 64-step window would otherwise carry it.
+    settle = 0 if os.environ.get("TNF_BENCH_NO_SETTLE") == "1" else (1 << 16) // BATCH + 2
+
     # ---- device-resident arm (value) ----
     tr = make_trainer(host=False)
-    for _ in range(args.warmup):
+    for _ in range(settle + args.warmup):
         one_step(tr, False)
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -371,7 +376,7 @@ def main():
 
     # ---- end-to-end arm (host buffers, H2D per batch, loss read back) ----
     tr = make_trainer(host=True)
-    for _ in range(args.warmup):
+    for _ in range(settle + args.warmup):
         one_step(tr, True)
     h0 = tr.store.h2d_bytes
     n2, ms2, _, _ = timed(tr, args.steps, True, profile=False)
@@ -407,7 +412,8 @@ def main():
             "config": {"workload": "kplanes_aabb_2e18", "rays_per_chunk": BATCH, "samples_per_ray": N_SAMPLES,
                        "packed_samples_per_step_per_gpu": round(n / args.steps / world), "grid": "128^3 analytic ball+torus",
                        "l2": "inputs change every step (fresh rays; 396 MB of plane params+grads+Adam state stream through L2 > 126 MB)",
-                       "parallelism": f"ray-sharded dp{world}", "host_wait": "blocking" if blocking_sync else "spin"},
+                       "parallelism": f"ray-sharded dp{world}", "host_wait": "blocking" if blocking_sync else "spin",
+                       "settle_steps": settle},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": round(ms2 / args.steps, 4)},
             "gpu_launches": int(launches), "host_ms_per_step": round(host_ms[0], 4), "host_step_ms": {"value_arm": host_dist[0], "e2e_arm": host_dist[-1]}, "clocks": clk, "roofline": roof, "kernels": table,

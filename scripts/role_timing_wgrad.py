@@ -19,4 +19,4 @@ for (k, n) in ((64, 64), (96, 64), (148, 64)):
         _lib.call("tnf_linear_bwd_weight", dy.data_ptr(), n, x.data_ptr(), ld, dw.data_ptr(), db.data_ptr(), m, n, k, _lib.stream_ptr())
         e.record(); torch.cuda.synchronize()
     v = buf.tolist()
-    print(f"K={k}: {s.elapsed_time(e)*1e3:.1f} us | mma warp: wait_yfull {v[8]} wait_xfull {v[9]} issue {v[11]} total {v[10]} | wait done {v[12]} | flush {v[13]}")
+    print(f"K={k}: {s.elapsed_time(e)*1e3:.1f} us | mma warp: wait_yfull {v[8]} wait_xfull {v[9]} issue {v[11]} total {v[10]} | loader 0: issue {v[16]} land {v[17]} pair {v[18]} (aempty {v[20]}) x {v[19]} (lempty {v[21]})")

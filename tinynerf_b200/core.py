@@ -245,7 +245,10 @@ class OccupancyGrid(torch.nn.Module):
                     u = torch.stack([torch.rand(H, W, 3) for _ in range(z0, z1)]).view(-1, 3).to(dev)
                 else:
                     u = None
-                coords = torch.empty(n, 3, device=dev)
+                ws = getattr(self, "_coords_ws", None)   # grow-only: the update allocates nothing in steady state
+                if ws is None or ws.size(0) < n or ws.device != dev:
+                    ws = self._coords_ws = torch.empty(n, 3, device=dev)
+                coords = ws[:n]
                 _lib.call("tnf_occ_update_coords", D, H, W, z0 * per_slice, n, _lib.ptr(u), 0x7E57,
                           self._update_calls * D * per_slice, coords.data_ptr(), stream, nbytes=12 * n)
                 sigma = sigma_fn(coords).reshape(-1).float().contiguous()

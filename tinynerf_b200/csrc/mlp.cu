@@ -569,14 +569,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
 // global loads in flight: it is bound by load latency, not by HBM or the tensor pipe.  Here the loader warps transpose the
 // raw dY tile shared memory -> registers -> tcgen05.st (thread == TMEM lane == one output feature, hi or lo half; the
 // column sums for the bias gradient fall out of the same registers), so shared memory holds only a raw dY staging ring
-// (2 x 32 KB) and a five-stage X ring: four items (64-80 KB per SM) of loads in flight, and the MMA reads one operand from
+// (2 x 32 KB), an eight-slot ring of X hi images (the cp.async landing zones) and two X lo slots (the lo image is made
+// just before the tensor core reads it and lives only that long; the [X_hi | X_lo] operand is addressed with a per-atom
+// leading-dimension offset): five to six items (~100 KB per SM) of loads in flight, and the MMA reads one operand from
 // shared memory instead of two (33 instead of 48 cycles per 128x64x8 MMA, scripts/ubench/mma_bench.cu).
 //   warps 0-7 loaders: item sequence per tile = [dY pair][X atom 0]..[X atom kx-1], each one cp.async group, kTsDist ahead
 //   warp  8   MMA    : per X atom j: D[128, 64j..64j+64) += A_tmem[128, 128 samples] * [X_hi | X_lo] (16 k-steps), D in TMEM
 //                      for the whole kernel, flushed like the stacked kernel (quadrants summed, one reduction per 16 B)
-constexpr int kTsXStages = 5;
-constexpr int kTsYSlots = 2;
-constexpr int kTsDist = 4;
+constexpr int kTsXStages = 8;   // X hi slots (16 KB)
+constexpr int kTsXLo = 2;       // X lo slots (16 KB)
+constexpr int kTsYSlots = 2;    // raw dY pair slots (32 KB)
+constexpr int kTsDist = 6;
 
 template <int NT>
 __device__ __forceinline__ void cp_async_atom_raw(const float* __restrict__ g, long long ld, long long row0, long long rows,
@@ -600,18 +603,20 @@ __device__ __forceinline__ void loaders_bar_sync() { asm volatile("bar.sync 1, %
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_ts_kernel(const LinArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t s_xfull[kTsXStages], s_xempty[kTsXStages], s_afull[2], s_aempty[2], s_done;
+  __shared__ uint64_t s_xfull[kTsXStages], s_xempty[kTsXStages], s_lempty[kTsXLo], s_afull[2], s_aempty[2], s_done;
   __shared__ uint32_t s_tmem;
   __shared__ float s_db[64];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kx = (A.K + 31) >> 5;       // X atoms per tile
   const int n_sets = A.raw;             // A sets in tensor memory (2 when 2*128 + 64*kx <= 512 columns)
-  constexpr int S = kTsXStages;
+  constexpr int S = kTsXStages, L = kTsXLo;
   uint8_t* yraw = smem;                                  // raw dY pair slots: [atom 0 (features 0-31)][atom 1]
-  uint8_t* xst = smem + kTsYSlots * 2 * kAtomBytes;      // X stage s: hi image at +s*2*kAtomBytes, lo right after
+  uint8_t* xhi = smem + kTsYSlots * 2 * kAtomBytes;      // X hi slot s at +s*kAtomBytes
+  uint8_t* xlo = xhi + S * kAtomBytes;                   // X lo slot l at +l*kAtomBytes (above every hi slot)
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&s_xfull[s], kWgLoadThreads); mbar_init(&s_xempty[s], 1); }
+    for (int l = 0; l < L; ++l) mbar_init(&s_lempty[l], 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&s_afull[i], kWgLoadThreads); mbar_init(&s_aempty[i], 1); }
     mbar_init(&s_done, 1);
     fence_mbar_init();
@@ -644,25 +649,30 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_ts_kernel(const LinArgs A
         } else {
           const int xi = tl * kx + item - 1;
           mbar_wait(&s_xempty[xi % S], ((xi / S) & 1) ^ 1);   // the MMAs that read the stage's previous atom have completed
-          cp_async_atom_swz<kWgLoadThreads>(A.X2, A.ldx2, row0, A.M, 32 * (item - 1), A.K, tid, xst + (xi % S) * 2 * kAtomBytes, true);
+          cp_async_atom_swz<kWgLoadThreads>(A.X2, A.ldx2, row0, A.M, 32 * (item - 1), A.K, tid, xhi + (xi % S) * kAtomBytes, true);
         }
       }
       cp_async_commit();
     };
-    // items in flight: a dY slot is rewritten two tiles later (after the barrier that ends its transposition), an X stage
+    // items in flight: a dY slot is rewritten two tiles later (after the barrier that ends its transposition), an X hi slot
     // S atoms later (after atoms this loop has already handed to the MMA warp) -- neither can wait on a later item
     int dist = kTsDist;
     if (dist > 2 * per_tile - 1) dist = 2 * per_tile - 1;
     if (dist > S - 1) dist = S - 1;
     for (int it = 0; it < dist; ++it) issue(it);
+    long long c_issue = 0, c_land = 0, c_pair = 0, c_x = 0, c_aempty = 0, c_lempty = 0;
+    Tm tm;
     for (int it = 0; it < n_items; ++it) {
       const int tl = it / per_tile, item = it - tl * per_tile;
+      tm.start();
       issue(it + dist);
+      tm.stop(c_issue); tm.start();
       cp_async_wait_dyn(dist);
+      tm.stop(c_land); tm.start();
       if (item == 0) {
         loaders_bar_sync();                              // every loader's part of the pair has landed
         const int set = tl % n_sets;
-        mbar_wait(&s_aempty[set], ((tl / n_sets) & 1) ^ 1);   // the MMAs that read this A set have completed
+        { Tm t2; t2.start(); mbar_wait(&s_aempty[set], ((tl / n_sets) & 1) ^ 1); t2.stop(c_aempty); }   // the MMAs that read this A set have completed
         tc_fence_after();
         const uint8_t* src = yraw + (tl % kTsYSlots) * 2 * kAtomBytes + (q & 1) * kAtomBytes + lane * 4;
         const uint32_t taddr = tmem_a + ((uint32_t)(32 * q) << 16) + 128 * set + s0;
@@ -681,14 +691,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_ts_kernel(const LinArgs A
         tc_fence_before();
         mbar_arrive(&s_afull[set]);
         loaders_bar_sync();                              // the raw slot may be rewritten (by the pair two tiles ahead)
+        tm.stop(c_pair);
       } else {
         const int xi = tl * kx + item - 1;
-        uint8_t* hi = xst + (xi % S) * 2 * kAtomBytes;
-        make_lo_atom<kWgLoadThreads>(hi, hi + kAtomBytes, tid, true, nullptr);
+        { Tm t2; t2.start(); mbar_wait(&s_lempty[xi % L], ((xi / L) & 1) ^ 1); t2.stop(c_lempty); }   // the MMAs that read the lo slot's previous image have completed
+        make_lo_atom<kWgLoadThreads>(xhi + (xi % S) * kAtomBytes, xlo + (xi % L) * kAtomBytes, tid, true, nullptr);
         fence_async_smem();
         mbar_arrive(&s_xfull[xi % S]);
+        tm.stop(c_x);
       }
     }
+    if (g_dbg && tid == 0 && blockIdx.x == 0) { g_dbg[16] = c_issue; g_dbg[17] = c_land; g_dbg[18] = c_pair; g_dbg[19] = c_x; g_dbg[20] = c_aempty; g_dbg[21] = c_lempty; }
     cp_async_wait<0>();
     if (A.db && is_hi) atomicAdd(&s_db[32 * (q & 1) + lane], bsum);
   } else {
@@ -706,12 +719,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_ts_kernel(const LinArgs A
         const long long ti = TNF_CLK();
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t xh = smem_u32(xst + s * 2 * kAtomBytes);
+          const uint32_t xh = smem_u32(xhi + s * kAtomBytes);
+          const uint32_t lbo = smem_u32(xlo + (xi % L) * kAtomBytes) - xh;   // MN block 1 of the B operand = the lo image
           const uint32_t aa = tmem_a + 128 * set;
 #pragma unroll 4
           for (int kk = 0; kk < 16; ++kk)
-            mma_tf32_ts(tmem_d + 64 * j, aa + 8 * kk, desc_mnmajor(xh, kk), idesc, !(tl == 0 && kk == 0));
+            mma_tf32_ts(tmem_d + 64 * j, aa + 8 * kk, desc_mnmajor(xh, kk, lbo), idesc, !(tl == 0 && kk == 0));
           mma_commit(&s_xempty[s]);
+          mma_commit(&s_lempty[xi % L]);
           if (j == kx - 1) mma_commit(&s_aempty[set]);
         }
         __syncwarp();
@@ -754,10 +769,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_ts_kernel(const LinArgs A
 //   dpre[o] = dOut[o] * act'(.) ; dH[m,j] = (H[m,j] > 0) * sum_o dpre[o] * Wh[o,j] ; dWh[o,j] += dpre[o]*H[m,j] ; dbh[o] += dpre[o]
 // act: 1 = truncated_exp(x-1) (backward uses exp(clamp(x-1,-15,15)), src/models.py:52-53; out = exp(x-1) is given),
 //      2 = sigmoid (out given).  One warp handles 32 rows at a time; lanes own columns j, j+32 (+64, +96).
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ H, long long ldh, const float* __restrict__ Wh,
+constexpr int kHbU = 4;
+template <int NH>  // n_head
+__global__ void __launch_bounds__(256, 3) head_bwd_kernel(const float* __restrict__ H, long long ldh, const float* __restrict__ Wh,
                                                        const float* __restrict__ out, const float* __restrict__ dout,
                                                        float* __restrict__ dH, float* __restrict__ dWh, float* __restrict__ dbh,
-                                                       long long M, int N, int n_head, int act) {
+                                                       long long M, int N, int act) {
+  constexpr int n_head = NH;
   // N/4 lanes per row (one float4 of H each), 32/(N/4) rows per warp iteration; N in {32, 64, 128}
   __shared__ float s_dw[4 * 128];
   __shared__ float s_dbh[4];
@@ -771,22 +789,40 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   const int c4 = (lane % lpr) * 4;   // first column of this lane
   const long long warps_total = (long long)gridDim.x * 8;
   const long long wid = blockIdx.x * 8LL + (tid >> 5);
-  float4 wreg[4], dwacc[4];
+  float4 wreg[NH], dwacc[NH];
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    wreg[o] = (o < n_head) ? __ldg(reinterpret_cast<const float4*>(Wh + o * N + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int o = 0; o < NH; ++o) {
+    wreg[o] = __ldg(reinterpret_cast<const float4*>(Wh + o * N + c4));
     dwacc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long m0 = wid * rpw; m0 < M; m0 += warps_total * rpw) {
-    const long long m = m0 + sub;
-    if (m >= M) continue;
-    float dpre[4];
+  float dbacc[NH];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      float d = 0.f;
-      if (o < n_head) {
-        const float y = __ldg(out + m * n_head + o), g = __ldg(dout + m * n_head + o);
+  for (int o = 0; o < NH; ++o) dbacc[o] = 0.f;
+  // kHbU independent rows per lane and iteration: all their loads are issued before the first use, so a warp keeps
+  // kHbU x 512 B (+ the out/dout scalars) in flight instead of one row's worth
+  for (long long m0 = wid * rpw * kHbU; m0 < M; m0 += warps_total * rpw * kHbU) {
+    float4 h[kHbU];
+    float yv[kHbU][NH], gv[kHbU][NH];
+#pragma unroll
+    for (int u = 0; u < kHbU; ++u) {
+      const long long m = m0 + u * rpw + sub;
+      const bool ok = m < M;
+      h[u] = ok ? ld_stream_f4(H + m * ldh + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < NH; ++o) {
+        yv[u][o] = ok ? __ldg(out + m * n_head + o) : 0.f;
+        gv[u][o] = ok ? __ldg(dout + m * n_head + o) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kHbU; ++u) {
+      const long long m = m0 + u * rpw + sub;
+      if (m >= M) continue;
+      float dpre[NH];
+#pragma unroll
+      for (int o = 0; o < NH; ++o) {
+        const float y = yv[u][o], g = gv[u][o];
+        float d;
         if (act == 1) {
           // y = exp(x-1); backward multiplies by exp(clamp(x-1, -15, 15)) (src/models.py:52-53)
           d = g * fminf(fmaxf(y, 3.0590232050182579e-07f), 3269017.372472110639f);
@@ -795,24 +831,23 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
         } else {
           d = g;
         }
+        dpre[o] = d;
+        if (lane % lpr == 0) dbacc[o] += d;
       }
-      dpre[o] = d;
-      if (lane % lpr == 0) dbacc[o] += d;
-    }
-    const float4 h = __ldg(reinterpret_cast<const float4*>(H + m * ldh + c4));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      acc.x = __fmaf_rn(dpre[o], wreg[o].x, acc.x); acc.y = __fmaf_rn(dpre[o], wreg[o].y, acc.y);
-      acc.z = __fmaf_rn(dpre[o], wreg[o].z, acc.z); acc.w = __fmaf_rn(dpre[o], wreg[o].w, acc.w);
-      dwacc[o].x = __fmaf_rn(dpre[o], h.x, dwacc[o].x); dwacc[o].y = __fmaf_rn(dpre[o], h.y, dwacc[o].y);
-      dwacc[o].z = __fmaf_rn(dpre[o], h.z, dwacc[o].z); dwacc[o].w = __fmaf_rn(dpre[o], h.w, dwacc[o].w);
+      for (int o = 0; o < NH; ++o) {
+        acc.x = __fmaf_rn(dpre[o], wreg[o].x, acc.x); acc.y = __fmaf_rn(dpre[o], wreg[o].y, acc.y);
+        acc.z = __fmaf_rn(dpre[o], wreg[o].z, acc.z); acc.w = __fmaf_rn(dpre[o], wreg[o].w, acc.w);
+        dwacc[o].x = __fmaf_rn(dpre[o], h[u].x, dwacc[o].x); dwacc[o].y = __fmaf_rn(dpre[o], h[u].y, dwacc[o].y);
+        dwacc[o].z = __fmaf_rn(dpre[o], h[u].z, dwacc[o].z); dwacc[o].w = __fmaf_rn(dpre[o], h[u].w, dwacc[o].w);
+      }
+      st_stream_f4(dH + m * ldh + c4, make_float4(h[u].x > 0.f ? acc.x : 0.f, h[u].y > 0.f ? acc.y : 0.f,
+                                                  h[u].z > 0.f ? acc.z : 0.f, h[u].w > 0.f ? acc.w : 0.f));
     }
-    *reinterpret_cast<float4*>(dH + m * ldh + c4) =
-        make_float4(h.x > 0.f ? acc.x : 0.f, h.y > 0.f ? acc.y : 0.f, h.z > 0.f ? acc.z : 0.f, h.w > 0.f ? acc.w : 0.f);
   }
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
+  for (int o = 0; o < NH; ++o) {
     atomicAdd(&s_dw[o * 128 + c4 + 0], dwacc[o].x); atomicAdd(&s_dw[o * 128 + c4 + 1], dwacc[o].y);
     atomicAdd(&s_dw[o * 128 + c4 + 2], dwacc[o].z); atomicAdd(&s_dw[o * 128 + c4 + 3], dwacc[o].w);
     atomicAdd(&s_dbh[o], dbacc[o]);
@@ -949,7 +984,7 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
     // 64-wide layers: A operand in tensor memory (wgrad_ts_kernel)
     const int kx = (k + 31) / 32;
     A.raw = (2 * 128 + 64 * kx <= 512) ? 2 : 1;
-    const size_t smem = (size_t)(kTsYSlots + kTsXStages) * 2 * kAtomBytes + 1024;
+    const size_t smem = (size_t)(2 * kTsYSlots + kTsXStages + kTsXLo) * kAtomBytes + 1024;
     static thread_local bool configured_ts = false;
     if (!configured_ts) {
       TNF_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -1002,9 +1037,16 @@ extern "C" int tnf_head_bwd(const float* h, int64_t ldh, const float* head_w, co
               "h/dh/head_w must be 16-byte aligned with ldh %% 4 == 0");
   if (m == 0) return TNF_OK;
   TNF_REQUIRE(h && head_w && out && dout && dh && dhead_w && dhead_b, "null pointer");
-  const int grid = (int)(ceil_div(m, 8 * 8) < 8 * sm_count() ? ceil_div(m, 8 * 8) : 8 * sm_count());
-  head_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ldh, head_w, out, dout, dh, dhead_w, dhead_b, m, n,
-                                                                         n_head, head_act);
+  // one resident wave: every block strides over the rows, so the per-block flush of the head-weight partials is paid once
+  using HeadBwd = void (*)(const float*, long long, const float*, const float*, const float*, float*, float*, float*, long long, int, int);
+  static const HeadBwd kerns[4] = {head_bwd_kernel<1>, head_bwd_kernel<2>, head_bwd_kernel<3>, head_bwd_kernel<4>};
+  static thread_local int occ[4] = {0, 0, 0, 0};
+  const HeadBwd kern = kerns[n_head - 1];
+  if (!occ[n_head - 1]) TNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[n_head - 1], kern, 256, 0));
+  const int64_t rows_per_iter = 8 * (32 / (n / 4)) * kHbU;
+  const int64_t want = ceil_div(m, rows_per_iter), cap = (int64_t)(occ[n_head - 1] > 0 ? occ[n_head - 1] : 1) * sm_count();
+  const int grid = (int)(want < cap ? want : cap);
+  kern<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ldh, head_w, out, dout, dh, dhead_w, dhead_b, m, n, head_act);
   TNF_LAUNCH_CHECK("head_bwd_kernel");
   return TNF_OK;
 }

@@ -185,9 +185,10 @@ __device__ __forceinline__ void cp_async_atom_swz(const float* __restrict__ g, l
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // pending in 0..4
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // pending in 0..6
   if (pending <= 0) cp_async_wait<0>(); else if (pending == 1) cp_async_wait<1>(); else if (pending == 2) cp_async_wait<2>();
-  else if (pending == 3) cp_async_wait<3>(); else cp_async_wait<4>();
+  else if (pending == 3) cp_async_wait<3>(); else if (pending == 4) cp_async_wait<4>(); else if (pending == 5) cp_async_wait<5>();
+  else cp_async_wait<6>();
 }
 // lo image of an atom from its hi image: every thread handles the 8 chunks it copied itself (no cross-thread hazard)
 template <int NT = 128>

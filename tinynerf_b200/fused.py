@@ -145,6 +145,29 @@ class FusedKPlanesStep:
             self._ws["loss"] = torch.zeros(1, device=self.dev)
             self._cap_r = cap
 
+    # ---- density only (the occupancy update's sigma_fn, src/run.py:249) ----------------------------
+    @torch.no_grad()
+    def density(self, coords: torch.Tensor) -> torch.Tensor:
+        """sigma_decoder(feature_module(coords)) for [n,3] contracted coordinates: the same two kernels the modules run,
+        on the iteration's own workspaces (no allocations, no torch glue).  Returns a view of the workspace that stays
+        valid until the next density() / forward_backward() call on this stream."""
+        _lib.require_cuda(coords, "coords")
+        if coords.dim() != 2 or coords.size(1) != 3 or coords.dtype != torch.float32 or not coords.is_contiguous():
+            raise RuntimeError("coords must be a contiguous [n,3] float32 tensor")
+        n = coords.size(0)
+        if n == 0:
+            return torch.empty(0, 1, device=self.dev)
+        self._reserve(n, 1)
+        ws, call, st = self._ws, _lib.call, _lib.stream_ptr()
+        F, l0, l1 = self.feat, self.sig_lin[0], self.sig_lin[1]
+        with torch.cuda.device(self.dev):
+            call("tnf_kplanes_fwd", self._plane_ptrs, self._res_scales, self.n_scales, self.channels, coords.data_ptr(), 3, n,
+                 ws["feats"].data_ptr(), st, nbytes=n * (12 + 4 * F) + self._plane_bytes)
+            call("tnf_linear_fwd", ws["feats"].data_ptr(), F, l0.weight.data_ptr(), l0.bias.data_ptr(), None, l0.out_features, n,
+                 l0.out_features, F, 1, l1.weight.data_ptr(), l1.bias.data_ptr(), ws["sigma"].data_ptr(), 1, 1, st,
+                 nbytes=4 * (n * (F + 1) + l0.out_features * F), flops=2 * n * l0.out_features * (F + 1))
+        return ws["sigma"][:n].view(n, 1)
+
     # ---- the iteration -----------------------------------------------------------------------------
     @torch.no_grad()
     def forward_backward(self, packed: torch.Tensor, info: torch.Tensor, target: torch.Tensor,

@@ -334,7 +334,10 @@ class Trainer:
     @torch.no_grad()
     def update_occupancy(self):
         og = self.occupancy_grid
-        sigma_fn = lambda t: self.renderer.sigma_decoder(self.renderer.feature_module(t))
+        if self._fused is not None:
+            sigma_fn = self._fused.density   # same kernels on the iteration's workspaces: no allocations in the update
+        else:
+            sigma_fn = lambda t: self.renderer.sigma_decoder(self.renderer.feature_module(t))
         if self.world == 1:
             og.update(sigma_fn)
             return
