@@ -46,7 +46,7 @@ def run(label, env=None, **kw):
 
 run("default")
 run("default again")
-run("wgrad SS (slower)", env={"TNF_WGRAD_SS": "1"})
+run("wgrad SS (slower)", env={"TNF_WGRAD": "ss"})
 run("no prefetch", prefetch=False)
 run("inflight unbounded", max_inflight_steps=0)
 run("inflight 2", max_inflight_steps=2)

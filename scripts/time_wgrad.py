@@ -14,11 +14,8 @@ for k, n in shapes:
     bufs[(k, n)] = (torch.randn(m, ld, device="cuda"), torch.randn(m, n, device="cuda"), torch.zeros(n, k, device="cuda"),
                     torch.zeros(n, device="cuda"), ld)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for mode in ("ss", "ts", "ss", "ts"):
-    if mode == "ss":
-        os.environ["TNF_WGRAD_SS"] = "1"
-    else:
-        os.environ.pop("TNF_WGRAD_SS", None)
+for mode in ("ss", "ts", "tma", "ts", "tma"):
+    os.environ["TNF_WGRAD"] = mode
     for k, n in shapes:
         x, dy, dw, db, ld = bufs[(k, n)]
         ts = []

@@ -20,7 +20,9 @@
 // one CTA's loads overlap the other's MMAs/epilogue; operands staged by all threads (LDG -> split -> STS),
 // one elected thread issues the MMAs, completion through tcgen05.commit -> mbarrier, accumulator read back
 // with tcgen05.ld (thread == TMEM lane == output row) for the fused bias / ReLU / head epilogue.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -769,6 +771,195 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_ts_kernel(const LinArgs A
 //   dpre[o] = dOut[o] * act'(.) ; dH[m,j] = (H[m,j] > 0) * sum_o dpre[o] * Wh[o,j] ; dWh[o,j] += dpre[o]*H[m,j] ; dbh[o] += dpre[o]
 // act: 1 = truncated_exp(x-1) (backward uses exp(clamp(x-1,-15,15)), src/models.py:52-53; out = exp(x-1) is given),
 //      2 = sigmoid (out given).  One warp handles 32 rows at a time; lanes own columns j, j+32 (+64, +96).
+// Same algorithm with the copy engine doing the loads ("TMA" form, the default): in wgrad_ts_kernel every loader thread issues
+// its own cp.async chunks, makes lo images and transposes dY in lockstep, and the role timing shows that serial loader chain
+// -- not HBM latency, not the tensor pipe -- setting the pace (per tile of a 64x64 layer: 540 cycles issuing copies per item,
+// 1330 transposing the dY pair, 540 per X lo image; the MMA warp waits 60 % of the time).  Here
+//   warp  9   producer : one thread issues 2-D tensor-map loads, the dY tile as one raw 128 x 64 box, every X atom straight
+//                        into its SWIZZLE_128B_ATOM_32B operand image; up to 2 dY tiles + 8 X atoms (192 KB) in flight
+//   warps 0-3 dY       : raw tile -> registers -> tcgen05.st (thread == TMEM lane == feature, hi or lo half) + bias sums
+//   warps 4-7 X lo     : lo image of each landed X atom into one of two lo slots
+//   warp  8   MMA      : as above
+// so the three stages run concurrently instead of back to back.
+constexpr int kW3XHi = 8, kW3XLo = 2, kW3Y = 2;
+constexpr int kW3Threads = 10 * 32;
+
+__global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs A, const __grid_constant__ CUtensorMap tm_dy,
+                                                                  const __grid_constant__ CUtensorMap tm_x) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t s_pfull[kW3Y], s_pempty[kW3Y], s_xland[kW3XHi], s_xfull[kW3XHi], s_xempty[kW3XHi], s_lempty[kW3XLo],
+      s_afull[2], s_aempty[2], s_done;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_db[64];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kx = (A.K + 31) >> 5;       // X atoms per tile
+  const int n_sets = A.raw;             // A sets in tensor memory (2 when 2*128 + 64*kx <= 512 columns)
+  constexpr int S = kW3XHi, L = kW3XLo;
+  uint8_t* yraw = smem;                                  // raw dY tile slots: 128 rows x 256 B
+  uint8_t* xhi = smem + kW3Y * 2 * kAtomBytes;           // X hi slot s at +s*kAtomBytes
+  uint8_t* xlo = xhi + S * kAtomBytes;                   // X lo slot l at +l*kAtomBytes (above every hi slot)
+  if (tid == 0) {
+    for (int i = 0; i < kW3Y; ++i) { mbar_init(&s_pfull[i], 1); mbar_init(&s_pempty[i], 128); }
+    for (int s = 0; s < S; ++s) { mbar_init(&s_xland[s], 1); mbar_init(&s_xfull[s], 128); mbar_init(&s_xempty[s], 1); }
+    for (int l = 0; l < L; ++l) mbar_init(&s_lempty[l], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_afull[i], 128); mbar_init(&s_aempty[i], 1); }
+    mbar_init(&s_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(&s_tmem, 512);
+  if (tid < 64) s_db[tid] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_a = s_tmem;                        // A set i: columns [128 i, 128 i + 128)
+  const uint32_t tmem_d = s_tmem + 128 * n_sets;         // D: 64 columns per X atom
+  const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 9) {
+    // ===== producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_dy);
+      tma_prefetch_desc(&tm_x);
+      int xi = 0;
+      long long c_pe = 0, c_xe = 0;
+      Tm tm;
+      const long long t_start = TNF_CLK();
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int row0 = (int)(((long long)blockIdx.x + (long long)tl * gridDim.x) * 128);
+        const int ps = tl % kW3Y;
+        tm.start();
+        mbar_wait(&s_pempty[ps], ((tl / kW3Y) & 1) ^ 1);            // the dY warps have read the slot's previous tile
+        tm.stop(c_pe);
+        mbar_expect_tx(&s_pfull[ps], 2 * kAtomBytes);
+        tma_load_2d(yraw + ps * 2 * kAtomBytes, &tm_dy, 0, row0, &s_pfull[ps]);
+        for (int j = 0; j < kx; ++j, ++xi) {
+          const int s = xi % S;
+          tm.start();
+          mbar_wait(&s_xempty[s], ((xi / S) & 1) ^ 1);              // the MMAs that read the slot's previous atom have completed
+          tm.stop(c_xe);
+          mbar_expect_tx(&s_xland[s], kAtomBytes);
+          tma_load_2d(xhi + s * kAtomBytes, &tm_x, 32 * j, row0, &s_xland[s]);
+        }
+      }
+      if (g_dbg && blockIdx.x == 0) { g_dbg[16] = c_pe; g_dbg[17] = c_xe; g_dbg[18] = TNF_CLK() - t_start; }
+    }
+  } else if (warp < 4) {
+    // ===== dY warps: transpose the raw tile into the A set =====
+    const int q = warp;                  // TMEM lane quarter: lanes 32q..32q+31
+    const bool is_hi = q < 2;            // quarters 0,1: dY_hi of features 0-31 / 32-63; quarters 2,3: dY_lo of the same
+    float bsum = 0.f;
+    long long c_pf = 0, c_ae = 0, c_work = 0;
+    Tm tm;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int ps = tl % kW3Y, set = tl % n_sets;
+      tm.start();
+      mbar_wait(&s_pfull[ps], (tl / kW3Y) & 1);
+      tm.stop(c_pf); tm.start();
+      mbar_wait(&s_aempty[set], ((tl / n_sets) & 1) ^ 1);           // the MMAs that read this A set have completed
+      tm.stop(c_ae); tm.start();
+      tc_fence_after();
+      const uint8_t* src = yraw + ps * 2 * kAtomBytes + (32 * (q & 1) + lane) * 4;
+      const uint32_t taddr = tmem_a + ((uint32_t)(32 * q) << 16) + 128 * set;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = *reinterpret_cast<const float*>(src + (32 * c + i) * 256);
+          if (is_hi) { bsum += x; v[i] = x; }
+          else v[i] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        }
+        tmem_st32(taddr + 32 * c, v);
+      }
+      mbar_arrive(&s_pempty[ps]);                                   // every value of the slot is in registers
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&s_afull[set]);
+      tm.stop(c_work);
+    }
+    if (g_dbg && tid == 0 && blockIdx.x == 0) { g_dbg[19] = c_pf; g_dbg[20] = c_ae; g_dbg[21] = c_work; }
+    if (A.db && is_hi) atomicAdd(&s_db[32 * (q & 1) + lane], bsum);
+  } else if (warp < 8) {
+    // ===== X lo warps =====
+    const int t = tid - 128;
+    const int n_x = my_tiles * kx;
+    long long c_xl = 0, c_le = 0, c_work = 0;
+    Tm tm;
+    for (int xi = 0; xi < n_x; ++xi) {
+      const int s = xi % S, l = xi % L;
+      tm.start();
+      mbar_wait(&s_xland[s], (xi / S) & 1);
+      tm.stop(c_xl); tm.start();
+      mbar_wait(&s_lempty[l], ((xi / L) & 1) ^ 1);                  // the MMAs that read the lo slot's previous image have completed
+      tm.stop(c_le); tm.start();
+      make_lo_atom<128>(xhi + s * kAtomBytes, xlo + l * kAtomBytes, t, true, nullptr);
+      fence_async_smem();
+      mbar_arrive(&s_xfull[s]);
+      tm.stop(c_work);
+    }
+    if (g_dbg && t == 0 && blockIdx.x == 0) { g_dbg[22] = c_xl; g_dbg[23] = c_le; g_dbg[25] = c_work; }
+  } else {
+    // ===== MMA issuer =====
+    const uint32_t idesc = instr_desc(128, 64, false, true);
+    int xi = 0;
+    long long w_y = 0, w_x = 0, w_iss = 0;
+    const long long t_start = TNF_CLK();
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int set = tl % n_sets;
+      { const long long t0 = TNF_CLK(); mbar_wait(&s_afull[set], (tl / n_sets) & 1); w_y += TNF_CLK() - t0; }
+      for (int j = 0; j < kx; ++j, ++xi) {
+        const int s = xi % S;
+        { const long long t0 = TNF_CLK(); mbar_wait(&s_xfull[s], (xi / S) & 1); w_x += TNF_CLK() - t0; }
+        const long long ti = TNF_CLK();
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t xh = smem_u32(xhi + s * kAtomBytes);
+          const uint32_t lbo = smem_u32(xlo + (xi % L) * kAtomBytes) - xh;   // MN block 1 of the B operand = the lo image
+          const uint32_t aa = tmem_a + 128 * set;
+#pragma unroll 4
+          for (int kk = 0; kk < 16; ++kk)
+            mma_tf32_ts(tmem_d + 64 * j, aa + 8 * kk, desc_mnmajor(xh, kk, lbo), idesc, !(tl == 0 && kk == 0));
+          mma_commit(&s_xempty[s]);
+          mma_commit(&s_lempty[xi % L]);
+          if (j == kx - 1) mma_commit(&s_aempty[set]);
+        }
+        __syncwarp();
+        w_iss += TNF_CLK() - ti;
+      }
+    }
+    if (elect_one()) mma_commit(&s_done);
+    __syncwarp();
+    if (g_dbg && lane == 0 && blockIdx.x == 0) { g_dbg[8] = w_y; g_dbg[9] = w_x; g_dbg[10] = TNF_CLK() - t_start; g_dbg[11] = w_iss; }
+  }
+  mbar_wait(&s_done, 0);   // every MMA of this CTA has completed
+  tc_fence_after();
+  __syncthreads();
+  if (A.db && tid < 64) atomicAdd(A.db + tid, s_db[tid]);
+  if (warp < 4) {
+    const int n_out = (warp * 32 + lane) & 63;      // lanes n and n + 64 hold the dY_hi / dY_lo rows of feature n
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+    for (int j = 0; j < kx; ++j) {
+      float v[32], u[32];
+      tmem_ld32(taddr + 64 * j, v);        // x X_hi
+      tmem_ld32(taddr + 64 * j + 32, u);   // x X_lo
+      float* dst = A.dW + (long long)n_out * A.K + 32 * j;
+      if ((A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(A.dW) & 15u) == 0 && 32 * j + 31 < A.K) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)   // one L2 reduction per 16 bytes
+          red_add_f4(dst + i, make_float4(v[i] + u[i], v[i + 1] + u[i + 1], v[i + 2] + u[i + 2], v[i + 3] + u[i + 3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (32 * j + i < A.K) atomicAdd(dst + i, v[i] + u[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(s_tmem, 512);
+}
+
 constexpr int kHbU = 4;
 template <int NH>  // n_head
 __global__ void __launch_bounds__(256, 3) head_bwd_kernel(const float* __restrict__ H, long long ldh, const float* __restrict__ Wh,
@@ -893,6 +1084,29 @@ int check_lin(long long M, int N, int K) {
 }
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// row-major fp32 [rows, cols] with leading dimension ld -> tensor map with a box_cols x 128 box (rows/cols outside the matrix
+// read as zero)
+int make_box_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, CUtensorMapSwizzle swz) {
+  static EncodeTiledFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(fn);
+  }();
+  TNF_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TNF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TNF_OK;
+}
+
 // shared-memory plan of linear_kernel: weight images + H hi slots + L lo slots (16 KB each) + 16 KB epilogue staging.
 // L = 3 lets the lo pass run two atoms ahead of the tensor core; every further hi slot is another atom of global loads
 // in flight (H - L of them, up to 4).
@@ -980,7 +1194,29 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   A.X = dy; A.ldx = lddy; A.X2 = x; A.ldx2 = ldx; A.dW = dweight; A.db = dbias; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (n == 64 && !getenv("TNF_WGRAD_SS")) {
+  const char* variant = getenv("TNF_WGRAD");   // diagnostics: "ss" / "ts" select the older kernels
+  const bool want_ss = variant && !strcmp(variant, "ss"), want_ts = variant && !strcmp(variant, "ts");
+  if (n == 64 && m < (1LL << 31) - 256 && !want_ss && !want_ts) {
+    // 64-wide layers: A operand in tensor memory, loads by the copy engine (wgrad_tma_kernel)
+    const int kx = (k + 31) / 32;
+    A.raw = (2 * 128 + 64 * kx <= 512) ? 2 : 1;
+    CUtensorMap tm_dy, tm_x;
+    rc = make_box_map(&tm_dy, dy, m, n, lddy, 64, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != TNF_OK) return rc;
+    rc = make_box_map(&tm_x, x, m, k, ldx, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc != TNF_OK) return rc;
+    const size_t smem = (size_t)(2 * kW3Y + kW3XHi + kW3XLo) * kAtomBytes + 1024;
+    static thread_local bool configured_tma = false;
+    if (!configured_tma) {
+      TNF_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      configured_tma = true;
+    }
+    const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
+    wgrad_tma_kernel<<<grid, kW3Threads, smem, st>>>(A, tm_dy, tm_x);
+    TNF_LAUNCH_CHECK("linear_wgrad_tma_kernel");
+    return TNF_OK;
+  }
+  if (n == 64 && !want_ss) {
     // 64-wide layers: A operand in tensor memory (wgrad_ts_kernel)
     const int kx = (k + 31) / 32;
     A.raw = (2 * 128 + 64 * kx <= 512) ? 2 : 1;
