@@ -21,4 +21,4 @@ for (k, n) in ((64, 64), (96, 64), (148, 64)):
         _lib.call("tnf_linear_bwd_weight", dy.data_ptr(), n, x.data_ptr(), ld, dw.data_ptr(), db.data_ptr(), m, n, k, _lib.stream_ptr())
         e.record(); torch.cuda.synchronize()
     v = buf.tolist()
-    print(f"K={k}: {s.elapsed_time(e)*1e3:.1f} us | mma warp: wait_yfull {v[8]} wait_xfull {v[9]} issue {v[11]} total {v[10]} | producer: wait pempty {v[16]} xempty {v[17]} total {v[18]} | dY warps: wait pfull {v[19]} aempty {v[20]} work {v[21]} | X lo warps: wait land {v[22]} lempty {v[23]} work {v[25]}")
+    print(f"K={k}: {s.elapsed_time(e)*1e3:.1f} us | mma warp: wait_yfull {v[8]} wait_xfull {v[9]} issue {v[11]} total {v[10]} | producer: wait pempty {v[16]} xempty {v[17]} total {v[18]} | dY warps: wait pfull {v[19]} aempty {v[20]} work {v[21]} | X lo warps: wait land {v[22]} lempty {v[23]} work {v[25]} | CTA 0 clocks since entry: loop start {v[26]} first A {v[27]} loop end {v[28]} all MMAs done {v[29]} flushed {v[30]}")

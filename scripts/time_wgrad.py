@@ -14,7 +14,7 @@ for k, n in shapes:
     bufs[(k, n)] = (torch.randn(m, ld, device="cuda"), torch.randn(m, n, device="cuda"), torch.zeros(n, k, device="cuda"),
                     torch.zeros(n, device="cuda"), ld)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for mode in ("ss", "ts", "tma", "ts", "tma"):
+for mode in (sys.argv[1:] or ["ss", "ts", "tma", "ts", "tma"]):
     os.environ["TNF_WGRAD"] = mode
     for k, n in shapes:
         x, dy, dw, db, ld = bufs[(k, n)]

@@ -776,17 +776,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_ts_kernel(const LinArgs A
 // -- not HBM latency, not the tensor pipe -- setting the pace (per tile of a 64x64 layer: 540 cycles issuing copies per item,
 // 1330 transposing the dY pair, 540 per X lo image; the MMA warp waits 60 % of the time).  Here
 //   warp  9   producer : one thread issues 2-D tensor-map loads, the dY tile as one raw 128 x 64 box, every X atom straight
-//                        into its SWIZZLE_128B_ATOM_32B operand image; up to 2 dY tiles + 8 X atoms (192 KB) in flight
+//                        into its SWIZZLE_128B_ATOM_32B operand image; up to 3 dY tiles + 6 X atoms (192 KB) in flight
 //   warps 0-3 dY       : raw tile -> registers -> tcgen05.st (thread == TMEM lane == feature, hi or lo half) + bias sums
 //   warps 4-7 X lo     : lo image of each landed X atom into one of two lo slots
 //   warp  8   MMA      : as above
 // so the three stages run concurrently instead of back to back.
-constexpr int kW3XHi = 8, kW3XLo = 2, kW3Y = 2;
+constexpr int kW3XHi = 6, kW3XLo = 2, kW3Y = 3;
 constexpr int kW3Threads = 10 * 32;
 
 __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs A, const __grid_constant__ CUtensorMap tm_dy,
                                                                   const __grid_constant__ CUtensorMap tm_x) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const long long c0 = TNF_CLK();
   __shared__ uint64_t s_pfull[kW3Y], s_pempty[kW3Y], s_xland[kW3XHi], s_xfull[kW3XHi], s_xempty[kW3XHi], s_lempty[kW3XLo],
       s_afull[2], s_aempty[2], s_done;
   __shared__ uint32_t s_tmem;
@@ -908,6 +909,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs 
     for (int tl = 0; tl < my_tiles; ++tl) {
       const int set = tl % n_sets;
       { const long long t0 = TNF_CLK(); mbar_wait(&s_afull[set], (tl / n_sets) & 1); w_y += TNF_CLK() - t0; }
+      if (tl == 0 && g_dbg && lane == 0 && blockIdx.x == 0) { g_dbg[26] = t_start - c0; g_dbg[27] = TNF_CLK() - c0; }
       for (int j = 0; j < kx; ++j, ++xi) {
         const int s = xi % S;
         { const long long t0 = TNF_CLK(); mbar_wait(&s_xfull[s], (xi / S) & 1); w_x += TNF_CLK() - t0; }
@@ -930,33 +932,43 @@ __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs 
     }
     if (elect_one()) mma_commit(&s_done);
     __syncwarp();
-    if (g_dbg && lane == 0 && blockIdx.x == 0) { g_dbg[8] = w_y; g_dbg[9] = w_x; g_dbg[10] = TNF_CLK() - t_start; g_dbg[11] = w_iss; }
+    if (g_dbg && lane == 0 && blockIdx.x == 0) { g_dbg[8] = w_y; g_dbg[9] = w_x; g_dbg[10] = TNF_CLK() - t_start; g_dbg[11] = w_iss; g_dbg[28] = TNF_CLK() - c0; }
   }
   mbar_wait(&s_done, 0);   // every MMA of this CTA has completed
   tc_fence_after();
   __syncthreads();
+  if (g_dbg && tid == 0 && blockIdx.x == 0) g_dbg[29] = TNF_CLK() - c0;
   if (A.db && tid < 64) atomicAdd(A.db + tid, s_db[tid]);
   if (warp < 4) {
+    // Flush: every CTA adds its 64 x K partial into dW.  All CTAs get here at about the same time, and reductions to one
+    // address are serialised in L2, so each CTA walks the (atom, 16-byte chunk) positions from its own starting point.
+    // (Transposing the tile through shared memory for contiguous reductions was measured and is no faster.)
     const int n_out = (warp * 32 + lane) & 63;      // lanes n and n + 64 hold the dY_hi / dY_lo rows of feature n
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int j = 0; j < kx; ++j) {
-      float v[32], u[32];
-      tmem_ld32(taddr + 64 * j, v);        // x X_hi
-      tmem_ld32(taddr + 64 * j + 32, u);   // x X_lo
+    const bool vec = (A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(A.dW) & 15u) == 0;
+    const int j0 = blockIdx.x % kx, i0 = (blockIdx.x / kx) & 7;
+    for (int jj = 0; jj < kx; ++jj) {
+      const int j = (j0 + jj) % kx;
       float* dst = A.dW + (long long)n_out * A.K + 32 * j;
-      if ((A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(A.dW) & 15u) == 0 && 32 * j + 31 < A.K) {
+#pragma unroll 2
+      for (int ii = 0; ii < 8; ++ii) {
+        const int c4 = 4 * ((i0 + ii) & 7);
+        float v[4], u[4];
+        tmem_ld4x2(taddr + 64 * j + c4, taddr + 64 * j + 32 + c4, v, u);   // x X_hi, x X_lo
+        const int col = 32 * j + c4;
+        float* p = dst + c4;
+        if (vec && col + 3 < A.K) red_add_f4(p, make_float4(v[0] + u[0], v[1] + u[1], v[2] + u[2], v[3] + u[3]));   // one L2 reduction per 16 bytes
+        else {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)   // one L2 reduction per 16 bytes
-          red_add_f4(dst + i, make_float4(v[i] + u[i], v[i + 1] + u[i + 1], v[i + 2] + u[i + 2], v[i + 3] + u[i + 3]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (32 * j + i < A.K) atomicAdd(dst + i, v[i] + u[i]);
+          for (int e = 0; e < 4; ++e)
+            if (col + e < A.K) atomicAdd(p + e, v[e] + u[e]);
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (g_dbg && tid == 0 && blockIdx.x == 0) g_dbg[30] = TNF_CLK() - c0;
   if (warp == 8) tmem_dealloc(s_tmem, 512);
 }
 

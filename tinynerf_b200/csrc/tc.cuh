@@ -75,6 +75,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 4-column reads (thread i of warp w: TMEM lane 32*(w%4)+i, columns [c, c+4) of each address), one wait
+__device__ __forceinline__ void tmem_ld4x2(uint32_t taddr_a, uint32_t taddr_b, float a[4], float b[4]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr_a) : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr_b) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[4 + i]); }
+}
+
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor, InstrDescriptor) -------------------
 // shared-memory matrix descriptor, version 1 (Blackwell); layout_type 2 = SWIZZLE_128B (16-byte chunks XOR row%8),
 // 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4) -- the only layout available to MN-major tf32 operands
