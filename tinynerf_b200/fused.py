@@ -217,7 +217,15 @@ class FusedKPlanesStep:
                  nbytes=4 * (n * (nn_ + (2 if relu_src else 1) * k) + nn_ * k), flops=2 * n * nn_ * k)
 
         with torch.cuda.device(self.dev):
-            self.flat_grad.zero_()
+            # gradient buffer: the TV pass WRITES the plane gradients (value + gradient of the regulariser from one read of
+            # the planes; loss += tv_alpha * loss_tv, src/run.py:254-255) -- it depends on nothing in this iteration, so it
+            # doubles as the zero-fill of 99.8 % of the buffer; the data term is scattered on top of it in backward
+            if self.tv_alpha != 0.0:
+                call("tnf_tv_fwd_bwd", self._plane_ptrs, self._grad_ptrs, self._res_planes, len(self.planes), self.channels,
+                     self._tv_w, P(self._tv_gscale), 0, P(self._tv_sums), st, nbytes=2 * self._plane_bytes)
+                self.flat_grad[self._plane_grad_end:].zero_()
+            else:
+                self.flat_grad.zero_()
             # ---- forward (src/core.py:225-267) ----
             call("tnf_kplanes_fwd", self._plane_ptrs, self._res_scales, self.n_scales, self.channels, P(packed), 7, n,
                  P(ws["feats"]), st, nbytes=n * (12 + 4 * F) + self._plane_bytes)
@@ -282,13 +290,9 @@ class FusedKPlanesStep:
                 # the features feed both heads: d feats = d(sigma branch) + d(colour input)[:, feature columns]
                 torch.add(dfeat, ws["dxc"][:n, xw - F:xw], out=dfeat)
                 _lib.launch_count += 1
-            # plane gradients: scatter-add of the data term, then TV value + gradient (loss += tv_alpha * loss_tv,
-            # src/run.py:254-255) from one pass over the planes
+            # plane gradients: scatter-add of the data term on top of the TV gradient written at the start
             call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
                  P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
-            if self.tv_alpha != 0.0:
-                call("tnf_tv_fwd_bwd", self._plane_ptrs, self._grad_ptrs, self._res_planes, len(self.planes), self.channels,
-                     self._tv_w, P(self._tv_gscale), 1, P(self._tv_sums), st, nbytes=3 * self._plane_bytes)
             work = None
             if reduce and self.world > 1:
                 work = dist.all_reduce(self.flat_grad[:self._plane_grad_end], async_op=True)  # runs under the wgrads
