@@ -81,7 +81,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.stamps, self.proc, self.t_mark = gpu_index, [], [], None, 0.0
 
     def start(self):
         try:
@@ -95,12 +95,21 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+            self.stamps.append(time.perf_counter())
+
+    def mark(self):
+        """Start of the timed region: only samples taken from here on are reported.  (The sampler itself is started
+        before the warm-up: nvidia-smi's first query initialises NVML and was seen to block kernel launches for ~100 ms.)"""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.t.join(timeout=2)
+        n_all = len(self.rows)
+        keep = [r for r, ts in zip(self.rows, self.stamps) if ts >= self.t_mark]
+        self.rows = keep if keep else self.rows[-1:]   # a region shorter than the sampling period: the closest sample
         sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -255,7 +264,7 @@ def summarise_profile(records, peak, tf32_peak):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -359,11 +368,12 @@ def main():
 
     # ---- device-resident arm (value) ----
     tr = make_trainer(host=False)
-    for _ in range(settle + args.warmup):
-        one_step(tr, False)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(settle + args.warmup):
+        one_step(tr, False)
+    clocks.mark()
     n, ms, _, launches = timed(tr, args.steps, False, profile=False)
     clk = clocks.stop() if rank == 0 else None
     value = n / (ms * 1e-3)

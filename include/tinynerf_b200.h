@@ -219,6 +219,16 @@ int tnf_linear_bwd_data(const float* dy, int64_t lddy, const float* weight, floa
                         const float* relu_src, int64_t ldrs, int64_t m, int32_t n, int32_t k, void* stream);
 int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dweight, float* dbias,
                           int64_t m, int32_t n, int32_t k, void* stream);
+/* wgrad of a layer whose input is a concatenation that was never materialised: x = [xa (ka columns) | xb (kb columns)],
+ * dweight [n, ka+kb] += dy^T x, dbias += column sums of dy (NULL to skip).  The colour head's first layer reads
+ * cat([PE(d), d], features) (src/models.py:87): xa = the [PE(d) | d] rows, xb = the feature rows.  n must be 64.
+ * scratch: optional device buffer of tnf_wgrad_cat_scratch_bytes(ka, kb) bytes, 16-byte aligned, ZERO before the first
+ * call (every call leaves it zero again).  With it the per-CTA partial sums are reduced with 16-byte operations even
+ * though rows of dweight (ka+kb floats) and the column ka are not 16-byte aligned; without it they are scalar atomics. */
+int64_t tnf_wgrad_cat_scratch_bytes(int32_t ka, int32_t kb);
+int tnf_linear_bwd_weight_cat(const float* dy, int64_t lddy, const float* xa, int64_t ldxa, int32_t ka, const float* xb,
+                              int64_t ldxb, int32_t kb, float* dweight, float* dbias, int64_t m, int32_t n, float* scratch,
+                              void* stream);
 /* Input row of VanillaColorDecoder.forward (src/models.py:87): out[m] = [PE_{n_freqs}(dirs[m]) | dirs[m] | feats[m]],
  * zero-padded to ld_out floats (PositionalEncoding layout, src/models.py:36-39). */
 int tnf_color_input(const float* dirs, int64_t ld_dirs, const float* feats, int64_t ld_feats, int32_t n_freqs,
@@ -235,10 +245,13 @@ int tnf_head_bwd(const float* h, int64_t ldh, const float* head_w, const float* 
  * (the reference's VanillaColorDecoder(8, dim, 64, 3) / VanillaOpacityDecoder(dim), src/run.py:131-150).
  * h_out: optional [host] array of 4 device pointers [m,64] receiving the colour head's hidden activations, hs_out [m,64]
  * the density head's (the backward kernels read them); rgb [m,3], sigma [m].  workspace: device scratch of
- * tnf_heads_workspace_bytes(feat_dim, k0) bytes (packed weight images), 16-byte aligned. */
+ * tnf_heads_workspace_bytes(feat_dim, k0) bytes (packed weight images), 16-byte aligned.
+ * xc_cols: how many leading columns of the colour-input row `xc` holds.  xc_cols == k0: the whole row (tnf_color_input with
+ * the features).  xc_cols == k0 - feat_dim: only [PE(d) | d]; the trailing feat_dim columns of the row are the feature row
+ * itself and are taken from `feats` (the concatenation is never written). */
 int64_t tnf_heads_workspace_bytes(int32_t feat_dim, int32_t k0);
 int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_dim, const float* xc, int64_t ld_xc, int32_t k0,
-                  const float* const* color_w /*[host]*/, const float* const* color_b /*[host]*/,
+                  int32_t xc_cols, const float* const* color_w /*[host]*/, const float* const* color_b /*[host]*/,
                   const float* const* sigma_w /*[host]*/, const float* const* sigma_b /*[host]*/,
                   float* const* h_out /*[host], optional*/, float* hs_out /*optional*/, float* rgb, float* sigma, int64_t m,
                   void* workspace, void* stream);

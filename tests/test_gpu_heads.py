@@ -11,11 +11,18 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _run_fused(sig, col, feats, dirs):
+def _run_fused(sig, col, feats, dirs, split=False):
+    """split: xc handed to the kernel holds only [PE(d) | d]; the feature columns of the colour input come from `feats`."""
     lib = _lib.load()
     n, F = feats.shape
     xc = mlp_ops.color_input(feats, dirs, col.pe.freqs.numel())
     k0, ld = xc.size(1), xc.stride(0)
+    xc_cols = k0 - F if split else k0
+    xc_in = xc
+    if split:
+        xc_in = torch.full((n, (xc_cols + 3) // 4 * 4), float("nan"), device=DEV)   # padding must never be read as data
+        xc_in[:, :xc_cols] = xc[:, :xc_cols]
+        ld = xc_in.stride(0)
     sl, cl = sig.net.linears(), col.net.linears()
     tab = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
     hs = torch.full((n, 64), float("nan"), device=DEV)
@@ -23,7 +30,7 @@ def _run_fused(sig, col, feats, dirs):
     rgb = torch.full((n, 3), float("nan"), device=DEV)
     sigma = torch.full((n,), float("nan"), device=DEV)
     ws = torch.empty(int(lib.tnf_heads_workspace_bytes(F, k0)) // 4, device=DEV)
-    _lib.call("tnf_heads_fwd", feats.data_ptr(), feats.stride(0), F, xc.data_ptr(), ld, k0, tab([l.weight for l in cl]),
+    _lib.call("tnf_heads_fwd", feats.data_ptr(), feats.stride(0), F, xc_in.data_ptr(), ld, k0, xc_cols, tab([l.weight for l in cl]),
               tab([l.bias for l in cl]), tab([l.weight for l in sl]), tab([l.bias for l in sl]), tab(h), hs.data_ptr(),
               rgb.data_ptr(), sigma.data_ptr(), n, ws.data_ptr(), _lib.stream_ptr())
     torch.cuda.synchronize()
@@ -44,14 +51,15 @@ def _ref64(sig, col, feats, xc):
     return sigma, rgb, hs, hl
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 300, 148 * 128 + 5, 2 * 148 * 128 + 77, 1 << 18])
-def test_heads_fwd_matches_float64_and_per_layer_kernels(n):
+def test_heads_fwd_matches_float64_and_per_layer_kernels(n, split):
     torch.manual_seed(n)
     sig = models.VanillaOpacityDecoder(96).to(DEV)
     col = models.VanillaColorDecoder(8, 96, 64, 3).to(DEV)
     feats = torch.randn(n, 96, device=DEV) * 0.5
     dirs = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
-    sigma, rgb, hs, h, xc = _run_fused(sig, col, feats, dirs)
+    sigma, rgb, hs, h, xc = _run_fused(sig, col, feats, dirs, split)
     s64, r64, hs64, h64 = _ref64(sig, col, feats, xc)
 
     def close(a, b, what):

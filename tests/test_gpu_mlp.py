@@ -61,6 +61,29 @@ def test_linear_dgrad_and_wgrad(m, k, n):
     check(gb, dy.double().sum(0), dy.double().abs().sum(0))
 
 
+@pytest.mark.parametrize("m,ka,kb", [(1000, 51, 96), (70001, 51, 96), (300, 20, 33), (40000, 64, 64)])
+def test_wgrad_of_a_concatenated_input(m, ka, kb):
+    """tnf_linear_bwd_weight_cat: dW += dy^T [xa | xb] without the concatenation ever being written (the colour head's
+    first layer, src/models.py:87)."""
+    g = torch.Generator().manual_seed(m + ka)
+    xa = torch.full((m, (ka + 3) // 4 * 4), float("nan"))
+    xa[:, :ka] = torch.randn(m, ka, generator=g)
+    xb = torch.full((m, (kb + 3) // 4 * 4), float("nan"))
+    xb[:, :kb] = torch.randn(m, kb, generator=g).relu()
+    dy = torch.randn(m, 64, generator=g)
+    xa, xb, dy = xa.to(DEV), xb.to(DEV), dy.to(DEV)
+    x = torch.cat([xa[:, :ka], xb[:, :kb]], 1).double()
+    scratch = torch.zeros(int(_lib.load().tnf_wgrad_cat_scratch_bytes(ka, kb)) // 4, device=DEV)
+    for scr in (None, scratch, scratch):   # scalar-atomic flush, then the scratch-tile flush twice (it must come back zeroed)
+        gw, gb = torch.zeros(64, ka + kb, device=DEV), torch.zeros(64, device=DEV)
+        with torch.cuda.device(0):
+            _lib.call("tnf_linear_bwd_weight_cat", dy.data_ptr(), 64, xa.data_ptr(), xa.stride(0), ka, xb.data_ptr(), xb.stride(0), kb,
+                      gw.data_ptr(), gb.data_ptr(), m, 64, _lib.ptr(scr), _lib.stream_ptr())
+        check(gw, dy.double().t() @ x, dy.double().abs().t() @ x.abs())
+        check(gb, dy.double().sum(0), dy.double().abs().sum(0))
+        assert not scratch.any()
+
+
 def test_heads_match_reference_golden(golden):
     g = golden("heads")
     torch.manual_seed(41)
@@ -142,3 +165,11 @@ def test_color_input_matches_positional_encoding_bitwise(golden):
     assert torch.equal(f.grad, torch.ones_like(f))
     xg = mlp_ops.color_input(g["feats"].to(DEV), g["dirs"].to(DEV), 8)
     assert torch.allclose(xg[:, :48].cpu(), g["pe"], rtol=0, atol=2e-6)  # CPU sinf/cosf of the golden run vs GPU
+    # the row without its feature columns ([PE(d) | d | 0], what the fused heads read when the features come from their own
+    # rows): packed samples are [N,7] with the directions at columns 3..5
+    packed = torch.zeros(5000, 7, device=DEV)
+    packed[:, 3:6] = d
+    out = torch.full((5000, 52), float("nan"), device=DEV)
+    with torch.cuda.device(0):
+        _lib.call("tnf_color_input", packed.data_ptr() + 12, 7, None, 0, 8, 0, out.data_ptr(), 52, 5000, _lib.stream_ptr())
+    assert torch.equal(out[:, :51], want[:, :51]) and bool((out[:, 51] == 0).all())

@@ -1,7 +1,10 @@
 // a15/a16 -- both decoder heads of a sample tile in ONE persistent tcgen05 kernel (forward):
 //   sigma  = truncated_exp(W_s1 relu(W_s0 f + b_s0) + b_s1 - 1)                     VanillaOpacityDecoder, src/models.py:70-77
 //   rgb    = sigmoid(W_c4 relu(W_c3 relu(W_c2 relu(W_c1 relu(W_c0 x + b)...))))     VanillaColorDecoder,   src/models.py:79-89
-// with x = [PE(d) | d | f] (the colour-input row, tnf_color_input) and f the feature row.
+// with x = [PE(d) | d | f] (the colour-input row, tnf_color_input) and f the feature row.  The row need not be materialised:
+// with xc_cols < k0 the buffer `xc` holds only its first xc_cols columns ([PE(d) | d]) and the rest IS the feature row, whose
+// atoms are then multiplied into both heads' layer-0 accumulators (the concatenation of src/models.py:87 becomes a split
+// of W_c0's columns).
 //
 // The per-layer kernels (mlp.cu) stream every hidden activation through HBM and pay a launch per layer.  Here a
 // 128-sample tile stays on chip from the inputs to sigma/rgb:
@@ -48,6 +51,7 @@ __device__ long long* g_hdbg = nullptr;   // diagnostics: wait cycles per role (
 struct HeadsArgs {
   const float* feats; long long ld_feats; int F;
   const float* xc; long long ld_xc; int K0;
+  int kxp, kfc;   // layer-0 items: kxp atoms of xc (colour), then kfc feature atoms (colour; 0 when xc holds the whole row), then kf feature atoms (sigma)
   const uint8_t* wimg;
   const float* bias_c[4]; const float* bias_s;
   const float* head_c_w; const float* head_c_b; const float* head_s_w; const float* head_s_b;
@@ -56,7 +60,7 @@ struct HeadsArgs {
 };
 
 // ---- the static schedule ---------------------------------------------------------------------------------------------
-// Layer-0 work of a tile is n0 = kx + kf "items" (kx colour-input atoms, then kf feature atoms); the hidden layers are
+// Layer-0 work of a tile is n0 = nc + kf "items" (nc colour-head atoms, then kf feature atoms for sigma); the hidden layers are
 // three more units.  Units in issue order for a CTA with T tiles:
 //   prologue: L0(tile 0) items 0..n0-1
 //   tile t  : H1(t) | L0(t+1) items 0,1 | H2(t) | L0(t+1) items 2,3 | H3(t) | L0(t+1) items 4..n0-1     (no L0 after the last tile)
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
   uint8_t* alo = ahi + kAH * kAtomBytes;             // kAL x 16 KB
   uint8_t* wring = alo + kAL * kAtomBytes;           // kWN x 16 KB
   uint8_t* epi = wring + kWN * kChunkBytes;          // 8 x 2 KB warp transpose buffers + 4 KB head partial sums
-  const int kx = (A.K0 + 31) >> 5, kf = (A.F + 31) >> 5, n0 = kx + kf;
+  const int kxp = A.kxp, nc = A.kxp + A.kfc, kf = (A.F + 31) >> 5, n0 = nc + kf;
   const int T = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int NU = n_units(T, n0);
 
@@ -134,8 +138,8 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
           mbar_wait(&s_ahempty[h], ((ia / kAH) & 1) ^ 1);
           const int row0 = (blockIdx.x + x.tile * gridDim.x) * 128;
           mbar_expect_tx(&s_ahfull[h], kAtomBytes);
-          if (x.q < kx) tma_load_2d(ahi + h * kAtomBytes, &tm_xc, 32 * x.q, row0, &s_ahfull[h]);
-          else tma_load_2d(ahi + h * kAtomBytes, &tm_feats, 32 * (x.q - kx), row0, &s_ahfull[h]);
+          if (x.q < kxp) tma_load_2d(ahi + h * kAtomBytes, &tm_xc, 32 * x.q, row0, &s_ahfull[h]);
+          else tma_load_2d(ahi + h * kAtomBytes, &tm_feats, 32 * (x.q - (x.q < nc ? kxp : nc)), row0, &s_ahfull[h]);
           ++ia;
         }
         const int n_chunks = x.hidden ? 2 : 1;
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
       const int b = x.tile & 1;
       if (x.hidden == 0) {
         const int h = ca % kAH, l = ca % kAL, w = cw % kWN;
-        const bool colour = x.q < kx;
-        { HT0(); if (x.q == kx) mbar_wait(&s_dsempty[b], ((x.tile >> 1) & 1) ^ 1); HT1(d_ds); }  // sigma epilogue of tile-2 has drained Ds[b]
+        const bool colour = x.q < nc;
+        { HT0(); if (x.q == nc) mbar_wait(&s_dsempty[b], ((x.tile >> 1) & 1) ^ 1); HT1(d_ds); }  // sigma epilogue of tile-2 has drained Ds[b]
         { HT0(); mbar_wait(&s_afull[l], (ca / kAL) & 1); HT1(d_af); }
         { HT0(); mbar_wait(&s_wfull[w], (cw / kWN) & 1); HT1(d_wf); }
         tc_fence_after();
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
           const uint32_t a_h = smem_u32(ahi + h * kAtomBytes), a_l = smem_u32(alo + l * kAtomBytes);
           const uint32_t w_h = smem_u32(wring + w * kChunkBytes), w_l = w_h + kChunkBytes / 2;
           const uint32_t d = (colour ? tm_dc : tm_ds) + b * kHid;
-          const bool first = (x.q == 0) || (x.q == kx);
+          const bool first = (x.q == 0) || (x.q == nc);
 #pragma unroll 1
           for (int pass = 0; pass < 3; ++pass) {
             const uint32_t aa = (pass == 1) ? a_l : a_h;
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(kHThreads, 1) heads_fwd_kernel(const HeadsArgs
           }
           mma_commit(&s_ahempty[h]);
           mma_commit(&s_wempty[w]);
-          if (x.q == kx - 1) mma_commit(&s_tfull_c[b]);
+          if (x.q == nc - 1) mma_commit(&s_tfull_c[b]);
           if (x.q == n0 - 1) mma_commit(&s_tfull_s[b]);
         }
         __syncwarp();
@@ -344,31 +348,36 @@ struct PackArgs {
   const float* ws0; int F;    // [64, F]
   const float* w123[3];       // [64, 64]
   uint8_t* img;
-  int kx, kf;
+  int kxp, kfc, kf, xc_cols;  // layer-0 items as in HeadsArgs; xc_cols = columns of W_c0 covered by the xc atoms
 };
+// layer-0 item q -> the weight matrix, its leading dimension and the column range [k0, k1) the item's 32-wide atom covers
+__device__ __forceinline__ void item_weights(const PackArgs& P, int q, const float*& W, int& ld, int& k0, int& k1) {
+  if (q < P.kxp) { W = P.wc0; ld = P.K0; k0 = 32 * q; k1 = min(k0 + 32, P.xc_cols); }
+  else if (q < P.kxp + P.kfc) { W = P.wc0; ld = P.K0; k0 = P.xc_cols + 32 * (q - P.kxp); k1 = min(k0 + 32, P.K0); }
+  else { W = P.ws0; ld = P.F; k0 = 32 * (q - P.kxp - P.kfc); k1 = min(k0 + 32, P.F); }
+}
 __global__ void __launch_bounds__(256) pack_heads_kernel(const PackArgs P) {
-  const int n_chunks = 6 + P.kx + P.kf;
+  const int n_chunks = 6 + P.kxp + P.kfc + P.kf;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (chunk, row, 16-byte column chunk)
   if (t >= n_chunks * 64 * 8) return;
   const int chunk = t / 512, r = (t % 512) / 8, c = t % 8;
   // which matrix / k-atom does this chunk hold?
   const float* W = nullptr;
-  int ld = 0, K = 0, atom = 0;
+  int ld = 0, k0 = 0, k1 = 0;                       // the chunk holds W[:, k0:k1) (zero-padded to 32 columns)
   const int blk = chunk / 4, pos = chunk % 4;       // blocks of [Wi a, Wi b, item, item] for the first two groups
   if (chunk < 8) {
-    if (pos < 2) { W = P.w123[blk]; ld = K = kHid; atom = pos; }
-    else { const int q = blk * 2 + (pos - 2); if (q < P.kx) { W = P.wc0; ld = K = P.K0; atom = q; } else { W = P.ws0; ld = K = P.F; atom = q - P.kx; } }
+    if (pos < 2) { W = P.w123[blk]; ld = kHid; k0 = 32 * pos; k1 = k0 + 32; }
+    else item_weights(P, blk * 2 + (pos - 2), W, ld, k0, k1);
   } else if (chunk < 10) {
-    W = P.w123[2]; ld = K = kHid; atom = chunk - 8;
+    W = P.w123[2]; ld = kHid; k0 = 32 * (chunk - 8); k1 = k0 + 32;
   } else {
-    const int q = chunk - 6;
-    if (q < P.kx) { W = P.wc0; ld = K = P.K0; atom = q; } else { W = P.ws0; ld = K = P.F; atom = q - P.kx; }
+    item_weights(P, chunk - 6, W, ld, k0, k1);
   }
   float v[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int k = atom * 32 + c * 4 + i;
-    v[i] = (k < K) ? __ldg(W + (long long)r * ld + k) : 0.f;
+    const int k = k0 + c * 4 + i;
+    v[i] = (k < k1) ? __ldg(W + (long long)r * ld + k) : 0.f;
   }
   uint8_t* base = P.img + (size_t)chunk * kChunkBytes;
   const int off = r * 128 + ((c ^ (r & 7)) << 4);
@@ -417,11 +426,11 @@ int make_atom_map(CUtensorMap* map, const float* base, int64_t rows, int64_t col
 
 extern "C" int64_t tnf_heads_workspace_bytes(int32_t feat_dim, int32_t k0) {
   const int kx = (k0 + 31) / 32, kf = (feat_dim + 31) / 32;
-  return (int64_t)(6 + kx + kf) * tnf::kChunkBytes;
+  return (int64_t)(6 + kx + 1 + 2 * kf) * tnf::kChunkBytes;   // enough for either layout of the colour input
 }
 
 extern "C" int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_dim, const float* xc, int64_t ld_xc, int32_t k0,
-                             const float* const* color_w, const float* const* color_b, const float* const* sigma_w,
+                             int32_t xc_cols, const float* const* color_w, const float* const* color_b, const float* const* sigma_w,
                              const float* const* sigma_b, float* const* h_out, float* hs_out, float* rgb, float* sigma,
                              int64_t m, void* workspace, void* stream) {
   using namespace tnf;
@@ -429,8 +438,10 @@ extern "C" int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_
   if (m == 0) return TNF_OK;
   TNF_REQUIRE(feats && xc && color_w && color_b && sigma_w && sigma_b && rgb && sigma && workspace, "null pointer");
   TNF_REQUIRE(feat_dim >= 1 && k0 >= 1, "bad widths");
-  const int kx = (k0 + 31) / 32, kf = (feat_dim + 31) / 32;
-  TNF_REQUIRE(kx + kf >= 4 && kx + kf <= 12, "unsupported input widths (k0=%d, feat_dim=%d)", k0, feat_dim);
+  TNF_REQUIRE(xc_cols >= 1 && (xc_cols == k0 || xc_cols + feat_dim == k0),
+              "xc_cols must be k0 (xc holds the whole colour-input row) or k0 - feat_dim (its trailing columns are the feature row)");
+  const int kxp = (xc_cols + 31) / 32, kf = (feat_dim + 31) / 32, kfc = (xc_cols == k0) ? 0 : kf;
+  TNF_REQUIRE(kxp + kfc + kf >= 4 && kxp + kfc + kf <= 12, "unsupported input widths (k0=%d, feat_dim=%d)", k0, feat_dim);
   TNF_REQUIRE(ld_feats % 4 == 0 && ld_xc % 4 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15u) == 0 &&
                   (reinterpret_cast<uintptr_t>(xc) & 15u) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0,
               "feats/xc/workspace must be 16-byte aligned with leading dimensions multiple of 4");
@@ -440,12 +451,12 @@ extern "C" int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_
   PackArgs P{};
   P.wc0 = color_w[0]; P.K0 = k0; P.ws0 = sigma_w[0]; P.F = feat_dim;
   for (int i = 0; i < 3; ++i) P.w123[i] = color_w[1 + i];
-  P.img = static_cast<uint8_t*>(workspace); P.kx = kx; P.kf = kf;
-  const int pack_threads = (6 + kx + kf) * 512;
+  P.img = static_cast<uint8_t*>(workspace); P.kxp = kxp; P.kfc = kfc; P.kf = kf; P.xc_cols = xc_cols;
+  const int pack_threads = (6 + kxp + kfc + kf) * 512;
   pack_heads_kernel<<<(pack_threads + 255) / 256, 256, 0, st>>>(P);
   TNF_LAUNCH_CHECK("pack_heads_kernel");
   HeadsArgs A{};
-  A.feats = feats; A.ld_feats = ld_feats; A.F = feat_dim; A.xc = xc; A.ld_xc = ld_xc; A.K0 = k0;
+  A.feats = feats; A.ld_feats = ld_feats; A.F = feat_dim; A.xc = xc; A.ld_xc = ld_xc; A.K0 = k0; A.kxp = kxp; A.kfc = kfc;
   A.wimg = static_cast<const uint8_t*>(workspace);
   for (int i = 0; i < 4; ++i) { A.bias_c[i] = color_b[i]; A.h[i] = h_out ? h_out[i] : nullptr; }
   A.bias_s = sigma_b[0];
@@ -460,7 +471,7 @@ extern "C" int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_
   }
   TNF_REQUIRE(m < (1LL << 31) - 256, "too many rows for the tensor-map coordinates");
   CUtensorMap tm_xc, tm_feats;
-  int rc = make_atom_map(&tm_xc, xc, m, k0, ld_xc);
+  int rc = make_atom_map(&tm_xc, xc, m, xc_cols, ld_xc);
   if (rc != TNF_OK) return rc;
   rc = make_atom_map(&tm_feats, feats, m, feat_dim, ld_feats);
   if (rc != TNF_OK) return rc;

@@ -52,6 +52,9 @@ struct LinArgs {
   long long M; int N, K;
   int relu;
   int n_tiles;
+  float* scratch;  // wgrad_tma_kernel, optional: [64][32 kx] partial sums + one counter word, zero on entry and on exit
+  int kxa, col_b;  // wgrad_tma_kernel: X atoms [0, kxa) come from the first tensor map and land at dW columns 32 j, atoms
+                   // [kxa, kx) from the second map at dW columns col_b + 32 (j - kxa)  (X = [X_a | X_b], col_b = width of X_a)
   int ring;        // hi-image slots of the operand ring (16 KB each), chosen by the host from the smem budget
   int raw;         // lo-image slots (16 KB each); ring - raw atoms of global loads are kept in flight
 };
@@ -785,7 +788,8 @@ constexpr int kW3XHi = 6, kW3XLo = 2, kW3Y = 3;
 constexpr int kW3Threads = 10 * 32;
 
 __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs A, const __grid_constant__ CUtensorMap tm_dy,
-                                                                  const __grid_constant__ CUtensorMap tm_x) {
+                                                                  const __grid_constant__ CUtensorMap tm_x,
+                                                                  const __grid_constant__ CUtensorMap tm_xb) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const long long c0 = TNF_CLK();
   __shared__ uint64_t s_pfull[kW3Y], s_pempty[kW3Y], s_xland[kW3XHi], s_xfull[kW3XHi], s_xempty[kW3XHi], s_lempty[kW3XLo],
@@ -794,7 +798,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs 
   __shared__ float s_db[64];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kx = (A.K + 31) >> 5;       // X atoms per tile
+  const int kxa = A.kxa;                                  // X atoms of the first source
+  const int kx = kxa + ((A.K - A.col_b + 31) >> 5);       // X atoms per tile (A.col_b == A.K: one source)
   const int n_sets = A.raw;             // A sets in tensor memory (2 when 2*128 + 64*kx <= 512 columns)
   constexpr int S = kW3XHi, L = kW3XLo;
   uint8_t* yraw = smem;                                  // raw dY tile slots: 128 rows x 256 B
@@ -822,6 +827,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs 
     if (lane == 0) {
       tma_prefetch_desc(&tm_dy);
       tma_prefetch_desc(&tm_x);
+      if (kx > kxa) tma_prefetch_desc(&tm_xb);
       int xi = 0;
       long long c_pe = 0, c_xe = 0;
       Tm tm;
@@ -840,7 +846,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs 
           mbar_wait(&s_xempty[s], ((xi / S) & 1) ^ 1);              // the MMAs that read the slot's previous atom have completed
           tm.stop(c_xe);
           mbar_expect_tx(&s_xland[s], kAtomBytes);
-          tma_load_2d(xhi + s * kAtomBytes, &tm_x, 32 * j, row0, &s_xland[s]);
+          if (j < kxa) tma_load_2d(xhi + s * kAtomBytes, &tm_x, 32 * j, row0, &s_xland[s]);
+          else tma_load_2d(xhi + s * kAtomBytes, &tm_xb, 32 * (j - kxa), row0, &s_xland[s]);
         }
       }
       if (g_dbg && blockIdx.x == 0) { g_dbg[16] = c_pe; g_dbg[17] = c_xe; g_dbg[18] = TNF_CLK() - t_start; }
@@ -945,28 +952,54 @@ __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs 
     // (Transposing the tile through shared memory for contiguous reductions was measured and is no faster.)
     const int n_out = (warp * 32 + lane) & 63;      // lanes n and n + 64 hold the dY_hi / dY_lo rows of feature n
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-    const bool vec = (A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(A.dW) & 15u) == 0;
+    // With a scratch tile (rows of 32 kx floats, atom j at columns 32 j) every reduction is a 16-byte one whatever the
+    // alignment of dW's rows and of the second source's first column; the last CTA to finish adds the tile into dW.
+    const bool to_scratch = A.scratch != nullptr;
+    const bool vec = to_scratch || ((A.K & 3) == 0 && (A.col_b & 3) == 0 && (reinterpret_cast<uintptr_t>(A.dW) & 15u) == 0);
     const int j0 = blockIdx.x % kx, i0 = (blockIdx.x / kx) & 7;
     for (int jj = 0; jj < kx; ++jj) {
       const int j = (j0 + jj) % kx;
-      float* dst = A.dW + (long long)n_out * A.K + 32 * j;
+      const int cb = to_scratch ? 32 * j : (j < kxa ? 32 * j : A.col_b + 32 * (j - kxa));   // first column of the atom
+      const int lim = to_scratch ? 32 * kx : (j < kxa ? A.col_b : A.K);                    // its source's columns end here
+      float* dst = to_scratch ? A.scratch + (long long)n_out * (32 * kx) + cb : A.dW + (long long)n_out * A.K + cb;
 #pragma unroll 2
       for (int ii = 0; ii < 8; ++ii) {
         const int c4 = 4 * ((i0 + ii) & 7);
         float v[4], u[4];
         tmem_ld4x2(taddr + 64 * j + c4, taddr + 64 * j + 32 + c4, v, u);   // x X_hi, x X_lo
-        const int col = 32 * j + c4;
+        const int col = cb + c4;
         float* p = dst + c4;
-        if (vec && col + 3 < A.K) red_add_f4(p, make_float4(v[0] + u[0], v[1] + u[1], v[2] + u[2], v[3] + u[3]));   // one L2 reduction per 16 bytes
+        if (vec && col + 3 < lim) red_add_f4(p, make_float4(v[0] + u[0], v[1] + u[1], v[2] + u[2], v[3] + u[3]));   // one L2 reduction per 16 bytes
         else {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if (col + e < A.K) atomicAdd(p + e, v[e] + u[e]);
+            if (col + e < lim) atomicAdd(p + e, v[e] + u[e]);
         }
       }
     }
   }
   tc_fence_before();
+  if (A.scratch) {
+    // last CTA: dW += scratch tile, which it leaves zeroed for the next launch (threadfence-reduction pattern)
+    __shared__ int s_last;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(A.scratch + 64 * 32 * kx);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int W = 32 * kx;
+      for (int e = tid; e < 64 * W; e += kW3Threads) {
+        const int r = e / W, sc = e - r * W, j = sc >> 5;
+        const float v = __ldcg(A.scratch + e);
+        A.scratch[e] = 0.f;
+        const int col = j < kxa ? sc : A.col_b + (sc - 32 * kxa);
+        if (col < (j < kxa ? A.col_b : A.K)) A.dW[(long long)r * A.K + col] += v;
+      }
+      if (tid == 0) *counter = 0u;
+    }
+  }
   __syncthreads();
   if (g_dbg && tid == 0 && blockIdx.x == 0) g_dbg[30] = TNF_CLK() - c0;
   if (warp == 8) tmem_dealloc(s_tmem, 512);
@@ -1088,6 +1121,34 @@ __global__ void __launch_bounds__(256) color_input_kernel(const float* __restric
   }
 }
 
+// The same row without feature columns ([PE_8(d) | d | 0], 52 floats: the colour input when the feature part is read from the
+// feature rows, tnf_heads_fwd xc_cols < k0).  The generic kernel spends ~300 warp instructions per row on loop and index
+// overhead with 24 of 32 lanes in sincosf; here four threads share a row: thread c < 3 evaluates the 8 frequencies of
+// coordinate c and writes its 16 outputs as four 16-byte stores, thread 3 writes [d | 0].  Same arguments, same sincosf.
+__global__ void __launch_bounds__(256) pe8_dirs_kernel(const float* __restrict__ dirs, long long ld_dirs, float* __restrict__ out,
+                                                       long long ld_out, long long n) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long row = t >> 2;
+  const int c = (int)(t & 3);
+  if (row >= n) return;
+  const float* d = dirs + row * ld_dirs;
+  float* o = out + row * ld_out;
+  if (c == 3) {
+    *reinterpret_cast<float4*>(o + 48) = make_float4(__ldg(d), __ldg(d + 1), __ldg(d + 2), 0.f);
+    for (int j = 52; j < ld_out; ++j) o[j] = 0.f;
+    return;
+  }
+  const float x = __ldg(d + c);
+  float sv[8], cv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sincosf(__fmul_rn(x, ldexpf(3.14159274101257324219f, k)), &sv[k], &cv[k]);
+  float4* o4 = reinterpret_cast<float4*>(o + 16 * c);
+  o4[0] = make_float4(sv[0], sv[1], sv[2], sv[3]);
+  o4[1] = make_float4(sv[4], sv[5], sv[6], sv[7]);
+  o4[2] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+  o4[3] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+}
+
 int check_lin(long long M, int N, int K) {
   TNF_REQUIRE(M >= 0, "negative M");
   TNF_REQUIRE(N >= 8 && N <= 128 && N % 8 == 0, "out_features must be a multiple of 8 in [8,128] (got %d)", N);
@@ -1116,6 +1177,37 @@ int make_box_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TNF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TNF_OK;
+}
+
+// 64-wide layers: A operand in tensor memory, loads by the copy engine (wgrad_tma_kernel).  X = [xa (ka columns) | xb (kb columns)].
+int launch_wgrad_tma(const float* dy, int64_t lddy, const float* xa, int64_t ldxa, int ka, const float* xb, int64_t ldxb, int kb,
+                     float* dweight, float* dbias, float* scratch, int64_t m, cudaStream_t st) {
+  LinArgs A{};
+  A.dW = dweight; A.db = dbias; A.M = m; A.N = 64; A.K = ka + kb; A.scratch = scratch;
+  A.n_tiles = (int)ceil_div(m, 128);
+  A.kxa = (ka + 31) / 32;
+  A.col_b = ka;
+  const int kx = A.kxa + (kb + 31) / 32;
+  TNF_REQUIRE(kx >= 1 && kx <= kMaxKAtoms, "wgrad: at most %d input atoms (got %d)", kMaxKAtoms, kx);
+  A.raw = (2 * 128 + 64 * kx <= 512) ? 2 : 1;
+  CUtensorMap tm_dy, tm_x, tm_xb;
+  int rc = make_box_map(&tm_dy, dy, m, 64, lddy, 64, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc != TNF_OK) return rc;
+  rc = make_box_map(&tm_x, xa, m, ka, ldxa, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != TNF_OK) return rc;
+  rc = kb > 0 ? make_box_map(&tm_xb, xb, m, kb, ldxb, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : TNF_OK;
+  if (rc != TNF_OK) return rc;
+  if (kb == 0) tm_xb = tm_x;
+  const size_t smem = (size_t)(2 * kW3Y + kW3XHi + kW3XLo) * kAtomBytes + 1024;
+  static thread_local bool configured_tma = false;
+  if (!configured_tma) {
+    TNF_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    configured_tma = true;
+  }
+  const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
+  wgrad_tma_kernel<<<grid, kW3Threads, smem, st>>>(A, tm_dy, tm_x, tm_xb);
+  TNF_LAUNCH_CHECK("linear_wgrad_tma_kernel");
   return TNF_OK;
 }
 
@@ -1208,26 +1300,8 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const char* variant = getenv("TNF_WGRAD");   // diagnostics: "ss" / "ts" select the older kernels
   const bool want_ss = variant && !strcmp(variant, "ss"), want_ts = variant && !strcmp(variant, "ts");
-  if (n == 64 && m < (1LL << 31) - 256 && !want_ss && !want_ts) {
-    // 64-wide layers: A operand in tensor memory, loads by the copy engine (wgrad_tma_kernel)
-    const int kx = (k + 31) / 32;
-    A.raw = (2 * 128 + 64 * kx <= 512) ? 2 : 1;
-    CUtensorMap tm_dy, tm_x;
-    rc = make_box_map(&tm_dy, dy, m, n, lddy, 64, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc != TNF_OK) return rc;
-    rc = make_box_map(&tm_x, x, m, k, ldx, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc != TNF_OK) return rc;
-    const size_t smem = (size_t)(2 * kW3Y + kW3XHi + kW3XLo) * kAtomBytes + 1024;
-    static thread_local bool configured_tma = false;
-    if (!configured_tma) {
-      TNF_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      configured_tma = true;
-    }
-    const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
-    wgrad_tma_kernel<<<grid, kW3Threads, smem, st>>>(A, tm_dy, tm_x);
-    TNF_LAUNCH_CHECK("linear_wgrad_tma_kernel");
-    return TNF_OK;
-  }
+  if (n == 64 && m < (1LL << 31) - 256 && !want_ss && !want_ts)
+    return launch_wgrad_tma(dy, lddy, x, ldx, k, nullptr, 0, 0, dweight, dbias, nullptr, m, st);
   if (n == 64 && !want_ss) {
     // 64-wide layers: A operand in tensor memory (wgrad_ts_kernel)
     const int kx = (k + 31) / 32;
@@ -1263,6 +1337,25 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   return TNF_OK;
 }
 
+extern "C" int64_t tnf_wgrad_cat_scratch_bytes(int32_t ka, int32_t kb) {
+  return (int64_t)(64 * 32 * ((ka + 31) / 32 + (kb + 31) / 32) + 4) * 4;
+}
+
+extern "C" int tnf_linear_bwd_weight_cat(const float* dy, int64_t lddy, const float* xa, int64_t ldxa, int32_t ka, const float* xb,
+                                         int64_t ldxb, int32_t kb, float* dweight, float* dbias, int64_t m, int32_t n,
+                                         float* scratch, void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(m >= 0 && ka >= 1 && kb >= 1, "bad sizes");
+  TNF_REQUIRE(n == 64, "the two-source weight gradient is implemented for 64 output features");
+  TNF_REQUIRE(m < (1LL << 31) - 256, "too many rows for the tensor-map coordinates");
+  if (m == 0) return TNF_OK;
+  TNF_REQUIRE(dy && xa && xb && dweight, "null pointer");
+  TNF_REQUIRE(al16(dy) && lddy % 4 == 0 && al16(xa) && ldxa % 4 == 0 && al16(xb) && ldxb % 4 == 0,
+              "dy/xa/xb must be 16-byte aligned with ld %% 4 == 0");
+  TNF_REQUIRE(!scratch || al16(scratch), "scratch must be 16-byte aligned");
+  return launch_wgrad_tma(dy, lddy, xa, ldxa, ka, xb, ldxb, kb, dweight, dbias, scratch, m, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int tnf_color_input(const float* dirs, int64_t ld_dirs, const float* feats, int64_t ld_feats, int32_t n_freqs,
                                int32_t feat_dim, float* out, int64_t ld_out, int64_t n, void* stream) {
   using namespace tnf;
@@ -1270,6 +1363,11 @@ extern "C" int tnf_color_input(const float* dirs, int64_t ld_dirs, const float* 
   if (n == 0) return TNF_OK;
   TNF_REQUIRE(dirs && (feats || feat_dim == 0) && out, "null pointer");
   TNF_REQUIRE(ld_out >= 6 * n_freqs + 3 + feat_dim, "ld_out too small");
+  if (n_freqs == 8 && feat_dim == 0 && ld_out >= 52 && ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    pe8_dirs_kernel<<<(unsigned)ceil_div(n * 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dirs, ld_dirs, out, ld_out, n);
+    TNF_LAUNCH_CHECK("pe8_dirs_kernel");
+    return TNF_OK;
+  }
   color_input_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       dirs, ld_dirs, feats, ld_feats, n_freqs, feat_dim, out, ld_out, n);
   TNF_LAUNCH_CHECK("color_input_kernel");

@@ -114,6 +114,15 @@ class FusedKPlanesStep:
                 self._heads_bwd_ws = torch.empty(int(_lib.load().tnf_heads_bwd_workspace_bytes(self.feat)) // 4, device=self.dev)
         else:
             self.fused_heads_bwd = False
+        # With both fused head kernels the colour-input row cat([PE(d), d], features) (src/models.py:87) is never written:
+        # `xc` holds only its first pe_width columns, the heads' forward and the first layer's weight gradient read the
+        # rest from the feature rows (TNF_SPLIT_XC=0 keeps the materialised row).
+        self.pe_width = 6 * self.n_freqs + 3
+        self.split_xc = self.fused_heads and self.fused_heads_bwd and os.environ.get("TNF_SPLIT_XC", "1") != "0"
+        if self.split_xc:
+            self.xc_ld = _pad4(self.pe_width)
+            # partial-sum tile of the first colour layer's weight gradient (zero between calls)
+            self._wcat_scratch = torch.zeros(int(_lib.load().tnf_wgrad_cat_scratch_bytes(self.pe_width, self.feat)) // 4, device=self.dev)
 
     def attach_grads(self) -> None:
         """p.grad = its view of the flat gradient buffer (undoes optimizer.zero_grad(set_to_none=True))."""
@@ -131,7 +140,9 @@ class FusedKPlanesStep:
             ws["feats"], ws["dfeat"] = e(cap, self.feat), e(cap, self.feat)
             ws["hs"], ws["dhs"] = e(cap, hid_s), e(cap, hid_s)
             ws["sigma"], ws["gsigma"], ws["w"], ws["gw"] = e(cap), e(cap), e(cap), e(cap)
-            ws["xc"], ws["dxc"] = e(cap, self.xc_ld), e(cap, self.xc_ld)
+            ws["xc"] = e(cap, self.xc_ld)
+            if not self.fused_heads_bwd:
+                ws["dxc"] = e(cap, self.xc_ld)
             for i in range(len(self.col_lin) - 1):
                 ws[f"h{i}"] = e(cap, hid_c)
             for i in range(len(self.col_lin) - 1):
@@ -230,11 +241,13 @@ class FusedKPlanesStep:
             call("tnf_kplanes_fwd", self._plane_ptrs, self._res_scales, self.n_scales, self.channels, P(packed), 7, n,
                  P(ws["feats"]), st, nbytes=n * (12 + 4 * F) + self._plane_bytes)
             if self.fused_heads:
-                call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, F, P(ws["xc"]), xld, n, st,
-                     nbytes=n * (12 + 4 * F + 4 * xld))
+                xc_feat = 0 if self.split_xc else F   # feature columns copied into the colour-input row
+                call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, xc_feat, P(ws["xc"]), xld, n, st,
+                     nbytes=n * (12 + 4 * xc_feat + 4 * xld))
                 hptrs = (C.c_void_p * 4)(*[P(ws[f"h{i}"]) for i in range(4)])
                 mlp_flops = 2 * n * (64 * (F + 1) + 64 * xw + 3 * 64 * 64 + 3 * 64)
-                call("tnf_heads_fwd", P(ws["feats"]), F, F, P(ws["xc"]), xld, xw, self._cw, self._cb, self._sw, self._sb, hptrs,
+                call("tnf_heads_fwd", P(ws["feats"]), F, F, P(ws["xc"]), xld, xw, self.pe_width if self.split_xc else xw,
+                     self._cw, self._cb, self._sw, self._sb, hptrs,
                      P(ws["hs"]), P(ws["rgb"]), P(ws["sigma"]), n, P(self._heads_ws), st,
                      nbytes=4 * n * (F + xld + 5 * 64 + 4), flops=mlp_flops)
             else:
@@ -299,7 +312,12 @@ class FusedKPlanesStep:
             # weight gradients of both heads
             for i in range(nh - 1, 0, -1):
                 wgrad(P(dh[i]), hc_w, P(ws[f"h{i - 1}"]), hc_w, cl[i])
-            wgrad(P(dh[0]), hc_w, P(ws["xc"]), xld, cl[0])
+            if self.split_xc:
+                call("tnf_linear_bwd_weight_cat", P(dh[0]), hc_w, P(ws["xc"]), xld, self.pe_width, P(ws["feats"]), F, F,
+                     G(cl[0].weight), G(cl[0].bias), n, hc_w, P(self._wcat_scratch), st, nbytes=4 * (n * (hc_w + xld + F) + hc_w * xw),
+                     flops=2 * n * hc_w * xw)
+            else:
+                wgrad(P(dh[0]), hc_w, P(ws["xc"]), xld, cl[0])
             wgrad(P(ws["dhs"]), hs_w, P(ws["feats"]), F, sl[0])
             if work is not None:
                 dist.all_reduce(self.flat_grad[self._plane_grad_end:])
