@@ -321,9 +321,13 @@ def main():
 
     def one_step(tr, read_loss: bool):
         info = tr.step()
-        if read_loss:
-            float(info["loss"])  # D2H of the step's result
+        if read_loss and tr.train_step >= 2:
+            # D2H of the step's result: every iteration's loss is copied to pinned host memory (Trainer._publish_loss) and
+            # consumed here one iteration late, so the host never drains the pipeline (the last one is read in timed())
+            losses.append(tr.read_loss(tr.train_step - 2))
         return info["n_samples"]
+
+    losses = []
 
     def barrier():
         if world > 1:
@@ -345,6 +349,8 @@ def main():
         for _ in range(steps):
             n += one_step(tr, read_loss)
             per.append(time.perf_counter())
+        if read_loss:
+            losses.append(tr.read_loss())   # the latest iteration's loss: inside the timed region
         e.record()
         host_ms.append((time.perf_counter() - h0) * 1e3 / steps)  # host time per step (includes the batch-size sync)
         raw = [b - a for a, b in zip([h0] + per[:-1], per)]
@@ -423,7 +429,8 @@ def main():
                        "packed_samples_per_step_per_gpu": round(n / args.steps / world), "grid": "128^3 analytic ball+torus",
                        "l2": "inputs change every step (fresh rays; 396 MB of plane params+grads+Adam state stream through L2 > 126 MB)",
                        "parallelism": f"ray-sharded dp{world}", "host_wait": "blocking" if blocking_sync else "spin",
-                       "settle_steps": settle},
+                       "settle_steps": settle,
+                       "e2e_loss_readback": "every step, async D2H into a pinned ring, consumed one step late"},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": round(ms2 / args.steps, 4)},
             "gpu_launches": int(launches), "host_ms_per_step": round(host_ms[0], 4), "host_step_ms": {"value_arm": host_dist[0], "e2e_arm": host_dist[-1]}, "clocks": clk, "roofline": roof, "kernels": table,

@@ -293,6 +293,13 @@ int tnf_mse_loss_grad(const float* rendered, const float* target, int64_t n_rays
                       const float* n_rays_global_dev /*optional*/, float grad_scale, float* grad_rendered /*optional*/,
                       float* loss_out /*optional*/, void* stream);
 
+/* ---- host helper: lazily shuffled ray order (DataLoader(shuffle=True), src/run.py:116-122) --------------------------------
+ * HOST pointers.  perm: n entries, initially 0..n-1 (any permutation); out receives `count` ray indices.  pos is a global
+ * position counter (a multiple of world; advance it by count*world), *fresh_from the first position never drawn so far
+ * (start at 0), rng_state one 64-bit word of generator state.  Positions below *fresh_from are replayed unchanged. */
+int tnf_shuffle_next(int64_t* perm, int64_t n, int64_t pos, int64_t count, int32_t rank, int32_t world, int64_t* fresh_from,
+                     uint64_t* rng_state, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

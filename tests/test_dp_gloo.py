@@ -49,7 +49,7 @@ def _worker(rank, world, port, n_rays, out_path):
     # ranks take different numbers of rays (dynamic batches): rank 0 -> 40, rank 1 -> 24
     take = 40 if rank == 0 else 24
     ro, rd, target = store.next(take)
-    idx = store._perm[:take].clone()
+    idx = store.last_indices.clone()
     m = _model(5)
     out = _render(m, ro, rd, grid)
     loss = dp_mse(out, target, global_ray_count(take, "cpu", world))
@@ -101,6 +101,18 @@ def test_ray_store_shards_are_a_partition_of_each_epoch():
         a, _, _ = st.next(10)
         seen += a[:, 0].int().tolist()
     assert sorted(seen) == list(range(30))
+    # the order is shuffled lazily (tnf_shuffle_next): over any n consecutive positions every ray appears once, a rewind
+    # replays the same rays, and the next epoch is a different order
+    st = RayStore(o, o, o, "cpu", seed=5)
+    first = st.next(30)[0][:, 0].int().tolist()
+    assert sorted(first) == list(range(30)) and first != list(range(30))
+    a = st.next(12)[0][:, 0].int().tolist()
+    st.rewind(7)
+    b = st.next(7)[0][:, 0].int().tolist()
+    assert b == a[5:]
+    rest = st.next(18)[0][:, 0].int().tolist()
+    assert sorted(a + rest) == list(range(30)) and a + rest != first
+    assert RayStore(o, o, o, "cpu", seed=5).next(30)[0][:, 0].int().tolist() == first   # seeded
     assert shard_slices(128, 3, 8) == (48, 64)
     with pytest.raises(ValueError):
         shard_slices(128, 0, 3)

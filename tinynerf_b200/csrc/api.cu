@@ -43,3 +43,49 @@ extern "C" int tnf_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   TNF_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
   return TNF_OK;
 }
+
+// ---- host-side ray shuffling (the reference shuffles with DataLoader(shuffle=True), src/run.py:116-122) --------------------
+// Incremental Fisher-Yates: `perm` (host, n entries, initially 0..n-1) is shuffled lazily, `count` positions per call, so an
+// epoch never starts with an O(n) randperm (tens of milliseconds for millions of rays, seconds for a full-resolution scene)
+// landing inside one training step.  Positions are a global counter g (slot g % n); g < *fresh_from have been drawn before
+// (rays handed back by the dynamic-batch accumulator) and are re-read without consuming random numbers, so a replay returns
+// the same rays.  With `world` ranks every rank walks the same sequence and keeps the positions g % world == rank.
+static inline uint64_t tnf_splitmix64(uint64_t* s) {
+  uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static inline uint64_t tnf_bounded(uint64_t* s, uint64_t range) {   // uniform in [0, range), Lemire's method (unbiased)
+  uint64_t x = tnf_splitmix64(s);
+  __uint128_t m = (__uint128_t)x * range;
+  uint64_t lo = (uint64_t)m;
+  if (lo < range) {
+    const uint64_t t = (0 - range) % range;
+    while (lo < t) {
+      x = tnf_splitmix64(s);
+      m = (__uint128_t)x * range;
+      lo = (uint64_t)m;
+    }
+  }
+  return (uint64_t)(m >> 64);
+}
+extern "C" int tnf_shuffle_next(int64_t* perm, int64_t n, int64_t pos, int64_t count, int32_t rank, int32_t world,
+                                int64_t* fresh_from, uint64_t* rng_state, int64_t* out) {
+  using namespace tnf;
+  TNF_REQUIRE(perm && fresh_from && rng_state && out, "null pointer");
+  TNF_REQUIRE(n >= 1 && pos >= 0 && count >= 0 && world >= 1 && rank >= 0 && rank < world, "bad sizes");
+  int64_t k = 0;
+  for (int64_t g = pos; g < pos + count * world; ++g) {
+    const int64_t i = g % n;
+    if (g >= *fresh_from) {
+      const int64_t j = i + (int64_t)tnf_bounded(rng_state, (uint64_t)(n - i));
+      const int64_t t = perm[i];
+      perm[i] = perm[j];
+      perm[j] = t;
+      *fresh_from = g + 1;
+    }
+    if (g % world == rank) out[k++] = perm[i];
+  }
+  return TNF_OK;
+}

@@ -8,6 +8,8 @@
 //
 // tnf_adam_step: torch.optim.Adam (src/run.py:186: lr, betas, eps, L2 weight_decay, no amsgrad) for a
 // table of tensors in one launch: p, g, m, v read once, p, m, v written once (28 B/param).
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace tnf {
@@ -129,6 +131,118 @@ __global__ void __launch_bounds__(256) tv_bwd_kernel(const TVArgs A) {
   }
 }
 
+// The same pass for 32-channel planes whose resolution is a multiple of 32, organised so that every texel is fetched from
+// HBM once: a warp owns 4 adjacent columns (lane = texel-in-group * 8 + channel quad: one row of the group is 512
+// contiguous bytes) and marches down a segment of kTvRows rows with the rows above / at / below in registers; the left and
+// right neighbours come from the adjacent lane groups by shuffle, only the two edge columns of the group are loaded (lines
+// the neighbouring warp of the same block is streaming anyway).  tv_bwd_kernel loads five texels per output texel and
+// leans on L1/L2 for the four re-reads (3.1 TB/s of algorithmic traffic); this one issues 1 + 2/4 loads per texel.
+// Arithmetic per texel is identical to tv_bwd_kernel; the sums are accumulated per thread in fp32 (128 terms) and across threads in double.
+constexpr int kTvRows = 32;
+struct TVMarchArgs {
+  TVArgs tv;
+  long long first_warp[kMaxPlanes + 1];   // warps [first_warp[i], first_warp[i+1]) work on plane i
+};
+template <bool SUMS, bool ACC>
+__global__ void __launch_bounds__(256, 3) tv_march_kernel(const TVMarchArgs M) {
+  const TVArgs& A = M.tv;
+  __shared__ double s_red[2][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * 8 + wid;
+  int pi = 0;
+  while (pi + 1 < A.n_planes && gw >= M.first_warp[pi + 1]) ++pi;   // all warps of a block are in one plane (res % 32 == 0)
+  const int res = A.res[pi];
+  const long long lw = gw - M.first_warp[pi];
+  const int groups = res >> 2;                        // column groups per row segment
+  const int seg = (int)(lw / groups), grp = (int)(lw % groups);
+  const int tg = lane >> 3, quad = lane & 7;
+  const int w = 4 * grp + tg, h0 = seg * kTvRows;
+  const float gs = __ldg(A.gscale);
+  const float ch = A.coef_h[pi] * gs, cw = A.coef_w[pi] * gs;
+  const long long sH = (long long)res * 32;           // floats per row
+  const float* p = A.planes[pi] + ((long long)h0 * res + w) * 32 + quad * 4;
+  float* gout = A.grads[pi] + ((long long)h0 * res + w) * 32 + quad * 4;
+  const bool has_l = w > 0, has_r = w + 1 < res;
+  const bool edge_l = tg == 0 && has_l, edge_r = tg == 3 && has_r;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 up = h0 > 0 ? ld_stream_f4(p - sH) : zero;
+  float4 cur = ld_stream_f4(p);
+  float shf = 0.f, swf = 0.f;   // 32 rows x 4 channels per thread: fp32 is plenty; widened before the cross-thread sums
+#pragma unroll 1
+  for (int r0 = 0; r0 < kTvRows; r0 += 4) {
+    float4 nxt[4], el[4], er[4], old[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // every load of the four rows is issued before the first use
+      const int h = h0 + r0 + i;
+      nxt[i] = (h + 1 < res) ? ld_stream_f4(p + (long long)(r0 + i + 1) * sH) : zero;
+      el[i] = edge_l ? ld4(p + (long long)(r0 + i) * sH - 32) : zero;
+      er[i] = edge_r ? ld4(p + (long long)(r0 + i) * sH + 32) : zero;
+      if (ACC) old[i] = *reinterpret_cast<const float4*>(gout + (long long)(r0 + i) * sH);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int h = h0 + r0 + i;
+      const float4 v = cur, dn = nxt[i];
+      float4 lf, rt;
+      lf.x = __shfl_up_sync(kFullMask, v.x, 8); lf.y = __shfl_up_sync(kFullMask, v.y, 8);
+      lf.z = __shfl_up_sync(kFullMask, v.z, 8); lf.w = __shfl_up_sync(kFullMask, v.w, 8);
+      rt.x = __shfl_down_sync(kFullMask, v.x, 8); rt.y = __shfl_down_sync(kFullMask, v.y, 8);
+      rt.z = __shfl_down_sync(kFullMask, v.z, 8); rt.w = __shfl_down_sync(kFullMask, v.w, 8);
+      if (tg == 0) lf = el[i];
+      if (tg == 3) rt = er[i];
+      float4 g = zero;
+      if (h > 0) { g.x += ch * (v.x - up.x); g.y += ch * (v.y - up.y); g.z += ch * (v.z - up.z); g.w += ch * (v.w - up.w); }
+      if (h + 1 < res) {
+        g.x -= ch * (dn.x - v.x); g.y -= ch * (dn.y - v.y); g.z -= ch * (dn.z - v.z); g.w -= ch * (dn.w - v.w);
+        if (SUMS) shf += sq4(dn, v);
+      }
+      if (has_l) { g.x += cw * (v.x - lf.x); g.y += cw * (v.y - lf.y); g.z += cw * (v.z - lf.z); g.w += cw * (v.w - lf.w); }
+      if (has_r) {
+        g.x -= cw * (rt.x - v.x); g.y -= cw * (rt.y - v.y); g.z -= cw * (rt.z - v.z); g.w -= cw * (rt.w - v.w);
+        if (SUMS) swf += sq4(rt, v);
+      }
+      if (ACC) { g.x += old[i].x; g.y += old[i].y; g.z += old[i].z; g.w += old[i].w; }
+      st_stream_f4(gout + (long long)(r0 + i) * sH, g);
+      up = cur;
+      cur = dn;
+    }
+  }
+  if (SUMS) {
+    double sh = (double)shf, sw = (double)swf;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sh += __shfl_xor_sync(kFullMask, sh, d);
+      sw += __shfl_xor_sync(kFullMask, sw, d);
+    }
+    if (lane == 0) { s_red[0][wid] = sh; s_red[1][wid] = sw; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc += s_red[threadIdx.x][i];
+      atomicAdd(A.sums + 2 * pi + threadIdx.x, acc);
+    }
+  }
+}
+// launches tv_march_kernel when the planes allow it; returns false (nothing launched) otherwise
+template <bool SUMS>
+bool launch_tv_march(const TVArgs& A, cudaStream_t st) {
+  const char* force = getenv("TNF_TV_KERNEL");   // diagnostics / tests: "texel" keeps the one-thread-per-texel kernel
+  if (A.channels != 32 || (force && !strcmp(force, "texel"))) return false;
+  TVMarchArgs M{};
+  M.tv = A;
+  long long warps = 0;
+  for (int i = 0; i < A.n_planes; ++i) {
+    if (A.res[i] % 32 != 0 || A.res[i] < 32) return false;
+    M.first_warp[i] = warps;
+    warps += (long long)(A.res[i] / 4) * (A.res[i] / kTvRows);
+  }
+  M.first_warp[A.n_planes] = warps;   // a multiple of 8: res/4 is
+  if (A.accumulate) tv_march_kernel<SUMS, true><<<(unsigned)(warps / 8), 256, 0, st>>>(M);
+  else tv_march_kernel<SUMS, false><<<(unsigned)(warps / 8), 256, 0, st>>>(M);
+  return true;
+}
+
 int fill_tv(TVArgs* A, const float* const* planes, float* const* grads, const int32_t* res, int n_planes,
             int channels) {
   TNF_REQUIRE(n_planes >= 1 && n_planes <= kMaxPlanes, "n_planes must be in [1,%d]", kMaxPlanes);
@@ -237,7 +351,8 @@ extern "C" int tnf_tv_bwd(const float* const* planes, float* const* grads, const
     for (int i = 0; i < n_planes; ++i) { A.coef_h[i] *= plane_weight[i]; A.coef_w[i] *= plane_weight[i]; }
   A.gscale = gscale;
   A.accumulate = accumulate;
-  tv_bwd_kernel<false><<<(unsigned)A.first_block[n_planes], 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  if (!launch_tv_march<false>(A, static_cast<cudaStream_t>(stream)))
+    tv_bwd_kernel<false><<<(unsigned)A.first_block[n_planes], 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   TNF_LAUNCH_CHECK("tv_bwd_kernel");
   return TNF_OK;
 }
@@ -257,7 +372,7 @@ extern "C" int tnf_tv_fwd_bwd(const float* const* planes, float* const* grads, c
   A.sums = sums;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TNF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * n_planes, st));
-  tv_bwd_kernel<true><<<(unsigned)A.first_block[n_planes], 256, 0, st>>>(A);
+  if (!launch_tv_march<true>(A, st)) tv_bwd_kernel<true><<<(unsigned)A.first_block[n_planes], 256, 0, st>>>(A);
   TNF_LAUNCH_CHECK("tv_fwd_bwd_kernel");
   return TNF_OK;
 }

@@ -13,6 +13,7 @@ metrics, image writing and the CLI are out of scope (callers own them).
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
@@ -102,31 +103,52 @@ class RayStore:
         data = torch.cat([rays_o, rays_d, rgbs], -1).float().contiguous()  # [n, 9]
         self.data = data.pin_memory() if host else data.to(self.device)
         self.n = data.size(0)
-        self.gen = torch.Generator(device="cpu" if host else self.device)
-        self.gen.manual_seed(seed)
+        # The order is an incremental Fisher-Yates shuffle on the host (tnf_shuffle_next): each call shuffles just the
+        # positions it hands out, so no step ever pays an O(n) randperm at an epoch boundary (tens of milliseconds for
+        # millions of rays).  Every n positions each ray has been handed out exactly once; every rank walks the same seeded
+        # sequence and keeps the positions g % world == rank.
+        self._order = torch.arange(self.n, dtype=torch.int64)
+        self._rng = C.c_uint64((0x9E3779B97F4A7C15 * (2 * int(seed) + 1)) & 0xFFFFFFFFFFFFFFFF)
+        self._fresh = C.c_int64(0)     # first global position never drawn so far
+        self._pos = 0                  # global position of this rank's next batch (a multiple of world)
         self.h2d_bytes = 0
-        self._perm = None
-        self._pos = 0
         self._stage = None
-
-    def _reshuffle(self):
-        perm = torch.randperm(self.n, generator=self.gen, device=self.gen.device)
-        self._perm = perm[self.rank::self.world]
-        self._pos = 0
+        self._idx_ring, self._idx_i = [], 0
 
     def rewind(self, n_rays: int) -> None:
-        """Give back the last `n_rays` rays handed out by next() (speculatively marched, not used)."""
-        self._pos -= n_rays
+        """Give back the last `n_rays` rays handed out by next() (speculatively marched, not used): the same rays come
+        out again, in the same order."""
+        self._pos -= n_rays * self.world
         assert self._pos >= 0
 
     def remaining(self) -> int:
-        return 0 if self._perm is None else self._perm.numel() - self._pos
+        """Rays left before the order wraps around; the shuffle is continuous, so a batch may straddle the wrap."""
+        return self.n
+
+    def _next_indices(self, batch: int) -> torch.Tensor:
+        on_gpu = (not self.host) and self.device.type == "cuda"
+        if on_gpu:
+            # pinned staging for the asynchronous upload of the indices; a small ring, because an upload may still be in
+            # flight when the next batch is drawn (the consumer syncs once per batch, so 4 slots are never all busy)
+            if len(self._idx_ring) < 4 or self._idx_ring[self._idx_i].numel() < batch:
+                buf = torch.empty(max(batch, 1), dtype=torch.int64).pin_memory()
+                if len(self._idx_ring) < 4:
+                    self._idx_ring.append(buf)
+                    self._idx_i = len(self._idx_ring) - 1
+                else:
+                    self._idx_ring[self._idx_i] = buf
+            out = self._idx_ring[self._idx_i][:batch]
+            self._idx_i = (self._idx_i + 1) % 4
+        else:
+            out = torch.empty(batch, dtype=torch.int64)
+        _lib.check(_lib.load().tnf_shuffle_next(self._order.data_ptr(), self.n, self._pos, batch, self.rank, self.world,
+                                                C.byref(self._fresh), C.byref(self._rng), out.data_ptr()), "tnf_shuffle_next")
+        self._pos += batch * self.world
+        self.last_indices = out   # host view of the batch just drawn (valid until the staging slot is reused)
+        return out.to(self.device, non_blocking=True) if on_gpu else out
 
     def next(self, batch: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        if self._perm is None or self._pos + batch > self._perm.numel():
-            self._reshuffle()
-        idx = self._perm[self._pos:self._pos + batch]
-        self._pos += batch
+        idx = self._next_indices(batch)
         if self.host:
             if self._stage is None or self._stage.size(0) < batch:  # grow-only: pinning memory is a slow, synchronising call
                 self._stage = torch.empty(max(batch, 2 * (0 if self._stage is None else self._stage.size(0))), 9).pin_memory()
@@ -227,6 +249,7 @@ class Trainer:
         self._gc_frozen = False
         self._queue: List = []          # prefetched (batch, done event), oldest first
         self._inflight: List = []       # end-of-iteration events of the iterations enqueued and not yet waited for
+        self._loss_ring = None          # pinned host ring the loss of every iteration is copied into (read_loss)
         self._grid_event = None         # recorded after the latest occupancy update: batches marched later must see it
         self.last: Dict[str, float] = {}
 
@@ -424,6 +447,7 @@ class Trainer:
         self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
+        self._publish_loss(loss)
         self._mark_enqueued()
         if self._side is not None:
             # everything above is enqueued; the coming batches are marched on the side stream while the GPU is still
@@ -436,6 +460,32 @@ class Trainer:
         if self.cfg.max_inflight_steps > 0 and self.device.type == "cuda":
             self._inflight.append(torch.cuda.current_stream(self.device).record_event())
 
+    # ---- loss read-back without stalling the pipeline (the reference reads loss.item() every step, src/run.py:263) ----
+    _LOSS_RING = 8
+
+    def _publish_loss(self, loss: torch.Tensor) -> None:
+        """Device -> pinned-host copy of this iteration's loss, asynchronous on the main stream."""
+        if self.device.type != "cuda":
+            return
+        if self._loss_ring is None:
+            self._loss_ring = (torch.zeros(self._LOSS_RING, dtype=torch.float32).pin_memory(),
+                               [torch.cuda.Event() for _ in range(self._LOSS_RING)])
+        buf, evs = self._loss_ring
+        slot = (self.train_step - 1) % self._LOSS_RING
+        buf[slot:slot + 1].copy_(loss.detach().reshape(1).float(), non_blocking=True)
+        evs[slot].record(torch.cuda.current_stream(self.device))
+
+    def read_loss(self, step: int | None = None) -> float:
+        """Host value of the loss of iteration `step` (0-based; default: the latest).  Waits only for that iteration's
+        copy, so reading iteration t-1 while t is in flight costs nothing; at most _LOSS_RING iterations are kept."""
+        last = self.train_step - 1
+        step = last if step is None else step
+        if self._loss_ring is None or not (max(0, last - self._LOSS_RING + 1) <= step <= last):
+            raise ValueError(f"loss of iteration {step} is not available (latest: {last})")
+        buf, evs = self._loss_ring
+        evs[step % self._LOSS_RING].synchronize()
+        return float(buf[step % self._LOSS_RING])
+
     def _step_fused(self, packed, rgbs, info) -> Dict[str, float]:
         """Same iteration through fused.FusedKPlanesStep: identical kernels and order, no autograd / glue ops."""
         n_glob = work = None
@@ -446,6 +496,7 @@ class Trainer:
         self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
+        self._publish_loss(out["loss"])
         self._mark_enqueued()
         if self._side is not None:
             self._prefetch()
