@@ -34,6 +34,11 @@ int tnf_version(void);
 const char* tnf_last_error(void);
 /* Fills [host] ints: SM count, major, minor of the current device. */
 int tnf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* The persistent kernels launch one CTA per SM and split their tiles statically.  While a collective's kernel occupies
+ * some SMs (a gradient all-reduce running under the weight-gradient kernels), CTAs that find no free SM start a whole wave
+ * late; capping the grid at the SMs actually free avoids that.  n_sms <= 0 removes the cap.  Per calling thread; returns
+ * the previous value. */
+int tnf_set_sm_budget(int n_sms);
 
 /* ---- a1/a2: NeRF-equation weights over packed rays -------------------------------------------
  * Replaces src/cuda.cu:66-95 (compute_weights_fwd, kernel :3-30) and src/cuda.cu:97-132

@@ -14,6 +14,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local int g_sm_budget = 0;   // tnf_set_sm_budget: persistent grids of this thread use at most this many SMs
+
 int sm_count() {
   // per-device cache; benign race (same value written)
   static int cache[64] = {0};
@@ -24,12 +26,18 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cache[dev] = n;
   }
-  return cache[dev];
+  return (g_sm_budget > 0 && g_sm_budget < cache[dev]) ? g_sm_budget : cache[dev];
 }
 
 }  // namespace tnf
 
 extern "C" int tnf_version(void) { return 1000; }
+
+extern "C" int tnf_set_sm_budget(int n_sms) {
+  const int prev = tnf::g_sm_budget;
+  tnf::g_sm_budget = n_sms > 0 ? n_sms : 0;
+  return prev;
+}
 
 extern "C" const char* tnf_last_error(void) { return tnf::g_err; }
 

@@ -78,6 +78,11 @@ class FusedKPlanesStep:
         self.flat_grad = torch.zeros(tot, device=self.dev)
         self.grads = [torch.as_strided(self.flat_grad, p.shape, p.stride(), off) for p, off in zip(params, offs)]
         self._plane_grad_end = offs[len(self.planes)]   # flat_grad[:end] = plane gradients, [end:] = the heads' 
+        self._scale_off = [offs[3 * sc] for sc in range(self.n_scales)] + [self._plane_grad_end]   # planes are stored scale by scale
+        self._scale_bytes = [4 * (self._scale_off[sc + 1] - self._scale_off[sc]) for sc in range(self.n_scales)]
+        # per-scale scatter + per-scale all-reduce (finest scale first) was measured at 2 GPUs and is slower than one scatter +
+        # one all-reduce under the weight gradients (294 vs 308 M samples/s: three launches, each disturbed by the collective)
+        self.bucket_scales = os.environ.get("TNF_BUCKET_SCALES", "0") != "0"
         self.params = params
         self._g = {id(p): g for p, g in zip(params, self.grads)}
         self.attach_grads()
@@ -98,6 +103,10 @@ class FusedKPlanesStep:
                                       for r in self._res_planes for _ in range(2)], dtype=torch.float64, device=self.dev)
         self._cap_n = self._cap_r = 0
         self._ws: Dict[str, torch.Tensor] = {}
+        # SMs a concurrent collective kernel occupies (NCCL_MAX_CTAS when set, else the 32 CTAs NCCL uses on NVLink here:
+        # measured at 2 GPUs, capping NCCL at 16 / 8 CTAs slows the step 316 -> 288 -> 244 M samples/s)
+        self._sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        self.collective_ctas = int(os.environ.get("TNF_COLLECTIVE_CTAS", os.environ.get("NCCL_MAX_CTAS", "32"))) if world > 1 else 0
         # both heads' forward in one kernel (tnf_heads_fwd) when the shapes are the reference's: hidden width 64,
         # three hidden colour layers, one hidden density layer.  TNF_FUSED_HEADS=0 keeps the per-layer kernels.
         self.fused_heads = (os.environ.get("TNF_FUSED_HEADS", "1") != "0" and len(self.col_lin) == 5
@@ -304,11 +313,23 @@ class FusedKPlanesStep:
                 torch.add(dfeat, ws["dxc"][:n, xw - F:xw], out=dfeat)
                 _lib.launch_count += 1
             # plane gradients: scatter-add of the data term on top of the TV gradient written at the start
-            call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
-                 P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
-            work = None
-            if reduce and self.world > 1:
-                work = dist.all_reduce(self.flat_grad[:self._plane_grad_end], async_op=True)  # runs under the wgrads
+            work, works = None, []
+            if reduce and self.world > 1 and self.bucket_scales:
+                # data-parallel: finest scale first (76 % of the bytes); its all-reduce starts while the coarser scales are
+                # still being scattered and then runs on under the heads' weight gradients
+                for sc in range(self.n_scales - 1, -1, -1):
+                    call("tnf_kplanes_bwd_scales", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
+                         P(packed), 7, n, P(dfeat), sc, sc + 1, st, nbytes=(n * (12 + 4 * F)) // self.n_scales + 2 * self._scale_bytes[sc])
+                    works.append(dist.all_reduce(self.flat_grad[self._scale_off[sc]:self._scale_off[sc + 1]], async_op=True))
+                work = works.pop()
+            else:
+                call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
+                     P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
+                if reduce and self.world > 1:
+                    work = dist.all_reduce(self.flat_grad[:self._plane_grad_end], async_op=True)  # runs under the wgrads
+            if work is not None and self.collective_ctas > 0:
+                # the collective's CTAs hold whole SMs; leave them out of the weight-gradient kernels' one-CTA-per-SM grids
+                _lib.load().tnf_set_sm_budget(max(16, self._sms - self.collective_ctas))
             # weight gradients of both heads
             for i in range(nh - 1, 0, -1):
                 wgrad(P(dh[i]), hc_w, P(ws[f"h{i - 1}"]), hc_w, cl[i])
@@ -320,7 +341,10 @@ class FusedKPlanesStep:
                 wgrad(P(dh[0]), hc_w, P(ws["xc"]), xld, cl[0])
             wgrad(P(ws["dhs"]), hs_w, P(ws["feats"]), F, sl[0])
             if work is not None:
+                _lib.load().tnf_set_sm_budget(0)
                 dist.all_reduce(self.flat_grad[self._plane_grad_end:])
+                for w in works:
+                    w.wait()
                 work.wait()
             loss = ws["loss"][0]
             if self.tv_alpha != 0.0:
