@@ -224,15 +224,17 @@ def weights_microbench(dev, logn: int, peak: float):
     return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r01_ncu_full.md, M = 2^18 rows / N ~ 2^18 samples): the `traffic` of the roofline object.
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of one training
+# iteration (profiles/r01_ncu_full.md, N = 233,625 packed samples): the `traffic` of the roofline object.
 NCU_TRAFFIC_BYTES = {
-    "tnf_linear_bwd_weight": 171.5e6,   # wgrad_kernel, 96-wide layer instance: 167.9 MB read + 3.6 MB written
-    "tnf_heads_fwd": 548.2e6,           # 257.0 + 291.2 MB
-    "tnf_kplanes_bwd": 652.8e6,         # ~0.5 GB + 152.8 MB
-    "tnf_kplanes_fwd": 294.4e6,         # ~0.2 GB + 94.4 MB
-    "tnf_linear_bwd_data": 171.3e6,
-    "tnf_linear_fwd": 133.0e6,
+    "tnf_kplanes_bwd": 639.1e6,         # kplanes_kernel<1>: 488.1 MB read + 151.0 MB written
+    "tnf_kplanes_fwd": 230.9e6,         # kplanes_kernel<0>: 151.8 + 79.1 MB
+    "tnf_heads_fwd": 390.7e6,           # 138.9 + 251.8 MB
+    "tnf_heads_bwd_data": 596.6e6,      # 331.3 + 265.3 MB
+    "tnf_linear_bwd_weight": 136.5e6,   # wgrad_tma_kernel, 64x64 layer: 132.0 + 4.5 MB
+    "tnf_adam_step": 871.0e6,           # 529.1 + 341.9 MB
+    "tnf_tv_fwd_bwd": 215.5e6,          # tv_march_kernel: 138.7 + 76.8 MB
+    "tnf_head_bwd": 94.0e6,             # head_bwd_kernel<3>: 72.2 + 21.8 MB
 }
 
 
