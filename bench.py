@@ -232,7 +232,7 @@ NCU_TRAFFIC_BYTES = {
     "tnf_heads_fwd": 390.7e6,           # 138.9 + 251.8 MB
     "tnf_heads_bwd_data": 596.6e6,      # 331.3 + 265.3 MB
     "tnf_linear_bwd_weight": 136.5e6,   # wgrad_tma_kernel, 64x64 layer: 132.0 + 4.5 MB
-    "tnf_adam_step": 871.0e6,           # 529.1 + 341.9 MB
+    "tnf_adam_step_grid": 871.0e6,           # 529.1 + 341.9 MB
     "tnf_tv_fwd_bwd": 215.5e6,          # tv_march_kernel: 138.7 + 76.8 MB
     "tnf_head_bwd": 94.0e6,             # head_bwd_kernel<3>: 72.2 + 21.8 MB
 }
@@ -307,6 +307,8 @@ def main():
     analytic = synthetic.analytic_grid(128, seed=SEED + 2).to(dev)
     analytic_mean = analytic.mean().item()
     cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=BATCH, n_samples=N_SAMPLES, seed=SEED)
+    if os.environ.get("TNF_OVERLAP_ADAM") == "1":   # diagnostics: A/B of the planes' Adam beside the weight-gradient kernels
+        cfg.overlap_plane_adam = True
 
     def make_trainer(host: bool):
         torch.manual_seed(SEED)

@@ -191,6 +191,12 @@ int tnf_tv_fwd_bwd(const float* const* planes, float* const* grads, const int32_
 int tnf_adam_step(float* const* params, const float* const* grads, float* const* exp_avg,
                   float* const* exp_avg_sq, const int64_t* numel, int32_t n_tensors, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, void* stream);
+/* Same update with the grid capped at max_blocks 256-thread blocks that stride over the work (0 = one block per 4096
+ * elements): a small persistent grid (one block per SM) can share the SMs with a one-CTA-per-SM tensor-core kernel on another
+ * stream instead of queueing in front of its CTAs. */
+int tnf_adam_step_grid(float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, const int64_t* numel, int32_t n_tensors, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int64_t step, int32_t max_blocks, void* stream);
 
 /* ---- a14: Cobafa fused basis/coefficient lookup ----------------------------------------------
  * Replaces CobafaFeatureField.forward up to the concat (src/models.py:258-264): coef = trilinear

@@ -30,7 +30,7 @@ def test_fused_step_matches_autograd_step():
     for fused in (False, True):
         tr = _trainer(fused)
         assert (tr._fused is not None) == fused
-        tr.optimizer.step = lambda: None  # keep this step's gradients for inspection
+        tr.optimizer.step = lambda *a, **k: None  # keep this step's gradients for inspection
         torch.manual_seed(10)
         info = tr.step()
         res[fused] = ({k: p.grad.clone() for k, p in tr.renderer.named_parameters()}, float(info["loss"]), info["n_samples"])

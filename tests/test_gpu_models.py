@@ -280,7 +280,7 @@ def test_trainer_fused_tv_grad_equals_autograd_path():
         tr.occupancy_grid.grid.copy_(grid_vals)
         tr.occupancy_grid.mean = tr.occupancy_grid.grid.mean().item()
         tr.train_step = 1          # skip the occupancy update of step 0
-        tr.optimizer.step = lambda: None   # keep the gradients of this step for inspection
+        tr.optimizer.step = lambda *a, **k: None   # keep the gradients of this step for inspection
         torch.manual_seed(10)
         info = tr.step()
         grads[fused] = ({k: p.grad.clone() for k, p in tr.renderer.named_parameters()}, float(info["loss"]))

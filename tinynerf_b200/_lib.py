@@ -90,6 +90,9 @@ _SIGNATURES = {
     "tnf_adam_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                 C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
+    "tnf_adam_step_grid": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_float, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int32, C.c_void_p]),
     "tnf_linear_fwd": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                  C.c_int32, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_void_p]),
     "tnf_linear_bwd_data": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64,

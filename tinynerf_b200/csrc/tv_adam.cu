@@ -283,6 +283,7 @@ struct AdamArgs {
   int n_tensors;
   float lr, beta1, beta2, eps, weight_decay;
   float bias1, bias2_sqrt;  // 1 - beta1^t, sqrt(1 - beta2^t)
+  long long total_blocks;   // virtual blocks of 4096 elements; the grid strides over them (grid < total_blocks: persistent form)
 };
 constexpr int kAdamVec = 4;       // floats per thread per iteration
 constexpr int kAdamPerBlock = 256 * kAdamVec * 4;  // 4096 elements per block
@@ -299,8 +300,9 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs A) {
   int ti = 0;
-  while (ti + 1 < A.n_tensors && (long long)blockIdx.x >= A.first_block[ti + 1]) ++ti;
-  const long long base = ((long long)blockIdx.x - A.first_block[ti]) * kAdamPerBlock;
+  for (long long vb = blockIdx.x; vb < A.total_blocks; vb += gridDim.x) {
+  while (ti + 1 < A.n_tensors && vb >= A.first_block[ti + 1]) ++ti;
+  const long long base = (vb - A.first_block[ti]) * kAdamPerBlock;
   const long long n = A.n[ti];
   float* p = A.p[ti]; const float* g = A.g[ti]; float* m = A.m[ti]; float* v = A.v[ti];
   const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -318,6 +320,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs A) {
       for (int k = 0; k < kAdamVec; ++k)
         if (i + k < n) adam_one(p[i + k], g[i + k], m[i + k], v[i + k], A);
     }
+  }
   }
 }
 
@@ -377,9 +380,19 @@ extern "C" int tnf_tv_fwd_bwd(const float* const* planes, float* const* grads, c
   return TNF_OK;
 }
 
+extern "C" int tnf_adam_step_grid(float* const* params, const float* const* grads, float* const* exp_avg,
+                                  float* const* exp_avg_sq, const int64_t* numel, int32_t n_tensors, float lr,
+                                  float beta1, float beta2, float eps, float weight_decay, int64_t step, int32_t max_blocks,
+                                  void* stream);
 extern "C" int tnf_adam_step(float* const* params, const float* const* grads, float* const* exp_avg,
                              float* const* exp_avg_sq, const int64_t* numel, int32_t n_tensors, float lr,
                              float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream) {
+  return tnf_adam_step_grid(params, grads, exp_avg, exp_avg_sq, numel, n_tensors, lr, beta1, beta2, eps, weight_decay, step, 0, stream);
+}
+extern "C" int tnf_adam_step_grid(float* const* params, const float* const* grads, float* const* exp_avg,
+                                  float* const* exp_avg_sq, const int64_t* numel, int32_t n_tensors, float lr,
+                                  float beta1, float beta2, float eps, float weight_decay, int64_t step, int32_t max_blocks,
+                                  void* stream) {
   using namespace tnf;
   TNF_REQUIRE(n_tensors >= 0 && step >= 1, "bad n_tensors/step");
   TNF_REQUIRE(n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && numel), "null table");
@@ -403,7 +416,9 @@ extern "C" int tnf_adam_step(float* const* params, const float* const* grads, fl
     A.bias2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     if (blocks == 0) continue;
     TNF_REQUIRE(blocks < (1LL << 31), "too many blocks");
-    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(A);
+    A.total_blocks = blocks;
+    const long long grid = (max_blocks > 0 && max_blocks < blocks) ? max_blocks : blocks;
+    adam_kernel<<<(unsigned)grid, 256, 0, st>>>(A);
     TNF_LAUNCH_CHECK("adam_kernel");
   }
   return TNF_OK;

@@ -191,7 +191,8 @@ class FusedKPlanesStep:
     # ---- the iteration -----------------------------------------------------------------------------
     @torch.no_grad()
     def forward_backward(self, packed: torch.Tensor, info: torch.Tensor, target: torch.Tensor,
-                         n_rays_global: torch.Tensor | None = None, reduce: bool = False, n_rays_work=None) -> Dict[str, torch.Tensor]:
+                         n_rays_global: torch.Tensor | None = None, reduce: bool = False, n_rays_work=None,
+                         after_plane_grads=None) -> Dict[str, torch.Tensor]:
         """packed [N,7], info [R,2] int32 (a RayProvider partition), target [R,3].  Sets p.grad of every parameter to
         d(grad_scale * (MSE_union + tv_alpha/world * loss_tv))/dp and returns {"loss", "rendered"}.  With `reduce` the
         gradients are all-reduced over the ranks (sum) before returning, overlapped with the tail of backward."""
@@ -327,6 +328,8 @@ class FusedKPlanesStep:
                      P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
                 if reduce and self.world > 1:
                     work = dist.all_reduce(self.flat_grad[:self._plane_grad_end], async_op=True)  # runs under the wgrads
+            if after_plane_grads is not None and work is None:
+                after_plane_grads()   # the plane gradients are final (single-GPU): their optimiser update may start now
             if work is not None and self.collective_ctas > 0:
                 # the collective's CTAs hold whole SMs; leave them out of the weight-gradient kernels' one-CTA-per-SM grids
                 _lib.load().tnf_set_sm_budget(max(16, self._sms - self.collective_ctas))

@@ -20,7 +20,11 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, subset=None, max_blocks: int = 0):
+        """subset: optional collection of parameters -- only these are updated by this call (the trainer updates the
+        feature planes on a second stream beside the heads' weight-gradient kernels and everything else afterwards);
+        max_blocks > 0 caps the grid (persistent form, tnf_adam_step_grid)."""
+        only = None if subset is None else frozenset(id(p) for p in subset)
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -30,7 +34,7 @@ class FusedAdam(torch.optim.Optimizer):
             ps, gs, ms, vs = [], [], [], []
             step = None
             for p in group["params"]:
-                if p.grad is None:
+                if p.grad is None or (only is not None and id(p) not in only):
                     continue
                 _lib.require_cuda(p, "parameter")
                 if p.dtype != torch.float32:
@@ -53,15 +57,15 @@ class FusedAdam(torch.optim.Optimizer):
             n = len(ps)
             key = tuple(t.data_ptr() for ts in (ps, gs, ms, vs) for t in ts)
             tables = self.__dict__.setdefault("_tnf_tables", {})
-            cached = tables.get(id(group))
+            cached = tables.get((id(group), only))
             if cached is None or cached[0] != key:  # pointer tables are rebuilt only when a tensor moved
                 tab = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
                 cached = (key, tab(ps), tab(gs), tab(ms), tab(vs), (C.c_int64 * n)(*[t.numel() for t in ps]))
-                tables[id(group)] = cached
+                tables[(id(group), only)] = cached
             _, tp, tg, tm, tv, numel = cached
             b1, b2 = group["betas"]
             with torch.cuda.device(ps[0].device):
-                _lib.call("tnf_adam_step", tp, tg, tm, tv, numel, n, float(group["lr"]), float(b1),
-                          float(b2), float(group["eps"]), float(group["weight_decay"]), int(step), _lib.stream_ptr(),
+                _lib.call("tnf_adam_step_grid", tp, tg, tm, tv, numel, n, float(group["lr"]), float(b1),
+                          float(b2), float(group["eps"]), float(group["weight_decay"]), int(step), int(max_blocks), _lib.stream_ptr(),
                           nbytes=28 * sum(t.numel() for t in ps), extra_kernels=math.ceil(n / 48) - 1)
         return loss

@@ -14,6 +14,7 @@ metrics, image writing and the CLI are out of scope (callers own them).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
@@ -181,6 +182,10 @@ class TrainConfig:
                                         # free-running host ends up a launch-queue's worth of steps ahead, every batch it has
                                         # marched stays allocated until the GPU gets there, and the allocator's cudaMalloc
                                         # calls then wait for the whole queue
+    overlap_plane_adam: bool = False    # single GPU, fused step: Adam of the planes (99.8 % of the parameters, HBM-bound) on a
+                                        # second stream beside the heads' weight-gradient kernels.  Measured and OFF: the
+                                        # one-CTA-per-SM tensor-core kernels then start late or share HBM badly -- 188.6 M
+                                        # samples/s sequential vs 166.9 M (8064 Adam blocks) / 151-164 M (persistent 148/296)
     manual_gc: bool = True              # collect Python garbage at the occupancy-update cadence instead of at random steps
                                         # (a generation-2 pause on ONE rank stalls every rank at the next collective)
     occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
@@ -249,6 +254,9 @@ class Trainer:
         self._gc_frozen = False
         self._queue: List = []          # prefetched (batch, done event), oldest first
         self._inflight: List = []       # end-of-iteration events of the iterations enqueued and not yet waited for
+        self._adam_blocks = int(os.environ.get("TNF_ADAM_BLOCKS", "0")) or (
+            torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == "cuda" else 0)
+        self._opt_stream = None         # second stream for the planes' optimiser update (overlap_plane_adam)
         self._loss_ring = None          # pinned host ring the loss of every iteration is copied into (read_loss)
         self._grid_event = None         # recorded after the latest occupancy update: batches marched later must see it
         self.last: Dict[str, float] = {}
@@ -492,8 +500,26 @@ class Trainer:
         if self.world > 1:  # ray count of the union batch: reduced while the forward runs
             n_glob = torch.tensor(float(info.size(0)), device=self.device)
             work = dist.all_reduce(n_glob, async_op=True)
-        out = self._fused.forward_backward(packed, info, rgbs, n_glob, reduce=self.world > 1, n_rays_work=work)  # incl. the gradient all-reduce
-        self.optimizer.step()
+        hook = None
+        if self.cfg.overlap_plane_adam and self.world == 1:
+            main = torch.cuda.current_stream(self.device)
+            if self._opt_stream is None:
+                self._opt_stream = torch.cuda.Stream(device=self.device)
+            planes = self._fused.planes
+
+            def hook():
+                self._opt_stream.wait_event(main.record_event())
+                with torch.cuda.stream(self._opt_stream):
+                    self.optimizer.step(subset=planes, max_blocks=self._adam_blocks)
+                    self._planes_done = self._opt_stream.record_event()
+        out = self._fused.forward_backward(packed, info, rgbs, n_glob, reduce=self.world > 1, n_rays_work=work,
+                                           after_plane_grads=hook)  # incl. the gradient all-reduce
+        if hook is not None:
+            plane_ids = {id(p) for p in self._fused.planes}
+            self.optimizer.step(subset=[p for p in self._fused.params if id(p) not in plane_ids])
+            torch.cuda.current_stream(self.device).wait_event(self._planes_done)
+        else:
+            self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
         self._publish_loss(out["loss"])
