@@ -104,8 +104,111 @@ __global__ void __launch_bounds__(1024) mse_loss_grad_kernel(const float* __rest
   }
 }
 
+// composite forward + MSE + composite backward of one iteration in a single pass (src/core.py:256-265, src/run.py:252,259):
+// the loss gradient of a ray depends on that ray's rendered colour only (the normaliser is a scalar known beforehand), so
+// the warp that reduced a ray's segment turns round and writes the segment's grad_weights / grad_rgbs while its samples
+// are still in L1.  Same arithmetic per element as the three separate kernels; the loss is summed in double per block and
+// across blocks with one atomic each, the last block to finish writes loss_out and re-zeroes the scratch words.
+__global__ void __launch_bounds__(kWarpsC * 32)
+composite_loss_kernel(const float* __restrict__ w, const float* __restrict__ rgb, const int2* __restrict__ info,
+                      long long n_samples, long long n_rays, bool has_bg, float bg0, float bg1, float bg2,
+                      const float* __restrict__ target, float n_rays_global, const float* __restrict__ n_rays_global_dev,
+                      float grad_scale, float* __restrict__ out_rgb, float* __restrict__ gw, float* __restrict__ grgb,
+                      float* __restrict__ loss_out, double* __restrict__ scratch) {
+  __shared__ double s_part[kWarpsC];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long ray = blockIdx.x * (long long)kWarpsC + wid;
+  const float denom = (n_rays_global_dev ? __ldg(n_rays_global_dev) : n_rays_global) * 3.f;
+  const float gs = grad_scale / denom;
+  double part = 0.0;
+  if (ray < n_rays) {
+    const int2 e = __ldg(&info[ray]);
+    long long k0 = e.x, k1 = (long long)e.x + e.y;
+    if (k0 < 0) k0 = 0;
+    if (k1 > n_samples) k1 = n_samples;
+    float r = 0.f, g = 0.f, b = 0.f, op = 0.f;
+    for (long long k = k0 + lane; k < k1; k += 32) {
+      const float wk = __ldg(w + k);
+      if (wk > 0.f) {
+        r = __fmaf_rn(wk, __ldg(rgb + 3 * k + 0), r);
+        g = __fmaf_rn(wk, __ldg(rgb + 3 * k + 1), g);
+        b = __fmaf_rn(wk, __ldg(rgb + 3 * k + 2), b);
+      }
+      op += wk;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      r += __shfl_xor_sync(kFullMask, r, d);
+      g += __shfl_xor_sync(kFullMask, g, d);
+      b += __shfl_xor_sync(kFullMask, b, d);
+      op += __shfl_xor_sync(kFullMask, op, d);
+    }
+    if (has_bg) {
+      const float t = __fsub_rn(1.f, op);
+      r = __fadd_rn(r, __fmul_rn(bg0, t));
+      g = __fadd_rn(g, __fmul_rn(bg1, t));
+      b = __fadd_rn(b, __fmul_rn(bg2, t));
+    }
+    const float d0 = r - __ldg(target + 3 * ray), d1 = g - __ldg(target + 3 * ray + 1), d2 = b - __ldg(target + 3 * ray + 2);
+    if (lane == 0) {
+      out_rgb[3 * ray + 0] = r;
+      out_rgb[3 * ray + 1] = g;
+      out_rgb[3 * ray + 2] = b;
+      part = (double)(d0 * d0) + (double)(d1 * d1) + (double)(d2 * d2);
+    }
+    const float g0 = gs * 2.f * d0, g1 = gs * 2.f * d1, g2 = gs * 2.f * d2;
+    const float gbg = has_bg ? (bg0 * g0 + bg1 * g1 + bg2 * g2) : 0.f;
+    for (long long k = k0 + lane; k < k1; k += 32) {
+      const float wk = __ldg(w + k);
+      const bool on = wk > 0.f;
+      gw[k] = (on ? __ldg(rgb + 3 * k) * g0 + __ldg(rgb + 3 * k + 1) * g1 + __ldg(rgb + 3 * k + 2) * g2 : 0.f) - gbg;
+      grgb[3 * k + 0] = on ? wk * g0 : 0.f;
+      grgb[3 * k + 1] = on ? wk * g1 : 0.f;
+      grgb[3 * k + 2] = on ? wk * g2 : 0.f;
+    }
+  }
+  if (lane == 0) s_part[wid] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < kWarpsC; ++i) acc += s_part[i];
+    atomicAdd(scratch, acc);
+    __threadfence();
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(scratch + 1);
+    s_last = atomicAdd(counter, 1ull) == (unsigned long long)gridDim.x - 1;
+    if (s_last) {
+      __threadfence();
+      const double total = atomicAdd(scratch, 0.0);
+      *loss_out = (float)(total / (double)denom);
+      *scratch = 0.0;
+      *counter = 0ull;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace tnf
+
+extern "C" int tnf_composite_loss_fwd_bwd(const float* weights, const float* rgbs, const int32_t* info, int64_t n_samples,
+                                          int64_t n_rays, const float* bg, const float* target, float n_rays_global,
+                                          const float* n_rays_global_dev, float grad_scale, float* out_rgb,
+                                          float* grad_weights, float* grad_rgbs, float* loss_out, void* scratch,
+                                          void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(n_samples >= 0 && n_rays >= 1, "bad sizes");
+  TNF_REQUIRE(weights && rgbs && info && target && out_rgb && grad_weights && grad_rgbs && loss_out && scratch, "null pointer");
+  TNF_REQUIRE((reinterpret_cast<uintptr_t>(info) & 7u) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 7u) == 0,
+              "info / scratch must be 8-byte aligned");
+  TNF_REQUIRE(n_rays_global_dev || n_rays_global > 0.f, "n_rays_global must be positive");
+  composite_loss_kernel<<<(unsigned)ceil_div(n_rays, kWarpsC), kWarpsC * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      weights, rgbs, reinterpret_cast<const int2*>(info), n_samples, n_rays, bg != nullptr, bg ? bg[0] : 0.f, bg ? bg[1] : 0.f,
+      bg ? bg[2] : 0.f, target, n_rays_global, n_rays_global_dev, grad_scale, out_rgb, grad_weights, grad_rgbs, loss_out,
+      static_cast<double*>(scratch));
+  TNF_LAUNCH_CHECK("composite_loss_kernel");
+  return TNF_OK;
+}
 
 extern "C" int tnf_mse_loss_grad(const float* rendered, const float* target, int64_t n_rays, float n_rays_global,
                                  const float* n_rays_global_dev, float grad_scale, float* grad_rendered, float* loss_out,

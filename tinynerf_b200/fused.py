@@ -103,6 +103,8 @@ class FusedKPlanesStep:
                                       for r in self._res_planes for _ in range(2)], dtype=torch.float64, device=self.dev)
         self._cap_n = self._cap_r = 0
         self._ws: Dict[str, torch.Tensor] = {}
+        self.fused_composite = os.environ.get("TNF_FUSED_COMPOSITE", "1") != "0"   # 0: the three separate kernels
+        self._closs_scratch = torch.zeros(2, dtype=torch.float64, device=self.dev)   # tnf_composite_loss_fwd_bwd (zero between calls)
         # SMs a concurrent collective kernel occupies (NCCL_MAX_CTAS when set, else the 32 CTAs NCCL uses on NVLink here:
         # measured at 2 GPUs, capping NCCL at 16 / 8 CTAs slows the step 316 -> 288 -> 244 M samples/s)
         self._sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
@@ -273,16 +275,21 @@ class FusedKPlanesStep:
                 lin_fwd(x, ldx, cl[i], ws[f"h{i}"], head=cl[-1] if last else None,
                         head_out=ws["rgb"] if last else None, head_act=2 if last else 0)
                 x, ldx = P(ws[f"h{i}"]), hc_w
-            call("tnf_composite_fwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(ws["rendered"]), None, st,
-                 nbytes=16 * n + 20 * r)
-            # ---- loss + its gradient (src/run.py:252,259) ----
+            # ---- composite + loss + their gradients in one pass over the rays (src/core.py:256-265, src/run.py:252,259) ----
             if n_rays_work is not None:
                 n_rays_work.wait()   # the union batch's ray count (async all-reduce started before the forward)
-            call("tnf_mse_loss_grad", P(ws["rendered"]), P(target), r, float(r), _lib.ptr(n_rays_global), self.grad_scale,
-                 P(ws["grend"]), P(ws["loss"]), st, nbytes=36 * r)
+            if self.fused_composite:
+                call("tnf_composite_loss_fwd_bwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(target), float(r),
+                     _lib.ptr(n_rays_global), self.grad_scale, P(ws["rendered"]), P(ws["gw"]), P(ws["grgb"]), P(ws["loss"]),
+                     P(self._closs_scratch), st, nbytes=48 * n + 56 * r)
+            else:
+                call("tnf_composite_fwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(ws["rendered"]), None, st,
+                     nbytes=16 * n + 20 * r)
+                call("tnf_mse_loss_grad", P(ws["rendered"]), P(target), r, float(r), _lib.ptr(n_rays_global), self.grad_scale,
+                     P(ws["grend"]), P(ws["loss"]), st, nbytes=36 * r)
+                call("tnf_composite_bwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(ws["grend"]), P(ws["gw"]),
+                     P(ws["grgb"]), st, nbytes=32 * n + 20 * r)
             # ---- backward ----
-            call("tnf_composite_bwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(ws["grend"]), P(ws["gw"]),
-                 P(ws["grgb"]), st, nbytes=32 * n + 20 * r)
             # Order: the data-gradient chain first (it ends in the plane gradients, 99.8 % of the bytes a data-parallel run
             # has to all-reduce), then the weight gradients of the heads -- 0.5 ms of work that depends only on the saved
             # dh / activations and hides the plane all-reduce completely.
