@@ -129,24 +129,30 @@ class RayStore:
     def _next_indices(self, batch: int) -> torch.Tensor:
         on_gpu = (not self.host) and self.device.type == "cuda"
         if on_gpu:
-            # pinned staging for the asynchronous upload of the indices; a small ring, because an upload may still be in
-            # flight when the next batch is drawn (the consumer syncs once per batch, so 4 slots are never all busy)
-            if len(self._idx_ring) < 4 or self._idx_ring[self._idx_i].numel() < batch:
-                buf = torch.empty(max(batch, 1), dtype=torch.int64).pin_memory()
-                if len(self._idx_ring) < 4:
-                    self._idx_ring.append(buf)
-                    self._idx_i = len(self._idx_ring) - 1
-                else:
-                    self._idx_ring[self._idx_i] = buf
-            out = self._idx_ring[self._idx_i][:batch]
-            self._idx_i = (self._idx_i + 1) % 4
+            # pinned staging for the asynchronous upload of the indices: a ring of four slots, each guarded by the event of
+            # its last upload (a slot is rewritten only after that copy has run; in the trainer it always has, because the
+            # batch loop reads the sample count back before it draws the next batch)
+            slot = self._idx_i
+            if len(self._idx_ring) <= slot:
+                self._idx_ring.append([torch.empty(max(batch, 1), dtype=torch.int64).pin_memory(), None])
+            buf, ev = self._idx_ring[slot]
+            if ev is not None:
+                ev.synchronize()
+            if buf.numel() < batch:
+                buf = self._idx_ring[slot][0] = torch.empty(batch, dtype=torch.int64).pin_memory()
+            out = buf[:batch]
+            self._idx_i = (slot + 1) % 4
         else:
             out = torch.empty(batch, dtype=torch.int64)
         _lib.check(_lib.load().tnf_shuffle_next(self._order.data_ptr(), self.n, self._pos, batch, self.rank, self.world,
                                                 C.byref(self._fresh), C.byref(self._rng), out.data_ptr()), "tnf_shuffle_next")
         self._pos += batch * self.world
         self.last_indices = out   # host view of the batch just drawn (valid until the staging slot is reused)
-        return out.to(self.device, non_blocking=True) if on_gpu else out
+        if not on_gpu:
+            return out
+        dev_idx = out.to(self.device, non_blocking=True)
+        self._idx_ring[slot][1] = torch.cuda.current_stream(self.device).record_event()
+        return dev_idx
 
     def next(self, batch: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         idx = self._next_indices(batch)
@@ -154,8 +160,12 @@ class RayStore:
             if self._stage is None or self._stage.size(0) < batch:  # grow-only: pinning memory is a slow, synchronising call
                 self._stage = torch.empty(max(batch, 2 * (0 if self._stage is None else self._stage.size(0))), 9).pin_memory()
             stage = self._stage[:batch]
+            if getattr(self, "_stage_event", None) is not None:
+                self._stage_event.synchronize()   # the previous batch's upload has read the staging buffer
             torch.index_select(self.data, 0, idx, out=stage)
             rows = stage.to(self.device, non_blocking=True)
+            if rows.is_cuda:
+                self._stage_event = torch.cuda.current_stream(self.device).record_event()
             self.h2d_bytes += rows.numel() * 4
         else:
             rows = self.data.index_select(0, idx)
