@@ -75,52 +75,93 @@ def make_scene(n_rays: int, seed: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md recipe).  Sampled in-process through NVML
+    (nvidia_ml_py) every 50 ms; `nvidia-smi -lms` is the fallback.  The sampler is started BEFORE the warm-up and only samples
+    taken after mark() are reported: a looping nvidia-smi was seen to block kernel launches for 80-100 ms, at its first query
+    and now and then later, which a sub-second timed region cannot absorb; the NVML calls used here read two registers."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
         self.idx, self.rows, self.stamps, self.proc, self.t_mark = gpu_index, [], [], None, 0.0
+        self.nvml, self.stop_flag, self.t = None, threading.Event(), None
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.idx < len(ids) and ids[self.idx].isdigit():
+                return int(ids[self.idx])
+        return self.idx
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index()))
+            pynvml.nvmlDeviceGetClockInfo(self.nvml[1], pynvml.NVML_CLOCK_SM)            # both queries must work, else fall back
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.nvml[1])
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self._physical_index())], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        bits = [(nv.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")]
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((sm, mx, [name for bit, name in bits if mask & bit]))
+                self.stamps.append(time.perf_counter())
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-            self.stamps.append(time.perf_counter())
+            r = [c.strip() for c in line.split(",")]
+            if len(r) > 8 and r[1].replace(".", "").isdigit():
+                reasons = [nm for nm, v in zip(self.NAMES, r[5:9]) if v.lower().startswith("active")]
+                mx = float(r[2]) if r[2].replace(".", "").isdigit() else None
+                self.rows.append((float(r[1]), mx, reasons))
+                self.stamps.append(time.perf_counter())
 
     def mark(self):
-        """Start of the timed region: only samples taken from here on are reported.  (The sampler itself is started
-        before the warm-up: nvidia-smi's first query initialises NVML and was seen to block kernel launches for ~100 ms.)"""
+        """Start of the timed region: only samples taken from here on are reported."""
         self.t_mark = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        n_all = len(self.rows)
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML / nvidia-smi unavailable"]}
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.t is not None:
+            self.t.join(timeout=2)
         keep = [r for r, ts in zip(self.rows, self.stamps) if ts >= self.t_mark]
-        self.rows = keep if keep else self.rows[-1:]   # a region shorter than the sampling period: the closest sample
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) > 8:
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-        mx = max((float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()), default=None)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        rows = keep if keep else self.rows[-1:]   # a region shorter than the sampling period: the closest sample
+        sm = sorted(r[0] for r in rows)
+        reasons = sorted({nm for r in rows for nm in r[2]})
+        mx = max((r[1] for r in rows if r[1] is not None), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---- the reference arm / cpu_baseline: the oracle's CPU restatement of the same step -------------

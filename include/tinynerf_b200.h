@@ -306,12 +306,15 @@ int tnf_mse_loss_grad(const float* rendered, const float* target, int64_t n_rays
 
 /* tnf_composite_fwd + tnf_mse_loss_grad + tnf_composite_bwd of one training iteration in a single pass over the rays (the
  * loss gradient of a ray depends only on that ray's rendered colour): out_rgb [n_rays,3], grad_weights [n], grad_rgbs [n,3],
- * *loss_out as tnf_mse_loss_grad.  scratch: 16 bytes of device memory, 8-byte aligned, ZERO before the first call (left
- * zero by every call). */
+ * *loss_out as tnf_mse_loss_grad, plus sum_i extra_terms[i]*extra_coef[i] (n_extra device doubles each; e.g. the TV sums of
+ * tnf_tv_fwd_bwd and their weights, so the reported loss is complete without further kernels).  scratch: 16 bytes of device
+ * memory, 8-byte aligned, ZERO before the first call (left zero by every call). */
 int tnf_composite_loss_fwd_bwd(const float* weights, const float* rgbs, const int32_t* info, int64_t n_samples,
                                int64_t n_rays, const float* bg, const float* target, float n_rays_global,
                                const float* n_rays_global_dev /*optional*/, float grad_scale, float* out_rgb,
-                               float* grad_weights, float* grad_rgbs, float* loss_out, void* scratch, void* stream);
+                               float* grad_weights, float* grad_rgbs, float* loss_out, void* scratch,
+                               const double* extra_terms /*optional*/, const double* extra_coef /*optional*/, int32_t n_extra,
+                               void* stream);
 
 /* ---- host helper: lazily shuffled ray order (DataLoader(shuffle=True), src/run.py:116-122) --------------------------------
  * HOST pointers.  perm: n entries, initially 0..n-1 (any permutation); out receives `count` ray indices.  pos is a global

@@ -128,10 +128,17 @@ def test_composite_loss_kernel_equals_the_three_separate_kernels():
         for _ in range(2):   # twice: the scratch words must come back zeroed
             _lib.call("tnf_composite_loss_fwd_bwd", w.data_ptr(), rgb.data_ptr(), info.data_ptr(), n, r, bg, target.data_ptr(), float(r),
                       _lib.ptr(n_glob), 1024.0, out_b.data_ptr(), gw_b.data_ptr(), grgb_b.data_ptr(), loss_b.data_ptr(),
-                      scratch.data_ptr(), st)
+                      scratch.data_ptr(), None, None, 0, st)
             assert torch.equal(out_a, out_b) and torch.equal(gw_a, gw_b) and torch.equal(grgb_a, grgb_b)
             assert float(loss_b) == pytest.approx(float(loss_a), rel=1e-6)
             assert not scratch.any()
+        # extra loss terms (the weighted TV sums in the training iteration) are added to the reported value only
+        terms = torch.tensor([0.5, 2.0, 3.0], dtype=torch.float64, device=DEV)
+        coef = torch.tensor([0.25, 0.125, 1.0], dtype=torch.float64, device=DEV)
+        _lib.call("tnf_composite_loss_fwd_bwd", w.data_ptr(), rgb.data_ptr(), info.data_ptr(), n, r, bg, target.data_ptr(), float(r),
+                  _lib.ptr(n_glob), 1024.0, out_b.data_ptr(), gw_b.data_ptr(), grgb_b.data_ptr(), loss_b.data_ptr(),
+                  scratch.data_ptr(), terms.data_ptr(), coef.data_ptr(), 3, st)
+        assert float(loss_b) == pytest.approx(float(loss_a) + 3.375, rel=1e-6) and torch.equal(gw_a, gw_b)
 
 
 def test_tv_fwd_bwd_equals_separate_passes():

@@ -51,7 +51,8 @@ _SIGNATURES = {
     "tnf_last_error": (C.c_char_p, []),
     "tnf_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "tnf_composite_loss_fwd_bwd": (C.c_int, [c_f32p, c_f32p, c_i32p, C.c_int64, C.c_int64, C.POINTER(C.c_float), c_f32p, C.c_float,
-                                             c_f32p, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p]),
+                                             c_f32p, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_int32, C.c_void_p]),
     "tnf_set_sm_budget": (C.c_int, [C.c_int]),
     "tnf_shuffle_next": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64),
                                    C.POINTER(C.c_uint64), C.c_void_p]),

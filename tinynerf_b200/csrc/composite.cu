@@ -114,7 +114,8 @@ composite_loss_kernel(const float* __restrict__ w, const float* __restrict__ rgb
                       long long n_samples, long long n_rays, bool has_bg, float bg0, float bg1, float bg2,
                       const float* __restrict__ target, float n_rays_global, const float* __restrict__ n_rays_global_dev,
                       float grad_scale, float* __restrict__ out_rgb, float* __restrict__ gw, float* __restrict__ grgb,
-                      float* __restrict__ loss_out, double* __restrict__ scratch) {
+                      float* __restrict__ loss_out, double* __restrict__ scratch, const double* __restrict__ extra_terms,
+                      const double* __restrict__ extra_coef, int n_extra) {
   __shared__ double s_part[kWarpsC];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -180,8 +181,9 @@ composite_loss_kernel(const float* __restrict__ w, const float* __restrict__ rgb
     s_last = atomicAdd(counter, 1ull) == (unsigned long long)gridDim.x - 1;
     if (s_last) {
       __threadfence();
-      const double total = atomicAdd(scratch, 0.0);
-      *loss_out = (float)(total / (double)denom);
+      double loss = atomicAdd(scratch, 0.0) / (double)denom;
+      for (int i = 0; i < n_extra; ++i) loss += extra_terms[i] * extra_coef[i];   // e.g. the weighted TV sums of this iteration
+      *loss_out = (float)loss;
       *scratch = 0.0;
       *counter = 0ull;
     }
@@ -195,17 +197,18 @@ extern "C" int tnf_composite_loss_fwd_bwd(const float* weights, const float* rgb
                                           int64_t n_rays, const float* bg, const float* target, float n_rays_global,
                                           const float* n_rays_global_dev, float grad_scale, float* out_rgb,
                                           float* grad_weights, float* grad_rgbs, float* loss_out, void* scratch,
-                                          void* stream) {
+                                          const double* extra_terms, const double* extra_coef, int32_t n_extra, void* stream) {
   using namespace tnf;
   TNF_REQUIRE(n_samples >= 0 && n_rays >= 1, "bad sizes");
   TNF_REQUIRE(weights && rgbs && info && target && out_rgb && grad_weights && grad_rgbs && loss_out && scratch, "null pointer");
   TNF_REQUIRE((reinterpret_cast<uintptr_t>(info) & 7u) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 7u) == 0,
               "info / scratch must be 8-byte aligned");
   TNF_REQUIRE(n_rays_global_dev || n_rays_global > 0.f, "n_rays_global must be positive");
+  TNF_REQUIRE(n_extra >= 0 && (n_extra == 0 || (extra_terms && extra_coef)), "bad extra loss terms");
   composite_loss_kernel<<<(unsigned)ceil_div(n_rays, kWarpsC), kWarpsC * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       weights, rgbs, reinterpret_cast<const int2*>(info), n_samples, n_rays, bg != nullptr, bg ? bg[0] : 0.f, bg ? bg[1] : 0.f,
       bg ? bg[2] : 0.f, target, n_rays_global, n_rays_global_dev, grad_scale, out_rgb, grad_weights, grad_rgbs, loss_out,
-      static_cast<double*>(scratch));
+      static_cast<double*>(scratch), extra_terms, extra_coef, n_extra);
   TNF_LAUNCH_CHECK("composite_loss_kernel");
   return TNF_OK;
 }

@@ -278,10 +278,12 @@ class FusedKPlanesStep:
             # ---- composite + loss + their gradients in one pass over the rays (src/core.py:256-265, src/run.py:252,259) ----
             if n_rays_work is not None:
                 n_rays_work.wait()   # the union batch's ray count (async all-reduce started before the forward)
+            tv_in_loss = self.fused_composite and self.tv_alpha != 0.0   # the kernel adds tv_alpha/world * loss_tv to the loss it reports
             if self.fused_composite:
                 call("tnf_composite_loss_fwd_bwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(target), float(r),
                      _lib.ptr(n_rays_global), self.grad_scale, P(ws["rendered"]), P(ws["gw"]), P(ws["grgb"]), P(ws["loss"]),
-                     P(self._closs_scratch), st, nbytes=48 * n + 56 * r)
+                     P(self._closs_scratch), P(self._tv_sums) if tv_in_loss else None, P(self._tv_coef) if tv_in_loss else None,
+                     self._tv_sums.numel() if tv_in_loss else 0, st, nbytes=48 * n + 56 * r)
             else:
                 call("tnf_composite_fwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(ws["rendered"]), None, st,
                      nbytes=16 * n + 20 * r)
@@ -357,7 +359,7 @@ class FusedKPlanesStep:
                     w.wait()
                 work.wait()
             loss = ws["loss"][0]
-            if self.tv_alpha != 0.0:
+            if self.tv_alpha != 0.0 and not tv_in_loss:
                 loss = loss + torch.dot(self._tv_sums, self._tv_coef).float()
             else:
                 loss = loss.clone()
