@@ -133,13 +133,13 @@ class RayStore:
             # its last upload (a slot is rewritten only after that copy has run; in the trainer it always has, because the
             # batch loop reads the sample count back before it draws the next batch)
             slot = self._idx_i
-            if len(self._idx_ring) <= slot:
-                self._idx_ring.append([torch.empty(max(batch, 1), dtype=torch.int64).pin_memory(), None])
+            if len(self._idx_ring) <= slot:   # 1 MB per slot up front: pinning memory is a slow, device-synchronising call
+                self._idx_ring.append([torch.empty(max(batch, 1 << 17), dtype=torch.int64).pin_memory(), None])
             buf, ev = self._idx_ring[slot]
             if ev is not None:
                 ev.synchronize()
             if buf.numel() < batch:
-                buf = self._idx_ring[slot][0] = torch.empty(batch, dtype=torch.int64).pin_memory()
+                buf = self._idx_ring[slot][0] = torch.empty(2 * batch, dtype=torch.int64).pin_memory()
             out = buf[:batch]
             self._idx_i = (slot + 1) % 4
         else:
@@ -158,7 +158,7 @@ class RayStore:
         idx = self._next_indices(batch)
         if self.host:
             if self._stage is None or self._stage.size(0) < batch:  # grow-only: pinning memory is a slow, synchronising call
-                self._stage = torch.empty(max(batch, 2 * (0 if self._stage is None else self._stage.size(0))), 9).pin_memory()
+                self._stage = torch.empty(max(batch, 1 << 16, 2 * (0 if self._stage is None else self._stage.size(0))), 9).pin_memory()
             stage = self._stage[:batch]
             if getattr(self, "_stage_event", None) is not None:
                 self._stage_event.synchronize()   # the previous batch's upload has read the staging buffer
@@ -259,7 +259,10 @@ class Trainer:
         self._chunks_guess = 0.0
         if world > 1 and self.device.type == "cuda":
             self._warm_collectives()
-        self._side = torch.cuda.Stream(device=self.device) if (cfg.prefetch and self.device.type == "cuda") else None
+        # TNF_SIDE_PRIORITY=1 (diagnostics): march the coming batches on a high-priority stream, so their short kernels are not
+        # queued behind the main stream's long ones while the host waits for the sample count
+        prio = -1 if os.environ.get("TNF_SIDE_PRIORITY", "0") == "1" else 0
+        self._side = torch.cuda.Stream(device=self.device, priority=prio) if (cfg.prefetch and self.device.type == "cuda") else None
         self.post_update = None         # optional callable(trainer) run right after every occupancy update
         self._gc_frozen = False
         self._queue: List = []          # prefetched (batch, done event), oldest first
