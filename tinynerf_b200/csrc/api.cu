@@ -83,17 +83,33 @@ extern "C" int tnf_shuffle_next(int64_t* perm, int64_t n, int64_t pos, int64_t c
   using namespace tnf;
   TNF_REQUIRE(perm && fresh_from && rng_state && out, "null pointer");
   TNF_REQUIRE(n >= 1 && pos >= 0 && count >= 0 && world >= 1 && rank >= 0 && rank < world, "bad sizes");
+  // Blocks of 256 positions: the swap partners of a block are drawn first and their cache lines prefetched, then the swaps
+  // run -- early in an epoch every partner is a random line of an array far larger than the caches, and the misses of a
+  // block overlap instead of queueing one behind the other (the draws depend on the generator only, never on the data).
   int64_t k = 0;
-  for (int64_t g = pos; g < pos + count * world; ++g) {
-    const int64_t i = g % n;
-    if (g >= *fresh_from) {
-      const int64_t j = i + (int64_t)tnf_bounded(rng_state, (uint64_t)(n - i));
-      const int64_t t = perm[i];
-      perm[i] = perm[j];
-      perm[j] = t;
-      *fresh_from = g + 1;
+  const int64_t end = pos + count * world;
+  int64_t js[256];
+  for (int64_t g0 = pos; g0 < end; g0 += 256) {
+    const int64_t g1 = g0 + 256 < end ? g0 + 256 : end;
+    for (int64_t g = g0; g < g1; ++g) {
+      const int64_t i = g % n;
+      int64_t j = -1;
+      if (g >= *fresh_from) {
+        j = i + (int64_t)tnf_bounded(rng_state, (uint64_t)(n - i));
+        *fresh_from = g + 1;
+        __builtin_prefetch(perm + j, 1, 0);
+      }
+      js[g - g0] = j;
     }
-    if (g % world == rank) out[k++] = perm[i];
+    for (int64_t g = g0; g < g1; ++g) {
+      const int64_t i = g % n, j = js[g - g0];
+      if (j >= 0) {
+        const int64_t t = perm[i];
+        perm[i] = perm[j];
+        perm[j] = t;
+      }
+      if (g % world == rank) out[k++] = perm[i];
+    }
   }
   return TNF_OK;
 }

@@ -96,7 +96,7 @@ class RayStore:
     """Rays + colours of a scene, shuffled per epoch like DataLoader(shuffle=True) (src/run.py:116-122).
     Lives on `device` (HBM-resident, no per-batch H2D) or in pinned host memory (`host=True`), in which
     case every batch is gathered on the host and copied H2D, as in the reference (src/run.py:226-228).
-    With world_size > 1 each rank walks a disjoint 1/world slice of the same seeded permutation."""
+    With world_size > 1 each rank shuffles its own disjoint 1/world of the rays (ray index % world == rank)."""
 
     def __init__(self, rays_o: torch.Tensor, rays_d: torch.Tensor, rgbs: torch.Tensor, device, host: bool = False,
                  seed: int = 0, rank: int = 0, world: int = 1):
@@ -106,12 +106,14 @@ class RayStore:
         self.n = data.size(0)
         # The order is an incremental Fisher-Yates shuffle on the host (tnf_shuffle_next): each call shuffles just the
         # positions it hands out, so no step ever pays an O(n) randperm at an epoch boundary (tens of milliseconds for
-        # millions of rays).  Every n positions each ray has been handed out exactly once; every rank walks the same seeded
-        # sequence and keeps the positions g % world == rank.
-        self._order = torch.arange(self.n, dtype=torch.int64)
-        self._rng = C.c_uint64((0x9E3779B97F4A7C15 * (2 * int(seed) + 1)) & 0xFFFFFFFFFFFFFFFF)
+        # millions of rays).  Rank r owns the rays r, r + world, r + 2 world, ... and shuffles that subset on its own (its
+        # own seeded generator): the ranks stay disjoint, every ray is handed out once per epoch, and the host work per batch
+        # does not grow with the number of ranks.
+        self._order = torch.arange(rank, self.n, world, dtype=torch.int64)
+        self._m = self._order.numel()
+        self._rng = C.c_uint64((0x9E3779B97F4A7C15 * (2 * (int(seed) * 1024 + rank) + 1)) & 0xFFFFFFFFFFFFFFFF)
         self._fresh = C.c_int64(0)     # first global position never drawn so far
-        self._pos = 0                  # global position of this rank's next batch (a multiple of world)
+        self._pos = 0                  # position of the next batch in this rank's order
         self.h2d_bytes = 0
         self._stage = None
         self._idx_ring, self._idx_i = [], 0
@@ -119,7 +121,7 @@ class RayStore:
     def rewind(self, n_rays: int) -> None:
         """Give back the last `n_rays` rays handed out by next() (speculatively marched, not used): the same rays come
         out again, in the same order."""
-        self._pos -= n_rays * self.world
+        self._pos -= n_rays
         assert self._pos >= 0
 
     def remaining(self) -> int:
@@ -144,9 +146,9 @@ class RayStore:
             self._idx_i = (slot + 1) % 4
         else:
             out = torch.empty(batch, dtype=torch.int64)
-        _lib.check(_lib.load().tnf_shuffle_next(self._order.data_ptr(), self.n, self._pos, batch, self.rank, self.world,
+        _lib.check(_lib.load().tnf_shuffle_next(self._order.data_ptr(), self._m, self._pos, batch, 0, 1,
                                                 C.byref(self._fresh), C.byref(self._rng), out.data_ptr()), "tnf_shuffle_next")
-        self._pos += batch * self.world
+        self._pos += batch
         self.last_indices = out   # host view of the batch just drawn (valid until the staging slot is reused)
         if not on_gpu:
             return out
