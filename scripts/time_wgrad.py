@@ -1,5 +1,5 @@
 """Diagnostics: tnf_linear_bwd_weight on the five head-layer shapes of a K-Planes step (M = 2^18), stacked-SS kernel
-(TNF_WGRAD_SS=1) against the tensor-memory-A kernel (default)."""
+(TNF_WGRAD=ss) against the tensor-memory-A / TMA kernel (default)."""
 import os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -14,7 +14,7 @@ for k, n in shapes:
     bufs[(k, n)] = (torch.randn(m, ld, device="cuda"), torch.randn(m, n, device="cuda"), torch.zeros(n, k, device="cuda"),
                     torch.zeros(n, device="cuda"), ld)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for mode in (sys.argv[1:] or ["ss", "ts", "tma", "ts", "tma"]):
+for mode in (sys.argv[1:] or ["ss", "tma", "ss", "tma"]):
     os.environ["TNF_WGRAD"] = mode
     for k, n in shapes:
         x, dy, dw, db, ld = bufs[(k, n)]

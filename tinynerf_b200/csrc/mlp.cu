@@ -75,7 +75,6 @@ __device__ __forceinline__ float head_activation(float x, int act) {
 // so HBM loads, tensor-core work and the epilogue of consecutive tiles overlap inside one CTA.
 constexpr int kWsThreads = 416;   // 4 loader + 8 epilogue + 1 MMA warps
 constexpr int kMaxStages = 4;
-constexpr int kRawRing = 4;   // wgrad: raw cp.async ring slots of the loaders
 constexpr int kMaxHi = 7;     // fwd/dgrad: hi slots (cp.async targets + MMA operands)
 constexpr int kMaxLo = 3;     // fwd/dgrad: lo slots
 
@@ -569,220 +568,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const LinArgs A) {
   if (warp == kWgLoadWarps) tmem_dealloc(tmem_d, tmem_cols);
 }
 
-// wgrad for 64-wide layers, "TS" form: the A operand [dY_hi ; dY_lo]^T (128 x 128 samples) lives in TENSOR MEMORY.
+// wgrad for 64-wide layers: the A operand [dY_hi ; dY_lo]^T (128 x 128 samples) lives in TENSOR MEMORY.
 // The stacked kernel above keeps two dY sets (hi + lo images, 128 KB) in shared memory, which leaves room for two atoms of
-// global loads in flight: it is bound by load latency, not by HBM or the tensor pipe.  Here the loader warps transpose the
-// raw dY tile shared memory -> registers -> tcgen05.st (thread == TMEM lane == one output feature, hi or lo half; the
-// column sums for the bias gradient fall out of the same registers), so shared memory holds only a raw dY staging ring
-// (2 x 32 KB), an eight-slot ring of X hi images (the cp.async landing zones) and two X lo slots (the lo image is made
-// just before the tensor core reads it and lives only that long; the [X_hi | X_lo] operand is addressed with a per-atom
-// leading-dimension offset): five to six items (~100 KB per SM) of loads in flight, and the MMA reads one operand from
-// shared memory instead of two (33 instead of 48 cycles per 128x64x8 MMA, scripts/ubench/mma_bench.cu).
-//   warps 0-7 loaders: item sequence per tile = [dY pair][X atom 0]..[X atom kx-1], each one cp.async group, kTsDist ahead
-//   warp  8   MMA    : per X atom j: D[128, 64j..64j+64) += A_tmem[128, 128 samples] * [X_hi | X_lo] (16 k-steps), D in TMEM
-//                      for the whole kernel, flushed like the stacked kernel (quadrants summed, one reduction per 16 B)
-constexpr int kTsXStages = 8;   // X hi slots (16 KB)
-constexpr int kTsXLo = 2;       // X lo slots (16 KB)
-constexpr int kTsYSlots = 2;    // raw dY pair slots (32 KB)
-constexpr int kTsDist = 6;
-
-template <int NT>
-__device__ __forceinline__ void cp_async_atom_raw(const float* __restrict__ g, long long ld, long long row0, long long rows,
-                                                  int col0, int cols, int tid, uint8_t* raw) {
-  const int c = tid & 7;
-  const int r0 = tid >> 3;
-  const int col = col0 + 4 * c;
-  int nbytes = (cols - col) * 4;
-  nbytes = nbytes < 0 ? 0 : (nbytes > 16 ? 16 : nbytes);
-#pragma unroll
-  for (int i = 0; i < 1024 / NT; ++i) {
-    const int r = r0 + (NT / 8) * i;
-    const long long row = row0 + r;
-    const bool ok = row < rows && nbytes > 0;
-    const float* src = ok ? (g + row * ld + col) : g;
-    const uint32_t dst = smem_u32(raw + r * 128 + c * 16);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? nbytes : 0) : "memory");
-  }
-}
-__device__ __forceinline__ void loaders_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWgLoadThreads) : "memory"); }
-
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_ts_kernel(const LinArgs A) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t s_xfull[kTsXStages], s_xempty[kTsXStages], s_lempty[kTsXLo], s_afull[2], s_aempty[2], s_done;
-  __shared__ uint32_t s_tmem;
-  __shared__ float s_db[64];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kx = (A.K + 31) >> 5;       // X atoms per tile
-  const int n_sets = A.raw;             // A sets in tensor memory (2 when 2*128 + 64*kx <= 512 columns)
-  constexpr int S = kTsXStages, L = kTsXLo;
-  uint8_t* yraw = smem;                                  // raw dY pair slots: [atom 0 (features 0-31)][atom 1]
-  uint8_t* xhi = smem + kTsYSlots * 2 * kAtomBytes;      // X hi slot s at +s*kAtomBytes
-  uint8_t* xlo = xhi + S * kAtomBytes;                   // X lo slot l at +l*kAtomBytes (above every hi slot)
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&s_xfull[s], kWgLoadThreads); mbar_init(&s_xempty[s], 1); }
-    for (int l = 0; l < L; ++l) mbar_init(&s_lempty[l], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_afull[i], kWgLoadThreads); mbar_init(&s_aempty[i], 1); }
-    mbar_init(&s_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == kWgLoadWarps) tmem_alloc(&s_tmem, 512);
-  if (tid < 64) s_db[tid] = 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_a = s_tmem;                        // A set i: columns [128 i, 128 i + 128)
-  const uint32_t tmem_d = s_tmem + 128 * n_sets;         // D: 64 columns per X atom
-  const int per_tile = 1 + kx;
-  const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int n_items = my_tiles * per_tile;
-
-  if (warp < kWgLoadWarps) {
-    // ===== loaders =====
-    const int q = warp & 3;              // TMEM lane quarter of this warp: lanes 32q..32q+31
-    const bool is_hi = q < 2;            // quarters 0,1: dY_hi of features 0-31 / 32-63; quarters 2,3: dY_lo of the same
-    const int s0 = 64 * (warp >> 2);     // sample half of the tile this warp transposes
-    float bsum = 0.f;
-    auto issue = [&](int it) {
-      if (it < n_items) {
-        const int tl = it / per_tile, item = it - tl * per_tile;
-        const long long row0 = ((long long)blockIdx.x + (long long)tl * gridDim.x) * 128;
-        if (item == 0) {
-          uint8_t* dst = yraw + (tl % kTsYSlots) * 2 * kAtomBytes;
-          cp_async_atom_raw<kWgLoadThreads>(A.X, A.ldx, row0, A.M, 0, A.N, tid, dst);
-          cp_async_atom_raw<kWgLoadThreads>(A.X, A.ldx, row0, A.M, 32, A.N, tid, dst + kAtomBytes);
-        } else {
-          const int xi = tl * kx + item - 1;
-          mbar_wait(&s_xempty[xi % S], ((xi / S) & 1) ^ 1);   // the MMAs that read the stage's previous atom have completed
-          cp_async_atom_swz<kWgLoadThreads>(A.X2, A.ldx2, row0, A.M, 32 * (item - 1), A.K, tid, xhi + (xi % S) * kAtomBytes, true);
-        }
-      }
-      cp_async_commit();
-    };
-    // items in flight: a dY slot is rewritten two tiles later (after the barrier that ends its transposition), an X hi slot
-    // S atoms later (after atoms this loop has already handed to the MMA warp) -- neither can wait on a later item
-    int dist = kTsDist;
-    if (dist > 2 * per_tile - 1) dist = 2 * per_tile - 1;
-    if (dist > S - 1) dist = S - 1;
-    for (int it = 0; it < dist; ++it) issue(it);
-    long long c_issue = 0, c_land = 0, c_pair = 0, c_x = 0, c_aempty = 0, c_lempty = 0;
-    Tm tm;
-    for (int it = 0; it < n_items; ++it) {
-      const int tl = it / per_tile, item = it - tl * per_tile;
-      tm.start();
-      issue(it + dist);
-      tm.stop(c_issue); tm.start();
-      cp_async_wait_dyn(dist);
-      tm.stop(c_land); tm.start();
-      if (item == 0) {
-        loaders_bar_sync();                              // every loader's part of the pair has landed
-        const int set = tl % n_sets;
-        { Tm t2; t2.start(); mbar_wait(&s_aempty[set], ((tl / n_sets) & 1) ^ 1); t2.stop(c_aempty); }   // the MMAs that read this A set have completed
-        tc_fence_after();
-        const uint8_t* src = yraw + (tl % kTsYSlots) * 2 * kAtomBytes + (q & 1) * kAtomBytes + lane * 4;
-        const uint32_t taddr = tmem_a + ((uint32_t)(32 * q) << 16) + 128 * set + s0;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = *reinterpret_cast<const float*>(src + (s0 + 32 * c + i) * 128);
-            if (is_hi) { bsum += x; v[i] = x; }
-            else v[i] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-          }
-          tmem_st32(taddr + 32 * c, v);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&s_afull[set]);
-        loaders_bar_sync();                              // the raw slot may be rewritten (by the pair two tiles ahead)
-        tm.stop(c_pair);
-      } else {
-        const int xi = tl * kx + item - 1;
-        { Tm t2; t2.start(); mbar_wait(&s_lempty[xi % L], ((xi / L) & 1) ^ 1); t2.stop(c_lempty); }   // the MMAs that read the lo slot's previous image have completed
-        make_lo_atom<kWgLoadThreads>(xhi + (xi % S) * kAtomBytes, xlo + (xi % L) * kAtomBytes, tid, true, nullptr);
-        fence_async_smem();
-        mbar_arrive(&s_xfull[xi % S]);
-        tm.stop(c_x);
-      }
-    }
-    if (g_dbg && tid == 0 && blockIdx.x == 0) { g_dbg[16] = c_issue; g_dbg[17] = c_land; g_dbg[18] = c_pair; g_dbg[19] = c_x; g_dbg[20] = c_aempty; g_dbg[21] = c_lempty; }
-    cp_async_wait<0>();
-    if (A.db && is_hi) atomicAdd(&s_db[32 * (q & 1) + lane], bsum);
-  } else {
-    // ===== MMA issuer =====
-    const uint32_t idesc = instr_desc(128, 64, false, true);
-    int xi = 0;
-    long long w_y = 0, w_x = 0, w_iss = 0;
-    const long long t_start = TNF_CLK();
-    for (int tl = 0; tl < my_tiles; ++tl) {
-      const int set = tl % n_sets;
-      { const long long t0 = TNF_CLK(); mbar_wait(&s_afull[set], (tl / n_sets) & 1); w_y += TNF_CLK() - t0; }
-      for (int j = 0; j < kx; ++j, ++xi) {
-        const int s = xi % S;
-        { const long long t0 = TNF_CLK(); mbar_wait(&s_xfull[s], (xi / S) & 1); w_x += TNF_CLK() - t0; }
-        const long long ti = TNF_CLK();
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t xh = smem_u32(xhi + s * kAtomBytes);
-          const uint32_t lbo = smem_u32(xlo + (xi % L) * kAtomBytes) - xh;   // MN block 1 of the B operand = the lo image
-          const uint32_t aa = tmem_a + 128 * set;
-#pragma unroll 4
-          for (int kk = 0; kk < 16; ++kk)
-            mma_tf32_ts(tmem_d + 64 * j, aa + 8 * kk, desc_mnmajor(xh, kk, lbo), idesc, !(tl == 0 && kk == 0));
-          mma_commit(&s_xempty[s]);
-          mma_commit(&s_lempty[xi % L]);
-          if (j == kx - 1) mma_commit(&s_aempty[set]);
-        }
-        __syncwarp();
-        w_iss += TNF_CLK() - ti;
-      }
-    }
-    if (elect_one()) mma_commit(&s_done);
-    __syncwarp();
-    if (g_dbg && lane == 0 && blockIdx.x == 0) { g_dbg[8] = w_y; g_dbg[9] = w_x; g_dbg[10] = TNF_CLK() - t_start; g_dbg[11] = w_iss; }
-  }
-  mbar_wait(&s_done, 0);   // every MMA of this CTA has completed
-  tc_fence_after();
-  __syncthreads();
-  if (A.db && tid < 64) atomicAdd(A.db + tid, s_db[tid]);
-  if (warp < 4) {
-    const int n_out = (warp * 32 + lane) & 63;      // lanes n and n + 64 hold the dY_hi / dY_lo rows of feature n
-    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int j = 0; j < kx; ++j) {
-      float v[32], u[32];
-      tmem_ld32(taddr + 64 * j, v);        // x X_hi
-      tmem_ld32(taddr + 64 * j + 32, u);   // x X_lo
-      float* dst = A.dW + (long long)n_out * A.K + 32 * j;
-      if ((A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(A.dW) & 15u) == 0 && 32 * j + 31 < A.K) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)   // one L2 reduction per 16 bytes
-          red_add_f4(dst + i, make_float4(v[i] + u[i], v[i + 1] + u[i + 1], v[i + 2] + u[i + 2], v[i + 3] + u[i + 3]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (32 * j + i < A.K) atomicAdd(dst + i, v[i] + u[i]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kWgLoadWarps) tmem_dealloc(s_tmem, 512);
-}
-
-// Backward of a fused head (n_head <= 4 outputs on top of a ReLU hidden layer H[M,N]):
-//   dpre[o] = dOut[o] * act'(.) ; dH[m,j] = (H[m,j] > 0) * sum_o dpre[o] * Wh[o,j] ; dWh[o,j] += dpre[o]*H[m,j] ; dbh[o] += dpre[o]
-// act: 1 = truncated_exp(x-1) (backward uses exp(clamp(x-1,-15,15)), src/models.py:52-53; out = exp(x-1) is given),
-//      2 = sigmoid (out given).  One warp handles 32 rows at a time; lanes own columns j, j+32 (+64, +96).
-// Same algorithm with the copy engine doing the loads ("TMA" form, the default): in wgrad_ts_kernel every loader thread issues
-// its own cp.async chunks, makes lo images and transposes dY in lockstep, and the role timing shows that serial loader chain
-// -- not HBM latency, not the tensor pipe -- setting the pace (per tile of a 64x64 layer: 540 cycles issuing copies per item,
-// 1330 transposing the dY pair, 540 per X lo image; the MMA warp waits 60 % of the time).  Here
+// global loads in flight: it is bound by load latency, not by HBM or the tensor pipe.  Here warps transpose the raw dY tile
+// shared memory -> registers -> tcgen05.st (thread == TMEM lane == one output feature, hi or lo half; the column sums for
+// the bias gradient fall out of the same registers), so shared memory holds only landing zones, and the MMA reads one
+// operand from shared memory instead of two (33 instead of 48 cycles per 128x64x8 MMA, scripts/ubench/mma_bench.cu).
+// A first version issued the loads with per-thread cp.async from the same eight warps that transposed dY and made the lo
+// images (82 -> 55 us for a 64x64 layer at M = 2^18); its role timing showed that serial loader chain -- not HBM latency,
+// not the tensor pipe -- setting the pace (per tile: 540 cycles issuing copies per item, 1330 transposing the dY pair, 540
+// per X lo image; the MMA warp waited 60 % of the time).  This kernel (55 -> 41 us) splits the stages:
 //   warp  9   producer : one thread issues 2-D tensor-map loads, the dY tile as one raw 128 x 64 box, every X atom straight
 //                        into its SWIZZLE_128B_ATOM_32B operand image; up to 3 dY tiles + 6 X atoms (192 KB) in flight
 //   warps 0-3 dY       : raw tile -> registers -> tcgen05.st (thread == TMEM lane == feature, hi or lo half) + bias sums
 //   warps 4-7 X lo     : lo image of each landed X atom into one of two lo slots
-//   warp  8   MMA      : as above
+//   warp  8   MMA      : per X atom j: D[128, 64j..64j+64) += A_tmem[128, 128 samples] * [X_hi | X_lo] (16 k-steps, B addressed
+//                        with a per-atom leading-dimension offset to the lo slot); D stays in TMEM for the whole kernel
 // so the three stages run concurrently instead of back to back.
 constexpr int kW3XHi = 6, kW3XLo = 2, kW3Y = 3;
 constexpr int kW3Threads = 10 * 32;
@@ -1298,25 +1099,10 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   A.X = dy; A.ldx = lddy; A.X2 = x; A.ldx2 = ldx; A.dW = dweight; A.db = dbias; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* variant = getenv("TNF_WGRAD");   // diagnostics: "ss" / "ts" select the older kernels
-  const bool want_ss = variant && !strcmp(variant, "ss"), want_ts = variant && !strcmp(variant, "ts");
-  if (n == 64 && m < (1LL << 31) - 256 && !want_ss && !want_ts)
+  const char* variant = getenv("TNF_WGRAD");   // diagnostics: "ss" selects the both-operands-in-shared-memory kernel
+  const bool want_ss = variant && !strcmp(variant, "ss");
+  if (n == 64 && m < (1LL << 31) - 256 && !want_ss)
     return launch_wgrad_tma(dy, lddy, x, ldx, k, nullptr, 0, 0, dweight, dbias, nullptr, m, st);
-  if (n == 64 && !want_ss) {
-    // 64-wide layers: A operand in tensor memory (wgrad_ts_kernel)
-    const int kx = (k + 31) / 32;
-    A.raw = (2 * 128 + 64 * kx <= 512) ? 2 : 1;
-    const size_t smem = (size_t)(2 * kTsYSlots + kTsXStages + kTsXLo) * kAtomBytes + 1024;
-    static thread_local bool configured_ts = false;
-    if (!configured_ts) {
-      TNF_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      configured_ts = true;
-    }
-    const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
-    wgrad_ts_kernel<<<grid, kWgThreads, smem, st>>>(A);
-    TNF_LAUNCH_CHECK("linear_wgrad_ts_kernel");
-    return TNF_OK;
-  }
   // shared-memory plan: dY sets (hi + lo images of n/32 atoms each; two sets when they leave room for >= 2 X stages)
   // + S X stages (32 KB each)
   const size_t set_bytes = (size_t)(2 * ((n + 31) / 32)) * kAtomBytes;
