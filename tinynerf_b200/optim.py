@@ -30,7 +30,39 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         _lib.load()
+        tables = self.__dict__.setdefault("_tnf_tables", {})
         for group in self.param_groups:
+            # fast path: same parameter / gradient / state tensor OBJECTS as in the previous call of this (group, subset) --
+            # the fused iteration keeps every p.grad a view of one flat buffer, so nothing moves between steps and the ~100
+            # data_ptr() calls + list building below are skipped
+            fast = tables.get((id(group), only, "fast"))
+            ok = fast is not None
+            if ok:
+                cnt = 0
+                for p in group["params"]:
+                    if p.grad is not None and (only is None or id(p) in only):
+                        cnt += 1
+                ok = cnt == fast["n"]
+            if ok:
+                for p, g, m, v, dp in zip(fast["ps"], fast["gs"], fast["ms"], fast["vs"], fast["dptr"]):
+                    st = self.state[p]
+                    if p.grad is not g or st["exp_avg"] is not m or st["exp_avg_sq"] is not v or p.data_ptr() != dp:
+                        ok = False
+                        break
+            if ok:
+                step = None
+                for p in fast["ps"]:
+                    st = self.state[p]
+                    st["step"] += 1
+                    step = st["step"] if step is None else step
+                    if st["step"] != step:
+                        raise RuntimeError("FusedAdam expects all parameters of a group to share the step count")
+                b1, b2 = group["betas"]
+                with torch.cuda.device(fast["ps"][0].device):
+                    _lib.call("tnf_adam_step_grid", *fast["tabs"], fast["n"], float(group["lr"]), float(b1), float(b2),
+                              float(group["eps"]), float(group["weight_decay"]), int(step), int(max_blocks), _lib.stream_ptr(),
+                              nbytes=fast["nbytes"], extra_kernels=math.ceil(fast["n"] / 48) - 1)
+                continue
             ps, gs, ms, vs = [], [], [], []
             step = None
             for p in group["params"]:
@@ -56,13 +88,16 @@ class FusedAdam(torch.optim.Optimizer):
                 continue
             n = len(ps)
             key = tuple(t.data_ptr() for ts in (ps, gs, ms, vs) for t in ts)
-            tables = self.__dict__.setdefault("_tnf_tables", {})
             cached = tables.get((id(group), only))
             if cached is None or cached[0] != key:  # pointer tables are rebuilt only when a tensor moved
                 tab = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
                 cached = (key, tab(ps), tab(gs), tab(ms), tab(vs), (C.c_int64 * n)(*[t.numel() for t in ps]))
                 tables[(id(group), only)] = cached
             _, tp, tg, tm, tv, numel = cached
+            if all(g is p.grad for p, g in zip(ps, gs)):   # gradients already in the parameters' memory order: reusable as they are
+                tables[(id(group), only, "fast")] = {"ps": list(ps), "gs": list(gs), "ms": list(ms), "vs": list(vs),
+                                                     "dptr": [t.data_ptr() for t in ps], "tabs": (tp, tg, tm, tv, numel),
+                                                     "n": n, "nbytes": 28 * sum(t.numel() for t in ps)}
             b1, b2 = group["betas"]
             with torch.cuda.device(ps[0].device):
                 _lib.call("tnf_adam_step_grid", tp, tg, tm, tv, numel, n, float(group["lr"]), float(b1),
