@@ -78,6 +78,8 @@ _SIGNATURES = {
                                   C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_void_p]),
     "tnf_kplanes_bwd_scales": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
                                          C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_int32, C.c_int32, C.c_void_p]),
+    "tnf_kplanes_bwd_ex": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
+                                     C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_int32, C.c_void_p]),
     "tnf_cobafa_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_float), C.c_int32, c_f32p, C.c_int32, c_f32p, C.c_int64,
                                  C.c_int64, c_f32p, C.c_void_p]),

@@ -146,6 +146,112 @@ __global__ void __launch_bounds__(256) kplanes_kernel(const KPArgs A) {
   }
 }
 
+// ---- experimental variants of the scatter (scripts/time_kplanes.py; round-2 exploration) ----
+// MODE 1: gather + blend only (no reductions)   MODE 2: reductions only (no plane reads)
+// MODE 3: reductions issued by the TMA engine: the weighted rows are staged in shared memory and one
+//         cp.reduce.async.bulk (add.f32) per pair of x-adjacent corners (256 B) replaces 16 red.v4 lane operations.
+__device__ __forceinline__ void bulk_red_add(float* gdst, const float* ssrc, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+               : "memory");
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) kplanes_bwd_ex_kernel(const KPArgs A) {
+  extern __shared__ __align__(128) float stage[];
+  const int C = A.channels;
+  const int lps = C >> 2;
+  const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long n = gt / lps;
+  const int ch = (int)(gt % lps) * 4;
+  const bool live = n < A.n;
+  if (!live) n = A.n - 1;
+  const float* xp = A.x + n * A.x_stride;
+  const float cx = __ldg(xp), cy = __ldg(xp + 1), cz = __ldg(xp + 2);
+  const int F = A.n_scales * C;
+  const int s = blockIdx.y + A.scale0;
+  const int res = A.res[s];
+  const Axis ax = axis_setup(cx, res), ay = axis_setup(cy, res), az = axis_setup(cz, res);
+  Corners c[3];
+  c[0] = corners(ax, ay, res, C, ch);
+  c[1] = corners(ax, az, res, C, ch);
+  c[2] = corners(ay, az, res, C, ch);
+  float4 f[3];
+  if (MODE != 2) {
+    float4 v[3][4];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const float* pl = A.planes[s * 3 + p];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[p][k] = __ldg(reinterpret_cast<const float4*>(pl + c[p].off[k]));
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) f[p] = blend(v[p], c[p]);
+  } else {
+    f[0] = make_float4(cx, cy, cz, cx); f[1] = make_float4(cy, cz, cx, cy); f[2] = make_float4(cz, cx, cy, cz);
+  }
+  const float4 g = __ldg(reinterpret_cast<const float4*>(A.grad_out + n * F + s * C + ch));
+  const float4 g01 = mul4(g, f[2]);
+  float4 gp[3];
+  gp[0] = mul4(g01, f[1]);
+  gp[1] = mul4(g01, f[0]);
+  gp[2] = mul4(g, mul4(f[0], f[1]));
+  if (MODE == 1) {
+    const float t = gp[0].x + gp[1].y + gp[2].z + gp[0].w;
+    if (t == 1.2345678e-30f && live) A.grads[0][0] = t;
+    return;
+  }
+  if (MODE == 2) {
+    if (!live) return;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      float* gpl = A.grads[s * 3 + p];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float wk = c[p].w[k];
+        if (wk != 0.f)
+          red_add_f4(gpl + c[p].off[k], make_float4(TNF_MUL(wk, gp[p].x), TNF_MUL(wk, gp[p].y), TNF_MUL(wk, gp[p].z), TNF_MUL(wk, gp[p].w)));
+      }
+    }
+    return;
+  }
+  if (MODE == 3) {
+    // group of lps lanes = one sample; row (p, j) of the group's staging area = [x0 texel C floats | x1 texel C floats]
+    const int grp = threadIdx.x / lps, l = threadIdx.x % lps;
+    float* base = stage + (size_t)grp * 6 * 2 * C;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float wa = c[p].w[2 * j], wb = c[p].w[2 * j + 1];
+        float* row = base + (p * 2 + j) * 2 * C;
+        *reinterpret_cast<float4*>(row + l * 4) = make_float4(TNF_MUL(wa, gp[p].x), TNF_MUL(wa, gp[p].y), TNF_MUL(wa, gp[p].z), TNF_MUL(wa, gp[p].w));
+        *reinterpret_cast<float4*>(row + C + l * 4) = make_float4(TNF_MUL(wb, gp[p].x), TNF_MUL(wb, gp[p].y), TNF_MUL(wb, gp[p].z), TNF_MUL(wb, gp[p].w));
+      }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (live) {
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (l == p * 2 + j) {
+            float* gpl = A.grads[s * 3 + p];
+            const float* row = base + (p * 2 + j) * 2 * C;
+            const int o0 = c[p].off[2 * j] - ch, o1 = c[p].off[2 * j + 1] - ch;
+            const float wa = c[p].w[2 * j], wb = c[p].w[2 * j + 1];
+            if (wa != 0.f && wb != 0.f && o1 == o0 + C) {
+              bulk_red_add(gpl + o0, row, 8u * C);
+            } else {
+              if (wa != 0.f) bulk_red_add(gpl + o0, row, 4u * C);
+              if (wb != 0.f) bulk_red_add(gpl + o1, row + C, 4u * C);
+            }
+          }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
 int fill_args(KPArgs* A, const float* const* planes, float* const* grads, const int32_t* res, int n_scales,
               int channels, const float* x, int64_t x_stride, int64_t n) {
   TNF_REQUIRE(n >= 0, "negative n");
@@ -215,5 +321,28 @@ extern "C" int tnf_kplanes_bwd_scales(const float* const* planes, float* const* 
   const long long threads = n * (channels / 4);
   kplanes_kernel<true><<<dim3((unsigned)ceil_div(threads, 256), (unsigned)(scale_end - scale_begin)), 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   TNF_LAUNCH_CHECK("kplanes_bwd_kernel");
+  return TNF_OK;
+}
+
+// Experimental scatter variants (see kplanes_bwd_ex_kernel); not part of the reference-facing surface.
+extern "C" int tnf_kplanes_bwd_ex(const float* const* planes, float* const* grad_planes, const int32_t* res,
+                                  int32_t n_scales, int32_t channels, const float* x, int64_t x_stride, int64_t n,
+                                  const float* grad_out, int32_t mode, void* stream) {
+  using namespace tnf;
+  KPArgs A{};
+  int rc = fill_args(&A, planes, grad_planes, res, n_scales, channels, x, x_stride, n);
+  if (rc != TNF_OK || n == 0) return rc;
+  A.grad_out = grad_out;
+  const long long threads = n * (channels / 4);
+  const dim3 grid((unsigned)ceil_div(threads, 256), (unsigned)n_scales);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)(256 / (channels / 4)) * 6 * 2 * channels * sizeof(float);
+  if (mode == 1) kplanes_bwd_ex_kernel<1><<<grid, 256, 0, st>>>(A);
+  else if (mode == 2) kplanes_bwd_ex_kernel<2><<<grid, 256, 0, st>>>(A);
+  else if (mode == 3) {
+    cudaFuncSetAttribute(kplanes_bwd_ex_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kplanes_bwd_ex_kernel<3><<<grid, 256, smem, st>>>(A);
+  } else TNF_REQUIRE(false, "mode must be 1, 2 or 3");
+  TNF_LAUNCH_CHECK("kplanes_bwd_ex_kernel");
   return TNF_OK;
 }
