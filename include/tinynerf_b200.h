@@ -39,6 +39,10 @@ int tnf_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * late; capping the grid at the SMs actually free avoids that.  n_sms <= 0 removes the cap.  Per calling thread; returns
  * the previous value. */
 int tnf_set_sm_budget(int n_sms);
+/* Diagnostics: select an alternative kernel for the calling thread (which: 0 = weight gradient with both operands in
+ * shared memory, 1 = one-thread-per-texel TV kernel; value 1 = on, 0 = default).  Returns the previous value, -1 for an
+ * unknown `which`.  The library never reads the environment. */
+int tnf_set_variant(int which, int value);
 
 /* ---- a1/a2: NeRF-equation weights over packed rays -------------------------------------------
  * Replaces src/cuda.cu:66-95 (compute_weights_fwd, kernel :3-30) and src/cuda.cu:97-132
@@ -162,6 +166,14 @@ int tnf_kplanes_bwd(const float* const* planes, float* const* grad_planes, const
 int tnf_kplanes_bwd_scales(const float* const* planes, float* const* grad_planes, const int32_t* res, int32_t n_scales,
                            int32_t channels, const float* x, int64_t x_stride, int64_t n, const float* grad_out,
                            int32_t scale_begin, int32_t scale_end, void* stream);
+
+/* Diagnostics (scripts/time_kplanes.py): partial / alternative forms of tnf_kplanes_bwd used to
+ * measure what bounds it.  mode 1 = gather + blend only (no reductions), 2 = red.global.add.v4.f32 reductions only (no plane
+ * reads), 3 = full backward with the reductions issued by the TMA engine (rows staged in shared memory, one
+ * cp.reduce.async.bulk add.f32 per pair of x-adjacent corners).  Mode 3 computes the same gradients as tnf_kplanes_bwd. */
+int tnf_kplanes_bwd_ex(const float* const* planes, float* const* grad_planes, const int32_t* res, int32_t n_scales,
+                       int32_t channels, const float* x, int64_t x_stride, int64_t n, const float* grad_out, int32_t mode,
+                       void* stream);
 
 /* ---- a13: K-Planes total-variation regulariser ---------------------------------------------------
  * Replaces KPlanesFeaturePlane.loss_tv / KPlanesFeatureField.loss_tv (src/models.py:115-118,165-172)

@@ -4,6 +4,7 @@ import os, sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
+from tinynerf_b200 import _lib
 import bench
 from tinynerf_b200 import synthetic
 from tinynerf_b200.run import RayStore, TrainConfig, Trainer
@@ -46,7 +47,9 @@ def run(label, env=None, **kw):
 
 run("default")
 run("default again")
-run("wgrad SS (slower)", env={"TNF_WGRAD": "ss"})
+_lib.load().tnf_set_variant(0, 1)
+run("wgrad SS (slower)")
+_lib.load().tnf_set_variant(0, 0)
 run("no prefetch", prefetch=False)
 run("inflight unbounded", max_inflight_steps=0)
 run("inflight 2", max_inflight_steps=2)

@@ -15,7 +15,7 @@ for k, n in shapes:
                     torch.zeros(n, device="cuda"), ld)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for mode in (sys.argv[1:] or ["ss", "tma", "ss", "tma"]):
-    os.environ["TNF_WGRAD"] = mode
+    _lib.load().tnf_set_variant(0, 1 if mode == "ss" else 0)
     for k, n in shapes:
         x, dy, dw, db, ld = bufs[(k, n)]
         ts = []

@@ -169,12 +169,12 @@ def test_tv_fwd_bwd_equals_separate_passes():
     for acc in (1, 0):
         gc_, gd = [b.clone() for b in base], [b.clone() for b in base]
         sums_c = torch.empty_like(sums_b)
-        os.environ["TNF_TV_KERNEL"] = "texel"
+        _lib.load().tnf_set_variant(1, 1)   # the one-thread-per-texel kernel
         try:
             _lib.call("tnf_tv_fwd_bwd", ptrs, (C.c_void_p * n)(*[t.data_ptr() for t in gc_]), res, n, 32, wts, gs.data_ptr(), acc,
                       sums_c.data_ptr(), st)
         finally:
-            os.environ.pop("TNF_TV_KERNEL")
+            _lib.load().tnf_set_variant(1, 0)
         _lib.call("tnf_tv_fwd_bwd", ptrs, (C.c_void_p * n)(*[t.data_ptr() for t in gd]), res, n, 32, wts, gs.data_ptr(), acc,
                   sums_b.data_ptr(), st)
         assert torch.allclose(sums_c, sums_b, rtol=1e-6, atol=0)

@@ -80,3 +80,65 @@ def test_f32_rounding_helper():
     from tinynerf_b200.core import _f32
     for v in (0.01, 0.01 ** (1 / 16), 5.196152422706632 / 256, 1e5, 0.1, 1e-45, 3.4e38):
         assert _f32(v) == torch.tensor(v, dtype=torch.float32).item()
+
+
+def test_partition_and_steps_tags_are_voided_by_in_place_edits():
+    """the trusted-partition / contiguous-steps tags must not survive an in-place edit of the tensors (the
+    reference's own loop does `info[:, 0] += current_size`, src/run.py:236)."""
+    info = torch.tensor([[0, 3], [3, 2]], dtype=torch.int32)
+    assert not core.is_trusted_partition(info)
+    core.tag_partition(info)
+    assert core.is_trusted_partition(info)
+    info[:, 0] += 5
+    assert not core.is_trusted_partition(info)
+    packed, steps = torch.zeros(5, 7), torch.zeros(5)
+    assert core.tagged_steps(packed) is None
+    core.tag_steps(packed, steps)
+    assert core.tagged_steps(packed) is steps
+    packed[:, 6] = 1.0
+    assert core.tagged_steps(packed) is None
+    core.tag_steps(packed, steps)
+    steps.add_(1.0)
+    assert core.tagged_steps(packed) is None
+
+
+def test_ray_store_epoch_coverage_with_rewinds():
+    """Every ray is handed out exactly once per epoch even when speculative draws are handed back (RayStore.rewind) --
+    as long as the caller never rewinds across the epoch boundary, which `remaining()` lets it avoid (Trainer caps the
+    chunks it marches at once by it)."""
+    from tinynerf_b200.run import RayStore
+    n, B = 1000, 64
+    o = torch.arange(n, dtype=torch.float32)[:, None].expand(n, 3).contiguous()
+    store = RayStore(o, o, o, "cpu", seed=3)
+    g = torch.Generator().manual_seed(0)
+    for epoch in range(3):
+        seen = []
+        while True:
+            rem = store.remaining()
+            K = int(torch.randint(1, 5, (1,), generator=g))
+            K = min(K, rem // B) if rem >= B else 1
+            draw = min(K * B, rem) if rem < B else K * B
+            ro, _, _ = store.next(draw)
+            ids = ro[:, 0].long().tolist()
+            used = int(torch.randint(1, K + 1, (1,), generator=g)) if K > 1 else K
+            if used < K:
+                store.rewind((K - used) * B)
+                again, _, _ = store.next((K - used) * B)      # replay: the same rays in the same order
+                assert again[:, 0].long().tolist() == ids[used * B:]
+                store.rewind((K - used) * B)
+                ids = ids[:used * B]
+            seen += ids
+            if store.remaining() == store._m:   # wrapped exactly
+                break
+        assert sorted(seen) == list(range(n)), f"epoch {epoch}: coverage broken"
+
+
+def test_trainer_close_restores_gc_state():
+    """manual_gc freezes/disables the cyclic collector process-wide; close() must undo that."""
+    import gc
+    from tinynerf_b200.run import Trainer
+    t = Trainer.__new__(Trainer)
+    t._gc_frozen, t._gc_was_enabled = True, True
+    gc.freeze(); gc.disable()
+    t.close()
+    assert gc.isenabled() and gc.get_freeze_count() == 0 and not t._gc_frozen

@@ -54,6 +54,7 @@ _SIGNATURES = {
                                              c_f32p, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int32, C.c_void_p]),
     "tnf_set_sm_budget": (C.c_int, [C.c_int]),
+    "tnf_set_variant": (C.c_int, [C.c_int, C.c_int]),
     "tnf_shuffle_next": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64),
                                    C.POINTER(C.c_uint64), C.c_void_p]),
     "tnf_weights_fwd": (C.c_int, [c_f32p, c_f32p, C.c_int64, c_i32p, C.c_float, c_f32p, C.c_int64, C.c_int64,

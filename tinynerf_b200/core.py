@@ -117,6 +117,32 @@ class RayMarcherAABB:
 RayMarcher = RayMarcherUnbounded | RayMarcherAABB
 
 
+def tag_partition(info: torch.Tensor) -> None:
+    """Mark `info` as a 0-based contiguous partition of the packed samples (what RayProvider produces): the weights
+    kernels then skip their in-kernel validation (TNF_W_TRUSTED_PARTITION).  The tag records the tensor's version counter,
+    so an in-place edit afterwards (the reference's own loop does `info[:, 0] += current_size`, src/run.py:236) voids it."""
+    info._tnf_partition = info._version
+
+
+def is_trusted_partition(info: torch.Tensor) -> bool:
+    tag = getattr(info, "_tnf_partition", None)
+    return tag is not None and tag is not False and tag == info._version
+
+
+def tag_steps(packed: torch.Tensor, steps: torch.Tensor) -> None:
+    """Attach the contiguous copy of column 6 the pack kernel wrote beside the rows; honoured only while neither tensor
+    has been modified in place since."""
+    packed._tnf_steps = steps
+    packed._tnf_steps_versions = (packed._version, steps._version)
+
+
+def tagged_steps(packed: torch.Tensor) -> torch.Tensor | None:
+    steps = getattr(packed, "_tnf_steps", None)
+    if steps is None or getattr(packed, "_tnf_steps_versions", None) != (packed._version, steps._version):
+        return None
+    return steps
+
+
 def _f32(x) -> float:
     """Python float -> the fp32 value torch uses when the scalar meets a float32 tensor (round to nearest even)."""
     return C.c_float(float(x)).value
@@ -397,8 +423,9 @@ class RayProvider:
             _lib.call("tnf_march_pack", C.byref(h["p"]), h["rays_o"].data_ptr(), h["rays_d"].data_ptr(), R,
                       h["info_offset"], h["mask_bits"].data_ptr(), info.data_ptr(), packed.data_ptr(), steps.data_ptr(),
                       None, n, _lib.stream_ptr(), nbytes=24 * R + 8 * R + 4 * R * h["words"] + 32 * n)
-        packed._tnf_steps = steps
-        info._tnf_partition = h["info_offset"] == 0
+        tag_steps(packed, steps)
+        if h["info_offset"] == 0:
+            tag_partition(info)
         return packed, info
 
     @torch.no_grad()
@@ -427,7 +454,7 @@ class NerfWeights(torch.autograd.Function):
     def forward(ctx: Any, sigmas: torch.Tensor, steps: torch.Tensor, info: torch.Tensor, threshold: float):  # type: ignore
         sigmas = sigmas.contiguous()
         info = info.contiguous()
-        flags = _cuda.TRUSTED_PARTITION if getattr(info, "_tnf_partition", False) else 0
+        flags = _cuda.TRUSTED_PARTITION if is_trusted_partition(info) else 0
         weights = _cuda.weights_fwd(sigmas, steps, info, threshold, flags)  # steps may be a strided view
         ctx.save_for_backward(sigmas, steps, info, weights)
         ctx.flags = flags
@@ -495,7 +522,7 @@ class NerfRenderer(torch.nn.Module):
         device = packed_samples.device
         n_samples = packed_samples.size(0)
         n_rays = packing_info.size(0)
-        steps = getattr(packed_samples, "_tnf_steps", None)
+        steps = tagged_steps(packed_samples)
         if steps is None:
             steps = packed_samples[:, 6]  # strided view, read in place by the kernel
         try:

@@ -16,6 +16,9 @@ void set_error(const char* fmt, ...) {
 
 static thread_local int g_sm_budget = 0;   // tnf_set_sm_budget: persistent grids of this thread use at most this many SMs
 
+static thread_local int g_variant[kVariantCount] = {0};   // tnf_set_variant: diagnostic kernel selection of this thread
+int variant(int which) { return (which >= 0 && which < kVariantCount) ? g_variant[which] : 0; }
+
 int sm_count() {
   // per-device cache; benign race (same value written)
   static int cache[64] = {0};
@@ -36,6 +39,13 @@ extern "C" int tnf_version(void) { return 1000; }
 extern "C" int tnf_set_sm_budget(int n_sms) {
   const int prev = tnf::g_sm_budget;
   tnf::g_sm_budget = n_sms > 0 ? n_sms : 0;
+  return prev;
+}
+
+extern "C" int tnf_set_variant(int which, int value) {
+  if (which < 0 || which >= tnf::kVariantCount) return -1;
+  const int prev = tnf::g_variant[which];
+  tnf::g_variant[which] = value;
   return prev;
 }
 

@@ -41,6 +41,21 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int sm_count();  // cached per device
+// Diagnostic kernel variants, selected per calling thread with tnf_set_variant (never from the environment).
+constexpr int kVariantWgradSS = 0;   // 1: both-operands-in-shared-memory weight-gradient kernel
+constexpr int kVariantTvTexel = 1;   // 1: one-thread-per-texel TV kernel
+constexpr int kVariantCount = 4;
+int variant(int which);
+
+// Function attributes (cudaFuncSetAttribute) belong to the device/context, not to the calling thread: a call site keeps one
+// flag per device and opts in again the first time it runs on another GPU of the process.  The flag is set after the
+// attribute call, so a racing thread at worst repeats an idempotent call.
+struct PerDeviceOnce {
+  unsigned char done[64];
+  int dev() const { int d = 0; return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : -1; }
+  bool pending() const { const int d = dev(); return d < 0 || !done[d]; }
+  void mark() { const int d = dev(); if (d >= 0) done[d] = 1; }
+};
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

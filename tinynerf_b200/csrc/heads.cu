@@ -464,10 +464,10 @@ extern "C" int tnf_heads_fwd(const float* feats, int64_t ld_feats, int32_t feat_
   A.hs = hs_out; A.rgb = rgb; A.sigma = sigma; A.M = m;
   A.n_tiles = (int)ceil_div(m, 128);
   const size_t smem = (size_t)(kAH + kAL) * kAtomBytes + (size_t)kWN * kChunkBytes + 8 * 2048 + 4096 + 1024;
-  static thread_local bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured{};
+  if (configured.pending()) {
     TNF_CUDA(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured.mark();
   }
   TNF_REQUIRE(m < (1LL << 31) - 256, "too many rows for the tensor-map coordinates");
   CUtensorMap tm_xc, tm_feats;

@@ -395,10 +395,10 @@ extern "C" int tnf_heads_bwd_data(const float* dh3, const float* dhs, const floa
   rc = make_atom_map_b(&tm_dhs, dhs, m, kBHid, kBHid);
   if (rc != TNF_OK) return rc;
   const size_t smem = (size_t)(kBAH + kBAL) * kAtomBytes + (size_t)A.wn * slot + 8 * 2048 + 1024;
-  static thread_local bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured{};
+  if (configured.pending()) {
     TNF_CUDA(cudaFuncSetAttribute(heads_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    configured = true;
+    configured.mark();
   }
   const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
   heads_bwd_data_kernel<<<grid, kBThreads, smem, st>>>(A, tm_dh3, tm_dhs);

@@ -1001,10 +1001,10 @@ int launch_wgrad_tma(const float* dy, int64_t lddy, const float* xa, int64_t ldx
   if (rc != TNF_OK) return rc;
   if (kb == 0) tm_xb = tm_x;
   const size_t smem = (size_t)(2 * kW3Y + kW3XHi + kW3XLo) * kAtomBytes + 1024;
-  static thread_local bool configured_tma = false;
-  if (!configured_tma) {
+  static PerDeviceOnce configured_tma{};
+  if (configured_tma.pending()) {
     TNF_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    configured_tma = true;
+    configured_tma.mark();
   }
   const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
   wgrad_tma_kernel<<<grid, kW3Threads, smem, st>>>(A, tm_dy, tm_x, tm_xb);
@@ -1035,12 +1035,15 @@ template <typename Kern>
 int launch_lin(Kern kern, LinArgs& A, cudaStream_t st, const char* name) {
   const size_t smem = plan_smem(A.N, A.K, &A.ring, &A.raw);
   TNF_REQUIRE(A.ring >= 2 && A.raw >= 1, "layer too large for the shared-memory plan (n=%d, k=%d)", A.N, A.K);
-  static thread_local const void* configured[8] = {nullptr};
+  static const void* configured_all[64][8] = {};   // per device (the attribute is per device/context)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  const void** configured = configured_all[dev];
   bool done = false;
-  for (auto c : configured) done |= (c == (const void*)kern);
+  for (int i = 0; i < 8; ++i) done |= (configured[i] == (const void*)kern);
   if (!done) {
     TNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    for (auto& c : configured) if (!c) { c = (const void*)kern; break; }
+    for (int i = 0; i < 8; ++i) if (!configured[i]) { configured[i] = (const void*)kern; break; }
   }
   const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
   kern<<<grid, kWsThreads, smem, st>>>(A);
@@ -1099,8 +1102,7 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   A.X = dy; A.ldx = lddy; A.X2 = x; A.ldx2 = ldx; A.dW = dweight; A.db = dbias; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* variant = getenv("TNF_WGRAD");   // diagnostics: "ss" selects the both-operands-in-shared-memory kernel
-  const bool want_ss = variant && !strcmp(variant, "ss");
+  const bool want_ss = variant(kVariantWgradSS) == 1;   // diagnostics: the both-operands-in-shared-memory kernel
   if (n == 64 && m < (1LL << 31) - 256 && !want_ss)
     return launch_wgrad_tma(dy, lddy, x, ldx, k, nullptr, 0, 0, dweight, dbias, nullptr, m, st);
   // shared-memory plan: dY sets (hi + lo images of n/32 atoms each; two sets when they leave room for >= 2 X stages)
@@ -1112,10 +1114,10 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   int st_ = (int)((budget - (size_t)A.raw * set_bytes) / (2 * kAtomBytes));
   A.ring = st_ > kMaxStages ? kMaxStages : st_;
   const size_t smem = (size_t)A.raw * set_bytes + (size_t)A.ring * 2 * kAtomBytes + 1024;
-  static thread_local bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured{};
+  if (configured.pending()) {
     TNF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    configured = true;
+    configured.mark();
   }
   const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
   wgrad_kernel<<<grid, kWgThreads, smem, st>>>(A);

@@ -227,8 +227,7 @@ __global__ void __launch_bounds__(256, 3) tv_march_kernel(const TVMarchArgs M) {
 // launches tv_march_kernel when the planes allow it; returns false (nothing launched) otherwise
 template <bool SUMS>
 bool launch_tv_march(const TVArgs& A, cudaStream_t st) {
-  const char* force = getenv("TNF_TV_KERNEL");   // diagnostics / tests: "texel" keeps the one-thread-per-texel kernel
-  if (A.channels != 32 || (force && !strcmp(force, "texel"))) return false;
+  if (A.channels != 32 || variant(kVariantTvTexel) == 1) return false;   // diagnostics / tests: the one-thread-per-texel kernel
   TVMarchArgs M{};
   M.tv = A;
   long long warps = 0;

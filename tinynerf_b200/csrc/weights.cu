@@ -649,11 +649,6 @@ __global__ void fallback_bwd_kernel(const WArgs A) {
 int pick_tile(long long n, int warps_per_sm) {
   // Tiles between 256 and kMaxTile samples.  Small inputs get ONE wave: the tile is rounded UP so that the task count
   // does not exceed the resident warps (a second, mostly empty wave would double the latency-bound run time).
-  static const int forced = [] {
-    const char* e = getenv("TNF_W_TILE");  // tuning knob (multiple of 128, <= 2048)
-    return e ? atoi(e) : 0;
-  }();
-  if (forced >= 128 && forced <= kMaxTile && forced % 128 == 0) return forced;
   // One task per resident warp and k full waves: the smallest k whose tile fits kMaxTile, then the tile rounded UP
   // so the task count does not spill into a mostly empty extra wave (worth 13% at 2^24 samples).
   const long long slots = (long long)sm_count() * warps_per_sm;
@@ -680,12 +675,12 @@ int launch(bool bwd, WArgs A, cudaStream_t st) {
   const dim3 grid((unsigned)ctas), block(kWarps * 32);
   const size_t ring_fwd = (size_t)kWarps * kDepth * 2 * 32 * sizeof(float4);  // 32 KB
   const size_t ring_bwd = (size_t)kWarps * kDepth * 3 * 32 * sizeof(float4);  // 48 KB
-  static thread_local bool configured = false;
-  if (!configured) {  // the backward ring plus the static arrays exceeds the 48 KB default
+  static PerDeviceOnce configured{};
+  if (configured.pending()) {  // the backward ring plus the static arrays exceeds the 48 KB default
     TNF_CUDA(cudaFuncSetAttribute(weights_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bwd));
     TNF_CUDA(cudaFuncSetAttribute(weights_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bwd));
     TNF_CUDA(cudaFuncSetAttribute(weights_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bwd));
-    configured = true;
+    configured.mark();
   }
   if (!bwd) {
     const bool ftz = A.thr >= 1.5777218e-30f;  // 2^-99, the kernel's tiny_thr boundary (see exp_fast)

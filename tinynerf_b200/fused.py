@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from . import _cuda, _lib
-from .core import NerfRenderer
+from .core import NerfRenderer, is_trusted_partition, tagged_steps
 from .models import (KPlanesFeatureField, VanillaColorDecoder, VanillaOpacityDecoder, _channels_last_storage,
                      _ensure_channels_last_)
 
@@ -205,11 +205,11 @@ class FusedKPlanesStep:
         if not (packed.is_contiguous() and info.is_contiguous() and info.dtype == torch.int32):
             raise RuntimeError("packed samples / packing info must be contiguous ([N,7] fp32, [R,2] int32)")
         target = target.contiguous()
-        steps = getattr(packed, "_tnf_steps", None)
+        steps = tagged_steps(packed)
         sstride = 1
         if steps is None:
             steps, sstride = packed[:, 6], 7
-        flags = _cuda.TRUSTED_PARTITION if getattr(info, "_tnf_partition", False) else 0
+        flags = _cuda.TRUSTED_PARTITION if is_trusted_partition(info) else 0
         status = None if flags else torch.empty(1, dtype=torch.int32, device=self.dev)
         self._reserve(n, r)
         self.attach_grads()

@@ -23,7 +23,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .core import (ContractionAABB, ContractionMip360, NerfRenderer, OccupancyGrid, RayMarcherAABB,
-                   RayMarcherUnbounded, RayProvider)
+                   RayMarcherUnbounded, RayProvider, tag_partition, tag_steps, tagged_steps)
 from .optim import FusedAdam
 from .models import (CobafaFeatureField, KPlanesFeatureField, VanillaColorDecoder, VanillaFeatureMLP,
                      VanillaOpacityDecoder)
@@ -125,8 +125,10 @@ class RayStore:
         assert self._pos >= 0
 
     def remaining(self) -> int:
-        """Rays left before the order wraps around; the shuffle is continuous, so a batch may straddle the wrap."""
-        return self.n
+        """Rays of this rank left before its order wraps around (the next epoch's swaps start there).  A batch may
+        straddle the wrap, but it must not be handed back afterwards: the next epoch's swaps would already have moved
+        entries of the positions being replayed."""
+        return self._m - (self._pos % self._m)
 
     def _next_indices(self, batch: int) -> torch.Tensor:
         on_gpu = (not self.host) and self.device.type == "cuda"
@@ -203,7 +205,9 @@ class TrainConfig:
                                         # one-CTA-per-SM tensor-core kernels then start late or share HBM badly -- 188.6 M
                                         # samples/s sequential vs 166.9 M (8064 Adam blocks) / 151-164 M (persistent 148/296)
     manual_gc: bool = True              # collect Python garbage at the occupancy-update cadence instead of at random steps
-                                        # (a generation-2 pause on ONE rank stalls every rank at the next collective)
+                                        # (a generation-2 pause on ONE rank stalls every rank at the next collective).
+                                        # PROCESS-WIDE side effect while the trainer lives: gc.freeze() + gc.disable();
+                                        # Trainer.close() / `with Trainer(...)` restores the collector
     occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
     seed: int = 0
 
@@ -313,7 +317,7 @@ class Trainer:
             rays_o, rays_d, rgbs = self.store.next(self.cfg.batch_size)
             samples, info = self.ray_provider(rays_o, rays_d, training=True, info_offset=current)
             acc_s.append(samples)
-            acc_steps.append(samples._tnf_steps)
+            acc_steps.append(tagged_steps(samples))
             acc_i.append(info)
             acc_rgb.append(rgbs)
             current += samples.size(0)
@@ -322,9 +326,9 @@ class Trainer:
             if k > 4096:
                 raise RuntimeError("occupancy grid rejects every sample: cannot fill a batch")
         packed = torch.cat(acc_s, 0)
-        packed._tnf_steps = torch.cat(acc_steps, 0)
+        tag_steps(packed, torch.cat(acc_steps, 0))
         info = torch.cat(acc_i, 0)
-        info._tnf_partition = True  # consecutive batches were packed at consecutive offsets
+        tag_partition(info)  # consecutive batches were packed at consecutive offsets
         return packed, torch.cat(acc_rgb, 0), info
 
     @torch.no_grad()
@@ -341,7 +345,10 @@ class Trainer:
         parts = []
         while True:
             K = max(1, int(self._chunks_guess) + 1)
-            K = min(K, max(1, self.store.remaining() // B)) if self.store.remaining() >= B else K
+            rem = self.store.remaining()
+            # never speculate across the epoch boundary (RayStore.rewind must not cross it): cap the chunks marched at
+            # once at the rays left in the epoch; a chunk that straddles the wrap is marched alone (K = 1 is never rewound)
+            K = min(K, rem // B) if rem >= B else 1
             rays_o, rays_d, rgbs = self.store.next(K * B)
             noise = torch.empty(((K + 3) & ~3) * B, S, device=dev)[:K * B]   # allocation quantised to 4 chunks (see RayStore.next)
             offsets = []
@@ -375,10 +382,10 @@ class Trainer:
             packed, info, rgb = parts[0]
         else:
             packed = torch.cat([p[0] for p in parts], 0)
-            packed._tnf_steps = torch.cat([p[0]._tnf_steps for p in parts], 0)
+            tag_steps(packed, torch.cat([tagged_steps(p[0]) for p in parts], 0))
             info = torch.cat([p[1] for p in parts], 0)
             rgb = torch.cat([p[2] for p in parts], 0)
-        info._tnf_partition = True
+        tag_partition(info)
         return packed, rgb, info
 
     # ---- occupancy update, sharded by depth slice across ranks ----------------------------------
@@ -422,7 +429,7 @@ class Trainer:
         (packed, rgbs, info), done = self._queue.pop(0)
         main = torch.cuda.current_stream(self.device)
         main.wait_event(done)
-        for t in (packed, packed._tnf_steps, rgbs, info):
+        for t in (packed, tagged_steps(packed), rgbs, info):
             t.record_stream(main)
         return packed, rgbs, info
 
@@ -430,9 +437,10 @@ class Trainer:
         if self.cfg.manual_gc and self.device.type == "cuda":
             import gc
             if not self._gc_frozen:
+                self._gc_was_enabled = gc.isenabled()
                 gc.collect()
                 gc.freeze()    # everything allocated so far (torch's ~10^6 module objects) leaves the collector's reach:
-                gc.disable()   # later collections only scan what the loop itself created
+                gc.disable()   # later collections only scan what the loop itself created (undone by close())
                 self._gc_frozen = True
             elif self.train_step % self.occupancy_grid_updates == 0:
                 gc.collect()
@@ -483,6 +491,31 @@ class Trainer:
             self._prefetch()
         self.last = {"loss": loss.detach(), "n_samples": packed.size(0), "n_rays": info.size(0)}
         return self.last
+
+    # ---- process-wide side effects are undone here -------------------------------------------------
+    def close(self) -> None:
+        """Restore what step() changed process-wide: with `manual_gc` the cyclic collector is frozen and disabled while
+        the trainer runs (collections happen at the occupancy-update cadence); close() -- also called by `with Trainer(...)`
+        and on garbage collection of the trainer -- unfreezes it and re-enables it if it was enabled before."""
+        if self._gc_frozen:
+            import gc
+            gc.unfreeze()
+            if getattr(self, "_gc_was_enabled", True):
+                gc.enable()
+            self._gc_frozen = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _mark_enqueued(self) -> None:
         if self.cfg.max_inflight_steps > 0 and self.device.type == "cuda":
