@@ -181,3 +181,45 @@ def test_properties_at_full_size(logn):
     sub[:, 0] -= s0
     w_sub = _cuda.compute_weights_fwd(sig[s0:s1].clone(), steps[s0:s1].clone(), sub, 0.0)
     assert torch.allclose(w_sub, w[s0:s1], rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("n,scale,thr", [(1 << 18, 1.0, 1e-4), (1 << 18, 8.0, 0.0), (1 << 20, 4.0, 1e-4), (1 << 22, 8.0, 1e-4)])
+def test_trusted_partition_path_vs_reference_kernel(ref_cuda, n, scale, thr):
+    """TNF_W_TRUSTED_PARTITION (no in-kernel validation of `info`) is the path the trainer and the headline microbench
+    use: same bar against the UNMODIFIED reference kernel as the validated path (mask bit-identical, 1e-5 relative)."""
+    sig, steps, info, g = [t.to(DEV) for t in make(n, seed=2000 + n.bit_length() - 1, scale=scale)]
+    assert info.size(0) <= (1 << 20)
+    w_ref = ref_cuda.compute_weights_fwd(sig, steps, info, thr)
+    w = _cuda.weights_fwd(sig, steps, info, thr, _cuda.TRUSTED_PARTITION)
+    check_weights(w, w_ref)
+    assert torch.equal(w, _cuda.weights_fwd(sig, steps, info, thr, 0)), "trusted and validated paths must agree bit for bit"
+    g_ref = ref_cuda.compute_weights_bwd(sig, steps, info, w_ref, g)
+    gs = _cuda.weights_bwd(sig, steps, info, w_ref, g, _cuda.TRUSTED_PARTITION)
+    check_grads(gs, g_ref, steps, w_ref, g, info)
+    assert torch.equal(gs, _cuda.weights_bwd(sig, steps, info, w_ref, g, 0))
+
+
+@pytest.mark.parametrize("logn", [24, 26])
+def test_full_size_vs_c_oracle_with_termination(logn):
+    """Config-5 sizes with early termination (thr = 1e-4) against the C restatement of src/cuda.cu walking every sample
+    on the host (beyond the reference kernel's 2^20-ray validity).  The oracle evaluates expf, the kernel __expf like the
+    reference, so the termination decision may flip where T is within a few ulp of thr: such flips must stay below
+    1 in 20,000 samples and everything else meets the bar of test_fwd_bwd_vs_c_oracle."""
+    n = 1 << logn
+    sig, info, g = synthetic.packed_rays(n, seed=1000 + logn)
+    sig = sig * 4.0
+    steps = torch.full_like(sig, STEP)
+    w_ref = orc.weights_fwd(sig, steps, info, 1e-4)
+    assert (w_ref == 0).float().mean() > 0.01, "termination not exercised"
+    sd, td, idv, gd = sig.to(DEV), steps.to(DEV), info.to(DEV), g.to(DEV)
+    for flags in (_cuda.TRUSTED_PARTITION, 0):
+        w = _cuda.weights_fwd(sd, td, idv, 1e-4, flags).cpu()
+        flips = (w > 0) != (w_ref > 0)
+        assert int(flips.sum()) <= n // 20000, f"{int(flips.sum())} termination flips"
+        ok = ~flips
+        assert bool(((w - w_ref).abs()[ok] <= 2e-5 * w_ref.abs()[ok] + 3e-7).all())
+    g_ref = orc.weights_bwd(sig, steps, info, w_ref, g)
+    wd = w_ref.to(DEV)
+    for flags in (_cuda.TRUSTED_PARTITION, 0):
+        gs = _cuda.weights_bwd(sd, td, idv, wd, gd, flags).cpu()
+        check_grads(gs, g_ref, steps, w_ref, g, info, rtol=2e-5)
