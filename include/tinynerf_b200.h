@@ -175,6 +175,37 @@ int tnf_kplanes_bwd_ex(const float* const* planes, float* const* grad_planes, co
                        int32_t channels, const float* x, int64_t x_stride, int64_t n, const float* grad_out, int32_t mode,
                        void* stream);
 
+/* ---- stand-alone forms of the reference's public helper callables (csrc/helpers.cu) ----------------------------
+ * Not on the training hot path (RayProvider / the feature fields fuse these steps); they back the methods of the host-side
+ * mirror that callers may use on their own, so that no method of the mirror runs PyTorch arithmetic.
+ *   tnf_marcher_aabb      RayMarcherAABB.__call__ (src/core.py:73-88): t_values, step_sizes [n_rays][n_steps]
+ *   tnf_contract          ContractionAABB.__call__ (src/core.py:27-31; mask [n] bytes) / ContractionMip360.__call__
+ *                         with order = inf (src/core.py:16-20; mask must be NULL)
+ *   tnf_plane_lookup_*    KPlanesFeaturePlane.forward (src/models.py:105-113): one channels-last [h][w][C] plane,
+ *                         xy [n][xy_stride] (x -> w axis, y -> h axis) -> out [n][C]; bwd ACCUMULATES into grad_plane
+ *   tnf_grid3_lookup_*    CobafaGrid.forward (src/models.py:228-238): one channels-last [d][h][w][C] grid
+ *   tnf_abs_mean_*        KPlanesFeaturePlane.loss_l1 (src/models.py:120-121): *sum = sum |x| (double; the caller divides
+ *                         by n); bwd writes grad_x = sign(x) * (*grad_scale) / n */
+int tnf_marcher_aabb(const float* aabb6 /*[host] min xyz, max xyz*/, float near_, float far_, float step_size,
+                     const float* rays_o, const float* rays_d, int64_t n_rays, int32_t n_steps, float* t_values,
+                     float* step_sizes, void* stream);
+int tnf_contract(int32_t scene, const float* aabb6 /*[host], AABB scenes*/, const float* coords, int64_t n, float* out,
+                 uint8_t* mask, void* stream);
+int tnf_plane_lookup_fwd(const float* plane, int32_t h, int32_t w, int32_t channels, const float* xy, int64_t xy_stride,
+                         int64_t n, float* out, void* stream);
+int tnf_plane_lookup_bwd(float* grad_plane, int32_t h, int32_t w, int32_t channels, const float* xy, int64_t xy_stride,
+                         int64_t n, const float* grad_out, void* stream);
+int tnf_grid3_lookup_fwd(const float* grid, int32_t d, int32_t h, int32_t w, int32_t channels, const float* x,
+                         int64_t x_stride, int64_t n, float* out, void* stream);
+int tnf_grid3_lookup_bwd(float* grad_grid, int32_t d, int32_t h, int32_t w, int32_t channels, const float* x,
+                         int64_t x_stride, int64_t n, const float* grad_out, void* stream);
+/* PositionalEncoding.forward (src/models.py:30-39): x [n][x_stride] (first d columns) -> out [n][ld_out], columns
+ * c*2*n_freqs + k = sin(2^k pi x_c), c*2*n_freqs + n_freqs + k = cos(2^k pi x_c). */
+int tnf_positional_encoding(const float* x, int64_t x_stride, int32_t d, int32_t n_freqs, int64_t n, float* out,
+                            int64_t ld_out, void* stream);
+int tnf_abs_mean_fwd(const float* x, int64_t n, double* sum, void* stream);
+int tnf_abs_mean_bwd(const float* x, int64_t n, const float* grad_scale, float* grad_x, void* stream);
+
 /* ---- a13: K-Planes total-variation regulariser ---------------------------------------------------
  * Replaces KPlanesFeaturePlane.loss_tv / KPlanesFeatureField.loss_tv (src/models.py:115-118,165-172)
  * and their autograd backward for a table of n_planes channels-last planes [res][res][C].
@@ -235,6 +266,17 @@ int tnf_cobafa_bwd(const float* const* basis, float* const* grad_basis, const in
  *   wgrad: dweight += dy^T x ; dbias += column sums of dy      (atomic accumulation: zero them first)
  *   head_bwd: gradients of the fused head: dh (masked by h > 0), dhead_w, dhead_b (accumulated)
  */
+/* Layers wider than the resident-weight kernels above cover (in_features > 160 or out_features > 128: the reference's
+ * VanillaFeatureMLP(10, 256, 8), src/models.py:59-68, the decoders behind it and the Cobafa colour head's 179-wide first
+ * layer): the same 3xTF32 tcgen05 arithmetic with both operands streamed (csrc/wide.cu).  Any m, n, k >= 1; row-major fp32;
+ * weight [n][ldw]; act 0 = none, 1 = ReLU, 2 = exp(v - 1), 3 = sigmoid; dgrad masks with (relu_src > 0) when given;
+ * wgrad ACCUMULATES into dweight [n][lddw] / dbias [n] (zero them first). */
+int tnf_wide_linear_fwd(const float* x, int64_t ldx, const float* weight, int64_t ldw, const float* bias, float* y, int64_t ldy,
+                        int64_t m, int32_t n, int32_t k, int32_t act, void* stream);
+int tnf_wide_linear_bwd_data(const float* dy, int64_t lddy, const float* weight, int64_t ldw, float* dx, int64_t lddx,
+                             const float* relu_src, int64_t ldrs, int64_t m, int32_t n, int32_t k, void* stream);
+int tnf_wide_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dweight, int64_t lddw,
+                               float* dbias, int64_t m, int32_t n, int32_t k, void* stream);
 int tnf_linear_fwd(const float* x, int64_t ldx, const float* weight, const float* bias, float* y, int64_t ldy,
                    int64_t m, int32_t n, int32_t k, int32_t relu, const float* head_w, const float* head_b,
                    float* head_out, int32_t n_head, int32_t head_act, void* stream);

@@ -90,7 +90,7 @@ def test_heads_match_reference_golden(golden):
     sig = models.VanillaOpacityDecoder(96).to(DEV)
     col = models.VanillaColorDecoder(8, 96, 64, 3).to(DEV)
     f, d = g["feats"].to(DEV), g["dirs"].to(DEV)
-    assert sig.net.fused_ok(f)
+    sig.net.require_supported(f)
     assert torch.allclose(sig(f).cpu(), g["sigma"], rtol=1e-5, atol=1e-7)
     assert torch.allclose(col(f, d).cpu(), g["rgb"], rtol=1e-5, atol=1e-7)
 
@@ -159,7 +159,9 @@ def test_color_input_matches_positional_encoding_bitwise(golden):
     d = torch.nn.functional.normalize(torch.randn(5000, 3, generator=gen), dim=-1).to(DEV)
     f = torch.randn(5000, 96, generator=gen).to(DEV).requires_grad_(True)
     x = mlp_ops.color_input(f, d, 8)
-    want = torch.cat([pe(d), d, f], -1)
+    from oracle import ref_port as rp
+    want = torch.cat([rp.positional_encoding(d, 8), d, f], -1)   # the reference's formulation with torch's CUDA sin/cos
+    assert torch.equal(pe(d), want[:, :48])
     assert x.shape == (5000, 147) and torch.equal(x, want)
     x.backward(torch.ones_like(x))
     assert torch.equal(f.grad, torch.ones_like(f))
@@ -173,3 +175,51 @@ def test_color_input_matches_positional_encoding_bitwise(golden):
     with torch.cuda.device(0):
         _lib.call("tnf_color_input", packed.data_ptr() + 12, 7, None, 0, 8, 0, out.data_ptr(), 52, 5000, _lib.stream_ptr())
     assert torch.equal(out[:, :51], want[:, :51]) and bool((out[:, 51] == 0).all())
+
+
+@pytest.mark.parametrize("m", [77, 3000])
+def test_wide_stacks_forward_backward_vs_float64(m):
+    """a17 + the Cobafa colour head: stacks wider than the resident-weight kernels (in > 160 or out > 128) run on the
+    streamed-operand tcgen05 kernels (csrc/wide.cu) -- forward and every gradient against float64, same bar as the narrow
+    stacks (1e-5 relative on outputs, 2e-5 of the tensor's max on gradients, ReLU-kink rows excluded in both)."""
+    import copy
+    torch.manual_seed(2)
+    trunk = models.VanillaFeatureMLP(10, 256, 8).to(DEV)          # src/run.py:131 : 60 -> 256 (x9) -> 256
+    sig = models.VanillaOpacityDecoder(256).to(DEV)               # 256 -> 64 -> 1
+    col = models.VanillaColorDecoder(8, 256, 64, 3).to(DEV)       # 307 -> 64 (x4) -> 3
+    ccol = models.VanillaColorDecoder(8, 128, 64, 3).to(DEV)      # Cobafa's colour head: 179 -> 64 (x4) -> 3
+    gen = torch.Generator().manual_seed(m)
+    x0 = (torch.rand(m, 3, generator=gen) * 2 - 1).to(DEV)
+    f0 = (torch.randn(m, 256, generator=gen) * 0.3).to(DEV)
+    c0 = (torch.randn(m, 128, generator=gen) * 0.3).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(m, 3, generator=gen), dim=-1).to(DEV)
+    t64, s64, k64, cc64 = [copy.deepcopy(mm).double() for mm in (trunk, sig, col, ccol)]
+    pe10 = trunk.encoding(x0).double()   # fp32 sin/cos of the kernel, shared by both evaluations
+    f64 = f0.double().requires_grad_(True)
+    c64 = c0.double().requires_grad_(True)
+    pe8 = col.pe(d).double()
+    xk64 = torch.cat([pe8, d.double(), f64], -1)
+    xc64 = torch.cat([pe8, d.double(), c64], -1)
+    o64 = [t64.net.net(pe10), torch.exp(s64.net.net(f64) - 1.0), torch.sigmoid(k64.net.net(xk64)), torch.sigmoid(cc64.net.net(xc64))]
+    safes = [_safe_rows(t64.net, pe10), _safe_rows(s64.net, f64.detach()), _safe_rows(k64.net, xk64.detach()),
+             _safe_rows(cc64.net, xc64.detach())]
+    f = f0.clone().requires_grad_(True)
+    c = c0.clone().requires_grad_(True)
+    outs = [trunk(x0), sig(f), col(f, d), ccol(c, d)]
+    for a, b in zip(outs, o64):
+        assert a.shape == b.shape
+        assert torch.allclose(a.double(), b, rtol=1e-5, atol=1e-6), (a.double() - b).abs().max()
+    gos = [torch.randn_like(o) * s[:, None] for o, s in zip(outs, safes)]
+    sum((o * go).sum() for o, go in zip(outs, gos)).backward()
+    sum((o * go.double()).sum() for o, go in zip(o64, gos)).backward()
+    mine, ref = {"f": f.grad, "c": c.grad}, {"f": f64.grad, "c": c64.grad}
+    for name, mod, mod_ref in (("trunk", trunk, t64), ("sig", sig, s64), ("col", col, k64), ("ccol", ccol, cc64)):
+        for (k, p), (_, q) in zip(mod.named_parameters(), mod_ref.named_parameters()):
+            mine[f"{name}.{k}"], ref[f"{name}.{k}"] = p.grad, q.grad
+    bad = {}
+    for k in mine:
+        scale = ref[k].abs().max().clamp_min(1e-12)
+        e = ((mine[k].double() - ref[k]).abs().max() / scale).item()
+        if e > 2e-5:
+            bad[k] = e
+    assert not bad, bad

@@ -154,8 +154,7 @@ def _relu_kink_samples(layers, x64, margin):
     return near
 
 
-@pytest.mark.parametrize("tensor_core_mlp", [False, True])
-def test_kplanes_renderer_vs_torch_on_gpu(tensor_core_mlp):
+def test_kplanes_renderer_vs_torch_on_gpu():
     """Config 2 shape: K-Planes + vanilla heads, AABB, ~2^18-sample batch; whole render + backward against the
     PyTorch restatement on the same GPU (weights via the reference's own kernel), colours and every parameter
     gradient at the 1e-5 bar.
@@ -165,12 +164,7 @@ def test_kplanes_renderer_vs_torch_on_gpu(tensor_core_mlp):
     which changes that sample's gradient by O(1/64) in either of them.  Rays that contain such a sample (float64
     pre-activation within 3e-6 of the kink; a few % of the rays) are given zero loss weight in BOTH pipelines, so the
     comparison measures arithmetic, not the kink lottery."""
-    saved = models._USE_TC_MLP
-    models._USE_TC_MLP = tensor_core_mlp
-    try:
-        _renderer_case()
-    finally:
-        models._USE_TC_MLP = saved
+    _renderer_case()
 
 
 def _renderer_case():

@@ -32,27 +32,36 @@ def test_planes_are_channels_last_with_reference_init(golden):
     assert models._channels_last_storage(p).data_ptr() == p.data_ptr()
     chk = float(sum(q.double().sum() for q in f.parameters()))
     assert abs(chk - g["param_checksum"]) < 1e-6 * abs(g["param_checksum"])   # same values as the reference's seeded init
-    assert abs(float(f.loss_tv()) - g["tv"]) < 1e-6 * g["tv"] and abs(float(f.loss_l1()) - g["l1"]) < 1e-6 * g["l1"]
+    # (loss_tv / loss_l1 values against the same golden: tests/test_gpu_helpers.py -- the product has no CPU arithmetic)
     # round trip through a contiguous state_dict keeps the kernels' layout
     sd = {k: v.contiguous() for k, v in f.state_dict().items()}
     f.load_state_dict(sd)
     assert models._ensure_channels_last_(f.planes[0][0].plane) is not None
 
 
-def test_marchers_and_contractions_match_reference(golden):
-    g = golden("provider_aabb")
-    m = core.RayMarcherAABB(g["aabb"], 64, 0.1)
-    t, s = m(g["rays_o"], g["rays_d"])
-    assert torch.equal(t, g["t_values"]) and torch.equal(s, g["step_sizes"])
-    g = golden("provider_unbounded")
-    m = core.RayMarcherUnbounded(64, 0.1, 1e5, uniform_range=1.7)
-    t, s = m(g["rays_o"], g["rays_d"])
-    assert torch.equal(t.contiguous(), g["t_values"]) and torch.equal(s.contiguous(), g["step_sizes"])
-    pts = torch.randn(100, 3) * 3
-    c, mask = core.ContractionMip360()(pts)
-    assert mask is None and c.abs().max() <= 1.0
-    c, mask = core.ContractionAABB(torch.tensor([[0.0, 0, 0], [2.0, 2, 2]]))(pts)
-    assert bool(((c[mask] >= -1) & (c[mask] <= 1)).all())
+def test_no_cpu_or_eager_path_in_the_product():
+    """The mirror's compute methods need CUDA tensors and the built library: on CPU tensors they raise (the reference's
+    CHECK_CUDA message), they never fall back to PyTorch arithmetic."""
+    import pytest
+    pts = torch.randn(10, 3)
+    for fn in (lambda: core.ContractionMip360()(pts), lambda: core.ContractionAABB(torch.tensor([[0.0, 0, 0], [2.0, 2, 2]]))(pts),
+               lambda: core.RayMarcherAABB(torch.tensor([[-1.0, -1, -1], [1.0, 1, 1]]), 8, 0.1)(pts, pts),
+               lambda: models.KPlanesFeaturePlane(8, (16, 16))(pts[:, :2]), lambda: models.KPlanesFeaturePlane(8, (16, 16)).loss_tv(),
+               lambda: models.KPlanesFeaturePlane(8, (16, 16)).loss_l1(), lambda: models.CobafaGrid(8, 4)(pts),
+               lambda: models.PositionalEncoding(4)(pts), lambda: models.MLP(16, 32, 1, 1)(torch.randn(4, 16)),
+               lambda: models.VanillaOpacityDecoder(96)(torch.randn(4, 96))):
+        with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+            fn()
+    with pytest.raises(NotImplementedError):
+        core.ContractionMip360(order=2)(pts)
+    # and the product's host modules contain no call of the PyTorch ops the reference's bodies were made of
+    import ast
+    from tinynerf_b200 import fused, mlp_ops, run
+    banned = {"grid_sample", "mse_loss", "index_add_", "index_add", "linear", "relu", "sigmoid", "cumprod", "repeat_interleave"}
+    for mod in (core, models, fused, mlp_ops, run):
+        tree = ast.parse(open(mod.__file__).read())
+        calls = {n.func.attr for n in ast.walk(tree) if isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute)}
+        assert not (calls & banned), (mod.__name__, calls & banned)
 
 
 def test_synthetic_packed_rays_are_a_partition():

@@ -81,6 +81,18 @@ _SIGNATURES = {
                                          C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_int32, C.c_int32, C.c_void_p]),
     "tnf_kplanes_bwd_ex": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
                                      C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_int32, C.c_void_p]),
+    "tnf_marcher_aabb": (C.c_int, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, c_f32p, c_f32p, C.c_int64, C.c_int32,
+                                   c_f32p, c_f32p, C.c_void_p]),
+    "tnf_contract": (C.c_int, [C.c_int32, C.POINTER(C.c_float), c_f32p, C.c_int64, c_f32p, C.c_void_p, C.c_void_p]),
+    "tnf_plane_lookup_fwd": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_void_p]),
+    "tnf_plane_lookup_bwd": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_void_p]),
+    "tnf_grid3_lookup_fwd": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p,
+                                       C.c_void_p]),
+    "tnf_grid3_lookup_bwd": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p,
+                                       C.c_void_p]),
+    "tnf_positional_encoding": (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, c_f32p, C.c_int64, C.c_void_p]),
+    "tnf_abs_mean_fwd": (C.c_int, [c_f32p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tnf_abs_mean_bwd": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, C.c_void_p]),
     "tnf_cobafa_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_float), C.c_int32, c_f32p, C.c_int32, c_f32p, C.c_int64,
                                  C.c_int64, c_f32p, C.c_void_p]),
@@ -99,6 +111,12 @@ _SIGNATURES = {
     "tnf_adam_step_grid": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_float, C.c_float,
                                      C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int32, C.c_void_p]),
+    "tnf_wide_linear_fwd": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_void_p]),
+    "tnf_wide_linear_bwd_data": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64,
+                                           C.c_int32, C.c_int32, C.c_void_p]),
+    "tnf_wide_linear_bwd_weight": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int32,
+                                             C.c_int32, C.c_void_p]),
     "tnf_linear_fwd": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                  C.c_int32, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_void_p]),
     "tnf_linear_bwd_data": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64,

@@ -10,10 +10,11 @@ Same class names, constructor arguments, attributes and return values as the ref
     NerfWeights                              src/core.py:192-207
     NerfRenderer                             src/core.py:209-267
 
-The per-ray helpers (contractions, marchers) keep their stand-alone PyTorch definitions because they
-are part of the public surface, but RayProvider never calls them on the hot path: it hands their
-parameters to the fused march/contract/occupancy/pack kernels (tnf_march_count / tnf_march_pack).
-There is no CPU path: CUDA tensors are required and the C-ABI library must be built.
+The per-ray helpers (contractions, marchers) are part of the public surface and run their own small kernels
+(tnf_contract, tnf_marcher_aabb: the same device code the fused path uses, csrc/helpers.cu); RayProvider never
+calls them on the hot path: it hands their parameters to the fused march/contract/occupancy/pack kernels
+(tnf_march_count / tnf_march_pack).  There is no CPU or PyTorch path: CUDA tensors are required and the
+C-ABI library must be built; anything the kernels do not cover raises.
 """
 from __future__ import annotations
 
@@ -37,10 +38,11 @@ class ContractionMip360:
 
     @torch.no_grad()
     def __call__(self, coords: torch.Tensor) -> Tuple[torch.Tensor, None]:
-        """Mip-NeRF 360 contraction to [-1,1] (src/core.py:16-20)."""
-        norm = torch.norm(coords, p=self.order, dim=-1, keepdim=True)  # type: ignore
-        coords = torch.where(norm <= 1.0, coords, (2.0 - 1.0 / norm) * coords / norm) / 2.0
-        return coords, None
+        """Mip-NeRF 360 contraction to [-1,1] (src/core.py:16-20), infinity norm (the reference's default and the only
+        order its training loop uses, src/run.py:156); tnf_contract."""
+        if self.order != float("inf"):
+            raise NotImplementedError("ContractionMip360: only order=inf is implemented (src/run.py:156)")
+        return _contract(1, None, coords)[0], None
 
 
 @dataclass
@@ -49,10 +51,24 @@ class ContractionAABB:
 
     @torch.no_grad()
     def __call__(self, coords: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Affine map of the box to [-1,1] plus inside-box mask (src/core.py:27-31)."""
-        mask = torch.all((coords >= self.aabb[0]) & (coords <= self.aabb[1]), dim=-1)
-        coords = (coords - self.aabb[0]) / (self.aabb[1] - self.aabb[0]) * 2.0 - 1.0
-        return coords, mask
+        """Affine map of the box to [-1,1] plus inside-box mask (src/core.py:27-31); tnf_contract."""
+        return _contract(0, self.aabb, coords)
+
+
+def _aabb6(aabb: torch.Tensor):
+    return (C.c_float * 6)(*aabb.detach().to("cpu", torch.float32).reshape(-1).tolist())
+
+
+def _contract(scene: int, aabb: torch.Tensor | None, coords: torch.Tensor):
+    _lib.load()
+    _lib.require_cuda(coords, "coords")
+    flat = coords.reshape(-1, 3).to(torch.float32).contiguous()
+    out = torch.empty_like(flat)
+    mask = torch.empty(flat.size(0), dtype=torch.bool, device=flat.device) if scene == 0 else None
+    with torch.cuda.device(flat.device):
+        _lib.call("tnf_contract", scene, None if aabb is None else _aabb6(aabb), flat.data_ptr(), flat.size(0),
+                  out.data_ptr(), _lib.ptr(mask), _lib.stream_ptr(), nbytes=25 * flat.size(0))
+    return out.view(coords.shape), None if mask is None else mask.view(coords.shape[:-1])
 
 
 Contraction = ContractionMip360 | ContractionAABB
@@ -102,15 +118,19 @@ class RayMarcherAABB:
 
     @torch.no_grad()
     def __call__(self, rays_o: torch.Tensor, rays_d: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        device = rays_o.device
-        eps = 1e-9
-        aabb_distances = self.aabb.unsqueeze(1) - rays_o
-        aabb_intersections = aabb_distances / torch.where(rays_d == 0.0, rays_d + eps, rays_d)
-        t_min = torch.amax(torch.amin(aabb_intersections, dim=0), dim=1)
-        t_min = torch.clamp(t_min, min=self.near, max=self.far)
-        steps = torch.arange(self.n_samples, dtype=torch.float, device=device) * self.step_size
-        t_values = t_min[:, None] + steps
-        step_sizes = torch.full_like(t_values, self.step_size)
+        """t_values, step_sizes [R, n_samples] (src/core.py:73-88); tnf_marcher_aabb."""
+        _lib.load()
+        _lib.require_cuda(rays_o, "rays_o")
+        _lib.require_cuda(rays_d, "rays_d")
+        o, d = rays_o.to(torch.float32).contiguous(), rays_d.to(torch.float32).contiguous()
+        R, S = o.size(0), int(self.n_samples)
+        t_values = torch.empty(R, S, device=o.device)
+        step_sizes = torch.empty(R, S, device=o.device)
+        ss = self.step_size
+        step = float(ss.item()) if isinstance(ss, torch.Tensor) else _f32(ss)
+        with torch.cuda.device(o.device):
+            _lib.call("tnf_marcher_aabb", _aabb6(self.aabb), _f32(self.near), _f32(self.far), step, o.data_ptr(), d.data_ptr(),
+                      R, S, t_values.data_ptr(), step_sizes.data_ptr(), _lib.stream_ptr(), nbytes=24 * R + 8 * R * S)
         return t_values, step_sizes
 
 
@@ -510,9 +530,9 @@ class NerfRenderer(torch.nn.Module):
         self.sigma_decoder = sigma_decoder
         self.rgb_decoder = rgb_decoder
         self.bg_color = bg_color
-        # dense_rgb: evaluate the colour head on every sample instead of gathering the (weights > 0) subset.
+        # The colour head is evaluated on EVERY sample instead of the gathered (weights > 0) subset of src/core.py:243-250.
         # Same result (a masked-out sample has weight 0, so it adds exactly 0 to the ray and receives exactly 0
-        # gradient) without the nonzero() host sync and the gather/scatter passes of src/core.py:243-250.
+        # gradient) without the nonzero() host sync and the gather/scatter passes; there is no other branch.
         self.dense_rgb = True
         assert hasattr(self.feature_module, "feature_dim"), "feature module requires a feature_dim attribute"
 
@@ -532,16 +552,7 @@ class NerfRenderer(torch.nn.Module):
             samples_sigmas = self.sigma_decoder(samples_features).ravel()
             weights: torch.Tensor = NerfWeights.apply(samples_sigmas, steps, packing_info,
                                                       early_termination_threshold)  # type: ignore
-            if self.dense_rgb:
-                samples_rgbs = self.rgb_decoder(samples_features, packed_samples[:, 3:6])
-            else:
-                mask = weights > 0.0
-                idx = mask.nonzero(as_tuple=True)[0]  # one sync, shared by the three masked ops below
-                if idx.numel() == 0:
-                    raise ValueError("no samples remaining")
-                rgbs_m = self.rgb_decoder(samples_features.index_select(0, idx),
-                                          packed_samples[:, 3:6].index_select(0, idx))
-                samples_rgbs = torch.zeros((n_samples, 3), device=device).index_copy(0, idx, rgbs_m)
+            samples_rgbs = self.rgb_decoder(samples_features, packed_samples[:, 3:6])
         except ValueError:
             print("Empty iteration, every sample is masked")
             samples_rgbs = torch.zeros((n_samples, 3), device=device, requires_grad=True)

@@ -108,6 +108,30 @@ TNF_HD float trilinear_zeros(const float* __restrict__ g, int D, int H, int W, f
   return acc;
 }
 
+// Contraction of one world-space point (src/core.py:16-31): AABB -> affine map to [-1,1] + inside-box flag,
+// unbounded -> Mip-NeRF 360 contraction with the infinity norm (no mask: returns true).
+TNF_HD bool contract_point(const MarchConst& M, const float p[3], float q[3]) {
+  bool inside = true;
+  if (M.scene == 0) {  // ContractionAABB (src/core.py:29-30)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      inside = inside && (p[c] >= M.a0[c]) && (p[c] <= M.a1[c]);
+      q[c] = TNF_SUB(TNF_MUL(TNF_DIV(TNF_SUB(p[c], M.a0[c]), M.ext[c]), 2.f), 1.f);
+    }
+  } else {             // ContractionMip360, order=inf (src/core.py:18-19)
+    const float n = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fabsf(p[2]));
+    if (n <= 1.f) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) q[c] = TNF_MUL(p[c], 0.5f);
+    } else {
+      const float k = TNF_SUB(2.f, TNF_MUL(TNF_DIV(1.f, n), 1.f));  // 2. - norm.reciprocal()*1.
+#pragma unroll
+      for (int c = 0; c < 3; ++c) q[c] = TNF_MUL(TNF_DIV(TNF_MUL(k, p[c]), n), 0.5f);
+    }
+  }
+  return inside;
+}
+
 struct SampleOut {
   float p[3];   // contracted coordinates in [-1,1]
   float step;   // step size of this sample
@@ -131,24 +155,7 @@ TNF_HD SampleOut march_sample(const MarchConst& M, const float o[3], const float
   float p[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) p[c] = TNF_ADD(o[c], TNF_MUL(d[c], t));  // src/core.py:174
-  bool inside = true;
-  if (M.scene == 0) {  // ContractionAABB (src/core.py:29-30)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      inside = inside && (p[c] >= M.a0[c]) && (p[c] <= M.a1[c]);
-      s.p[c] = TNF_SUB(TNF_MUL(TNF_DIV(TNF_SUB(p[c], M.a0[c]), M.ext[c]), 2.f), 1.f);
-    }
-  } else {             // ContractionMip360, order=inf (src/core.py:18-19)
-    const float n = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fabsf(p[2]));
-    if (n <= 1.f) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) s.p[c] = TNF_MUL(p[c], 0.5f);
-    } else {
-      const float k = TNF_SUB(2.f, TNF_MUL(TNF_DIV(1.f, n), 1.f));  // 2. - norm.reciprocal()*1.
-#pragma unroll
-      for (int c = 0; c < 3; ++c) s.p[c] = TNF_MUL(TNF_DIV(TNF_MUL(k, p[c]), n), 0.5f);
-    }
-  }
+  const bool inside = contract_point(M, p, s.p);
   s.step = step;
   // src/core.py:151-156,176: mask = marcher_mask & (trilinear(grid) > thr); the lookup has no side effect,
   // so it is skipped for samples the marcher mask already rejects (about half of an AABB lattice)

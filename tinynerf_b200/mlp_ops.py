@@ -18,23 +18,26 @@ from torch.autograd import Function
 
 from . import _lib
 
-MAX_IN = 160
+MAX_IN = 160   # resident-weight kernels (csrc/mlp.cu): in_features <= 160, out_features a multiple of 32 up to 128
+_HEAD_ACT_TO_WIDE = {0: 0, 1: 2, 2: 3}   # fused-head activation code -> tnf_wide_linear_fwd `act`
+
+
+def _resident(n: int, k: int) -> bool:
+    """Layer [n, k] fits the resident-weight tcgen05 kernels; otherwise the streamed-operand kernels (csrc/wide.cu) run it."""
+    return n % 32 == 0 and n <= 128 and k <= MAX_IN
 
 
 def supported(linears: Sequence[torch.nn.Linear], x: torch.Tensor) -> bool:
-    """True if the stack can run on the tensor-core kernels (CUDA fp32, hidden widths multiple of 32 <= 128,
-    inputs <= 160 wide)."""
+    """True if the stack can run on the tensor-core kernels: CUDA fp32 with biases; every width is covered by one of the
+    two kernel families, except a <= 4-wide head behind a hidden layer wider than 128 (tnf_head_bwd's limit; no
+    configuration of the reference has one)."""
     if not x.is_cuda or x.dtype != torch.float32 or len(linears) < 2:
         return False
     if any(l.weight.dtype != torch.float32 or l.bias is None for l in linears):
         return False
-    hidden = [l.out_features for l in linears[:-1]]
-    if any(h % 32 != 0 or h > 128 for h in hidden):
+    if linears[-1].out_features <= 4 and linears[-2].out_features > 128:
         return False
-    if linears[0].in_features > MAX_IN:
-        return False
-    last = linears[-1].out_features
-    return last <= 4 or (last % 32 == 0 and last <= 128)
+    return True
 
 
 def _prep(x: torch.Tensor) -> torch.Tensor:
@@ -52,6 +55,18 @@ def _prep(x: torch.Tensor) -> torch.Tensor:
 def _lin_fwd(x, w, b, relu, head=None, head_act=0, want_y=True):
     m, k = x.shape
     n = w.size(0)
+    if not _resident(n, k):
+        y = torch.empty(m, n, device=x.device)
+        _lib.call("tnf_wide_linear_fwd", x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _lib.ptr(b), y.data_ptr(), n, m, n, k,
+                  1 if relu else 0, _lib.stream_ptr(), nbytes=4 * (m * (k + n) + n * k), flops=2 * m * n * k)
+        ho = None
+        if head is not None:   # the small output layer as its own launch (the resident kernels fuse it into the epilogue)
+            hw, hb = head
+            nh = hw.size(0)
+            ho = torch.empty(m, nh, device=x.device)
+            _lib.call("tnf_wide_linear_fwd", y.data_ptr(), n, hw.data_ptr(), hw.stride(0), hb.data_ptr(), ho.data_ptr(), nh, m, nh, n,
+                      _HEAD_ACT_TO_WIDE[head_act], _lib.stream_ptr(), nbytes=4 * m * (n + nh), flops=2 * m * nh * n)
+        return y, ho
     y = torch.empty(m, n, device=x.device) if want_y else None
     hw = hb = ho = None
     nh = 0
@@ -63,6 +78,30 @@ def _lin_fwd(x, w, b, relu, head=None, head_act=0, want_y=True):
               int(relu), _lib.ptr(hw), _lib.ptr(hb), _lib.ptr(ho), nh, head_act, _lib.stream_ptr(),
               nbytes=4 * (m * (k + (n if want_y else 0) + nh) + n * k), flops=2 * m * n * (k + nh))
     return y, ho
+
+
+def _wgrad(dy, x, gw, gb, stream):
+    m, (n, k) = dy.size(0), gw.shape
+    if _resident(n, k):
+        _lib.call("tnf_linear_bwd_weight", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gw.data_ptr(), gb.data_ptr(), m, n, k,
+                  stream, nbytes=4 * (m * (n + k) + n * k), flops=2 * m * n * k)
+    else:
+        _lib.call("tnf_wide_linear_bwd_weight", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gw.data_ptr(), k, gb.data_ptr(),
+                  m, n, k, stream, nbytes=4 * (m * (n + k) + n * k), flops=2 * m * n * k)
+
+
+def _dgrad(dy, w, dx, relu_src, stream, k_begin=0):
+    """dx[:, :] = dy @ w[:, k_begin:k_begin + dx.size(1)] (masked by relu_src > 0 when given)."""
+    m, n = dy.shape
+    k = dx.size(1)
+    if _resident(n, w.size(1)) and k_begin == 0 and k == w.size(1):
+        _lib.call("tnf_linear_bwd_data", dy.data_ptr(), dy.stride(0), w.data_ptr(), dx.data_ptr(), dx.stride(0),
+                  _lib.ptr(relu_src), 0 if relu_src is None else relu_src.stride(0), m, n, k, stream,
+                  nbytes=4 * (m * (n + (2 if relu_src is not None else 1) * k) + n * k), flops=2 * m * n * k)
+    else:
+        _lib.call("tnf_wide_linear_bwd_data", dy.data_ptr(), dy.stride(0), w.data_ptr() + 4 * k_begin, w.stride(0), dx.data_ptr(),
+                  dx.stride(0), _lib.ptr(relu_src), 0 if relu_src is None else relu_src.stride(0), m, n, k, stream,
+                  nbytes=4 * (m * (n + (2 if relu_src is not None else 1) * k) + n * k), flops=2 * m * n * k)
 
 
 class _FusedMLP(Function):
@@ -126,32 +165,22 @@ class _FusedMLP(Function):
                           h_last.size(1), ws[-1].size(0), ctx.head_act, stream,
                           nbytes=4 * m * (2 * h_last.size(1) + 2 * ws[-1].size(0)))
             else:  # wide last layer without activation
-                n, k = ws[-1].shape
-                _lib.call("tnf_linear_bwd_weight", grad_out.data_ptr(), grad_out.stride(0), h_last.data_ptr(),
-                          h_last.stride(0), gws[-1].data_ptr(), gbs[-1].data_ptr(), m, n, k, stream,
-                          nbytes=4 * (m * (n + k) + n * k), flops=2 * m * n * k)
+                _wgrad(grad_out, h_last, gws[-1], gbs[-1], stream)
                 dh = torch.empty_like(h_last)
-                _lib.call("tnf_linear_bwd_data", grad_out.data_ptr(), grad_out.stride(0), ws[-1].data_ptr(), dh.data_ptr(),
-                          dh.stride(0), h_last.data_ptr(), h_last.stride(0), m, n, k, stream,
-                          nbytes=4 * (m * (n + 2 * k) + n * k), flops=2 * m * n * k)
+                _dgrad(grad_out, ws[-1], dh, h_last, stream)
             gx = None
             for i in range(L - 2, -1, -1):
                 inp = acts[i - 1] if i > 0 else x2
                 n, k = ws[i].shape
-                _lib.call("tnf_linear_bwd_weight", dh.data_ptr(), dh.stride(0), inp.data_ptr(), inp.stride(0),
-                          gws[i].data_ptr(), gbs[i].data_ptr(), m, n, k, stream,
-                          nbytes=4 * (m * (n + k) + n * k), flops=2 * m * n * k)
+                _wgrad(dh, inp, gws[i], gbs[i], stream)
                 if i > 0:
                     dprev = torch.empty_like(inp)
-                    _lib.call("tnf_linear_bwd_data", dh.data_ptr(), dh.stride(0), ws[i].data_ptr(), dprev.data_ptr(),
-                              dprev.stride(0), inp.data_ptr(), inp.stride(0), m, n, k, stream,
-                              nbytes=4 * (m * (n + 2 * k) + n * k), flops=2 * m * n * k)
+                    _dgrad(dh, ws[i], dprev, inp, stream)
                     dh = dprev
                 elif ctx.x_needs_grad:
                     ld = (k + 3) // 4 * 4
                     buf = torch.empty(m, ld, device=dev)
-                    _lib.call("tnf_linear_bwd_data", dh.data_ptr(), dh.stride(0), ws[i].data_ptr(), buf.data_ptr(), ld,
-                              None, 0, m, n, k, stream, nbytes=4 * (m * (n + k) + n * k), flops=2 * m * n * k)
+                    _dgrad(dh, ws[i], buf[:, :k], None, stream)
                     gx = buf[:, :k].reshape(ctx.in_shape)
         grads = []
         for gw, gb in zip(gws, gbs):

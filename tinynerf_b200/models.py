@@ -9,7 +9,9 @@ Same module names, constructor arguments, `feature_dim` attributes and state_dic
 
 Feature grids keep their logical [1,C,...] parameter shape but are stored channels-last, which is
 what the fused gather kernels (tnf_kplanes_*, tnf_cobafa_*) read: one interpolation corner = one
-contiguous C*4-byte line.  The small MLPs are dense contractions and stay nn.Linear stacks here.
+contiguous C*4-byte line.  The MLPs keep the reference's nn.Linear module tree (state_dict keys) but are
+evaluated by the tcgen05 kernels (mlp_ops); there is no cuBLAS / grid_sample / eager path: a shape the kernels do
+not cover, or a non-CUDA tensor, raises.
 """
 from __future__ import annotations
 
@@ -20,12 +22,7 @@ from typing import Any, Callable, List, Tuple, cast
 import torch
 from torch.autograd import Function
 
-import os
-
 from . import _lib, mlp_ops
-
-# TNF_MLP=torch keeps the dense layers on cuBLAS fp32 (A/B switch; default: tcgen05 3xTF32 kernels on CUDA)
-_USE_TC_MLP = os.environ.get("TNF_MLP", "tcgen05") != "torch"
 
 
 class MLP(torch.nn.Module):
@@ -47,16 +44,21 @@ class MLP(torch.nn.Module):
         """The Linear layers in evaluation order (used by the fused MLP kernels)."""
         return [m for m in self.net.modules() if isinstance(m, torch.nn.Linear)]
 
-    def fused_ok(self, x: torch.Tensor) -> bool:
-        return _USE_TC_MLP and self._relu and mlp_ops.supported(self.linears(), x)
+    def require_supported(self, x: torch.Tensor) -> None:
+        """The stack runs on the tcgen05 kernels or not at all (no cuBLAS dispatch): raise for anything they do not cover."""
+        _lib.require_cuda(x, "MLP input")
+        if not self._relu:
+            raise NotImplementedError("MLP: only ReLU activations are implemented on the tensor-core kernels")
+        if not mlp_ops.supported(self.linears(), x):
+            dims = [self.linears()[0].in_features] + [l.out_features for l in self.linears()]
+            raise NotImplementedError(
+                f"MLP {dims}: the tcgen05 kernels need fp32 layers with biases, and a <= 4-wide output layer must follow a hidden "
+                "layer of at most 128 units; there is no cuBLAS fallback")
 
     def forward(self, x: torch.Tensor, head_act: int = 0):
-        """head_act != 0 asks for the decoder's output activation fused into the last layer (tensor-core path
-        only; see mlp_ops)."""
-        if self.fused_ok(x):
-            return mlp_ops.fused_mlp(x, self.linears(), head_act)
-        assert head_act == 0
-        return self.net(x)
+        """head_act != 0 asks for the decoder's output activation fused into the last layer (see mlp_ops)."""
+        self.require_supported(x)
+        return mlp_ops.fused_mlp(x, self.linears(), head_act)
 
 
 class PositionalEncoding(torch.nn.Module):
@@ -66,9 +68,19 @@ class PositionalEncoding(torch.nn.Module):
         self.register_buffer("freqs", 2 ** torch.arange(0, n_freqs) * torch.pi)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = x[..., None] * self.freqs
-        x = torch.cat([torch.sin(x), torch.cos(x)], -1)
-        return x.flatten(-2)
+        """[..., d] -> [..., d * 2 * n_freqs] (src/models.py:36-39); tnf_positional_encoding.  The frequencies are the
+        buffer's 2^k * pi (the kernel rebuilds them as fl32(pi) * 2^k, the same fp32 values)."""
+        _lib.load()
+        _lib.require_cuda(x, "x")
+        d, nf = x.shape[-1], int(self.freqs.numel())
+        flat = x.reshape(-1, d).to(torch.float32)
+        if flat.stride(-1) != 1:
+            flat = flat.contiguous()
+        out = torch.empty(flat.size(0), 2 * d * nf, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("tnf_positional_encoding", flat.data_ptr(), flat.stride(0) if flat.size(0) > 1 else d, d, nf, flat.size(0),
+                      out.data_ptr(), out.stride(0), _lib.stream_ptr(), nbytes=4 * flat.size(0) * d * (1 + 2 * nf))
+        return out.view(*x.shape[:-1], 2 * d * nf)
 
 
 class TruncatedExponential(Function):
@@ -110,9 +122,7 @@ class VanillaOpacityDecoder(torch.nn.Module):
         self.activation = lambda x: truncated_exp(x - 1.0)
 
     def forward(self, features: torch.Tensor) -> torch.Tensor:
-        if self.net.fused_ok(features):
-            return self.net(features, head_act=1)  # truncated_exp(x - 1.) fused into the layer epilogue
-        return self.activation(self.net(features))
+        return self.net(features, head_act=1)  # truncated_exp(x - 1.) fused into the layer epilogue
 
 
 class VanillaColorDecoder(torch.nn.Module):
@@ -124,20 +134,12 @@ class VanillaColorDecoder(torch.nn.Module):
         self.activation = torch.nn.Sigmoid()
 
     def forward(self, features: torch.Tensor, rays_d: torch.Tensor) -> torch.Tensor:
-        if (_USE_TC_MLP and features.is_cuda and features.dim() == 2 and features.dtype == torch.float32
-                and rays_d.dtype == torch.float32):
-            x = mlp_ops.color_input(features, rays_d, self.pe.freqs.numel())  # one kernel instead of sin/cos/cat/cat
-            if self.net.fused_ok(x):
-                return self.net(x, head_act=2)
-        parts = [self.pe(rays_d), rays_d, features]
-        width = sum(p.shape[-1] for p in parts)
-        if _USE_TC_MLP and features.is_cuda and width % 4 != 0:
-            # pad the row to a multiple of 4 floats so the kernels can read it in place with 128-bit loads
-            parts.append(features.new_zeros(*features.shape[:-1], 4 - width % 4))
-        x = torch.cat(parts, -1)[..., :width]
-        if self.net.fused_ok(x):
-            return self.net(x, head_act=2)  # sigmoid fused into the layer epilogue
-        return self.activation(self.net(x))
+        _lib.require_cuda(features, "features")
+        lead = features.shape[:-1]
+        f2 = features.reshape(-1, features.shape[-1]).float()
+        d2 = rays_d.reshape(-1, 3).float()
+        x = mlp_ops.color_input(f2, d2, self.pe.freqs.numel())  # [PE(d) | d | features] in one kernel (src/models.py:87)
+        return self.net(x, head_act=2).view(*lead, 3)  # sigmoid fused into the layer epilogue
 
 
 """K-Planes https://arxiv.org/abs/2301.10241"""
@@ -181,23 +183,93 @@ class KPlanesFeaturePlane(torch.nn.Module):
         self.plane = _channels_last_param((1, feature_dim, *resolution), init)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x: (..., 2).  Stand-alone single-plane lookup (src/models.py:105-113); the hot path is
-        KPlanesFeatureField.forward, which fuses all nine planes and never calls this."""
-        new_shape = [*x.size()[:-1], self.feature_dim]
-        output = torch.nn.functional.grid_sample(self.plane, x.view(1, -1, 1, 2), align_corners=True)
-        return output.squeeze().transpose(0, -1).contiguous().view(new_shape)
+        """x: (..., 2).  Stand-alone single-plane lookup (src/models.py:105-113) via tnf_plane_lookup_fwd/bwd; the hot
+        path is KPlanesFeatureField.forward, which fuses all nine planes and never calls this."""
+        _ensure_channels_last_(self.plane)
+        return _GridLookup.apply(x, self.plane)
 
     def loss_tv(self) -> torch.Tensor:
-        """mse(p[1:]-p[:-1]) along H + along W (src/models.py:115-118); one fused kernel for square CUDA planes."""
-        if self.plane.is_cuda and self.plane.shape[2] == self.plane.shape[3] and self.feature_dim % 4 == 0:
-            _ensure_channels_last_(self.plane)
-            return _KPlanesTV.apply(self.feature_dim, self.plane)
-        tv_x = torch.nn.functional.mse_loss(self.plane[:, :, 1:, :], self.plane[:, :, :-1, :])
-        tv_y = torch.nn.functional.mse_loss(self.plane[:, :, :, 1:], self.plane[:, :, :, :-1])
-        return tv_x + tv_y
+        """mse(p[1:]-p[:-1]) along H + along W (src/models.py:115-118); one fused kernel (square planes, C % 4 == 0)."""
+        _lib.require_cuda(self.plane, "plane")
+        if self.plane.shape[2] != self.plane.shape[3] or self.feature_dim % 4 != 0:
+            raise NotImplementedError("loss_tv: the TV kernel covers square planes with a multiple of 4 channels")
+        _ensure_channels_last_(self.plane)
+        return _KPlanesTV.apply(self.feature_dim, self.plane)
 
     def loss_l1(self) -> torch.Tensor:
-        return torch.mean(torch.abs(self.plane))
+        """mean |plane| (src/models.py:120-121); tnf_abs_mean_fwd/bwd."""
+        return _AbsMean.apply(self.plane)
+
+
+class _AbsMean(Function):
+    """mean |t| of a dense tensor of any stride order."""
+
+    @staticmethod
+    def forward(ctx: Any, t: torch.Tensor):  # type: ignore
+        _lib.load()
+        _lib.require_cuda(t, "tensor")
+        flat = torch.as_strided(t.detach(), (t.numel(),), (1,), t.storage_offset())   # dense memory in storage order
+        s = torch.empty(1, dtype=torch.float64, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.call("tnf_abs_mean_fwd", flat.data_ptr(), flat.numel(), s.data_ptr(), _lib.stream_ptr(), nbytes=4 * flat.numel())
+        ctx.save_for_backward(t)
+        return (s / t.numel()).float().reshape(())
+
+    @staticmethod
+    def backward(ctx: Any, g: torch.Tensor):  # type: ignore
+        (t,) = ctx.saved_tensors
+        grad = torch.empty_like(t, memory_format=torch.preserve_format)
+        gs = g.detach().float().reshape(1).contiguous()
+        with torch.cuda.device(t.device):
+            _lib.call("tnf_abs_mean_bwd", t.data_ptr(), t.numel(), gs.data_ptr(), grad.data_ptr(), _lib.stream_ptr(),
+                      nbytes=8 * t.numel())
+        return grad
+
+
+class _GridLookup(Function):
+    """grid_sample(param[1,C,*spatial], x, bilinear, zeros, align_corners=True) for one channels-last 2-D plane
+    (x [...,2]) or 3-D grid (x [...,3]) -> [..., C]; tnf_plane_lookup_* / tnf_grid3_lookup_*."""
+
+    @staticmethod
+    def forward(ctx: Any, x: torch.Tensor, param: torch.Tensor):  # type: ignore
+        _lib.load()
+        _lib.require_cuda(x, "x")
+        _lib.require_cuda(param, "grid")
+        stor = _channels_last_storage(param)
+        if stor is None or param.dtype != torch.float32:
+            raise RuntimeError("grid parameters must be fp32 and channels-last")
+        nd = param.dim() - 2
+        if x.shape[-1] != nd:
+            raise RuntimeError(f"expected coordinates with last dimension {nd}")
+        x2 = x.detach().reshape(-1, nd).float().contiguous()
+        n, ch = x2.size(0), int(param.shape[1])
+        out = torch.empty(n, ch, device=x.device)
+        with torch.cuda.device(x.device):
+            if nd == 2:
+                _lib.call("tnf_plane_lookup_fwd", stor.data_ptr(), int(param.shape[2]), int(param.shape[3]), ch, x2.data_ptr(), 2, n,
+                          out.data_ptr(), _lib.stream_ptr(), nbytes=n * (8 + 4 * ch))
+            else:
+                _lib.call("tnf_grid3_lookup_fwd", stor.data_ptr(), int(param.shape[2]), int(param.shape[3]), int(param.shape[4]), ch,
+                          x2.data_ptr(), 3, n, out.data_ptr(), _lib.stream_ptr(), nbytes=n * (12 + 4 * ch))
+        ctx.save_for_backward(x2, param)
+        return out.view(*x.shape[:-1], ch)
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore
+        x2, param = ctx.saved_tensors
+        nd = param.dim() - 2
+        n, ch = x2.size(0), int(param.shape[1])
+        g = grad_out.reshape(n, ch).float().contiguous()
+        grad = torch.zeros_like(param, memory_format=torch.preserve_format)
+        gstor = _channels_last_storage(grad)
+        with torch.cuda.device(x2.device):
+            if nd == 2:
+                _lib.call("tnf_plane_lookup_bwd", gstor.data_ptr(), int(param.shape[2]), int(param.shape[3]), ch, x2.data_ptr(), 2, n,
+                          g.data_ptr(), _lib.stream_ptr(), nbytes=n * (8 + 4 * ch))
+            else:
+                _lib.call("tnf_grid3_lookup_bwd", gstor.data_ptr(), int(param.shape[2]), int(param.shape[3]), int(param.shape[4]), ch,
+                          x2.data_ptr(), 3, n, g.data_ptr(), _lib.stream_ptr(), nbytes=n * (12 + 4 * ch))
+        return None, grad
 
 
 class _KPlanesTV(Function):
@@ -335,15 +407,10 @@ class KPlanesFeatureField(torch.nn.Module):
     def loss_tv(self) -> torch.Tensor:
         """mean over the nine planes of plane.loss_tv() (src/models.py:165-172); one kernel each way."""
         params = self._plane_params()
-        if params[0].is_cuda and self.plane_channels % 4 == 0:
-            return _KPlanesTV.apply(self.plane_channels, *params)
-        loss = 0.0
-        count = 0
-        for plane_scale in self.planes:
-            for plane in plane_scale:  # type: ignore
-                loss += plane.loss_tv()
-                count += 1
-        return cast(torch.Tensor, loss) / count
+        _lib.require_cuda(params[0], "planes")
+        if self.plane_channels % 4 != 0:
+            raise NotImplementedError("loss_tv: the TV kernel needs a multiple of 4 channels")
+        return _KPlanesTV.apply(self.plane_channels, *params)
 
     def loss_l1(self) -> torch.Tensor:
         loss = 0.0
@@ -385,6 +452,8 @@ class SawtoothEncoding(torch.nn.Module):
         self.f = f
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """2 * ((f x) mod 1) - 1 (src/models.py:213-214).  The fused Cobafa lookup (tnf_cobafa_fwd) applies this inside the
+        kernel; as a stand-alone module it is a parameter-free elementwise map kept in torch (three pointwise ops)."""
         return 2.0 * ((self.f * x) % 1.0) - 1.0  # also normalize to [-1, 1]
 
 
@@ -396,11 +465,10 @@ class CobafaGrid(torch.nn.Module):
         self.feature_dim = feature_dim
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x: (..., 3).  Stand-alone lookup (src/models.py:228-238); the hot path is the fused
-        CobafaFeatureField.forward."""
-        new_shape = [*x.size()[:-1], self.feature_dim]
-        output = torch.nn.functional.grid_sample(self.grid, x.view(1, -1, 1, 1, 3), align_corners=True)
-        return output.squeeze().transpose(0, -1).contiguous().view(new_shape)
+        """x: (..., 3).  Stand-alone lookup (src/models.py:228-238) via tnf_grid3_lookup_fwd/bwd; the hot path is the
+        fused CobafaFeatureField.forward."""
+        _ensure_channels_last_(self.grid)
+        return _GridLookup.apply(x, self.grid)
 
 
 class _CobafaLookup(Function):
