@@ -23,3 +23,13 @@ for path in sys.argv[1:]:
             extra = f" tensor {v['tensor_frac_issued']}" if "tensor_frac_issued" in v else ""
             print(f"  {k:24s} {v['launches']:4d} x {v['avg_us']:8.1f} us = {ms:7.3f} ms/step  hbm frac {v['frac']}{extra}")
         print(f"  sum of kernels {tot:.3f} ms/step")
+        for name, w in (d.get("workloads") or {}).items():
+            if "error" in w:
+                print(f"  workload {name}: ERROR {w['error']}")
+                continue
+            rf = w.get("roofline") or {}
+            print(f"  workload {name}: {w['value']/1e6:.2f} M {w['unit']}  {w.get('ms_per_step', w.get('ms_per_image'))} ms | dominant {rf.get('kernel')} "
+                  f"{rf.get('bound')} frac {rf.get('frac')} | updates {w.get('occupancy_update')}")
+        for key in ("gpu_reference", "parity", "occupancy_update"):
+            if d.get(key):
+                print(f"  {key}", d[key])

@@ -186,85 +186,30 @@ def test_tv_fwd_bwd_equals_separate_passes():
     assert float((sums_b / denom).sum() / n) == pytest.approx(float(ref), rel=1e-6)
 
 
-def _relu_kink(layers, x64, margin):
-    near = torch.zeros(x64.size(0), dtype=torch.bool, device=x64.device)
-    h = x64
-    for w, b in layers[:-1]:
-        pre = torch.nn.functional.linear(h, w.double(), b.double())
-        near |= (pre.abs() < margin).any(1)
-        h = pre.relu()
-    return near
-
-
 def test_fused_step_vs_reference_restatement():
     """the path bench.py times (FusedKPlanesStep.forward_backward: tnf_heads_fwd, tnf_heads_bwd_data,
     the TMA weight-gradient kernels, split colour input, tnf_composite_loss_fwd_bwd, TV written into the gradients)
     DIRECTLY against the reference restatement (oracle/ref_port.py on the GPU: stock grid_sample / Linear / index_add_ +
-    the UNMODIFIED reference weights kernel) on a ~2^18-sample batch -- no autograd path of ours in between.
+    the UNMODIFIED reference weights kernel) on a ~2^18-sample batch -- no autograd path of ours in between.  The
+    measurement lives in oracle/parity.py (bench.py prints the same numbers as its `parity` object).
     Bar: rendered colours and loss 1e-5 relative; every parameter gradient rel-L2 <= 2e-5 and worst entry <= 5e-5 of the
     tensor's max (same bar as test_gpu_models.test_kplanes_renderer_vs_torch_on_gpu).  Rays holding a sample whose hidden
     pre-activation lies within 3e-6 of a ReLU kink (decided differently by two correct fp32 evaluations) are removed
     from the batch of BOTH pipelines."""
-    from oracle import ref_port as rp
-    from tinynerf_b200 import core
-    from tinynerf_b200.fused import FusedKPlanesStep
-    torch.manual_seed(0)
-    field = models.KPlanesFeatureField(32)
-    sd = models.VanillaOpacityDecoder(96)
-    cd = models.VanillaColorDecoder(8, 96, 64, 3)
-    with torch.no_grad():
-        sd.net.net[-1].bias += 3.0
-    renderer = core.NerfRenderer(field, sd, cd, bg_color=torch.ones(3)).to(DEV)
-    aabb = torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]], device=DEV)
-    marcher = core.RayMarcherAABB(aabb, 256, 0.1)
-    og = core.OccupancyGrid(128, marcher.step_size, 0.01, synthetic.DECAY).to(DEV)
-    og.grid.copy_(synthetic.analytic_grid(128, seed=1))
-    og.mean = og.grid.mean().item()
-    prov = core.RayProvider(og, core.ContractionAABB(aabb), marcher)
-    o, d = synthetic.blender_rays(9600, seed=2)
-    torch.manual_seed(5)
-    packed, info = prov(o.to(DEV), d.to(DEV), training=True)
-    s_layers = [(l.weight, l.bias) for l in sd.net.linears()]
-    c_layers = [(l.weight, l.bias) for l in cd.net.linears()]
-    planes = [[p.plane for p in scale] for scale in field.planes]
-    # drop the rays with a sample at a ReLU kink (evaluated in float64 on the reference's features), re-pack the rest
-    with torch.no_grad():
-        feats = rp.kplanes_features(planes, packed[:, :3])
-        xcol = torch.cat([rp.positional_encoding(packed[:, 3:6], 8), packed[:, 3:6], feats], -1).double()
-        kink = _relu_kink(s_layers, feats.double(), 3e-6) | _relu_kink(c_layers, xcol, 3e-6)
-        ray_id = torch.repeat_interleave(torch.arange(info.size(0), device=DEV), info[:, 1].long())
-        bad_ray = torch.zeros(info.size(0), device=DEV).index_add_(0, ray_id, kink.float()) > 0
-        assert bad_ray.float().mean() < 0.25
-        keep_s = ~bad_ray[ray_id]
-        packed2 = packed[keep_s].contiguous()
-        cnt = info[~bad_ray, 1]
-        info2 = torch.stack([torch.cumsum(cnt, 0, dtype=torch.int32) - cnt, cnt], -1).contiguous()
-    n, r = packed2.size(0), info2.size(0)
-    assert n > 200_000 and int(info2[-1].sum()) == n
-    target = torch.rand(r, 3, device=DEV)
-    tv_alpha, gscale = 1e-4, 2.0 ** 10
-    fs = FusedKPlanesStep(renderer, tv_alpha=tv_alpha, grad_scale=gscale)
-    res = fs.forward_backward(packed2, info2, target)
-    mine = {k: p.grad.clone() for k, p in renderer.named_parameters()}
-    out, loss = res["rendered"].clone(), float(res["loss"])
-    for p in renderer.parameters():
-        p.grad = None
-    want = rp.render(lambda x: rp.kplanes_features(planes, x), lambda f: rp.sigma_head(s_layers, f),
-                     lambda f, dd: rp.rgb_head(c_layers, 8, f, dd), packed2, info2, torch.ones(3))
-    ref_loss = torch.nn.functional.mse_loss(want, target) + tv_alpha * rp.kplanes_tv(planes)
-    (ref_loss * gscale).backward()
-    err = (out.double() - want.double()).abs()
-    assert bool((err <= 1e-5 * want.double().abs() + 2e-6).all()), f"rendered: worst {err.max().item():.3e}"
-    assert loss == pytest.approx(float(ref_loss), rel=1e-5)
-    bad, worst_all = {}, {}
-    for k, p in renderer.named_parameters():
-        ref, got = p.grad.double(), mine[k].double()
-        assert got.shape == ref.shape
-        scale = ref.abs().max().clamp_min(1e-12)
-        rel_l2 = ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
-        worst = ((got - ref).abs().max() / scale).item()
-        worst_all[k] = (rel_l2, worst)
-        if rel_l2 > 2e-5 or worst > 5e-5:
-            bad[k] = (rel_l2, worst)
-    print("fused-vs-reference worst (rel_l2, max/scale):", max(v[0] for v in worst_all.values()), max(v[1] for v in worst_all.values()))
+    from oracle import parity
+    r = parity.fused_step_parity()
+    print("fused-vs-reference:", {k: v for k, v in r.items() if k != "per_parameter"})
+    assert r["n_samples"] > 200_000 and r["kink_rays_excluded_frac"] < 0.25
+    assert r["rendered_excess_over_1e-5rel+2e-6"] <= 0.0, r["rendered_max_abs_err"]
+    assert r["loss_rel_err"] <= 1e-5
+    bad = {k: v for k, v in r["per_parameter"].items() if v[0] > 2e-5 or v[1] > 5e-5}
     assert not bad, bad
+
+
+def test_parity_object_of_the_bench_line():
+    """The march and weights entries of bench.py's `parity` object: bit-exact flags true, errors inside the stated bars."""
+    from oracle import parity
+    m = parity.march_parity()
+    assert m["packing_info_bit_exact"] and m["packed_rows_bit_exact"] and m["n_samples"] > 50_000
+    w = parity.weights_parity()
+    assert w["termination_mask_bit_exact"] and w["weights_max_rel_err"] <= 1e-5 and w["grad_sigmas_max_err_over_bound"] <= 1.0

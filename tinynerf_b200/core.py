@@ -449,6 +449,37 @@ class RayProvider:
         return packed, info
 
     @torch.no_grad()
+    def pack_range(self, h, r0: int, r1: int, sample_offset: int, n: int, packed_buf: torch.Tensor | None = None,
+                   steps_buf: torch.Tensor | None = None):
+        """Packed samples of the rays [r0, r1) of a count() handle taken WITHOUT jitter (training=False): `sample_offset`
+        is the packed index of ray r0's first sample in the handle's numbering, `n` the packed-sample total of the range
+        (both known on the host from the handle's info).  Returns (packed [n,7], info [r1-r0,2] with 0-based starts): what
+        RayProvider()(rays_o[r0:r1], rays_d[r0:r1], training=False) returns, without re-marching the lattice and without a
+        host sync.  `packed_buf` [>=n,7] / `steps_buf` [>=n] are optional fixed-capacity destinations (the render loop of
+        src/run.py:34-42 reuses one pair for every chunk of an image)."""
+        if h["noise"] is not None:
+            raise RuntimeError("pack_range needs a handle counted with training=False (jitter is indexed by ray)")
+        dev = h["rays_o"].device
+        R, words = r1 - r0, h["words"]
+        with torch.cuda.device(dev):
+            if packed_buf is None:
+                cap = (n + 16383) & ~16383
+                packed_buf, steps_buf = torch.empty(cap, 7, device=dev), torch.empty(cap, device=dev)
+            if packed_buf.size(0) < n or steps_buf.numel() < n:
+                raise RuntimeError("pack_range: destination buffers are smaller than the packed-sample count")
+            packed, steps = packed_buf[:n], steps_buf[:n]
+            info = h["info"][r0:r1].clone()
+            if n > 0:
+                _lib.call("tnf_march_pack", C.byref(h["p"]), h["rays_o"][r0:].data_ptr(), h["rays_d"][r0:].data_ptr(), R,
+                          h["info_offset"] + sample_offset, h["mask_bits"][r0 * words:].data_ptr(), info.data_ptr(),
+                          packed.data_ptr(), steps.data_ptr(), None, n, _lib.stream_ptr(),
+                          nbytes=24 * R + 8 * R + 4 * R * words + 32 * n)
+            info[:, 0] -= h["info_offset"] + sample_offset
+        tag_steps(packed, steps)
+        tag_partition(info)
+        return packed, info
+
+    @torch.no_grad()
     def __call__(self, rays_o: torch.Tensor, rays_d: torch.Tensor, training: bool,
                  noise: torch.Tensor | None = None, info_offset: int = 0):
         """-> (packed_samples [N,7], packing_info [R,2] int32), same contents and order as the

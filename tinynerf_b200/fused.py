@@ -190,6 +190,53 @@ class FusedKPlanesStep:
                  nbytes=4 * (n * (F + 1) + l0.out_features * F), flops=2 * n * l0.out_features * (F + 1))
         return ws["sigma"][:n].view(n, 1)
 
+    # ---- forward only: the render half of the path (src/run.py:34-42, NerfRenderer.forward in eval mode) -----------
+    @torch.no_grad()
+    def render(self, packed: torch.Tensor, info: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """rendered [R,3] of a packed batch: gather -> both heads -> weights -> composite, five launches, nothing saved for
+        a backward pass (tnf_heads_fwd is called without activation outputs).  `out` [R,3] is an optional destination."""
+        _lib.require_cuda(packed, "packed_samples")
+        n, r = packed.size(0), info.size(0)
+        if not (self.fused_heads and self.split_xc):
+            raise RuntimeError("FusedKPlanesStep.render needs the fused heads kernel (reference head shapes)")
+        if not (packed.is_contiguous() and info.is_contiguous() and info.dtype == torch.int32):
+            raise RuntimeError("packed samples / packing info must be contiguous ([N,7] fp32, [R,2] int32)")
+        if out is None:
+            out = torch.empty(r, 3, device=self.dev)
+        if n == 0 or r == 0:
+            raise ValueError("no samples remaining")
+        steps = tagged_steps(packed)
+        sstride = 1
+        if steps is None:
+            steps, sstride = packed[:, 6], 7
+        flags = _cuda.TRUSTED_PARTITION if is_trusted_partition(info) else 0
+        status = None if flags else torch.empty(1, dtype=torch.int32, device=self.dev)
+        self._reserve_render(n)
+        ws, call, st = self._rws, _lib.call, _lib.stream_ptr()
+        P = lambda t: t.data_ptr()
+        F, xw, xld = self.feat, self.xc_width, self.xc_ld
+        with torch.cuda.device(self.dev):
+            call("tnf_kplanes_fwd", self._plane_ptrs, self._res_scales, self.n_scales, self.channels, P(packed), 7, n,
+                 P(ws["feats"]), st, nbytes=n * (12 + 4 * F) + self._plane_bytes)
+            call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, 0, P(ws["xc"]), xld, n, st,
+                 nbytes=n * (12 + 4 * xld))
+            call("tnf_heads_fwd", P(ws["feats"]), F, F, P(ws["xc"]), xld, xw, self.pe_width, self._cw, self._cb, self._sw,
+                 self._sb, None, None, P(ws["rgb"]), P(ws["sigma"]), n, P(self._heads_ws), st,
+                 nbytes=4 * n * (F + xld + 4), flops=2 * n * (64 * (F + 1) + 64 * xw + 3 * 64 * 64 + 3 * 64))
+            call("tnf_weights_fwd", P(ws["sigma"]), P(steps), sstride, P(info), float(self.threshold), P(ws["w"]), n, r,
+                 flags, _lib.ptr(status), st, nbytes=12 * n + 8 * r, extra_kernels=0 if flags else 3)
+            call("tnf_composite_fwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(out), None, st,
+                 nbytes=16 * n + 20 * r)
+        return out
+
+    def _reserve_render(self, n: int) -> None:
+        """Forward-only workspaces (feature rows, [PE(d)|d] rows, sigma, rgb, weights): 4*(96+52+5) B per sample."""
+        if n > getattr(self, "_rcap", 0):
+            cap = (n + 65535) & ~65535
+            e = lambda *s: torch.empty(*s, device=self.dev)
+            self._rws = {"feats": e(cap, self.feat), "xc": e(cap, self.xc_ld), "sigma": e(cap), "rgb": e(cap, 3), "w": e(cap)}
+            self._rcap = cap
+
     # ---- the iteration -----------------------------------------------------------------------------
     @torch.no_grad()
     def forward_backward(self, packed: torch.Tensor, info: torch.Tensor, target: torch.Tensor,

@@ -584,12 +584,68 @@ class Trainer:
 
     # ---- render half of the path (src/run.py:15-50, without image IO) ---------------------------
     @torch.no_grad()
-    def render(self, rays_o: torch.Tensor, rays_d: torch.Tensor, batch_size: int = 2048) -> torch.Tensor:
+    def render(self, rays_o: torch.Tensor, rays_d: torch.Tensor, batch_size: int = 2048,
+               max_samples: int = 1 << 20, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Rendered colours [R,3] (on the device) of the rays of an image, row for row what the reference's loop returns
+        (src/run.py:34-44: chunks of `batch_size` rays through ray_provider(training=False) + renderer, concatenated).
+        A ray's colour does not depend on which rays share its chunk, so the chunking is free to change:
+          * the sample lattice of ALL rays is marched in one launch (keep-mask bitfield + packing info on the device);
+          * ONE host sync per image reads the packed-sample total at every `batch_size`-th ray; the host then groups those
+            blocks into chunks of at most `max_samples` packed samples (a fixed-capacity buffer pair, reused by every chunk);
+          * each chunk is packed straight from the bitfield (no second march, no sync) and rendered forward-only:
+            K-Planes through FusedKPlanesStep.render (5 launches, no activations saved), other fields through the modules.
+        The reference syncs twice per chunk and copies every chunk to the host; here the image stays on the device until
+        the caller reads it."""
         self.renderer.eval()
-        out = []
-        for k in range(0, rays_o.size(0), batch_size):
-            o = rays_o[k:k + batch_size].to(self.device)
-            d = rays_d[k:k + batch_size].to(self.device)
-            samples, info = self.ray_provider(o, d, training=False)
-            out.append(self.renderer(samples, info))
-        return torch.cat(out, 0)
+        dev = self.device
+        o = rays_o.reshape(-1, 3).to(dev, torch.float32, non_blocking=True).contiguous()
+        d = rays_d.reshape(-1, 3).to(dev, torch.float32, non_blocking=True).contiguous()
+        R = o.size(0)
+        if out is None:
+            out = torch.empty(R, 3, device=dev)
+        if R == 0:
+            return out
+        h = self.ray_provider.count(o, d, training=False)
+        info = h["info"]
+        idx = list(range(batch_size - 1, R, batch_size))
+        if not idx or idx[-1] != R - 1:
+            idx.append(R - 1)
+        last = torch.tensor(idx, device=dev)
+        ends = (info[last, 0].long() + info[last, 1].long()).tolist()      # the one host sync of the image
+        ray_ends = [min(R, (i + 1) * batch_size) for i in range(len(ends))]
+        cap = max(max_samples, max(e - s for s, e in zip([0] + ends[:-1], ends)))
+        cap = (cap + 16383) & ~16383
+        if getattr(self, "_render_cap", 0) < cap:
+            self._render_buf = (torch.empty(cap, 7, device=dev), torch.empty(cap, device=dev))
+            self._render_cap = cap
+        pbuf, sbuf = self._render_buf
+        bg = self.renderer.bg_color
+        r0 = s0 = 0
+        i = 0
+        while i < len(ends):
+            j = i   # extend the chunk block by block while it fits the buffer
+            while j + 1 < len(ends) and ends[j + 1] - s0 <= max_samples:
+                j += 1
+            r1, s1 = ray_ends[j], ends[j]
+            n = s1 - s0
+            if n == 0:   # every sample masked: the reference composites nothing, the rays show the background (src/core.py:251-265)
+                out[r0:r1] = 0.0 if bg is None else bg.to(dev).reshape(1, 3)
+            else:
+                packed, ic = self.ray_provider.pack_range(h, r0, r1, s0, n, pbuf, sbuf)
+                if self._fused is not None and self._fused.fused_heads and self._fused.split_xc:
+                    self._fused.render(packed, ic, out[r0:r1])
+                else:
+                    out[r0:r1] = self.renderer(packed, ic)
+            r0, s0, i = r1, s1, j + 1
+        return out
+
+
+@torch.no_grad()
+def infer(trainer: "Trainer", poses, batch_size: int = 2048):
+    """The reference's `infer` (src/run.py:15-50) without the PNG writing: `poses` yields (rays_o [H,W,3], rays_d [H,W,3])
+    per image; returns the list of rendered [H,W,3] images on the host."""
+    rendered = []
+    for rays_o, rays_d in poses:
+        img = trainer.render(rays_o, rays_d, batch_size=batch_size)
+        rendered.append(img.view(*rays_o.shape[:-1], 3).cpu())
+    return rendered

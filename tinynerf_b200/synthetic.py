@@ -83,3 +83,47 @@ def analytic_density(x: torch.Tensor) -> torch.Tensor:
     ball = (w ** 2).sum(-1) < 0.25
     torus = ((torch.sqrt(w[..., 0] ** 2 + w[..., 1] ** 2) - 0.9) ** 2 + w[..., 2] ** 2) < 0.0625
     return torch.where(ball | torus, torch.full_like(w[..., 0], 40.0), torch.zeros_like(w[..., 0]))
+
+
+def _look_at(pos: torch.Tensor) -> torch.Tensor:
+    """Camera-to-world rotations [n,3,3] (columns: right, up, -forward) of cameras at `pos` looking at the origin, z up."""
+    fwd = -pos / pos.norm(dim=-1, keepdim=True)
+    up = torch.tensor([0.0, 0.0, 1.0]).expand_as(fwd)
+    right = torch.linalg.cross(fwd, up)
+    right = right / right.norm(dim=-1, keepdim=True)
+    true_up = torch.linalg.cross(right, fwd)
+    return torch.stack([right, true_up, -fwd], -1)
+
+
+def camera_rays(width: int, height: int, focal: float, pos, device="cpu") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Every pixel of ONE pinhole camera at `pos` looking at the origin, in the reference's ray convention and pixel order
+    (src/data.py:49-73: meshgrid "xy", pixel centre +0.5, (fx, -fy), z = -1, d = grid @ R.T normalised).
+    -> (rays_o, rays_d) [height*width, 3], row-major over (row, column) like PoseDataset's [h, w, 3] images."""
+    pos = torch.as_tensor(pos, dtype=torch.float32)
+    rot = _look_at(pos[None])[0]
+    gx, gy = torch.meshgrid(torch.arange(width, dtype=torch.float32), torch.arange(height, dtype=torch.float32), indexing="xy")
+    cam = torch.stack([(gx - width / 2 + 0.5) / focal, (gy - height / 2 + 0.5) / (-focal), -torch.ones_like(gx)], -1).view(-1, 3)
+    d = cam @ rot.T
+    d = d / d.norm(dim=-1, keepdim=True)
+    return pos.expand_as(d).contiguous().to(device), d.contiguous().to(device)
+
+
+def colmap_rays(n_rays: int, seed: int, n_cameras: int = 200, width: int = 1000, height: int = 750,
+                focal: float = 800.0, device="cpu") -> Tuple[torch.Tensor, torch.Tensor, float]:
+    """Config 4: random pixels of `n_cameras` inward-facing pinhole cameras on a jittered ring
+    (radius 1.5 +- 0.2, height +- 0.3).  -> (rays_o, rays_d, scene_scale) with scene_scale = the largest per-axis variance
+    of the camera positions, as NerfData.scene_scale computes it (src/data.py:75-76)."""
+    g = torch.Generator().manual_seed(seed)
+    ang = torch.rand(n_cameras, generator=g) * 2 * math.pi
+    rad = 1.5 + (torch.rand(n_cameras, generator=g) * 2 - 1) * 0.2
+    hgt = (torch.rand(n_cameras, generator=g) * 2 - 1) * 0.3
+    cams = torch.stack([rad * torch.cos(ang), rad * torch.sin(ang), hgt], -1)
+    rots = _look_at(cams)
+    scene_scale = float(torch.max(torch.var(cams, 0)))
+    which = torch.randint(0, n_cameras, (n_rays,), generator=g)
+    px = torch.floor(torch.rand(n_rays, generator=g) * width)
+    py = torch.floor(torch.rand(n_rays, generator=g) * height)
+    cam = torch.stack([(px - width / 2 + 0.5) / focal, (py - height / 2 + 0.5) / (-focal), -torch.ones_like(px)], -1)
+    d = torch.einsum("nij,nj->ni", rots[which], cam)
+    d = d / d.norm(dim=-1, keepdim=True)
+    return cams[which].float().contiguous().to(device), d.float().contiguous().to(device), scene_scale
