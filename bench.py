@@ -475,7 +475,7 @@ def train_workload(ctx: Ctx, name: str, steps: int, warmup: int, e2e_arm: bool, 
     n_store = 80_000 if spec["rays"] == "dummy" else N_STORE
     o, d, rgbs, scene_scale = make_scene(spec["rays"], n_store, SEED)
     cfg = TrainConfig(method=spec["method"], scene_type=spec["scene"], batch_size=BATCH, n_samples=spec["n_samples"],
-                      scene_scale=scene_scale, seed=SEED)
+                      scene_scale=scene_scale, seed=SEED, dp_mode=os.environ.get("TNF_DP_MODE", "peer"))
     if os.environ.get("TNF_OVERLAP_ADAM") == "1":   # diagnostics: A/B of the planes' Adam beside the weight-gradient kernels
         cfg.overlap_plane_adam = True
     analytic = synthetic.analytic_grid(128, seed=SEED + 2).to(dev) if spec["pin_grid"] else None
@@ -820,7 +820,9 @@ def main():
                        "packed_samples_per_step_per_gpu": main_res["packed_samples_per_step_per_gpu"],
                        "grid": "128^3 analytic ball+torus, pinned after every update" if spec["pin_grid"] else "128^3, starts all-ones, evolves (updates + decay)",
                        "l2": "inputs change every step (fresh rays; parameters + gradients + Adam state stream through L2 > 126 MB)",
-                       "parallelism": f"ray-sharded dp{world}", "host_wait": "blocking" if ctx.blocking_sync else "spin",
+                       "parallelism": f"ray-sharded dp{world}" + ("" if world == 1 else ", parameter update: " + (
+                           "one reduce+Adam+broadcast kernel over NVLink peer memory" if os.environ.get("TNF_DP_MODE", "peer") == "peer"
+                           else "NCCL all-reduce + replicated Adam")), "host_wait": "blocking" if ctx.blocking_sync else "spin",
                        "settle_steps": main_res["settle_steps"],
                        "e2e_loss_readback": "every step, async D2H into a pinned ring, consumed one step late"},
             "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "host_ms_per_step": main_res["host_ms_per_step"],

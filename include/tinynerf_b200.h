@@ -370,6 +370,38 @@ int tnf_composite_loss_fwd_bwd(const float* weights, const float* rgbs, const in
                                const double* extra_terms /*optional*/, const double* extra_coef /*optional*/, int32_t n_extra,
                                void* stream);
 
+/* ---- (e) + 8f rank 1: the data-parallel parameter path over NVLink peer memory ----------------------------------------
+ * New work (the reference trains on one device, src/run.py:98); the update it distributes is optimizer.step() of
+ * torch.optim.Adam as configured at src/run.py:186, applied at src/run.py:258-261 to the gradients of the union batch.
+ *
+ * Every rank holds a flat fp32 gradient buffer and a flat fp32 parameter buffer at the SAME offsets in symmetric memory:
+ * peer_grads[r] / peer_params[r] / peer_flags[r] are this process's mappings of rank r's buffers ([host] arrays of `world`
+ * device pointers, entry `rank` being the local buffer); mc_grad / mc_param are the NVSwitch multicast addresses of the two
+ * buffers, or both NULL (then the kernel loads from / stores to the peers one by one).  Called by every rank in the same
+ * step on its own slice [lo, hi) (multiples of 4 elements; slices of different ranks must not overlap), it reduces the
+ * slice's gradients over the ranks, applies tnf_adam_step's update to the local parameters / exp_avg / exp_avg_sq (flat,
+ * indexed like the parameters; only the owning rank's slice is ever touched) and writes the new parameters to every rank --
+ * reduce-scatter + sharded Adam + all-gather in one pass, bracketed by two rank barriers (flags: [n_ctas][TNF_DP_MAX_RANKS]
+ * uint32 words per rank, n_ctas <= 4 x SM count, zero before the first call; each call consumes the epochs `epoch` and `epoch + 1`, so successive
+ * calls on one flag pad pass epoch = 1, 3, 5, ...).  n_ctas identical on every rank.  *error (local device
+ * int32) becomes non-zero if a barrier gave up after ~4 s (a peer died): the result is then undefined. */
+#define TNF_DP_MAX_RANKS   16
+#define TNF_DP_COUNT_SLOTS 4
+int tnf_dp_reduce_adam_bcast(const float* const* peer_grads, float* const* peer_params, const float* mc_grad,
+                             float* mc_param, float* exp_avg, float* exp_avg_sq, int64_t lo, int64_t hi,
+                             uint32_t* const* peer_flags, int32_t n_ctas, int32_t rank, int32_t world, uint32_t epoch,
+                             int32_t* error, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                             void* stream);
+/* Ray count of the union batch (the MSE normaliser of src/run.py:252 when ranks hold different ray counts).  peer_slots[r]:
+ * this process's mapping of rank r's slot table, uint64 [TNF_DP_COUNT_SLOTS][TNF_DP_MAX_RANKS] in symmetric memory, zero
+ * before the first call.  publish: stores {step, count} into entry [slot][rank] of every rank's table (step != 0; use
+ * slot = step % TNF_DP_COUNT_SLOTS).  sum: waits until the local table holds every rank's word of `step`, then writes the
+ * total to *out (float, exact for counts < 2^24); *error = 2 on a ~4 s timeout. */
+int tnf_dp_publish_count(uint64_t* const* peer_slots, int32_t world, int32_t rank, int32_t slot, uint32_t step, float count,
+                         void* stream);
+int tnf_dp_sum_counts(const uint64_t* slots, int32_t world, int32_t slot, uint32_t step, float* out, int32_t* error,
+                      void* stream);
+
 /* ---- host helper: lazily shuffled ray order (DataLoader(shuffle=True), src/run.py:116-122) --------------------------------
  * HOST pointers.  perm: n entries, initially 0..n-1 (any permutation); out receives `count` ray indices.  pos is a global
  * position counter (a multiple of world; advance it by count*world), *fresh_from the first position never drawn so far

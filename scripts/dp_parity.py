@@ -1,0 +1,175 @@
+"""G ranks == 1 rank on the union batch (VERDICT r1 weak #2 / next #2c), on real GPUs:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29611 \
+        scripts/dp_parity.py [--mode peer|nccl] > profiles/r02_dp_parity_nG.json
+
+Every rank builds the data-parallel Trainer (K-Planes, AABB, BASELINE config 2 shapes) and draws its own dynamic batch.  The
+batches are gathered, and on every rank a SINGLE-GPU trainer (world = 1, same initial parameters) runs the same iterations
+on the union batch.  Checked, per iteration, for `--steps` iterations (so the optimiser state and the barrier epochs of the
+peer-memory path are exercised beyond the first call):
+  * loss: sum over ranks of the per-rank loss shares == the single-GPU loss (1e-5 relative);
+  * every parameter gradient, summed over the ranks, == the single-GPU gradient (rel-L2 2e-5, worst entry 5e-5 of max:
+    float atomics order differs, same bar as tests/test_gpu_fused.py);
+  * every parameter after the data-parallel update == the single-GPU parameter after tnf_adam_step (FusedAdam) on the
+    SAME reduced gradient (the ranks' sum; so this isolates reduce + Adam + broadcast from the float-atomics noise of the
+    gradients themselves), on the entries whose gradient is not a rounding residue (|g| > 1e-4 max|g|: Adam moves an entry
+    by ~lr*sign(g), ill-conditioned where g ~ 0) -- 1e-5 relative + 1e-6; and all ranks hold bit-identical parameters;
+  * the occupancy grid after the slice-sharded update + all-gather == the grid after the single-GPU update, bit for bit.
+Exit code 0 and "ok": true only if everything holds on every rank.
+"""
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from tinynerf_b200 import synthetic  # noqa: E402
+from tinynerf_b200.core import tag_partition, tag_steps, tagged_steps  # noqa: E402
+from tinynerf_b200.run import RayStore, TrainConfig, Trainer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--steps", type=int, default=3)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    seed = 4321
+    o, d = synthetic.blender_rays(1 << 18, seed=seed)
+    rgbs = torch.rand(o.size(0), 3, generator=torch.Generator().manual_seed(seed + 1))
+    analytic = synthetic.analytic_grid(128, seed=seed + 2).to(dev)
+
+    def make(world_, rank_, mode):
+        torch.manual_seed(seed)
+        cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=1024, n_samples=256, seed=seed, prefetch=False, dp_mode=mode)
+        tr = Trainer(cfg, RayStore(o, d, rgbs, dev, seed=seed, rank=rank_, world=world_), dev, rank=rank_, world=world_)
+        return tr
+
+    tr = make(world, rank, args.mode)          # data-parallel trainer (parameters broadcast from rank 0)
+    ref = make(1, 0, "nccl")                   # single-GPU trainer on the union batch
+    ref.renderer.load_state_dict(tr.renderer.state_dict())
+    report = {"world": world, "mode": args.mode, "multicast": bool(tr._fused.peer.multicast) if tr._fused.peer is not None else None,
+              "steps": [], "ok": True}
+
+    def fail(msg):
+        report["ok"] = False
+        report.setdefault("failures", []).append(f"rank {rank}: {msg}")
+
+    # ---- occupancy update: slice-sharded + all-gather vs the full update on one GPU (grid starts all-ones) ----
+    tr.update_occupancy()
+    ref.update_occupancy()
+    same_grid = bool(torch.equal(tr.occupancy_grid.grid, ref.occupancy_grid.grid))
+    report["occupancy_grid_bit_exact_after_sharded_update"] = same_grid
+    report["occupancy_mean"] = [float(tr.occupancy_grid.mean), float(ref.occupancy_grid.mean)]
+    if not same_grid:
+        fail("occupancy grid differs after the sharded update")
+    for t_ in (tr, ref):   # train on the analytic scene state from here on
+        t_.occupancy_grid.grid.copy_(analytic)
+        t_.occupancy_grid.mean = analytic.mean().item()
+        t_.train_step = 1  # no further update
+
+    for it in range(args.steps):
+        packed, rgb, info = tr.next_batch()
+        # gather the per-rank batches: the union batch in rank order
+        steps = tagged_steps(packed)
+        mine = (packed.cpu(), rgb.cpu(), info.cpu(), steps.cpu())
+        allb = [None] * world
+        dist.all_gather_object(allb, mine)
+        up = torch.cat([b[0] for b in allb]).to(dev)
+        ur = torch.cat([b[1] for b in allb]).to(dev)
+        us = torch.cat([b[3] for b in allb]).to(dev)
+        infos, base = [], 0
+        for b in allb:
+            i2 = b[2].clone()
+            i2[:, 0] += base
+            base += b[0].size(0)
+            infos.append(i2)
+        ui = torch.cat(infos).to(dev)
+        tag_steps(up, us)
+        tag_partition(ui)
+        # single GPU on the union batch: gradients, then the optimiser step
+        out_ref = ref._fused.forward_backward(up, ui, ur)
+        g_ref = {k: p.grad.clone() for k, p in ref.renderer.named_parameters()}
+        # data-parallel iteration (gradient reduction + update inside)
+        res = tr._step_fused(packed, rgb, info)
+        torch.cuda.synchronize()
+        loss = res["loss"].detach().clone().double()
+        dist.all_reduce(loss)
+        row = {"iteration": it, "n_samples_union": int(up.size(0)), "n_rays_union": int(ui.size(0)),
+               "loss_dp": float(loss), "loss_single": float(out_ref["loss"])}
+        row["loss_rel_err"] = abs(row["loss_dp"] - row["loss_single"]) / abs(row["loss_single"])
+        if row["loss_rel_err"] > 1e-5:
+            fail(f"it {it}: loss {row['loss_dp']} vs {row['loss_single']}")
+        worst_g, worst_l2, worst_p, ident = 0.0, 0.0, 0.0, True
+        ref_params = dict(ref.renderer.named_parameters())
+        g_sum = {}
+        for k, p in tr.renderer.named_parameters():
+            if args.mode == "peer":
+                g = p.grad.detach().clone()
+                dist.all_reduce(g.view(-1) if g.is_contiguous() else torch.as_strided(g, (g.numel(),), (1,), g.storage_offset()))
+            else:
+                g = p.grad.detach()        # already all-reduced
+            g_sum[k] = g
+            gr = g_ref[k].double()
+            scale = gr.abs().max().clamp_min(1e-12)
+            l2 = float(((g.double() - gr).norm() / gr.norm().clamp_min(1e-30)))
+            mx = float((g.double() - gr).abs().max() / scale)
+            worst_g, worst_l2 = max(worst_g, mx), max(worst_l2, l2)
+            if l2 > 2e-5 or mx > 5e-5:
+                fail(f"it {it}: gradient of {k}: rel-L2 {l2:.3e}, worst/max {mx:.3e}")
+        # the single-GPU optimiser on the same reduced gradient
+        for k, p in ref_params.items():
+            p.grad.copy_(g_sum[k])
+        ref.optimizer.step()
+        ref.scheduler.step()
+        ref.train_step += 1
+        for k, p in tr.renderer.named_parameters():
+            pr = ref_params[k].detach()
+            gr = g_sum[k].double()
+            live = gr.abs() > 1e-4 * gr.abs().max().clamp_min(1e-12)
+            perr = ((p.detach() - pr).abs() - (1e-6 + 1e-5 * pr.abs()))[live]
+            if perr.numel():
+                worst_p = max(worst_p, float(perr.max()))
+                if float(perr.max()) > 0:
+                    fail(f"it {it}: parameter {k} after the update: excess {float(perr.max()):.3e} on {int((perr > 0).sum())} entries")
+            # every rank holds the same bits
+            flat = p.detach().reshape(-1) if p.is_contiguous() else torch.as_strided(p.detach(), (p.numel(),), (1,), p.storage_offset())
+            lo, hi = flat.clone(), flat.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if not torch.equal(lo, hi):
+                ident = False
+                fail(f"it {it}: parameter {k} differs between ranks")
+        with torch.no_grad():   # re-base the single-GPU replica on the data-parallel parameters (drops the rounding residue)
+            for k, p in tr.renderer.named_parameters():
+                ref_params[k].copy_(p)
+        row.update({"grad_worst_err_over_tensor_max": worst_g, "grad_worst_rel_l2": worst_l2,
+                    "param_excess_over_1e-5rel+1e-6": worst_p, "params_bit_identical_across_ranks": ident})
+        report["steps"].append(row)
+
+    if tr._fused.peer is not None:
+        torch.cuda.synchronize()
+        report["peer_error_word"] = int(tr._fused.peer.error.item())
+        if report["peer_error_word"] != 0:
+            fail("a rank barrier timed out")
+    flag = torch.tensor([0 if report["ok"] else 1], device=dev)
+    dist.all_reduce(flag)
+    report["ok_all_ranks"] = int(flag) == 0
+    fails = [None] * world
+    dist.all_gather_object(fails, report.get("failures", []))
+    if rank == 0:
+        report["failures"] = [f for fl in fails for f in fl][:40]
+        print(json.dumps(report))
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -151,3 +151,16 @@ def test_trainer_close_restores_gc_state():
     gc.freeze(); gc.disable()
     t.close()
     assert gc.isenabled() and gc.get_freeze_count() == 0 and not t._gc_frozen
+
+
+def test_dp_slices_partition_the_parameter_space():
+    """dp.slice_of: the ranks' shares of a flat range are contiguous, 4-element aligned (the kernel moves float4), disjoint
+    and cover the range -- for ranges that do not divide evenly too."""
+    from tinynerf_b200.dp import slice_of
+    for lo, hi, world in [(0, 33_030_144, 8), (33_030_144, 33_058_592, 8), (0, 100, 3), (8, 12, 8), (0, 4, 2), (16, 16, 4)]:
+        cur = lo
+        for r in range(world):
+            a, b = slice_of(lo, hi, r, world)
+            assert a == cur and a <= b <= hi and (a - lo) % 4 == 0
+            cur = b
+        assert cur == hi

@@ -111,6 +111,11 @@ _SIGNATURES = {
     "tnf_adam_step_grid": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_float, C.c_float,
                                      C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int32, C.c_void_p]),
+    "tnf_dp_reduce_adam_bcast": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, c_f32p, c_f32p,
+                                           C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
+                                           C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
+    "tnf_dp_publish_count": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_float, C.c_void_p]),
+    "tnf_dp_sum_counts": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, c_f32p, C.c_void_p, C.c_void_p]),
     "tnf_wide_linear_fwd": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_void_p]),
     "tnf_wide_linear_bwd_data": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64,
@@ -190,7 +195,7 @@ def profile_stop():
     return out
 
 
-def call(name: str, *args, nbytes: int = 0, extra_kernels: int = 0, flops: int = 0):
+def call(name: str, *args, nbytes: int = 0, extra_kernels: int = 0, flops: int = 0, label: str | None = None):
     """Invoke a C-ABI entry point on the current stream, raise on error, count its kernel launches and,
     when profiling is on, bracket it with CUDA events on the launching stream."""
     global launch_count
@@ -202,7 +207,7 @@ def call(name: str, *args, nbytes: int = 0, extra_kernels: int = 0, flops: int =
         s.record()
         rc = fn(*args)
         e.record()
-        _prof.append((name, s, e, nbytes, flops))
+        _prof.append((label or name, s, e, nbytes, flops))
     check(rc, name)
     launch_count += KERNELS_PER_CALL.get(name, 1) + extra_kernels
 

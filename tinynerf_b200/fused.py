@@ -47,7 +47,9 @@ class FusedKPlanesStep:
         return all(p.is_cuda and p.dtype == torch.float32 for p in renderer.parameters())
 
     def __init__(self, renderer: NerfRenderer, tv_alpha: float = 0.0, grad_scale: float = 1.0, world: int = 1,
-                 threshold: float = 1e-4):
+                 threshold: float = 1e-4, rank: int = 0, peer_update: bool = False):
+        """peer_update (world > 1): parameters and gradients live in symmetric memory (dp.PeerMemory) and the optimiser
+        update is the one-kernel reduce + Adam + broadcast over NVLink peer memory, issued from forward_backward."""
         if not self.supported(renderer):
             raise RuntimeError("FusedKPlanesStep needs KPlanesFeatureField + VanillaOpacityDecoder + VanillaColorDecoder on CUDA")
         _lib.load()
@@ -75,8 +77,24 @@ class FusedKPlanesStep:
         for p in params:
             offs.append(tot)
             tot += _pad4(p.numel())
-        self.flat_grad = torch.zeros(tot, device=self.dev)
-        self.grads = [torch.as_strided(self.flat_grad, p.shape, p.stride(), off) for p, off in zip(params, offs)]
+        self.peer = None
+        if peer_update and world > 1:
+            from .dp import PeerMemory
+            self.peer = PeerMemory(tot, self.dev, rank, world)
+            self.flat_grad = self.peer.grad[:tot]
+            # the parameters move into the symmetric buffer: every nn.Parameter becomes a view of it (same shape, strides
+            # and values; state_dict() is unchanged), at the offset its gradient has in the gradient buffer
+            with torch.no_grad():
+                for p, off in zip(params, offs):
+                    view = torch.as_strided(self.peer.param, p.shape, p.stride(), self.peer.param.storage_offset() + off)
+                    view.copy_(p.data)
+                    p.data = view
+            self.peer_overlap = os.environ.get("TNF_DP_OVERLAP", "1") != "0"   # planes' update on a side stream (0: in line)
+            self._peer_stream = torch.cuda.Stream(device=self.dev) if self.peer_overlap else None
+        else:
+            self.flat_grad = torch.zeros(tot, device=self.dev)
+        self.grads = [torch.as_strided(self.flat_grad, p.shape, p.stride(), self.flat_grad.storage_offset() + off)
+                      for p, off in zip(params, offs)]
         self._plane_grad_end = offs[len(self.planes)]   # flat_grad[:end] = plane gradients, [end:] = the heads' 
         self._scale_off = [offs[3 * sc] for sc in range(self.n_scales)] + [self._plane_grad_end]   # planes are stored scale by scale
         self._scale_bytes = [4 * (self._scale_off[sc + 1] - self._scale_off[sc]) for sc in range(self.n_scales)]
@@ -241,10 +259,14 @@ class FusedKPlanesStep:
     @torch.no_grad()
     def forward_backward(self, packed: torch.Tensor, info: torch.Tensor, target: torch.Tensor,
                          n_rays_global: torch.Tensor | None = None, reduce: bool = False, n_rays_work=None,
-                         after_plane_grads=None) -> Dict[str, torch.Tensor]:
+                         after_plane_grads=None, peer_step: dict | None = None) -> Dict[str, torch.Tensor]:
         """packed [N,7], info [R,2] int32 (a RayProvider partition), target [R,3].  Sets p.grad of every parameter to
         d(grad_scale * (MSE_union + tv_alpha/world * loss_tv))/dp and returns {"loss", "rendered"}.  With `reduce` the
-        gradients are all-reduced over the ranks (sum) before returning, overlapped with the tail of backward."""
+        gradients are all-reduced over the ranks (sum) before returning, overlapped with the tail of backward.
+        peer_step = {"step", "lr", "betas", "eps", "weight_decay"} (peer_update mode): the union batch's ray count comes
+        from the peers' slot tables and the optimiser update of iteration `step` (1-based) happens in here -- the planes'
+        right after their gradients are complete, the heads' after the weight gradients -- so on return the parameters
+        already hold the new values on every rank and p.grad holds this rank's un-reduced gradients."""
         _lib.require_cuda(packed, "packed_samples")
         n, r = packed.size(0), info.size(0)
         if n == 0 or r == 0:
@@ -325,6 +347,8 @@ class FusedKPlanesStep:
             # ---- composite + loss + their gradients in one pass over the rays (src/core.py:256-265, src/run.py:252,259) ----
             if n_rays_work is not None:
                 n_rays_work.wait()   # the union batch's ray count (async all-reduce started before the forward)
+            if peer_step is not None:
+                n_rays_global = self.peer.sum_counts(peer_step["step"])   # published by every rank at the start of its step
             tv_in_loss = self.fused_composite and self.tv_alpha != 0.0   # the kernel adds tv_alpha/world * loss_tv to the loss it reports
             if self.fused_composite:
                 call("tnf_composite_loss_fwd_bwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(target), float(r),
@@ -379,6 +403,32 @@ class FusedKPlanesStep:
                          P(packed), 7, n, P(dfeat), sc, sc + 1, st, nbytes=(n * (12 + 4 * F)) // self.n_scales + 2 * self._scale_bytes[sc])
                     works.append(dist.all_reduce(self.flat_grad[self._scale_off[sc]:self._scale_off[sc + 1]], async_op=True))
                 work = works.pop()
+            elif peer_step is not None:
+                # Data-parallel update over NVLink peer memory: gradient sum over the ranks + Adam on this rank's share + new
+                # planes to every rank, one kernel per range (99.9 % of the parameter bytes; nothing below depends on it).  The
+                # kernel is NVLink-bound (~280 us for the 132 MB of planes whatever the rank count), so it runs on a side stream:
+                # the finest scale (76 % of the bytes) is scattered first and its update starts while the coarser scales are
+                # still being scattered, then runs on under the heads' weight gradients.
+                ps = peer_step
+                upd = lambda lo, hi, st_: self.peer.reduce_adam_bcast(lo, hi, 0, ps["step"], ps["lr"], ps["betas"], ps["eps"],
+                                                                      ps["weight_decay"], st_)
+                kp_bwd = lambda a, b: call("tnf_kplanes_bwd_scales", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales,
+                                           self.channels, P(packed), 7, n, P(dfeat), a, b, st, label="tnf_kplanes_bwd",
+                                           nbytes=((n * (12 + 4 * F)) * (b - a)) // self.n_scales + 2 * sum(self._scale_bytes[a:b]))
+                if self.peer_overlap:
+                    main, comm = torch.cuda.current_stream(self.dev), self._peer_stream
+                    fine = self.n_scales - 1
+                    for a, b in ((fine, self.n_scales), (0, fine)):
+                        if a == b:
+                            continue
+                        kp_bwd(a, b)
+                        comm.wait_event(main.record_event())
+                        with torch.cuda.stream(comm):
+                            upd(self._scale_off[a], self._scale_off[b], comm.cuda_stream)
+                    planes_done = comm.record_event()
+                else:
+                    kp_bwd(0, self.n_scales)
+                    upd(0, self._plane_grad_end, st)
             else:
                 call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
                      P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
@@ -399,6 +449,12 @@ class FusedKPlanesStep:
             else:
                 wgrad(P(dh[0]), hc_w, P(ws["xc"]), xld, cl[0])
             wgrad(P(ws["dhs"]), hs_w, P(ws["feats"]), F, sl[0])
+            if peer_step is not None:
+                # the heads' 28 K parameters the same way, now that their gradients are complete
+                self.peer.reduce_adam_bcast(self._plane_grad_end, self.peer.n, 1, peer_step["step"], peer_step["lr"],
+                                            peer_step["betas"], peer_step["eps"], peer_step["weight_decay"], st)
+                if self.peer_overlap:
+                    torch.cuda.current_stream(self.dev).wait_event(planes_done)
             if work is not None:
                 _lib.load().tnf_set_sm_budget(0)
                 dist.all_reduce(self.flat_grad[self._plane_grad_end:])

@@ -209,6 +209,10 @@ class TrainConfig:
                                         # PROCESS-WIDE side effect while the trainer lives: gc.freeze() + gc.disable();
                                         # Trainer.close() / `with Trainer(...)` restores the collector
     occupancy_jitter: str = "device"    # "cpu" = the reference's generator stream
+    dp_mode: str = "peer"               # world > 1, fused K-Planes step: "peer" = parameters/gradients in symmetric memory, ONE
+                                        # kernel per step reduces the gradients over NVLink, applies Adam to this rank's share
+                                        # and writes the new parameters to every rank (dp.PeerMemory, csrc/dp.cu);
+                                        # "nccl" = the round-1 baseline: all-reduce of the flat gradient + replicated Adam
     seed: int = 0
 
 
@@ -264,8 +268,18 @@ class Trainer:
         if cfg.fused_step and cfg.method == "kplanes" and self.device.type == "cuda" and self.l1_reg_alpha == 0.0:
             from .fused import FusedKPlanesStep
             if FusedKPlanesStep.supported(self.renderer):
+                if cfg.dp_mode not in ("peer", "nccl"):
+                    raise ValueError(f"unknown dp_mode {cfg.dp_mode!r}")
                 self._fused = FusedKPlanesStep(self.renderer, tv_alpha=self.tv_reg_alpha, grad_scale=cfg.grad_scale,
-                                               world=world)
+                                               world=world, rank=rank, peer_update=(world > 1 and cfg.dp_mode == "peer"))
+                if self._fused.peer is not None:
+                    # optimizer.state keeps torch.optim.Adam's keys (checkpoints): exp_avg / exp_avg_sq are views of the flat
+                    # state the peer kernel updates; only this rank's share is live until PeerMemory.gather_optimizer_state()
+                    peer, off = self._fused.peer, 0
+                    for p in self._fused.params:
+                        view = lambda flat: torch.as_strided(flat, p.shape, p.stride(), off)
+                        self.optimizer.state[p] = {"step": 0, "exp_avg": view(peer.exp_avg), "exp_avg_sq": view(peer.exp_avg_sq)}
+                        off += (p.numel() + 3) // 4 * 4
         self._chunks_guess = 0.0
         if world > 1 and self.device.type == "cuda":
             self._warm_collectives()
@@ -288,15 +302,17 @@ class Trainer:
     def _warm_collectives(self) -> None:
         """Run every collective of an iteration once at its real size (gradient all-reduce, ray-count all-reduce,
         occupancy all-gather) so NCCL's lazy channel/buffer set-up happens at construction, not inside a step."""
+        peer = self._fused is not None and self._fused.peer is not None
         grads = self._fused.flat_grad if self._fused is not None else torch.zeros(
             sum(p.numel() for p in self.renderer.parameters()), device=self.device)
         for _ in range(2):
-            dist.all_reduce(grads)
+            if not peer:
+                dist.all_reduce(grads)
             global_ray_count(1, self.device, self.world)
             g = self.occupancy_grid.grid
             z0, z1 = shard_slices(g.size(0), self.rank, self.world)
             dist.all_gather_into_tensor(torch.empty_like(g).view(-1), g[z0:z1].reshape(-1).clone())
-        if self._fused is not None:
+        if self._fused is not None and not peer:
             grads.zero_()
         torch.cuda.synchronize(self.device)
 
@@ -549,6 +565,8 @@ class Trainer:
 
     def _step_fused(self, packed, rgbs, info) -> Dict[str, float]:
         """Same iteration through fused.FusedKPlanesStep: identical kernels and order, no autograd / glue ops."""
+        if self._fused.peer is not None:
+            return self._step_fused_peer(packed, rgbs, info)
         n_glob = work = None
         if self.world > 1:  # ray count of the union batch: reduced while the forward runs
             n_glob = torch.tensor(float(info.size(0)), device=self.device)
@@ -573,6 +591,30 @@ class Trainer:
             torch.cuda.current_stream(self.device).wait_event(self._planes_done)
         else:
             self.optimizer.step()
+        self.scheduler.step()
+        self.train_step += 1
+        self._publish_loss(out["loss"])
+        self._mark_enqueued()
+        if self._side is not None:
+            self._prefetch()
+        self.last = {"loss": out["loss"], "n_samples": packed.size(0), "n_rays": info.size(0)}
+        return self.last
+
+    def _step_fused_peer(self, packed, rgbs, info) -> Dict[str, float]:
+        """Data-parallel iteration with the update over NVLink peer memory: no NCCL call in the step.  The ray count goes to
+        the peers' slot tables before the forward; forward_backward consumes the union count, and issues the planes' and the
+        heads' reduce + Adam + broadcast kernels (src/run.py:258-261's optimizer.step(), distributed)."""
+        peer = self._fused.peer
+        t = self._peer_adam_step = getattr(self, "_peer_adam_step", 0) + 1   # Adam's own 1-based step count
+        with torch.cuda.device(self.device):
+            peer.publish_count(t, info.size(0))
+        g = self.optimizer.param_groups[0]
+        out = self._fused.forward_backward(packed, info, rgbs, peer_step={
+            "step": t, "lr": g["lr"], "betas": g["betas"], "eps": g["eps"], "weight_decay": g["weight_decay"]})
+        for st in self.optimizer.state.values():
+            st["step"] = t
+        if t % self.occupancy_grid_updates == 0:
+            peer.check()
         self.scheduler.step()
         self.train_step += 1
         self._publish_loss(out["loss"])
