@@ -517,6 +517,7 @@ def train_workload(ctx: Ctx, name: str, steps: int, warmup: int, e2e_arm: bool, 
 
     def timed(tr, k, read_loss, profile):
         ctx.barrier()
+        seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
         l0, u0 = _lib.launch_count, upd["count"]
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if profile:
@@ -535,7 +536,8 @@ def train_workload(ctx: Ctx, name: str, steps: int, warmup: int, e2e_arm: bool, 
         raw = [b - a for a, b in zip([h0] + per[:-1], per)]
         dd = sorted(raw)
         host_dist.append({"p50": round(dd[len(dd) // 2] * 1e3, 3), "p90": round(dd[int(len(dd) * 0.9)] * 1e3, 3),
-                          "max": round(dd[-1] * 1e3, 3), "argmax": raw.index(dd[-1])})
+                          "max": round(dd[-1] * 1e3, 3), "argmax": raw.index(dd[-1]),
+                          "cudaMalloc_calls_in_window": int(torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0)})
         ctx.barrier()
         recs = _lib.profile_stop() if profile else None
         ms = s.elapsed_time(e)

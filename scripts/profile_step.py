@@ -11,7 +11,7 @@ from tinynerf_b200 import synthetic
 from tinynerf_b200.run import RayStore, TrainConfig, Trainer
 
 dev = torch.device("cuda", 0)
-o, d, rgbs = bench.make_scene(1 << 18, bench.SEED)
+o, d, rgbs, _ = bench.make_scene("blender", 1 << 18, bench.SEED)
 torch.manual_seed(bench.SEED)
 cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=bench.BATCH, n_samples=bench.N_SAMPLES, seed=bench.SEED, prefetch=False)
 tr = Trainer(cfg, RayStore(o, d, rgbs, dev, seed=bench.SEED), dev)

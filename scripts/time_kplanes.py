@@ -84,33 +84,8 @@ for g_ in grads: g_.zero_()
 _lib.call("tnf_kplanes_bwd_ex", ptrs, gptrs, res, 3, 32, packs[0].data_ptr(), 7, n, go.data_ptr(), 3, st); torch.cuda.synchronize()
 print("  TMA scatter max rel err vs red.v4:", max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(grads, ref)))
 
-# ---- processing order: does spatial locality help? (samples re-ordered on the host side of the call; diagnostic) ----
-def morton3(ix, iy, iz, bits):
-    key = torch.zeros_like(ix)
-    for b in range(bits):
-        key |= ((ix >> b) & 1) << (3 * b) | ((iy >> b) & 1) << (3 * b + 1) | ((iz >> b) & 1) << (3 * b + 2)
-    return key
-def reorder(p, kind):
-    x = p[:, :3]
-    if kind == "morton512":
-        i = ((x + 1) * 0.5 * 511).floor().long().clamp(0, 511)
-        key = morton3(i[:, 0], i[:, 1], i[:, 2], 9)
-    elif kind == "morton128":
-        i = ((x + 1) * 0.5 * 127).floor().long().clamp(0, 127)
-        key = morton3(i[:, 0], i[:, 1], i[:, 2], 7)
-    elif kind == "xy_tile16":   # 2-D tiles of 16x16 texels of the 512 plane (x,y), z free
-        i = ((x + 1) * 0.5 * 511).floor().long().clamp(0, 511)
-        key = (i[:, 1] // 16) * 32 + i[:, 0] // 16
-    return p[key.argsort()].contiguous()
-for kind in ("morton512", "morton128", "xy_tile16"):
-    sp = [reorder(p[:n], kind) for p in packs]
-    fs = lambda i: _lib.call("tnf_kplanes_fwd", ptrs, res, 3, 32, sp[i].data_ptr(), 7, n, out.data_ptr(), st)
-    bs = lambda i: _lib.call("tnf_kplanes_bwd", ptrs, gptrs, res, 3, 32, sp[i].data_ptr(), 7, n, go.data_ptr(), st)
-    print(f"  order {kind}: fwd {timeit(fs):.1f} us | bwd {timeit(bs):.1f} us")
-    for s_, r in enumerate((128, 256, 512)):
-        p1 = (C.c_void_p * 3)(*[t.data_ptr() for t in stor[3 * s_:3 * s_ + 3]])
-        g1 = (C.c_void_p * 3)(*[t.data_ptr() for t in grads[3 * s_:3 * s_ + 3]])
-        r1 = (C.c_int32 * 1)(r)
-        f1 = lambda i: _lib.call("tnf_kplanes_fwd", p1, r1, 1, 32, sp[i].data_ptr(), 7, n, out1.data_ptr(), st)
-        b1 = lambda i: _lib.call("tnf_kplanes_bwd", p1, g1, r1, 1, 32, sp[i].data_ptr(), 7, n, go1.data_ptr(), st)
-        print(f"    scale {r}: fwd {timeit(f1):.1f} us | bwd {timeit(b1):.1f} us")
+# ---- occupancy variants (tnf_set_variant 2: blocks per SM the kernel is compiled for) ----
+for k in (0, 1, 5, 6, 8):   # 0 = the default builds (forward 6, backward 4), 1 = uncapped
+    _lib.load().tnf_set_variant(2, k)
+    print(f"  occupancy variant {k}: fwd {timeit(fwd):.1f} us | bwd {timeit(bwd):.1f} us")
+_lib.load().tnf_set_variant(2, 0)

@@ -118,4 +118,7 @@ def test_trainer_render_matches_renderer_call():
     tr.renderer.eval()
     with torch.no_grad():
         s, i = tr.ray_provider(o[:384].to(DEV), d[:384].to(DEV), training=False)
-        assert torch.equal(img[:384], tr.renderer(s, i))
+        # Trainer.render evaluates the heads with the fused forward kernel, the module path layer by layer: same
+        # arithmetic, different fp32 summation order inside the MLP
+        want = tr.renderer(s, i)
+        assert bool(((img[:384] - want).abs() <= 1e-5 * want.abs() + 2e-6).all())

@@ -44,6 +44,7 @@ int sm_count();  // cached per device
 // Diagnostic kernel variants, selected per calling thread with tnf_set_variant (never from the environment).
 constexpr int kVariantWgradSS = 0;   // 1: both-operands-in-shared-memory weight-gradient kernel
 constexpr int kVariantTvTexel = 1;   // 1: one-thread-per-texel TV kernel
+constexpr int kVariantKplanesOcc = 2; // K-Planes lookup kernels built for another occupancy (value = blocks per SM, 1 = uncapped; 0 = default)
 constexpr int kVariantCount = 4;
 int variant(int which);
 

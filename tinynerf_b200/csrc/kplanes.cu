@@ -87,8 +87,13 @@ __device__ __forceinline__ float4 mul4(float4 a, float4 b) {
 
 // Planes of a scale use the coordinate pairs of itertools.combinations(range(3), 2) (src/models.py:145):
 // plane 0 = (x,y), plane 1 = (x,z), plane 2 = (y,z); first coordinate -> W axis, second -> H axis.
-template <bool BWD>
-__global__ void __launch_bounds__(256) kplanes_kernel(const KPArgs A) {
+// MINB: minimum resident blocks per SM asked of the compiler (register cap 65536 / (256 MINB)); 0 = no cap (44 registers
+// forward, 66 backward = 5 / 3 blocks per SM).  Measured at the bench shape (scripts/time_kplanes.py, round 2): forward
+// 110.6 us uncapped / 99.0 us at 6 blocks (40 registers) / 100.4 us at 8; backward 276.5 us uncapped / 260.1 us at 4 blocks
+// (64 registers) / 279 at 5 / 292 at 6 / 381 at 8 (spills).  Defaults: forward 6, backward 4; tnf_set_variant(2, k) selects
+// another build for diagnostics (k = blocks per SM, 1 = uncapped).
+template <bool BWD, int MINB>
+__global__ void __launch_bounds__(256, MINB) kplanes_kernel(const KPArgs A) {
   const int C = A.channels;
   const int lps = C >> 2;  // lanes per sample (power of two, <= 8)
   const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -294,7 +299,13 @@ extern "C" int tnf_kplanes_fwd(const float* const* planes, const int32_t* res, i
   TNF_REQUIRE(out && (reinterpret_cast<uintptr_t>(out) & 15u) == 0, "out null/misaligned");
   A.out = out;
   const long long threads = n * (channels / 4);
-  kplanes_kernel<false><<<dim3((unsigned)ceil_div(threads, 256), (unsigned)n_scales), 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  const dim3 grid((unsigned)ceil_div(threads, 256), (unsigned)n_scales);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (variant(kVariantKplanesOcc)) {
+    case 1: kplanes_kernel<false, 0><<<grid, 256, 0, st>>>(A); break;
+    case 8: kplanes_kernel<false, 8><<<grid, 256, 0, st>>>(A); break;
+    default: kplanes_kernel<false, 6><<<grid, 256, 0, st>>>(A);
+  }
   TNF_LAUNCH_CHECK("kplanes_fwd_kernel");
   return TNF_OK;
 }
@@ -319,7 +330,14 @@ extern "C" int tnf_kplanes_bwd_scales(const float* const* planes, float* const* 
   A.grad_out = grad_out;
   A.scale0 = scale_begin;
   const long long threads = n * (channels / 4);
-  kplanes_kernel<true><<<dim3((unsigned)ceil_div(threads, 256), (unsigned)(scale_end - scale_begin)), 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  const dim3 grid((unsigned)ceil_div(threads, 256), (unsigned)(scale_end - scale_begin));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (variant(kVariantKplanesOcc)) {
+    case 1: kplanes_kernel<true, 0><<<grid, 256, 0, st>>>(A); break;
+    case 5: kplanes_kernel<true, 5><<<grid, 256, 0, st>>>(A); break;
+    case 6: kplanes_kernel<true, 6><<<grid, 256, 0, st>>>(A); break;
+    default: kplanes_kernel<true, 4><<<grid, 256, 0, st>>>(A);
+  }
   TNF_LAUNCH_CHECK("kplanes_bwd_kernel");
   return TNF_OK;
 }

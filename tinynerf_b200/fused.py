@@ -89,8 +89,11 @@ class FusedKPlanesStep:
                     view = torch.as_strided(self.peer.param, p.shape, p.stride(), self.peer.param.storage_offset() + off)
                     view.copy_(p.data)
                     p.data = view
-            self.peer_overlap = os.environ.get("TNF_DP_OVERLAP", "1") != "0"   # planes' update on a side stream (0: in line)
+            self.peer_overlap = os.environ.get("TNF_DP_OVERLAP", "1") != "0"   # the updates on a side stream (0: in line)
             self._peer_stream = torch.cuda.Stream(device=self.dev) if self.peer_overlap else None
+            # events of the side stream: the planes' / the heads' update of the latest iteration has landed on every rank.
+            # The NEXT reader of the parameters on the main stream waits for them (wait_updates), not the iteration's end.
+            self._planes_done = self._heads_done = None
         else:
             self.flat_grad = torch.zeros(tot, device=self.dev)
         self.grads = [torch.as_strided(self.flat_grad, p.shape, p.stride(), self.flat_grad.storage_offset() + off)
@@ -158,6 +161,19 @@ class FusedKPlanesStep:
         for p, g in zip(self.params, self.grads):
             p.grad = g
 
+    def wait_updates(self, planes: bool = True, heads: bool = True) -> None:
+        """Peer-update mode: make the current stream wait for the side stream's parameter updates of the latest iteration
+        (no-op otherwise).  Every reader of the parameters calls it: the next iteration, density(), render()."""
+        if self.peer is None:
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        if planes and self._planes_done is not None:
+            cur.wait_event(self._planes_done)
+            self._planes_done = None
+        if heads and self._heads_done is not None:
+            cur.wait_event(self._heads_done)
+            self._heads_done = None
+
     # ---- workspace ---------------------------------------------------------------------------------
     def _reserve(self, n: int, r: int) -> None:
         if n > self._cap_n:
@@ -198,6 +214,7 @@ class FusedKPlanesStep:
         if n == 0:
             return torch.empty(0, 1, device=self.dev)
         self._reserve(n, 1)
+        self.wait_updates()
         ws, call, st = self._ws, _lib.call, _lib.stream_ptr()
         F, l0, l1 = self.feat, self.sig_lin[0], self.sig_lin[1]
         with torch.cuda.device(self.dev):
@@ -230,6 +247,7 @@ class FusedKPlanesStep:
         flags = _cuda.TRUSTED_PARTITION if is_trusted_partition(info) else 0
         status = None if flags else torch.empty(1, dtype=torch.int32, device=self.dev)
         self._reserve_render(n)
+        self.wait_updates()
         ws, call, st = self._rws, _lib.call, _lib.stream_ptr()
         P = lambda t: t.data_ptr()
         F, xw, xld = self.feat, self.xc_width, self.xc_ld
@@ -312,15 +330,23 @@ class FusedKPlanesStep:
             # gradient buffer: the TV pass WRITES the plane gradients (value + gradient of the regulariser from one read of
             # the planes; loss += tv_alpha * loss_tv, src/run.py:254-255) -- it depends on nothing in this iteration, so it
             # doubles as the zero-fill of 99.8 % of the buffer; the data term is scattered on top of it in backward
+            defer_heads = peer_step is not None and self.peer_overlap and self.tv_alpha != 0.0
+            self.wait_updates(planes=True, heads=not defer_heads)   # the planes are read first (TV pass, gather); the heads later
             if self.tv_alpha != 0.0:
                 call("tnf_tv_fwd_bwd", self._plane_ptrs, self._grad_ptrs, self._res_planes, len(self.planes), self.channels,
                      self._tv_w, P(self._tv_gscale), 0, P(self._tv_sums), st, nbytes=2 * self._plane_bytes)
-                self.flat_grad[self._plane_grad_end:].zero_()
+                if not defer_heads:
+                    self.flat_grad[self._plane_grad_end:].zero_()
             else:
                 self.flat_grad.zero_()
             # ---- forward (src/core.py:225-267) ----
             call("tnf_kplanes_fwd", self._plane_ptrs, self._res_scales, self.n_scales, self.channels, P(packed), 7, n,
                  P(ws["feats"]), st, nbytes=n * (12 + 4 * F) + self._plane_bytes)
+            if defer_heads:
+                # the heads' update of the previous iteration (side stream) must have landed before their weights are read,
+                # and every rank must have consumed the heads' gradients before they are zeroed for this iteration
+                self.wait_updates(planes=False, heads=True)
+                self.flat_grad[self._plane_grad_end:].zero_()
             if self.fused_heads:
                 xc_feat = 0 if self.split_xc else F   # feature columns copied into the colour-input row
                 call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, xc_feat, P(ws["xc"]), xld, n, st,
@@ -451,10 +477,18 @@ class FusedKPlanesStep:
             wgrad(P(ws["dhs"]), hs_w, P(ws["feats"]), F, sl[0])
             if peer_step is not None:
                 # the heads' 28 K parameters the same way, now that their gradients are complete
-                self.peer.reduce_adam_bcast(self._plane_grad_end, self.peer.n, 1, peer_step["step"], peer_step["lr"],
-                                            peer_step["betas"], peer_step["eps"], peer_step["weight_decay"], st)
+                hupd = lambda st_: self.peer.reduce_adam_bcast(self._plane_grad_end, self.peer.n, 1, peer_step["step"], peer_step["lr"],
+                                                               peer_step["betas"], peer_step["eps"], peer_step["weight_decay"], st_)
                 if self.peer_overlap:
-                    torch.cuda.current_stream(self.dev).wait_event(planes_done)
+                    # on the side stream too: the main stream goes on to the next iteration's TV pass and gather, which read
+                    # only the planes; the heads' kernel (two rank barriers: ~40-90 us of latency and skew) leaves its path
+                    comm.wait_event(main.record_event())
+                    with torch.cuda.stream(comm):
+                        hupd(comm.cuda_stream)
+                        self._heads_done = comm.record_event()
+                    self._planes_done = planes_done
+                else:
+                    hupd(st)
             if work is not None:
                 _lib.load().tnf_set_sm_budget(0)
                 dist.all_reduce(self.flat_grad[self._plane_grad_end:])

@@ -281,6 +281,8 @@ class Trainer:
                         self.optimizer.state[p] = {"step": 0, "exp_avg": view(peer.exp_avg), "exp_avg_sq": view(peer.exp_avg_sq)}
                         off += (p.numel() + 3) // 4 * 4
         self._chunks_guess = 0.0
+        if self.device.type == "cuda":
+            self._prewarm_allocator()
         if world > 1 and self.device.type == "cuda":
             self._warm_collectives()
         # The coming batches are marched on a HIGH-PRIORITY stream: their short kernels are then not queued behind the main
@@ -298,6 +300,17 @@ class Trainer:
         self._loss_ring = None          # pinned host ring the loss of every iteration is copied into (read_loss)
         self._grid_event = None         # recorded after the latest occupancy update: batches marched later must see it
         self.last: Dict[str, float] = {}
+
+    def _prewarm_allocator(self, blocks: int = 24, mb: int = 64) -> None:
+        """Leave ~1.5 GB of free blocks in PyTorch's caching allocator.  The per-batch buffers (rays, jitter, bitfield,
+        packed rows) change size with the dynamic batch; a size the cache has not seen makes the allocator call cudaMalloc
+        in the middle of a step, which waits for all queued GPU work and -- in a process with peer access enabled (NCCL,
+        symmetric memory) -- maps the new memory into every peer: stalls of 5-60 ms were measured inside 64-step windows.
+        Free 64 MB blocks are split on demand instead."""
+        if os.environ.get("TNF_PREWARM_ALLOCATOR", "1") == "0":
+            return
+        hold = [torch.empty(mb << 20, dtype=torch.uint8, device=self.device) for _ in range(blocks)]
+        del hold
 
     def _warm_collectives(self) -> None:
         """Run every collective of an iteration once at its real size (gradient all-reduce, ray-count all-reduce,
@@ -513,6 +526,8 @@ class Trainer:
         """Restore what step() changed process-wide: with `manual_gc` the cyclic collector is frozen and disabled while
         the trainer runs (collections happen at the occupancy-update cadence); close() -- also called by `with Trainer(...)`
         and on garbage collection of the trainer -- unfreezes it and re-enables it if it was enabled before."""
+        if getattr(self, "_fused", None) is not None and self.device.type == "cuda":
+            self._fused.wait_updates()   # peer-update mode: the side stream's last parameter updates join the main stream
         if self._gc_frozen:
             import gc
             gc.unfreeze()
@@ -607,7 +622,11 @@ class Trainer:
         peer = self._fused.peer
         t = self._peer_adam_step = getattr(self, "_peer_adam_step", 0) + 1   # Adam's own 1-based step count
         with torch.cuda.device(self.device):
-            peer.publish_count(t, info.size(0))
+            if self._fused.peer_overlap:   # nothing on the main stream depends on it: beside the TV pass
+                with torch.cuda.stream(self._fused._peer_stream):
+                    peer.publish_count(t, info.size(0))
+            else:
+                peer.publish_count(t, info.size(0))
         g = self.optimizer.param_groups[0]
         out = self._fused.forward_backward(packed, info, rgbs, peer_step={
             "step": t, "lr": g["lr"], "betas": g["betas"], "eps": g["eps"], "weight_decay": g["weight_decay"]})
