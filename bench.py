@@ -596,7 +596,7 @@ def train_workload(ctx: Ctx, name: str, steps: int, warmup: int, e2e_arm: bool, 
         n2, ms2, _, _, _ = timed(tr, steps, True, profile=False)
         e2e = n2 / (ms2 * 1e-3)
         h2d = (tr.store.h2d_bytes - h0) / steps
-        batches_per_step = h2d / (BATCH * 36)
+        batches_per_step = h2d / (BATCH * 44)   # 36 B of ray data + an 8-byte index per ray
         d2h = 4 + 8 * batches_per_step  # loss + one packed-sample count per provider call
         tr.close()
         del tr

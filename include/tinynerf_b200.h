@@ -402,6 +402,13 @@ int tnf_dp_publish_count(uint64_t* const* peer_slots, int32_t world, int32_t ran
 int tnf_dp_sum_counts(const uint64_t* slots, int32_t world, int32_t slot, uint32_t step, float* out, int32_t* error,
                       void* stream);
 
+/* ---- ray batches (DataLoader collate + .to(device), src/run.py:116-122,226-228) --------------------------------------------
+ * out[i][:] = table[idx[i]][:] for n_rows rows of row_floats floats.  idx: DEVICE int64 (entries in [0, n_table_rows), not
+ * checked).  `table` is a device pointer OR a pointer into pinned host memory (cudaHostAlloc / torch pin_memory under unified
+ * addressing): the kernel then reads the rows over the host link (zero-copy) -- the H2D transfer of exactly these rows. */
+int tnf_gather_rows(const float* table, int64_t n_table_rows, int32_t row_floats, const int64_t* idx, int64_t n_rows, float* out,
+                    void* stream);
+
 /* ---- host helper: lazily shuffled ray order (DataLoader(shuffle=True), src/run.py:116-122) --------------------------------
  * HOST pointers.  perm: n entries, initially 0..n-1 (any permutation); out receives `count` ray indices.  pos is a global
  * position counter (a multiple of world; advance it by count*world), *fresh_from the first position never drawn so far

@@ -122,3 +122,20 @@ def test_trainer_render_matches_renderer_call():
         # arithmetic, different fp32 summation order inside the MLP
         want = tr.renderer(s, i)
         assert bool(((img[:384] - want).abs() <= 1e-5 * want.abs() + 2e-6).all())
+
+
+def test_host_resident_ray_store_hands_out_the_same_batches():
+    """RayStore(host=True): the rows are read by the GPU straight out of pinned host memory (tnf_gather_rows, zero-copy) --
+    same rays, same order as the HBM-resident store, and the H2D bytes are accounted."""
+    o, d = synthetic.blender_rays(50_000, seed=3)
+    rgb = torch.rand(50_000, 3, generator=torch.Generator().manual_seed(1))
+    a, b = RayStore(o, d, rgb, DEV, host=False, seed=7), RayStore(o, d, rgb, DEV, host=True, seed=7)
+    assert b.data.is_pinned() and not b.data.is_cuda
+    table = torch.cat([o, d, rgb], -1)
+    for n in (1024, 3 * 1024, 1, 40_000, 30_000):   # the last call wraps around the epoch
+        ra, rb = a.next(n), b.next(n)
+        torch.cuda.synchronize()
+        for x, y in zip(ra, rb):
+            assert x.is_cuda and torch.equal(x, y)
+        assert torch.equal(torch.cat(ra, -1).cpu(), table[a.last_indices])
+    assert b.h2d_bytes == (1024 + 3 * 1024 + 1 + 40_000 + 30_000) * 44 and a.h2d_bytes == 0

@@ -116,6 +116,7 @@ _SIGNATURES = {
                                            C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
     "tnf_dp_publish_count": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_float, C.c_void_p]),
     "tnf_dp_sum_counts": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, c_f32p, C.c_void_p, C.c_void_p]),
+    "tnf_gather_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, c_f32p, C.c_void_p]),
     "tnf_wide_linear_fwd": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_void_p]),
     "tnf_wide_linear_bwd_data": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64,

@@ -289,3 +289,34 @@ extern "C" int tnf_abs_mean_bwd(const float* x, int64_t n, const float* grad_sca
   TNF_LAUNCH_CHECK("abs_mean_bwd_kernel");
   return TNF_OK;
 }
+
+// ---- ray batches: rows of the scene's ray table picked by the shuffled order (src/run.py:116-122,226-228) --------------
+// The reference's DataLoader collates `batch_size` random rows of the pinned ray table on the host and copies them to the
+// device.  Here the GPU picks the rows itself: `table` may live in HBM or in PINNED HOST memory (unified addressing makes
+// cudaHostAlloc'd memory readable from the device at the same address), in which case the 36-byte rows cross the host link as
+// zero-copy reads -- the H2D transfer of exactly the rows the batch needs, with no host gather and no staging buffer.
+namespace tnf {
+namespace {
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, long long row_floats,
+                                                          const long long* __restrict__ idx, long long n_rows, float* __restrict__ out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = n_rows * row_floats;
+  if (t >= total) return;
+  const long long r = t / row_floats, c = t - r * row_floats;
+  out[t] = ld_stream_f1(table + __ldg(idx + r) * row_floats + c);
+}
+}  // namespace
+}  // namespace tnf
+
+extern "C" int tnf_gather_rows(const float* table, int64_t n_table_rows, int32_t row_floats, const int64_t* idx, int64_t n_rows,
+                               float* out, void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(n_rows >= 0 && n_table_rows >= 0 && row_floats >= 1, "bad sizes");
+  if (n_rows == 0) return TNF_OK;
+  TNF_REQUIRE(table && idx && out, "null pointer");
+  const long long total = n_rows * (long long)row_floats;
+  gather_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, row_floats,
+      reinterpret_cast<const long long*>(idx), n_rows, out);
+  TNF_LAUNCH_CHECK("gather_rows_kernel");
+  return TNF_OK;
+}

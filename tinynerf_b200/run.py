@@ -95,7 +95,8 @@ class MultiStepLR:
 class RayStore:
     """Rays + colours of a scene, shuffled per epoch like DataLoader(shuffle=True) (src/run.py:116-122).
     Lives on `device` (HBM-resident, no per-batch H2D) or in pinned host memory (`host=True`), in which
-    case every batch is gathered on the host and copied H2D, as in the reference (src/run.py:226-228).
+    case every batch's rows cross the host link inside next(): the reference collates them on the host and copies
+    (src/run.py:226-228), here the GPU reads exactly those rows out of the pinned table (tnf_gather_rows, zero-copy).
     With world_size > 1 each rank shuffles its own disjoint 1/world of the rays (ray index % world == rank)."""
 
     def __init__(self, rays_o: torch.Tensor, rays_d: torch.Tensor, rgbs: torch.Tensor, device, host: bool = False,
@@ -115,7 +116,6 @@ class RayStore:
         self._fresh = C.c_int64(0)     # first global position never drawn so far
         self._pos = 0                  # position of the next batch in this rank's order
         self.h2d_bytes = 0
-        self._stage = None
         self._idx_ring, self._idx_i = [], 0
 
     def rewind(self, n_rays: int) -> None:
@@ -131,7 +131,7 @@ class RayStore:
         return self._m - (self._pos % self._m)
 
     def _next_indices(self, batch: int) -> torch.Tensor:
-        on_gpu = (not self.host) and self.device.type == "cuda"
+        on_gpu = self.device.type == "cuda"
         if on_gpu:
             # pinned staging for the asynchronous upload of the indices: a ring of four slots, each guarded by the event of
             # its last upload (a slot is rewritten only after that copy has run; in the trainer it always has, because the
@@ -160,23 +160,21 @@ class RayStore:
 
     def next(self, batch: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         idx = self._next_indices(batch)
+        if self.device.type != "cuda":   # CPU plumbing tests (gloo): plain torch
+            rows = torch.index_select(self.data, 0, idx)
+            return rows[:, 0:3], rows[:, 3:6], rows[:, 6:9]
+        # capacity in 16 Ki-row quanta, like RayProvider.pack: the chunk count of a batch wanders, and a request slightly
+        # larger than every cached block makes the caching allocator cudaMalloc in the middle of a step
+        cap = (batch + 16383) & ~16383
+        rows = torch.empty(cap, 9, device=self.device)[:batch]
+        # the GPU picks the rows itself -- from HBM, or (host=True) straight out of the pinned host table over the host link:
+        # the H2D copy of exactly this batch's rows, without a host-side gather or a staging buffer (the reference's loader
+        # collates on the host and copies, src/run.py:116-122,226-228)
+        with torch.cuda.device(self.device):
+            _lib.call("tnf_gather_rows", self.data.data_ptr(), self.n, 9, idx.data_ptr(), batch, rows.data_ptr(), _lib.stream_ptr(),
+                      nbytes=batch * (36 + 36 + 8))
         if self.host:
-            if self._stage is None or self._stage.size(0) < batch:  # grow-only: pinning memory is a slow, synchronising call
-                self._stage = torch.empty(max(batch, 1 << 16, 2 * (0 if self._stage is None else self._stage.size(0))), 9).pin_memory()
-            stage = self._stage[:batch]
-            if getattr(self, "_stage_event", None) is not None:
-                self._stage_event.synchronize()   # the previous batch's upload has read the staging buffer
-            torch.index_select(self.data, 0, idx, out=stage)
-            rows = stage.to(self.device, non_blocking=True)
-            if rows.is_cuda:
-                self._stage_event = torch.cuda.current_stream(self.device).record_event()
-            self.h2d_bytes += rows.numel() * 4
-        else:
-            # capacity in 16 Ki-row quanta, like RayProvider.pack: the chunk count of a batch wanders, and a request slightly
-            # larger than every cached block makes the caching allocator cudaMalloc in the middle of a step
-            cap = (batch + 16383) & ~16383
-            rows = torch.empty(cap, 9, device=self.device)[:batch]
-            torch.index_select(self.data, 0, idx, out=rows)
+            self.h2d_bytes += batch * (36 + 8)   # the rows (zero-copy reads) + their indices
         return rows[:, 0:3], rows[:, 3:6], rows[:, 6:9]
 
 
