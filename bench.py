@@ -378,16 +378,16 @@ def weights_microbench(dev, logn: int, peak: float, with_reference: bool = True)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of one training
-# iteration (profiles/r01_ncu_full.md, N = 233,625 packed samples): the `traffic` of the roofline object.
+# iteration (profiles/r02_ncu_full.md, N = 234,218 packed samples): the `traffic` of the roofline object.
 NCU_TRAFFIC_BYTES = {
-    "tnf_kplanes_bwd": 639.1e6,         # kplanes_kernel<1>: 488.1 MB read + 151.0 MB written
-    "tnf_kplanes_fwd": 230.9e6,         # kplanes_kernel<0>: 151.8 + 79.1 MB
-    "tnf_heads_fwd": 390.7e6,           # 138.9 + 251.8 MB
-    "tnf_heads_bwd_data": 596.6e6,      # 331.3 + 265.3 MB
-    "tnf_linear_bwd_weight": 136.5e6,   # wgrad_tma_kernel, 64x64 layer: 132.0 + 4.5 MB
-    "tnf_adam_step_grid": 871.0e6,           # 529.1 + 341.9 MB
-    "tnf_tv_fwd_bwd": 215.5e6,          # tv_march_kernel: 138.7 + 76.8 MB
-    "tnf_head_bwd": 94.0e6,             # head_bwd_kernel<3>: 72.2 + 21.8 MB
+    "tnf_kplanes_bwd": 643.3e6,         # kplanes_kernel<1,4>: 492.6 MB read + 150.7 MB written
+    "tnf_kplanes_fwd": 255.9e6,         # kplanes_kernel<0,6>: 165.2 + 90.7 MB
+    "tnf_heads_fwd": 444.3e6,           # 156.1 + 288.2 MB
+    "tnf_heads_bwd_data": 606.6e6,      # 337.0 + 269.6 MB
+    "tnf_linear_bwd_weight": 138.2e6,   # wgrad_tma_kernel, 64x64 layer: 134.5 + 3.7 MB
+    "tnf_adam_step_grid": 869.7e6,      # 529.0 + 340.7 MB
+    "tnf_tv_fwd_bwd": 215.7e6,          # tv_march_kernel: 139.1 + 76.6 MB
+    "tnf_head_bwd": 96.7e6,             # head_bwd_kernel<3>: 73.5 + 23.2 MB
 }
 TENSOR_BOUND = {"tnf_heads_fwd", "tnf_heads_bwd_data", "tnf_linear_fwd", "tnf_linear_bwd_data", "tnf_wide_linear_fwd",
                 "tnf_wide_linear_bwd_data", "tnf_wide_linear_bwd_weight"}
@@ -427,7 +427,7 @@ def roofline_of(table, dom, peak, tf32_peak, peak_src):
                 "frac": t["tensor_frac_issued"], "traffic": NCU_TRAFFIC_BYTES.get(dom), "peak_source": peak_src + " (bf16 burst / 2 = TF32)",
                 "avg_us": t["avg_us"], "hbm_frac": t["frac"], "note": "3xTF32: three issued TF32 MMAs per fp32-accurate product"}
     return {"kernel": dom, "bound": "hbm", "achieved": t["GB/s"], "peak": peak, "unit": "GB/s", "frac": t["frac"],
-            "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r01_ncu_full.md" if dom in NCU_TRAFFIC_BYTES else None,
+            "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r02_ncu_full.md" if dom in NCU_TRAFFIC_BYTES else None,
             "peak_source": peak_src, "avg_us": t["avg_us"], "alg_bytes_per_launch": int(t["alg_MB_per_launch"] * 1e6)}
 
 
