@@ -75,7 +75,7 @@ def test_cobafa_matches_reference_golden(golden):
     for i, b in enumerate(field.basis_grids):
         close(b.grid.grad.cpu(), g[f"gbasis_{i}"], atol=1e-6)
     close(field.coef_grid.grid.grad.cpu(), g["gcoef"], atol=1e-6)
-    close(field(x).cpu(), g["forward_eval"], rtol=1e-4, atol=1e-6)  # through the cuBLAS trunk MLP
+    close(field(x).cpu(), g["forward_eval"], rtol=1e-4, atol=1e-6)  # vs the CPU reference run (its trunk MLP is SGEMM)
 
 
 def test_cobafa_full_size_vs_torch_on_gpu():
@@ -135,7 +135,7 @@ def test_renderer_matches_reference_golden(golden):
     packed, info = prov(g["rays_o"].to(DEV), g["rays_d"].to(DEV), training=False)
     assert torch.equal(packed.cpu(), g["packed"]) and torch.equal(info.cpu(), g["info"])
     out = renderer(packed, info)
-    close(out.cpu(), g["rendered"], rtol=1e-4, atol=1e-6)   # through cuBLAS MLPs vs the CPU reference run
+    close(out.cpu(), g["rendered"], rtol=1e-4, atol=1e-6)   # tensor-core MLPs vs the CPU reference run
     loss = ((out - 0.25) ** 2).mean()
     loss.backward()
     assert float(loss) == pytest.approx(g["loss"], rel=1e-4)

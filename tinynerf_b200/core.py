@@ -580,10 +580,19 @@ class NerfRenderer(torch.nn.Module):
             if n_samples == 0:
                 raise ValueError("no samples remaining")
             samples_features = self.feature_module(packed_samples[:, :3])
-            samples_sigmas = self.sigma_decoder(samples_features).ravel()
-            weights: torch.Tensor = NerfWeights.apply(samples_sigmas, steps, packing_info,
-                                                      early_termination_threshold)  # type: ignore
-            samples_rgbs = self.rgb_decoder(samples_features, packed_samples[:, 3:6])
+            from . import heads_ops
+            if heads_ops.supported(self.sigma_decoder, self.rgb_decoder, samples_features):
+                # both decoders of the reference's shapes in the fused head kernels (one forward kernel, one data-gradient
+                # kernel); same values as the two module calls below
+                sig, samples_rgbs = heads_ops.fused_heads(self.sigma_decoder, self.rgb_decoder, samples_features,
+                                                          packed_samples[:, 3:6])
+                samples_sigmas = sig.ravel()
+                weights: torch.Tensor = NerfWeights.apply(samples_sigmas, steps, packing_info,
+                                                          early_termination_threshold)  # type: ignore
+            else:
+                samples_sigmas = self.sigma_decoder(samples_features).ravel()
+                weights = NerfWeights.apply(samples_sigmas, steps, packing_info, early_termination_threshold)  # type: ignore
+                samples_rgbs = self.rgb_decoder(samples_features, packed_samples[:, 3:6])
         except ValueError:
             print("Empty iteration, every sample is masked")
             samples_rgbs = torch.zeros((n_samples, 3), device=device, requires_grad=True)

@@ -1105,6 +1105,16 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   const bool want_ss = variant(kVariantWgradSS) == 1;   // diagnostics: the both-operands-in-shared-memory kernel
   if (n == 64 && m < (1LL << 31) - 256 && !want_ss)
     return launch_wgrad_tma(dy, lddy, x, ldx, k, nullptr, 0, 0, dweight, dbias, nullptr, m, st);
+  if (n == 128 && (k + 31) / 32 <= kMaxKAtoms && m < (1LL << 31) - 256 && !want_ss) {
+    // 128 output features (the Cobafa trunk, src/models.py:254-266) = two 64-row halves of dW through the tensor-memory /
+    // TMA kernel: 2 x ~60 us against ~200 us for the both-operands-in-shared-memory kernel below (M = 2^18, K = 128)
+    for (int h = 0; h < 2; ++h) {
+      rc = launch_wgrad_tma(dy + 64 * h, lddy, x, ldx, k, nullptr, 0, 0, dweight + (size_t)64 * h * k, dbias ? dbias + 64 * h : nullptr,
+                            nullptr, m, st);
+      if (rc != TNF_OK) return rc;
+    }
+    return TNF_OK;
+  }
   // shared-memory plan: dY sets (hi + lo images of n/32 atoms each; two sets when they leave room for >= 2 X stages)
   // + S X stages (32 KB each)
   const size_t set_bytes = (size_t)(2 * ((n + 31) / 32)) * kAtomBytes;
