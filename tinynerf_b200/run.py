@@ -55,12 +55,16 @@ def _flat_dense(t: torch.Tensor) -> torch.Tensor:
 
 
 def allreduce_gradients(params, world: int) -> None:
-    """Sum the per-rank gradients (NCCL over NVLink on the GPU box)."""
+    """Sum the per-rank gradients (NCCL over NVLink on the GPU box): ONE collective over a flat copy of all gradients
+    instead of one per parameter (35 launches and their latencies for Cobafa), copied back with one foreach op."""
     if world <= 1:
         return
-    for p in params:
-        if p.grad is not None:
-            dist.all_reduce(_flat_dense(p.grad))
+    flats = [_flat_dense(p.grad) for p in params if p.grad is not None]
+    if not flats:
+        return
+    buf = torch.cat(flats)
+    dist.all_reduce(buf)
+    torch._foreach_copy_(flats, list(buf.split([f.numel() for f in flats])))
 
 
 def shard_slices(depth: int, rank: int, world: int) -> Tuple[int, int]:
