@@ -108,7 +108,21 @@ typedef struct tnf_march_params {
   uint64_t seed, offset;    /* Philox4x32-10 key/counter base when jitter && !noise */
   const float* threshold_dev; /* optional DEVICE scalar that replaces `threshold` (e.g. min(base, grid.mean()) computed on the
                                device right after an occupancy update, so the update needs no host synchronisation) */
+  const uint32_t* empty_bits; /* optional DEVICE bitfield from tnf_occ_build_empty_bits for THIS grid and threshold (NULL: none).
+                               tnf_march_count stages it in shared memory and skips the float lookup for lattice points in
+                               blocks it marks certainly empty; the keep-mask is bit-identical with and without it. */
 } tnf_march_params;
+
+/* "Certainly empty" classifier of an occupancy grid (the mask of src/core.py:148-156 is trilinear(grid) > threshold on float
+ * values, so a bit test can only short-circuit where the outcome is certain).  bits: tnf_occ_empty_bits_words(gd,gh,gw) 32-bit
+ * words, two levels back to back: coarse [ceil(gd/2)][ceil(gh/2)][ceil(ceil(gw/2)/32)] -- bit (bz,by,bx) set when every lattice
+ * value a lookup in the 2x2x2-cell block can touch is <= threshold*(1 - 1e-5) (32 KB for 128^3, staged in shared memory by
+ * tnf_march_count) -- then fine [gd][gh][ceil(gw/32)], one bit per cell (its 8 corners).  Where a bit is set the lookup's convex
+ * combination cannot exceed the threshold in fp32 either.  Rebuild after every change of the grid or of the threshold
+ * (threshold_dev, when given, is read by the kernel). */
+int64_t tnf_occ_empty_bits_words(int32_t gd, int32_t gh, int32_t gw);
+int tnf_occ_build_empty_bits(const float* grid, int32_t gd, int32_t gh, int32_t gw, float threshold,
+                             const float* threshold_dev /*optional*/, uint32_t* bits, void* stream);
 
 int tnf_march_count(const tnf_march_params* p /*[host]*/, const float* rays_o, const float* rays_d,
                     int64_t n_rays, int32_t info_offset, uint32_t* mask_bits, int32_t* info,

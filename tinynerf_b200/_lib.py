@@ -43,6 +43,7 @@ class MarchParams(C.Structure):
         ("seed", C.c_uint64),
         ("offset", C.c_uint64),
         ("threshold_dev", C.c_void_p),
+        ("empty_bits", C.c_void_p),
     ]
 
 
@@ -65,6 +66,8 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     "tnf_march_pack": (C.c_int, [C.POINTER(MarchParams), c_f32p, c_f32p, C.c_int64, C.c_int32, c_u32p, c_i32p,
                                  c_f32p, c_f32p, c_i32p, C.c_int64, C.c_void_p]),
+    "tnf_occ_empty_bits_words": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "tnf_occ_build_empty_bits": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, c_f32p, c_u32p, C.c_void_p]),
     "tnf_occ_query": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int64, C.c_float,
                                 C.c_void_p, c_f32p, C.c_void_p]),
     "tnf_occ_update_coords": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_f32p,

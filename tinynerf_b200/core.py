@@ -203,6 +203,15 @@ class OccupancyGrid(torch.nn.Module):
         self.jitter_source = "cpu"
         self.slices_per_call = size[0]
         self._update_calls = 0
+        # "certainly empty" classifier bitfields for the march kernel (tnf_occ_build_empty_bits): rebuilt lazily whenever the
+        # grid or the threshold changed; two buffers alternate so a kernel in flight on another stream keeps reading a
+        # consistent image while the next one is built.  OFF by default: bit-identical masks, but measured slower than the
+        # plain kernel on the bench scene (csrc/march.cu)
+        self.use_empty_bits = False
+        self._bits_gen = 0
+        self._bits_key = None
+        self._bits_bufs: List[torch.Tensor] = []
+        self._bits_cur = 0
 
     @property
     def mean(self) -> float:
@@ -215,6 +224,35 @@ class OccupancyGrid(torch.nn.Module):
     @mean.setter
     def mean(self, value: float) -> None:
         self._mean, self._mean_t, self._thr_t = float(value), None, None
+        self._bits_gen += 1
+
+    def invalidate(self) -> None:
+        """Call after writing `grid` through anything torch does not version (a raw pointer, a collective)."""
+        self._bits_gen += 1
+
+    def empty_bits(self) -> torch.Tensor | None:
+        """The classifier bitfield for the current grid and threshold, built on the current stream when stale
+        (32 KB coarse + 256 KB fine for 128^3; None when disabled or when the coarse level would not fit the march kernel's
+        shared-memory staging)."""
+        if not self.use_empty_bits or not self.grid.is_cuda:
+            return None
+        D, H, W = self.grid.shape
+        n_words = int(_lib.load().tnf_occ_empty_bits_words(D, H, W))
+        if ((D + 1) // 2) * ((H + 1) // 2) * ((((W + 1) // 2) + 31) // 32) * 4 > 64 * 1024:   # coarse level must fit the staging
+            return None
+        key = (self.grid.data_ptr(), self.grid._version, self._bits_gen, self._update_calls)
+        if key != self._bits_key:
+            if len(self._bits_bufs) < 2 or self._bits_bufs[0].device != self.grid.device or self._bits_bufs[0].numel() != n_words:
+                self._bits_bufs = [torch.empty(n_words, dtype=torch.int32, device=self.grid.device) for _ in range(2)]
+            self._bits_cur ^= 1
+            bits = self._bits_bufs[self._bits_cur]
+            thr_t = self.threshold_tensor()
+            thr = _f32(self.base_threshold) if thr_t is not None else _f32(self.threshold)
+            with torch.cuda.device(self.grid.device):
+                _lib.call("tnf_occ_build_empty_bits", self.grid.data_ptr(), D, H, W, thr, _lib.ptr(thr_t), bits.data_ptr(),
+                          _lib.stream_ptr(), nbytes=4 * self.grid.numel() + 4 * n_words)
+            self._bits_key = key
+        return self._bits_bufs[self._bits_cur]
 
     def threshold_tensor(self) -> torch.Tensor | None:
         """Device scalar min(base_threshold, mean) when the mean currently lives on the device, else None."""
@@ -227,6 +265,7 @@ class OccupancyGrid(torch.nn.Module):
     def _set_mean_from_grid(self) -> None:
         self._mean, self._thr_t = None, None
         self._mean_t = self.grid.mean()
+        self._bits_gen += 1
 
     @torch.no_grad()
     def occupancy(self) -> float:
@@ -363,6 +402,10 @@ class RayProvider:
             p._keep = list(p._keep) + [thr_t]
         else:
             p.threshold = _f32(self.occupancy_grid.threshold)
+        bits = self.occupancy_grid.empty_bits()
+        if bits is not None:
+            p.empty_bits = bits.data_ptr()
+            p._keep = list(p._keep) + [bits]
         return p
 
     def _scene_params(self, device, n_steps: int) -> _lib.MarchParams:

@@ -34,7 +34,7 @@ int sm_count() {
 
 }  // namespace tnf
 
-extern "C" int tnf_version(void) { return 1000; }
+extern "C" int tnf_version(void) { return 1001; }   // 1001: tnf_march_params.empty_bits
 
 extern "C" int tnf_set_sm_budget(int n_sms) {
   const int prev = tnf::g_sm_budget;

@@ -46,6 +46,7 @@ struct MarchConst {
   const float* noise;
   int jitter;
   unsigned long long seed, offset;
+  const uint32_t* empty_bits;   // optional classifier bitfields (tnf_occ_build_empty_bits), see occ_certainly_empty
 };
 
 // NaN-propagating min/max/clamp like torch.amin/amax/clamp
@@ -132,6 +133,44 @@ TNF_HD bool contract_point(const MarchConst& M, const float p[3], float q[3]) {
   return inside;
 }
 
+// Occupancy classifier, two levels, one buffer (tnf_occ_build_empty_bits):
+//   coarse  bit (bz, by, bx): EVERY lattice value a lookup in the 2x2x2-cell block can touch (corners [2b, 2b+2] per axis)
+//           is <= threshold * (1 - 1e-5).  [ceil(D/2)][ceil(H/2)][ceil(ceil(W/2)/32)] words, 32 KB for 128^3: the march
+//           kernel stages this level in SHARED memory.
+//   fine    bit (z, y, x): the 8 corners of cell (x, y, z) are all <= threshold * (1 - 1e-5).  [D][H][ceil(W/32)] words
+//           after the coarse level (256 KB for 128^3: L1/L2-resident, one 4-byte load).
+// A lookup's result is a convex combination of its 8 corners (weights >= 0, their fp32 sum <= 1 + 5e-7, 8 fused
+// multiply-adds: <= 1e-6 relative excess in all), so where a bit is set `trilinear(grid) > threshold` is false whatever
+// the weights -- exactly what the float path would return.  Isolated occupied cells ("floaters") defeat the coarse level
+// (27 corners) more often than the fine one (8 corners).
+TNF_HD int occ_bits_words_per_row(int W) { return (((W + 1) >> 1) + 31) >> 5; }
+TNF_HD long long occ_bits_coarse_words(int D, int H, int W) {
+  return (long long)((D + 1) >> 1) * ((H + 1) >> 1) * occ_bits_words_per_row(W);
+}
+TNF_HD long long occ_bits_words(int D, int H, int W) {
+  return occ_bits_coarse_words(D, H, W) + (long long)D * H * ((W + 31) >> 5);
+}
+// coarse: level-1 words (shared or global memory); fine: level-2 words (global) or nullptr
+TNF_HD bool occ_certainly_empty(const uint32_t* coarse, const uint32_t* fine, int D, int H, int W, float x, float y, float z) {
+  const float ix = TNF_MUL(TNF_MUL(TNF_ADD(x, 1.f), 0.5f), (float)(W - 1));
+  const float iy = TNF_MUL(TNF_MUL(TNF_ADD(y, 1.f), 0.5f), (float)(H - 1));
+  const float iz = TNF_MUL(TNF_MUL(TNF_ADD(z, 1.f), 0.5f), (float)(D - 1));
+  const int x0 = (int)floorf(ix), y0 = (int)floorf(iy), z0 = (int)floorf(iz);
+  // only lookups whose near corner is a lattice point (far corners beyond the grid are skipped by the lookup: they only
+  // lower the sum); anything else -- outside coordinates, NaN -- takes the float path
+  if (!((unsigned)x0 < (unsigned)W && (unsigned)y0 < (unsigned)H && (unsigned)z0 < (unsigned)D)) return false;
+  const int bx = x0 >> 1;
+  const uint32_t w = coarse[((long long)(z0 >> 1) * ((H + 1) >> 1) + (y0 >> 1)) * occ_bits_words_per_row(W) + (bx >> 5)];
+  if ((w >> (bx & 31)) & 1u) return true;
+  if (!fine) return false;
+#ifdef __CUDA_ARCH__
+  const uint32_t f = __ldg(fine + ((long long)z0 * H + y0) * ((W + 31) >> 5) + (x0 >> 5));
+#else
+  const uint32_t f = fine[((long long)z0 * H + y0) * ((W + 31) >> 5) + (x0 >> 5)];
+#endif
+  return (f >> (x0 & 31)) & 1u;
+}
+
 struct SampleOut {
   float p[3];   // contracted coordinates in [-1,1]
   float step;   // step size of this sample
@@ -141,7 +180,7 @@ struct SampleOut {
 // One lattice point (ray, step j) of RayProvider.__call__ (src/core.py:171-176).
 // u = jitter in [0,1) (ignored when !jitter); tmin only used for AABB scenes.
 TNF_HD SampleOut march_sample(const MarchConst& M, const float o[3], const float d[3], float tmin, int j,
-                              float u) {
+                              float u, const uint32_t* coarse_bits = nullptr, const uint32_t* fine_bits = nullptr) {
   SampleOut s;
   float t, step;
   if (M.scene == 0) {  // AABB: t = t_min + j*step ; step constant (src/core.py:84-86)
@@ -159,7 +198,9 @@ TNF_HD SampleOut march_sample(const MarchConst& M, const float o[3], const float
   s.step = step;
   // src/core.py:151-156,176: mask = marcher_mask & (trilinear(grid) > thr); the lookup has no side effect,
   // so it is skipped for samples the marcher mask already rejects (about half of an AABB lattice)
-  s.keep = inside && (trilinear_zeros(M.grid, M.gd, M.gh, M.gw, s.p[0], s.p[1], s.p[2]) > (M.thr_dev ? *M.thr_dev : M.thr));
+  // ... and for samples the classifier bitfields know to be empty (most of the rest in a trained scene)
+  s.keep = inside && !(coarse_bits && occ_certainly_empty(coarse_bits, fine_bits, M.gd, M.gh, M.gw, s.p[0], s.p[1], s.p[2])) &&
+           (trilinear_zeros(M.grid, M.gd, M.gh, M.gw, s.p[0], s.p[1], s.p[2]) > (M.thr_dev ? *M.thr_dev : M.thr));
   return s;
 }
 
