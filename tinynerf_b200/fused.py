@@ -125,6 +125,13 @@ class FusedKPlanesStep:
         self._cap_n = self._cap_r = 0
         self._ws: Dict[str, torch.Tensor] = {}
         self.fused_composite = os.environ.get("TNF_FUSED_COMPOSITE", "1") != "0"   # 0: the three separate kernels
+        # Kernels of an iteration that depend on nothing before them run on an auxiliary stream beside kernels bound by a
+        # different resource (TNF_AUX_OVERLAP=0: everything in line): the TV pass (HBM streaming) and the [PE(d)|d] rows
+        # (issue-bound sincos) beside the plane gather (L2 -> SM bound); the colour head's output-layer backward (HBM) beside
+        # the density branch's weights backward + output-layer backward.
+        self.aux_overlap = os.environ.get("TNF_AUX_OVERLAP", "1") != "0"
+        self._aux = torch.cuda.Stream(device=self.dev, priority=int(os.environ.get("TNF_AUX_PRIO", "0"))) if self.aux_overlap else None
+        self._aux_tv_first = os.environ.get("TNF_AUX_ORDER", "color_first") == "tv_first"
         self._closs_scratch = torch.zeros(2, dtype=torch.float64, device=self.dev)   # tnf_composite_loss_fwd_bwd (zero between calls)
         # SMs a concurrent collective kernel occupies (NCCL_MAX_CTAS when set, else the 32 CTAs NCCL uses on NVLink here:
         # measured at 2 GPUs, capping NCCL at 16 / 8 CTAs slows the step 316 -> 288 -> 244 M samples/s)
@@ -332,7 +339,28 @@ class FusedKPlanesStep:
             # doubles as the zero-fill of 99.8 % of the buffer; the data term is scattered on top of it in backward
             defer_heads = peer_step is not None and self.peer_overlap and self.tv_alpha != 0.0
             self.wait_updates(planes=True, heads=not defer_heads)   # the planes are read first (TV pass, gather); the heads later
-            if self.tv_alpha != 0.0:
+            aux_on = self.aux_overlap and self.fused_heads and self.split_xc and self.tv_alpha != 0.0
+            main = torch.cuda.current_stream(self.dev)
+            xc_ready = tv_done = None
+            if aux_on:
+                aux = self._aux
+                aux.wait_event(main.record_event())   # everything of the previous iteration (and the waits above) first
+                with torch.cuda.stream(aux):
+                    ast = aux.cuda_stream
+                    for which in (("tv", "color") if self._aux_tv_first else ("color", "tv")):
+                        if which == "color":
+                            call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, 0, P(ws["xc"]), xld, n, ast,
+                                 nbytes=n * (12 + 4 * xld))
+                            xc_ready = aux.record_event()
+                        else:
+                            call("tnf_tv_fwd_bwd", self._plane_ptrs, self._grad_ptrs, self._res_planes, len(self.planes),
+                                 self.channels, self._tv_w, P(self._tv_gscale), 0, P(self._tv_sums), ast, nbytes=2 * self._plane_bytes)
+                            tv_done = aux.record_event()
+                for t_ in (packed, target):   # read on the auxiliary stream too
+                    t_.record_stream(aux)
+                if not defer_heads:
+                    self.flat_grad[self._plane_grad_end:].zero_()
+            elif self.tv_alpha != 0.0:
                 call("tnf_tv_fwd_bwd", self._plane_ptrs, self._grad_ptrs, self._res_planes, len(self.planes), self.channels,
                      self._tv_w, P(self._tv_gscale), 0, P(self._tv_sums), st, nbytes=2 * self._plane_bytes)
                 if not defer_heads:
@@ -349,8 +377,11 @@ class FusedKPlanesStep:
                 self.flat_grad[self._plane_grad_end:].zero_()
             if self.fused_heads:
                 xc_feat = 0 if self.split_xc else F   # feature columns copied into the colour-input row
-                call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, xc_feat, P(ws["xc"]), xld, n, st,
-                     nbytes=n * (12 + 4 * xc_feat + 4 * xld))
+                if xc_ready is not None:
+                    main.wait_event(xc_ready)
+                else:
+                    call("tnf_color_input", P(packed) + 12, 7, P(ws["feats"]), F, self.n_freqs, xc_feat, P(ws["xc"]), xld, n, st,
+                         nbytes=n * (12 + 4 * xc_feat + 4 * xld))
                 hptrs = (C.c_void_p * 4)(*[P(ws[f"h{i}"]) for i in range(4)])
                 mlp_flops = 2 * n * (64 * (F + 1) + 64 * xw + 3 * 64 * 64 + 3 * 64)
                 call("tnf_heads_fwd", P(ws["feats"]), F, F, P(ws["xc"]), xld, xw, self.pe_width if self.split_xc else xw,
@@ -376,6 +407,8 @@ class FusedKPlanesStep:
             if peer_step is not None:
                 n_rays_global = self.peer.sum_counts(peer_step["step"])   # published by every rank at the start of its step
             tv_in_loss = self.fused_composite and self.tv_alpha != 0.0   # the kernel adds tv_alpha/world * loss_tv to the loss it reports
+            if tv_done is not None:
+                main.wait_event(tv_done)   # the loss kernel reads the regulariser's sums; the scatter adds onto its gradients
             if self.fused_composite:
                 call("tnf_composite_loss_fwd_bwd", P(ws["w"]), P(ws["rgb"]), P(info), n, r, self.bg, P(target), float(r),
                      _lib.ptr(n_rays_global), self.grad_scale, P(ws["rendered"]), P(ws["gw"]), P(ws["grgb"]), P(ws["loss"]),
@@ -394,8 +427,16 @@ class FusedKPlanesStep:
             # dh / activations and hides the plane all-reduce completely.
             # colour head: fused output layer + sigmoid, then the hidden layers' data gradients from the last to the first
             dh = [ws[f"dh{i}"] for i in range(nh)]   # dh[i] = gradient wrt the pre-activation of colour layer i
-            call("tnf_head_bwd", P(ws[f"h{nh - 1}"]), hc_w, P(cl[-1].weight), P(ws["rgb"]), P(ws["grgb"]), P(dh[nh - 1]),
-                 G(cl[-1].weight), G(cl[-1].bias), n, hc_w, 3, 2, st, nbytes=4 * n * (2 * hc_w + 6))
+            colour_done = None
+            if aux_on and self.fused_heads_bwd:
+                aux.wait_event(main.record_event())
+                with torch.cuda.stream(aux):
+                    call("tnf_head_bwd", P(ws[f"h{nh - 1}"]), hc_w, P(cl[-1].weight), P(ws["rgb"]), P(ws["grgb"]), P(dh[nh - 1]),
+                         G(cl[-1].weight), G(cl[-1].bias), n, hc_w, 3, 2, aux.cuda_stream, nbytes=4 * n * (2 * hc_w + 6))
+                    colour_done = aux.record_event()
+            else:
+                call("tnf_head_bwd", P(ws[f"h{nh - 1}"]), hc_w, P(cl[-1].weight), P(ws["rgb"]), P(ws["grgb"]), P(dh[nh - 1]),
+                     G(cl[-1].weight), G(cl[-1].bias), n, hc_w, 3, 2, st, nbytes=4 * n * (2 * hc_w + 6))
             if not self.fused_heads_bwd:
                 for i in range(nh - 1, 0, -1):
                     inp = ws[f"h{i - 1}"]
@@ -407,6 +448,8 @@ class FusedKPlanesStep:
             call("tnf_head_bwd", P(ws["hs"]), hs_w, P(sl[1].weight), P(ws["sigma"]), P(ws["gsigma"]), P(ws["dhs"]),
                  G(sl[1].weight), G(sl[1].bias), n, hs_w, 1, 1, st, nbytes=4 * n * (2 * hs_w + 2))
             dfeat = ws["dfeat"][:n]
+            if colour_done is not None:
+                main.wait_event(colour_done)
             if self.fused_heads_bwd:
                 # the whole data-gradient chain of both heads, down to the feature rows, in one kernel
                 masks = (C.c_void_p * 3)(*[P(ws[f"h{i}"]) for i in (2, 1, 0)])
