@@ -54,6 +54,8 @@ N_STORE = 1 << 21          # rays in the synthetic scene store (x36 B = 75 MB; >
 BATCH, N_SAMPLES = 1024, 256
 SEED = 1234
 
+DP_MODE_USED = [os.environ.get("TNF_DP_MODE", "peer")]
+
 TRAIN_SPECS = {
     "kplanes_aabb_2e18": dict(method="kplanes", scene="aabb", n_samples=256, pin_grid=True, rays="blender", min_steps=0),
     "cobafa_aabb_dyn": dict(method="cobafa", scene="aabb", n_samples=256, pin_grid=True, rays="blender", min_steps=0),
@@ -485,7 +487,15 @@ def train_workload(ctx: Ctx, name: str, steps: int, warmup: int, e2e_arm: bool, 
     def make_trainer(host: bool):
         torch.manual_seed(SEED)
         store = RayStore(o, d, rgbs, dev, host=host, seed=SEED, rank=rank, world=world)
-        tr = Trainer(cfg, store, dev, rank=rank, world=world)
+        try:
+            tr = Trainer(cfg, store, dev, rank=rank, world=world)
+        except Exception as ex:   # symmetric memory unavailable on this box (no P2P / fabric): the NCCL baseline, loudly
+            if world == 1 or cfg.dp_mode != "peer":
+                raise
+            sys.stderr.write(f"[bench] rank {rank}: peer-memory update unavailable ({ex!r}); falling back to dp_mode='nccl'\n")
+            cfg.dp_mode = "nccl"
+            DP_MODE_USED[0] = "nccl (peer-memory set-up failed)"
+            tr = Trainer(cfg, store, dev, rank=rank, world=world)
         if analytic is not None:
             tr.occupancy_grid.grid.copy_(analytic)
             tr.occupancy_grid.mean = analytic_mean
@@ -823,8 +833,8 @@ def main():
                        "grid": "128^3 analytic ball+torus, pinned after every update" if spec["pin_grid"] else "128^3, starts all-ones, evolves (updates + decay)",
                        "l2": "inputs change every step (fresh rays; parameters + gradients + Adam state stream through L2 > 126 MB)",
                        "parallelism": f"ray-sharded dp{world}" + ("" if world == 1 else ", parameter update: " + (
-                           "one reduce+Adam+broadcast kernel over NVLink peer memory" if os.environ.get("TNF_DP_MODE", "peer") == "peer"
-                           else "NCCL all-reduce + replicated Adam")), "host_wait": "blocking" if ctx.blocking_sync else "spin",
+                           "one reduce+Adam+broadcast kernel over NVLink peer memory" if DP_MODE_USED[0] == "peer"
+                           else "NCCL all-reduce + replicated Adam [" + DP_MODE_USED[0] + "]")), "host_wait": "blocking" if ctx.blocking_sync else "spin",
                        "settle_steps": main_res["settle_steps"],
                        "e2e_loss_readback": "every step, async D2H into a pinned ring, consumed one step late"},
             "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "host_ms_per_step": main_res["host_ms_per_step"],

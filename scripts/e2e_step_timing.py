@@ -9,7 +9,7 @@ from tinynerf_b200 import synthetic
 from tinynerf_b200.run import RayStore, TrainConfig, Trainer
 
 dev = torch.device("cuda", 0)
-o, d, rgbs = bench.make_scene(bench.N_STORE, bench.SEED)
+o, d, rgbs, _ = bench.make_scene("blender", bench.N_STORE, bench.SEED)
 analytic = synthetic.analytic_grid(128, seed=bench.SEED + 2).to(dev)
 amean = analytic.mean().item()
 for host in (False, True):

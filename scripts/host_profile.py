@@ -11,7 +11,7 @@ from tinynerf_b200 import synthetic
 from tinynerf_b200.run import RayStore, TrainConfig, Trainer
 
 dev = torch.device("cuda", 0)
-o, d, rgbs = bench.make_scene(1 << 20, bench.SEED)
+o, d, rgbs, _ = bench.make_scene("blender", 1 << 20, bench.SEED)
 cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=1024, n_samples=256, seed=1)
 tr = Trainer(cfg, RayStore(o, d, rgbs, dev, seed=1), dev)
 tr.occupancy_grid.grid.copy_(synthetic.analytic_grid(128, seed=bench.SEED + 2).to(dev))
