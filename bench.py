@@ -420,7 +420,7 @@ def summarise_profile(records, peak, tf32_peak):
     return table, dom
 
 
-def roofline_of(table, dom, peak, tf32_peak, peak_src):
+def roofline_of(table, dom, peak, tf32_peak, peak_src, samples_per_launch=0):
     if not dom:
         return None
     t = table[dom]
@@ -428,9 +428,19 @@ def roofline_of(table, dom, peak, tf32_peak, peak_src):
         return {"kernel": dom, "bound": "tensor", "achieved": t["TFLOP/s_tf32_issued"], "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": t["tensor_frac_issued"], "traffic": NCU_TRAFFIC_BYTES.get(dom), "peak_source": peak_src + " (bf16 burst / 2 = TF32)",
                 "avg_us": t["avg_us"], "hbm_frac": t["frac"], "note": "3xTF32: three issued TF32 MMAs per fp32-accurate product"}
-    return {"kernel": dom, "bound": "hbm", "achieved": t["GB/s"], "peak": peak, "unit": "GB/s", "frac": t["frac"],
+    roof = {"kernel": dom, "bound": "hbm", "achieved": t["GB/s"], "peak": peak, "unit": "GB/s", "frac": t["frac"],
             "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r02_ncu_full.md" if dom in NCU_TRAFFIC_BYTES else None,
             "peak_source": peak_src, "avg_us": t["avg_us"], "alg_bytes_per_launch": int(t["alg_MB_per_launch"] * 1e6)}
+    if dom in ("tnf_kplanes_bwd", "tnf_kplanes_fwd") and samples_per_launch:
+        # informational: the resource this kernel actually saturates.  Every sample moves 36 corner lines x 128 B through L2
+        # each way; the L2 executes 128-byte-line reductions at 6.7 TB/s of payload and serves line gathers at 16 TB/s
+        # (scripts/ubench/atomics_bench.cu, profiles/r02_atomics_ubench.txt) -- the HBM-byte accounting above cannot see that.
+        payload = 36 * 128 * samples_per_launch
+        l2_peak = 6700.0 if dom == "tnf_kplanes_bwd" else 16000.0
+        roof["l2_line_traffic"] = {"what": "red.v4 payload (scatter half)" if dom == "tnf_kplanes_bwd" else "corner-line gathers",
+                                   "bytes_per_launch": int(payload), "GB/s": round(payload / t["avg_us"] / 1e3, 1),
+                                   "measured_l2_peak_GB/s": l2_peak, "frac": round(payload / t["avg_us"] / 1e3 / l2_peak, 3)}
+    return roof
 
 
 class Ctx:
@@ -585,7 +595,7 @@ def train_workload(ctx: Ctx, name: str, steps: int, warmup: int, e2e_arm: bool, 
            "ms_per_step": round(ms / steps, 4), "packed_samples_per_step_per_gpu": round(n / steps / world),
            "gpu_launches": int(launches), "host_ms_per_step": round(host_ms[0], 4), "host_step_ms": {"value_arm": host_dist[0]},
            "settle_steps": settle, "clocks": clk, "kernels": table,
-           "roofline": roofline_of(table, dom, ctx.peak, ctx.tf32_peak, ctx.peak_src)}
+           "roofline": roofline_of(table, dom, ctx.peak, ctx.tf32_peak, ctx.peak_src, n / steps / world)}
     # occupancy update inside / outside the window (SURVEY 8d defines the metric with the update amortised at its cadence)
     all_upd = upd_ms or settle_upd_ms[-1:]
     upd_avg = sum(all_upd) / len(all_upd) if all_upd else None

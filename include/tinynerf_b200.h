@@ -255,6 +255,21 @@ int tnf_adam_step_grid(float* const* params, const float* const* grads, float* c
                        float* const* exp_avg_sq, const int64_t* numel, int32_t n_tensors, float lr, float beta1,
                        float beta2, float eps, float weight_decay, int64_t step, int32_t max_blocks, void* stream);
 
+/* Sorted scatter for the scales below the finest (same result as tnf_kplanes_bwd up to fp32 summation order).
+ * tnf_kplanes_sort: for each orientation o of itertools.combinations(range(3), 2) a counting sort of the n samples by their
+ * cell at resolution sort_res -> pos [3][n] int32 (slot of sample i in orientation o's order) and uv [3][n][2] (the
+ * orientation's two coordinates in slot order).  scratch: tnf_kplanes_sort_scratch_ints(sort_res, n) int32 words.
+ * tnf_kplanes_bwd_sorted: scales [0, sorted_scales) go through `rows` ([3*sorted_scales][n][32] floats: their per-plane
+ * gradient rows in slot order) and are reduced run by run -- one red.v4 per corner per run of samples in the same cell
+ * instead of per sample; the other scales scatter directly.  phase 0 = both kernels, 1 = gather + direct scatters + row
+ * stores only, 2 = the run-merging scatter of the stored rows only (callers that start work between the two).  32 channels. */
+int64_t tnf_kplanes_sort_scratch_ints(int32_t sort_res, int64_t n);
+int tnf_kplanes_sort(const float* x, int64_t x_stride, int64_t n, int32_t sort_res, int32_t* scratch, int32_t* pos, float* uv,
+                     void* stream);
+int tnf_kplanes_bwd_sorted(const float* const* planes, float* const* grad_planes, const int32_t* res, int32_t n_scales,
+                           int32_t channels, const float* x, int64_t x_stride, int64_t n, const float* grad_out,
+                           int32_t sorted_scales, const int32_t* pos, const float* uv, float* rows, int32_t phase, void* stream);
+
 /* ---- a14: Cobafa fused basis/coefficient lookup ----------------------------------------------
  * Replaces CobafaFeatureField.forward up to the concat (src/models.py:258-264): coef = trilinear
  * (coef_grid, x); y_l = trilinear(basis_l, 2*((f_l*x) mod 1)-1) * coef[l]; out = cat_l y_l.

@@ -213,3 +213,64 @@ def test_parity_object_of_the_bench_line():
     assert m["packing_info_bit_exact"] and m["packed_rows_bit_exact"] and m["n_samples"] > 50_000
     w = parity.weights_parity()
     assert w["termination_mask_bit_exact"] and w["weights_max_rel_err"] <= 1e-5 and w["grad_sigmas_max_err_over_bound"] <= 1.0
+
+
+def test_sorted_plane_scatter_equals_direct_scatter():
+    """tnf_kplanes_sort + tnf_kplanes_bwd_sorted (coarse scales reduced run by run in each plane's own 2-D order) against
+    tnf_kplanes_bwd (one reduction per sample and corner) on a ~2^18-sample batch: same plane gradients up to fp32
+    summation order; the sort tables are permutations and carry the right coordinates."""
+    from oracle import parity
+    renderer, prov, og, aabb, o, d = parity.kplanes_case(9600)
+    torch.manual_seed(5)
+    packed, info = prov(o, d, training=True)
+    n = packed.size(0)
+    field = renderer.feature_module
+    planes = field._plane_params()
+    stor = [models._channels_last_storage(p) for p in planes]
+    ptrs = (C.c_void_p * 9)(*[t.data_ptr() for t in stor])
+    res = (C.c_int32 * 3)(128, 256, 512)
+    go = torch.randn(n, 96, device=DEV)
+    st = _lib.stream_ptr()
+    lib = _lib.load()
+    direct = [torch.zeros_like(t) for t in stor]
+    _lib.call("tnf_kplanes_bwd", ptrs, (C.c_void_p * 9)(*[t.data_ptr() for t in direct]), res, 3, 32, packed.data_ptr(), 7, n,
+              go.data_ptr(), st)
+    pos = torch.empty(3, n, dtype=torch.int32, device=DEV)
+    uv = torch.empty(3, n, 2, device=DEV)
+    scratch = torch.empty(int(lib.tnf_kplanes_sort_scratch_ints(256, n)), dtype=torch.int32, device=DEV)
+    _lib.call("tnf_kplanes_sort", packed.data_ptr(), 7, n, 256, scratch.data_ptr(), pos.data_ptr(), uv.data_ptr(), st)
+    torch.cuda.synchronize()
+    for o_, (a, b) in enumerate(((0, 1), (0, 2), (1, 2))):
+        assert torch.equal(pos[o_].long().sort().values, torch.arange(n, device=DEV))          # a permutation
+        assert torch.equal(uv[o_][pos[o_].long()], packed[:, [a, b]])                            # slot holds its sample's coordinates
+        cell = ((uv[o_] + 1) * 0.5 * 255).floor().long().clamp(0, 255)
+        key = (((cell[:, 1] >> 1) * 128 + (cell[:, 0] >> 1)) << 2) | ((cell[:, 1] & 1) << 1) | (cell[:, 0] & 1)
+        assert bool((key[1:] >= key[:-1]).all())                                                # slot order is sorted by cell
+    rows = torch.empty(6 * n * 32, device=DEV)
+    for phases in ((0,), (1, 2)):
+        got = [torch.zeros_like(t) for t in stor]
+        gp = (C.c_void_p * 9)(*[t.data_ptr() for t in got])
+        for ph in phases:
+            _lib.call("tnf_kplanes_bwd_sorted", ptrs, gp, res, 3, 32, packed.data_ptr(), 7, n, go.data_ptr(), 2, pos.data_ptr(),
+                      uv.data_ptr(), rows.data_ptr(), ph, st)
+        for i, (a, b) in enumerate(zip(got, direct)):
+            scale = b.abs().max()
+            assert float((a - b).abs().max()) <= 2e-5 * float(scale), (phases, i)
+            assert float((a - b).norm() / b.norm()) <= 2e-6, (phases, i)
+    # and through the trainer (opt-in): a batch drawn by the trainer is tagged, the fused step takes the sorted path
+    import os
+    os.environ["TNF_KPLANES_SORTED"] = "1"
+    try:
+        tr = _trainer(True, seed=13)
+    finally:
+        del os.environ["TNF_KPLANES_SORTED"]
+    batch = tr.next_batch()
+    assert tr._fused.sorted_scales == 2 and tr._fused.sorted_tag(batch[0]) is not None
+    out_a = tr._fused.forward_backward(batch[0], batch[2], batch[1])
+    ga = {k: p.grad.clone() for k, p in tr.renderer.named_parameters()}
+    del batch[0]._tnf_ksort
+    out_b = tr._fused.forward_backward(batch[0], batch[2], batch[1])
+    assert float(out_a["loss"]) == float(out_b["loss"])
+    for k, p in tr.renderer.named_parameters():
+        sc = p.grad.abs().max().clamp_min(1e-12)
+        assert float((ga[k] - p.grad).abs().max()) <= 2e-5 * float(sc), k

@@ -82,6 +82,11 @@ _SIGNATURES = {
                                   C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_void_p]),
     "tnf_kplanes_bwd_scales": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
                                          C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_int32, C.c_int32, C.c_void_p]),
+    "tnf_kplanes_sort_scratch_ints": (C.c_int64, [C.c_int32, C.c_int64]),
+    "tnf_kplanes_sort": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int32, c_i32p, c_i32p, c_f32p, C.c_void_p]),
+    "tnf_kplanes_bwd_sorted": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
+                                         C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_int32, c_i32p, c_f32p, c_f32p,
+                                         C.c_int32, C.c_void_p]),
     "tnf_kplanes_bwd_ex": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
                                      C.c_int32, c_f32p, C.c_int64, C.c_int64, c_f32p, C.c_int32, C.c_void_p]),
     "tnf_marcher_aabb": (C.c_int, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, c_f32p, c_f32p, C.c_int64, C.c_int32,

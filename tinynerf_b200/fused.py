@@ -129,6 +129,13 @@ class FusedKPlanesStep:
         # different resource (TNF_AUX_OVERLAP=0: everything in line): the TV pass (HBM streaming) and the [PE(d)|d] rows
         # (issue-bound sincos) beside the plane gather (L2 -> SM bound); the colour head's output-layer backward (HBM) beside
         # the density branch's weights backward + output-layer backward.
+        # Sorted scatter of the scales below the finest (csrc/kplanes.cu): the batch is counting-sorted per plane orientation
+        # when it is packed (sort_batch, on the prefetch stream) and the coarse scales' plane gradients are reduced run by
+        # run instead of sample by sample.  Same gradients (tests/test_gpu_fused.py) but MEASURED SLOWER than the direct
+        # scatter (profiles/r02_kplanes_sorted.txt: 320 vs 270 us + a 75 us sort), so it is opt-in: TNF_KPLANES_SORTED=1.
+        self.sorted_scales = (self.n_scales - 1) if (os.environ.get("TNF_KPLANES_SORTED", "0") != "0" and self.channels == 32
+                                                     and self.n_scales >= 2) else 0
+        self.sort_res = self.res[self.sorted_scales - 1] if self.sorted_scales else 0
         self.aux_overlap = os.environ.get("TNF_AUX_OVERLAP", "1") != "0"
         self._aux = torch.cuda.Stream(device=self.dev, priority=int(os.environ.get("TNF_AUX_PRIO", "0"))) if self.aux_overlap else None
         self._aux_tv_first = os.environ.get("TNF_AUX_ORDER", "color_first") == "tv_first"
@@ -181,6 +188,29 @@ class FusedKPlanesStep:
             cur.wait_event(self._heads_done)
             self._heads_done = None
 
+    # ---- per-batch sort for the sorted scatter -------------------------------------------------------
+    @torch.no_grad()
+    def sort_batch(self, packed: torch.Tensor) -> None:
+        """Counting-sort the batch per plane orientation (tnf_kplanes_sort) on the current stream and tag `packed` with the
+        result; forward_backward uses the sorted scatter when the tag is present and current."""
+        n = packed.size(0)
+        if not self.sorted_scales or n == 0:
+            return
+        cap = (n + 16383) & ~16383    # quantised like the packed rows (allocator reuse)
+        pos = torch.empty(3 * cap, dtype=torch.int32, device=self.dev)[:3 * n]
+        uv = torch.empty(3 * cap * 2, device=self.dev)[:3 * n * 2]
+        words = int(_lib.load().tnf_kplanes_sort_scratch_ints(self.sort_res, cap))
+        scratch = torch.empty(words, dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.call("tnf_kplanes_sort", packed.data_ptr(), 7, n, self.sort_res, scratch.data_ptr(), pos.data_ptr(), uv.data_ptr(),
+                      _lib.stream_ptr(), nbytes=n * (12 + 3 * 16), extra_kernels=3)
+        packed._tnf_ksort = (pos, uv, packed._version)
+
+    @staticmethod
+    def sorted_tag(packed: torch.Tensor):
+        tag = getattr(packed, "_tnf_ksort", None)
+        return tag if tag is not None and tag[2] == packed._version else None
+
     # ---- workspace ---------------------------------------------------------------------------------
     def _reserve(self, n: int, r: int) -> None:
         if n > self._cap_n:
@@ -200,6 +230,8 @@ class FusedKPlanesStep:
             for i in range(len(self.col_lin) - 1):
                 ws[f"dh{i}"] = e(cap, hid_c)
             ws["rgb"], ws["grgb"] = e(cap, 3), e(cap, 3)
+            if self.sorted_scales:
+                ws["krows"] = e(3 * self.sorted_scales * cap * self.channels)   # per-plane gradient rows in slot order
             self._cap_n = cap
         if r > self._cap_r:
             cap = int(r * 1.25) + 256
@@ -464,6 +496,12 @@ class FusedKPlanesStep:
                 _lib.launch_count += 1
             # plane gradients: scatter-add of the data term on top of the TV gradient written at the start
             work, works = None, []
+            ksort = self.sorted_tag(packed) if self.sorted_scales else None
+            kp_sorted = lambda phase: call(
+                "tnf_kplanes_bwd_sorted", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels, P(packed), 7, n,
+                P(dfeat), self.sorted_scales, P(ksort[0]), P(ksort[1]), P(ws["krows"]), phase, st,
+                label="tnf_kplanes_bwd" + ("" if phase == 0 else f"(phase {phase})"), extra_kernels=1 if phase == 0 else 0,
+                nbytes=(n * (12 + 4 * F) + 2 * self._plane_bytes) if phase != 2 else 0)
             if reduce and self.world > 1 and self.bucket_scales:
                 # data-parallel: finest scale first (76 % of the bytes); its all-reduce starts while the coarser scales are
                 # still being scattered and then runs on under the heads' weight gradients
@@ -487,20 +525,35 @@ class FusedKPlanesStep:
                 if self.peer_overlap:
                     main, comm = torch.cuda.current_stream(self.dev), self._peer_stream
                     fine = self.n_scales - 1
-                    for a, b in ((fine, self.n_scales), (0, fine)):
-                        if a == b:
-                            continue
-                        kp_bwd(a, b)
+                    if ksort is not None and self.sorted_scales == fine:
+                        # phase 1 finishes the finest scale (direct scatter) and stores the coarse scales' rows; the finest
+                        # scale's update then runs beside phase 2 (the run-merging scatter of the coarse scales)
+                        kp_sorted(1)
                         comm.wait_event(main.record_event())
                         with torch.cuda.stream(comm):
-                            upd(self._scale_off[a], self._scale_off[b], comm.cuda_stream)
+                            upd(self._scale_off[fine], self._scale_off[self.n_scales], comm.cuda_stream)
+                        kp_sorted(2)
+                        comm.wait_event(main.record_event())
+                        with torch.cuda.stream(comm):
+                            upd(0, self._scale_off[fine], comm.cuda_stream)
+                    else:
+                        for a, b in ((fine, self.n_scales), (0, fine)):
+                            if a == b:
+                                continue
+                            kp_bwd(a, b)
+                            comm.wait_event(main.record_event())
+                            with torch.cuda.stream(comm):
+                                upd(self._scale_off[a], self._scale_off[b], comm.cuda_stream)
                     planes_done = comm.record_event()
                 else:
-                    kp_bwd(0, self.n_scales)
+                    kp_sorted(0) if ksort is not None else kp_bwd(0, self.n_scales)
                     upd(0, self._plane_grad_end, st)
             else:
-                call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
-                     P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
+                if ksort is not None:
+                    kp_sorted(0)
+                else:
+                    call("tnf_kplanes_bwd", self._plane_ptrs, self._grad_ptrs, self._res_scales, self.n_scales, self.channels,
+                         P(packed), 7, n, P(dfeat), st, nbytes=n * (12 + 4 * F) + 2 * self._plane_bytes)
                 if reduce and self.world > 1:
                     work = dist.all_reduce(self.flat_grad[:self._plane_grad_end], async_op=True)  # runs under the wgrads
             if after_plane_grads is not None and work is None:

@@ -417,6 +417,8 @@ class Trainer:
             info = torch.cat([p[1] for p in parts], 0)
             rgb = torch.cat([p[2] for p in parts], 0)
         tag_partition(info)
+        if self._fused is not None:
+            self._fused.sort_batch(packed)   # per-orientation counting sort for the sorted plane scatter (same stream as the pack)
         return packed, rgb, info
 
     # ---- occupancy update, sharded by depth slice across ranks ----------------------------------
@@ -460,7 +462,8 @@ class Trainer:
         (packed, rgbs, info), done = self._queue.pop(0)
         main = torch.cuda.current_stream(self.device)
         main.wait_event(done)
-        for t in (packed, tagged_steps(packed), rgbs, info):
+        extra = getattr(packed, "_tnf_ksort", None)
+        for t in (packed, tagged_steps(packed), rgbs, info) + (tuple(extra[:2]) if extra else ()):
             t.record_stream(main)
         return packed, rgbs, info
 
