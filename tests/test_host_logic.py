@@ -164,3 +164,24 @@ def test_dp_slices_partition_the_parameter_space():
             assert a == cur and a <= b <= hi and (a - lo) % 4 == 0
             cur = b
         assert cur == hi
+
+
+def test_render_chunk_grouping():
+    """run.group_render_chunks (the host half of Trainer.render): chunks are contiguous, cover every ray block once, stay
+    within the sample capacity unless a single block exceeds it, and empty blocks are carried along."""
+    from tinynerf_b200.run import group_render_chunks
+    counts = [0, 0, 500, 900, 100, 0, 2500, 10, 0, 0, 990, 10, 0]
+    ends, ray_ends, tot = [], [], 0
+    for i, c in enumerate(counts):
+        tot += c
+        ends.append(tot)
+        ray_ends.append(min(2048 * (i + 1), 2048 * len(counts) - 7))
+    chunks = group_render_chunks(ends, ray_ends, 1000)
+    assert chunks[0][0] == 0 and chunks[0][2] == 0 and chunks[-1][1] == ray_ends[-1] and chunks[-1][3] == tot
+    for (a0, a1, s0, s1), (b0, b1, t0, t1) in zip(chunks, chunks[1:]):
+        assert a1 == b0 and s1 == t0 and a0 < a1
+    sizes = [s1 - s0 for _, _, s0, s1 in chunks]
+    assert all(sz <= 1000 or sz == 2500 for sz in sizes) and 2500 in sizes
+    assert sum(sizes) == tot
+    assert group_render_chunks([0], [5], 1000) == [(0, 5, 0, 0)]
+    assert group_render_chunks([], [], 1000) == []

@@ -182,6 +182,20 @@ class RayStore:
         return rows[:, 0:3], rows[:, 3:6], rows[:, 6:9]
 
 
+def group_render_chunks(ends: List[int], ray_ends: List[int], max_samples: int) -> List[Tuple[int, int, int, int]]:
+    """Chunks of a whole-image render (Trainer.render).  `ends[i]` = packed samples of the image up to and including ray
+    block i, `ray_ends[i]` = rays up to and including it.  Consecutive blocks are grouped while the chunk stays within
+    `max_samples` packed samples (a block larger than that is a chunk of its own).  -> [(ray0, ray1, sample0, sample1)]."""
+    out, r0, s0, i = [], 0, 0, 0
+    while i < len(ends):
+        j = i
+        while j + 1 < len(ends) and ends[j + 1] - s0 <= max_samples:
+            j += 1
+        out.append((r0, ray_ends[j], s0, ends[j]))
+        r0, s0, i = ray_ends[j], ends[j], j + 1
+    return out
+
+
 @dataclass
 class TrainConfig:
     """The hot-path subset of the reference's TrainConfig (src/run.py:83-94) + scene description."""
@@ -686,13 +700,7 @@ class Trainer:
             self._render_cap = cap
         pbuf, sbuf = self._render_buf
         bg = self.renderer.bg_color
-        r0 = s0 = 0
-        i = 0
-        while i < len(ends):
-            j = i   # extend the chunk block by block while it fits the buffer
-            while j + 1 < len(ends) and ends[j + 1] - s0 <= max_samples:
-                j += 1
-            r1, s1 = ray_ends[j], ends[j]
+        for r0, r1, s0, s1 in group_render_chunks(ends, ray_ends, max_samples):
             n = s1 - s0
             if n == 0:   # every sample masked: the reference composites nothing, the rays show the background (src/core.py:251-265)
                 out[r0:r1] = 0.0 if bg is None else bg.to(dev).reshape(1, 3)
@@ -702,7 +710,6 @@ class Trainer:
                     self._fused.render(packed, ic, out[r0:r1])
                 else:
                     out[r0:r1] = self.renderer(packed, ic)
-            r0, s0, i = r1, s1, j + 1
         return out
 
 
