@@ -136,7 +136,9 @@ class FusedKPlanesStep:
         self.sorted_scales = (self.n_scales - 1) if (os.environ.get("TNF_KPLANES_SORTED", "0") != "0" and self.channels == 32
                                                      and self.n_scales >= 2) else 0
         self.sort_res = self.res[self.sorted_scales - 1] if self.sorted_scales else 0
-        self.aux_overlap = os.environ.get("TNF_AUX_OVERLAP", "1") != "0"
+        # Single GPU only by default: in data-parallel runs the update kernels already share the SMs with the step, and the
+        # extra concurrency costs more than it hides (8 GPUs: 1.355 ms without, 1.40-1.45 ms with; 1 GPU: 1.303 -> 1.268 ms).
+        self.aux_overlap = os.environ.get("TNF_AUX_OVERLAP", "1" if world == 1 else "0") != "0"
         self._aux = torch.cuda.Stream(device=self.dev, priority=int(os.environ.get("TNF_AUX_PRIO", "0"))) if self.aux_overlap else None
         self._aux_tv_first = os.environ.get("TNF_AUX_ORDER", "color_first") == "tv_first"
         self._closs_scratch = torch.zeros(2, dtype=torch.float64, device=self.dev)   # tnf_composite_loss_fwd_bwd (zero between calls)
