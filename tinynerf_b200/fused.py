@@ -324,8 +324,9 @@ class FusedKPlanesStep:
         gradients are all-reduced over the ranks (sum) before returning, overlapped with the tail of backward.
         peer_step = {"step", "lr", "betas", "eps", "weight_decay"} (peer_update mode): the union batch's ray count comes
         from the peers' slot tables and the optimiser update of iteration `step` (1-based) happens in here -- the planes'
-        right after their gradients are complete, the heads' after the weight gradients -- so on return the parameters
-        already hold the new values on every rank and p.grad holds this rank's un-reduced gradients."""
+        right after their gradients are complete, the heads' after the weight gradients, on a side stream.  On return the
+        updates are enqueued, not joined: whoever reads the parameters next on another stream calls wait_updates() first (the
+        next forward_backward, density() and render() do); p.grad holds this rank's un-reduced gradients."""
         _lib.require_cuda(packed, "packed_samples")
         n, r = packed.size(0), info.size(0)
         if n == 0 or r == 0:
