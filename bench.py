@@ -551,6 +551,8 @@ def train_workload(ctx: Ctx, name: str, steps: int, warmup: int, e2e_arm: bool, 
             per.append(time.perf_counter())
         if read_loss:
             losses.append(tr.read_loss())   # the latest iteration's loss: inside the timed region
+        if getattr(tr, "_fused", None) is not None:
+            tr._fused.wait_updates()        # data-parallel: the last iteration's parameter updates (side stream) end inside the window
         e.record()
         host_ms.append((time.perf_counter() - h0) * 1e3 / k)  # host time per step (includes the batch-size sync)
         raw = [b - a for a, b in zip([h0] + per[:-1], per)]
