@@ -297,8 +297,6 @@ class Trainer:
                         self.optimizer.state[p] = {"step": 0, "exp_avg": view(peer.exp_avg), "exp_avg_sq": view(peer.exp_avg_sq)}
                         off += (p.numel() + 3) // 4 * 4
         self._chunks_guess = 0.0
-        if self.device.type == "cuda":
-            self._prewarm_allocator()
         if world > 1 and self.device.type == "cuda":
             self._warm_collectives()
         # The coming batches are marched on a HIGH-PRIORITY stream: their short kernels are then not queued behind the main
@@ -306,6 +304,8 @@ class Trainer:
         # 188.6 -> 192.0 M, and a much tighter per-step distribution; TNF_SIDE_PRIORITY=0 restores equal priorities)
         prio = -1 if os.environ.get("TNF_SIDE_PRIORITY", "1") == "1" else 0
         self._side = torch.cuda.Stream(device=self.device, priority=prio) if (cfg.prefetch and self.device.type == "cuda") else None
+        if self.device.type == "cuda":
+            self._prewarm_allocator()
         self.post_update = None         # optional callable(trainer) run right after every occupancy update
         self._gc_frozen = False
         self._queue: List = []          # prefetched (batch, done event), oldest first
@@ -325,8 +325,16 @@ class Trainer:
         Free 64 MB blocks are split on demand instead."""
         if os.environ.get("TNF_PREWARM_ALLOCATOR", "1") == "0":
             return
-        hold = [torch.empty(mb << 20, dtype=torch.uint8, device=self.device) for _ in range(blocks)]
-        del hold
+        # The allocator keeps separate free lists PER STREAM: the batches are allocated on the prefetch stream, the
+        # iteration's temporaries on the main stream -- both get their own reserve.  Large blocks (split on demand) and the
+        # SMALL pool (requests < 1 MB are carved out of 2 MB segments: ray indices, packing info, bitfields, counters): a new
+        # 2 MB segment in the middle of a run was measured to stall one step for 82 ms.
+        side = getattr(self, "_side", None)
+        for stream in ([torch.cuda.current_stream(self.device)] + ([side] if side is not None else [])):
+            with torch.cuda.stream(stream):
+                hold = [torch.empty(mb << 20, dtype=torch.uint8, device=self.device) for _ in range(blocks if stream is not side else blocks // 2)]
+                hold += [torch.empty(512 << 10, dtype=torch.uint8, device=self.device) for _ in range(128)]
+                del hold
 
     def _warm_collectives(self) -> None:
         """Run every collective of an iteration once at its real size (gradient all-reduce, ray-count all-reduce,
@@ -505,7 +513,9 @@ class Trainer:
             if self._side is not None:
                 self._grid_event = torch.cuda.current_stream(self.device).record_event()
         if self._fused is not None:
-            return self._step_fused(packed, rgbs, info)
+            out = self._step_fused(packed, rgbs, info)
+            self._after_first_steps()
+            return out
         rendered = self.renderer(packed, info)
         loss = dp_mse(rendered, rgbs, global_ray_count(info.size(0), self.device, self.world))
         tv_direct = 0.0
@@ -661,6 +671,12 @@ class Trainer:
             self._prefetch()
         self.last = {"loss": out["loss"], "n_samples": packed.size(0), "n_rays": info.size(0)}
         return self.last
+
+    def _after_first_steps(self) -> None:
+        """The iteration's workspaces are allocated lazily by the first steps and split the pre-warmed blocks; top the
+        allocator's free lists up again once they exist (steps 1 and 3, and after the first occupancy update)."""
+        if self.device.type == "cuda" and self.train_step in (1, 3, self.occupancy_grid_updates + 1):
+            self._prewarm_allocator()
 
     # ---- render half of the path (src/run.py:15-50, without image IO) ---------------------------
     @torch.no_grad()
