@@ -144,3 +144,29 @@ def test_host_resident_ray_store_hands_out_the_same_batches():
             assert x.is_cuda and torch.equal(x, y)
         assert torch.equal(torch.cat(ra, -1).cpu(), table[a.last_indices])
     assert b.h2d_bytes == (1024 + 3 * 1024 + 1 + 40_000 + 30_000) * 44 and a.h2d_bytes == 0
+
+
+@pytest.mark.parametrize("scene", ["aabb", "unbounded"])
+def test_render_edge_cases(scene):
+    """Trainer.render: rays that miss the scene show the background (every chunk empty: src/core.py:251-265 composites
+    nothing), a ray count that is not a multiple of the block size, a sample capacity smaller than one block, no rays."""
+    torch.manual_seed(2)
+    tr = Trainer(TrainConfig(method="kplanes", scene_type=scene, batch_size=256, n_samples=64, scene_scale=1.3, seed=2), _store(), DEV)
+    og = tr.occupancy_grid
+    if scene == "aabb":
+        o = torch.tensor([[4.0, 0.0, 0.0]]).repeat(1000, 1)
+        d = torch.tensor([[1.0, 0.0, 0.0]]).repeat(1000, 1)          # pointing away from the box
+        img = tr.render(o, d, batch_size=300)
+        assert torch.equal(img, torch.ones(1000, 3, device=DEV))
+    og.grid.zero_()                                                     # nothing is occupied anywhere
+    og.grid += 1e-6
+    og.mean = 0.5
+    o, d = synthetic.blender_rays(777, seed=9, radius=4.0311 if scene == "aabb" else 1.2)
+    assert torch.equal(tr.render(o, d, batch_size=100), torch.ones(777, 3, device=DEV))
+    og.grid.fill_(1.0)
+    og.mean = 1.0
+    a = tr.render(o, d, batch_size=100, max_samples=1 << 20)
+    b = tr.render(o, d, batch_size=333, max_samples=10)              # capacity below one block: one block per chunk
+    assert a.shape == (777, 3) and torch.isfinite(a).all()
+    assert bool(((a - b).abs() <= 1e-6 + 1e-6 * a.abs()).all())
+    assert tr.render(o[:0], d[:0]).shape == (0, 3)
