@@ -22,7 +22,7 @@ def check(got, want64, scale64, rtol=1e-5):
 
 
 @pytest.mark.parametrize("m,k,n", [(1000, 96, 64), (300, 147, 64), (257, 64, 64), (4096, 36, 128), (129, 128, 128), (1, 96, 64),
-                                   (70000, 96, 64)])
+                                   (70000, 96, 64), (70001, 128, 128), (1, 128, 128)])
 @pytest.mark.parametrize("relu", [False, True])
 def test_linear_forward(m, k, n, relu):
     g = torch.Generator().manual_seed(m + k)
@@ -40,7 +40,8 @@ def test_linear_forward(m, k, n, relu):
 # the large cases give every CTA several tiles: operand rings wrap, both tensor-memory A sets of the 64-wide weight-gradient
 # kernel are reused (K = 148 has room for one set only), K <= 32 shortens its load-ahead distance
 @pytest.mark.parametrize("m,k,n", [(1000, 96, 64), (300, 147, 64), (513, 64, 64), (2048, 36, 128), (129, 128, 128),
-                                   (200000, 64, 64), (70001, 96, 64), (90000, 148, 64), (50000, 20, 64), (60000, 64, 128)])
+                                   (200000, 64, 64), (70001, 96, 64), (90000, 148, 64), (50000, 20, 64), (60000, 64, 128),
+                                   (70001, 128, 128), (127, 128, 128)])
 def test_linear_dgrad_and_wgrad(m, k, n):
     g = torch.Generator().manual_seed(m * 3 + k)
     x = torch.randn(m, k, generator=g).relu().to(DEV)   # an activation: some entries are exactly 0
@@ -59,6 +60,49 @@ def test_linear_dgrad_and_wgrad(m, k, n):
     check(dx[:, :k], want_dx, dy.double().abs() @ w.double().abs())
     check(gw, dy.double().t() @ x.double(), dy.double().abs().t() @ x.double().abs())
     check(gb, dy.double().sum(0), dy.double().abs().sum(0))
+
+
+@pytest.mark.parametrize("m", [300, 40000])
+def test_weight_stationary_128_layers_vs_resident_kernel(m):
+    """128 x 128 layers run with the weights stationary in tensor memory (csrc/wstat.cu); the shared-memory-resident
+    linear_kernel (variant 3 = 1) is the same 3xTF32 computation: results agree to fp32 rounding of the accumulation order,
+    also without bias / mask and with padded leading dimensions."""
+    g = torch.Generator().manual_seed(m)
+    ldx, ldy = 132, 136
+    xbuf = torch.full((m, ldx), float("nan"))
+    xbuf[:, :128] = torch.randn(m, 128, generator=g).relu()
+    w = (torch.randn(128, 128, generator=g) / 128 ** 0.5)
+    b = torch.randn(128, generator=g)
+    xbuf, w, b = xbuf.to(DEV), w.to(DEV), b.to(DEV)
+    x = xbuf[:, :128]
+    lib = _lib.load()
+    outs = {}
+    for variant in (0, 1):
+        lib.tnf_set_variant(3, variant)
+        try:
+            y = torch.full((m, ldy), float("nan"), device=DEV)
+            dx = torch.full((m, ldy), float("nan"), device=DEV)
+            dx0 = torch.full((m, ldy), float("nan"), device=DEV)
+            with torch.cuda.device(0):
+                _lib.call("tnf_linear_fwd", x.data_ptr(), ldx, w.data_ptr(), None, y.data_ptr(), ldy, m, 128, 128, 0, None, None, None, 0, 0,
+                          _lib.stream_ptr())
+                _lib.call("tnf_linear_bwd_data", x.data_ptr(), ldx, w.data_ptr(), dx.data_ptr(), ldy, x.data_ptr(), ldx, m, 128, 128,
+                          _lib.stream_ptr())
+                _lib.call("tnf_linear_bwd_data", x.data_ptr(), ldx, w.data_ptr(), dx0.data_ptr(), ldy, None, 0, m, 128, 128,
+                          _lib.stream_ptr())
+            outs[variant] = (y, dx, dx0)
+        finally:
+            lib.tnf_set_variant(3, 0)
+    x64, w64 = x.double(), w.double()
+    scale_f = x64.abs() @ w64.abs().t()
+    scale_b = x64.abs() @ w64.abs()
+    for variant in (0, 1):
+        y, dx, dx0 = outs[variant]
+        assert torch.isnan(y[:, 128:]).all() and torch.isnan(dx[:, 128:]).all()   # nothing written outside the 128 columns
+        check(y[:, :128], x64 @ w64.t(), scale_f)
+        check(dx[:, :128], (x64 @ w64) * (x > 0), scale_b)
+        check(dx0[:, :128], x64 @ w64, scale_b)
+    assert torch.equal(outs[0][1][:, :128] == 0, outs[1][1][:, :128] == 0)   # identical ReLU masks
 
 
 @pytest.mark.parametrize("m,ka,kb", [(1000, 51, 96), (70001, 51, 96), (300, 20, 33), (40000, 64, 64)])

@@ -45,8 +45,16 @@ int sm_count();  // cached per device
 constexpr int kVariantWgradSS = 0;   // 1: both-operands-in-shared-memory weight-gradient kernel
 constexpr int kVariantTvTexel = 1;   // 1: one-thread-per-texel TV kernel
 constexpr int kVariantKplanesOcc = 2; // K-Planes lookup kernels built for another occupancy (value = blocks per SM, 1 = uncapped; 0 = default)
+constexpr int kVariantNoWstat = 3;    // 1: 128x128 layers through linear_kernel (weights in shared memory) instead of the weight-stationary kernel
 constexpr int kVariantCount = 4;
 int variant(int which);
+
+// 128 x 128 layers with the weights stationary in tensor memory (wstat.cu); mode 0 = forward (bias, optional ReLU),
+// 1 = data gradient (optional ReLU mask of the producing layer)
+bool wstat_linear_supported(int64_t m, int n, int k, const void* x, int64_t ldx, const void* w, const void* y, int64_t ldy,
+                            const void* mask, int64_t ldmask);
+int launch_wstat_linear(int mode, const float* x, int64_t ldx, const float* w, const float* bias, int relu, const float* mask,
+                        int64_t ldmask, float* y, int64_t ldy, int64_t m, cudaStream_t st);
 
 // Function attributes (cudaFuncSetAttribute) belong to the device/context, not to the calling thread: a call site keeps one
 // flag per device and opts in again the first time it runs on another GPU of the process.  The flag is set after the
