@@ -1,4 +1,5 @@
-"""Where the HOST time of a training iteration goes (cProfile over N steps of the bench workload)."""
+"""Where the HOST time of a training iteration goes (cProfile over N steps of the bench workload).
+`python scripts/host_profile.py [kplanes|cobafa|vanilla]`"""
 import cProfile
 import pstats
 import sys
@@ -12,7 +13,8 @@ from tinynerf_b200.run import RayStore, TrainConfig, Trainer
 
 dev = torch.device("cuda", 0)
 o, d, rgbs, _ = bench.make_scene("blender", 1 << 20, bench.SEED)
-cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=1024, n_samples=256, seed=1)
+method = sys.argv[1] if len(sys.argv) > 1 else "kplanes"
+cfg = TrainConfig(method=method, scene_type="aabb", batch_size=1024, n_samples=256, seed=1)
 tr = Trainer(cfg, RayStore(o, d, rgbs, dev, seed=1), dev)
 tr.occupancy_grid.grid.copy_(synthetic.analytic_grid(128, seed=bench.SEED + 2).to(dev))
 tr.occupancy_grid.mean = tr.occupancy_grid.grid.mean().item()

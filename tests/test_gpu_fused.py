@@ -11,11 +11,11 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _trainer(fused_step, seed=9, **kw):
+def _trainer(fused_step, seed=9, method="kplanes", **kw):
     from tinynerf_b200.run import RayStore, TrainConfig, Trainer
     o, d = synthetic.blender_rays(1 << 15, seed=3)
     rgb = torch.rand(1 << 15, 3, generator=torch.Generator().manual_seed(4))
-    cfg = TrainConfig(method="kplanes", scene_type="aabb", batch_size=256, n_samples=128, fused_tv_grad=False,
+    cfg = TrainConfig(method=method, scene_type="aabb", batch_size=256, n_samples=128, fused_tv_grad=False,
                       prefetch=False, fused_step=fused_step, **kw)
     torch.manual_seed(seed)
     tr = Trainer(cfg, RayStore(o, d, rgb, DEV, seed=1), DEV)
@@ -48,6 +48,47 @@ def test_fused_step_matches_autograd_step():
         err = (a - b).abs()
         assert err.max() <= 1e-3 * scale, k
         assert float((err > 1e-5 * scale).float().mean()) <= (1e-3 if a.numel() > 100000 else 0.1), k
+
+
+def test_fused_cobafa_step_matches_autograd_step():
+    """fused_cobafa.FusedCobafaStep against the module/autograd path on the same batch and the same generator state (the
+    Dropout(0.01) mask is drawn by the same kernel from the same stream in both): loss and every gradient, same bars as the
+    K-Planes test above."""
+    res = {}
+    for fused in (False, True):
+        tr = _trainer(fused, method="cobafa")
+        assert (tr._fused_cobafa is not None) == fused and tr._fused is None
+        tr.optimizer.step = lambda *a, **k: None  # keep this step's gradients for inspection
+        torch.manual_seed(10)
+        info = tr.step()
+        res[fused] = ({k: p.grad.clone() for k, p in tr.renderer.named_parameters()}, float(info["loss"]), info["n_samples"])
+        tr.close()
+    assert res[True][2] == res[False][2] > 0
+    assert res[True][1] == pytest.approx(res[False][1], rel=2e-6)
+    for k, b in res[False][0].items():
+        a = res[True][0][k]
+        assert a.shape == b.shape and a.stride() == b.stride(), k
+        scale = b.abs().max().clamp_min(1e-12)
+        err = (a - b).abs()
+        assert err.max() <= 1e-3 * scale, (k, float(err.max() / scale))
+        assert float((err > 1e-5 * scale).float().mean()) <= (1e-3 if a.numel() > 100000 else 0.1), k
+
+
+def test_fused_cobafa_training_runs_and_learns():
+    """A few full iterations (Adam, scheduler, an occupancy update through the modules in between): finite, decreasing loss,
+    and the fused step survives optimizer.zero_grad() and a workspace re-allocation."""
+    tr = _trainer(True, seed=12, method="cobafa")
+    tr.train_step = 0   # include the occupancy update of iteration 0 (module path's sigma_fn)
+    losses = []
+    for it in range(6):
+        torch.manual_seed(200 + it)
+        losses.append(float(tr.step()["loss"]))
+        if it == 2:
+            tr.optimizer.zero_grad()
+            tr._fused_cobafa._cap_n = tr._fused_cobafa._cap_r = 0
+    assert all(l == l and l < 1e3 for l in losses)
+    assert losses[-1] < losses[0]
+    tr.close()
 
 
 def test_fused_training_trajectory_matches_autograd():

@@ -231,7 +231,20 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device=None) -> int:
+    """cudaStream_t of torch's current stream on `device` (default: the current device).  The raw accessor costs ~0.3 us,
+    torch.cuda.current_stream() ~18 us (measured under the module path: 25 calls = 0.45 ms of host time per iteration)."""
+    if _raw_stream is not None:
+        if device is None:
+            idx = torch.cuda.current_device()
+        else:
+            idx = device.index if isinstance(device, torch.device) else (device if isinstance(device, int) else torch.device(device).index)
+            if idx is None:
+                idx = torch.cuda.current_device()
+        return _raw_stream(idx)
     return torch.cuda.current_stream(device).cuda_stream
 
 

@@ -49,11 +49,11 @@ constexpr int kVariantNoWstat = 3;    // 1: 128x128 layers through linear_kernel
 constexpr int kVariantCount = 4;
 int variant(int which);
 
-// 128 x 128 layers with the weights stationary in tensor memory (wstat.cu); mode 0 = forward (bias, optional ReLU),
-// 1 = data gradient (optional ReLU mask of the producing layer)
-bool wstat_linear_supported(int64_t m, int n, int k, const void* x, int64_t ldx, const void* w, const void* y, int64_t ldy,
+// Layers with 128 outputs and <= 128 inputs with the weights stationary in tensor memory (wstat.cu); mode 0 = forward
+// (x [m,k] -> y [m,128], bias, optional ReLU), 1 = data gradient (x = dy [m,128] -> y = dx [m,k], optional ReLU mask [m,k])
+bool wstat_linear_supported(int mode, int64_t m, int n, int k, const void* x, int64_t ldx, const void* w, const void* y, int64_t ldy,
                             const void* mask, int64_t ldmask);
-int launch_wstat_linear(int mode, const float* x, int64_t ldx, const float* w, const float* bias, int relu, const float* mask,
+int launch_wstat_linear(int mode, const float* x, int64_t ldx, const float* w, int k, const float* bias, int relu, const float* mask,
                         int64_t ldmask, float* y, int64_t ldy, int64_t m, cudaStream_t st);
 
 // Function attributes (cudaFuncSetAttribute) belong to the device/context, not to the calling thread: a call site keeps one

@@ -1068,8 +1068,8 @@ extern "C" int tnf_linear_fwd(const float* x, int64_t ldx, const float* weight, 
   TNF_REQUIRE(n % 32 == 0, "forward needs out_features to be a multiple of 32");
   TNF_REQUIRE(al16(x) && ldx % 4 == 0 && (!y || (al16(y) && ldy % 4 == 0)), "x/y must be 16-byte aligned with ld %% 4 == 0");
   TNF_REQUIRE(n_head >= 0 && n_head <= 4 && (n_head == 0 || (head_w && head_b && head_out)), "bad head");
-  if (n_head == 0 && !variant(kVariantNoWstat) && wstat_linear_supported(m, n, k, x, ldx, weight, y, ldy, nullptr, 0))
-    return launch_wstat_linear(0, x, ldx, weight, bias, relu, nullptr, 0, y, ldy, m, static_cast<cudaStream_t>(stream));
+  if (n_head == 0 && !variant(kVariantNoWstat) && wstat_linear_supported(0, m, n, k, x, ldx, weight, y, ldy, nullptr, 0))
+    return launch_wstat_linear(0, x, ldx, weight, k, bias, relu, nullptr, 0, y, ldy, m, static_cast<cudaStream_t>(stream));
   LinArgs A{};
   A.X = x; A.ldx = ldx; A.W = weight; A.bias = bias; A.Y = y; A.ldy = ldy; A.M = m; A.N = n; A.K = k; A.relu = relu;
   A.head_w = head_w; A.head_b = head_b; A.head_out = head_out; A.n_head = n_head; A.head_act = head_act;
@@ -1086,8 +1086,8 @@ extern "C" int tnf_linear_bwd_data(const float* dy, int64_t lddy, const float* w
   TNF_REQUIRE(n % 32 == 0, "dgrad needs out_features to be a multiple of 32");
   TNF_REQUIRE(al16(dy) && lddy % 4 == 0 && al16(dx) && lddx % 4 == 0, "dy/dx must be 16-byte aligned with ld %% 4 == 0");
   TNF_REQUIRE(!relu_src || (al16(relu_src) && ldrs % 4 == 0), "relu_src must be 16-byte aligned with ld %% 4 == 0");
-  if (!variant(kVariantNoWstat) && wstat_linear_supported(m, n, k, dy, lddy, weight, dx, lddx, relu_src, ldrs))
-    return launch_wstat_linear(1, dy, lddy, weight, nullptr, 0, relu_src, ldrs, dx, lddx, m, static_cast<cudaStream_t>(stream));
+  if (!variant(kVariantNoWstat) && wstat_linear_supported(1, m, n, k, dy, lddy, weight, dx, lddx, relu_src, ldrs))
+    return launch_wstat_linear(1, dy, lddy, weight, k, nullptr, 0, relu_src, ldrs, dx, lddx, m, static_cast<cudaStream_t>(stream));
   LinArgs A{};
   A.X = dy; A.ldx = lddy; A.W = weight; A.Y = dx; A.ldy = lddx; A.X2 = relu_src; A.ldx2 = ldrs; A.M = m; A.N = n; A.K = k;
   A.n_tiles = (int)ceil_div(m, 128);

@@ -1,5 +1,5 @@
-// a14 (Cobafa trunk, src/models.py:7-28 MLP(36,128,5)) -- 128 x 128 dense layers, forward and data gradient, with the
-// WEIGHTS STATIONARY IN TENSOR MEMORY.
+// a14 (Cobafa trunk, src/models.py:7-28 MLP(36,128,5)) -- dense layers with 128 outputs and up to 128 inputs (36 -> 128 and
+// 128 -> 128 in the trunk), forward and data gradient, with the WEIGHTS STATIONARY IN TENSOR MEMORY.
 //
 // linear_kernel (mlp.cu) keeps the hi/lo tf32 images of W resident in shared memory.  For a 128 x 128 layer that is 128 KB of
 // the SM's 227 KB: three 16 KB slots are left for the operand rings, i.e. ONE atom of global loads in flight per SM, and the
@@ -33,14 +33,13 @@ constexpr int kSTmaWarp = kSLoWarps + 9;
 constexpr int kSThreads = (kSLoWarps + 10) * 32;
 constexpr int kSH = 8, kSL = 3;                     // hi (TMA) slots, lo slots (forward)
 constexpr int kSHm = 6;                             // hi slots of the data gradient: four more 16 KB slots hold the tile's ReLU-mask atoms
-constexpr int kSDim = 128;                          // layer width (in == out == 128)
-constexpr int kSAtoms = kSDim / 32;                 // contraction atoms per tile
+constexpr int kSDim = 128;                          // out_features (= TMEM lanes of the forward's A operand); in_features <= 128
 
 struct WStatArgs {
-  const float* W;                // [128,128] row-major (nn.Linear.weight: [out, in])
+  const float* W; int K;         // [128,K] row-major (nn.Linear.weight: [out, in]), K = in_features <= 128
   const float* bias;             // fwd: [128] or null
   const float* mask; long long ldmask;   // dgrad: activation whose > 0 gates dX (or null)
-  float* Y; long long ldy;       // fwd: Y [M,128]; dgrad: dX [M,128]
+  float* Y; long long ldy;       // fwd: Y [M,128]; dgrad: dX [M,K]
   long long M; int n_tiles;
   int relu;
 };
@@ -59,7 +58,10 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
   uint8_t* m_ring = lo_ring + kSL * kAtomBytes;       // dgrad: mask atom q (features 32 q .. 32 q + 31) of the tile in flight
   const bool masked = (MODE == 1) && A.mask != nullptr;
   const int T = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
-  const int n_items = T * kSAtoms;
+  const int K = A.K;
+  const int atoms = (MODE == 0) ? (K + 31) >> 5 : kSDim / 32;   // contraction atoms per tile: in_features (fwd) / the 128 outputs (dgrad)
+  const int lanes = (MODE == 0) ? kSDim : K;                    // valid rows of the A operand = features of the result
+  const int n_items = T * atoms;
 
   if (tid == 0) {
     for (int i = 0; i < H; ++i) { mbar_init(&s_hfull[i], 1); mbar_init(&s_hempty[i], 1); }
@@ -83,17 +85,24 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
 #pragma unroll 1
     for (int ch = 2 * g; ch < 2 * g + 2; ++ch) {
+      if (ch >= atoms) break;                 // columns the MMAs never read
       const int c0 = 32 * ch;
       float v[32];
-      if (MODE == 0) {   // A[a][k] = W[a][k]: the thread's own row, 16-byte loads
+      if (MODE == 0) {   // A[a][k] = W[a][k] (zero for k >= K): the thread's own row
+        if ((K & 3) == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(A.W + (long long)a * kSDim + c0 + i));
-          v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+          for (int i = 0; i < 32; i += 4) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + i < K) t = __ldg(reinterpret_cast<const float4*>(A.W + (long long)a * K + c0 + i));
+            v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = (c0 + i < K) ? __ldg(A.W + (long long)a * K + c0 + i) : 0.f;
         }
-      } else {           // A[a][f] = W[f][a]: column a, coalesced across the warp
+      } else {           // A[a][f] = W[f][a] (zero rows for a >= K): column a, coalesced across the warp
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __ldg(A.W + (long long)(c0 + i) * kSDim + a);
+        for (int i = 0; i < 32; ++i) v[i] = (a < K) ? __ldg(A.W + (long long)(c0 + i) * K + a) : 0.f;
       }
       tmem_st32(tm_whi + lane_off + c0, v);   // the tensor core truncates: the fp32 value is the hi operand
 #pragma unroll
@@ -107,14 +116,14 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
   tc_fence_after();
 
   if (warp == kSTmaWarp) {
-    // ===== TMA producer: the sample tiles, 4 atoms (32 contraction indices each) per tile =====
+    // ===== TMA producer: the sample tiles, `atoms` atoms (32 contraction indices each; columns beyond the matrix arrive as zeros) =====
     if (lane == 0) {
       tma_prefetch_desc(&tm_x);
       if (masked) tma_prefetch_desc(&tm_m);
       // mask atoms of tile tt: slot q is free once the 64 epilogue threads of lane quarter q have read tile tt-1's
       auto issue_mask = [&](int tt) {
         const int row0 = (blockIdx.x + tt * gridDim.x) * 128;
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; 32 * q < K; ++q) {   // quarters without a valid feature neither wait for nor release a mask atom
           mbar_wait(&s_mempty[q], (tt & 1) ^ 1);
           mbar_expect_tx(&s_mfull[q], kAtomBytes);
           tma_load_2d(m_ring + q * kAtomBytes, &tm_m, 32 * q, row0, &s_mfull[q]);
@@ -122,8 +131,8 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
       };
       for (int tl = 0; tl < T; ++tl) {
         const int row0 = (blockIdx.x + tl * gridDim.x) * 128;
-        for (int j = 0; j < kSAtoms; ++j) {
-          const int it = tl * kSAtoms + j, h = it % H;
+        for (int j = 0; j < atoms; ++j) {
+          const int it = tl * atoms + j, h = it % H;
           mbar_wait(&s_hempty[h], ((it / H) & 1) ^ 1);
           mbar_expect_tx(&s_hfull[h], kAtomBytes);
           tma_load_2d(hi_ring + h * kAtomBytes, &tm_x, 32 * j, row0, &s_hfull[h]);
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
     // ===== MMA issuer: per atom 3 x 4 MMAs (M = 128 features, N = 128 samples, K = 8), A from tensor memory =====
     const uint32_t idesc = instr_desc(128, 128, false, false);
     for (int it = 0; it < n_items; ++it) {
-      const int h = it % H, l = it % kSL, j = it % kSAtoms, tl = it / kSAtoms, b = tl & 1;
+      const int h = it % H, l = it % kSL, j = it % atoms, tl = it / atoms, b = tl & 1;
       if (j == 0) mbar_wait(&s_tempty[b], ((tl >> 1) & 1) ^ 1);   // the epilogue has drained accumulator b
       mbar_wait(&s_afull[l], (it / kSL) & 1);                     // hi landed (the lo pass saw it) and lo written
       tc_fence_after();
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
           if (pass == 1) mma_commit(&s_lempty[l]);    // the lo slot is free once its only pass has read it
         }
         mma_commit(&s_hempty[h]);
-        if (j == kSAtoms - 1) mma_commit(&s_tfull[b]);
+        if (j == atoms - 1) mma_commit(&s_tfull[b]);
       }
       __syncwarp();
     }
@@ -174,13 +183,15 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
     const int a = q4 * 32 + lane;                       // output feature of this thread
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float bias = (MODE == 0 && A.bias) ? __ldg(A.bias + a) : 0.f;
+    const bool quarter_live = 32 * q4 < lanes;          // warp-uniform: this lane quarter holds valid features
+    const bool feat_ok = a < lanes;
     for (int tl = 0; tl < T; ++tl) {
       const int b = tl & 1;
       const long long row0 = (long long)(blockIdx.x + tl * gridDim.x) * 128 + 64 * g;   // first sample row of this thread's columns
       // ReLU mask of this thread's 64 outputs as two bit words, from the quarter's mask atom in shared memory (row = sample,
       // 128-byte swizzle: the 32 lanes of a warp read the 32 features of one row, conflict-free)
       unsigned mbits[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-      if (masked) {
+      if (masked && quarter_live) {
         mbar_wait(&s_mfull[q4], tl & 1);
         // 32-bit shared addresses: thread constant (atom, sample half, lane's 16-byte chunk and word) XOR the row's swizzle term
         const uint32_t mbase = smem_u32(m_ring + q4 * kAtomBytes) + (uint32_t)(64 * g) * 128u + ((lane >> 2) << 4) + ((lane & 3) << 2);
@@ -199,6 +210,11 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
       }
       mbar_wait(&s_tfull[b], (tl >> 1) & 1);
       tc_fence_after();
+      if (!quarter_live) {   // nothing to read or store (dgrad of a narrow input): just hand the accumulator back
+        tc_fence_before();
+        mbar_arrive(&s_tempty[b]);
+        continue;
+      }
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         float v[32];
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
           } else {
             y = ((mbits[ch] >> i) & 1u) ? y : 0.f;
           }
-          if (row0 + 32 * ch + i < A.M) yp[(long long)i * A.ldy] = y;   // 32 lanes = 32 consecutive features of one row
+          if (feat_ok && row0 + 32 * ch + i < A.M) yp[(long long)i * A.ldy] = y;   // lanes = consecutive features of one row
         }
       }
     }
@@ -227,8 +243,8 @@ __global__ void __launch_bounds__(kSThreads, 1) wstat_linear_kernel(const WStatA
 typedef CUresult (*EncodeTiledFnS)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-// row-major fp32 [rows, 128] with leading dimension ld -> 32 x 128 boxes in the 128-byte swizzle (rows beyond the end read 0)
-int make_atom_map_s(CUtensorMap* map, const float* base, int64_t rows, int64_t ld) {
+// row-major fp32 [rows, cols] with leading dimension ld -> 32 x 128 boxes in the 128-byte swizzle (outside the matrix reads 0)
+int make_atom_map_s(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
   static EncodeTiledFnS encode = [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -236,7 +252,7 @@ int make_atom_map_s(CUtensorMap* map, const float* base, int64_t rows, int64_t l
     return reinterpret_cast<EncodeTiledFnS>(fn);
   }();
   TNF_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[2] = {(cuuint64_t)kSDim, (cuuint64_t)rows};
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   const cuuint32_t box[2] = {32, 128};
   const cuuint32_t estr[2] = {1, 1};
@@ -249,23 +265,25 @@ int make_atom_map_s(CUtensorMap* map, const float* base, int64_t rows, int64_t l
 
 }  // namespace
 
-bool wstat_linear_supported(int64_t m, int n, int k, const void* x, int64_t ldx, const void* w, const void* y, int64_t ldy,
+// fwd: x [m,k], y [m,128]; dgrad: x = dy [m,128], y = dx [m,k], mask [m,k]
+bool wstat_linear_supported(int mode, int64_t m, int n, int k, const void* x, int64_t ldx, const void* w, const void* y, int64_t ldy,
                             const void* mask, int64_t ldmask) {
-  const bool mask_ok = !mask || (ldmask % 4 == 0 && ldmask >= kSDim && (reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
-  return n == kSDim && k == kSDim && m > 0 && m < (1LL << 31) - 256 && x && w && y && ldx % 4 == 0 && ldx >= kSDim && ldy >= kSDim &&
-         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15u) == 0 && mask_ok;
+  const int x_cols = mode == 0 ? k : kSDim, y_cols = mode == 0 ? kSDim : k;
+  const bool mask_ok = !mask || (ldmask % 4 == 0 && ldmask >= k && (reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
+  return n == kSDim && k >= 1 && k <= kSDim && m > 0 && m < (1LL << 31) - 256 && x && w && y && ldx % 4 == 0 && ldx >= x_cols &&
+         ldy >= y_cols && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15u) == 0 && mask_ok;
 }
 
-int launch_wstat_linear(int mode, const float* x, int64_t ldx, const float* w, const float* bias, int relu, const float* mask,
+int launch_wstat_linear(int mode, const float* x, int64_t ldx, const float* w, int k, const float* bias, int relu, const float* mask,
                         int64_t ldmask, float* y, int64_t ldy, int64_t m, cudaStream_t st) {
   WStatArgs A{};
-  A.W = w; A.bias = bias; A.mask = mask; A.ldmask = ldmask; A.Y = y; A.ldy = ldy; A.M = m; A.relu = relu;
+  A.W = w; A.K = k; A.bias = bias; A.mask = mask; A.ldmask = ldmask; A.Y = y; A.ldy = ldy; A.M = m; A.relu = relu;
   A.n_tiles = (int)ceil_div(m, 128);
   CUtensorMap tm_x, tm_m;
-  int rc = make_atom_map_s(&tm_x, x, m, ldx);
+  int rc = make_atom_map_s(&tm_x, x, m, mode == 0 ? k : kSDim, ldx);
   if (rc != TNF_OK) return rc;
   if (mode == 1 && mask) {
-    rc = make_atom_map_s(&tm_m, mask, m, ldmask);
+    rc = make_atom_map_s(&tm_m, mask, m, k, ldmask);
     if (rc != TNF_OK) return rc;
   } else {
     tm_m = tm_x;

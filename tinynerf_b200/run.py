@@ -211,7 +211,8 @@ class TrainConfig:
     prefetch_depth: int = 2             # batches kept marched ahead (2: the host's per-batch sync never waits for the step
                                         # in flight, so a host hiccup on one rank is absorbed instead of stalling a collective)
     fused_tv_grad: bool = True          # TV gradient written straight into the plane grads (no autograd temporaries)
-    fused_step: bool = True             # K-Planes: forward+loss+backward as one C-ABI call sequence (fused.py), no autograd
+    fused_step: bool = True             # K-Planes / Cobafa: forward+loss+backward as one C-ABI call sequence (fused.py,
+                                        # fused_cobafa.py), no autograd
     max_inflight_steps: int = 3         # the host enqueues at most this many iterations ahead of the GPU (0 = unbounded): a
                                         # free-running host ends up a launch-queue's worth of steps ahead, every batch it has
                                         # marched stays allocated until the GPU gets there, and the allocator's cudaMalloc
@@ -296,6 +297,12 @@ class Trainer:
                         view = lambda flat: torch.as_strided(flat, p.shape, p.stride(), off)
                         self.optimizer.state[p] = {"step": 0, "exp_avg": view(peer.exp_avg), "exp_avg_sq": view(peer.exp_avg_sq)}
                         off += (p.numel() + 3) // 4 * 4
+        # Cobafa: the same idea (fused_cobafa.py) -- the module path's host work exceeds the iteration's kernel time
+        self._fused_cobafa = None
+        if cfg.fused_step and cfg.method == "cobafa" and self.device.type == "cuda":
+            from .fused_cobafa import FusedCobafaStep
+            if FusedCobafaStep.supported(self.renderer):
+                self._fused_cobafa = FusedCobafaStep(self.renderer, grad_scale=cfg.grad_scale, world=world)
         self._chunks_guess = 0.0
         if world > 1 and self.device.type == "cuda":
             self._warm_collectives()
@@ -516,6 +523,8 @@ class Trainer:
             out = self._step_fused(packed, rgbs, info)
             self._after_first_steps()
             return out
+        if self._fused_cobafa is not None:
+            return self._step_fused_cobafa(packed, rgbs, info)
         rendered = self.renderer(packed, info)
         loss = dp_mse(rendered, rgbs, global_ray_count(info.size(0), self.device, self.world))
         tv_direct = 0.0
@@ -635,6 +644,25 @@ class Trainer:
             torch.cuda.current_stream(self.device).wait_event(self._planes_done)
         else:
             self.optimizer.step()
+        self.scheduler.step()
+        self.train_step += 1
+        self._publish_loss(out["loss"])
+        self._mark_enqueued()
+        if self._side is not None:
+            self._prefetch()
+        self.last = {"loss": out["loss"], "n_samples": packed.size(0), "n_rays": info.size(0)}
+        return self.last
+
+    def _step_fused_cobafa(self, packed, rgbs, info) -> Dict[str, float]:
+        """The Cobafa iteration through fused_cobafa.FusedCobafaStep: same kernels and order as the module path, no autograd /
+        glue ops; data-parallel: the union batch's ray count is reduced while the forward runs, the flat gradient in one
+        collective, then the replicated Adam (src/run.py:251-261)."""
+        n_glob = work = None
+        if self.world > 1:
+            n_glob = torch.tensor(float(info.size(0)), device=self.device)
+            work = dist.all_reduce(n_glob, async_op=True)
+        out = self._fused_cobafa.forward_backward(packed, info, rgbs, n_glob, reduce=self.world > 1, n_rays_work=work)
+        self.optimizer.step()
         self.scheduler.step()
         self.train_step += 1
         self._publish_loss(out["loss"])
