@@ -806,6 +806,172 @@ __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs 
   if (warp == 8) tmem_dealloc(s_tmem, 512);
 }
 
+// wgrad for layers with 128 outputs and <= 128 inputs (the Cobafa trunk) in ONE pass over dY and X.
+// Two launches of wgrad_tma_kernel (one per 64-row half of dW) read X twice: 768 B per sample and launch where 1,024 B per
+// sample would do for the whole layer.  Here all 128 output features are TMEM lanes: the transposed dY tile is written
+// twice, as a hi image (columns 0..127 = the tile's 128 samples) and a lo image (128..255), by four warps (thread == lane
+// == feature); per X atom the issuer runs, for each of the 16 k-steps,
+//     D[:, 64 j .. 64 j + 64) += dY_hi^T [X_hi | X_lo]      (N = 64, the lo image as the second MN block, as above)
+//     D[:, 64 j .. 64 j + 32) += dY_lo^T  X_hi              (N = 32)
+// i.e. the three 3xTF32 products with two instructions; D (64 columns per atom, <= 256) fills the rest of tensor memory, so
+// there is ONE A set: the transposition of tile t+1 waits for the MMAs of tile t (~1.5 of ~5 k cycles per tile, far below
+// the tile's HBM time).  Shared memory: two raw dY tiles (64 KB each, two 64-column TMA boxes), four X atoms, two lo images.
+constexpr int kG_Y = 2, kG_XH = 4, kG_XL = 2;
+constexpr int kGThreads = 10 * 32;
+
+__global__ void __launch_bounds__(kGThreads, 1) wgrad128_tma_kernel(const LinArgs A, const __grid_constant__ CUtensorMap tm_dy,
+                                                                    const __grid_constant__ CUtensorMap tm_x) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t s_pfull[kG_Y], s_pempty[kG_Y], s_xland[kG_XH], s_xfull[kG_XH], s_xempty[kG_XH], s_lempty[kG_XL], s_afull,
+      s_aempty, s_done;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_db[128];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kx = (A.K + 31) >> 5;                        // X atoms per tile (<= 4)
+  constexpr int S = kG_XH, L = kG_XL;
+  uint8_t* yraw = smem;                                  // raw dY tile slots: two [128 rows x 256 B] boxes (features 0-63 | 64-127)
+  uint8_t* xhi = smem + kG_Y * 4 * kAtomBytes;
+  uint8_t* xlo = xhi + S * kAtomBytes;
+  if (tid == 0) {
+    for (int i = 0; i < kG_Y; ++i) { mbar_init(&s_pfull[i], 1); mbar_init(&s_pempty[i], 128); }
+    for (int s = 0; s < S; ++s) { mbar_init(&s_xland[s], 1); mbar_init(&s_xfull[s], 128); mbar_init(&s_xempty[s], 1); }
+    for (int l = 0; l < L; ++l) mbar_init(&s_lempty[l], 1);
+    mbar_init(&s_afull, 128); mbar_init(&s_aempty, 1); mbar_init(&s_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(&s_tmem, 512);
+  if (tid < 128) s_db[tid] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_ahi = s_tmem, tmem_alo = s_tmem + 128, tmem_d = s_tmem + 256;
+  const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 9) {
+    // ===== producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_dy);
+      tma_prefetch_desc(&tm_x);
+      int xi = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int row0 = (int)(((long long)blockIdx.x + (long long)tl * gridDim.x) * 128);
+        const int ps = tl % kG_Y;
+        mbar_wait(&s_pempty[ps], ((tl / kG_Y) & 1) ^ 1);
+        mbar_expect_tx(&s_pfull[ps], 4 * kAtomBytes);
+        tma_load_2d(yraw + ps * 4 * kAtomBytes, &tm_dy, 0, row0, &s_pfull[ps]);
+        tma_load_2d(yraw + ps * 4 * kAtomBytes + 2 * kAtomBytes, &tm_dy, 64, row0, &s_pfull[ps]);
+        for (int j = 0; j < kx; ++j, ++xi) {
+          const int s = xi % S;
+          mbar_wait(&s_xempty[s], ((xi / S) & 1) ^ 1);
+          mbar_expect_tx(&s_xland[s], kAtomBytes);
+          tma_load_2d(xhi + s * kAtomBytes, &tm_x, 32 * j, row0, &s_xland[s]);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===== dY warps: thread == TMEM lane == output feature 32 q + lane; hi and lo images of the tile's 128 samples =====
+    const int q = warp;
+    float bsum = 0.f;
+    const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int ps = tl % kG_Y;
+      mbar_wait(&s_pfull[ps], (tl / kG_Y) & 1);
+      mbar_wait(&s_aempty, (tl & 1) ^ 1);                           // the MMAs of the previous tile have read the A images
+      tc_fence_after();
+      const uint8_t* src = yraw + ps * 4 * kAtomBytes + (q >> 1) * 2 * kAtomBytes + (32 * (q & 1) + lane) * 4;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = *reinterpret_cast<const float*>(src + (32 * c + i) * 256);
+          bsum += v[i];
+        }
+        tmem_st32(tmem_ahi + lane_off + 32 * c, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+        tmem_st32(tmem_alo + lane_off + 32 * c, v);
+      }
+      mbar_arrive(&s_pempty[ps]);                                   // every value of the slot is in registers
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&s_afull);
+    }
+    if (A.db) atomicAdd(&s_db[32 * q + lane], bsum);
+  } else if (warp < 8) {
+    // ===== X lo warps =====
+    const int t = tid - 128;
+    const int n_x = my_tiles * kx;
+    for (int xi = 0; xi < n_x; ++xi) {
+      const int s = xi % S, l = xi % L;
+      mbar_wait(&s_xland[s], (xi / S) & 1);
+      mbar_wait(&s_lempty[l], ((xi / L) & 1) ^ 1);
+      make_lo_atom<128>(xhi + s * kAtomBytes, xlo + l * kAtomBytes, t, true, nullptr);
+      fence_async_smem();
+      mbar_arrive(&s_xfull[s]);
+    }
+  } else {
+    // ===== MMA issuer =====
+    const uint32_t idesc64 = instr_desc(128, 64, false, true), idesc32 = instr_desc(128, 32, false, true);
+    int xi = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      mbar_wait(&s_afull, tl & 1);
+      for (int j = 0; j < kx; ++j, ++xi) {
+        const int s = xi % S;
+        mbar_wait(&s_xfull[s], (xi / S) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t xh = smem_u32(xhi + s * kAtomBytes);
+          const uint32_t lbo = smem_u32(xlo + (xi % L) * kAtomBytes) - xh;   // MN block 1 of the B operand = the lo image
+#pragma unroll 4
+          for (int kk = 0; kk < 16; ++kk) {
+            mma_tf32_ts(tmem_d + 64 * j, tmem_ahi + 8 * kk, desc_mnmajor(xh, kk, lbo), idesc64, !(tl == 0 && kk == 0));
+            mma_tf32_ts(tmem_d + 64 * j, tmem_alo + 8 * kk, desc_mnmajor(xh, kk, lbo), idesc32, true);
+          }
+          mma_commit(&s_xempty[s]);
+          mma_commit(&s_lempty[xi % L]);
+          if (j == kx - 1) mma_commit(&s_aempty);
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) mma_commit(&s_done);
+    __syncwarp();
+  }
+  mbar_wait(&s_done, 0);   // every MMA of this CTA has completed
+  tc_fence_after();
+  __syncthreads();
+  if (A.db && tid < 128) atomicAdd(A.db + tid, s_db[tid]);
+  if (warp < 4 && my_tiles > 0) {
+    // Flush as in wgrad_tma_kernel: every CTA adds its 128 x K partial into dW from its own starting (atom, chunk) position.
+    const int n_out = warp * 32 + lane;
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+    const bool vec = (A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(A.dW) & 15u) == 0;
+    const int j0 = blockIdx.x % kx, i0 = (blockIdx.x / kx) & 7;
+    for (int jj = 0; jj < kx; ++jj) {
+      const int j = (j0 + jj) % kx;
+      float* dst = A.dW + (long long)n_out * A.K + 32 * j;
+#pragma unroll 2
+      for (int ii = 0; ii < 8; ++ii) {
+        const int c4 = 4 * ((i0 + ii) & 7);
+        float v[4], u[4];
+        tmem_ld4x2(taddr + 64 * j + c4, taddr + 64 * j + 32 + c4, v, u);   // (dY_hi + dY_lo) x X_hi, dY_hi x X_lo
+        const int col = 32 * j + c4;
+        if (vec && col + 3 < A.K) red_add_f4(dst + c4, make_float4(v[0] + u[0], v[1] + u[1], v[2] + u[2], v[3] + u[3]));
+        else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (col + e < A.K) atomicAdd(dst + c4 + e, v[e] + u[e]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(s_tmem, 512);
+}
+
 constexpr int kHbU = 4;
 template <int NH>  // n_head
 __global__ void __launch_bounds__(256, 3) head_bwd_kernel(const float* __restrict__ H, long long ldh, const float* __restrict__ Wh,
@@ -1012,6 +1178,29 @@ int launch_wgrad_tma(const float* dy, int64_t lddy, const float* xa, int64_t ldx
   return TNF_OK;
 }
 
+// 128 outputs, <= 128 inputs: one pass over dY and X (wgrad128_tma_kernel)
+int launch_wgrad128(const float* dy, int64_t lddy, const float* x, int64_t ldx, int k, float* dweight, float* dbias, int64_t m,
+                    cudaStream_t st) {
+  LinArgs A{};
+  A.dW = dweight; A.db = dbias; A.M = m; A.N = 128; A.K = k;
+  A.n_tiles = (int)ceil_div(m, 128);
+  CUtensorMap tm_dy, tm_x;
+  int rc = make_box_map(&tm_dy, dy, m, 128, lddy, 64, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc != TNF_OK) return rc;
+  rc = make_box_map(&tm_x, x, m, k, ldx, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != TNF_OK) return rc;
+  const size_t smem = (size_t)(4 * kG_Y + kG_XH + kG_XL) * kAtomBytes + 1024;
+  static PerDeviceOnce configured128{};
+  if (configured128.pending()) {
+    TNF_CUDA(cudaFuncSetAttribute(wgrad128_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured128.mark();
+  }
+  const int grid = A.n_tiles < sm_count() ? A.n_tiles : sm_count();
+  wgrad128_tma_kernel<<<grid, kGThreads, smem, st>>>(A, tm_dy, tm_x);
+  TNF_LAUNCH_CHECK("linear_wgrad128_tma_kernel");
+  return TNF_OK;
+}
+
 // shared-memory plan of linear_kernel: weight images + H hi slots + L lo slots (16 KB each) + 16 KB epilogue staging.
 // L = 3 lets the lo pass run two atoms ahead of the tensor core; every further hi slot is another atom of global loads
 // in flight (H - L of them, up to 4).
@@ -1109,6 +1298,8 @@ extern "C" int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float*
   const bool want_ss = variant(kVariantWgradSS) == 1;   // diagnostics: the both-operands-in-shared-memory kernel
   if (n == 64 && m < (1LL << 31) - 256 && !want_ss)
     return launch_wgrad_tma(dy, lddy, x, ldx, k, nullptr, 0, 0, dweight, dbias, nullptr, m, st);
+  if (n == 128 && k <= 128 && m < (1LL << 31) - 256 && !want_ss && !variant(kVariantNoWstat))
+    return launch_wgrad128(dy, lddy, x, ldx, k, dweight, dbias, m, st);   // the whole layer in one pass (Cobafa trunk)
   if (n == 128 && (k + 31) / 32 <= kMaxKAtoms && m < (1LL << 31) - 256 && !want_ss) {
     // 128 output features (the Cobafa trunk, src/models.py:254-266) = two 64-row halves of dW through the tensor-memory /
     // TMA kernel: 2 x ~60 us against ~200 us for the both-operands-in-shared-memory kernel below (M = 2^18, K = 128)
