@@ -74,6 +74,23 @@ def test_fused_cobafa_step_matches_autograd_step():
         assert float((err > 1e-5 * scale).float().mean()) <= (1e-3 if a.numel() > 100000 else 0.1), k
 
 
+def test_fused_cobafa_density_matches_modules():
+    """FusedCobafaStep.density (the occupancy update's sigma_fn) == sigma_decoder(feature_module(x)) of the modules, in
+    training mode (same dropout mask from the same generator state) and in eval mode."""
+    tr = _trainer(True, method="cobafa")
+    x = (torch.rand(20000, 3, device=DEV) * 2 - 1).contiguous()
+    for training in (True, False):
+        tr.renderer.train(training)
+        torch.manual_seed(77)
+        with torch.no_grad():
+            want = tr.renderer.sigma_decoder(tr.renderer.feature_module(x))
+        torch.manual_seed(77)
+        got = tr._fused_cobafa.density(x)
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-7), float((got - want).abs().max())
+    tr.close()
+
+
 def test_fused_cobafa_training_runs_and_learns():
     """A few full iterations (Adam, scheduler, an occupancy update through the modules in between): finite, decreasing loss,
     and the fused step survives optimizer.zero_grad() and a workspace re-allocation."""

@@ -152,6 +152,44 @@ class FusedCobafaStep:
             self._ws["loss"] = torch.zeros(1, device=self.dev)
             self._cap_r = cap
 
+    # ---- density only (the occupancy update's sigma_fn, src/run.py:249) ----------------------------
+    @torch.no_grad()
+    def density(self, coords: torch.Tensor) -> torch.Tensor:
+        """sigma_decoder(feature_module(coords)) for [n,3] contracted coordinates on the iteration's own workspaces: lookup,
+        dropout when the module is in training mode (the reference updates the grid from inside the training loop, so its
+        Dropout(0.01) is active there too), trunk, density head with the fused output layer.  Returns a view of the workspace
+        that stays valid until the next density() / forward_backward() call on this stream."""
+        _lib.require_cuda(coords, "coords")
+        if coords.dim() != 2 or coords.size(1) != 3 or coords.dtype != torch.float32 or not coords.is_contiguous():
+            raise RuntimeError("coords must be a contiguous [n,3] float32 tensor")
+        n = coords.size(0)
+        if n == 0:
+            return torch.empty(0, 1, device=self.dev)
+        self._reserve(n, 1)
+        ws, call, st = self._ws, _lib.call, _lib.stream_ptr(self.dev)
+        P = lambda t: t.data_ptr()
+        F, F0, tl, sl = self.feat, self.feat_in, self.trunk, self.sig_lin
+        p_drop = float(self.fm.dropout.p) if self.fm.dropout.training else 0.0
+        with torch.cuda.device(self.dev):
+            call("tnf_cobafa_fwd", self._basis_ptrs, self._res, self._ch, self._freqs, self.n_levels, self._coef_ptr, self.coef_res,
+                 P(coords), 3, n, P(ws["f36"]), st, nbytes=n * (12 + 4 * F0) + self._grid_bytes)
+            x0 = ws["f36"][:n]
+            if p_drop > 0.0:
+                x0 = torch.native_dropout(x0, p_drop, True)[0]
+            x, ldx = P(x0), x0.stride(0)
+            for i, lin in enumerate(tl):
+                last = i == len(tl) - 1
+                y = ws["feats"] if last else ws[f"t{i}"]
+                nn_, k = lin.out_features, lin.in_features
+                call("tnf_linear_fwd", x, ldx, P(lin.weight), P(lin.bias), P(y), nn_, n, nn_, k, int(not last), None, None, None, 0, 0, st,
+                     nbytes=4 * (n * (k + nn_) + nn_ * k), flops=2 * n * nn_ * k)
+                x, ldx = P(y), nn_
+            l0, l1 = sl[0], sl[1]
+            call("tnf_linear_fwd", P(ws["feats"]), F, P(l0.weight), P(l0.bias), None, l0.out_features, n, l0.out_features, F, 1,
+                 P(l1.weight), P(l1.bias), P(ws["sigma"]), 1, 1, st,
+                 nbytes=4 * (n * (F + 1) + l0.out_features * F), flops=2 * n * l0.out_features * (F + 1))
+        return ws["sigma"][:n].view(n, 1)
+
     @torch.no_grad()
     def forward_backward(self, packed: torch.Tensor, info: torch.Tensor, target: torch.Tensor,
                          n_rays_global: torch.Tensor | None = None, reduce: bool = False, n_rays_work=None) -> Dict[str, torch.Tensor]:

@@ -456,6 +456,8 @@ class Trainer:
         og = self.occupancy_grid
         if self._fused is not None:
             sigma_fn = self._fused.density   # same kernels on the iteration's workspaces: no allocations in the update
+        elif getattr(self, "_fused_cobafa", None) is not None:
+            sigma_fn = self._fused_cobafa.density
         else:
             sigma_fn = lambda t: self.renderer.sigma_decoder(self.renderer.feature_module(t))
         if self.world == 1:
