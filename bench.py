@@ -420,16 +420,19 @@ def summarise_profile(records, peak, tf32_peak):
     return table, dom
 
 
-def roofline_of(table, dom, peak, tf32_peak, peak_src, samples_per_launch=0):
+def roofline_of(table, dom, peak, tf32_peak, peak_src, samples_per_launch=0, ncu_applies=True):
+    """ncu_applies: the committed ncu capture (NCU_TRAFFIC_BYTES) is of the K-Planes iteration; other workloads launch the same
+    entry points at other shapes (Cobafa: 128-wide layers), so their `traffic` is left null rather than borrowed."""
     if not dom:
         return None
     t = table[dom]
+    traffic = NCU_TRAFFIC_BYTES.get(dom) if ncu_applies else None
     if dom in TENSOR_BOUND and "TFLOP/s_tf32_issued" in t:
         return {"kernel": dom, "bound": "tensor", "achieved": t["TFLOP/s_tf32_issued"], "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": t["tensor_frac_issued"], "traffic": NCU_TRAFFIC_BYTES.get(dom), "peak_source": peak_src + " (bf16 burst / 2 = TF32)",
+                "frac": t["tensor_frac_issued"], "traffic": traffic, "peak_source": peak_src + " (bf16 burst / 2 = TF32)",
                 "avg_us": t["avg_us"], "hbm_frac": t["frac"], "note": "3xTF32: three issued TF32 MMAs per fp32-accurate product"}
     roof = {"kernel": dom, "bound": "hbm", "achieved": t["GB/s"], "peak": peak, "unit": "GB/s", "frac": t["frac"],
-            "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r02_ncu_full.md" if dom in NCU_TRAFFIC_BYTES else None,
+            "traffic": traffic, "traffic_source": "profiles/r02_ncu_full.md" if traffic is not None else None,
             "peak_source": peak_src, "avg_us": t["avg_us"], "alg_bytes_per_launch": int(t["alg_MB_per_launch"] * 1e6)}
     if dom in ("tnf_kplanes_bwd", "tnf_kplanes_fwd") and samples_per_launch:
         # informational: the resource this kernel actually saturates.  Every sample moves 36 corner lines x 128 B through L2
@@ -597,7 +600,8 @@ def train_workload(ctx: Ctx, name: str, steps: int, warmup: int, e2e_arm: bool, 
            "ms_per_step": round(ms / steps, 4), "packed_samples_per_step_per_gpu": round(n / steps / world),
            "gpu_launches": int(launches), "host_ms_per_step": round(host_ms[0], 4), "host_step_ms": {"value_arm": host_dist[0]},
            "settle_steps": settle, "clocks": clk, "kernels": table,
-           "roofline": roofline_of(table, dom, ctx.peak, ctx.tf32_peak, ctx.peak_src, n / steps / world)}
+           "roofline": roofline_of(table, dom, ctx.peak, ctx.tf32_peak, ctx.peak_src, n / steps / world,
+                                   ncu_applies=spec["method"] == "kplanes")}
     # occupancy update inside / outside the window (SURVEY 8d defines the metric with the update amortised at its cadence)
     all_upd = upd_ms or settle_upd_ms[-1:]
     upd_avg = sum(all_upd) / len(all_upd) if all_upd else None

@@ -294,6 +294,9 @@ int tnf_cobafa_bwd(const float* const* basis, float* const* grad_basis, const in
  *   dgrad: dx = (dy W) (* (relu_src > 0) when relu_src != NULL: ReLU backward of the producer of x)
  *   wgrad: dweight += dy^T x ; dbias += column sums of dy      (atomic accumulation: zero them first)
  *   head_bwd: gradients of the fused head: dh (masked by h > 0), dhead_w, dhead_b (accumulated)
+ * Layers with n == 128 and k <= 128 (the Cobafa trunk) run with the weights stationary in tensor memory (csrc/wstat.cu: the
+ * transposed GEMM, W as the TMEM A operand, sample tiles and the ReLU mask by TMA) and their weight gradient in one pass over
+ * dy and x (wgrad128_tma_kernel); same arithmetic, same arguments -- the entry points choose by shape, never by backend.
  */
 /* Layers wider than the resident-weight kernels above cover (in_features > 160 or out_features > 128: the reference's
  * VanillaFeatureMLP(10, 256, 8), src/models.py:59-68, the decoders behind it and the Cobafa colour head's 179-wide first
