@@ -316,6 +316,14 @@ int tnf_linear_bwd_data(const float* dy, int64_t lddy, const float* weight, floa
                         const float* relu_src, int64_t ldrs, int64_t m, int32_t n, int32_t k, void* stream);
 int tnf_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dweight, float* dbias,
                           int64_t m, int32_t n, int32_t k, void* stream);
+/* Several 64-output weight gradients over the SAME m rows in one launch (the heads' dW_i = dh_i^T h_{i-1}, src/models.py:7-28
+ * backward): job j adds dy[j]^T x[j] into dweight[j] [64, k[j]] and the column sums of dy[j] into dbias[j] (dbias or dbias[j]
+ * NULL to skip).  All tables are [host] arrays of n_jobs <= 4 entries; dy[j] [m,64], x[j] [m,k[j]] with k[j] <= 128, 16-byte
+ * aligned, leading dimensions multiple of 4.  Same arithmetic as n_jobs calls of tnf_linear_bwd_weight with n = 64; one cold
+ * start and one drain instead of n_jobs. */
+int tnf_linear_bwd_weight_multi(int32_t n_jobs, const float* const* dy /*[host]*/, const int64_t* lddy /*[host]*/,
+                                const float* const* x /*[host]*/, const int64_t* ldx /*[host]*/, const int32_t* k /*[host]*/,
+                                float* const* dweight /*[host]*/, float* const* dbias /*[host], optional*/, int64_t m, void* stream);
 /* wgrad of a layer whose input is a concatenation that was never materialised: x = [xa (ka columns) | xb (kb columns)],
  * dweight [n, ka+kb] += dy^T x, dbias += column sums of dy (NULL to skip).  The colour head's first layer reads
  * cat([PE(d), d], features) (src/models.py:87): xa = the [PE(d) | d] rows, xb = the feature rows.  n must be 64.

@@ -105,6 +105,35 @@ def test_weight_stationary_128_layers_vs_resident_kernel(m):
     assert torch.equal(outs[0][1][:, :128] == 0, outs[1][1][:, :128] == 0)   # identical ReLU masks
 
 
+@pytest.mark.parametrize("m,ks", [(1000, (64, 64, 64, 96)), (70001, (64, 64, 64, 96)), (129, (128,)), (50000, (64, 30, 128, 96)),
+                                  (200000, (64, 64))])
+def test_multi_job_wgrad(m, ks):
+    """tnf_linear_bwd_weight_multi: several 64-output weight gradients of one batch in one launch (the operand rings and A
+    sets keep counting across the job boundaries, D is flushed per job) == one fp64 matmul per job; twice, accumulating."""
+    import ctypes as C
+    g = torch.Generator().manual_seed(m + len(ks))
+    nj = len(ks)
+    dys = [torch.randn(m, 64, generator=g).to(DEV) for _ in ks]
+    xs = []
+    for k in ks:
+        ld = (k + 3) // 4 * 4
+        buf = torch.full((m, ld), float("nan"))
+        buf[:, :k] = torch.randn(m, k, generator=g).relu()
+        xs.append(buf.to(DEV))
+    gws = [torch.zeros(64, k, device=DEV) for k in ks]
+    gbs = [torch.zeros(64, device=DEV) for _ in ks]
+    vp, i64, i32 = (C.c_void_p * nj), (C.c_int64 * nj), (C.c_int32 * nj)
+    for rep in (1, 2):
+        with torch.cuda.device(0):
+            _lib.call("tnf_linear_bwd_weight_multi", nj, vp(*[t.data_ptr() for t in dys]), i64(*[64] * nj), vp(*[t.data_ptr() for t in xs]),
+                      i64(*[t.stride(0) for t in xs]), i32(*ks), vp(*[t.data_ptr() for t in gws]), vp(*[t.data_ptr() for t in gbs]), m,
+                      _lib.stream_ptr())
+        for dy, x, k, gw, gb in zip(dys, xs, ks, gws, gbs):
+            x64 = x[:, :k].double()
+            check(gw, rep * (dy.double().t() @ x64), rep * (dy.double().abs().t() @ x64.abs()))
+            check(gb, rep * dy.double().sum(0), rep * dy.double().abs().sum(0))
+
+
 @pytest.mark.parametrize("m,ka,kb", [(1000, 51, 96), (70001, 51, 96), (300, 20, 33), (40000, 64, 64)])
 def test_wgrad_of_a_concatenated_input(m, ka, kb):
     """tnf_linear_bwd_weight_cat: dW += dy^T [xa | xb] without the concatenation ever being written (the colour head's

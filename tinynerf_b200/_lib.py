@@ -137,6 +137,9 @@ _SIGNATURES = {
                                       C.c_int32, C.c_int32, C.c_void_p]),
     "tnf_linear_bwd_weight": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, C.c_int32,
                                         C.c_int32, C.c_void_p]),
+    "tnf_linear_bwd_weight_multi": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                              C.c_int64, C.c_void_p]),
     "tnf_wgrad_cat_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "tnf_linear_bwd_weight_cat": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int32, c_f32p, C.c_int64, C.c_int32, c_f32p, c_f32p,
                                             C.c_int64, C.c_int32, c_f32p, C.c_void_p]),
@@ -187,7 +190,7 @@ KERNELS_PER_CALL = {"tnf_weights_fwd": 1, "tnf_weights_bwd": 1, "tnf_march_count
                     "tnf_kplanes_bwd": 1, "tnf_cobafa_fwd": 1, "tnf_cobafa_bwd": 1, "tnf_composite_fwd": 1,
                     "tnf_composite_bwd": 1, "tnf_tv_fwd": 1, "tnf_tv_bwd": 1, "tnf_adam_step": 1, "tnf_linear_fwd": 1,
                     "tnf_linear_bwd_data": 1, "tnf_linear_bwd_weight": 1, "tnf_head_bwd": 1, "tnf_color_input": 1,
-                    "tnf_heads_fwd": 2, "tnf_heads_bwd_data": 2, "tnf_linear_bwd_weight_cat": 1}
+                    "tnf_heads_fwd": 2, "tnf_heads_bwd_data": 2, "tnf_linear_bwd_weight_cat": 1, "tnf_linear_bwd_weight_multi": 1}
 launch_count = 0
 _prof = None
 

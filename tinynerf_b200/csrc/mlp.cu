@@ -806,6 +806,184 @@ __global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_kernel(const LinArgs 
   if (warp == 8) tmem_dealloc(s_tmem, 512);
 }
 
+// Several 64-output weight gradients of ONE batch in one launch ("jobs": the heads' dW_i = dh_i^T h_{i-1} layers and the
+// density head's first layer).  Each wgrad_tma_kernel launch costs a cold start (tensor-map fetch, TMEM allocation, the first
+// loads' latency: ~6 us before the first MMA) and a tail (flush, drain), ~17 us of the 43 us an in-step launch takes, while
+// its loop streams at 5 TB/s.  Here the roles of wgrad_tma_kernel simply walk a job list: the operand rings, the two A sets
+// and every barrier keep counting across jobs, so the producer prefetches job j+1's first tiles while job j's last MMAs run;
+// at a job boundary the dY warps wait for job j's MMAs, flush D (their own TMEM lanes) into dW_j and carry on with job j+1's
+// first tile -- the issuer's next wait (A set full) orders the overwrite of D behind that flush.
+constexpr int kWgMaxJobs = 4;
+struct WgJobs {
+  CUtensorMap dy[kWgMaxJobs];   // [M,64] dY of job j: one raw 128 x 64 box
+  CUtensorMap x[kWgMaxJobs];    // [M,K_j] X of job j: 32-column atoms in the SWIZZLE_128B_ATOM_32B operand image
+  float* dW[kWgMaxJobs];        // [64, K_j]
+  float* db[kWgMaxJobs];        // [64] or null
+  int K[kWgMaxJobs];
+  int n_jobs;
+  int n_tiles;
+};
+
+__global__ void __launch_bounds__(kW3Threads, 1) wgrad_tma_multi_kernel(const __grid_constant__ WgJobs J) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t s_pfull[kW3Y], s_pempty[kW3Y], s_xland[kW3XHi], s_xfull[kW3XHi], s_xempty[kW3XHi], s_lempty[kW3XLo],
+      s_afull[2], s_aempty[2], s_done;
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int S = kW3XHi, L = kW3XLo;
+  uint8_t* yraw = smem;                                  // raw dY tile slots: 128 rows x 256 B
+  uint8_t* xhi = smem + kW3Y * 2 * kAtomBytes;
+  uint8_t* xlo = xhi + S * kAtomBytes;
+  if (tid == 0) {
+    for (int i = 0; i < kW3Y; ++i) { mbar_init(&s_pfull[i], 1); mbar_init(&s_pempty[i], 128); }
+    for (int s = 0; s < S; ++s) { mbar_init(&s_xland[s], 1); mbar_init(&s_xfull[s], 128); mbar_init(&s_xempty[s], 1); }
+    for (int l = 0; l < L; ++l) mbar_init(&s_lempty[l], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_afull[i], 128); mbar_init(&s_aempty[i], 1); }
+    mbar_init(&s_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(&s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_a = s_tmem;                        // A set i: columns [128 i, 128 i + 128)
+  const uint32_t tmem_d = s_tmem + 256;                  // D: 64 columns per X atom (<= 4 atoms)
+  const int my_tiles = (J.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_jobs = J.n_jobs;
+
+  if (warp == 9) {
+    // ===== producer =====
+    if (lane == 0) {
+      for (int j = 0; j < n_jobs; ++j) { tma_prefetch_desc(&J.dy[j]); tma_prefetch_desc(&J.x[j]); }
+      int xi = 0, tg = 0;
+      for (int job = 0; job < n_jobs; ++job) {
+        const int kx = (J.K[job] + 31) >> 5;
+        for (int tl = 0; tl < my_tiles; ++tl, ++tg) {
+          const int row0 = (int)(((long long)blockIdx.x + (long long)tl * gridDim.x) * 128);
+          const int ps = tg % kW3Y;
+          mbar_wait(&s_pempty[ps], ((tg / kW3Y) & 1) ^ 1);
+          mbar_expect_tx(&s_pfull[ps], 2 * kAtomBytes);
+          tma_load_2d(yraw + ps * 2 * kAtomBytes, &J.dy[job], 0, row0, &s_pfull[ps]);
+          for (int a = 0; a < kx; ++a, ++xi) {
+            const int s = xi % S;
+            mbar_wait(&s_xempty[s], ((xi / S) & 1) ^ 1);
+            mbar_expect_tx(&s_xland[s], kAtomBytes);
+            tma_load_2d(xhi + s * kAtomBytes, &J.x[job], 32 * a, row0, &s_xland[s]);
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===== dY warps: transpose the raw tile into the A set; at the end of a job, flush D =====
+    const int q = warp;                  // TMEM lane quarter: lanes 32q..32q+31
+    const bool is_hi = q < 2;            // quarters 0,1: dY_hi of features 0-31 / 32-63; quarters 2,3: dY_lo of the same
+    const int n_out = (warp * 32 + lane) & 63;
+    int tg = 0;
+    for (int job = 0; job < n_jobs; ++job) {
+      float bsum = 0.f;
+      for (int tl = 0; tl < my_tiles; ++tl, ++tg) {
+        const int ps = tg % kW3Y, set = tg & 1;
+        mbar_wait(&s_pfull[ps], (tg / kW3Y) & 1);
+        mbar_wait(&s_aempty[set], ((tg >> 1) & 1) ^ 1);            // the MMAs that read this A set have completed
+        tc_fence_after();
+        const uint8_t* src = yraw + ps * 2 * kAtomBytes + (32 * (q & 1) + lane) * 4;
+        const uint32_t taddr = tmem_a + ((uint32_t)(32 * q) << 16) + 128 * set;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = *reinterpret_cast<const float*>(src + (32 * c + i) * 256);
+            if (is_hi) { bsum += x; v[i] = x; }
+            else v[i] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+          }
+          tmem_st32(taddr + 32 * c, v);
+        }
+        mbar_arrive(&s_pempty[ps]);                                   // every value of the slot is in registers
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&s_afull[set]);
+      }
+      // ---- job boundary: this job's MMAs have completed -> add the CTA's 64 x K partial into dW (as wgrad_tma_kernel) ----
+      mbar_wait(&s_done, job & 1);
+      tc_fence_after();
+      if (my_tiles > 0) {
+        const int K = J.K[job], kx = (K + 31) >> 5;
+        float* dW = J.dW[job];
+        if (J.db[job] && is_hi) atomicAdd(J.db[job] + n_out, bsum);
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+        const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15u) == 0;
+        const int j0 = blockIdx.x % kx, i0 = (blockIdx.x / kx) & 7;
+        for (int jj = 0; jj < kx; ++jj) {
+          const int a = (j0 + jj) % kx;
+          float* dst = dW + (long long)n_out * K + 32 * a;
+#pragma unroll 2
+          for (int ii = 0; ii < 8; ++ii) {
+            const int c4 = 4 * ((i0 + ii) & 7);
+            float v[4], u[4];
+            tmem_ld4x2(taddr + 64 * a + c4, taddr + 64 * a + 32 + c4, v, u);   // x X_hi, x X_lo
+            const int col = 32 * a + c4;
+            if (vec && col + 3 < K) red_add_f4(dst + c4, make_float4(v[0] + u[0], v[1] + u[1], v[2] + u[2], v[3] + u[3]));
+            else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col + e < K) atomicAdd(dst + c4 + e, v[e] + u[e]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp < 8) {
+    // ===== X lo warps =====
+    const int t = tid - 128;
+    int n_x = 0;
+    for (int job = 0; job < n_jobs; ++job) n_x += my_tiles * ((J.K[job] + 31) >> 5);
+    for (int xi = 0; xi < n_x; ++xi) {
+      const int s = xi % S, l = xi % L;
+      mbar_wait(&s_xland[s], (xi / S) & 1);
+      mbar_wait(&s_lempty[l], ((xi / L) & 1) ^ 1);
+      make_lo_atom<128>(xhi + s * kAtomBytes, xlo + l * kAtomBytes, t, true, nullptr);
+      fence_async_smem();
+      mbar_arrive(&s_xfull[s]);
+    }
+  } else {
+    // ===== MMA issuer =====
+    const uint32_t idesc = instr_desc(128, 64, false, true);
+    int xi = 0, tg = 0;
+    for (int job = 0; job < n_jobs; ++job) {
+      const int kx = (J.K[job] + 31) >> 5;
+      for (int tl = 0; tl < my_tiles; ++tl, ++tg) {
+        const int set = tg & 1;
+        mbar_wait(&s_afull[set], (tg >> 1) & 1);   // (the first of a job also orders this job's MMAs behind the flush of the previous D)
+        for (int a = 0; a < kx; ++a, ++xi) {
+          const int s = xi % S;
+          mbar_wait(&s_xfull[s], (xi / S) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t xh = smem_u32(xhi + s * kAtomBytes);
+            const uint32_t lbo = smem_u32(xlo + (xi % L) * kAtomBytes) - xh;   // MN block 1 of the B operand = the lo image
+            const uint32_t aa = tmem_a + 128 * set;
+#pragma unroll 4
+            for (int kk = 0; kk < 16; ++kk)
+              mma_tf32_ts(tmem_d + 64 * a, aa + 8 * kk, desc_mnmajor(xh, kk, lbo), idesc, !(tl == 0 && kk == 0));
+            mma_commit(&s_xempty[s]);
+            mma_commit(&s_lempty[xi % L]);
+            if (a == kx - 1) mma_commit(&s_aempty[set]);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) mma_commit(&s_done);   // every MMA of this job has completed when this arrives
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(s_tmem, 512);
+}
+
 // wgrad for layers with 128 outputs and <= 128 inputs (the Cobafa trunk) in ONE pass over dY and X.
 // Two launches of wgrad_tma_kernel (one per 64-row half of dW) read X twice: 768 B per sample and launch where 1,024 B per
 // sample would do for the whole layer.  Here all 128 output features are TMEM lanes: the transposed dY tile is written
@@ -1178,6 +1356,31 @@ int launch_wgrad_tma(const float* dy, int64_t lddy, const float* xa, int64_t ldx
   return TNF_OK;
 }
 
+// several 64-output layers of one batch in one launch (wgrad_tma_multi_kernel)
+int launch_wgrad_multi(int n_jobs, const float* const* dy, const int64_t* lddy, const float* const* x, const int64_t* ldx,
+                       const int32_t* k, float* const* dweight, float* const* dbias, int64_t m, cudaStream_t st) {
+  WgJobs J{};
+  J.n_jobs = n_jobs;
+  J.n_tiles = (int)ceil_div(m, 128);
+  for (int j = 0; j < n_jobs; ++j) {
+    int rc = make_box_map(&J.dy[j], dy[j], m, 64, lddy[j], 64, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != TNF_OK) return rc;
+    rc = make_box_map(&J.x[j], x[j], m, k[j], ldx[j], 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc != TNF_OK) return rc;
+    J.dW[j] = dweight[j]; J.db[j] = dbias ? dbias[j] : nullptr; J.K[j] = k[j];
+  }
+  const size_t smem = (size_t)(2 * kW3Y + kW3XHi + kW3XLo) * kAtomBytes + 1024;
+  static PerDeviceOnce configured_multi{};
+  if (configured_multi.pending()) {
+    TNF_CUDA(cudaFuncSetAttribute(wgrad_tma_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    configured_multi.mark();
+  }
+  const int grid = J.n_tiles < sm_count() ? J.n_tiles : sm_count();
+  wgrad_tma_multi_kernel<<<grid, kW3Threads, smem, st>>>(J);
+  TNF_LAUNCH_CHECK("linear_wgrad_tma_multi_kernel");
+  return TNF_OK;
+}
+
 // 128 outputs, <= 128 inputs: one pass over dY and X (wgrad128_tma_kernel)
 int launch_wgrad128(const float* dy, int64_t lddy, const float* x, int64_t ldx, int k, float* dweight, float* dbias, int64_t m,
                     cudaStream_t st) {
@@ -1347,6 +1550,24 @@ extern "C" int tnf_linear_bwd_weight_cat(const float* dy, int64_t lddy, const fl
               "dy/xa/xb must be 16-byte aligned with ld %% 4 == 0");
   TNF_REQUIRE(!scratch || al16(scratch), "scratch must be 16-byte aligned");
   return launch_wgrad_tma(dy, lddy, xa, ldxa, ka, xb, ldxb, kb, dweight, dbias, scratch, m, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tnf_linear_bwd_weight_multi(int32_t n_jobs, const float* const* dy, const int64_t* lddy, const float* const* x,
+                                           const int64_t* ldx, const int32_t* k, float* const* dweight, float* const* dbias,
+                                           int64_t m, void* stream) {
+  using namespace tnf;
+  TNF_REQUIRE(n_jobs >= 1 && n_jobs <= kWgMaxJobs, "n_jobs must be in [1,%d]", kWgMaxJobs);
+  TNF_REQUIRE(m >= 0, "negative m");
+  if (m == 0) return TNF_OK;
+  TNF_REQUIRE(dy && lddy && x && ldx && k && dweight, "null table");
+  TNF_REQUIRE(m < (1LL << 31) - 256, "too many rows for the tensor-map coordinates");
+  for (int j = 0; j < n_jobs; ++j) {
+    TNF_REQUIRE(dy[j] && x[j] && dweight[j], "null pointer in job %d", j);
+    TNF_REQUIRE(k[j] >= 1 && k[j] <= 128, "job %d: in_features must be in [1,128] (got %d)", j, k[j]);
+    TNF_REQUIRE(al16(dy[j]) && lddy[j] % 4 == 0 && lddy[j] >= 64 && al16(x[j]) && ldx[j] % 4 == 0 && ldx[j] >= k[j],
+                "job %d: dy/x must be 16-byte aligned with leading dimensions multiple of 4", j);
+  }
+  return launch_wgrad_multi(n_jobs, dy, lddy, x, ldx, k, dweight, dbias, m, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tnf_color_input(const float* dirs, int64_t ld_dirs, const float* feats, int64_t ld_feats, int32_t n_freqs,

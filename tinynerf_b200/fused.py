@@ -125,6 +125,7 @@ class FusedKPlanesStep:
         self._cap_n = self._cap_r = 0
         self._ws: Dict[str, torch.Tensor] = {}
         self.fused_composite = os.environ.get("TNF_FUSED_COMPOSITE", "1") != "0"   # 0: the three separate kernels
+        self.wgrad_multi = os.environ.get("TNF_WGRAD_MULTI", "1") != "0"            # 0: one launch per 64-output weight gradient
         # Kernels of an iteration that depend on nothing before them run on an auxiliary stream beside kernels bound by a
         # different resource (TNF_AUX_OVERLAP=0: everything in line): the TV pass (HBM streaming) and the [PE(d)|d] rows
         # (issue-bound sincos) beside the plane gather (L2 -> SM bound); the colour head's output-layer backward (HBM) beside
@@ -565,15 +566,28 @@ class FusedKPlanesStep:
                 # the collective's CTAs hold whole SMs; leave them out of the weight-gradient kernels' one-CTA-per-SM grids
                 _lib.load().tnf_set_sm_budget(max(16, self._sms - self.collective_ctas))
             # weight gradients of both heads
-            for i in range(nh - 1, 0, -1):
-                wgrad(P(dh[i]), hc_w, P(ws[f"h{i - 1}"]), hc_w, cl[i])
+            multi = self.wgrad_multi and hc_w == 64 and hs_w == 64 and F <= 128 and 1 <= nh <= 4
+            if multi:
+                # the hidden colour layers' and the density layer's weight gradients as jobs of ONE launch (one cold start and
+                # one drain instead of nh: ~17 us of every 43 us launch, profiles/r01_role_timing_wgrad.txt)
+                jl = [(dh[i], ws[f"h{i - 1}"], hc_w, cl[i]) for i in range(nh - 1, 0, -1)] + [(ws["dhs"], ws["feats"], F, sl[0])]
+                nj = len(jl)
+                vp, i64, i32 = (C.c_void_p * nj), (C.c_int64 * nj), (C.c_int32 * nj)
+                call("tnf_linear_bwd_weight_multi", nj, vp(*[P(j[0]) for j in jl]), i64(*[64] * nj), vp(*[P(j[1]) for j in jl]),
+                     i64(*[j[2] for j in jl]), i32(*[j[2] for j in jl]), vp(*[G(j[3].weight) for j in jl]),
+                     vp(*[G(j[3].bias) for j in jl]), n, st,
+                     nbytes=sum(4 * (n * (64 + j[2]) + 64 * j[2]) for j in jl), flops=sum(2 * n * 64 * j[2] for j in jl))
+            else:
+                for i in range(nh - 1, 0, -1):
+                    wgrad(P(dh[i]), hc_w, P(ws[f"h{i - 1}"]), hc_w, cl[i])
             if self.split_xc:
                 call("tnf_linear_bwd_weight_cat", P(dh[0]), hc_w, P(ws["xc"]), xld, self.pe_width, P(ws["feats"]), F, F,
                      G(cl[0].weight), G(cl[0].bias), n, hc_w, P(self._wcat_scratch), st, nbytes=4 * (n * (hc_w + xld + F) + hc_w * xw),
                      flops=2 * n * hc_w * xw)
             else:
                 wgrad(P(dh[0]), hc_w, P(ws["xc"]), xld, cl[0])
-            wgrad(P(ws["dhs"]), hs_w, P(ws["feats"]), F, sl[0])
+            if not multi:
+                wgrad(P(ws["dhs"]), hs_w, P(ws["feats"]), F, sl[0])
             if peer_step is not None:
                 # the heads' 28 K parameters the same way, now that their gradients are complete
                 hupd = lambda st_: self.peer.reduce_adam_bcast(self._plane_grad_end, self.peer.n, 1, peer_step["step"], peer_step["lr"],

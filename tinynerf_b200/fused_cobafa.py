@@ -122,6 +122,8 @@ class FusedCobafaStep:
         self._closs_scratch = torch.zeros(2, dtype=torch.float64, device=self.dev)
         self._cap_n = self._cap_r = 0
         self._ws: Dict[str, torch.Tensor] = {}
+        import os
+        self.wgrad_multi = os.environ.get("TNF_WGRAD_MULTI", "1") != "0"   # 0: one launch per 64-output weight gradient
 
     def attach_grads(self) -> None:
         """p.grad = its view of the flat gradient buffer (undoes optimizer.zero_grad(set_to_none=True))."""
@@ -277,8 +279,18 @@ class FusedCobafaStep:
             call("tnf_heads_bwd_data", P(dh[3]), P(ws["dhs"]), masks, self._cw, xw, xw - F, P(sl[0].weight), F, dh_out,
                  P(ws["dfeat"]), F, n, P(self._heads_bwd_ws), st, nbytes=4 * n * (2 * 64 + 3 * 64 + 3 * 64 + F),
                  flops=2 * n * 64 * (3 * 64 + 2 * F))
-            for i in (3, 2, 1):   # dW_i += dh_i^T h_{i-1}
-                wgrad(P(dh[i]), 64, P(ws[f"h{i - 1}"]), 64, cl[i])
+            # dW_i += dh_i^T h_{i-1} of the hidden colour layers and the density layer: four jobs of one launch
+            jl = [(dh[i], ws[f"h{i - 1}"], 64, cl[i]) for i in (3, 2, 1)] + [(ws["dhs"], ws["feats"], F, sl[0])]
+            if self.wgrad_multi:
+                nj = len(jl)
+                vp, i64, i32 = (C.c_void_p * nj), (C.c_int64 * nj), (C.c_int32 * nj)
+                call("tnf_linear_bwd_weight_multi", nj, vp(*[P(j[0]) for j in jl]), i64(*[64] * nj), vp(*[P(j[1]) for j in jl]),
+                     i64(*[j[2] for j in jl]), i32(*[j[2] for j in jl]), vp(*[G(j[3].weight) for j in jl]),
+                     vp(*[G(j[3].bias) for j in jl]), n, st,
+                     nbytes=sum(4 * (n * (64 + j[2]) + 64 * j[2]) for j in jl), flops=sum(2 * n * 64 * j[2] for j in jl))
+            else:
+                for dy_, x_, k_, lin_ in jl:
+                    wgrad(P(dy_), 64, P(x_), k_, lin_)
             fa = self._fa
             if fa == F:
                 call("tnf_linear_bwd_weight_cat", P(dh[0]), 64, P(ws["xc"]), xld, pe_w, P(ws["feats"]), F, F, G(cl[0].weight),
@@ -293,7 +305,6 @@ class FusedCobafaStep:
                 gw0 = self._g[id(cl[0].weight)]
                 gw0[:, :pe_w + fa] = part_a
                 gw0[:, pe_w + fa:] = part_b
-            wgrad(P(ws["dhs"]), 64, P(ws["feats"]), F, sl[0])
             # ---- backward: the trunk (mlp_ops._FusedMLP.backward, wide last layer without activation) ----
             dcur, ldc = P(ws["dfeat"]), F
             bufs = (ws["dta"], ws["dtb"])
