@@ -74,6 +74,17 @@ def test_c_abi_argument_validation_without_gpu():
     assert b"xc_cols" in lib.tnf_last_error()
     assert lib.tnf_composite_loss_fwd_bwd(one, one, one, 10, 0, None, one, 1.0, None, 1.0, one, one, one, one, one, None, None, 0,
                                           None) == -1
+    # several weight gradients in one launch: the job tables are checked on the host
+    vp, i64, i32 = (ctypes.c_void_p * 2)(16, 16), (ctypes.c_int64 * 2)(64, 64), (ctypes.c_int32 * 2)(64, 96)
+    assert lib.tnf_linear_bwd_weight_multi(0, vp, i64, vp, i64, i32, vp, None, 1000, None) == -1
+    assert b"n_jobs" in lib.tnf_last_error()
+    assert lib.tnf_linear_bwd_weight_multi(5, vp, i64, vp, i64, i32, vp, None, 1000, None) == -1
+    assert lib.tnf_linear_bwd_weight_multi(2, vp, i64, vp, i64, i32, vp, None, 0, None) == 0        # m == 0: nothing to do
+    assert lib.tnf_linear_bwd_weight_multi(2, vp, i64, vp, i64, (ctypes.c_int32 * 2)(64, 160), vp, None, 1000, None) == -1
+    assert b"in_features" in lib.tnf_last_error()
+    assert lib.tnf_linear_bwd_weight_multi(2, vp, i64, vp, (ctypes.c_int64 * 2)(64, 94), i32, vp, None, 1000, None) == -1
+    assert b"leading dimensions" in lib.tnf_last_error()
+    assert lib.tnf_set_variant(3, 1) == 0 and lib.tnf_set_variant(3, 0) == 1   # 128-wide layers: kernel-generation switch
     assert lib.tnf_wgrad_cat_scratch_bytes(51, 96) == (64 * 32 * 5 + 4) * 4
     assert lib.tnf_heads_workspace_bytes(96, 147) >= (6 + 2 + 3 + 3) * 16384
 
