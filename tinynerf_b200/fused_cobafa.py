@@ -18,6 +18,7 @@ module path, so both paths draw the same mask from the same seed (tests/test_gpu
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List
 
 import torch
@@ -122,7 +123,6 @@ class FusedCobafaStep:
         self._closs_scratch = torch.zeros(2, dtype=torch.float64, device=self.dev)
         self._cap_n = self._cap_r = 0
         self._ws: Dict[str, torch.Tensor] = {}
-        import os
         self.wgrad_multi = os.environ.get("TNF_WGRAD_MULTI", "1") != "0"   # 0: one launch per 64-output weight gradient
 
     def attach_grads(self) -> None:
