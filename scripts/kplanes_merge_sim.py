@@ -1,38 +1,44 @@
-import torch, numpy as np, sys
-sys.path.insert(0,'/root/repo')
+"""Diagnostics (CPU, numpy/torch only): how many corner lines of the K-Planes scatter repeat among G consecutive packed
+samples -- the most an in-ray merge of the reductions could save.  Rays of the bench scene are marched inline (AABB slab
+entry, 256 uniform steps with jitter, trilinear occupancy lookup of the analytic grid), kept samples in (ray, step) order.
+Output under profiles/r02_kplanes_merge_sim.txt."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
+import torch
+import torch.nn.functional as F
 from tinynerf_b200 import synthetic
-from oracle import ref_port as rp
+
 torch.manual_seed(0)
-o,d = synthetic.blender_rays(10240, seed=5)
+R, S = 10240, 256
+o, d = synthetic.blender_rays(R, seed=5)
 grid = synthetic.analytic_grid(128, seed=3)
-aabb = torch.tensor([[-1.5]*3,[1.5]*3])
-noise = torch.rand(10240,256)
-thr = 0.01
-p, info, _ = rp.ray_provider(o,d,grid,thr,scene='aabb',n_samples=256,aabb=aabb,noise=noise)
-x = p[:, :3].numpy().astype(np.float64)
-N = len(x); print('samples',N,'rays with samples',(info[:,1]>0).sum().item())
-ray_id = np.repeat(np.arange(len(info)), info[:,1].numpy())
-for res in (128,256,512):
-    tot_direct=0; 
-    out={}
-    for G in (4,8,16,32):
-        out[G]=0
-    runs_cell=0; runs_line=0
-    for (a,b) in ((0,1),(0,2),(1,2)):
-        iu = (x[:,a]+1)*0.5*(res-1); iv=(x[:,b]+1)*0.5*(res-1)
-        x0=np.floor(iu).astype(np.int64); y0=np.floor(iv).astype(np.int64)
-        cell = y0*res+x0
-        # corner line ids
-        corners = np.stack([cell, cell+1, cell+res, cell+res+1],1)  # [N,4]
-        tot_direct += 4*N
-        for G in (4,8,16,32):
-            ng = N//G
-            c = corners[:ng*G].reshape(ng, G*4)
-            c.sort(axis=1)
-            distinct = 1 + (np.diff(c,axis=1)!=0).sum(1)
-            out[G]+= distinct.sum()
-        # serial run-merge: consecutive samples same cell (within chunk of 16)
-        same = (cell[1:]==cell[:-1])
-        runs_cell += N - same.sum()
-        # pair-line (two x-adjacent corners = 256B contiguous) distinct rows: row id (y, x0)
-    print(res, {G: round(out[G]/tot_direct,3) for G in out}, 'cell-runs frac', round(runs_cell/(3*N),3))
+lo, hi = torch.full((3,), -1.5), torch.full((3,), 1.5)
+step = float((hi - lo).norm()) / S
+dd = torch.where(d == 0, torch.full_like(d, 1e-9), d)
+t0, t1 = (lo - o) / dd, (hi - o) / dd
+t_min = torch.minimum(t0, t1).max(-1).values.clamp(0.1, 1e5)
+t = t_min[:, None] + (torch.arange(S) + torch.rand(R, S)) * step
+pts = o[:, None, :] + d[:, None, :] * t[..., None]
+inside = ((pts >= lo) & (pts <= hi)).all(-1)
+x = (pts - lo) / (hi - lo) * 2 - 1
+occ = F.grid_sample(grid[None, None], x.view(1, -1, 1, 1, 3), align_corners=True).view(R, S)
+keep = inside & (occ > 0.01)
+xs = x[keep].numpy().astype(np.float64)          # row-major (ray, step) order = the packed order
+N = len(xs)
+print("samples", N, "rays with samples", int(keep.any(-1).sum()))
+for res in (128, 256, 512):
+    tot, out, runs_cell = 0, {G: 0 for G in (4, 8, 16, 32)}, 0
+    for a, b in ((0, 1), (0, 2), (1, 2)):
+        iu, iv = (xs[:, a] + 1) * 0.5 * (res - 1), (xs[:, b] + 1) * 0.5 * (res - 1)
+        cell = np.floor(iv).astype(np.int64) * res + np.floor(iu).astype(np.int64)
+        corners = np.stack([cell, cell + 1, cell + res, cell + res + 1], 1)
+        tot += 4 * N
+        for G in out:
+            ng = N // G
+            c = np.sort(corners[:ng * G].reshape(ng, G * 4), axis=1)
+            out[G] += int((1 + (np.diff(c, axis=1) != 0).sum(1)).sum())
+        runs_cell += N - int((cell[1:] == cell[:-1]).sum())
+    print(res, "distinct corner lines / touches per group of G consecutive samples:",
+          {G: round(out[G] / tot, 3) for G in out}, "| cell runs / samples:", round(runs_cell / (3 * N), 3))
