@@ -5,11 +5,28 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import ctypes as C
 import torch
-from oracle import parity
-from tinynerf_b200 import _lib, models
+from tinynerf_b200 import _lib, core, models, synthetic
 
 dev = "cuda"
-renderer, prov, og, aabb, o, d = parity.kplanes_case(9600)
+
+
+def kplanes_case(n_rays, seed=0):
+    """BASELINE config 2 shape from the product's own modules: K-Planes + vanilla heads, AABB +-1.5, analytic 128^3 grid."""
+    torch.manual_seed(seed)
+    field = models.KPlanesFeatureField(32)
+    sd, cd = models.VanillaOpacityDecoder(96), models.VanillaColorDecoder(8, 96, 64, 3)
+    renderer = core.NerfRenderer(field, sd, cd, bg_color=torch.ones(3)).to(dev)
+    aabb = torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]], device=dev)
+    marcher = core.RayMarcherAABB(aabb, 256, 0.1)
+    og = core.OccupancyGrid(128, marcher.step_size, 0.01, synthetic.DECAY).to(dev)
+    og.grid.copy_(synthetic.analytic_grid(128, seed=1))
+    og.mean = og.grid.mean().item()
+    prov = core.RayProvider(og, core.ContractionAABB(aabb), marcher)
+    o, d = synthetic.blender_rays(n_rays, seed=2)
+    return renderer, prov, og, aabb, o.to(dev), d.to(dev)
+
+
+renderer, prov, og, aabb, o, d = kplanes_case(9600)
 torch.manual_seed(5)
 packed, info = prov(o, d, training=True)
 n = packed.size(0)
